@@ -1,0 +1,171 @@
+/* stylemc_b200.h -- C ABI of libstylemc_b200.so (sm_100a kernels for the StyleMC hot path).
+ *
+ * Plain pointers and sizes only; no torch types.  Every device pointer is borrowed, every output is
+ * allocated by the caller, every call is asynchronous on the `stream` argument (a cudaStream_t passed as
+ * void*; NULL = legacy default stream) and re-entrant.  Return value: 0 ok; < 0 argument error
+ * (SMC_E*); > 0 a cudaError_t.  The host-side Python mirror (stylemc_b200/ops, networks, clip) raises
+ * RuntimeError on any non-zero status, like TORCH_CHECK does in the reference plugins.
+ *
+ * Reference interfaces replaced (file:line under the reference tree):
+ *   smc_bias_act       torch_utils/ops/bias_act.cpp:32  `bias_act(x,b,xref,yref,dy,grad,dim,act,alpha,gain,clamp)`
+ *                      (pybind, bias_act.cpp:94-97; kernel params bias_act.h:12-31; called from bias_act.py:153,182,201)
+ *   smc_upfirdn2d      torch_utils/ops/upfirdn2d.cpp:16 `upfirdn2d(x,f,upx,upy,downx,downy,padx0,padx1,pady0,pady1,flip,gain)`
+ *                      (pybind, upfirdn2d.cpp:98-101; kernel params upfirdn2d.h:14-40; called from upfirdn2d.py:237-240)
+ *   smc_igemm          the cuDNN / cuBLAS calls reached through torch_utils/ops/conv2d_gradfix.py:35-43
+ *                      (F.conv2d / F.conv_transpose2d from conv2d_resample.py:29-54,138,147) and CLIP's nn.Linear
+ *   smc_demod_coefs, smc_pack_nhwc, smc_unpack_nchw, smc_fir_act, smc_torgb, smc_act_bwd, smc_fir_bwd,
+ *   smc_sgrad_finish, smc_grad_scale
+ *                      the ATen passes of [UPSTREAM] modulated_conv2d / SynthesisLayer / ToRGBLayer as driven by
+ *                      utils.py:13-53 (block_forward), plus fma.py:15-58 and the autograd of all of them
+ *   smc_resample_*     find_direction.py:49-52 `unprocess` (torchvision Resize(224, BICUBIC) + normalise)
+ *   smc_patchify .. smc_clip_loss
+ *                      openai/CLIP clip/model.py VisionTransformer / Transformer pieces behind
+ *                      clip_loss.py:15-16,25-26 (`encode_text`, `encode_image`) and clip_loss.py:24-34 (the loss)
+ *   smc_sgd_step       find_direction.py:285,298-301,339 (SGD without momentum, cosine LR computed by the host)
+ */
+#pragma once
+#include <stdint.h>
+
+#define SMC_OK 0
+#define SMC_EINVAL (-1)
+#define SMC_EUNSUPPORTED (-2)
+#define SMC_ETOOLARGE (-3)
+#define SMC_EDRIVER (-4)
+
+#define SMC_F32 0
+#define SMC_F16 1
+#define SMC_F64 2
+
+#define SMC_ABI_VERSION 1
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int smc_abi_version(void);
+
+/* ---- bias_act ------------------------------------------------------------------------------------
+ * y = clamp(act(x + b[(i / step_b) % size_b]) * gain)  (grad = 0), or the 1st / 2nd derivative pass
+ * (grad = 1 / 2) with the reference plugin's operand meaning (x = dy-like input, xref, yref, dy).
+ * b, xref, yref, dy may be NULL.  act = 1..9 = linear, relu, lrelu, tanh, sigmoid, elu, selu, softplus, swish
+ * (bias_act.py:23-33 cuda_idx).  clamp < 0 disables clamping.  All tensors dense, same layout, dtype `dtype`. */
+int smc_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                 int dtype, int64_t size_x, int32_t size_b, int64_t step_b, int grad, int act, float alpha,
+                 float gain, float clamp, void* stream);
+
+/* ---- upfirdn2d ----------------------------------------------------------------------------------- */
+typedef struct smc_upfirdn2d_params {
+  int32_t N, C, inH, inW, outH, outW;   /* outH/outW as computed at upfirdn2d.cpp:32-33 */
+  int64_t x_stride[4], y_stride[4];     /* element strides (n, c, h, w) */
+  int32_t fH, fW;
+  int64_t f_stride[2];                  /* fp32 filter strides (h, w) */
+  int32_t upx, upy, downx, downy, padx0, pady0, flip;
+  float gain;
+} smc_upfirdn2d_params;
+int smc_upfirdn2d(const void* x, const float* f, void* y, int dtype, const smc_upfirdn2d_params* p, void* stream);
+
+/* ---- implicit GEMM (tcgen05) --------------------------------------------------------------------- */
+/*   D[m, o] = sum_t sum_k A_t[m, k] * B_t[o, k]          fp16 operands, fp32 accumulate in TMEM
+ * A is an NHWC fp16 tensor [NA, HA, WA, C] read through ONE 4-D TMA map; a GEMM row m is a point (n, h, w)
+ * of the iteration space [n_img, H, W] and tap t reads A at (n + dn_t, h + dy_t, w + dx_t); out-of-range
+ * coordinates are zero-filled by TMA (that is the conv padding).  B is a K-major fp16 matrix [rowsB, C];
+ * tap t uses rows brow_t .. brow_t + n_out.  A plain GEMM is H = 1 with one tap.  Split-precision ("x3")
+ * runs are extra taps: (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi), the lo planes stacked behind the hi planes. */
+#define SMC_IGEMM_MAX_TAPS 32
+
+typedef struct smc_igemm_tap {
+  int32_t dn, dy, dx;   // A coordinate offsets (image/plane, row, column)
+  int32_t brow;         // first B row of this tap
+} smc_igemm_tap;
+
+// Epilogue: v = acc; v *= row_scale[n, o]; v += noise[h, w]; v += bias[o]; v = act(v) * gain;
+// v = clamp(v); out_raw = fp16(v); v *= post_scale[n, o]; v += residual; out = v.
+typedef struct smc_igemm_epilogue {
+  const float* row_scale;    // [n_img, n_out] or NULL   (demodulation coefficients)
+  const float* post_scale;   // [n_img, n_out] or NULL   (next layer's styles)
+  const float* bias;         // [n_out] or NULL
+  const float* noise;        // fp32 plane or NULL; element (h, w) at noise[h * noise_sh + w * noise_sw]
+  int64_t noise_sh, noise_sw;
+  int32_t act;               // 0 linear, 1 leaky relu
+  float alpha, gain, clamp;  // clamp < 0: none
+  const float* residual;     // fp32 or NULL, addressed like out_f32
+  float* out_f32;            // any subset of the four outputs may be NULL
+  void* out_hi;              // fp16
+  void* out_lo;              // fp16: rn(v - hi)
+  void* out_raw;             // fp16 value before post_scale / residual
+  int64_t o_sn, o_sh, o_sw;  // element strides of the output address for (n, h, w); channel stride 1
+  int64_t o_off;             // element offset of (0, 0, 0, channel 0)
+} smc_igemm_epilogue;
+
+typedef struct smc_igemm_desc {
+  const void* A;             // fp16 [NA, HA, WA, C], channel stride 1, pixel stride lda elements
+  int32_t NA, HA, WA, C;
+  int64_t lda;
+  const void* B;             // fp16 [rowsB, C] row-major (K contiguous), row stride ldb elements
+  int32_t rowsB;
+  int64_t ldb;
+  int32_t n_img, H, W;       // iteration space (GEMM M = n_img * H * W)
+  int32_t n_out;             // GEMM N
+  int32_t tw, th, tn;        // M-tile box (tw * th * tn == 128); 0 = choose automatically
+  int32_t ntaps;
+  smc_igemm_tap taps[SMC_IGEMM_MAX_TAPS];
+  smc_igemm_epilogue epi;
+} smc_igemm_desc;
+
+int smc_igemm(const smc_igemm_desc* desc, void* stream);
+
+/* ---- synthesis glue (synth.cu) -------------------------------------------------------------------
+ * Activations are NHWC fp16 ("hi" plane, optional "lo" plane = rn(v - hi)); styles are rows of the
+ * [N, 26, 512] S tensor addressed as base pointer + n * stride. */
+int smc_demod_coefs(const float* q, const float* s, int64_t s_stride, float* d, int n, int cin, int cout, void* stream);
+int smc_pack_nhwc(const float* x, int64_t x_stride_n, const float* s, int64_t s_stride, void* hi, void* lo, int n, int c,
+                  int hw, void* stream);
+int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, int n, int c, int hw, void* stream);
+int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* noise,
+                const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
+                void* out_raw, void* out_hi, void* out_lo, void* stream);
+int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w, int c, const float* w_rgb, const float* s_t,
+              int64_t st_stride, float wgain, const float* b_rgb, float clamp, const float* img_prev, const float* fk_up,
+              float* img, const float* s_next, int64_t sn_stride, void* xs_hi, void* xs_lo, void* stream);
+int smc_act_bwd(const void* y, int n, int h, int w, int c, const void* g_up, const float* s_next, int64_t sn_stride,
+                const float* g_img, const float* w_rgb, const float* s_t, int64_t st_stride, float wgain, const float* b_rgb,
+                float rgb_clamp, const float* gscale, const float* dcoef, const float* noise, const float* bias, float alpha,
+                float gain, float clamp, void* gd, float* t1, float* r, void* stream);
+int smc_fir_bwd(const void* gd, int n, int h, int w, int c, const float* fk, void* planes, void* stream);
+int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
+                     const float* gscale, float* grad_row, int n, int cin, int cout, void* stream);
+int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_scratch, float* gscale, void* stream);
+
+/* ---- unprocess + CLIP glue (vit.cu) --------------------------------------------------------------
+ * mean3 / std3 are HOST arrays of 3 floats; all other pointers are device pointers. */
+int smc_resample_fwd(const float* x, float* tmp, float* y, const int* start, const int* count, const float* wgt, int taps,
+                     int planes, int in_size, int out_size, int denorm_normalize, const float* mean3, const float* std3, void* stream);
+int smc_resample_bwd(const float* g, const float* x, float* tmp, float* gx, const int* oidx, const int* count, const float* wgt,
+                     int taps, int planes, int in_size, int out_size, const float* std3, void* stream);
+int smc_patchify(const float* img, void* hi, void* lo, int b, int res, int ps, void* stream);
+int smc_unpatchify(const float* gp, float* gimg, int b, int res, int ps, void* stream);
+int smc_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x0, int b, int t, int wd, void* stream);
+int smc_embed_text(const int64_t* text, const float* emb, const float* pos, float* x0, int b, int t, int wd, void* stream);
+int smc_layernorm_fwd(const float* x, int64_t in_row_stride, int64_t in_row_offset, const float* w, const float* b, float* y32,
+                      void* yhi, void* ylo, float* mean, float* rstd, int64_t rows, int wd, void* stream);
+int smc_layernorm_bwd(const float* dy, const float* x, int64_t in_row_stride, int64_t in_row_offset, const float* w,
+                      const float* mean, const float* rstd, float* dx, int64_t rows, int wd, int accumulate, void* stream);
+int smc_attention_fwd(const float* qkv, void* ohi, void* olo, float* o32, int b, int t, int wd, int heads, int causal, void* stream);
+int smc_attention_bwd(const float* qkv, const float* d_o, void* ghi, void* glo, int b, int t, int wd, int heads, int causal,
+                      void* stream);
+int smc_quickgelu_fwd(const float* h, void* hi, void* lo, int64_t n, void* stream);
+int smc_quickgelu_bwd(const float* dg, const float* h, void* hi, void* lo, int64_t n, void* stream);
+int smc_split_rows(const float* x, void* hi, void* lo, int64_t rows, int wd, int rows_per_group, int group_stride, int group_offset,
+                   void* stream);
+int smc_head_proj(const float* ln, const float* proj, float* out, int b, int wd, int e, void* stream);
+int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln, int b, int wd, int e, void* stream);
+int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
+                  float inv_count, void* stream);
+
+/* ---- optimiser -----------------------------------------------------------------------------------
+ * delta -= lr * (grad * grad_scale + l2_scale * delta)   (SGD, no momentum; L2 term of find_direction.py:190-191) */
+int smc_sgd_step(float* delta, const float* grad, int64_t numel, float lr, float grad_scale, float l2_scale, void* stream);
+
+#ifdef __cplusplus
+}  /* extern "C" */
+#endif

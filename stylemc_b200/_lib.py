@@ -1,0 +1,134 @@
+"""ctypes binding of libstylemc_b200.so (the C ABI declared in include/stylemc_b200.h).
+
+This is the FFI boundary that replaces the reference's ``custom_ops.get_plugin`` + pybind modules
+(torch_utils/custom_ops.py:46-124; upfirdn2d.py:26-35; bias_act.py:41-52).  Differences on purpose:
+the library is built ahead of time (stylemc_b200/build.py), and a missing library or a non-zero status
+raises -- there is no fallback to a slow reference implementation (upfirdn2d.py:33-35 warns and falls
+back; we never do).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libstylemc_b200.so')
+
+F32, F16, F64 = 0, 1, 2
+DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.float64: F64}
+MAX_TAPS = 32
+
+_STATUS = {-1: 'invalid argument', -2: 'unsupported configuration', -3: 'tensor too large', -4: 'CUDA driver entry point / tensor map failure'}
+
+
+class Tap(ctypes.Structure):
+    _fields_ = [('dn', ctypes.c_int32), ('dy', ctypes.c_int32), ('dx', ctypes.c_int32), ('brow', ctypes.c_int32)]
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [('row_scale', ctypes.c_void_p), ('post_scale', ctypes.c_void_p), ('bias', ctypes.c_void_p),
+                ('noise', ctypes.c_void_p), ('noise_sh', ctypes.c_int64), ('noise_sw', ctypes.c_int64),
+                ('act', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
+                ('residual', ctypes.c_void_p), ('out_f32', ctypes.c_void_p), ('out_hi', ctypes.c_void_p),
+                ('out_lo', ctypes.c_void_p), ('out_raw', ctypes.c_void_p),
+                ('o_sn', ctypes.c_int64), ('o_sh', ctypes.c_int64), ('o_sw', ctypes.c_int64), ('o_off', ctypes.c_int64)]
+
+
+class IgemmDesc(ctypes.Structure):
+    _fields_ = [('A', ctypes.c_void_p), ('NA', ctypes.c_int32), ('HA', ctypes.c_int32), ('WA', ctypes.c_int32),
+                ('C', ctypes.c_int32), ('lda', ctypes.c_int64),
+                ('B', ctypes.c_void_p), ('rowsB', ctypes.c_int32), ('ldb', ctypes.c_int64),
+                ('n_img', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('n_out', ctypes.c_int32),
+                ('tw', ctypes.c_int32), ('th', ctypes.c_int32), ('tn', ctypes.c_int32), ('ntaps', ctypes.c_int32),
+                ('taps', Tap * MAX_TAPS), ('epi', Epilogue)]
+
+
+class UpfirdnParams(ctypes.Structure):
+    _fields_ = [('N', ctypes.c_int32), ('C', ctypes.c_int32), ('inH', ctypes.c_int32), ('inW', ctypes.c_int32),
+                ('outH', ctypes.c_int32), ('outW', ctypes.c_int32),
+                ('x_stride', ctypes.c_int64 * 4), ('y_stride', ctypes.c_int64 * 4),
+                ('fH', ctypes.c_int32), ('fW', ctypes.c_int32), ('f_stride', ctypes.c_int64 * 2),
+                ('upx', ctypes.c_int32), ('upy', ctypes.c_int32), ('downx', ctypes.c_int32), ('downy', ctypes.c_int32),
+                ('padx0', ctypes.c_int32), ('pady0', ctypes.c_int32), ('flip', ctypes.c_int32), ('gain', ctypes.c_float)]
+
+
+_T = {'p': ctypes.c_void_p, 'i': ctypes.c_int, 'q': ctypes.c_int64, 'f': ctypes.c_float}
+
+# name -> argument kinds, in header order (p pointer, i int32, q int64, f float)
+SIGNATURES = {
+    'smc_abi_version': '',
+    'smc_bias_act': 'pppppp iqiq ii fff p',
+    'smc_upfirdn2d': 'ppp i p p',
+    'smc_igemm': 'pp',
+    'smc_demod_coefs': 'pp q p iii p',
+    'smc_pack_nhwc': 'p q p q pp iii p',
+    'smc_unpack_nchw': 'p i pp iii p',
+    'smc_fir_act': 'p i iiii ppp fff p q ppp p',
+    'smc_torgb': 'pp iiii pp q f p f ppp p q pp p',
+    'smc_act_bwd': 'p iiii pp q ppp q f p f pppp fff ppp p',
+    'smc_fir_bwd': 'p iiii pp p',
+    'smc_sgrad_finish': 'ppppp q pp iii p',
+    'smc_grad_scale': 'p q f pp p',
+    'smc_resample_fwd': 'pppppp i iii i pp p',
+    'smc_resample_bwd': 'ppppppp i iii p p',
+    'smc_patchify': 'ppp iii p',
+    'smc_unpatchify': 'pp iii p',
+    'smc_assemble_tokens': 'pppp iii p',
+    'smc_embed_text': 'pppp iii p',
+    'smc_layernorm_fwd': 'p qq pp pppp p q i p',
+    'smc_layernorm_bwd': 'pp qq ppp p q ii p',
+    'smc_attention_fwd': 'pppp iiiii p',
+    'smc_attention_bwd': 'pppp iiiii p',
+    'smc_quickgelu_fwd': 'ppp q p',
+    'smc_quickgelu_bwd': 'pppp q p',
+    'smc_split_rows': 'ppp q iiii p',
+    'smc_head_proj': 'ppp iii p',
+    'smc_head_proj_bwd': 'ppp iii p',
+    'smc_clip_loss': 'ppppp ii ff p',
+    'smc_sgd_step': 'pp q fff p',
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: run `python -m stylemc_b200.build` (there is no CPU/torch fallback)')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, sig in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_T[c] for c in sig.replace(' ', '')]
+        if handle.smc_abi_version() != 1:
+            raise RuntimeError('libstylemc_b200.so ABI version mismatch; rebuild')
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = _STATUS.get(status)
+        if msg is None and status > 0:
+            msg = f'CUDA error {status}'
+        raise RuntimeError(f'{what}: {msg} (status {status})')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must reside on a CUDA device: stylemc_b200 has no CPU path')
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

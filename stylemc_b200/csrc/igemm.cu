@@ -1,0 +1,394 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for sm_100a: the dense contraction behind modulated_conv2d
+// (forward, dgrad) and the CLIP ViT linears.  Replaces the cuDNN/cuBLAS calls the reference reaches
+// through torch_utils/ops/conv2d_gradfix.py:35-43 and clip/model.py's nn.Linear / nn.MultiheadAttention.
+//
+// One CTA = one 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0     TMA producer   : per k-step one 4-D box of A (128 pixels x KC channels, shifted by the tap)
+//                               and one 2-D box of B (BN rows x KC) into a STAGES-deep smem ring
+//   warp 1     MMA issuer     : tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16), fp32 accum in TMEM;
+//                               tcgen05.commit releases smem stages and finally signals the epilogue
+//   warps 2-5  epilogue       : tcgen05.ld 32x32b (one TMEM lane = one output pixel per thread),
+//                               demod * noise + bias -> lrelu*gain -> clamp -> style of next layer,
+//                               fp16 hi (+lo) / fp32 stores
+// Two CTAs fit per SM (<= 3 x 32 KB stages, <= 256 TMEM columns each), so one tile's epilogue overlaps
+// the other's main loop without a persistent scheduler.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "stylemc_b200.h"
+
+namespace smc {
+
+struct IgParams {
+  int n_img, H, W, C, n_out, ntaps;
+  int tw, th, tn, tiles_w, tiles_h;
+  smc_igemm_tap taps[SMC_IGEMM_MAX_TAPS];
+  smc_igemm_epilogue epi;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], fp16 x fp16 -> fp32
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in smem, rows of SWZ bytes (SWZ = KC * 2 in {64, 128}), hardware swizzle SWZ,
+// 8-row core-matrix groups SWZ*8 bytes apart (cute::UMMA::SmemDescriptor layout, version 1 = sm_100).
+template <int SWZ>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);                  // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                                  // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(((SWZ * 8) >> 4) & 0x3FFF) << 32;        // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+  d |= (uint64_t)(SWZ == 128 ? 2 : 4) << 61;               // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  return d;
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------
+template <int BN, int KC, int STAGES>
+__global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                    const __grid_constant__ CUtensorMap mapB,
+                                                    const __grid_constant__ IgParams p) {
+  constexpr int A_BYTES = 128 * KC * 2;
+  constexpr int B_BYTES = BN * KC * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int SWZ = KC * 2;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0,
+  // A,B K-major [15],[16]=0, N>>3 at [17,23), M>>4 at [24,29)
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_tiles_n = p.n_out / BN;
+  const int nt = blockIdx.x % n_tiles_n;
+  const int mt = blockIdx.x / n_tiles_n;
+  const int w0 = (mt % p.tiles_w) * p.tw;
+  const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+  const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kchunks = p.C / KC;
+  const int total = p.ntaps * kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int t = it / kchunks;
+        const int kc = (it - t * kchunks) * KC;
+        const smc_igemm_tap tap = p.taps[t];
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        tma_load_4d(sa, &mapA, &full_bar[s], kc, w0 + tap.dx, h0 + tap.dy, n0 + tap.dn);
+        tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kc, tap.brow + nt * BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t da = make_kmajor_desc<SWZ>(a_addr);
+        const uint64_t db = make_kmajor_desc<SWZ>(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k)  // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in 16-B units
+          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (uint32_t)((it | k) != 0));
+        tcgen05_commit(&empty_bar[s]);
+      }
+      tcgen05_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: thread <-> TMEM lane <-> output pixel ----------------
+    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int m = q * 32 + lane;
+    const int wl = m % p.tw;
+    const int hl = (m / p.tw) % p.th;
+    const int nl = m / (p.tw * p.th);
+    const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+    const bool valid = (n < p.n_img) && (h < p.H) && (w < p.W);
+    const smc_igemm_epilogue& e = p.epi;
+    const long long opix = e.o_off + (long long)n * e.o_sn + (long long)h * e.o_sh + (long long)w * e.o_sw;
+    float nz = 0.f;
+    if (e.noise != nullptr && valid) nz = __ldg(e.noise + (long long)h * e.noise_sh + (long long)w * e.noise_sw);
+    const float* rs = e.row_scale ? e.row_scale + (long long)(valid ? n : 0) * p.n_out : nullptr;
+    const float* ps = e.post_scale ? e.post_scale + (long long)(valid ? n : 0) * p.n_out : nullptr;
+
+    mbar_wait(accum_bar, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (valid) {
+        const int o0 = nt * BN + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (rs) x *= __ldg(rs + o0 + j);
+          x += nz;
+          if (e.bias) x += __ldg(e.bias + o0 + j);
+          if (e.act == 1) x = x > 0.f ? x : x * e.alpha;
+          x *= e.gain;
+          if (e.clamp >= 0.f) x = fminf(fmaxf(x, -e.clamp), e.clamp);
+          v[j] = x;
+        }
+        if (e.out_raw) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw) + opix + o0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __half2 h0_ = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]), h1_ = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+            __half2 h2_ = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3_ = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+            dst[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0_), *reinterpret_cast<uint32_t*>(&h1_),
+                                *reinterpret_cast<uint32_t*>(&h2_), *reinterpret_cast<uint32_t*>(&h3_));
+          }
+        }
+        if (ps) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= __ldg(ps + o0 + j);
+        }
+        if (e.residual) {
+          const float4* res = reinterpret_cast<const float4*>(e.residual + opix + o0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(res + j);
+            v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        }
+        if (e.out_f32) {
+          float4* dst = reinterpret_cast<float4*>(e.out_f32 + opix + o0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (e.out_hi) {
+          uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_hi) + opix + o0);
+          uint4* dl = e.out_lo ? reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_lo) + opix + o0) : nullptr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float a = v[8 * j + 2 * u], b = v[8 * j + 2 * u + 1];
+              const __half2 hh = __floats2half2_rn(a, b);
+              const float2 hf = __half22float2(hh);
+              const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+              hi[u] = *reinterpret_cast<const uint32_t*>(&hh);
+              lo[u] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            dh[j] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (dl) dl[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int BN, int KC, int STAGES>
+static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const IgParams& p, int grid, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (128 * KC * 2 + BN * KC * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  igemm_kernel<BN, KC, STAGES><<<grid, 192, SMEM, st>>>(ma, mb, p);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+int igemm_launch(const smc_igemm_desc* d, cudaStream_t st) {
+  if (!d || !d->A || !d->B) return SMC_EINVAL;
+  if (d->ntaps < 1 || d->ntaps > SMC_IGEMM_MAX_TAPS) return SMC_EINVAL;
+  if (d->n_img < 1 || d->H < 1 || d->W < 1 || d->n_out < 1 || d->C < 1) return SMC_EINVAL;
+  if (d->C % 32 != 0 || d->lda % 8 != 0 || d->ldb % 8 != 0) return SMC_EUNSUPPORTED;
+  if (((uintptr_t)d->A & 15) || ((uintptr_t)d->B & 15)) return SMC_EINVAL;
+  const int KC = (d->C % 64 == 0) ? 64 : 32;
+  int BN = 0;
+  if (d->n_out % 128 == 0) BN = 128;
+  else if (d->n_out % 64 == 0) BN = 64;
+  else if (d->n_out % 32 == 0) BN = 32;
+  else return SMC_EUNSUPPORTED;
+
+  IgParams p;
+  p.n_img = d->n_img; p.H = d->H; p.W = d->W; p.C = d->C; p.n_out = d->n_out; p.ntaps = d->ntaps;
+  if (d->tw > 0) {
+    p.tw = d->tw; p.th = d->th; p.tn = d->tn;
+  } else if (d->H == 1) {
+    p.tw = d->W >= 128 ? 128 : pow2_ceil(d->W);
+    p.th = 1;
+    p.tn = 128 / p.tw;
+  } else {
+    p.tw = d->W >= 16 ? 16 : pow2_ceil(d->W);
+    const int hmax = 128 / p.tw;
+    p.th = d->H >= hmax ? hmax : pow2_ceil(d->H);
+    p.tn = 128 / (p.tw * p.th);
+  }
+  if (p.tw * p.th * p.tn != 128 || p.tw > 256 || p.th > 256 || p.tn > 256) return SMC_EINVAL;
+  p.tiles_w = ceil_div(d->W, p.tw);
+  p.tiles_h = ceil_div(d->H, p.th);
+  const long long tiles_m = (long long)p.tiles_w * p.tiles_h * ceil_div(d->n_img, p.tn);
+  const long long grid = tiles_m * (d->n_out / BN);
+  if (grid > 0x7fffffffLL) return SMC_ETOOLARGE;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.taps[t] = d->taps[t];
+    if (d->taps[t].brow < 0 || d->taps[t].brow + d->n_out > d->rowsB) return SMC_EINVAL;
+  }
+  p.epi = d->epi;
+  if (!p.epi.out_f32 && !p.epi.out_hi && !p.epi.out_raw) return SMC_EINVAL;
+  if ((p.epi.o_sn | p.epi.o_sh | p.epi.o_sw | p.epi.o_off) & 7) return SMC_EUNSUPPORTED;  // 16-B vector stores
+
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return SMC_EDRIVER;
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->WA, (cuuint64_t)d->HA, (cuuint64_t)d->NA};
+    cuuint64_t strides[3] = {(cuuint64_t)d->lda * 2, (cuuint64_t)d->lda * 2 * d->WA, (cuuint64_t)d->lda * 2 * d->WA * d->HA};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->A), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return SMC_EDRIVER;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->C, (cuuint64_t)d->rowsB};
+    cuuint64_t strides[1] = {(cuuint64_t)d->ldb * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->B), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return SMC_EDRIVER;
+  }
+  const int g = (int)grid;
+  if (KC == 64) {
+    if (BN == 128) return launch_cfg<128, 64, 3>(ma, mb, p, g, st);
+    if (BN == 64) return launch_cfg<64, 64, 4>(ma, mb, p, g, st);
+    return launch_cfg<32, 64, 4>(ma, mb, p, g, st);
+  }
+  if (BN == 128) return launch_cfg<128, 32, 4>(ma, mb, p, g, st);
+  if (BN == 64) return launch_cfg<64, 32, 4>(ma, mb, p, g, st);
+  return launch_cfg<32, 32, 4>(ma, mb, p, g, st);
+}
+
+}  // namespace smc
+
+extern "C" int smc_igemm(const smc_igemm_desc* desc, void* stream) {
+  return smc::igemm_launch(desc, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,682 @@
+// Bandwidth-bound kernels of the S-space synthesis path (sm_100a), NHWC fp16 activations.
+//
+// They sit around the tcgen05 implicit GEMM (igemm.cu) and replace, fused, what the reference does in
+// separate passes: the style multiply and demodulation of [UPSTREAM] modulated_conv2d, the 4x4 FIR of
+// conv2d_resample.py:132-139, the noise add, bias_act (bias_act.py:55-89), ToRGB + `img.add_`
+// (utils.py:45-49), upsample2d of the skip image (upfirdn2d.py:308-343) and their backward passes.
+// Channel vectors are 8 x fp16 = 16 B; consecutive lanes take consecutive channel groups so every warp
+// access is a contiguous 512-B span of one pixel (or of neighbouring pixels when C < 256).
+#include "common.cuh"
+#include "stylemc_b200.h"
+
+namespace smc {
+
+struct H8 { __half2 a, b, c, d; };  // 8 halves = 16 B
+static_assert(sizeof(H8) == 16, "H8");
+
+__device__ __forceinline__ void h8_to_f(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 f_to_h8(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ void f_to_h8_split(const float (&f)[8], uint4& hi, uint4& lo) {
+  __half2* h = reinterpret_cast<__half2*>(&hi);
+  __half2* l = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    const float2 t = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(f[2 * i] - t.x, f[2 * i + 1] - t.y);
+  }
+}
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// d[n, o] = rsqrt(sum_i q[o, i] * s[n, i]^2 + 1e-8), q[o, i] = sum_k W[o, i, k]^2   ([UPSTREAM] dcoefs)
+__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ q, const float* __restrict__ s, long long s_stride,
+                                                    float* __restrict__ d, int cin, int cout) {
+  extern __shared__ float s2[];
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < cin; i += blockDim.x) { const float v = s[n * s_stride + i]; s2[i] = v * v; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = blockIdx.x * 8 + warp; o < cout; o += gridDim.x * 8) {
+    float acc = 0.f;
+    for (int i = lane; i < cin; i += 32) acc += __ldg(q + (long long)o * cin + i) * s2[i];
+    acc = warp_sum(acc);
+    if (lane == 0) d[(long long)n * cout + o] = rsqrtf(acc + 1e-8f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC fp16 (hi [, lo]) with optional per-(n, c) scale: the style multiply of the op-level
+// modulated_conv2d and the b4 `const` input (x_stride_n = 0 broadcasts it over the batch).
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const float* __restrict__ x, long long xs_n, const float* __restrict__ s,
+                                                        long long s_stride, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                        int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) {
+      v = x[n * xs_n + (long long)c * HW + p];
+      if (s) v *= s[n * s_stride + c];
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    if (c < C && p < HW) {
+      const float v = tile[tx][r];
+      const long long o = ((long long)n * HW + p) * C + c;
+      const __half h = __float2half_rn(v);
+      hi[o] = h;
+      if (lo) lo[o] = __float2half_rn(v - __half2float(h));
+    }
+  }
+}
+
+// NHWC (fp32 or fp16) -> NCHW fp32, optional added plane noise[HW]  (op-level API results, `xs` maps)
+template <class T>
+__global__ void __launch_bounds__(256) unpack_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, const float* __restrict__ noise,
+                                                          int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) v = (float)x[((long long)n * HW + p) * C + c];
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (c < C && p < HW) y[((long long)n * C + c) * HW + p] = tile[tx][r] + (noise ? noise[p] : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv0 tail: 4x4 FIR (pad 1, gain folded into fk) over the (2H+1)x(2W+1) transposed-conv result held
+// as four parity planes P[r][c][n][a][b][C] (t[2a+r, 2b+c]), then + noise + bias -> lrelu * gain ->
+// clamp; writes the raw fp16 activation and/or the activation times the next layer's styles (hi/lo).
+// One thread = one 2x2 output quad x 8 channels: the quad shares a 5x5 window of t.
+template <class TIn>
+__global__ void __launch_bounds__(256) fir_act_kernel(const TIn* __restrict__ planes, int N, int H, int W, int C,
+                                                      const float* __restrict__ fk /*[4][4] flipped*gain*/, const float* __restrict__ noise,
+                                                      const float* __restrict__ bias, float alpha, float gain, float clamp,
+                                                      const float* __restrict__ post, long long post_stride,
+                                                      __half* __restrict__ out_raw, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int cg = C >> 3;
+  const long long quads = (long long)N * H * W;  // output is 2H x 2W
+  const long long total = quads * cg;
+  const long long plane_sz = (long long)N * (H + 1) * (W + 1) * C;
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = __ldg(fk + i);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    long long qd = idx / cg;
+    const int k = (int)(qd % W); qd /= W;
+    const int j = (int)(qd % H);
+    const int n = (int)(qd / H);
+    const int c = g * 8;
+    // window rows ty = 2j-1 .. 2j+3, columns tx = 2k-1 .. 2k+3
+    float acc[2][2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[a][b][e] = 0.f;
+#pragma unroll
+    for (int wy = 0; wy < 5; ++wy) {
+      const int ty = 2 * j - 1 + wy;
+      if (ty < 0 || ty > 2 * H) continue;
+      const int pr = ty & 1, pa = ty >> 1;
+#pragma unroll
+      for (int wx = 0; wx < 5; ++wx) {
+        const int tx = 2 * k - 1 + wx;
+        if (tx < 0 || tx > 2 * W) continue;
+        const int pc = tx & 1, pb = tx >> 1;
+        const TIn* src = planes + (long long)(pr * 2 + pc) * plane_sz + (((long long)n * (H + 1) + pa) * (W + 1) + pb) * C + c;
+        float v[8];
+        if (sizeof(TIn) == 2) h8_to_f(__ldg(reinterpret_cast<const uint4*>(src)), v);
+        else ld8f(reinterpret_cast<const float*>(src), v);
+        // output (oy, ox) = (2j + a, 2k + b) uses t[oy + fy - 1, ox + fx - 1]  =>  fy = wy - a, fx = wx - b
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int fy = wy - a;
+          if (fy < 0 || fy > 3) continue;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int fx = wx - b;
+            if (fx < 0 || fx > 3) continue;
+            const float wgt = f[fy * 4 + fx];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[a][b][e] += wgt * v[e];
+          }
+        }
+      }
+    }
+    float bs[8], ps[8];
+    ld8f(bias + c, bs);
+    if (post) ld8f(post + n * post_stride + c, ps);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int oy = 2 * j + a, ox = 2 * k + b;
+        const float nz = noise ? __ldg(noise + (long long)oy * (2 * W) + ox) : 0.f;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float t = acc[a][b][e] + nz + bs[e];
+          t = (t > 0.f ? t : t * alpha) * gain;
+          if (clamp >= 0.f) t = fminf(fmaxf(t, -clamp), clamp);
+          v[e] = t;
+        }
+        const long long o = (((long long)n * (2 * H) + oy) * (2 * W) + ox) * C + c;
+        if (out_raw) *reinterpret_cast<uint4*>(out_raw + o) = f_to_h8(v);
+        if (out_hi) {
+          if (post) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] *= ps[e];
+          }
+          if (out_lo) {
+            uint4 hi, lo;
+            f_to_h8_split(v, hi, lo);
+            *reinterpret_cast<uint4*>(out_hi + o) = hi;
+            *reinterpret_cast<uint4*>(out_lo + o) = lo;
+          } else {
+            *reinterpret_cast<uint4*>(out_hi + o) = f_to_h8(v);
+          }
+        }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ToRGB + skip: rgb = clamp(sum_c W[j,c] * (s_t[n,c] * wgain) * x[n,p,c] + b[j]);  img = up2(img_prev) + rgb
+// (ToRGBLayer [UPSTREAM], utils.py:45-49, upsample2d = upfirdn2d(up=2, pad [2,1,2,1], gain 4)).  Also emits
+// x * s_next (hi/lo) for the next block's conv0.  A group of LPP lanes owns one pixel.
+__global__ void __launch_bounds__(256) torgb_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, int N, int H, int W, int C,
+                                                    const float* __restrict__ w_rgb /*[3][C]*/, const float* __restrict__ s_t, long long st_stride,
+                                                    float wgain, const float* __restrict__ b_rgb, float clamp,
+                                                    const float* __restrict__ img_prev /*[N,3,H/2,W/2] or null*/, const float* __restrict__ fk_up,
+                                                    float* __restrict__ img /*[N,3,H,W]*/,
+                                                    const float* __restrict__ s_next, long long sn_stride,
+                                                    __half* __restrict__ xs_hi, __half* __restrict__ xs_lo, int lpp) {
+  const int cg = C >> 3;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpp;                       // lane within the pixel group
+  const int groups_per_warp = 32 / lpp;
+  const long long npix = (long long)N * H * W;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long base = warp_global * groups_per_warp; base < npix; base += nwarps * groups_per_warp) {
+    const long long pix = base + lane / lpp;
+    const bool live = pix < npix;
+    const int n = live ? (int)(pix / ((long long)H * W)) : 0;
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    if (live) {
+      for (int g = sub; g < cg; g += lpp) {
+        const int c = g * 8;
+        float v[8], st[8];
+        h8_to_f(__ldg(reinterpret_cast<const uint4*>(x_hi + pix * C + c)), v);
+        if (x_lo) {
+          float l[8];
+          h8_to_f(__ldg(reinterpret_cast<const uint4*>(x_lo + pix * C + c)), l);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += l[e];
+        }
+        ld8f(s_t + n * st_stride + c, st);
+        float w0[8], w1[8], w2[8];
+        ld8f(w_rgb + c, w0); ld8f(w_rgb + C + c, w1); ld8f(w_rgb + 2 * C + c, w2);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float m = v[e] * (st[e] * wgain);
+          r0 += w0[e] * m; r1 += w1[e] * m; r2 += w2[e] * m;
+        }
+        if (xs_hi) {
+          float sn[8], o[8];
+          ld8f(s_next + n * sn_stride + c, sn);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = v[e] * sn[e];
+          if (xs_lo) {
+            uint4 hi, lo;
+            f_to_h8_split(o, hi, lo);
+            *reinterpret_cast<uint4*>(xs_hi + pix * C + c) = hi;
+            *reinterpret_cast<uint4*>(xs_lo + pix * C + c) = lo;
+          } else {
+            *reinterpret_cast<uint4*>(xs_hi + pix * C + c) = f_to_h8(o);
+          }
+        }
+      }
+    }
+    for (int o = lpp >> 1; o > 0; o >>= 1) {
+      r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+      r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    if (live && sub < 3) {
+      const int j = sub;
+      float r = (j == 0 ? r0 : (j == 1 ? r1 : r2)) + __ldg(b_rgb + j);
+      if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
+      const int rem = (int)(pix % ((long long)H * W));
+      const int y = rem / W, xq = rem % W;
+      if (img_prev) {
+        const int h2 = H >> 1, w2 = W >> 1;
+        const float* ip = img_prev + ((long long)n * 3 + j) * h2 * w2;
+        float u = 0.f;
+        // out[y, x] = sum fk[fy][fx] * xup[y + fy - 2, x + fx - 2], xup nonzero at even coordinates
+#pragma unroll
+        for (int fy = 0; fy < 4; ++fy) {
+          const int ay = y + fy - 2;
+          if (ay < 0 || (ay & 1) || (ay >> 1) >= h2) continue;
+#pragma unroll
+          for (int fx = 0; fx < 4; ++fx) {
+            const int ax = xq + fx - 2;
+            if (ax < 0 || (ax & 1) || (ax >> 1) >= w2) continue;
+            u += __ldg(fk_up + fy * 4 + fx) * __ldg(ip + (long long)(ay >> 1) * w2 + (ax >> 1));
+          }
+        }
+        r += u;
+      }
+      img[(((long long)n * 3 + j) * H + y) * W + xq] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward through  y = clamp(lrelu(z) * gain),  z = d * u + noise + b  of one modulated-conv layer whose
+// saved fp16 output is y.  Incoming gradient w.r.t. y:
+//     g_y = s_next[n,c] * g_up[n,p,c]                          (consumer conv's dgrad output, scaled fp16)
+//         + gscale * sum_j wmod[n,j,c] * g_rgb[n,j,p]          (ToRGB branch; g_rgb masked by its clamp)
+// Emits gd = d[n,c] * g_z (fp16, the A operand of this layer's dgrad) and, for trainable style rows,
+//     T1[n,c] += sum_p g_up * y        (first style-grad term of the CONSUMER layer)
+//     R[n,c]  += sum_p g_z * (z - noise - b)   (demodulation term of THIS layer)
+// All fp16 gradients carry the global loss scale *gscale_ptr.
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__ y, int N, int H, int W, int C,
+                                                      const __half* __restrict__ g_up, const float* __restrict__ s_next, long long sn_stride,
+                                                      const float* __restrict__ g_img /*[N,3,H,W] or null*/, const float* __restrict__ w_rgb,
+                                                      const float* __restrict__ s_t, long long st_stride, float wgain,
+                                                      const float* __restrict__ b_rgb, float rgb_clamp, const float* __restrict__ gscale_ptr,
+                                                      const float* __restrict__ dcoef, const float* __restrict__ noise, const float* __restrict__ bias,
+                                                      float alpha, float gain, float clamp,
+                                                      __half* __restrict__ gd, float* __restrict__ T1, float* __restrict__ R, int lpp, int pix_per_block) {
+  extern __shared__ float red[];  // [2][C] block partials (T1, R)
+  const int cg = C >> 3;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpp;
+  const int groups_per_warp = 32 / lpp;
+  const int warps = blockDim.x >> 5;
+  const bool reduce = (T1 != nullptr) || (R != nullptr);
+  const float gscale = gscale_ptr ? __ldg(gscale_ptr) : 1.f;
+  const long long hw = (long long)H * W;
+  // a block stays inside one image so the (n, c) partial sums can be flushed once
+  const long long blocks_per_img = ceil_div_ll(hw, pix_per_block);
+  const int n = (int)(blockIdx.x / blocks_per_img);
+  const long long p_begin = (blockIdx.x % blocks_per_img) * pix_per_block;
+  const long long p_end = (p_begin + pix_per_block < hw) ? p_begin + pix_per_block : hw;
+  if (reduce) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+  }
+  const int passes = ceil_div(cg, lpp);
+  // per-thread partials for the channel groups this lane owns (cg / lpp <= 2 with lpp = min(32, cg))
+  float t1acc[2][8], racc[2][8];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { t1acc[a][e] = 0.f; racc[a][e] = 0.f; }
+
+  for (long long pbase = p_begin + (threadIdx.x >> 5) * groups_per_warp; pbase < p_end; pbase += (long long)groups_per_warp * warps) {
+    const long long p = pbase + lane / lpp;   // warp-uniform trip count: the shuffles below need all lanes
+    const bool live = p < p_end;
+    const long long pix = (long long)n * hw + (live ? p : 0);
+    // ---- ToRGB branch: recompute rgb (for the clamp mask), then its gradient
+    float grgb[3] = {0.f, 0.f, 0.f};
+    if (g_img) {
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      if (live && rgb_clamp >= 0.f) {
+        for (int g = sub; g < cg; g += lpp) {
+          const int c = g * 8;
+          float v[8], st[8], w0[8], w1[8], w2[8];
+          h8_to_f(__ldg(reinterpret_cast<const uint4*>(y + pix * C + c)), v);
+          ld8f(s_t + n * st_stride + c, st);
+          ld8f(w_rgb + c, w0); ld8f(w_rgb + C + c, w1); ld8f(w_rgb + 2 * C + c, w2);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float m = v[e] * (st[e] * wgain);
+            r0 += w0[e] * m; r1 += w1[e] * m; r2 += w2[e] * m;
+          }
+        }
+      }
+      for (int o = lpp >> 1; o > 0; o >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      }
+      if (live) {
+        const float rr[3] = {r0 + __ldg(b_rgb), r1 + __ldg(b_rgb + 1), r2 + __ldg(b_rgb + 2)};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const bool pass = (rgb_clamp < 0.f) || (rr[j] > -rgb_clamp && rr[j] < rgb_clamp);
+          grgb[j] = pass ? gscale * __ldg(g_img + ((long long)n * 3 + j) * hw + p) : 0.f;
+        }
+      }
+    }
+    if (!live) continue;
+    const float nz = noise ? __ldg(noise + p) : 0.f;
+#pragma unroll 2
+    for (int ps = 0; ps < passes; ++ps) {
+      const int g = sub + ps * lpp;
+      if (g >= cg) break;
+      const int c = g * 8;
+      float yv[8], gy[8], gu[8];
+      h8_to_f(__ldg(reinterpret_cast<const uint4*>(y + pix * C + c)), yv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { gy[e] = 0.f; gu[e] = 0.f; }
+      if (g_up) {
+        float sn[8];
+        h8_to_f(__ldg(reinterpret_cast<const uint4*>(g_up + pix * C + c)), gu);
+        ld8f(s_next + n * sn_stride + c, sn);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gy[e] = gu[e] * sn[e];
+      }
+      if (g_img) {
+        float st[8], w0[8], w1[8], w2[8];
+        ld8f(s_t + n * st_stride + c, st);
+        ld8f(w_rgb + c, w0); ld8f(w_rgb + C + c, w1); ld8f(w_rgb + 2 * C + c, w2);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gy[e] += (st[e] * wgain) * (w0[e] * grgb[0] + w1[e] * grgb[1] + w2[e] * grgb[2]);
+      }
+      float dc[8], bs[8], out[8];
+      if (dcoef) ld8f(dcoef + (long long)n * C + c, dc);
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dc[e] = 1.f;
+      }
+      ld8f(bias + c, bs);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float yy = yv[e];
+        const bool pass = (clamp < 0.f) || (yy > -clamp && yy < clamp);
+        const float slope = (yy > 0.f ? 1.f : alpha) * gain;
+        const float gz = pass ? gy[e] * slope : 0.f;
+        out[e] = gz * dc[e];
+        if (reduce) {
+          const float z = yy / slope;                    // pre-activation (exact where the clamp passes)
+          racc[ps & 1][e] += gz * (z - nz - bs[e]);
+          t1acc[ps & 1][e] += gu[e] * yy;
+        }
+      }
+      if (gd) *reinterpret_cast<uint4*>(gd + pix * C + c) = f_to_h8(out);
+    }
+  }
+  if (reduce) {
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int g = sub + ps * lpp;
+      if (g < cg && ps < passes) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          atomicAdd(&red[g * 8 + e], t1acc[ps][e]);
+          atomicAdd(&red[C + g * 8 + e], racc[ps][e]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      if (T1) atomicAdd(T1 + (long long)n * C + i, red[i]);
+      if (R) atomicAdd(R + (long long)n * C + i, red[C + i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Transpose of the conv0 FIR: g_t[ty, tx] = sum_f fk[fy][fx] * gd[ty - fy + 1, tx - fx + 1]   (gain in fk),
+// written as parity planes GP[r][c][n][a][b][C] (a <= H, b <= W; cells outside the (2H+1)^2 grid are 0).
+__global__ void __launch_bounds__(256) fir_bwd_kernel(const __half* __restrict__ gd, int N, int H, int W, int C,
+                                                      const float* __restrict__ fk, __half* __restrict__ planes) {
+  const int cg = C >> 3;
+  const long long cells = (long long)N * (H + 1) * (W + 1);
+  const long long total = cells * cg;
+  const long long plane_sz = cells * C;
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = __ldg(fk + i);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    long long cell = idx / cg;
+    const int b = (int)(cell % (W + 1)); cell /= (W + 1);
+    const int a = (int)(cell % (H + 1));
+    const int n = (int)(cell / (H + 1));
+    const int c = g * 8;
+    // the 2x2 cell covers t rows 2a, 2a+1 and columns 2b, 2b+1; it needs gd rows 2a-2 .. 2a+2
+    float acc[2][2][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[r][q][e] = 0.f;
+#pragma unroll
+    for (int wy = 0; wy < 5; ++wy) {
+      const int gy = 2 * a - 2 + wy;
+      if (gy < 0 || gy >= 2 * H) continue;
+#pragma unroll
+      for (int wx = 0; wx < 5; ++wx) {
+        const int gx = 2 * b - 2 + wx;
+        if (gx < 0 || gx >= 2 * W) continue;
+        float v[8];
+        h8_to_f(__ldg(reinterpret_cast<const uint4*>(gd + (((long long)n * 2 * H + gy) * (2 * W) + gx) * C + c)), v);
+        // gd row gy = ty - fy + 1  =>  fy = ty + 1 - gy = (2a + r) + 1 - (2a - 2 + wy) = r + 3 - wy
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int fy = r + 3 - wy;
+          if (fy < 0 || fy > 3) continue;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int fx = q + 3 - wx;
+            if (fx < 0 || fx > 3) continue;
+            const float wgt = f[fy * 4 + fx];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[r][q][e] += wgt * v[e];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const bool inside = (2 * a + r <= 2 * H) && (2 * b + q <= 2 * W);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = inside ? acc[r][q][e] : 0.f;
+        *reinterpret_cast<uint4*>(planes + (long long)(r * 2 + q) * plane_sz + (((long long)n * (H + 1) + a) * (W + 1) + b) * C + c) = f_to_h8(o);
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ds[n,i] = T1[n,i] - s[n,i] * sum_o q[o,i] * d[n,o]^2 * R[n,o]  (SURVEY.md section 8a style-gradient algebra;
+// R already carries d * dL/dd), summed over the batch into the delta gradient row and unscaled.
+__global__ void __launch_bounds__(256) sgrad_finish_kernel(const float* __restrict__ T1, const float* __restrict__ R, const float* __restrict__ q,
+                                                           const float* __restrict__ d, const float* __restrict__ s, long long s_stride,
+                                                           const float* __restrict__ gscale_ptr, float* __restrict__ grad_row, int N, int cin, int cout) {
+  extern __shared__ float coef[];  // [cout] = d^2 * R for the current image
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    __syncthreads();
+    for (int o = threadIdx.x; o < cout; o += blockDim.x) {
+      const float dd = d[(long long)n * cout + o];
+      coef[o] = dd * dd * R[(long long)n * cout + o];
+    }
+    __syncthreads();
+    if (i < cin) {
+      float t2 = 0.f;
+      for (int o = 0; o < cout; ++o) t2 += __ldg(q + (long long)o * cin + i) * coef[o];
+      acc += T1[(long long)n * cin + i] - s[n * s_stride + i] * t2;
+    }
+  }
+  if (i < cin) grad_row[i] += acc / __ldg(gscale_ptr);
+}
+
+// gscale = 2^k with amax(|g|) * gscale in [2^-3, 2^-2): head-room for the growth of the fp16 gradients
+__global__ void amax_kernel(const float* __restrict__ g, long long n, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));
+}
+__global__ void gscale_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ gscale, float target) {
+  const float a = __uint_as_float(*amax_bits);
+  float sc = 1.f;
+  if (a > 0.f && isfinite(a)) sc = exp2f(floorf(log2f(target / a)));
+  *gscale = sc;
+}
+
+static int grid_for(long long work_items, int per_block) {
+  long long b = ceil_div_ll(work_items, per_block);
+  const long long cap = (long long)kNumSMs * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+static int pick_lpp(int C) {
+  int lpp = C >> 3;
+  if (lpp > 32) lpp = 32;
+  return lpp < 1 ? 1 : lpp;
+}
+
+}  // namespace smc
+
+using namespace smc;
+
+extern "C" int smc_demod_coefs(const float* q, const float* s, int64_t s_stride, float* d, int n, int cin, int cout, void* stream) {
+  if (!q || !s || !d || n < 1 || cin < 1 || cout < 1) return SMC_EINVAL;
+  dim3 grid(ceil_div(cout, 8) < 64 ? ceil_div(cout, 8) : 64, n);
+  demod_kernel<<<grid, 256, cin * sizeof(float), (cudaStream_t)stream>>>(q, s, s_stride, d, cin, cout);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_pack_nhwc(const float* x, int64_t x_stride_n, const float* s, int64_t s_stride, void* hi, void* lo, int n, int c,
+                             int hw, void* stream) {
+  if (!x || !hi || n < 1 || c < 1 || hw < 1) return SMC_EINVAL;
+  if (n > 65535 || ceil_div(c, 32) > 65535) return SMC_ETOOLARGE;
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n);
+  pack_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride_n, s, s_stride, (__half*)hi, (__half*)lo, c, hw);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, int n, int c, int hw, void* stream) {
+  if (!x || !y || n < 1 || c < 1 || hw < 1) return SMC_EINVAL;
+  if (n > 65535 || ceil_div(c, 32) > 65535) return SMC_ETOOLARGE;
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n);
+  if (x_is_half) unpack_nchw_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, y, noise, c, hw);
+  else unpack_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, noise, c, hw);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* noise,
+                           const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
+                           void* out_raw, void* out_hi, void* out_lo, void* stream) {
+  if (!planes || !fk || !bias || n < 1 || h < 1 || w < 1 || c < 8 || (c & 7)) return SMC_EINVAL;
+  if (!out_raw && !out_hi) return SMC_EINVAL;
+  const long long items = (long long)n * h * w * (c >> 3);
+  const int g = grid_for(items, 256);
+  if (planes_is_half)
+    fir_act_kernel<__half><<<g, 256, 0, (cudaStream_t)stream>>>((const __half*)planes, n, h, w, c, fk, noise, bias, alpha, gain, clamp, post,
+                                                                   post_stride, (__half*)out_raw, (__half*)out_hi, (__half*)out_lo);
+  else
+    fir_act_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)planes, n, h, w, c, fk, noise, bias, alpha, gain, clamp, post,
+                                                                  post_stride, (__half*)out_raw, (__half*)out_hi, (__half*)out_lo);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w, int c, const float* w_rgb, const float* s_t,
+                         int64_t st_stride, float wgain, const float* b_rgb, float clamp, const float* img_prev, const float* fk_up,
+                         float* img, const float* s_next, int64_t sn_stride, void* xs_hi, void* xs_lo, void* stream) {
+  if (!x_hi || !w_rgb || !s_t || !b_rgb || !img || n < 1 || h < 1 || w < 1 || c < 8 || (c & 7)) return SMC_EINVAL;
+  if (img_prev && (!fk_up || (h & 1) || (w & 1))) return SMC_EINVAL;
+  if (xs_hi && !s_next) return SMC_EINVAL;
+  const int lpp = pick_lpp(c);
+  if (lpp < 4) return SMC_EUNSUPPORTED;  // three lanes of a group write r, g, b
+  const long long npix = (long long)n * h * w;
+  const int g = grid_for(npix * lpp, 256);
+  torgb_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const __half*)x_hi, (const __half*)x_lo, n, h, w, c, w_rgb, s_t, st_stride, wgain, b_rgb,
+                                                     clamp, img_prev, fk_up, img, s_next, sn_stride, (__half*)xs_hi, (__half*)xs_lo, lpp);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_act_bwd(const void* y, int n, int h, int w, int c, const void* g_up, const float* s_next, int64_t sn_stride,
+                           const float* g_img, const float* w_rgb, const float* s_t, int64_t st_stride, float wgain, const float* b_rgb,
+                           float rgb_clamp, const float* gscale, const float* dcoef, const float* noise, const float* bias, float alpha,
+                           float gain, float clamp, void* gd, float* t1, float* r, void* stream) {
+  if (!y || (!gd && !t1) || (gd && !dcoef) || !bias || n < 1 || h < 1 || w < 1 || c < 32 || (c & 7) || c > 512) return SMC_EINVAL;
+  if (!g_up && !g_img) return SMC_EINVAL;
+  if (g_up && !s_next) return SMC_EINVAL;
+  if (g_img && (!w_rgb || !s_t || !b_rgb)) return SMC_EINVAL;
+  const int lpp = pick_lpp(c);
+  const long long hw = (long long)h * w;
+  // enough blocks to fill the machine, few enough that the per-block atomics stay cheap
+  int pix_per_block = 8 * (32 / lpp) * 16;
+  while (pix_per_block > 8 * (32 / lpp) && ceil_div_ll(hw, pix_per_block) * n < 2 * kNumSMs) pix_per_block >>= 1;
+  const long long blocks = ceil_div_ll(hw, pix_per_block) * n;
+  if (blocks > 0x7fffffffLL) return SMC_ETOOLARGE;
+  act_bwd_kernel<<<(int)blocks, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)y, n, h, w, c, (const __half*)g_up, s_next, sn_stride, g_img, w_rgb, s_t, st_stride, wgain, b_rgb, rgb_clamp, gscale,
+      dcoef, noise, bias, alpha, gain, clamp, (__half*)gd, t1, r, lpp, pix_per_block);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_fir_bwd(const void* gd, int n, int h, int w, int c, const float* fk, void* planes, void* stream) {
+  if (!gd || !fk || !planes || n < 1 || h < 1 || w < 1 || c < 8 || (c & 7)) return SMC_EINVAL;
+  const long long items = (long long)n * (h + 1) * (w + 1) * (c >> 3);
+  fir_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)gd, n, h, w, c, fk, (__half*)planes);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
+                                const float* gscale, float* grad_row, int n, int cin, int cout, void* stream) {
+  if (!t1 || !r || !q || !d || !s || !gscale || !grad_row || n < 1 || cin < 1 || cout < 1) return SMC_EINVAL;
+  sgrad_finish_kernel<<<ceil_div(cin, 256), 256, cout * sizeof(float), (cudaStream_t)stream>>>(t1, r, q, d, s, s_stride, gscale, grad_row, n, cin, cout);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_scratch, float* gscale, void* stream) {
+  if (!g || !amax_scratch || !gscale || numel < 1) return SMC_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(amax_scratch, 0, sizeof(uint32_t), st);
+  if (e != cudaSuccess) return (int)e;
+  amax_kernel<<<grid_for(numel, 1024), 256, 0, st>>>(g, numel, amax_scratch);
+  gscale_kernel<<<1, 1, 0, st>>>(amax_scratch, gscale, target);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}

@@ -1,0 +1,559 @@
+// CLIP ViT-B/32 glue kernels for sm_100a: everything between the tcgen05 GEMMs (igemm.cu).
+//
+// Replaces, for the calls `model.encode_image` / `model.encode_text` made at clip_loss.py:15-16,25-26
+// (openai/CLIP clip/model.py: fp32-internal LayerNorm, nn.MultiheadAttention, QuickGELU) and for
+// find_direction.py:49-52 (`unprocess`), the ATen elementwise / softmax / resize kernels.  The residual
+// stream and all statistics stay fp32; GEMM operands are emitted as fp16 hi (+lo) planes.
+#include "common.cuh"
+#include "stylemc_b200.h"
+
+namespace smc {
+
+__device__ __forceinline__ void store_split(__half* hi, __half* lo, long long i, float v) {
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  if (lo) lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Separable antialiased bicubic resample (F.interpolate(mode='bicubic', antialias=True), i.e. what
+// torchvision Resize(224, BICUBIC) does on tensors; find_direction.py:258).  Tables come from the host:
+// output index o reads inputs [start[o], start[o] + count[o]) with weights wgt[o * taps + k].
+// pass 1 (horizontal): t[b,c,y,ox] = sum_k w * clamp(x[b,c,y,start+k] * 127.5 + 128, 0, 255)
+// pass 2 (vertical):   y[b,c,oy,ox] = (sum_k w * t[b,c,start+k,ox] / 255 - mean_c) / std_c
+__global__ void __launch_bounds__(256) resample_h_kernel(const float* __restrict__ x, float* __restrict__ t, const int* __restrict__ start,
+                                                         const int* __restrict__ count, const float* __restrict__ wgt, int taps, long long rows,
+                                                         int in_w, int out_w, int denorm) {
+  const long long total = rows * out_w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % out_w);
+    const long long r = i / out_w;
+    const float* src = x + r * in_w + start[ox];
+    const float* w = wgt + (long long)ox * taps;
+    const int cnt = count[ox];
+    float acc = 0.f;
+    for (int k = 0; k < cnt; ++k) {
+      float v = __ldg(src + k);
+      if (denorm) v = fminf(fmaxf(v * 127.5f + 128.f, 0.f), 255.f);
+      acc += __ldg(w + k) * v;
+    }
+    t[i] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) resample_v_kernel(const float* __restrict__ t, float* __restrict__ y, const int* __restrict__ start,
+                                                         const int* __restrict__ count, const float* __restrict__ wgt, int taps, int planes,
+                                                         int in_h, int out_h, int w, float scale, float m0, float m1, float m2, float s0, float s1,
+                                                         float s2, int normalize) {
+  const long long total = (long long)planes * out_h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % w);
+    long long r = i / w;
+    const int oy = (int)(r % out_h);
+    const int pl = (int)(r / out_h);
+    const float* src = t + ((long long)pl * in_h + start[oy]) * w + ox;
+    const float* wt = wgt + (long long)oy * taps;
+    const int cnt = count[oy];
+    float acc = 0.f;
+    for (int k = 0; k < cnt; ++k) acc += __ldg(wt + k) * __ldg(src + (long long)k * w);
+    if (normalize) {
+      const int c = pl % 3;
+      const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+      acc = (acc * scale - mean) / sd;
+    }
+    y[i] = acc;
+  }
+}
+// Transposed passes (backward): per INPUT index the host lists the outputs that read it.
+// gt[b,c,iy,ox] = sum_k wT[iy][k] * (g[b,c,oT[iy][k],ox] / (255 * std_c))
+__global__ void __launch_bounds__(256) resample_vT_kernel(const float* __restrict__ g, float* __restrict__ gt, const int* __restrict__ oidx,
+                                                          const int* __restrict__ count, const float* __restrict__ wgt, int taps, int planes,
+                                                          int in_h, int out_h, int w, float s0, float s1, float s2) {
+  const long long total = (long long)planes * in_h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % w);
+    long long r = i / w;
+    const int iy = (int)(r % in_h);
+    const int pl = (int)(r / in_h);
+    const int c = pl % 3;
+    const float k0 = 1.f / (255.f * (c == 0 ? s0 : (c == 1 ? s1 : s2)));
+    const float* src = g + (long long)pl * out_h * w + ox;
+    float acc = 0.f;
+    const int cnt = count[iy];
+    for (int k = 0; k < cnt; ++k) acc += __ldg(wgt + (long long)iy * taps + k) * __ldg(src + (long long)oidx[(long long)iy * taps + k] * w);
+    gt[i] = acc * k0;
+  }
+}
+// gx[b,c,y,ix] = 127.5 * [0 < x*127.5+128 < 255] * sum_k wT[ix][k] * gt[b,c,y,oT[ix][k]]
+__global__ void __launch_bounds__(256) resample_hT_kernel(const float* __restrict__ gt, const float* __restrict__ x, float* __restrict__ gx,
+                                                          const int* __restrict__ oidx, const int* __restrict__ count, const float* __restrict__ wgt,
+                                                          int taps, long long rows, int in_w, int out_w) {
+  const long long total = rows * in_w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % in_w);
+    const long long r = i / in_w;
+    const float v = x[i] * 127.5f + 128.f;
+    float acc = 0.f;
+    if (v > 0.f && v < 255.f) {   // torch clamp backward passes gradient on [min, max] inclusive; measure-zero difference
+      const float* src = gt + r * out_w;
+      const int cnt = count[ix];
+      for (int k = 0; k < cnt; ++k) acc += __ldg(wgt + (long long)ix * taps + k) * __ldg(src + oidx[(long long)ix * taps + k]);
+      acc *= 127.5f;
+    }
+    gx[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// [B,3,224,224] fp32 -> patch matrix [B*49, 3072] fp16 (row = b*49 + py*7 + px, col = c*1024 + ky*32 + kx):
+// the im2col of clip/model.py `conv1` (kernel = stride = 32), and its transpose for the backward.
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int B,
+                                                       int res, int ps) {
+  const int grid = res / ps, kk = 3 * ps * ps;
+  const long long total = (long long)B * grid * grid * kk;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % kk);
+    const long long row = i / kk;
+    const int kx = col % ps, ky = (col / ps) % ps, c = col / (ps * ps);
+    const int px = (int)(row % grid), py = (int)((row / grid) % grid);
+    const long long b = row / (grid * grid);
+    store_split(hi, lo, i, img[((b * 3 + c) * res + py * ps + ky) * res + px * ps + kx]);
+  }
+}
+__global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict__ gp, float* __restrict__ gimg, int B, int res, int ps) {
+  const int grid = res / ps, kk = 3 * ps * ps;
+  const long long total = (long long)B * 3 * res * res;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % res), y = (int)((i / res) % res), c = (int)((i / ((long long)res * res)) % 3);
+    const long long b = i / (3LL * res * res);
+    const long long row = (b * grid + y / ps) * grid + x / ps;
+    gimg[i] = gp[row * kk + (c * ps + y % ps) * ps + x % ps];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Token assembly: x0[b,0,:] = cls + pos[0];  x0[b,1+p,:] = patch[b*49+p,:] + pos[1+p]   (VisionTransformer.forward)
+// Text:           x0[b,t,:] = tok_emb[text[b,t]] + pos[t]                                (CLIP.encode_text)
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                                              const float* __restrict__ pos, float* __restrict__ x0, int B, int T, int Wd) {
+  const long long total = (long long)B * T * Wd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % Wd), t = (int)((i / Wd) % T);
+    const long long b = i / ((long long)Wd * T);
+    const float v = (t == 0) ? cls[d] : patch[(b * (T - 1) + (t - 1)) * Wd + d];
+    x0[i] = v + pos[(long long)t * Wd + d];
+  }
+}
+__global__ void __launch_bounds__(256) embed_text_kernel(const long long* __restrict__ text, const float* __restrict__ emb,
+                                                         const float* __restrict__ pos, float* __restrict__ x0, int B, int T, int Wd) {
+  const long long total = (long long)B * T * Wd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % Wd), t = (int)((i / Wd) % T);
+    const long long b = i / ((long long)Wd * T);
+    x0[i] = emb[text[b * T + t] * Wd + d] + pos[(long long)t * Wd + d];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (eps 1e-5), one warp per row.  Row r of the output reads input row
+// r * in_row_stride + in_row_offset (lets ln_post pick the class token).  Outputs: fp32 and/or fp16 hi/lo.
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long in_row_stride, long long in_row_offset,
+                                                            const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y32,
+                                                            __half* __restrict__ yhi, __half* __restrict__ ylo, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, long long rows, int Wd) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* xr = x + (r * in_row_stride + in_row_offset) * Wd;
+    float s = 0.f;
+    for (int d = lane; d < Wd; d += 32) s += xr[d];
+    const float mean = warp_sum(s) / Wd;
+    float v = 0.f;
+    for (int d = lane; d < Wd; d += 32) { const float t = xr[d] - mean; v += t * t; }
+    const float rstd = rsqrtf(warp_sum(v) / Wd + 1e-5f);
+    if (lane == 0 && mean_out) { mean_out[r] = mean; rstd_out[r] = rstd; }
+    for (int d = lane; d < Wd; d += 32) {
+      const float o = (xr[d] - mean) * rstd * w[d] + b[d];
+      if (y32) y32[r * Wd + d] = o;
+      if (yhi) store_split(yhi, ylo, r * Wd + d, o);
+    }
+  }
+}
+// dx = rstd * (w*dy - mean(w*dy) - xhat * mean(w*dy*xhat)); out row = out_row_stride*r + out_row_offset;
+// accumulate != 0 adds into dx (residual gradient).
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long in_row_stride,
+                                                            long long in_row_offset, const float* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ dx, long long rows, int Wd,
+                                                            int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const long long xr = (r * in_row_stride + in_row_offset) * Wd;
+    const float mu = mean[r], rs = rstd[r];
+    float a = 0.f, bsum = 0.f;
+    for (int d = lane; d < Wd; d += 32) {
+      const float g = w[d] * dy[r * Wd + d];
+      const float xh = (x[xr + d] - mu) * rs;
+      a += g; bsum += g * xh;
+    }
+    a = warp_sum(a) / Wd; bsum = warp_sum(bsum) / Wd;
+    for (int d = lane; d < Wd; d += 32) {
+      const float g = w[d] * dy[r * Wd + d];
+      const float xh = (x[xr + d] - mu) * rs;
+      const float o = rs * (g - a - xh * bsum);
+      if (accumulate) dx[xr + d] += o; else dx[xr + d] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-head attention core, one CTA per (sequence, head): S = (q*scale) k^T (+causal mask), P = softmax(S),
+// O = P v.  qkv fp32 [B, T, 3*Wd] (q | k | v blocks, head h at columns h*hd), output [B, T, Wd] fp16 hi/lo.
+__global__ void __launch_bounds__(256) attention_fwd_kernel(const float* __restrict__ qkv, __half* __restrict__ ohi, __half* __restrict__ olo,
+                                                            float* __restrict__ o32, int T, int Wd, int heads, int causal) {
+  extern __shared__ float sm[];
+  const int hd = Wd / heads;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  float* q = sm;                  // [T][hd+1]
+  float* k = q + T * (hd + 1);
+  float* v = k + T * (hd + 1);
+  float* S = v + T * (hd + 1);    // [T][T+1]
+  const float scale = rsqrtf((float)hd);
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    const float* row = qkv + ((long long)b * T + t) * 3 * Wd + h * hd + d;
+    q[t * (hd + 1) + d] = row[0] * scale;
+    k[t * (hd + 1) + d] = row[Wd];
+    v[t * (hd + 1) + d] = row[2 * Wd];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    const int r = i / T, c = i % T;
+    float acc = 0.f;
+    for (int d = 0; d < hd; ++d) acc += q[r * (hd + 1) + d] * k[c * (hd + 1) + d];
+    S[r * (T + 1) + c] = (causal && c > r) ? -INFINITY : acc;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < T; r += blockDim.x >> 5) {
+    float m = -INFINITY;
+    for (int c = lane; c < T; c += 32) m = fmaxf(m, S[r * (T + 1) + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < T; c += 32) { const float e = expf(S[r * (T + 1) + c] - m); S[r * (T + 1) + c] = e; s += e; }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int c = lane; c < T; c += 32) S[r * (T + 1) + c] *= inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    float acc = 0.f;
+    for (int c = 0; c < T; ++c) acc += S[t * (T + 1) + c] * v[c * (hd + 1) + d];
+    const long long o = ((long long)b * T + t) * Wd + h * hd + d;
+    if (ohi) store_split(ohi, olo, o, acc);
+    if (o32) o32[o] = acc;
+  }
+}
+// Backward of the core given dO fp32 [B,T,Wd]: recompute P; dV = P^T dO; dP = dO V^T;
+// dS = P * (dP - rowsum(dP * P)); dQ = scale * dS K; dK = scale * dS^T Q.  Output dqkv fp16 hi/lo [B,T,3*Wd].
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, __half* __restrict__ ghi,
+                                                            __half* __restrict__ glo, int T, int Wd, int heads, int causal) {
+  extern __shared__ float sm[];
+  const int hd = Wd / heads;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int ld = hd + 1;
+  float* q = sm;
+  float* k = q + T * ld;
+  float* v = k + T * ld;
+  float* go = v + T * ld;
+  float* P = go + T * ld;         // [T][T+1]
+  float* dS = P + T * (T + 1);    // [T][T+1]
+  const float scale = rsqrtf((float)hd);
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    const float* row = qkv + ((long long)b * T + t) * 3 * Wd + h * hd + d;
+    q[t * ld + d] = row[0];
+    k[t * ld + d] = row[Wd];
+    v[t * ld + d] = row[2 * Wd];
+    go[t * ld + d] = dO[((long long)b * T + t) * Wd + h * hd + d];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    const int r = i / T, c = i % T;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < hd; ++d) { s += q[r * ld + d] * k[c * ld + d]; dp += go[r * ld + d] * v[c * ld + d]; }
+    P[r * (T + 1) + c] = (causal && c > r) ? -INFINITY : s * scale;
+    dS[r * (T + 1) + c] = dp;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < T; r += blockDim.x >> 5) {
+    float m = -INFINITY;
+    for (int c = lane; c < T; c += 32) m = fmaxf(m, P[r * (T + 1) + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < T; c += 32) { const float e = expf(P[r * (T + 1) + c] - m); P[r * (T + 1) + c] = e; s += e; }
+    const float inv = 1.f / warp_sum(s);
+    float dot = 0.f;
+    for (int c = lane; c < T; c += 32) { const float p = P[r * (T + 1) + c] * inv; P[r * (T + 1) + c] = p; dot += p * dS[r * (T + 1) + c]; }
+    dot = warp_sum(dot);
+    for (int c = lane; c < T; c += 32) dS[r * (T + 1) + c] = P[r * (T + 1) + c] * (dS[r * (T + 1) + c] - dot) * scale;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int c = 0; c < T; ++c) {
+      dq += dS[t * (T + 1) + c] * k[c * ld + d];
+      dk += dS[c * (T + 1) + t] * q[c * ld + d];
+      dv += P[c * (T + 1) + t] * go[c * ld + d];
+    }
+    const long long o = ((long long)b * T + t) * 3 * Wd + h * hd + d;
+    store_split(ghi, glo, o, dq);
+    store_split(ghi, glo, o + Wd, dk);
+    store_split(ghi, glo, o + 2 * Wd, dv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// QuickGELU (x * sigmoid(1.702 x)) forward to fp16 operand planes, and backward dh = dg * gelu'(h).
+__global__ void __launch_bounds__(256) quickgelu_fwd_kernel(const float* __restrict__ h, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = h[i];
+    store_split(hi, lo, i, x / (1.f + expf(-1.702f * x)));
+  }
+}
+__global__ void __launch_bounds__(256) quickgelu_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ h, __half* __restrict__ hi,
+                                                            __half* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = h[i];
+    const float sg = 1.f / (1.f + expf(-1.702f * x));
+    store_split(hi, lo, i, dg[i] * (sg + 1.702f * x * sg * (1.f - sg)));
+  }
+}
+// fp32 rows -> fp16 hi/lo planes; output row r reads input row (r / rows_per_group) * group_stride + group_offset + r % rows_per_group
+// (drops the class-token row when feeding the patch-embedding backward GEMM).
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, long long rows,
+                                                         int Wd, int rows_per_group, int group_stride, int group_offset) {
+  const long long total = rows * Wd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % Wd);
+    const long long r = i / Wd;
+    const long long src = (r / rows_per_group) * group_stride + group_offset + r % rows_per_group;
+    store_split(hi, lo, i, x[src * Wd + d]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Head: E[b,:] = ln[b,:] @ proj   (ln = ln_post(x[:,0,:]) or ln_final(x[b, eot_b]); proj [Wd, E]) and its transpose.
+__global__ void __launch_bounds__(256) head_proj_kernel(const float* __restrict__ ln, const float* __restrict__ proj, float* __restrict__ out, int Wd,
+                                                        int E) {
+  extern __shared__ float row[];
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < Wd; d += blockDim.x) row[d] = ln[(long long)b * Wd + d];
+  __syncthreads();
+  for (int j = threadIdx.x; j < E; j += blockDim.x) {
+    float acc = 0.f;
+    for (int d = 0; d < Wd; ++d) acc += row[d] * __ldg(proj + (long long)d * E + j);
+    out[(long long)b * E + j] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) head_proj_bwd_kernel(const float* __restrict__ dE, const float* __restrict__ proj, float* __restrict__ dln,
+                                                            int Wd, int E) {
+  extern __shared__ float row[];
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < E; j += blockDim.x) row[j] = dE[(long long)b * E + j];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int d = warp; d < Wd; d += blockDim.x >> 5) {
+    float acc = 0.f;
+    for (int j = lane; j < E; j += 32) acc += row[j] * __ldg(proj + (long long)d * E + j);
+    acc = warp_sum(acc);
+    if (lane == 0) dln[(long long)b * Wd + d] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Directional CLIP loss (clip_loss.py:24-34): e = E_tgt - E_src; cos_n = <e, t> / (|e| |t|);
+// loss = coef * (count - sum_n cos_n) / count  with count = global batch (inv_count = 1 / count).
+// One block; writes loss_part (this rank's sum of -cos * coef * inv_count; the constant coef is added by
+// the caller) and dE_tgt[n,:] = -coef * inv_count * (t/|t| - cos * e/|e|) / |e|.
+__global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict__ e_src, const float* __restrict__ e_tgt, const float* __restrict__ text,
+                                                        float* __restrict__ loss_part, float* __restrict__ d_tgt, int N, int E, float coef,
+                                                        float inv_count) {
+  __shared__ float red[3][16];
+  __shared__ float bc[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float total = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float ee = 0.f, et = 0.f, tt = 0.f;
+    for (int j = threadIdx.x; j < E; j += blockDim.x) {
+      const float e = e_tgt[(long long)n * E + j] - e_src[(long long)n * E + j], t = text[j];
+      ee += e * e; et += e * t; tt += t * t;
+    }
+    ee = warp_sum(ee); et = warp_sum(et); tt = warp_sum(tt);
+    __syncthreads();
+    if (lane == 0) { red[0][warp] = ee; red[1][warp] = et; red[2][warp] = tt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b2 = 0.f, c = 0.f;
+      for (int w = 0; w < nw; ++w) { a += red[0][w]; b2 += red[1][w]; c += red[2][w]; }
+      bc[0] = a; bc[1] = b2; bc[2] = c;
+    }
+    __syncthreads();
+    const float ne = fmaxf(sqrtf(bc[0]), 1e-8f), nt = fmaxf(sqrtf(bc[2]), 1e-8f);
+    const float cosv = bc[1] / (ne * nt);
+    total -= cosv;
+    if (d_tgt) {
+      for (int j = threadIdx.x; j < E; j += blockDim.x) {
+        const float e = e_tgt[(long long)n * E + j] - e_src[(long long)n * E + j];
+        d_tgt[(long long)n * E + j] = -coef * inv_count * (text[j] / nt - cosv * e / ne) / ne;
+      }
+    }
+  }
+  if (threadIdx.x == 0) *loss_part = coef * inv_count * total;
+}
+
+static int grid1d(long long items) {
+  long long b = ceil_div_ll(items, 256);
+  const long long cap = (long long)kNumSMs * 16;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace smc
+
+using namespace smc;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int smc_resample_fwd(const float* x, float* tmp, float* y, const int* start, const int* count, const float* wgt, int taps,
+                                int planes, int in_size, int out_size, int denorm_normalize, const float* mean3, const float* std3, void* stream) {
+  if (!x || !tmp || !y || !start || !count || !wgt || taps < 1 || planes < 1 || in_size < 1 || out_size < 1) return SMC_EINVAL;
+  float m[3] = {0, 0, 0}, s[3] = {1, 1, 1};
+  if (denorm_normalize) {
+    if (!mean3 || !std3) return SMC_EINVAL;
+    for (int i = 0; i < 3; ++i) { m[i] = mean3[i]; s[i] = std3[i]; }
+  }
+  const long long rows = (long long)planes * in_size;
+  resample_h_kernel<<<grid1d(rows * out_size), 256, 0, ST>>>(x, tmp, start, count, wgt, taps, rows, in_size, out_size, denorm_normalize);
+  resample_v_kernel<<<grid1d((long long)planes * out_size * out_size), 256, 0, ST>>>(tmp, y, start, count, wgt, taps, planes, in_size, out_size,
+                                                                                      out_size, 1.f / 255.f, m[0], m[1], m[2], s[0], s[1], s[2],
+                                                                                      denorm_normalize);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_resample_bwd(const float* g, const float* x, float* tmp, float* gx, const int* oidx, const int* count, const float* wgt,
+                                int taps, int planes, int in_size, int out_size, const float* std3, void* stream) {
+  if (!g || !x || !tmp || !gx || !oidx || !count || !wgt || !std3 || taps < 1 || planes < 1) return SMC_EINVAL;
+  resample_vT_kernel<<<grid1d((long long)planes * in_size * out_size), 256, 0, ST>>>(g, tmp, oidx, count, wgt, taps, planes, in_size, out_size,
+                                                                                      out_size, std3[0], std3[1], std3[2]);
+  const long long rows = (long long)planes * in_size;
+  resample_hT_kernel<<<grid1d(rows * in_size), 256, 0, ST>>>(tmp, x, gx, oidx, count, wgt, taps, rows, in_size, out_size);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_patchify(const float* img, void* hi, void* lo, int b, int res, int ps, void* stream) {
+  if (!img || !hi || b < 1 || res < 1 || ps < 1 || res % ps) return SMC_EINVAL;
+  patchify_kernel<<<grid1d((long long)b * 3 * res * res), 256, 0, ST>>>(img, (__half*)hi, (__half*)lo, b, res, ps);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_unpatchify(const float* gp, float* gimg, int b, int res, int ps, void* stream) {
+  if (!gp || !gimg || b < 1 || res < 1 || ps < 1 || res % ps) return SMC_EINVAL;
+  unpatchify_kernel<<<grid1d((long long)b * 3 * res * res), 256, 0, ST>>>(gp, gimg, b, res, ps);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x0, int b, int t, int wd, void* stream) {
+  if (!patch || !cls || !pos || !x0 || b < 1 || t < 2 || wd < 1) return SMC_EINVAL;
+  assemble_tokens_kernel<<<grid1d((long long)b * t * wd), 256, 0, ST>>>(patch, cls, pos, x0, b, t, wd);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_embed_text(const int64_t* text, const float* emb, const float* pos, float* x0, int b, int t, int wd, void* stream) {
+  if (!text || !emb || !pos || !x0 || b < 1 || t < 1 || wd < 1) return SMC_EINVAL;
+  embed_text_kernel<<<grid1d((long long)b * t * wd), 256, 0, ST>>>((const long long*)text, emb, pos, x0, b, t, wd);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_layernorm_fwd(const float* x, int64_t in_row_stride, int64_t in_row_offset, const float* w, const float* b, float* y32,
+                                 void* yhi, void* ylo, float* mean, float* rstd, int64_t rows, int wd, void* stream) {
+  if (!x || !w || !b || rows < 1 || wd < 1 || (!y32 && !yhi) || ((mean == nullptr) != (rstd == nullptr))) return SMC_EINVAL;
+  layernorm_fwd_kernel<<<grid1d(rows * 32), 256, 0, ST>>>(x, in_row_stride, in_row_offset, w, b, y32, (__half*)yhi, (__half*)ylo, mean, rstd, rows, wd);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_layernorm_bwd(const float* dy, const float* x, int64_t in_row_stride, int64_t in_row_offset, const float* w,
+                                 const float* mean, const float* rstd, float* dx, int64_t rows, int wd, int accumulate, void* stream) {
+  if (!dy || !x || !w || !mean || !rstd || !dx || rows < 1 || wd < 1) return SMC_EINVAL;
+  layernorm_bwd_kernel<<<grid1d(rows * 32), 256, 0, ST>>>(dy, x, in_row_stride, in_row_offset, w, mean, rstd, dx, rows, wd, accumulate);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_attention_fwd(const float* qkv, void* ohi, void* olo, float* o32, int b, int t, int wd, int heads, int causal, void* stream) {
+  if (!qkv || (!ohi && !o32) || b < 1 || t < 1 || heads < 1 || wd % heads) return SMC_EINVAL;
+  const int hd = wd / heads;
+  const size_t smem = (size_t)(3 * t * (hd + 1) + t * (t + 1)) * sizeof(float);
+  if (smem > 200 * 1024) return SMC_EUNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  attention_fwd_kernel<<<b * heads, 256, smem, ST>>>(qkv, (__half*)ohi, (__half*)olo, o32, t, wd, heads, causal);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_attention_bwd(const float* qkv, const float* d_o, void* ghi, void* glo, int b, int t, int wd, int heads, int causal,
+                                 void* stream) {
+  if (!qkv || !d_o || !ghi || b < 1 || t < 1 || heads < 1 || wd % heads) return SMC_EINVAL;
+  const int hd = wd / heads;
+  const size_t smem = (size_t)(4 * t * (hd + 1) + 2 * t * (t + 1)) * sizeof(float);
+  if (smem > 200 * 1024) return SMC_EUNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  attention_bwd_kernel<<<b * heads, 256, smem, ST>>>(qkv, d_o, (__half*)ghi, (__half*)glo, t, wd, heads, causal);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_quickgelu_fwd(const float* h, void* hi, void* lo, int64_t n, void* stream) {
+  if (!h || !hi || n < 1) return SMC_EINVAL;
+  quickgelu_fwd_kernel<<<grid1d(n), 256, 0, ST>>>(h, (__half*)hi, (__half*)lo, n);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_quickgelu_bwd(const float* dg, const float* h, void* hi, void* lo, int64_t n, void* stream) {
+  if (!dg || !h || !hi || n < 1) return SMC_EINVAL;
+  quickgelu_bwd_kernel<<<grid1d(n), 256, 0, ST>>>(dg, h, (__half*)hi, (__half*)lo, n);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_split_rows(const float* x, void* hi, void* lo, int64_t rows, int wd, int rows_per_group, int group_stride, int group_offset,
+                              void* stream) {
+  if (!x || !hi || rows < 1 || wd < 1 || rows_per_group < 1) return SMC_EINVAL;
+  split_rows_kernel<<<grid1d(rows * wd), 256, 0, ST>>>(x, (__half*)hi, (__half*)lo, rows, wd, rows_per_group, group_stride, group_offset);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_head_proj(const float* ln, const float* proj, float* out, int b, int wd, int e, void* stream) {
+  if (!ln || !proj || !out || b < 1 || wd < 1 || e < 1) return SMC_EINVAL;
+  head_proj_kernel<<<b, 256, wd * sizeof(float), ST>>>(ln, proj, out, wd, e);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln, int b, int wd, int e, void* stream) {
+  if (!d_e || !proj || !dln || b < 1 || wd < 1 || e < 1) return SMC_EINVAL;
+  head_proj_bwd_kernel<<<b, 256, e * sizeof(float), ST>>>(d_e, proj, dln, wd, e);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+extern "C" int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
+                             float inv_count, void* stream) {
+  if (!e_src || !e_tgt || !text || !loss_part || n < 1 || e < 1) return SMC_EINVAL;
+  clip_loss_kernel<<<1, 512, 0, ST>>>(e_src, e_tgt, text, loss_part, d_tgt, n, e, coef, inv_count);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}

@@ -1,0 +1,89 @@
+"""Host-side launcher for the tcgen05 implicit GEMM (``smc_igemm``): builds the descriptor of
+include/stylemc_b200.h from torch tensors.  Operands are fp16 "planes" tensors:
+
+  A : [P, N, H, W, C]   P = 1 (hi only) or 2 (hi, lo) planes of an NHWC activation
+  B : [P, rows, C]      P planes of a K-major weight matrix (rows = taps * n_out)
+
+``precision='x1'`` multiplies hi*hi; ``'x3'`` adds hi*lo and lo*hi as extra taps (~21 mantissa bits).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+TAPS_3X3 = [(ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3)]          # (dy, dx, weight tap)
+TAPS_3X3_DGRAD = [(1 - ky, 1 - kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+TAPS_1X1 = [(0, 0, 0)]
+
+
+def up2_parity_taps(r, c):
+    """Taps of the stride-2 transposed 3x3 conv that land on output parity (r, c): out[2a+r, 2b+c] reads
+    in[a - ky//2, b - kx//2] * W[ky, kx] for ky in ({0,2} if r == 0 else {1}), same for kx."""
+    kys = (0, 2) if r == 0 else (1,)
+    kxs = (0, 2) if c == 0 else (1,)
+    return [(-(ky // 2), -(kx // 2), ky * 3 + kx) for ky in kys for kx in kxs]
+
+
+def up2_dgrad_taps(n_img):
+    """dgrad of the same conv reads the gradient parity planes (stacked on the image axis, plane-major):
+    g_in[iy, ix] += GP[ky%2][kx%2][iy + ky//2, ix + kx//2] * W[ky, kx]."""
+    return [(((ky % 2) * 2 + (kx % 2)) * n_img, ky // 2, kx // 2, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+
+
+def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=None, b_rows_per_tap=None,
+          row_scale=None, post_scale=None, bias=None, noise=None, noise_strides=(0, 0), act=0, alpha=0.2, gain=1.0,
+          clamp=-1.0, residual=None, out_f32=None, out_hi=None, out_lo=None, out_raw=None, out_strides=None, out_offset=0,
+          tile=None):
+    """Launch one implicit GEMM.
+
+    A: fp16 tensor viewed as [NA, HA, WA, C] (NA includes the hi/lo planes stacked on the image axis).
+    B: fp16 tensor [rowsB, C]; ``taps`` entries are (dn, dy, dx, tap_index) or (dy, dx, tap_index);
+       tap_index selects rows tap_index * n_out .. of the hi block, the lo block follows ``b_lo_row`` rows later.
+    out_strides: (sn, sh, sw) element strides of the output; default dense NHWC [n_img, H, W, n_out].
+    """
+    assert A.dtype == torch.float16 and B.dtype == torch.float16 and A.is_cuda and B.is_cuda
+    assert A.ndim == 4 and B.ndim == 2 and A.is_contiguous() and B.is_contiguous()
+    NA, HA, WA, C = A.shape
+    d = _lib.IgemmDesc()
+    d.A, d.NA, d.HA, d.WA, d.C, d.lda = A.data_ptr(), NA, HA, WA, C, C
+    d.B, d.rowsB, d.ldb = B.data_ptr(), B.shape[0], C
+    d.n_img, d.H, d.W, d.n_out = n_img, H, W, n_out
+    if tile is not None:
+        d.tw, d.th, d.tn = tile
+    full = []
+    for t in taps:
+        dn, dy, dx, ti = t if len(t) == 4 else (0,) + tuple(t)
+        full.append((dn, dy, dx, ti * n_out))
+    if precision == 'x3':
+        a_lo = a_plane_stride_imgs if a_plane_stride_imgs is not None else NA // 2
+        b_lo = b_rows_per_tap if b_rows_per_tap is not None else B.shape[0] // 2
+        full = full + [(dn, dy, dx, br + b_lo) for dn, dy, dx, br in full] + [(dn + a_lo, dy, dx, br) for dn, dy, dx, br in full]
+    elif precision != 'x1':
+        raise ValueError(precision)
+    if len(full) > _lib.MAX_TAPS:
+        raise RuntimeError(f'{len(full)} taps > {_lib.MAX_TAPS}')
+    d.ntaps = len(full)
+    for i, (dn, dy, dx, br) in enumerate(full):
+        d.taps[i].dn, d.taps[i].dy, d.taps[i].dx, d.taps[i].brow = dn, dy, dx, br
+    e = d.epi
+    e.row_scale, e.post_scale, e.bias = _lib.ptr(row_scale), _lib.ptr(post_scale), _lib.ptr(bias)
+    e.noise, e.noise_sh, e.noise_sw = _lib.ptr(noise), noise_strides[0], noise_strides[1]
+    e.act, e.alpha, e.gain, e.clamp = act, alpha, gain, clamp
+    e.residual, e.out_f32 = _lib.ptr(residual), _lib.ptr(out_f32)
+    e.out_hi, e.out_lo, e.out_raw = _lib.ptr(out_hi), _lib.ptr(out_lo), _lib.ptr(out_raw)
+    if out_strides is None:
+        out_strides = (H * W * n_out, W * n_out, n_out)
+    e.o_sn, e.o_sh, e.o_sw = out_strides
+    e.o_off = out_offset
+    with torch.cuda.device(A.device):
+        _lib.call('smc_igemm', ctypes.addressof(d), _lib.stream())
+
+
+def split_planes(x, two):
+    """fp32 tensor -> stacked fp16 planes [P, ...] (setup-time helper for frozen weights)."""
+    hi = x.to(torch.float16)
+    if not two:
+        return hi.unsqueeze(0).contiguous()
+    lo = (x - hi.float()).to(torch.float16)
+    return torch.stack([hi, lo]).contiguous()
