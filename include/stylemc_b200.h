@@ -118,9 +118,10 @@ int smc_igemm(const smc_igemm_desc* desc, void* stream);
  * Activations are NHWC fp16 ("hi" plane, optional "lo" plane = rn(v - hi)); styles are rows of the
  * [N, 26, 512] S tensor addressed as base pointer + n * stride. */
 int smc_demod_coefs(const float* q, const float* s, int64_t s_stride, float* d, int n, int cin, int cout, void* stream);
+/* c_pitch >= c is the channel pitch of the NHWC side (channels c .. c_pitch-1 are left untouched: zero them once). */
 int smc_pack_nhwc(const float* x, int64_t x_stride_n, const float* s, int64_t s_stride, void* hi, void* lo, int n, int c,
-                  int hw, void* stream);
-int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, int n, int c, int hw, void* stream);
+                  int hw, int c_pitch, void* stream);
+int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, int n, int c, int hw, int c_pitch, void* stream);
 int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* noise,
                 const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
                 void* out_raw, void* out_hi, void* out_lo, void* stream);

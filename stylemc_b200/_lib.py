@@ -61,8 +61,8 @@ SIGNATURES = {
     'smc_upfirdn2d': 'ppp i p p',
     'smc_igemm': 'pp',
     'smc_demod_coefs': 'pp q p iii p',
-    'smc_pack_nhwc': 'p q p q pp iii p',
-    'smc_unpack_nchw': 'p i pp iii p',
+    'smc_pack_nhwc': 'p q p q pp iiii p',
+    'smc_unpack_nchw': 'p i pp iiii p',
     'smc_fir_act': 'p i iiii ppp fff p q ppp p',
     'smc_torgb': 'pp iiii pp q f p f ppp p q pp p',
     'smc_act_bwd': 'p iiii pp q ppp q f p f pppp fff ppp p',

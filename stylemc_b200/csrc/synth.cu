@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ q,
 // modulated_conv2d and the b4 `const` input (x_stride_n = 0 broadcasts it over the batch).
 __global__ void __launch_bounds__(256) pack_nhwc_kernel(const float* __restrict__ x, long long xs_n, const float* __restrict__ s,
                                                         long long s_stride, __half* __restrict__ hi, __half* __restrict__ lo,
-                                                        int C, int HW) {
+                                                        int C, int HW, int CP) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) pack_nhwc_kernel(const float* __restrict_
     const int p = p0 + r, c = c0 + tx;
     if (c < C && p < HW) {
       const float v = tile[tx][r];
-      const long long o = ((long long)n * HW + p) * C + c;
+      const long long o = ((long long)n * HW + p) * CP + c;
       const __half h = __float2half_rn(v);
       hi[o] = h;
       if (lo) lo[o] = __float2half_rn(v - __half2float(h));
@@ -92,14 +92,14 @@ __global__ void __launch_bounds__(256) pack_nhwc_kernel(const float* __restrict_
 // NHWC (fp32 or fp16) -> NCHW fp32, optional added plane noise[HW]  (op-level API results, `xs` maps)
 template <class T>
 __global__ void __launch_bounds__(256) unpack_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, const float* __restrict__ noise,
-                                                          int C, int HW) {
+                                                          int C, int HW, int CP) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8) {
     const int p = p0 + r, c = c0 + tx;
     float v = 0.f;
-    if (c < C && p < HW) v = (float)x[((long long)n * HW + p) * C + c];
+    if (c < C && p < HW) v = (float)x[((long long)n * HW + p) * CP + c];
     tile[r][tx] = v;
   }
   __syncthreads();
@@ -580,21 +580,21 @@ extern "C" int smc_demod_coefs(const float* q, const float* s, int64_t s_stride,
 }
 
 extern "C" int smc_pack_nhwc(const float* x, int64_t x_stride_n, const float* s, int64_t s_stride, void* hi, void* lo, int n, int c,
-                             int hw, void* stream) {
-  if (!x || !hi || n < 1 || c < 1 || hw < 1) return SMC_EINVAL;
+                             int hw, int c_pitch, void* stream) {
+  if (!x || !hi || n < 1 || c < 1 || hw < 1 || c_pitch < c) return SMC_EINVAL;
   if (n > 65535 || ceil_div(c, 32) > 65535) return SMC_ETOOLARGE;
   dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n);
-  pack_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride_n, s, s_stride, (__half*)hi, (__half*)lo, c, hw);
+  pack_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride_n, s, s_stride, (__half*)hi, (__half*)lo, c, hw, c_pitch);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
 
-extern "C" int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, int n, int c, int hw, void* stream) {
-  if (!x || !y || n < 1 || c < 1 || hw < 1) return SMC_EINVAL;
+extern "C" int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, int n, int c, int hw, int c_pitch, void* stream) {
+  if (!x || !y || n < 1 || c < 1 || hw < 1 || c_pitch < c) return SMC_EINVAL;
   if (n > 65535 || ceil_div(c, 32) > 65535) return SMC_ETOOLARGE;
   dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n);
-  if (x_is_half) unpack_nchw_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, y, noise, c, hw);
-  else unpack_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, noise, c, hw);
+  if (x_is_half) unpack_nchw_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, y, noise, c, hw, c_pitch);
+  else unpack_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, noise, c, hw, c_pitch);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

@@ -70,6 +70,9 @@ def _functions(dim, act, alpha, gain, clamp):
         return _cache[key]
     spec = activation_funcs[act]
     needs_x = 'x' in spec.ref or spec.has_2nd_grad
+    # 'linear' needs nothing for its slope, but the clamp mask is defined on y (the reference's impl='ref' path gets it from
+    # autograd of clamp(); its plugin skips it) -- parity is stated against impl='ref', so keep y whenever a clamp is active.
+    needs_y = 'y' in spec.ref or (spec.ref == '' and clamp >= 0)
 
     class BiasAct(torch.autograd.Function):
         @staticmethod
@@ -78,7 +81,7 @@ def _functions(dim, act, alpha, gain, clamp):
             y = x
             if act != 'linear' or gain != 1 or clamp >= 0 or b is not None:
                 y = _launch(x, b, None, None, None, 0, dim, spec, alpha, gain, clamp)
-            ctx.save_for_backward(x if needs_x else None, b if needs_x else None, y if 'y' in spec.ref else None)
+            ctx.save_for_backward(x if needs_x else None, b if needs_x else None, y if needs_y else None)
             ctx.has_b = b is not None
             return y
 
@@ -98,7 +101,10 @@ def _functions(dim, act, alpha, gain, clamp):
         @staticmethod
         def forward(ctx, dy, x, b, y):
             ref = y if y is not None else x
-            dy = dy.contiguous(memory_format=torch.channels_last) if (ref.ndim > 2 and ref.stride(1) == 1) else dy.contiguous()
+            if ref is None:      # 'linear': the gradient depends on neither x nor y (bias_act.py:26), keep dy's own layout
+                dy = _dense(dy)
+            else:
+                dy = dy.contiguous(memory_format=torch.channels_last) if (ref.ndim > 2 and ref.stride(1) == 1) else dy.contiguous()
             dx = _launch(dy, b, x, y, None, 1, dim, spec, alpha, gain, clamp)
             ctx.save_for_backward(dy if spec.has_2nd_grad else None, x, b, y)
             return dx

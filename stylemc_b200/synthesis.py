@@ -1,0 +1,335 @@
+"""Fused S-space synthesis engine: the B200 execution plan behind ``utils.generate_image``.
+
+The reference walks ``G.synthesis.b{res}`` and calls, per layer, modulated_conv2d -> conv2d_resample -> (upfirdn2d) ->
+bias_act on NCHW fp32 tensors (utils.py:13-53,161-216; [UPSTREAM] training/networks.py).  Here the same arithmetic runs
+as a short chain of hand-written kernels over NHWC fp16 activations that never leave the GPU:
+
+  conv1 (3x3)        one tcgen05 implicit GEMM; demodulation, noise, bias, lrelu*sqrt2 and clamp in its epilogue
+  conv0 (3x3, up 2)  four parity implicit GEMMs (polyphase transposed conv, no multiply-by-zero) -> one kernel doing the
+                     4x4 FIR + noise + bias + lrelu + clamp and the next layer's style multiply
+  torgb + skip       one kernel: 1x1 modulated conv to RGB, clamp, upsample2d of the running image, add, and the style
+                     multiply for the next block's conv0
+  backward           act_bwd (activation/clamp mask, ToRGB branch, demodulation, style-gradient reductions) -> dgrad
+                     implicit GEMM (-> transposed FIR for conv0); only the S rows that are trainable get reductions, and no
+                     per-sample weight gradient is ever formed (SURVEY.md section 8a style-gradient algebra).
+
+Styles are applied to the activations (the reference's non-fused formulation, identical maths -- oracle/pin_reference.py
+checks fused vs non-fused), so the frozen weights are shared by the whole batch.
+"""
+import math
+
+import torch
+
+from . import _lib, gemm
+from .ops import upfirdn2d
+
+N_STYLE_ROWS = 26        # find_direction.py:38
+STYLE_WIDTH = 512        # utils.py:125
+LRELU_ALPHA = 0.2
+LRELU_GAIN = math.sqrt(2)
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class _Layer:
+    """Device-resident frozen parameters of one SynthesisLayer in the layouts the kernels want."""
+
+    def __init__(self, mod, device, up):
+        w = _f32(mod.weight, device)                                   # [O, I, 3, 3]
+        self.cout, self.cin = w.shape[:2]
+        self.up = up
+        self.resolution = int(mod.resolution)
+        taps_fwd = w.permute(2, 3, 0, 1).reshape(9 * self.cout, self.cin)      # row t*O + o, col i
+        taps_bwd = w.permute(2, 3, 1, 0).reshape(9 * self.cin, self.cout)      # row t*I + i, col o (dgrad)
+        self.B_fwd = gemm.split_planes(taps_fwd, True).reshape(2 * 9 * self.cout, self.cin)
+        self.B_bwd = taps_bwd.to(torch.float16).contiguous()
+        self.q = w.square().sum(dim=[2, 3]).contiguous()               # [O, I]
+        self.bias = _f32(mod.bias, device)
+        strength = float(mod.noise_strength) if getattr(mod, 'use_noise', True) else 0.0
+        self.noise_const = (_f32(mod.noise_const, device) * strength).contiguous() if getattr(mod, 'use_noise', True) else None
+        self.noise_strength = strength
+        self.clamp = float(mod.conv_clamp) if mod.conv_clamp is not None else -1.0
+        self.gain = float(getattr(mod, 'act_gain', LRELU_GAIN))
+        assert getattr(mod, 'activation', 'lrelu') == 'lrelu', 'the fused engine implements the lrelu synthesis layers'
+
+
+class _ToRGB:
+    def __init__(self, mod, device):
+        w = _f32(mod.weight, device)                                   # [3, C, 1, 1]
+        assert w.shape[0] == 3 and w.shape[2:] == (1, 1)
+        self.cin = w.shape[1]
+        self.w = w.reshape(3, self.cin).contiguous()
+        self.bias = _f32(mod.bias, device)
+        self.wgain = float(mod.weight_gain)
+        self.clamp = float(mod.conv_clamp) if mod.conv_clamp is not None else -1.0
+
+
+class _Block:
+    def __init__(self, blk, device):
+        self.resolution = int(blk.resolution)
+        self.const = _f32(blk.const, device) if int(blk.in_channels) == 0 else None
+        self.conv0 = _Layer(blk.conv0, device, up=2) if self.const is None else None
+        self.conv1 = _Layer(blk.conv1, device, up=1)
+        self.torgb = _ToRGB(blk.torgb, device)
+        assert getattr(blk, 'architecture', 'skip') == 'skip'
+
+
+class SavedForward:
+    """What one forward pass keeps for the backward pass (fp16 layer outputs, demodulation coefficients)."""
+
+    def __init__(self):
+        self.y0, self.y1, self.d0, self.d1 = {}, {}, {}, {}
+        self.styles = None
+        self.until_k = None
+
+
+class SynthesisEngine:
+    """Execution plan for one frozen ``G.synthesis`` on one GPU.
+
+    precision: 'x1' fp16 operands; 'x3' split-fp16 operands everywhere (fp32-grade); 'mixed' = 'x3' for blocks up to
+    ``x3_max_res`` (the low-resolution, 512-channel layers where the S gradient is formed) and 'x1' above.
+    """
+
+    def __init__(self, G, device='cuda', precision='mixed', x3_max_res=64):
+        syn = G.synthesis if hasattr(G, 'synthesis') else G
+        self.device = torch.device(device)
+        self.block_resolutions = list(syn.block_resolutions)
+        self.blocks = [_Block(getattr(syn, f'b{r}'), self.device) for r in self.block_resolutions]
+        self.img_resolution = int(syn.img_resolution)
+        f = upfirdn2d.setup_filter([1, 3, 3, 1], device=self.device)
+        blk0 = getattr(syn, f'b{self.block_resolutions[0]}')
+        if hasattr(blk0, 'resample_filter'):
+            f = _f32(blk0.resample_filter, self.device)
+        assert f.shape == (4, 4), 'the fused engine implements the 4x4 [1,3,3,1] resample filter'
+        self.filter = f
+        self.fk4 = (f.flip([0, 1]) * 4.0).contiguous()                 # flipped taps * gain (up=2 -> gain 4)
+        if precision not in ('x1', 'x3', 'mixed'):
+            raise ValueError(precision)
+        self.precision, self.x3_max_res = precision, x3_max_res
+        # style row of (conv0, conv1, torgb) per block (utils.py:169-185)
+        self.rows, r = [], 0
+        for b in self.blocks:
+            if b.conv0 is None:
+                self.rows.append((None, r, r + 1))
+                r += 2
+            else:
+                self.rows.append((r, r + 1, r + 2))
+                r += 3
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _prec(self, res):
+        if self.precision == 'mixed':
+            return 'x3' if res <= self.x3_max_res else 'x1'
+        return self.precision
+
+    @staticmethod
+    def _srow(styles, row):
+        """(device pointer of styles[0, row, 0], element stride between samples)."""
+        return styles.data_ptr() + row * styles.stride(1) * 4, styles.stride(0)
+
+    def _demod(self, layer, styles, row, n):
+        d = torch.empty([n, layer.cout], dtype=torch.float32, device=self.device)
+        sp, ss = self._srow(styles, row)
+        _lib.call('smc_demod_coefs', _lib.ptr(layer.q), sp, ss, _lib.ptr(d), n, layer.cin, layer.cout, _lib.stream())
+        return d
+
+    def _planes(self, n, h, w, c, two):
+        return torch.empty([2 if two else 1, n, h, w, c], dtype=torch.float16, device=self.device)
+
+    def _noise(self, layer, noise_mode, n):
+        if noise_mode == 'none' or layer.noise_const is None:
+            return None
+        if noise_mode == 'const':
+            return layer.noise_const
+        raise RuntimeError("the fused engine implements noise_mode 'const' and 'none' (find_direction.py:207 default 'const'); "
+                           "'random' draws per-sample noise and is not reproducible")
+
+    def _conv1(self, L, xs, d, noise, n, res, prec, want_lo):
+        """3x3 modulated conv + noise + bias + lrelu + clamp; returns y planes [P, n, res, res, cout]."""
+        y = self._planes(n, res, res, L.cout, want_lo)
+        gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec,
+                   a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, bias=L.bias, noise=noise,
+                   noise_strides=(res, 1), act=1, alpha=LRELU_ALPHA, gain=L.gain, clamp=L.clamp,
+                   out_hi=y[0], out_lo=y[1] if want_lo else None)
+        return y
+
+    def _conv0(self, L, xs, d, noise, styles, row_next, n, hin, prec, want_lo):
+        """3x3 transposed stride-2 modulated conv + 4x4 FIR + noise + bias + lrelu + clamp.
+        Returns (y raw fp16 [n, 2h, 2h, cout], xs_next planes = y * styles[:, row_next])."""
+        x3 = prec == 'x3'
+        planes = torch.empty([4, n, hin + 1, hin + 1, L.cout], dtype=torch.float32 if x3 else torch.float16, device=self.device)
+        for r in (0, 1):
+            for c in (0, 1):
+                kw = dict(out_f32=planes[r * 2 + c]) if x3 else dict(out_raw=planes[r * 2 + c])
+                gemm.igemm(xs.reshape(-1, hin, hin, L.cin), L.B_fwd, n, hin + 1, hin + 1, L.cout, gemm.up2_parity_taps(r, c),
+                           precision=prec, a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
+        res = 2 * hin
+        y = torch.empty([n, res, res, L.cout], dtype=torch.float16, device=self.device)
+        xn = self._planes(n, res, res, L.cout, want_lo)
+        sp, ss = self._srow(styles, row_next)
+        _lib.call('smc_fir_act', _lib.ptr(planes), 0 if x3 else 1, n, hin, hin, L.cout, _lib.ptr(self.fk4), _lib.ptr(noise),
+                  _lib.ptr(L.bias), LRELU_ALPHA, L.gain, L.clamp, sp, ss, _lib.ptr(y), _lib.ptr(xn[0]),
+                  _lib.ptr(xn[1]) if want_lo else None, _lib.stream())
+        return y, xn
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, styles, until_k=100, noise_mode='const', save=False, want_xs=False):
+        """styles [N, 26, 512] fp32 CUDA -> (xs list or None, img [N, 3, R, R] fp32, SavedForward or None).
+
+        Mirrors utils.generate_image (utils.py:161-216) without the blending branches."""
+        _lib.require_cuda(styles, 'styles')
+        if styles.ndim != 3 or styles.shape[1] < self.rows[min(until_k, len(self.blocks) - 1)][2] + 1:
+            raise RuntimeError(f'styles must be [N, >= {self.rows[-1][2] + 1}, C], got {tuple(styles.shape)}')
+        styles = styles.float().contiguous()
+        n = styles.shape[0]
+        saved = SavedForward() if save else None
+        xs_list = [] if want_xs else None
+        img = None
+        xs = None                      # input planes of the next conv (activation times that conv's styles)
+        with torch.cuda.device(self.device):
+            last = min(until_k, len(self.blocks) - 1)
+            for k, blk in enumerate(self.blocks[:last + 1]):
+                res = blk.resolution
+                r0, r1, rt = self.rows[k]
+                prec = self._prec(res)
+                two = prec == 'x3'
+                L1 = blk.conv1
+                if blk.const is not None:
+                    c = blk.const.shape[0]
+                    xs = self._planes(n, res, res, c, two)
+                    sp, ss = self._srow(styles, r1)
+                    _lib.call('smc_pack_nhwc', _lib.ptr(blk.const), 0, sp, ss, _lib.ptr(xs[0]), _lib.ptr(xs[1]) if two else None,
+                              n, c, res * res, c, _lib.stream())
+                else:
+                    L0 = blk.conv0
+                    d0 = self._demod(L0, styles, r0, n)
+                    y0, xs = self._conv0(L0, xs, d0, self._noise(L0, noise_mode, n), styles, r1, n, res // 2, prec, two)
+                    if save:
+                        saved.y0[k], saved.d0[k] = y0, d0
+                d1 = self._demod(L1, styles, r1, n)
+                y1 = self._conv1(L1, xs, d1, self._noise(L1, noise_mode, n), n, res, prec, two)
+                if save:
+                    saved.y1[k], saved.d1[k] = y1[0], d1
+                # ToRGB + skip + style multiply for the next block's conv0
+                T = blk.torgb
+                new_img = torch.empty([n, 3, res, res], dtype=torch.float32, device=self.device)
+                has_next = k < last
+                if has_next:
+                    nprec = self._prec(self.blocks[k + 1].resolution)
+                    xs = self._planes(n, res, res, L1.cout, nprec == 'x3')
+                    snp, sns = self._srow(styles, self.rows[k + 1][0])
+                stp, sts = self._srow(styles, rt)
+                _lib.call('smc_torgb', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if two else None, n, res, res, L1.cout, _lib.ptr(T.w), stp, sts,
+                          T.wgain, _lib.ptr(T.bias), T.clamp, _lib.ptr(img), _lib.ptr(self.fk4), _lib.ptr(new_img),
+                          snp if has_next else None, sns if has_next else 0, _lib.ptr(xs[0]) if has_next else None,
+                          _lib.ptr(xs[1]) if (has_next and xs.shape[0] == 2) else None, _lib.stream())
+                img = new_img
+                if want_xs:
+                    out = torch.empty([n, L1.cout, res, res], dtype=torch.float32, device=self.device)
+                    _lib.call('smc_unpack_nchw', _lib.ptr(y1[0]), 1, _lib.ptr(out), None, n, L1.cout, res * res, L1.cout, _lib.stream())
+                    if two:   # add the lo plane so xs carries the full precision that was computed
+                        lo = torch.empty_like(out)
+                        _lib.call('smc_unpack_nchw', _lib.ptr(y1[1]), 1, _lib.ptr(lo), None, n, L1.cout, res * res, L1.cout, _lib.stream())
+                        out += lo
+                    xs_list.append(out)
+        if save:
+            saved.styles, saved.until_k = styles, last
+        return xs_list, img, saved
+
+    # ---- backward ------------------------------------------------------------------------------
+    def backward(self, saved, g_img, trainable_rows, noise_mode='const', grad_scale_target=2.0 ** -3):
+        """Gradient of a scalar loss w.r.t. the trainable S rows, summed over the batch.
+
+        saved: SavedForward of the pass that produced img; g_img = dL/dimg [N, 3, R, R] fp32.
+        Returns grad [len(trainable_rows), 512] fp32 (zero beyond each layer's channel count), i.e. exactly
+        ``delta.grad`` of find_direction.py:336 for delta broadcast over the batch (:307-308)."""
+        styles, last = saved.styles, saved.until_k
+        n = styles.shape[0]
+        dev = self.device
+        trainable_rows = list(trainable_rows)
+        owner = {}
+        for k in range(last + 1):
+            r0, r1, rt = self.rows[k]
+            if r0 is not None:
+                owner[r0] = (k, 0)
+            owner[r1] = (k, 1)
+        for r in trainable_rows:
+            if r not in owner:
+                raise RuntimeError(f'style row {r} is not a conv layer of the blocks that ran (ToRGB rows are not trainable here)')
+        lowest_k = min(owner[r][0] for r in trainable_rows)
+        want = set(trainable_rows)
+        grad = torch.zeros([len(trainable_rows), STYLE_WIDTH], dtype=torch.float32, device=dev)
+        g_img = g_img.float().contiguous()
+        with torch.cuda.device(dev):
+            amax = torch.zeros(1, dtype=torch.int32, device=dev)
+            gscale = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.call('smc_grad_scale', _lib.ptr(g_img), g_img.numel(), grad_scale_target, _lib.ptr(amax), _lib.ptr(gscale), _lib.stream())
+            acc = {}     # row -> (T1, R)
+
+            def bufs(row, cin, cout):
+                if row not in acc:
+                    acc[row] = (torch.zeros([n, cin], dtype=torch.float32, device=dev), torch.zeros([n, cout], dtype=torch.float32, device=dev))
+                return acc[row]
+
+            g_up, up_row = None, None      # gradient w.r.t. the modulated input of the consumer conv above, and its style row
+            for k in range(last, -1, -1):
+                blk = self.blocks[k]
+                res = blk.resolution
+                r0, r1, rt = self.rows[k]
+                L1, T = blk.conv1, blk.torgb
+                y1, d1 = saved.y1[k], saved.d1[k]
+                stop_here = (k < lowest_k)       # below the lowest trainable block only T1 of the consumer is needed
+                # ---- conv1 output: consumers are ToRGB (g_img) and the next block's conv0 (g_up)
+                t1 = bufs(up_row, L1.cout, self.blocks[k + 1].conv0.cout)[0] if (g_up is not None and up_row in want) else None
+                rr = bufs(r1, L1.cin, L1.cout)[1] if r1 in want else None
+                need_gd = not stop_here
+                if not need_gd and t1 is None:
+                    break
+                gd1 = torch.empty([n, res, res, L1.cout], dtype=torch.float16, device=dev) if need_gd else None
+                sp, ss = self._srow(styles, up_row) if g_up is not None else (None, 0)
+                stp, sts = self._srow(styles, rt)
+                noise1 = self._noise(L1, noise_mode, n)
+                _lib.call('smc_act_bwd', _lib.ptr(y1), n, res, res, L1.cout, _lib.ptr(g_up), sp, ss,
+                          _lib.ptr(g_img) if need_gd else None, _lib.ptr(T.w), stp, sts, T.wgain, _lib.ptr(T.bias), T.clamp, _lib.ptr(gscale),
+                          _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA, L1.gain, L1.clamp, _lib.ptr(gd1),
+                          _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
+                if stop_here:
+                    break
+                # ---- dgrad conv1 -> gradient w.r.t. (y0 * s1) (or const * s1 for b4)
+                if blk.conv0 is None and r1 not in want:
+                    break
+                gx1 = torch.empty([n, res, res, L1.cin], dtype=torch.float16, device=dev)
+                gemm.igemm(gd1, L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, out_raw=gx1)
+                if blk.conv0 is None:
+                    # b4: the input is the constant; T1 of conv1 is sum_p gx1 * const
+                    raise RuntimeError('trainable style rows in b4 are not implemented (reference trains b8..b64 only)')
+                L0 = blk.conv0
+                y0, d0 = saved.y0[k], saved.d0[k]
+                t1 = bufs(r1, L1.cin, L1.cout)[0] if r1 in want else None
+                rr = bufs(r0, L0.cin, L0.cout)[1] if r0 in want else None
+                gd0 = torch.empty([n, res, res, L0.cout], dtype=torch.float16, device=dev)
+                sp, ss = self._srow(styles, r1)
+                noise0 = self._noise(L0, noise_mode, n)
+                _lib.call('smc_act_bwd', _lib.ptr(y0), n, res, res, L0.cout, _lib.ptr(gx1), sp, ss, None, None, None, 0, 0.0, None, -1.0,
+                          _lib.ptr(gscale), _lib.ptr(d0), _lib.ptr(noise0), _lib.ptr(L0.bias), LRELU_ALPHA, L0.gain, L0.clamp, _lib.ptr(gd0),
+                          _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
+                hin = res // 2
+                gp = torch.empty([4 * n, hin + 1, hin + 1, L0.cout], dtype=torch.float16, device=dev)
+                _lib.call('smc_fir_bwd', _lib.ptr(gd0), n, hin, hin, L0.cout, _lib.ptr(self.fk4), _lib.ptr(gp), _lib.stream())
+                g_up = torch.empty([n, hin, hin, L0.cin], dtype=torch.float16, device=dev)
+                gemm.igemm(gp, L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), out_raw=g_up)
+                up_row = r0
+                # ---- skip image: transpose of upsample2d (upfirdn2d.py:245-264)
+                if k > 0:
+                    g_img = upfirdn2d.upfirdn2d(g_img, self.filter, down=2, padding=[1, 1, 1, 1], flip_filter=True, gain=4)
+            for i, row in enumerate(trainable_rows):
+                k, which = owner[row]
+                L = self.blocks[k].conv1 if which == 1 else self.blocks[k].conv0
+                t1, rr = acc[row]
+                d = saved.d1[k] if which == 1 else saved.d0[k]
+                sp, ss = self._srow(styles, row)
+                _lib.call('smc_sgrad_finish', _lib.ptr(t1), _lib.ptr(rr), _lib.ptr(L.q), _lib.ptr(d), sp, ss, _lib.ptr(gscale),
+                          _lib.ptr(grad[i]), n, L.cin, L.cout, _lib.stream())
+        return grad

@@ -1,0 +1,178 @@
+"""GPU parity of the op-level API (stylemc_b200.ops) against the reference's own outputs (tests/golden/ops.npz, written by
+oracle/pin_reference.py from torch_utils.ops impl='ref') and against the CPU oracle on other shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import act as o_act
+from oracle import conv as o_conv
+from oracle import fir as o_fir
+
+pytestmark = pytest.mark.gpu
+
+FIR_KW = {
+    'fir_conv0': dict(padding=[1, 1, 1, 1], gain=4),
+    'fir_up2': dict(up=2, padding=[2, 1, 2, 1], gain=4),
+    'fir_down2': dict(down=2, padding=[1, 1, 1, 1]),
+    'fir_down2_bwd_of_up2': dict(down=2, padding=[1, 2, 1, 2], flip_filter=True, gain=4),
+    'fir_crop_flip': dict(padding=[-1, 2, 0, -2], flip_filter=True, gain=0.5),
+    'fir_updown_xy': dict(up=[2, 3], down=[3, 2], padding=[3, 2, 4, 1]),
+    'fir_sep8': dict(up=2, padding=[4, 3, 4, 3], gain=4),
+    'fir_identity': dict(up=2, padding=1),
+}
+CONV_KW = {
+    'conv_up2': dict(up=2, padding=1, flip_weight=False),
+    'conv_up2_grouped': dict(up=2, padding=1, groups=2, flip_weight=False),
+    'conv_plain': dict(padding=1),
+    'conv_1x1': dict(),
+    'conv_1x1_up2': dict(up=2),
+}
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a)).to('cuda', dtype)
+
+
+@pytest.mark.parametrize('name', list(FIR_KW))
+def test_upfirdn2d_golden(golden, name):
+    from stylemc_b200.ops import upfirdn2d
+    g = golden('ops')
+    f = dev(g[name + '.f']) if name + '.f' in g else None
+    y = upfirdn2d.upfirdn2d(dev(g[name + '.x']), f, **FIR_KW[name])
+    ref = torch.as_tensor(g[name + '.y'])
+    assert y.shape == ref.shape
+    assert (y.cpu() - ref).abs().max().item() <= 2e-6   # fp32 accumulate, different summation order than F.conv2d
+
+
+def test_upsample2d_golden(golden):
+    from stylemc_b200.ops import upfirdn2d
+    g = golden('ops')
+    f = upfirdn2d.setup_filter([1, 3, 3, 1], device='cuda')
+    y = upfirdn2d.upsample2d(dev(g['upsample2d.x']), f)
+    assert (y.cpu() - torch.as_tensor(g['upsample2d.y'])).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize('shape,kw', [
+    ((3, 7, 129, 129), dict(padding=[1, 1, 1, 1], gain=4)),                  # conv0 tail at 64 px, ragged tile edges
+    ((2, 3, 100, 60), dict(up=2, padding=[2, 1, 2, 1], gain=4)),             # skip-image upsample, non-square
+    ((2, 3, 128, 128), dict(down=2, padding=[1, 2, 1, 2], flip_filter=True, gain=4)),
+    ((1, 1, 1, 1), dict(up=2, padding=[2, 1, 2, 1], gain=4)),                # smallest legal input
+])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.float64])
+def test_upfirdn2d_vs_oracle(shape, kw, dtype):
+    from stylemc_b200.ops import upfirdn2d
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(*shape, generator=g)
+    f = o_fir.setup_filter([1, 3, 3, 1])
+    ref = o_fir.upfirdn2d(x.double(), f.double(), **kw)
+    y = upfirdn2d.upfirdn2d(x.to('cuda', dtype), f.cuda(), **kw)
+    tol = {torch.float32: 2e-6, torch.float16: 4e-3, torch.float64: 1e-7}[dtype]    # f is float32 in the plugin ABI
+    assert y.dtype == dtype
+    assert (y.double().cpu() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+def test_upfirdn2d_channels_last_and_grad():
+    from stylemc_b200.ops import upfirdn2d
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 8, 20, 20, generator=g)
+    f = o_fir.setup_filter([1, 3, 3, 1])
+    kw = dict(up=2, padding=[2, 1, 2, 1], gain=4)
+    xr = x.clone().requires_grad_(True)
+    yr = o_fir.upfirdn2d(xr, f, **kw)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = upfirdn2d.upfirdn2d(xc, f.cuda(), **kw)
+    y.backward(dy.cuda())
+    assert (y.detach().cpu() - yr.detach()).abs().max().item() <= 2e-6
+    assert (xc.grad.cpu() - xr.grad).abs().max().item() <= 5e-6
+
+
+def test_upfirdn2d_errors():
+    from stylemc_b200.ops import upfirdn2d
+    f = o_fir.setup_filter([1, 3, 3, 1]).cuda()
+    with pytest.raises(RuntimeError):
+        upfirdn2d.upfirdn2d(torch.zeros(1, 1, 4, 4), f)                      # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        upfirdn2d.upfirdn2d(torch.zeros(1, 1, 2, 2, device='cuda'), f, padding=-2)   # output smaller than 1x1
+    with pytest.raises(RuntimeError):
+        upfirdn2d.upfirdn2d(torch.zeros(1, 1, 4, 4, device='cuda'), f, impl='ref')
+
+
+@pytest.mark.parametrize('name', list(o_act.ACTIVATIONS))
+@pytest.mark.parametrize('tag,kw', [('def', {}), ('clamp', dict(gain=1.7, clamp=0.9, alpha=0.3))])
+def test_bias_act_golden(golden, name, tag, kw):
+    from stylemc_b200.ops import bias_act
+    g = golden('ops')
+    y = bias_act.bias_act(dev(g['bias_act.x']), dev(g['bias_act.b']), act=name, **kw)
+    ref = torch.as_tensor(g[f'bias_act.{name}.{tag}'])
+    assert (y.cpu() - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('kw', [dict(act='lrelu', gain=2 ** 0.5, clamp=256 * 2 ** 0.5), dict(act='linear', clamp=256),
+                                dict(act='lrelu', gain=1.5, clamp=1.0), dict(act='swish'), dict(act='tanh', clamp=0.5)])
+@pytest.mark.parametrize('shape', [(3, 6, 5, 4), (2, 32, 64, 64), (1, 5, 7, 3)])
+def test_bias_act_fwd_bwd_vs_oracle(kw, shape):
+    from stylemc_b200.ops import bias_act
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(*shape, generator=g) * 60
+    b = torch.randn(shape[1], generator=g)
+    dy = torch.randn(*shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = o_act.bias_act(xr, b, **kw)
+    yr.backward(dy)
+    xc = x.cuda().requires_grad_(True)
+    y = bias_act.bias_act(xc, b.cuda(), **kw)
+    y.backward(dy.cuda())
+    assert (y.detach().cpu() - yr.detach()).abs().max().item() <= 2e-6 * max(1.0, yr.abs().max().item())
+    assert (xc.grad.cpu() - xr.grad).abs().max().item() <= 2e-6 * max(1.0, xr.grad.abs().max().item())
+
+
+def test_bias_act_misc():
+    from stylemc_b200.ops import bias_act
+    g = torch.Generator().manual_seed(3)
+    x2, b2 = torch.randn(4, 7, generator=g), torch.randn(4, generator=g)
+    y = bias_act.bias_act(x2.cuda(), b2.cuda(), dim=0, act='lrelu')
+    assert (y.cpu() - o_act.bias_act(x2, b2, dim=0, act='lrelu')).abs().max().item() <= 1e-6
+    xh = torch.randn(2, 16, 9, 9, generator=g)
+    yh = bias_act.bias_act(xh.cuda().half().contiguous(memory_format=torch.channels_last), b=None, act='lrelu', clamp=1.0)
+    assert yh.dtype == torch.float16 and yh.stride(1) == 1
+    assert (yh.float().cpu() - o_act.bias_act(xh.half().float(), act='lrelu', clamp=1.0)).abs().max().item() <= 2e-3
+    assert bias_act.bias_act(torch.zeros(0, 3, 2, 2, device='cuda'), torch.zeros(3, device='cuda')).numel() == 0   # empty input
+    with pytest.raises(RuntimeError):
+        bias_act.bias_act(torch.zeros(2, 3), torch.zeros(3))                  # CPU tensors
+    with pytest.raises(RuntimeError):
+        bias_act.bias_act(torch.zeros(2, 3, device='cuda'), torch.zeros(4, device='cuda'))   # wrong bias size
+
+
+@pytest.mark.parametrize('name', list(CONV_KW))
+def test_conv2d_resample_golden(golden, name):
+    from stylemc_b200.ops import conv2d_resample, upfirdn2d
+    g = golden('ops')
+    kw = CONV_KW[name]
+    f = upfirdn2d.setup_filter([1, 3, 3, 1], device='cuda') if kw.get('up', 1) > 1 else None
+    y = conv2d_resample.conv2d_resample(dev(g[name + '.x']), dev(g[name + '.w']), f=f, **kw)
+    ref = torch.as_tensor(g[name + '.y'])
+    assert y.shape == ref.shape
+    assert (y.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())   # split-fp16 operands ~2^-21
+
+
+def test_conv2d_resample_input_grad():
+    from stylemc_b200.ops import conv2d_gradfix, conv2d_resample, upfirdn2d
+    g = torch.Generator().manual_seed(4)
+    f = o_fir.setup_filter([1, 3, 3, 1])
+    for kw, xs, ws in ((dict(padding=1), (2, 40, 9, 9), (33, 40, 3, 3)),
+                       (dict(up=2, padding=1, flip_weight=False), (2, 16, 6, 6), (8, 16, 3, 3)),
+                       (dict(), (2, 40, 5, 5), (3, 40, 1, 1))):
+        x, w = torch.randn(*xs, generator=g), torch.randn(*ws, generator=g)
+        ff = f if kw.get('up', 1) > 1 else None
+        xr = x.clone().requires_grad_(True)
+        yr = o_conv.conv2d_resample(xr, w, f=ff, **kw)
+        dy = torch.randn(yr.shape, generator=g)
+        yr.backward(dy)
+        xc = x.cuda().requires_grad_(True)
+        with conv2d_gradfix.no_weight_gradients():
+            y = conv2d_resample.conv2d_resample(xc, w.cuda(), f=None if ff is None else ff.cuda(), **kw)
+            y.backward(dy.cuda())
+        assert (y.detach().cpu() - yr.detach()).abs().max().item() <= 2e-5 * yr.abs().max().item()
+        assert (xc.grad.cpu() - xr.grad).abs().max().item() <= 2e-5 * xr.grad.abs().max().item()

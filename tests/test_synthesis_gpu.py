@@ -1,0 +1,67 @@
+"""GPU parity of the fused synthesis engine against the reference's own output (tests/golden/synth64.npz: the reference's
+utils.generate_image driving the restated network modules on CPU, impl='ref' ops) and against the CPU oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synthesis as o_syn
+
+pytestmark = pytest.mark.gpu
+
+TRAINABLE = [2, 3, 5, 6, 8, 9, 11, 12]     # find_direction.py:41
+IMG_TOL = {'x1': 1e-2, 'mixed': 1e-2, 'x3': 2e-4}   # north_star: images <= 1e-2 max-abs for 16-bit operand paths
+
+
+def small_net():
+    G = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)      # same as oracle/pin_reference.make_small_net
+    shapes = o_syn.get_temp_shapes(G)
+    return G, shapes
+
+
+@pytest.mark.parametrize('precision', ['x1', 'mixed', 'x3'])
+def test_generate_image_golden(golden, precision):
+    from stylemc_b200 import utils
+    g = golden('synth64')
+    G, shapes = small_net()
+    assert [tuple(s) for s in g['temp_shapes']] == shapes
+    styles = torch.as_tensor(g['styles']).cuda()
+    xs, img = utils.generate_image(G, 100, styles, shapes, 'const', 'cuda', precision=precision)
+    ref = torch.as_tensor(g['img'])
+    err = (img.cpu() - ref).abs().max().item()
+    print(f'{precision}: img max-abs err {err:.3e} (ref range {ref.min():.2f}..{ref.max():.2f})')
+    assert img.shape == ref.shape and err <= IMG_TOL[precision]
+    for i, x in enumerate(xs):
+        r = torch.as_tensor(g[f'xs{i}'])
+        e = (x.cpu() - r).abs().max().item() / r.abs().max().item()
+        print(f'  xs[{i}] rel err {e:.3e}')
+        assert e <= (5e-3 if precision != 'x3' else 1e-4)
+    _, img2 = utils.generate_image(G, 2, styles, shapes, 'const', 'cuda', precision=precision)
+    assert (img2.cpu() - torch.as_tensor(g['img_k2'])).abs().max().item() <= IMG_TOL[precision]
+
+
+@pytest.mark.parametrize('precision,tol', [('x1', 2e-2), ('mixed', 2e-3), ('x3', 1e-3)])
+def test_style_gradient_vs_oracle_autograd(golden, precision, tol):
+    """d(sum(img * g)) / d(delta) for delta added to the trainable S rows, batch-summed (find_direction.py:307-308,336)."""
+    from stylemc_b200 import utils
+    g = golden('synth64')
+    G, shapes = small_net()
+    styles = torch.as_tensor(g['styles'])
+    gen = torch.Generator().manual_seed(11)
+    delta = (0.1 * torch.randn(1, 8, 512, generator=gen)).requires_grad_(True)
+    g_img = torch.randn(styles.shape[0], 3, 64, 64, generator=gen)
+    direction = torch.zeros(1, 26, 512).index_put((torch.tensor([0]).view(1, 1), torch.tensor(TRAINABLE).view(1, -1)), delta)
+    styles2 = styles + direction
+    _, img_ref = o_syn.generate_image(G, 100, styles2, shapes, 'const')
+    (img_ref * g_img).sum().backward()
+    ref = delta.grad[0]
+
+    eng = utils.engine_for(G, 'cuda', precision)
+    _, img, saved = eng.forward(styles2.detach().cuda(), save=True)
+    grad = eng.backward(saved, g_img.cuda(), TRAINABLE).cpu()
+    assert (img.cpu() - img_ref.detach()).abs().max().item() <= IMG_TOL[precision]
+    for i, row in enumerate(TRAINABLE):
+        e = ((grad[i] - ref[i]).norm() / ref[i].norm()).item()
+        print(f'{precision}: row {row} grad rel-l2 err {e:.3e}  |ref| {ref[i].norm():.3e}')
+    rel = ((grad - ref).norm() / ref.norm()).item()
+    print(f'{precision}: total grad rel-l2 err {rel:.3e}')
+    assert rel <= tol
