@@ -78,7 +78,7 @@ typedef struct smc_igemm_tap {
   int32_t brow;         // first B row of this tap
 } smc_igemm_tap;
 
-// Epilogue: v = acc; v *= row_scale[n, o]; v += noise[h, w]; v += bias[o]; v = act(v) * gain;
+// Epilogue: v = acc * acc_scale; v *= row_scale[n, o]; v += noise[h, w]; v += bias[o]; v = act(v) * gain;
 // v = clamp(v); out_raw = fp16(v); v *= post_scale[n, o]; v += residual; out = v.
 typedef struct smc_igemm_epilogue {
   const float* row_scale;    // [n_img, n_out] or NULL   (demodulation coefficients)
@@ -95,6 +95,7 @@ typedef struct smc_igemm_epilogue {
   void* out_raw;             // fp16 value before post_scale / residual
   int64_t o_sn, o_sh, o_sw;  // element strides of the output address for (n, h, w); channel stride 1
   int64_t o_off;             // element offset of (0, 0, 0, channel 0)
+  float acc_scale;           // applied to the raw accumulator first (undoes a power-of-two pre-scaling of B); 0 means 1
 } smc_igemm_epilogue;
 
 typedef struct smc_igemm_desc {
@@ -110,6 +111,8 @@ typedef struct smc_igemm_desc {
   int32_t ntaps;
   smc_igemm_tap taps[SMC_IGEMM_MAX_TAPS];
   smc_igemm_epilogue epi;
+  int32_t acc_chunk_k;       // 0: one TMEM accumulation chain; > 0: drain the accumulator into fp32 registers every
+                             // ~acc_chunk_k K-elements (removes the tensor core's truncation bias on long chains)
 } smc_igemm_desc;
 
 int smc_igemm(const smc_igemm_desc* desc, void* stream);
@@ -124,15 +127,17 @@ int smc_pack_nhwc(const float* x, int64_t x_stride_n, const float* s, int64_t s_
 int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, int n, int c, int hw, int c_pitch, void* stream);
 int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* noise,
                 const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
-                void* out_raw, void* out_hi, void* out_lo, void* stream);
+                void* out_raw, void* out_raw_lo, void* out_hi, void* out_lo, void* stream);
 int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w, int c, const float* w_rgb, const float* s_t,
               int64_t st_stride, float wgain, const float* b_rgb, float clamp, const float* img_prev, const float* fk_up,
               float* img, const float* s_next, int64_t sn_stride, void* xs_hi, void* xs_lo, void* stream);
-int smc_act_bwd(const void* y, int n, int h, int w, int c, const void* g_up, const float* s_next, int64_t sn_stride,
-                const float* g_img, const float* w_rgb, const float* s_t, int64_t st_stride, float wgain, const float* b_rgb,
-                float rgb_clamp, const float* gscale, const float* dcoef, const float* noise, const float* bias, float alpha,
-                float gain, float clamp, void* gd, float* t1, float* r, void* stream);
-int smc_fir_bwd(const void* gd, int n, int h, int w, int c, const float* fk, void* planes, void* stream);
+/* y_lo / gd_lo: optional lo planes (split precision); g_up is fp16, or fp32 when g_up_is_f32 != 0. */
+int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w, int c, const void* g_up, int g_up_is_f32, const float* s_next,
+                int64_t sn_stride, const float* g_img, const float* w_rgb, const float* s_t, int64_t st_stride, float wgain,
+                const float* b_rgb, float rgb_clamp, const float* gscale, const float* dcoef, const float* noise, const float* bias,
+                float alpha, float gain, float clamp, void* gd, void* gd_lo, float* t1, float* r, void* stream);
+int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int w, int c, const float* fk, void* planes, void* planes_lo,
+                void* stream);
 int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
                      const float* gscale, float* grad_row, int n, int cin, int cout, void* stream);
 int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_scratch, float* gscale, void* stream);
@@ -141,8 +146,9 @@ int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_s
  * mean3 / std3 are HOST arrays of 3 floats; all other pointers are device pointers. */
 int smc_resample_fwd(const float* x, float* tmp, float* y, const int* start, const int* count, const float* wgt, int taps,
                      int planes, int in_size, int out_size, int denorm_normalize, const float* mean3, const float* std3, void* stream);
+/* unscale: optional DEVICE pointer to the loss scale S carried by g (see smc_clip_loss); gx = d/dx of the unscaled loss. */
 int smc_resample_bwd(const float* g, const float* x, float* tmp, float* gx, const int* oidx, const int* count, const float* wgt,
-                     int taps, int planes, int in_size, int out_size, const float* std3, void* stream);
+                     int taps, int planes, int in_size, int out_size, const float* std3, const float* unscale, void* stream);
 int smc_patchify(const float* img, void* hi, void* lo, int b, int res, int ps, void* stream);
 int smc_unpatchify(const float* gp, float* gimg, int b, int res, int ps, void* stream);
 int smc_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x0, int b, int t, int wd, void* stream);
@@ -160,8 +166,10 @@ int smc_split_rows(const float* x, void* hi, void* lo, int64_t rows, int wd, int
                    void* stream);
 int smc_head_proj(const float* ln, const float* proj, float* out, int b, int wd, int e, void* stream);
 int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln, int b, int wd, int e, void* stream);
+/* gscale_out (optional, device): d_tgt is multiplied by S = 2^k, max|d_tgt| * S in [target/2, target), and S is stored there
+ * (loss scaling for the fp16-operand backward GEMMs; smc_resample_bwd divides it out again). */
 int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
-                  float inv_count, void* stream);
+                  float inv_count, float* gscale_out, float gscale_target, void* stream);
 
 /* ---- optimiser -----------------------------------------------------------------------------------
  * delta -= lr * (grad * grad_scale + l2_scale * delta)   (SGD, no momentum; L2 term of find_direction.py:190-191) */

@@ -31,7 +31,8 @@ class Epilogue(ctypes.Structure):
                 ('act', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
                 ('residual', ctypes.c_void_p), ('out_f32', ctypes.c_void_p), ('out_hi', ctypes.c_void_p),
                 ('out_lo', ctypes.c_void_p), ('out_raw', ctypes.c_void_p),
-                ('o_sn', ctypes.c_int64), ('o_sh', ctypes.c_int64), ('o_sw', ctypes.c_int64), ('o_off', ctypes.c_int64)]
+                ('o_sn', ctypes.c_int64), ('o_sh', ctypes.c_int64), ('o_sw', ctypes.c_int64), ('o_off', ctypes.c_int64),
+                ('acc_scale', ctypes.c_float)]
 
 
 class IgemmDesc(ctypes.Structure):
@@ -40,7 +41,7 @@ class IgemmDesc(ctypes.Structure):
                 ('B', ctypes.c_void_p), ('rowsB', ctypes.c_int32), ('ldb', ctypes.c_int64),
                 ('n_img', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('n_out', ctypes.c_int32),
                 ('tw', ctypes.c_int32), ('th', ctypes.c_int32), ('tn', ctypes.c_int32), ('ntaps', ctypes.c_int32),
-                ('taps', Tap * MAX_TAPS), ('epi', Epilogue)]
+                ('taps', Tap * MAX_TAPS), ('epi', Epilogue), ('acc_chunk_k', ctypes.c_int32)]
 
 
 class UpfirdnParams(ctypes.Structure):
@@ -63,14 +64,14 @@ SIGNATURES = {
     'smc_demod_coefs': 'pp q p iii p',
     'smc_pack_nhwc': 'p q p q pp iiii p',
     'smc_unpack_nchw': 'p i pp iiii p',
-    'smc_fir_act': 'p i iiii ppp fff p q ppp p',
+    'smc_fir_act': 'p i iiii ppp fff p q pppp p',
     'smc_torgb': 'pp iiii pp q f p f ppp p q pp p',
-    'smc_act_bwd': 'p iiii pp q ppp q f p f pppp fff ppp p',
-    'smc_fir_bwd': 'p iiii pp p',
+    'smc_act_bwd': 'pp iiii p i p q ppp q f p f pppp fff pppp p',
+    'smc_fir_bwd': 'pp iiii ppp p',
     'smc_sgrad_finish': 'ppppp q pp iii p',
     'smc_grad_scale': 'p q f pp p',
     'smc_resample_fwd': 'pppppp i iii i pp p',
-    'smc_resample_bwd': 'ppppppp i iii p p',
+    'smc_resample_bwd': 'ppppppp i iii p p p',
     'smc_patchify': 'ppp iii p',
     'smc_unpatchify': 'pp iii p',
     'smc_assemble_tokens': 'pppp iii p',
@@ -84,7 +85,7 @@ SIGNATURES = {
     'smc_split_rows': 'ppp q iiii p',
     'smc_head_proj': 'ppp iii p',
     'smc_head_proj_bwd': 'ppp iii p',
-    'smc_clip_loss': 'ppppp ii ff p',
+    'smc_clip_loss': 'ppppp ii ff p f p',
     'smc_sgd_step': 'pp q fff p',
 }
 

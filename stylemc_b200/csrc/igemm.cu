@@ -22,6 +22,7 @@ namespace smc {
 struct IgParams {
   int n_img, H, W, C, n_out, ntaps;
   int tw, th, tn, tiles_w, tiles_h;
+  int chunk_iters;   // ACC mode: smem stages per accumulation chunk
   smc_igemm_tap taps[SMC_IGEMM_MAX_TAPS];
   smc_igemm_epilogue epi;
 };
@@ -97,15 +98,19 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
-template <int BN, int KC, int STAGES>
-__global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ CUtensorMap mapA,
+// ACC = true ("promoted accumulation"): the tensor core adds into its fp32 accumulator with truncation, a bias toward zero that
+// grows with the length of the accumulation chain (measured on B200: 2.3e-5 relative after 864 K=16 steps, 2.7e-6 after 96).
+// In this mode the K loop is cut into chunks that alternate between two TMEM accumulators; the epilogue warps drain each
+// finished chunk into fp32 registers (round-to-nearest adds) while the next chunk is being accumulated.
+template <int BN, int KC, int STAGES, bool ACC>
+__global__ void __launch_bounds__(192, ACC ? 1 : 2) igemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                     const __grid_constant__ CUtensorMap mapB,
                                                     const __grid_constant__ IgParams p) {
   constexpr int A_BYTES = 128 * KC * 2;
   constexpr int B_BYTES = BN * KC * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int SWZ = KC * 2;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = (ACC ? 2 : 1) * (BN < 32 ? 32 : BN);
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=f16 [7,10)=0, B=f16 [10,13)=0,
   // A,B K-major [15],[16]=0, N>>3 at [17,23), M>>4 at [24,29)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -115,8 +120,9 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ CUte
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* accum_bar = empty_bar + STAGES;          // [2] accumulator full
+  uint64_t* drained_bar = accum_bar + 2;               // [2] accumulator drained by the epilogue warps (ACC mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,7 +141,10 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ CUte
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    mbar_init(&accum_bar[0], 1);
+    mbar_init(&accum_bar[1], 1);
+    mbar_init(&drained_bar[0], 128);
+    mbar_init(&drained_bar[1], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -167,9 +176,16 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      const int chunk_iters = ACC ? p.chunk_iters : total;
+      int in_chunk = 0, chunk = 0;
       for (int it = 0; it < total; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int buf = ACC ? (chunk & 1) : 0;
+        if (ACC && in_chunk == 0 && chunk >= 2) {   // the epilogue must have drained this accumulator (chunk - 2)
+          mbar_wait(&drained_bar[buf], (uint32_t)((chunk >> 1) - 1) & 1u);
+          tcgen05_fence_after();
+        }
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
@@ -177,10 +193,14 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ CUte
         const uint64_t db = make_kmajor_desc<SWZ>(a_addr + A_BYTES);
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k)  // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in 16-B units
-          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (uint32_t)((it | k) != 0));
+          umma_f16(tmem_base + (uint32_t)(buf * BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (uint32_t)((in_chunk | k) != 0));
         tcgen05_commit(&empty_bar[s]);
+        if (++in_chunk == chunk_iters || it == total - 1) {
+          tcgen05_commit(&accum_bar[buf]);
+          in_chunk = 0;
+          ++chunk;
+        }
       }
-      tcgen05_commit(accum_bar);
     }
     __syncwarp();
   } else {
@@ -198,19 +218,46 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ CUte
     if (e.noise != nullptr && valid) nz = __ldg(e.noise + (long long)h * e.noise_sh + (long long)w * e.noise_sw);
     const float* rs = e.row_scale ? e.row_scale + (long long)(valid ? n : 0) * p.n_out : nullptr;
     const float* ps = e.post_scale ? e.post_scale + (long long)(valid ? n : 0) * p.n_out : nullptr;
+    const float acc_scale = e.acc_scale != 0.f ? e.acc_scale : 1.f;
 
-    mbar_wait(accum_bar, 0);
-    tcgen05_fence_after();
-#pragma unroll 1
+    float accr[ACC ? BN : 1];
+    if (ACC) {
+#pragma unroll
+      for (int j = 0; j < (ACC ? BN : 1); ++j) accr[j] = 0.f;
+      const int nchunks = (total + p.chunk_iters - 1) / p.chunk_iters;
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int buf = chunk & 1;
+        mbar_wait(&accum_bar[buf], (uint32_t)(chunk >> 1) & 1u);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) accr[(ACC ? c0 : 0) + (ACC ? j : 0)] += __uint_as_float(r[j]);
+        }
+        tcgen05_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&drained_bar[buf])) : "memory");
+      }
+    } else {
+      mbar_wait(&accum_bar[0], 0);
+      tcgen05_fence_after();
+    }
+#pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (ACC) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(accr[(ACC ? c0 : 0) + (ACC ? j : 0)]);
+      } else {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      }
       if (valid) {
         const int o0 = nt * BN + c0;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
+          float x = __uint_as_float(r[j]) * acc_scale;
           if (rs) x *= __ldg(rs + o0 + j);
           x += nz;
           if (e.bias) x += __ldg(e.bias + o0 + j);
@@ -299,16 +346,16 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-template <int BN, int KC, int STAGES>
+template <int BN, int KC, int STAGES, bool ACC>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const IgParams& p, int grid, cudaStream_t st) {
   constexpr int SMEM = STAGES * (128 * KC * 2 + BN * KC * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, KC, STAGES, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  igemm_kernel<BN, KC, STAGES><<<grid, 192, SMEM, st>>>(ma, mb, p);
+  igemm_kernel<BN, KC, STAGES, ACC><<<grid, 192, SMEM, st>>>(ma, mb, p);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
@@ -325,6 +372,7 @@ int igemm_launch(const smc_igemm_desc* d, cudaStream_t st) {
   else if (d->n_out % 64 == 0) BN = 64;
   else if (d->n_out % 32 == 0) BN = 32;
   else return SMC_EUNSUPPORTED;
+  if (d->acc_chunk_k > 0 && BN == 128) BN = 64;   // 64 register accumulators per epilogue thread (128 would spill)
 
   IgParams p;
   p.n_img = d->n_img; p.H = d->H; p.W = d->W; p.C = d->C; p.n_out = d->n_out; p.ntaps = d->ntaps;
@@ -377,14 +425,24 @@ int igemm_launch(const smc_igemm_desc* d, cudaStream_t st) {
     if (r != CUDA_SUCCESS) return SMC_EDRIVER;
   }
   const int g = (int)grid;
-  if (KC == 64) {
-    if (BN == 128) return launch_cfg<128, 64, 3>(ma, mb, p, g, st);
-    if (BN == 64) return launch_cfg<64, 64, 4>(ma, mb, p, g, st);
-    return launch_cfg<32, 64, 4>(ma, mb, p, g, st);
+  if (d->acc_chunk_k > 0) {   // promoted accumulation: chunks of about acc_chunk_k K-elements
+    p.chunk_iters = d->acc_chunk_k / KC < 1 ? 1 : d->acc_chunk_k / KC;
+    if (KC == 64) {
+      if (BN == 64) return launch_cfg<64, 64, 6, true>(ma, mb, p, g, st);
+      return launch_cfg<32, 64, 6, true>(ma, mb, p, g, st);
+    }
+    if (BN == 64) return launch_cfg<64, 32, 6, true>(ma, mb, p, g, st);
+    return launch_cfg<32, 32, 6, true>(ma, mb, p, g, st);
   }
-  if (BN == 128) return launch_cfg<128, 32, 4>(ma, mb, p, g, st);
-  if (BN == 64) return launch_cfg<64, 32, 4>(ma, mb, p, g, st);
-  return launch_cfg<32, 32, 4>(ma, mb, p, g, st);
+  p.chunk_iters = 0;
+  if (KC == 64) {
+    if (BN == 128) return launch_cfg<128, 64, 3, false>(ma, mb, p, g, st);
+    if (BN == 64) return launch_cfg<64, 64, 4, false>(ma, mb, p, g, st);
+    return launch_cfg<32, 64, 4, false>(ma, mb, p, g, st);
+  }
+  if (BN == 128) return launch_cfg<128, 32, 4, false>(ma, mb, p, g, st);
+  if (BN == 64) return launch_cfg<64, 32, 4, false>(ma, mb, p, g, st);
+  return launch_cfg<32, 32, 4, false>(ma, mb, p, g, st);
 }
 
 }  // namespace smc

@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256) fir_act_kernel(const TIn* __restrict__ pl
                                                       const float* __restrict__ fk /*[4][4] flipped*gain*/, const float* __restrict__ noise,
                                                       const float* __restrict__ bias, float alpha, float gain, float clamp,
                                                       const float* __restrict__ post, long long post_stride,
-                                                      __half* __restrict__ out_raw, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+                                                      __half* __restrict__ out_raw, __half* __restrict__ out_raw_lo,
+                                                      __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   const int cg = C >> 3;
   const long long quads = (long long)N * H * W;  // output is 2H x 2W
   const long long total = quads * cg;
@@ -190,7 +191,16 @@ __global__ void __launch_bounds__(256) fir_act_kernel(const TIn* __restrict__ pl
           v[e] = t;
         }
         const long long o = (((long long)n * (2 * H) + oy) * (2 * W) + ox) * C + c;
-        if (out_raw) *reinterpret_cast<uint4*>(out_raw + o) = f_to_h8(v);
+        if (out_raw) {
+          if (out_raw_lo) {
+            uint4 hi, lo;
+            f_to_h8_split(v, hi, lo);
+            *reinterpret_cast<uint4*>(out_raw + o) = hi;
+            *reinterpret_cast<uint4*>(out_raw_lo + o) = lo;
+          } else {
+            *reinterpret_cast<uint4*>(out_raw + o) = f_to_h8(v);
+          }
+        }
         if (out_hi) {
           if (post) {
 #pragma unroll
@@ -310,14 +320,16 @@ __global__ void __launch_bounds__(256) torgb_kernel(const __half* __restrict__ x
 //     T1[n,c] += sum_p g_up * y        (first style-grad term of the CONSUMER layer)
 //     R[n,c]  += sum_p g_z * (z - noise - b)   (demodulation term of THIS layer)
 // All fp16 gradients carry the global loss scale *gscale_ptr.
-__global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__ y, int N, int H, int W, int C,
-                                                      const __half* __restrict__ g_up, const float* __restrict__ s_next, long long sn_stride,
+template <class TG>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__ y, const __half* __restrict__ y_lo, int N, int H, int W, int C,
+                                                      const TG* __restrict__ g_up, const float* __restrict__ s_next, long long sn_stride,
                                                       const float* __restrict__ g_img /*[N,3,H,W] or null*/, const float* __restrict__ w_rgb,
                                                       const float* __restrict__ s_t, long long st_stride, float wgain,
                                                       const float* __restrict__ b_rgb, float rgb_clamp, const float* __restrict__ gscale_ptr,
                                                       const float* __restrict__ dcoef, const float* __restrict__ noise, const float* __restrict__ bias,
                                                       float alpha, float gain, float clamp,
-                                                      __half* __restrict__ gd, float* __restrict__ T1, float* __restrict__ R, int lpp, int pix_per_block) {
+                                                      __half* __restrict__ gd, __half* __restrict__ gd_lo, float* __restrict__ T1, float* __restrict__ R,
+                                                      int lpp, int pix_per_block) {
   extern __shared__ float red[];  // [2][C] block partials (T1, R)
   const int cg = C >> 3;
   const int lane = threadIdx.x & 31;
@@ -357,6 +369,12 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__
           const int c = g * 8;
           float v[8], st[8], w0[8], w1[8], w2[8];
           h8_to_f(__ldg(reinterpret_cast<const uint4*>(y + pix * C + c)), v);
+          if (y_lo) {
+            float l[8];
+            h8_to_f(__ldg(reinterpret_cast<const uint4*>(y_lo + pix * C + c)), l);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += l[e];
+          }
           ld8f(s_t + n * st_stride + c, st);
           ld8f(w_rgb + c, w0); ld8f(w_rgb + C + c, w1); ld8f(w_rgb + 2 * C + c, w2);
 #pragma unroll
@@ -389,11 +407,18 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__
       const int c = g * 8;
       float yv[8], gy[8], gu[8];
       h8_to_f(__ldg(reinterpret_cast<const uint4*>(y + pix * C + c)), yv);
+      if (y_lo) {
+        float l[8];
+        h8_to_f(__ldg(reinterpret_cast<const uint4*>(y_lo + pix * C + c)), l);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] += l[e];
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) { gy[e] = 0.f; gu[e] = 0.f; }
       if (g_up) {
         float sn[8];
-        h8_to_f(__ldg(reinterpret_cast<const uint4*>(g_up + pix * C + c)), gu);
+        if (sizeof(TG) == 2) h8_to_f(__ldg(reinterpret_cast<const uint4*>(g_up + pix * C + c)), gu);
+        else ld8f(reinterpret_cast<const float*>(g_up + pix * C + c), gu);
         ld8f(s_next + n * sn_stride + c, sn);
 #pragma unroll
         for (int e = 0; e < 8; ++e) gy[e] = gu[e] * sn[e];
@@ -417,15 +442,27 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__
         const float yy = yv[e];
         const bool pass = (clamp < 0.f) || (yy > -clamp && yy < clamp);
         const float slope = (yy > 0.f ? 1.f : alpha) * gain;
-        const float gz = pass ? gy[e] * slope : 0.f;
+        float gz = pass ? gy[e] * slope : 0.f;
         out[e] = gz * dc[e];
+        // single-plane gradients: let the demodulation term see exactly the rounded value the dgrad GEMM will see, so the
+        // two style-gradient terms keep cancelling along s (scale invariance of the demodulated conv)
+        if (reduce && gd && !gd_lo) gz = __half2float(__float2half_rn(out[e])) / dc[e];
         if (reduce) {
           const float z = yy / slope;                    // pre-activation (exact where the clamp passes)
           racc[ps & 1][e] += gz * (z - nz - bs[e]);
           t1acc[ps & 1][e] += gu[e] * yy;
         }
       }
-      if (gd) *reinterpret_cast<uint4*>(gd + pix * C + c) = f_to_h8(out);
+      if (gd) {
+        if (gd_lo) {
+          uint4 hi, lo;
+          f_to_h8_split(out, hi, lo);
+          *reinterpret_cast<uint4*>(gd + pix * C + c) = hi;
+          *reinterpret_cast<uint4*>(gd_lo + pix * C + c) = lo;
+        } else {
+          *reinterpret_cast<uint4*>(gd + pix * C + c) = f_to_h8(out);
+        }
+      }
     }
   }
   if (reduce) {
@@ -451,8 +488,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // Transpose of the conv0 FIR: g_t[ty, tx] = sum_f fk[fy][fx] * gd[ty - fy + 1, tx - fx + 1]   (gain in fk),
 // written as parity planes GP[r][c][n][a][b][C] (a <= H, b <= W; cells outside the (2H+1)^2 grid are 0).
-__global__ void __launch_bounds__(256) fir_bwd_kernel(const __half* __restrict__ gd, int N, int H, int W, int C,
-                                                      const float* __restrict__ fk, __half* __restrict__ planes) {
+__global__ void __launch_bounds__(256) fir_bwd_kernel(const __half* __restrict__ gd, const __half* __restrict__ gd_lo, int N, int H, int W, int C,
+                                                      const float* __restrict__ fk, __half* __restrict__ planes, __half* __restrict__ planes_lo) {
   const int cg = C >> 3;
   const long long cells = (long long)N * (H + 1) * (W + 1);
   const long long total = cells * cg;
@@ -484,7 +521,14 @@ __global__ void __launch_bounds__(256) fir_bwd_kernel(const __half* __restrict__
         const int gx = 2 * b - 2 + wx;
         if (gx < 0 || gx >= 2 * W) continue;
         float v[8];
-        h8_to_f(__ldg(reinterpret_cast<const uint4*>(gd + (((long long)n * 2 * H + gy) * (2 * W) + gx) * C + c)), v);
+        const long long gi = (((long long)n * 2 * H + gy) * (2 * W) + gx) * C + c;
+        h8_to_f(__ldg(reinterpret_cast<const uint4*>(gd + gi)), v);
+        if (gd_lo) {
+          float l[8];
+          h8_to_f(__ldg(reinterpret_cast<const uint4*>(gd_lo + gi)), l);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += l[e];
+        }
         // gd row gy = ty - fy + 1  =>  fy = ty + 1 - gy = (2a + r) + 1 - (2a - 2 + wy) = r + 3 - wy
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -509,7 +553,15 @@ __global__ void __launch_bounds__(256) fir_bwd_kernel(const __half* __restrict__
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = inside ? acc[r][q][e] : 0.f;
-        *reinterpret_cast<uint4*>(planes + (long long)(r * 2 + q) * plane_sz + (((long long)n * (H + 1) + a) * (W + 1) + b) * C + c) = f_to_h8(o);
+        const long long po = (long long)(r * 2 + q) * plane_sz + (((long long)n * (H + 1) + a) * (W + 1) + b) * C + c;
+        if (planes_lo) {
+          uint4 hi, lo;
+          f_to_h8_split(o, hi, lo);
+          *reinterpret_cast<uint4*>(planes + po) = hi;
+          *reinterpret_cast<uint4*>(planes_lo + po) = lo;
+        } else {
+          *reinterpret_cast<uint4*>(planes + po) = f_to_h8(o);
+        }
       }
   }
 }
@@ -539,7 +591,8 @@ __global__ void __launch_bounds__(256) sgrad_finish_kernel(const float* __restri
   if (i < cin) grad_row[i] += acc / __ldg(gscale_ptr);
 }
 
-// gscale = 2^k with amax(|g|) * gscale in [2^-3, 2^-2): head-room for the growth of the fp16 gradients
+// gscale = 2^k with amax(|g|) * gscale in (target/2, target]: keeps the fp16 gradient planes (and their lo halves) in the
+// normal range; d * g_z is ~1e-2 of g, so the target sits well above 1 (fp16 tops out at 65504)
 __global__ void amax_kernel(const float* __restrict__ g, long long n, unsigned int* __restrict__ amax_bits) {
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(g[i]));
@@ -601,17 +654,17 @@ extern "C" int smc_unpack_nchw(const void* x, int x_is_half, float* y, const flo
 
 extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* noise,
                            const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
-                           void* out_raw, void* out_hi, void* out_lo, void* stream) {
+                           void* out_raw, void* out_raw_lo, void* out_hi, void* out_lo, void* stream) {
   if (!planes || !fk || !bias || n < 1 || h < 1 || w < 1 || c < 8 || (c & 7)) return SMC_EINVAL;
   if (!out_raw && !out_hi) return SMC_EINVAL;
   const long long items = (long long)n * h * w * (c >> 3);
   const int g = grid_for(items, 256);
   if (planes_is_half)
     fir_act_kernel<__half><<<g, 256, 0, (cudaStream_t)stream>>>((const __half*)planes, n, h, w, c, fk, noise, bias, alpha, gain, clamp, post,
-                                                                   post_stride, (__half*)out_raw, (__half*)out_hi, (__half*)out_lo);
+                                                                   post_stride, (__half*)out_raw, (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo);
   else
     fir_act_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)planes, n, h, w, c, fk, noise, bias, alpha, gain, clamp, post,
-                                                                  post_stride, (__half*)out_raw, (__half*)out_hi, (__half*)out_lo);
+                                                                  post_stride, (__half*)out_raw, (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
@@ -632,10 +685,10 @@ extern "C" int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w
   return SMC_OK;
 }
 
-extern "C" int smc_act_bwd(const void* y, int n, int h, int w, int c, const void* g_up, const float* s_next, int64_t sn_stride,
-                           const float* g_img, const float* w_rgb, const float* s_t, int64_t st_stride, float wgain, const float* b_rgb,
-                           float rgb_clamp, const float* gscale, const float* dcoef, const float* noise, const float* bias, float alpha,
-                           float gain, float clamp, void* gd, float* t1, float* r, void* stream) {
+extern "C" int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w, int c, const void* g_up, int g_up_is_f32, const float* s_next,
+                           int64_t sn_stride, const float* g_img, const float* w_rgb, const float* s_t, int64_t st_stride, float wgain,
+                           const float* b_rgb, float rgb_clamp, const float* gscale, const float* dcoef, const float* noise, const float* bias,
+                           float alpha, float gain, float clamp, void* gd, void* gd_lo, float* t1, float* r, void* stream) {
   if (!y || (!gd && !t1) || (gd && !dcoef) || !bias || n < 1 || h < 1 || w < 1 || c < 32 || (c & 7) || c > 512) return SMC_EINVAL;
   if (!g_up && !g_img) return SMC_EINVAL;
   if (g_up && !s_next) return SMC_EINVAL;
@@ -647,17 +700,24 @@ extern "C" int smc_act_bwd(const void* y, int n, int h, int w, int c, const void
   while (pix_per_block > 8 * (32 / lpp) && ceil_div_ll(hw, pix_per_block) * n < 2 * kNumSMs) pix_per_block >>= 1;
   const long long blocks = ceil_div_ll(hw, pix_per_block) * n;
   if (blocks > 0x7fffffffLL) return SMC_ETOOLARGE;
-  act_bwd_kernel<<<(int)blocks, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)y, n, h, w, c, (const __half*)g_up, s_next, sn_stride, g_img, w_rgb, s_t, st_stride, wgain, b_rgb, rgb_clamp, gscale,
-      dcoef, noise, bias, alpha, gain, clamp, (__half*)gd, t1, r, lpp, pix_per_block);
+  if (g_up_is_f32)
+    act_bwd_kernel<float><<<(int)blocks, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+        (const __half*)y, (const __half*)y_lo, n, h, w, c, (const float*)g_up, s_next, sn_stride, g_img, w_rgb, s_t, st_stride, wgain, b_rgb,
+        rgb_clamp, gscale, dcoef, noise, bias, alpha, gain, clamp, (__half*)gd, (__half*)gd_lo, t1, r, lpp, pix_per_block);
+  else
+    act_bwd_kernel<__half><<<(int)blocks, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+        (const __half*)y, (const __half*)y_lo, n, h, w, c, (const __half*)g_up, s_next, sn_stride, g_img, w_rgb, s_t, st_stride, wgain, b_rgb,
+        rgb_clamp, gscale, dcoef, noise, bias, alpha, gain, clamp, (__half*)gd, (__half*)gd_lo, t1, r, lpp, pix_per_block);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
 
-extern "C" int smc_fir_bwd(const void* gd, int n, int h, int w, int c, const float* fk, void* planes, void* stream) {
+extern "C" int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int w, int c, const float* fk, void* planes, void* planes_lo,
+                           void* stream) {
   if (!gd || !fk || !planes || n < 1 || h < 1 || w < 1 || c < 8 || (c & 7)) return SMC_EINVAL;
   const long long items = (long long)n * (h + 1) * (w + 1) * (c >> 3);
-  fir_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)gd, n, h, w, c, fk, (__half*)planes);
+  fir_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)gd, (const __half*)gd_lo, n, h, w, c, fk, (__half*)planes,
+                                                                                    (__half*)planes_lo);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

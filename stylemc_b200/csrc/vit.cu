@@ -86,8 +86,9 @@ __global__ void __launch_bounds__(256) resample_vT_kernel(const float* __restric
 // gx[b,c,y,ix] = 127.5 * [0 < x*127.5+128 < 255] * sum_k wT[ix][k] * gt[b,c,y,oT[ix][k]]
 __global__ void __launch_bounds__(256) resample_hT_kernel(const float* __restrict__ gt, const float* __restrict__ x, float* __restrict__ gx,
                                                           const int* __restrict__ oidx, const int* __restrict__ count, const float* __restrict__ wgt,
-                                                          int taps, long long rows, int in_w, int out_w) {
+                                                          int taps, long long rows, int in_w, int out_w, const float* __restrict__ unscale) {
   const long long total = rows * in_w;
+  const float k127 = 127.5f / (unscale ? __ldg(unscale) : 1.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ix = (int)(i % in_w);
     const long long r = i / in_w;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) resample_hT_kernel(const float* __restric
       const float* src = gt + r * out_w;
       const int cnt = count[ix];
       for (int k = 0; k < cnt; ++k) acc += __ldg(wgt + (long long)ix * taps + k) * __ldg(src + oidx[(long long)ix * taps + k]);
-      acc *= 127.5f;
+      acc *= k127;
     }
     gx[i] = acc;
   }
@@ -384,9 +385,10 @@ __global__ void __launch_bounds__(256) head_proj_bwd_kernel(const float* __restr
 // the caller) and dE_tgt[n,:] = -coef * inv_count * (t/|t| - cos * e/|e|) / |e|.
 __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict__ e_src, const float* __restrict__ e_tgt, const float* __restrict__ text,
                                                         float* __restrict__ loss_part, float* __restrict__ d_tgt, int N, int E, float coef,
-                                                        float inv_count) {
+                                                        float inv_count, float* __restrict__ gscale_out, float gscale_target) {
   __shared__ float red[3][16];
   __shared__ float bc[3];
+  float dmax = 0.f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float total = 0.f;
   for (int n = 0; n < N; ++n) {
@@ -411,11 +413,27 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
     if (d_tgt) {
       for (int j = threadIdx.x; j < E; j += blockDim.x) {
         const float e = e_tgt[(long long)n * E + j] - e_src[(long long)n * E + j];
-        d_tgt[(long long)n * E + j] = -coef * inv_count * (text[j] / nt - cosv * e / ne) / ne;
+        const float dv = -coef * inv_count * (text[j] / nt - cosv * e / ne) / ne;
+        d_tgt[(long long)n * E + j] = dv;
+        dmax = fmaxf(dmax, fabsf(dv));
       }
     }
   }
   if (threadIdx.x == 0) *loss_part = coef * inv_count * total;
+  if (d_tgt && gscale_out) {
+    // loss scaling for the fp16 backward GEMMs: d_tgt *= S, S = 2^k with max|d_tgt| * S in [target/2, target)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    __syncthreads();
+    if (lane == 0) red[0][warp] = dmax;
+    __syncthreads();
+    float m = 0.f;
+    for (int w = 0; w < nw; ++w) m = fmaxf(m, red[0][w]);
+    float S = 1.f;
+    if (m > 0.f && isfinite(m)) S = exp2f(floorf(log2f(gscale_target / m)));
+    for (int i = threadIdx.x; i < N * E; i += blockDim.x) d_tgt[i] *= S;
+    if (threadIdx.x == 0) *gscale_out = S;
+  }
 }
 
 static int grid1d(long long items) {
@@ -448,12 +466,12 @@ extern "C" int smc_resample_fwd(const float* x, float* tmp, float* y, const int*
 }
 
 extern "C" int smc_resample_bwd(const float* g, const float* x, float* tmp, float* gx, const int* oidx, const int* count, const float* wgt,
-                                int taps, int planes, int in_size, int out_size, const float* std3, void* stream) {
+                                int taps, int planes, int in_size, int out_size, const float* std3, const float* unscale, void* stream) {
   if (!g || !x || !tmp || !gx || !oidx || !count || !wgt || !std3 || taps < 1 || planes < 1) return SMC_EINVAL;
   resample_vT_kernel<<<grid1d((long long)planes * in_size * out_size), 256, 0, ST>>>(g, tmp, oidx, count, wgt, taps, planes, in_size, out_size,
                                                                                       out_size, std3[0], std3[1], std3[2]);
   const long long rows = (long long)planes * in_size;
-  resample_hT_kernel<<<grid1d(rows * in_size), 256, 0, ST>>>(tmp, x, gx, oidx, count, wgt, taps, rows, in_size, out_size);
+  resample_hT_kernel<<<grid1d(rows * in_size), 256, 0, ST>>>(tmp, x, gx, oidx, count, wgt, taps, rows, in_size, out_size, unscale);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
@@ -551,9 +569,9 @@ extern "C" int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln
   return SMC_OK;
 }
 extern "C" int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
-                             float inv_count, void* stream) {
+                             float inv_count, float* gscale_out, float gscale_target, void* stream) {
   if (!e_src || !e_tgt || !text || !loss_part || n < 1 || e < 1) return SMC_EINVAL;
-  clip_loss_kernel<<<1, 512, 0, ST>>>(e_src, e_tgt, text, loss_part, d_tgt, n, e, coef, inv_count);
+  clip_loss_kernel<<<1, 512, 0, ST>>>(e_src, e_tgt, text, loss_part, d_tgt, n, e, coef, inv_count, gscale_out, gscale_target);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

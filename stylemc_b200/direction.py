@@ -1,0 +1,130 @@
+"""The find_direction optimisation step (find_direction.py:256-353) on the fused engines, and its data-parallel form.
+
+One step = two synthesis forwards (edited + original S), ``unprocess`` of both, two CLIP ViT-B/32 forwards, the directional
+CLIP loss (clip_loss.py:24-34), the backward pass CLIP -> unprocess -> synthesis down to the trainable S rows, the analytic
+gradient of the L2 term (find_direction.py:190-191) and one SGD update (:285,339).  Across GPUs the seed batch is sharded by
+rows; the only exchange is an all-reduce of the ``[8, 512]`` gradient (16 KiB) and of the loss scalars.
+
+Only ``clip_type='small'`` (ViT-B/32) with ``clip_loss_type='default'`` is implemented; identity and landmark terms are outside
+the accelerated path.
+"""
+import math
+
+import torch
+
+from . import _lib, resample, synthesis, utils
+
+S_TRAINABLE_SPACE_CHANNELS = [2, 3, 5, 6, 8, 9, 11, 12]     # find_direction.py:41
+N_STYLE_CHANNELS = 26                                       # find_direction.py:38
+RESOLUTION_DICT = {256: 6, 512: 7, 1024: 8}                 # find_direction.py:263
+
+
+class CLIPLoss:
+    """clip_loss.CLIPLoss (clip_loss.py:8-34) with the model and the token ids injected (``clip.load`` / ``clip.tokenize`` are
+    external).  ``__call__`` is the differentiable drop-in; ``loss_and_grad`` is the fused kernel used by the step."""
+
+    def __init__(self, model, pos_tokens, neg_tokens):
+        self.model = model
+        t = model.encode_text(pos_tokens) - model.encode_text(neg_tokens)            # clip_loss.py:15-17
+        self.text_features = (t / t.norm(dim=1, keepdim=True)).contiguous()          # :18, [1, 512]
+
+    def __call__(self, src_image, tgt_image):
+        e = self.model.encode_image(tgt_image) - self.model.encode_image(src_image)  # :25-27
+        e = e / e.norm(dim=1, keepdim=True)                                          # :28
+        cos = torch.nn.functional.cosine_similarity(e, self.text_features)           # :29-32
+        return (len(src_image) - cos.sum()) / len(src_image)                         # :34
+
+    def loss_and_grad(self, e_src, e_tgt, coef, inv_count, want_grad=True, gscale_target=64.0):
+        """Returns (loss_part, d_tgt, gscale): loss_part = -coef * inv_count * sum_n cos_n (add ``coef * n * inv_count`` for
+        the full term); d_tgt = S * d(loss)/d(e_tgt) with the power-of-two loss scale S stored in the device scalar gscale."""
+        n, e = e_tgt.shape
+        dev = e_tgt.device
+        part = torch.empty(1, dtype=torch.float32, device=dev)
+        d_tgt = torch.empty_like(e_tgt) if want_grad else None
+        gscale = torch.ones(1, dtype=torch.float32, device=dev) if want_grad else None
+        with torch.cuda.device(dev):
+            _lib.call('smc_clip_loss', _lib.ptr(e_src), _lib.ptr(e_tgt), _lib.ptr(self.text_features), _lib.ptr(part), _lib.ptr(d_tgt), n, e,
+                      float(coef), float(inv_count), _lib.ptr(gscale), float(gscale_target), _lib.stream())
+        return part, d_tgt, gscale
+
+
+def cosine_lr(base_lr, it, total):
+    """find_direction.py:298-299 (``it`` is 1-based)."""
+    return math.cos(math.pi * it / total) * base_lr * 0.5 + base_lr * 0.5
+
+
+class DirectionFinder:
+    """State and step function of the S-space direction search for one prompt pair.
+
+    G: frozen generator (attribute structure of the unpickled network); clip_model: stylemc_b200.clip.CLIPModel;
+    resolution: 256 / 512 / 1024 -> until_k per find_direction.py:263 (the network is truncated after that block).
+    precision: synthesis engine mode; 'x3p' reproduces the fp32 reference's gradient to <= 1e-3, 'x1' is the fast fp16-operand
+    mode (images <= 1e-2, loss <= 1e-3, gradient ~1e-2: the lrelu kinks amplify forward rounding, DESIGN.md "Numerics").
+    process_group: torch.distributed group for the data-parallel run (None = single process)."""
+
+    def __init__(self, G, clip_model, pos_tokens, neg_tokens, resolution, device='cuda', learning_rate=1.5, clip_loss_coef=1.0,
+                 l2_reg_coef=0.1, noise_mode='const', precision='x3p', micro_batch=16, process_group=None,
+                 trainable_rows=S_TRAINABLE_SPACE_CHANNELS):
+        self.device = torch.device(device)
+        self.engine = utils.engine_for(G, self.device, precision)
+        self.until_k = RESOLUTION_DICT[resolution] if resolution in RESOLUTION_DICT else int(math.log2(resolution)) - 2
+        self.until_k = min(self.until_k, len(self.engine.blocks) - 1)
+        self.clip = clip_model
+        self.loss_fn = CLIPLoss(clip_model, pos_tokens, neg_tokens)
+        self.lr, self.clip_loss_coef, self.l2_reg_coef = learning_rate, clip_loss_coef, l2_reg_coef
+        self.noise_mode, self.micro_batch = noise_mode, micro_batch
+        self.rows = list(trainable_rows)
+        self.delta = torch.zeros([1, len(self.rows), synthesis.STYLE_WIDTH], dtype=torch.float32, device=self.device)   # :270-273
+        self.group = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.kernel_launches = 0
+
+    # ---- pieces ----------------------------------------------------------------------------------
+    def direction(self):
+        """styles_direction [1, 26, 512] (find_direction.py:306-307; the tensor saved as direction_*.npz, :349-351)."""
+        d = torch.zeros([1, N_STYLE_CHANNELS, synthesis.STYLE_WIDTH], dtype=torch.float32, device=self.device)
+        d[:, self.rows] = self.delta
+        return d
+
+    def loss_and_grad(self, styles, global_count=None):
+        """styles [n, 26, 512] (this rank's shard, device) -> (grad [8, 512] summed over the shard, clip-loss partial sum).
+        ``global_count`` is the number of seeds in the whole step (all ranks); the CLIP loss is their mean (clip_loss.py:34)."""
+        n_total = styles.shape[0]
+        count = n_total if global_count is None else global_count
+        grad = torch.zeros([len(self.rows), synthesis.STYLE_WIDTH], dtype=torch.float32, device=self.device)
+        part_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
+        direction = self.direction()
+        eng = self.engine
+        for lo in range(0, n_total, self.micro_batch):
+            s = styles[lo:lo + self.micro_batch].to(self.device, torch.float32)
+            s2 = s + direction                                                        # find_direction.py:308
+            _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True)                 # :309
+            _, original, _ = eng.forward(s, self.until_k, self.noise_mode, save=False)                # :312
+            u_t = resample.unprocess_fwd(img)                                                      # :159-160
+            u_s = resample.unprocess_fwd(original)
+            e_s, _ = self.clip.encode_image_fwd(u_s, save=False)
+            e_t, csaved = self.clip.encode_image_fwd(u_t, save=True)
+            part, d_t, gscale = self.loss_fn.loss_and_grad(e_s, e_t, self.clip_loss_coef, 1.0 / count)
+            g224 = self.clip.encode_image_bwd(csaved, d_t)
+            g_img = resample.unprocess_bwd(g224, img, unscale=gscale)
+            grad += eng.backward(saved, g_img, self.rows, self.noise_mode)
+            part_sum += part
+        return grad, part_sum
+
+    def step(self, styles, lr=None, global_count=None):
+        """One optimisation step on this rank's shard.  Returns a dict of device scalars (loss, clip_loss, l2_loss, grad_norm)."""
+        lr = self.lr if lr is None else lr
+        count = styles.shape[0] * self.world if global_count is None else global_count
+        grad, part = self.loss_and_grad(styles, count)
+        if self.world > 1:
+            buf = torch.cat([grad.reshape(-1), part])
+            torch.distributed.all_reduce(buf, group=self.group)
+            grad, part = buf[:-1].reshape(grad.shape), buf[-1:]
+        numel = self.delta.numel()
+        l2 = self.l2_reg_coef * self.delta.square().mean()                            # find_direction.py:190-191 (batch independent)
+        clip_loss = self.clip_loss_coef + part                                        # coef * (count - sum cos) / count
+        l2_scale = 2.0 * self.l2_reg_coef / numel
+        grad_total = grad + l2_scale * self.delta[0]
+        with torch.cuda.device(self.device):
+            _lib.call('smc_sgd_step', _lib.ptr(self.delta), _lib.ptr(grad), numel, float(lr), 1.0, float(l2_scale), _lib.stream())   # :339
+        return dict(loss=clip_loss + l2, clip_loss=clip_loss, l2_loss=l2, grad=grad_total, grad_norm=grad_total.norm())

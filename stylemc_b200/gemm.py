@@ -34,7 +34,7 @@ def up2_dgrad_taps(n_img):
 def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=None, b_rows_per_tap=None,
           row_scale=None, post_scale=None, bias=None, noise=None, noise_strides=(0, 0), act=0, alpha=0.2, gain=1.0,
           clamp=-1.0, residual=None, out_f32=None, out_hi=None, out_lo=None, out_raw=None, out_strides=None, out_offset=0,
-          tile=None):
+          tile=None, acc_scale=1.0, acc_chunk_k=0):
     """Launch one implicit GEMM.
 
     A: fp16 tensor viewed as [NA, HA, WA, C] (NA includes the hi/lo planes stacked on the image axis).
@@ -76,8 +76,20 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
         out_strides = (H * W * n_out, W * n_out, n_out)
     e.o_sn, e.o_sh, e.o_sw = out_strides
     e.o_off = out_offset
+    e.acc_scale = acc_scale
+    d.acc_chunk_k = acc_chunk_k
     with torch.cuda.device(A.device):
         _lib.call('smc_igemm', ctypes.addressof(d), _lib.stream())
+
+
+def pow2_prescale(x, target=256.0):
+    """Power of two k such that max|x| * k lies in [target/2, target): keeps the lo plane of small weights out of the fp16
+    subnormal range.  The GEMM undoes it with ``acc_scale = 1 / k``."""
+    import math
+    amax = float(x.abs().max())
+    if amax == 0.0 or not math.isfinite(amax):
+        return 1.0
+    return 2.0 ** (math.floor(math.log2(target / amax)))
 
 
 def split_planes(x, two):

@@ -44,7 +44,7 @@ class _Layer:
         taps_fwd = w.permute(2, 3, 0, 1).reshape(9 * self.cout, self.cin)      # row t*O + o, col i
         taps_bwd = w.permute(2, 3, 1, 0).reshape(9 * self.cin, self.cout)      # row t*I + i, col o (dgrad)
         self.B_fwd = gemm.split_planes(taps_fwd, True).reshape(2 * 9 * self.cout, self.cin)
-        self.B_bwd = taps_bwd.to(torch.float16).contiguous()
+        self.B_bwd = gemm.split_planes(taps_bwd, True).reshape(2 * 9 * self.cin, self.cout)
         self.q = w.square().sum(dim=[2, 3]).contiguous()               # [O, I]
         self.bias = _f32(mod.bias, device)
         strength = float(mod.noise_strength) if getattr(mod, 'use_noise', True) else 0.0
@@ -88,8 +88,9 @@ class SavedForward:
 class SynthesisEngine:
     """Execution plan for one frozen ``G.synthesis`` on one GPU.
 
-    precision: 'x1' fp16 operands; 'x3' split-fp16 operands everywhere (fp32-grade); 'mixed' = 'x3' for blocks up to
-    ``x3_max_res`` (the low-resolution, 512-channel layers where the S gradient is formed) and 'x1' above.
+    precision: 'x1' fp16 operands (fast); 'x3' split-fp16 operands everywhere; 'mixed' = 'x3' for blocks up to ``x3_max_res``
+    and 'x1' above; 'x3p' = 'x3' with promoted accumulation (the K loop is drained into fp32 registers every 512 elements),
+    the mode that reproduces an fp32 reference to fp32 accuracy -- see DESIGN.md "Numerics".
     """
 
     def __init__(self, G, device='cuda', precision='mixed', x3_max_res=64):
@@ -105,9 +106,10 @@ class SynthesisEngine:
         assert f.shape == (4, 4), 'the fused engine implements the 4x4 [1,3,3,1] resample filter'
         self.filter = f
         self.fk4 = (f.flip([0, 1]) * 4.0).contiguous()                 # flipped taps * gain (up=2 -> gain 4)
-        if precision not in ('x1', 'x3', 'mixed'):
+        if precision not in ('x1', 'x3', 'mixed', 'x3p'):
             raise ValueError(precision)
-        self.precision, self.x3_max_res = precision, x3_max_res
+        self.acc_k = 512 if precision == 'x3p' else 0
+        self.precision, self.x3_max_res = ('x3' if precision == 'x3p' else precision), x3_max_res
         # style row of (conv0, conv1, torgb) per block (utils.py:169-185)
         self.rows, r = [], 0
         for b in self.blocks:
@@ -149,29 +151,29 @@ class SynthesisEngine:
     def _conv1(self, L, xs, d, noise, n, res, prec, want_lo):
         """3x3 modulated conv + noise + bias + lrelu + clamp; returns y planes [P, n, res, res, cout]."""
         y = self._planes(n, res, res, L.cout, want_lo)
-        gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec,
+        gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec, acc_chunk_k=self.acc_k,
                    a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, bias=L.bias, noise=noise,
                    noise_strides=(res, 1), act=1, alpha=LRELU_ALPHA, gain=L.gain, clamp=L.clamp,
                    out_hi=y[0], out_lo=y[1] if want_lo else None)
         return y
 
-    def _conv0(self, L, xs, d, noise, styles, row_next, n, hin, prec, want_lo):
+    def _conv0(self, L, xs, d, noise, styles, row_next, n, hin, prec, want_lo, save_lo=False):
         """3x3 transposed stride-2 modulated conv + 4x4 FIR + noise + bias + lrelu + clamp.
-        Returns (y raw fp16 [n, 2h, 2h, cout], xs_next planes = y * styles[:, row_next])."""
+        Returns (y planes [P, n, 2h, 2h, cout] (lo only when saving for an x3 backward), xs_next planes = y * styles[:, row_next])."""
         x3 = prec == 'x3'
         planes = torch.empty([4, n, hin + 1, hin + 1, L.cout], dtype=torch.float32 if x3 else torch.float16, device=self.device)
         for r in (0, 1):
             for c in (0, 1):
                 kw = dict(out_f32=planes[r * 2 + c]) if x3 else dict(out_raw=planes[r * 2 + c])
                 gemm.igemm(xs.reshape(-1, hin, hin, L.cin), L.B_fwd, n, hin + 1, hin + 1, L.cout, gemm.up2_parity_taps(r, c),
-                           precision=prec, a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
+                           precision=prec, acc_chunk_k=self.acc_k, a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
         res = 2 * hin
-        y = torch.empty([n, res, res, L.cout], dtype=torch.float16, device=self.device)
+        y = self._planes(n, res, res, L.cout, x3 and save_lo)
         xn = self._planes(n, res, res, L.cout, want_lo)
         sp, ss = self._srow(styles, row_next)
         _lib.call('smc_fir_act', _lib.ptr(planes), 0 if x3 else 1, n, hin, hin, L.cout, _lib.ptr(self.fk4), _lib.ptr(noise),
-                  _lib.ptr(L.bias), LRELU_ALPHA, L.gain, L.clamp, sp, ss, _lib.ptr(y), _lib.ptr(xn[0]),
-                  _lib.ptr(xn[1]) if want_lo else None, _lib.stream())
+                  _lib.ptr(L.bias), LRELU_ALPHA, L.gain, L.clamp, sp, ss, _lib.ptr(y[0]), _lib.ptr(y[1]) if y.shape[0] == 2 else None,
+                  _lib.ptr(xn[0]), _lib.ptr(xn[1]) if want_lo else None, _lib.stream())
         return y, xn
 
     # ---- forward -------------------------------------------------------------------------------
@@ -205,13 +207,13 @@ class SynthesisEngine:
                 else:
                     L0 = blk.conv0
                     d0 = self._demod(L0, styles, r0, n)
-                    y0, xs = self._conv0(L0, xs, d0, self._noise(L0, noise_mode, n), styles, r1, n, res // 2, prec, two)
+                    y0, xs = self._conv0(L0, xs, d0, self._noise(L0, noise_mode, n), styles, r1, n, res // 2, prec, two, save_lo=save)
                     if save:
                         saved.y0[k], saved.d0[k] = y0, d0
                 d1 = self._demod(L1, styles, r1, n)
                 y1 = self._conv1(L1, xs, d1, self._noise(L1, noise_mode, n), n, res, prec, two)
                 if save:
-                    saved.y1[k], saved.d1[k] = y1[0], d1
+                    saved.y1[k], saved.d1[k] = y1, d1
                 # ToRGB + skip + style multiply for the next block's conv0
                 T = blk.torgb
                 new_img = torch.empty([n, 3, res, res], dtype=torch.float32, device=self.device)
@@ -239,7 +241,7 @@ class SynthesisEngine:
         return xs_list, img, saved
 
     # ---- backward ------------------------------------------------------------------------------
-    def backward(self, saved, g_img, trainable_rows, noise_mode='const', grad_scale_target=2.0 ** -3):
+    def backward(self, saved, g_img, trainable_rows, noise_mode='const', grad_scale_target=256.0):
         """Gradient of a scalar loss w.r.t. the trainable S rows, summed over the batch.
 
         saved: SavedForward of the pass that produced img; g_img = dL/dimg [N, 3, R, R] fp32.
@@ -273,13 +275,15 @@ class SynthesisEngine:
                     acc[row] = (torch.zeros([n, cin], dtype=torch.float32, device=dev), torch.zeros([n, cout], dtype=torch.float32, device=dev))
                 return acc[row]
 
-            g_up, up_row = None, None      # gradient w.r.t. the modulated input of the consumer conv above, and its style row
+            g_up, up_row, up_f32 = None, None, False   # gradient w.r.t. the modulated input of the consumer conv above, its style row, dtype
             for k in range(last, -1, -1):
                 blk = self.blocks[k]
                 res = blk.resolution
                 r0, r1, rt = self.rows[k]
                 L1, T = blk.conv1, blk.torgb
                 y1, d1 = saved.y1[k], saved.d1[k]
+                prec = self._prec(res)
+                two = prec == 'x3'             # split-precision backward for the blocks whose forward was split-precision
                 stop_here = (k < lowest_k)       # below the lowest trainable block only T1 of the consumer is needed
                 # ---- conv1 output: consumers are ToRGB (g_img) and the next block's conv0 (g_up)
                 t1 = bufs(up_row, L1.cout, self.blocks[k + 1].conv0.cout)[0] if (g_up is not None and up_row in want) else None
@@ -287,40 +291,44 @@ class SynthesisEngine:
                 need_gd = not stop_here
                 if not need_gd and t1 is None:
                     break
-                gd1 = torch.empty([n, res, res, L1.cout], dtype=torch.float16, device=dev) if need_gd else None
+                gd1 = self._planes(n, res, res, L1.cout, two) if need_gd else None
                 sp, ss = self._srow(styles, up_row) if g_up is not None else (None, 0)
                 stp, sts = self._srow(styles, rt)
                 noise1 = self._noise(L1, noise_mode, n)
-                _lib.call('smc_act_bwd', _lib.ptr(y1), n, res, res, L1.cout, _lib.ptr(g_up), sp, ss,
-                          _lib.ptr(g_img) if need_gd else None, _lib.ptr(T.w), stp, sts, T.wgain, _lib.ptr(T.bias), T.clamp, _lib.ptr(gscale),
-                          _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA, L1.gain, L1.clamp, _lib.ptr(gd1),
+                _lib.call('smc_act_bwd', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if y1.shape[0] == 2 else None, n, res, res, L1.cout,
+                          _lib.ptr(g_up), int(up_f32), sp, ss, _lib.ptr(g_img) if need_gd else None, _lib.ptr(T.w), stp, sts, T.wgain,
+                          _lib.ptr(T.bias), T.clamp, _lib.ptr(gscale), _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA,
+                          L1.gain, L1.clamp, _lib.ptr(gd1[0]) if need_gd else None, _lib.ptr(gd1[1]) if (need_gd and two) else None,
                           _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
                 if stop_here:
                     break
                 # ---- dgrad conv1 -> gradient w.r.t. (y0 * s1) (or const * s1 for b4)
-                if blk.conv0 is None and r1 not in want:
-                    break
-                gx1 = torch.empty([n, res, res, L1.cin], dtype=torch.float16, device=dev)
-                gemm.igemm(gd1, L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, out_raw=gx1)
                 if blk.conv0 is None:
-                    # b4: the input is the constant; T1 of conv1 is sum_p gx1 * const
-                    raise RuntimeError('trainable style rows in b4 are not implemented (reference trains b8..b64 only)')
+                    if r1 in want:
+                        raise RuntimeError('trainable style rows in b4 are not implemented (reference trains b8..b64 only)')
+                    break
+                gx1 = torch.empty([n, res, res, L1.cin], dtype=torch.float32 if two else torch.float16, device=dev)
+                gemm.igemm(gd1.reshape(-1, res, res, L1.cout), L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, precision=prec, acc_chunk_k=self.acc_k,
+                           a_plane_stride_imgs=n, b_rows_per_tap=9 * L1.cin, **(dict(out_f32=gx1) if two else dict(out_raw=gx1)))
                 L0 = blk.conv0
                 y0, d0 = saved.y0[k], saved.d0[k]
                 t1 = bufs(r1, L1.cin, L1.cout)[0] if r1 in want else None
                 rr = bufs(r0, L0.cin, L0.cout)[1] if r0 in want else None
-                gd0 = torch.empty([n, res, res, L0.cout], dtype=torch.float16, device=dev)
+                gd0 = self._planes(n, res, res, L0.cout, two)
                 sp, ss = self._srow(styles, r1)
                 noise0 = self._noise(L0, noise_mode, n)
-                _lib.call('smc_act_bwd', _lib.ptr(y0), n, res, res, L0.cout, _lib.ptr(gx1), sp, ss, None, None, None, 0, 0.0, None, -1.0,
-                          _lib.ptr(gscale), _lib.ptr(d0), _lib.ptr(noise0), _lib.ptr(L0.bias), LRELU_ALPHA, L0.gain, L0.clamp, _lib.ptr(gd0),
+                _lib.call('smc_act_bwd', _lib.ptr(y0[0]), _lib.ptr(y0[1]) if y0.shape[0] == 2 else None, n, res, res, L0.cout, _lib.ptr(gx1),
+                          int(two), sp, ss, None, None, None, 0, 0.0, None, -1.0, _lib.ptr(gscale), _lib.ptr(d0), _lib.ptr(noise0),
+                          _lib.ptr(L0.bias), LRELU_ALPHA, L0.gain, L0.clamp, _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None,
                           _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
                 hin = res // 2
-                gp = torch.empty([4 * n, hin + 1, hin + 1, L0.cout], dtype=torch.float16, device=dev)
-                _lib.call('smc_fir_bwd', _lib.ptr(gd0), n, hin, hin, L0.cout, _lib.ptr(self.fk4), _lib.ptr(gp), _lib.stream())
-                g_up = torch.empty([n, hin, hin, L0.cin], dtype=torch.float16, device=dev)
-                gemm.igemm(gp, L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), out_raw=g_up)
-                up_row = r0
+                gp = torch.empty([2 if two else 1, 4 * n, hin + 1, hin + 1, L0.cout], dtype=torch.float16, device=dev)
+                _lib.call('smc_fir_bwd', _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None, n, hin, hin, L0.cout, _lib.ptr(self.fk4),
+                          _lib.ptr(gp[0]), _lib.ptr(gp[1]) if two else None, _lib.stream())
+                g_up = torch.empty([n, hin, hin, L0.cin], dtype=torch.float32 if two else torch.float16, device=dev)
+                gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=prec, acc_chunk_k=self.acc_k,
+                           a_plane_stride_imgs=4 * n, b_rows_per_tap=9 * L0.cin, **(dict(out_f32=g_up) if two else dict(out_raw=g_up)))
+                up_row, up_f32 = r0, two
                 # ---- skip image: transpose of upsample2d (upfirdn2d.py:245-264)
                 if k > 0:
                     g_img = upfirdn2d.upfirdn2d(g_img, self.filter, down=2, padding=[1, 1, 1, 1], flip_filter=True, gain=4)

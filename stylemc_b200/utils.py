@@ -16,7 +16,7 @@ from . import synthesis
 _engines = weakref.WeakKeyDictionary()
 
 
-def engine_for(G, device='cuda', precision='mixed'):
+def engine_for(G, device='cuda', precision='x3p'):
     """The (cached) execution plan of a frozen generator.  Parameters are snapshotted on first use."""
     per_g = _engines.setdefault(G, {})
     key = (str(torch.device(device)), precision)
@@ -69,7 +69,7 @@ def get_styles(G, ws, block_ws, device):
 
 
 def generate_image(G, until_k, styles, temp_shapes, noise_mode, device, use_blending=False, xs_original=None, masks_dict=None,
-                   precision='mixed'):
+                   precision='x3p'):
     """utils.py:161-216.  Returns (xs, img): per-block feature maps [N, C, res, res] fp32 and the running skip image.
 
     ``temp_shapes`` is accepted for signature compatibility and checked against the network."""

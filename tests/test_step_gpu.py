@@ -1,0 +1,61 @@
+"""GPU parity of one find_direction step against the reference's own loop body run on CPU (tests/golden/step64.npz and
+config1.npz, written by oracle/pin_reference.py).  Tolerances are BASELINE.json's: images <= 1e-2 max-abs, CLIP loss and
+direction gradient <= 1e-3 relative."""
+import pytest
+import torch
+
+from oracle import synthesis as o_syn
+from oracle import vit as o_vit
+
+pytestmark = pytest.mark.gpu
+
+
+def finder(G, resolution, **kw):
+    from stylemc_b200 import clip, direction
+    model = clip.CLIPModel(o_vit.random_clip_params(seed=0), 'cuda', precision='x3p')
+    return direction.DirectionFinder(G, model, o_vit.synthetic_tokens('pos'), o_vit.synthetic_tokens('neg'), resolution, **kw)
+
+
+def check_step(f, g, styles, tag):
+    f.delta.copy_(torch.as_tensor(g['delta']).cuda())
+    delta0 = f.delta.clone()
+    out = f.step(styles.cuda(), lr=0.5)
+    ref_grad = torch.as_tensor(g['grad'])[0]
+    grad_rel = ((out['grad'].cpu() - ref_grad).norm() / ref_grad.norm()).item()
+    loss_rel = abs(out['loss'].item() - float(g['loss'])) / abs(float(g['loss']))
+    clip_rel = abs(out['clip_loss'].item() - float(g['clip_loss'])) / abs(float(g['clip_loss']))
+    print(f'{tag}: loss {out["loss"].item():.6f} ref {float(g["loss"]):.6f} rel {loss_rel:.2e}; clip rel {clip_rel:.2e}; grad rel-l2 {grad_rel:.3e} '
+          f'|grad| {ref_grad.norm():.3e}')
+    assert loss_rel <= 1e-3 and clip_rel <= 1e-3
+    assert grad_rel <= 1e-3
+    # SGD update (find_direction.py:339)
+    want = delta0.cpu()[0] - 0.5 * ref_grad
+    assert ((f.delta.cpu()[0] - want).norm() / (0.5 * ref_grad).norm()).item() <= 2e-3
+
+
+def test_step_64px_golden(golden):
+    g = golden('step64')
+    G = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    o_syn.get_temp_shapes(G)
+    f = finder(G, 64)
+    styles = torch.as_tensor(g['styles'])
+    _, img, _ = f.engine.forward((styles.cuda() + 0), until_k=100)
+    assert (img.cpu() - torch.as_tensor(g['original_img'])).abs().max().item() <= 1e-2
+    check_step(f, g, styles, 'step64')
+
+
+def test_step_config1_256px_golden(golden):
+    """BASELINE.json configs[0]: FFHQ-256 config-f net, batch 4, CLIP ViT-B/32, one step."""
+    g = golden('config1')
+    G = o_syn.make_generator(256, seed=0)
+    ws = torch.as_tensor(g['ws'])
+    S, shapes = o_syn.get_styles(G, ws, o_syn.split_ws(G, ws))
+    f = finder(G, 256, micro_batch=2)          # two micro-batches: exercises the accumulation
+    f.delta.copy_(torch.as_tensor(g['delta']).cuda())
+    _, img, _ = f.engine.forward(S.cuda() + f.direction(), until_k=f.until_k)
+    crop = img[:, :, 96:160, 96:160].cpu()
+    err = (crop - torch.as_tensor(g['img_crop'])).abs().max().item()
+    print('config1 img crop max-abs err', err)
+    assert err <= 1e-2
+    assert (torch.nn.functional.avg_pool2d(img, 8).cpu() - torch.as_tensor(g['img_down'])).abs().max().item() <= 1e-2
+    check_step(f, g, S, 'config1')
