@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Headline benchmark: find_direction synth + CLIP fwd/bwd images/sec @1024px (BASELINE.json metric, configs[3]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on the host cores (CPU oracle)
+
+One "step" = one find_direction optimisation step on a batch of seeds: two synthesis forwards, two unprocess, two CLIP ViT-B/32
+forwards, the directional loss, the backward pass to the trainable S rows, (all-reduce,) SGD.  One image = one seed through one
+step.  ``value`` is measured with the S batch resident in HBM; ``e2e`` runs the same step through the public API with the S batch
+coming from pinned host memory and the loss read back every step.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'find_direction synth+CLIP fwd/bwd images/sec @1024px'
+POS_BODY = [320, 1125, 539, 320, 1710, 539, 320, 14387, 2308]       # placeholder token ids (no BPE vocabulary offline)
+NEG_BODY = [320, 1125, 539, 320, 1710, 539, 320, 25173, 786, 1237]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--resolution', type=int, default=1024)
+    ap.add_argument('--batch', type=int, default=64, help='seeds per GPU per step (BASELINE configs[3]: 64/GPU)')
+    ap.add_argument('--micro-batch', type=int, default=16, help='seeds per pass through the network inside a step')
+    ap.add_argument('--precision', default='x3p', choices=['x1', 'mixed', 'x3', 'x3p'])
+    ap.add_argument('--lr', type=float, default=0.05, help='SGD learning rate (reference default 1.5 is tuned for trained weights; random-init nets diverge with it)')
+    ap.add_argument('--cpu-sample', type=int, default=1, help='seeds per step of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-step', action='store_true', help='run warm-up, then ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=p.get('bf16_tflops_sustained', p.get('bf16_tflops')), hbm=p.get('hbm_gbs'), src='measured (MEASURED_PEAKS.json, sustained bf16)')
+    return dict(tflops=1400.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+
+
+def synth_flops_per_image(blocks, until_k):
+    """Algorithmic forward FLOPs of the synthesis network per image (2*9*Cin*Cout*Hin^2 for conv0,
+    2*9*C^2*H^2 for conv1, 2*C*3*H^2 for ToRGB); the dgrad backward costs the same minus b4."""
+    total = 0
+    for k, b in enumerate(blocks[:until_k + 1]):
+        r = b.resolution
+        if b.conv0 is not None:
+            total += 2 * 9 * b.conv0.cin * b.conv0.cout * (r // 2) ** 2
+        total += 2 * 9 * b.conv1.cin * b.conv1.cout * r * r + 2 * 3 * b.torgb.cin * r * r
+    return total
+
+
+VIT_FLOPS_FWD = 2 * (49 * 3072 * 768 + 12 * 50 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) + 12 * 12 * 2 * 50 * 50 * 64)   # per image
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], None, set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        busy = sorted(sm)[len(sm) // 4:] if sm else []       # drop the idle tail of the sampling window
+        return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    from stylemc_b200 import _lib, clip, direction, networks, utils
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --impl ours needs a CUDA device (there is no CPU path)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    group = None
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+        group = torch.distributed.group.WORLD
+    assert world == a.gpus, f'--gpus {a.gpus} but WORLD_SIZE={world} (launch N > 1 under torch.distributed.run)'
+
+    G = networks.make_generator(a.resolution, seed=0)
+    # S pool: W -> S through the affine layers once (w_s_converter.py:75-82); two batches per rank alternate between steps
+    pool = 2 * a.batch
+    ws = torch.randn(pool, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(1000 + rank))
+    styles_host, shapes = utils.get_styles(G, ws, utils.split_ws(G, ws), 'cpu')
+    styles_host = styles_host.pin_memory()
+    model = clip.CLIPModel(clip.random_params(seed=0), dev, precision='x3p' if a.precision == 'x3p' else ('x3' if a.precision != 'x1' else 'x1'))
+    finder = direction.DirectionFinder(G, model, clip.placeholder_tokens(POS_BODY), clip.placeholder_tokens(NEG_BODY), a.resolution, device=dev,
+                                       precision=a.precision, micro_batch=a.micro_batch, process_group=group, learning_rate=a.lr)
+    # delta == 0 makes edited == original and the directional loss 0/0 (NaN in the reference): start from a small random direction
+    finder.delta.copy_(0.05 * torch.randn(finder.delta.shape, generator=torch.Generator().manual_seed(7)).to(dev))
+    styles_dev = styles_host.to(dev)
+    total_steps = a.steps + a.warmup
+
+    def sync():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident(i):
+        lr = direction.cosine_lr(finder.lr, i + 1, total_steps)
+        finder.step(styles_dev[(i % 2) * a.batch:(i % 2 + 1) * a.batch], lr=lr)
+
+    losses = []
+
+    def step_e2e(i):
+        lr = direction.cosine_lr(finder.lr, i + 1, total_steps)
+        s = styles_host[(i % 2) * a.batch:(i % 2 + 1) * a.batch].to(dev, non_blocking=True)      # H2D from pinned memory
+        losses.append(finder.step(s, lr=lr)['loss'].item())                                       # D2H of the step's loss
+
+    for i in range(a.warmup):
+        step_resident(i)
+    if a.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count
+    ms = timed(step_resident, a.steps)
+    launches = _lib.launch_count - n0
+    ms_e2e = timed(step_e2e, a.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline of the dominant kernel family (smc_igemm): every launch of ONE extra step bracketed by CUDA events
+    records = []
+
+    @contextlib.contextmanager
+    def hook(d, alg_taps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        records.append((e0, e1, 2.0 * d.n_img * d.H * d.W * d.n_out * d.C * alg_taps))
+
+    _lib.igemm_hook = hook
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    step_resident(0)
+    t1.record()
+    torch.cuda.synchronize()
+    _lib.igemm_hook = None
+    ig_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
+    ig_flops = sum(f for _, _, f in records)
+    step_ms_hooked = t0.elapsed_time(t1)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    eng = finder.engine
+    sf = synth_flops_per_image(eng.blocks, finder.until_k)
+    alg_flops_img = 3 * sf + 3 * VIT_FLOPS_FWD                # 2 fwd + dgrad bwd of synthesis, 2 fwd + input-grad bwd of the ViT
+    imgs = a.batch * world * a.steps
+    value = imgs / (ms / 1e3)
+    e2e = imgs / (ms_e2e / 1e3)
+    achieved = ig_flops / (ig_ms / 1e3) / 1e12
+    out = {
+        'metric': METRIC, 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': round(ms / a.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16x3 operands (hi+lo split), f32 accumulate' if a.precision != 'x1' else 'f16 operands, f32 accumulate',
+        'data': 'synthetic (random-init StyleGAN2 config-f + random-init CLIP ViT-B/32, S from randn W)',
+        'config': {'workload': f'find_direction {a.resolution}px, batch {a.batch}/GPU (BASELINE configs[3]), fwd+bwd to delta-S [1,8,512]',
+                   'resolution': a.resolution, 'batch_per_gpu': a.batch, 'global_batch': a.batch * world, 'micro_batch': a.micro_batch,
+                   'precision': a.precision, 'learning_rate': a.lr, 'parallelism': f'dp{world} (seed shards; all-reduce of the 16 KiB gradient)',
+                   'l2_flush': 'none needed: each step streams >10 GB of activations, far larger than the 126 MB L2'},
+        'clocks': clocks,
+        'e2e': {'value': round(e2e, 3), 'unit': 'images/s', 'ms_per_step': round(ms_e2e / a.steps, 3),
+                'h2d_bytes_per_step': a.batch * 26 * 512 * 4, 'd2h_bytes_per_step': 4, 'losses': [round(v, 6) for v in losses]},
+        'gpu_launches': launches,
+        'roofline': {'bound': 'tensor', 'kernel': 'igemm_kernel (tcgen05 implicit GEMM; all launches of one step)', 'achieved': round(achieved, 2),
+                     'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': round(achieved / pk['tflops'], 4), 'traffic': None,
+                     'peak_source': pk['src'], 'launches_per_step': len(records), 'share_of_step': round(ig_ms / step_ms_hooked, 3),
+                     'algorithmic_gflop_per_image': round(alg_flops_img / 1e9, 1),
+                     'step_algorithmic_tflops': round(alg_flops_img * a.batch / (ms / a.steps / 1e3) / 1e12, 2)},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_reference(a, steps=2, warmup=1)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference(a, steps, warmup):
+    """The reference algorithm (CPU oracle: restated network modules + the reference's op semantics, fp32, oneDNN) on a bounded
+    sample of the same workload: ``cpu_sample`` seeds per step at the benchmark resolution, all host threads."""
+    from oracle import direction as o_dir
+    from oracle import synthesis as o_syn
+    from oracle import vit as o_vit
+    torch.set_num_threads(os.cpu_count())
+    G = o_syn.make_generator(a.resolution, seed=0)
+    ws = torch.randn(a.cpu_sample, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(1000))
+    S, shapes = o_syn.get_styles(G, ws, o_syn.split_ws(G, ws))
+    model = o_vit.CLIP(seed=0)
+    loss_fn = o_dir.CLIPLoss(model, o_vit.synthetic_tokens('pos'), o_vit.synthetic_tokens('neg'))
+    delta = 0.05 * torch.randn(1, 8, 512, generator=torch.Generator().manual_seed(7))
+    until_k = o_dir.RESOLUTION_TO_K.get(a.resolution, len(shapes) - 1)
+    times = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        r = o_dir.direction_step(G, shapes, loss_fn, S, delta, until_k)
+        delta = o_dir.sgd_update(delta, r['grad'], a.lr)
+        times.append(time.perf_counter() - t)
+    sec = sum(times[warmup:]) / steps
+    return {'value': round(a.cpu_sample / sec, 4), 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{a.cpu_sample} seed(s) per step at {a.resolution}px, {steps} timed steps after {warmup} warm-up, fp32 oneDNN',
+            'seconds_per_step': round(sec, 3)}
+
+
+def run_reference(a):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    b = cpu_reference(a, steps=a.steps, warmup=a.warmup)
+    out = {'impl': 'reference', 'metric': METRIC, 'value': b['value'], 'unit': 'images/s', 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+           'ms_per_step': round(b['seconds_per_step'] * 1e3, 1), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+           'data': 'synthetic (same random-init networks and S as the CUDA arm)',
+           'config': {'workload': f'find_direction {a.resolution}px, {a.cpu_sample} seed(s) per step on the host cores (bounded sample of configs[3])',
+                      'resolution': a.resolution, 'batch_per_step': a.cpu_sample},
+           'cpu_baseline': b, 'e2e': {'value': b['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == '__main__':
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -131,5 +131,13 @@ def require_cuda(t, name):
         raise RuntimeError(f'{name} must reside on a CUDA device: stylemc_b200 has no CPU path')
 
 
+# kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
+_LAUNCHES = {'smc_abi_version': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2}
+launch_count = 0
+igemm_hook = None      # bench.py installs a callable(desc_addr) -> context manager to time every smc_igemm launch
+
+
 def call(name, *args):
+    global launch_count
+    launch_count += _LAUNCHES.get(name, 1)
     check(getattr(lib(), name)(*args), name)

@@ -407,13 +407,16 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
       bc[0] = a; bc[1] = b2; bc[2] = c;
     }
     __syncthreads();
+    // e == 0 (edited image identical to the original, i.e. delta == 0): the direction is undefined -- the reference divides
+    // 0/0 and turns the whole run into NaN (clip_loss.py:28).  Here that sample contributes cos = 0 and no gradient.
+    const bool degenerate = !(bc[0] > 0.f);
     const float ne = fmaxf(sqrtf(bc[0]), 1e-8f), nt = fmaxf(sqrtf(bc[2]), 1e-8f);
-    const float cosv = bc[1] / (ne * nt);
+    const float cosv = degenerate ? 0.f : bc[1] / (ne * nt);
     total -= cosv;
     if (d_tgt) {
       for (int j = threadIdx.x; j < E; j += blockDim.x) {
         const float e = e_tgt[(long long)n * E + j] - e_src[(long long)n * E + j];
-        const float dv = -coef * inv_count * (text[j] / nt - cosv * e / ne) / ne;
+        const float dv = degenerate ? 0.f : -coef * inv_count * (text[j] / nt - cosv * e / ne) / ne;
         d_tgt[(long long)n * E + j] = dv;
         dmax = fmaxf(dmax, fabsf(dv));
       }

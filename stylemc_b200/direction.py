@@ -48,6 +48,22 @@ class CLIPLoss:
         return part, d_tgt, gscale
 
 
+def shard_rows(n_total, rank, world):
+    """Rows [lo, hi) of a global batch that rank ``rank`` of ``world`` processes (contiguous, sizes differ by at most one)."""
+    base, extra = divmod(n_total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allreduce_step(grad, part, group):
+    """Sum the shard gradients [rows, 512] and the loss partial sums over the ranks in ONE collective (16 KiB + 4 B).  Because
+    every rank divides by the GLOBAL seed count (loss_and_grad's ``global_count``), the sum is exactly the full-batch mean
+    gradient of clip_loss.py:34, also for ragged shards."""
+    buf = torch.cat([grad.reshape(-1), part.reshape(-1)])
+    torch.distributed.all_reduce(buf, op=torch.distributed.ReduceOp.SUM, group=group)
+    return buf[:grad.numel()].reshape(grad.shape), buf[grad.numel():]
+
+
 def cosine_lr(base_lr, it, total):
     """find_direction.py:298-299 (``it`` is 1-based)."""
     return math.cos(math.pi * it / total) * base_lr * 0.5 + base_lr * 0.5
@@ -117,9 +133,7 @@ class DirectionFinder:
         count = styles.shape[0] * self.world if global_count is None else global_count
         grad, part = self.loss_and_grad(styles, count)
         if self.world > 1:
-            buf = torch.cat([grad.reshape(-1), part])
-            torch.distributed.all_reduce(buf, group=self.group)
-            grad, part = buf[:-1].reshape(grad.shape), buf[-1:]
+            grad, part = allreduce_step(grad, part, self.group)
         numel = self.delta.numel()
         l2 = self.l2_reg_coef * self.delta.square().mean()                            # find_direction.py:190-191 (batch independent)
         clip_loss = self.clip_loss_coef + part                                        # coef * (count - sum cos) / count

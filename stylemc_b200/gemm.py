@@ -79,7 +79,11 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
     e.acc_scale = acc_scale
     d.acc_chunk_k = acc_chunk_k
     with torch.cuda.device(A.device):
-        _lib.call('smc_igemm', ctypes.addressof(d), _lib.stream())
+        if _lib.igemm_hook is not None:
+            with _lib.igemm_hook(d, len(full) // (3 if precision == 'x3' else 1)):
+                _lib.call('smc_igemm', ctypes.addressof(d), _lib.stream())
+        else:
+            _lib.call('smc_igemm', ctypes.addressof(d), _lib.stream())
 
 
 def pow2_prescale(x, target=256.0):

@@ -1,0 +1,154 @@
+"""CPU: host-side logic of the product (no kernel launches): resampling tap tables, implicit-GEMM tap tables (checked by
+emulating the smc_igemm contract with plain torch), S-space bookkeeping, network parameter naming, schedules."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import direction as o_dir
+from oracle import synthesis as o_syn
+
+
+def emulate_igemm(A, B, n_img, H, W, n_out, taps):
+    """D[n,h,w,o] = sum_t sum_c A[n+dn_t, h+dy_t, w+dx_t, c] * B[tap_t*n_out + o, c], zero outside A (include/stylemc_b200.h)."""
+    NA, HA, WA, C = A.shape
+    out = torch.zeros(n_img, H, W, n_out, dtype=A.dtype)
+    for t in taps:
+        dn, dy, dx, ti = t if len(t) == 4 else (0,) + tuple(t)
+        shifted = torch.zeros(n_img, H, W, C, dtype=A.dtype)
+        for n in range(n_img):
+            if not 0 <= n + dn < NA:
+                continue
+            h0, h1 = max(0, -dy), min(H, HA - dy)
+            w0, w1 = max(0, -dx), min(W, WA - dx)
+            if h1 > h0 and w1 > w0:
+                shifted[n, h0:h1, w0:w1] = A[n + dn, h0 + dy:h1 + dy, w0 + dx:w1 + dx]
+        out += shifted @ B[ti * n_out:(ti + 1) * n_out].t()
+    return out
+
+
+def test_tap_tables_reproduce_the_convolutions():
+    from stylemc_b200 import gemm
+    g = torch.Generator().manual_seed(0)
+    n, c, o, h = 2, 5, 4, 6
+    x = torch.randn(n, c, h, h, generator=g, dtype=torch.float64)
+    w = torch.randn(o, c, 3, 3, generator=g, dtype=torch.float64)
+    A = x.permute(0, 2, 3, 1).contiguous()
+    Bf = w.permute(2, 3, 0, 1).reshape(9 * o, c)
+    Bb = w.permute(2, 3, 1, 0).reshape(9 * c, o)
+    # forward 3x3
+    y = emulate_igemm(A, Bf, n, h, h, o, gemm.TAPS_3X3)
+    assert torch.allclose(y, F.conv2d(x, w, padding=1).permute(0, 2, 3, 1), atol=1e-12)
+    # its dgrad
+    gy = torch.randn(n, o, h, h, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, w, padding=1).backward(gy)
+    gx = emulate_igemm(gy.permute(0, 2, 3, 1).contiguous(), Bb, n, h, h, c, gemm.TAPS_3X3_DGRAD)
+    assert torch.allclose(gx, xr.grad.permute(0, 2, 3, 1), atol=1e-12)
+    # transposed stride-2 conv as four parity GEMMs
+    ref = F.conv_transpose2d(x, w.transpose(0, 1), stride=2).permute(0, 2, 3, 1)            # [n, 2h+1, 2h+1, o]
+    t = torch.zeros(n, 2 * h + 2, 2 * h + 2, o, dtype=torch.float64)
+    for r in (0, 1):
+        for cc in (0, 1):
+            t[:, r::2, cc::2] = emulate_igemm(A, Bf, n, h + 1, h + 1, o, gemm.up2_parity_taps(r, cc))
+    assert torch.allclose(t[:, :2 * h + 1, :2 * h + 1], ref, atol=1e-12)
+    assert t[:, 2 * h + 1].abs().max() == 0 and t[:, :, 2 * h + 1].abs().max() == 0
+    # and its dgrad from gradient parity planes stacked on the image axis
+    gt = torch.randn(n, o, 2 * h + 1, 2 * h + 1, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    F.conv_transpose2d(xr, w.transpose(0, 1), stride=2).backward(gt)
+    gl = F.pad(gt, (0, 1, 0, 1)).permute(0, 2, 3, 1)
+    gp = torch.cat([gl[:, r::2, cc::2] for r in (0, 1) for cc in (0, 1)])                    # [4n, h+1, h+1, o]
+    gx = emulate_igemm(gp, Bb, n, h, h, c, gemm.up2_dgrad_taps(n))
+    assert torch.allclose(gx, xr.grad.permute(0, 2, 3, 1), atol=1e-12)
+
+
+def test_x3_tap_expansion_counts():
+    from stylemc_b200 import _lib, gemm
+    assert len(gemm.TAPS_3X3) * 3 <= _lib.MAX_TAPS
+    assert sorted(t[2] for r in (0, 1) for c in (0, 1) for t in gemm.up2_parity_taps(r, c)) == list(range(9))
+
+
+@pytest.mark.parametrize('res', [64, 100, 224, 256, 512, 1024])
+def test_antialias_tables_match_interpolate(res):
+    from stylemc_b200 import resample
+    x = torch.randn(1, 1, res, res, dtype=torch.float64, generator=torch.Generator().manual_seed(res))
+    ref = F.interpolate(x, size=(224, 224), mode='bicubic', antialias=True, align_corners=False)[0, 0]
+    M = torch.as_tensor(resample.dense_matrix(res, 224))
+    assert (M @ x[0, 0] @ M.t() - ref).abs().max().item() <= 2e-6
+    start, count, wgt, taps = resample.aa_tables(res, 224)
+    oidx, cnt, wt, taps_t = resample.transpose_tables(start, count, wgt, res)
+    Mt = torch.zeros(224, res, dtype=torch.float64)
+    for i in range(res):
+        for k in range(cnt[i]):
+            Mt[oidx[i, k], i] += float(wt[i, k])
+    assert torch.allclose(Mt, M.to(torch.float64), atol=1e-7)
+
+
+def test_unprocess_constants_match_reference():
+    from stylemc_b200 import resample
+    assert resample.CLIP_MEAN == o_dir.CLIP_MEAN and resample.CLIP_STD == o_dir.CLIP_STD
+
+
+def test_s_space_bookkeeping_matches_oracle():
+    """split_ws / get_styles / get_temp_shapes (utils.py:77-158) on the product's own network modules."""
+    from stylemc_b200 import networks, utils
+    G = networks.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    Go = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == {k: tuple(v.shape) for k, v in Go.state_dict().items()}
+    Go.load_state_dict(G.state_dict())
+    ws = torch.randn(3, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(2))
+    for a, b in zip(utils.split_ws(G, ws), o_syn.split_ws(Go, ws)):
+        assert torch.equal(a, b)
+    S, shapes = utils.get_styles(G, ws, utils.split_ws(G, ws), 'cpu')
+    So, shapes_o = o_syn.get_styles(Go, ws, o_syn.split_ws(Go, ws))
+    assert shapes == shapes_o and (S - So).abs().max().item() <= 1e-5
+    assert S.shape == (3, 26, 512) and S[:, 15:].abs().max().item() == 0           # rows beyond this net stay zero
+    assert utils.get_temp_shapes(networks.make_generator(64, seed=1, channel_base=2048, channel_max=512)) == shapes
+
+
+def test_parameter_names_follow_legacy_map():
+    """legacy.py:173-202 names: synthesis.b{res}.{conv0,conv1,torgb}.{weight,bias,affine.weight,affine.bias,noise_const,...}."""
+    from stylemc_b200 import networks
+    G = networks.make_generator(32, seed=0, channel_base=1024)
+    sd = G.state_dict()
+    for key in ('synthesis.b4.const', 'synthesis.b4.conv1.weight', 'synthesis.b4.conv1.affine.weight', 'synthesis.b4.conv1.noise_const',
+                'synthesis.b4.conv1.noise_strength', 'synthesis.b4.torgb.weight', 'synthesis.b8.conv0.weight', 'synthesis.b8.conv0.resample_filter',
+                'synthesis.b32.torgb.affine.bias', 'synthesis.b32.resample_filter'):
+        assert key in sd, key
+    assert tuple(sd['synthesis.b8.conv0.weight'].shape) == (128, 256, 3, 3) and tuple(sd['synthesis.b8.torgb.weight'].shape) == (3, 128, 1, 1)
+    assert G.synthesis.num_ws == 2 * int(math.log2(32)) - 2
+    assert all(not p.requires_grad for p in G.parameters())
+
+
+def test_schedules_and_sharding():
+    from stylemc_b200 import direction
+    for it in (1, 5, 10):
+        assert abs(direction.cosine_lr(1.5, it, 10) - o_dir.cosine_lr(1.5, it, 10)) < 1e-15
+    assert direction.S_TRAINABLE_SPACE_CHANNELS == o_dir.S_TRAINABLE_ROWS and direction.RESOLUTION_DICT == o_dir.RESOLUTION_TO_K
+    for n, world in ((129, 8), (64, 8), (5, 2), (3, 4)):
+        spans = [direction.shard_rows(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_fma_backward_unbroadcasts():
+    from stylemc_b200.ops import fma
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(2, 3, 4, 4, generator=g, requires_grad=True)
+    b = torch.randn(2, 3, 1, 1, generator=g, requires_grad=True)
+    c = torch.randn(4, 4, generator=g, requires_grad=True)
+    dy = torch.randn(2, 3, 4, 4, generator=g)
+    fma.fma(a, b, c).backward(dy)
+    a2, b2, c2 = (t.detach().clone().requires_grad_(True) for t in (a, b, c))
+    (a2 * b2 + c2).backward(dy)
+    for x, y in ((a, a2), (b, b2), (c, c2)):
+        assert torch.allclose(x.grad, y.grad, atol=1e-6)
+
+
+def test_setup_filter_matches_oracle():
+    from oracle import fir
+    from stylemc_b200.ops import upfirdn2d
+    for taps, kw in (([1, 3, 3, 1], {}), ([1, 2, 3, 4, 4, 3, 2, 1], {}), ([1, 2, 1], dict(gain=3, flip_filter=True)), (None, {})):
+        assert torch.equal(upfirdn2d.setup_filter(taps, **kw), fir.setup_filter(taps, **kw))

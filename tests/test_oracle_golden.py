@@ -1,0 +1,82 @@
+"""CPU: the oracle reproduces the golden vectors that oracle/pin_reference.py recorded from the reference's own code
+(torch_utils.ops impl='ref', utils.generate_image, find_direction.unprocess / compute_clip_loss, clip_loss.CLIPLoss)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import act, conv, direction, fir, synthesis, vit
+from cases import CONV_KW, FIR_KW
+
+
+def T(a):
+    return torch.as_tensor(np.asarray(a))
+
+
+@pytest.mark.parametrize('name', list(FIR_KW))
+def test_fir_golden(golden, name):
+    g = golden('ops')
+    f = T(g[name + '.f']) if name + '.f' in g else None
+    assert torch.equal(fir.upfirdn2d(T(g[name + '.x']), f, **FIR_KW[name]), T(g[name + '.y']))
+
+
+@pytest.mark.parametrize('name', list(act.ACTIVATIONS))
+def test_bias_act_golden(golden, name):
+    g = golden('ops')
+    x, b = T(g['bias_act.x']), T(g['bias_act.b'])
+    assert torch.equal(act.bias_act(x, b, act=name), T(g[f'bias_act.{name}.def']))
+    assert torch.equal(act.bias_act(x, b, act=name, gain=1.7, clamp=0.9, alpha=0.3), T(g[f'bias_act.{name}.clamp']))
+
+
+@pytest.mark.parametrize('name', list(CONV_KW) + ['conv_down2', 'conv_1x1_down2'])
+def test_conv2d_resample_golden(golden, name):
+    g = golden('ops')
+    kw = dict(CONV_KW.get(name, {}))
+    if name == 'conv_down2':
+        kw = dict(down=2, padding=1)
+    if name == 'conv_1x1_down2':
+        kw = dict(down=2)
+    f = fir.setup_filter([1, 3, 3, 1]) if (kw.get('up', 1) > 1 or kw.get('down', 1) > 1) else None
+    y = conv.conv2d_resample(T(g[name + '.x']), T(g[name + '.w']), f=f, **kw)
+    assert (y - T(g[name + '.y'])).abs().max().item() <= 1e-6      # oneDNN may pick another algorithm between runs
+
+
+def test_modulated_conv2d_vs_e4e_reference(golden):
+    g = golden('ops')
+    f4 = fir.setup_filter([1, 3, 3, 1])
+    for tag, kw in (('plain', {}), ('up2', dict(up=2, resample_filter=f4, flip_weight=False))):
+        y = conv.modulated_conv2d(T(g[f'e4e_{tag}.x']), T(g[f'e4e_{tag}.w']), T(g[f'e4e_{tag}.s']), padding=1, **kw)
+        assert (y - T(g[f'e4e_{tag}.y'])).abs().max().item() <= 5e-6
+
+
+def test_generate_image_golden(golden):
+    g = golden('synth64')
+    G = synthesis.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    ws = T(g['ws'])
+    S, shapes = synthesis.get_styles(G, ws, synthesis.split_ws(G, ws))
+    assert (S - T(g['styles'])).abs().max().item() <= 1e-6
+    assert [tuple(s) for s in g['temp_shapes']] == shapes
+    xs, img = synthesis.generate_image(G, 100, T(g['styles']), shapes)
+    assert (img - T(g['img'])).abs().max().item() <= 1e-5
+    for i, x in enumerate(xs):
+        assert (x - T(g[f'xs{i}'])).abs().max().item() <= 1e-4
+    assert (synthesis.generate_image(G, 2, T(g['styles']), shapes)[1] - T(g['img_k2'])).abs().max().item() <= 1e-5
+
+
+def test_clip_golden(golden):
+    g = golden('clip')
+    model = vit.CLIP(seed=0)
+    images = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        assert (model.encode_image(images) - T(g['image_features'])).abs().max().item() <= 1e-5
+        assert (model.encode_text(T(g['tokens'])) - T(g['text_features'])).abs().max().item() <= 1e-5
+
+
+def test_step_golden(golden):
+    g = golden('step64')
+    G = synthesis.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    shapes = synthesis.get_temp_shapes(G)
+    loss_fn = direction.CLIPLoss(vit.CLIP(seed=0), vit.synthetic_tokens('pos'), vit.synthetic_tokens('neg'))
+    o = direction.direction_step(G, shapes, loss_fn, T(g['styles']), T(g['delta']), 100)
+    assert abs(o['loss'].item() - float(g['loss'])) <= 1e-6
+    assert ((o['grad'] - T(g['grad'])).norm() / T(g['grad']).norm()).item() <= 1e-4
+    assert (direction.unprocess(T(g['original_img']))[:1] - T(g['unprocessed'])).abs().max().item() <= 1e-5

@@ -59,3 +59,26 @@ def test_step_config1_256px_golden(golden):
     assert err <= 1e-2
     assert (torch.nn.functional.avg_pool2d(img, 8).cpu() - torch.as_tensor(g['img_down'])).abs().max().item() <= 1e-2
     check_step(f, g, S, 'config1')
+
+
+def test_three_step_trajectory_vs_oracle():
+    """Three consecutive optimisation steps (cosine LR, SGD) on the 64-px network track the CPU oracle's trajectory."""
+    from oracle import direction as o_dir
+    from stylemc_b200 import direction
+    G = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    ws = torch.randn(4, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(21))
+    S, shapes = o_syn.get_styles(G, ws, o_syn.split_ws(G, ws))
+    loss_fn = o_dir.CLIPLoss(o_vit.CLIP(o_vit.random_clip_params(seed=0)), o_vit.synthetic_tokens('pos'), o_vit.synthetic_tokens('neg'))
+    f = finder(G, 64)
+    delta = 0.05 * torch.randn(1, 8, 512, generator=torch.Generator().manual_seed(22))   # delta == 0 makes the reference's loss 0/0
+    f.delta.copy_(delta.cuda())
+    for it in range(1, 4):
+        lr = o_dir.cosine_lr(1.5, it, 3)
+        assert abs(lr - direction.cosine_lr(1.5, it, 3)) < 1e-12
+        r = o_dir.direction_step(G, shapes, loss_fn, S, delta, 100)
+        delta = o_dir.sgd_update(delta, r['grad'], lr)
+        out = f.step(S.cuda(), lr=lr)
+        d_rel = ((f.delta.cpu() - delta).norm() / delta.norm().clamp_min(1e-12)).item()
+        print(f'it {it}: loss {out["loss"].item():.6f} / {r["loss"].item():.6f}  |delta| {delta.norm():.4f}  delta rel diff {d_rel:.2e}')
+        assert abs(out['loss'].item() - r['loss'].item()) <= 1e-3 * abs(r['loss'].item())
+        assert d_rel <= 2e-3
