@@ -116,6 +116,11 @@ typedef struct smc_igemm_desc {
 } smc_igemm_desc;
 
 int smc_igemm(const smc_igemm_desc* desc, void* stream);
+/* Tuning / diagnostics knobs of the convolution path (process-global; set before launching, not thread-safe):
+ *   key 0: halo-tile kernel (hconv.cu) use: 0 never, 1 auto (default), 2 whenever the shape is supported
+ *   key 2: weight-stage ring depth (0 = by stage size)   key 3: tile width Wt in pixels (0 = widest that fits, <= 64)
+ *   key 4: persistent grid size (0 = one CTA per SM)      key 5: bit mask of conv kinds routed to hconv.cu (diagnostics) */
+int smc_igemm_config(int key, int value);
 
 /* ---- synthesis glue (synth.cu) -------------------------------------------------------------------
  * Activations are NHWC fp16 ("hi" plane, optional "lo" plane = rn(v - hi)); styles are rows of the

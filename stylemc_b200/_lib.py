@@ -61,6 +61,7 @@ SIGNATURES = {
     'smc_bias_act': 'pppppp iqiq ii fff p',
     'smc_upfirdn2d': 'ppp i p p',
     'smc_igemm': 'pp',
+    'smc_igemm_config': 'ii',
     'smc_demod_coefs': 'pp q p iii p',
     'smc_pack_nhwc': 'p q p q pp iiii p',
     'smc_unpack_nchw': 'p i pp iiii p',
@@ -106,6 +107,9 @@ def lib():
         if handle.smc_abi_version() != 1:
             raise RuntimeError('libstylemc_b200.so ABI version mismatch; rebuild')
         _lib = handle
+        for key, env in ((0, 'STYLEMC_HCONV'), (2, 'STYLEMC_HCONV_NB'), (3, 'STYLEMC_HCONV_WT'), (4, 'STYLEMC_HCONV_GRID'), (5, 'STYLEMC_HCONV_MASK')):
+            if os.environ.get(env):          # diagnostics only: A/B the halo-tile conv kernel against the per-tap kernel
+                handle.smc_igemm_config(key, int(os.environ[env]))
     return _lib
 
 
@@ -132,7 +136,7 @@ def require_cuda(t, name):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
-_LAUNCHES = {'smc_abi_version': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2}
+_LAUNCHES = {'smc_abi_version': 0, 'smc_igemm_config': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2}
 launch_count = 0
 igemm_hook = None      # bench.py installs a callable(desc_addr) -> context manager to time every smc_igemm launch
 

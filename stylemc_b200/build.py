@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, 'csrc')
 INCLUDE = os.path.join(os.path.dirname(ROOT), 'include')
 LIB = os.path.join(ROOT, 'libstylemc_b200.so')
-SOURCES = ['misc.cu', 'bias_act.cu', 'upfirdn2d.cu', 'igemm.cu', 'synth.cu', 'vit.cu']
+SOURCES = ['misc.cu', 'bias_act.cu', 'upfirdn2d.cu', 'igemm.cu', 'hconv.cu', 'synth.cu', 'vit.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
               '-I' + INCLUDE, '-I' + CSRC]
 
@@ -23,7 +23,7 @@ def _newer(a, b):
 
 def build(force=False, verbose=False):
     nvcc = os.environ.get('NVCC', 'nvcc')
-    deps = [os.path.join(CSRC, 'common.cuh'), os.path.join(INCLUDE, 'stylemc_b200.h')]
+    deps = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'tc.cuh'), os.path.join(INCLUDE, 'stylemc_b200.h')]
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

@@ -1,0 +1,699 @@
+// Halo-tile implicit GEMM for the 3x3 (and polyphase) modulated convolutions, sm_100a: tcgen05 + TMEM + TMA.
+//
+// Same contract as igemm.cu (smc_igemm_desc: D[m, o] = sum_t sum_k A_t[m, k] * B_t[o, k]) and the same reference call sites
+// (torch_utils/ops/conv2d_gradfix.py:35-43 via conv2d_resample.py:125-147), but built around on-chip reuse of the
+// activation tile: igemm.cu re-loads the A tile once per filter tap and per hi/lo term (27 loads of the same pixels for a
+// split-precision 3x3 conv), which makes it L2->SM bound at ~25% of the tensor pipe.  Here
+//
+//   * one CTA owns 256 consecutive "positions" of a halo-padded row-major window of one image (pitch Wp = Wt + halo):
+//     the TMA box [RB rows][Wp cols][64 channels] (128-byte swizzled rows) is loaded ONCE per 64-channel slab and every
+//     tap is the same smem tile read through a UMMA descriptor whose start address is shifted by (dy * Wp + dx) rows
+//     (matrix-descriptor base_offset = (addr >> 7) & 7 keeps the swizzle phase right); positions that fall in the halo
+//     columns are computed and discarded (Wt / Wp efficiency);
+//   * the weights of one tap (BN x 64, hi or lo plane) are a small ring stage; a B_hi stage is used by the A_hi and the
+//     A_lo term before it is released, so the split costs 2 B loads per tap, not 3;
+//   * two 128-row accumulator blocks share every B stage (M = 256 per CTA), halving weight traffic per FLOP again;
+//   * persistent CTAs (grid = #SMs) walk the tile list; TMEM holds two accumulator sets so a chunk can be drained into
+//     fp32 registers by the 16 epilogue warps ("promoted accumulation", see igemm.cu) while the next chunk accumulates,
+//     and the stores of tile i overlap the MMAs of tile i+1.
+//
+// Warp roles (608 threads): warp 0 = A-tile TMA producer, warp 1 = weight-stage TMA producer, warp 2 = MMA issuer
+// (one elected thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16), warps 3..18 = epilogue
+// (TMEM lane quadrant = warp % 4; block = bit 0, column half = bit 1 of the per-quadrant index).
+#include "tc.cuh"
+
+namespace smc {
+
+constexpr int HC_MB = 2;            // accumulator blocks of 128 positions per CTA
+constexpr int HC_MT = 128 * HC_MB;  // positions per tile
+constexpr int HC_MAX_GROUPS = 4;
+constexpr int HC_MAX_TAPS = 16;
+constexpr int HC_THREADS = 32 * (3 + 16);
+
+struct HcTap {
+  int32_t posoff;            // (dy + padT) * Wp + dx + padL
+  int32_t brow_hi, brow_lo;  // first weight row of this tap in the hi / lo plane
+};
+struct HcGroup {             // one A source (image-axis offset of its hi and lo plane) and the taps that read it
+  int32_t dn_hi, dn_lo;
+  int32_t tap_begin, tap_end;
+};
+// A slab (KC channels) is processed as a list of segments = runs of taps of one group.  x3: a segment is a B_hi pass
+// (A_hi*B_hi -> main, A_lo*B_hi -> cross) followed by a B_lo pass (A_hi*B_lo -> cross); the main accumulator may be committed
+// for draining after a segment's B_hi pass, so that a main accumulation chain is at most `max_chain` MMAs long and is drained
+// while the segment's B_lo pass runs.
+constexpr int HC_MAX_SEGS = 16;
+enum : int32_t { HC_SEG_FIRST = 1, HC_SEG_LAST = 2, HC_SEG_COMMIT = 4, HC_SEG_SLABEND = 8 };
+struct HcSeg {
+  int32_t g, tb, te, flags;   // group, tap range, FIRST / LAST segment of its group, COMMIT main after it, last segment of the slab
+};
+struct HcParams {
+  int n_img, H, W, C, n_out;
+  int Wt, Wp, RB, padL, padT;
+  int col_tiles, tiles_per_col, n_tiles_n;
+  long long total_tiles;
+  int ngroups, kchunks, kcs_per_drain, nb;
+  int nsegs, ndrains;  // segments per slab; main-accumulator drains per tile
+  int lo_double;     // x3: the lo tile has two buffers (small tiles: the next lo tile must land before the B_lo pass ends)
+  int b_resident;    // every weight stage of a tile has its own smem slot and is loaded once per CTA (n_tiles_n == 1)
+  int na;            // number of A buffers
+  uint32_t a_box_bytes, a_buf_bytes;
+  HcGroup groups[HC_MAX_GROUPS];
+  HcSeg segs[HC_MAX_SEGS];
+  HcTap taps[HC_MAX_TAPS];
+  smc_igemm_epilogue epi;
+};
+
+// K-major operand tile with rows of KC * 2 bytes (128: SWIZZLE_128B, 64: SWIZZLE_64B), 8-row groups contiguous.  The start
+// address may sit on ANY row of the tile: measured on B200, the swizzle XOR is taken from the absolute shared-memory address
+// bits (what TMA wrote), so a shifted start needs no matrix-descriptor base_offset (setting it per the PTX formula gives
+// wrong results; tools/hconv_probe.py, profiles/r01b_hconv.md).  The upper descriptor word is a constant; the lower word is
+// the start address in 16-byte units, so stepping along K or to the second 128-row block is one 32-bit add.
+template <int KC>
+struct HcDesc {
+  static constexpr uint32_t HI = (uint32_t)((KC * 2 * 8) >> 4)      // stride byte offset (8 rows), bits [32,46)
+                                 | (1u << 14)                        // descriptor version (Blackwell), bit 46
+                                 | ((KC == 64 ? 2u : 4u) << 29);     // SWIZZLE_128B / SWIZZLE_64B, bits [61,64)
+  static __device__ __forceinline__ uint64_t make(uint32_t lo16) { return ((uint64_t)HI << 32) | (uint64_t)lo16; }
+};
+// D[tmem] += A * B (accumulate always)
+__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc) : "memory");
+}
+// exactly one lane of a converged warp: lets ptxas keep the MMA operands in uniform registers (no per-lane R2UR loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}" : "+r"(pred));
+  return pred != 0;
+}
+// one tap of one pass for both 128-row blocks: 2 * KC/16 MMAs; `first` = 0 makes the first MMA of each block overwrite
+template <int BN, int KC>
+__device__ __forceinline__ void hc_issue_tap(uint32_t tm, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate_first) {
+  constexpr uint32_t MBOFF = (uint32_t)(128 * KC * 2) >> 4;
+#pragma unroll
+  for (int mb = 0; mb < HC_MB; ++mb) {
+    umma_f16(tm + (uint32_t)(mb * BN), HcDesc<KC>::make(alo + mb * MBOFF), HcDesc<KC>::make(blo), idesc, accumulate_first);
+#pragma unroll
+    for (int k = 1; k < KC / 16; ++k)
+      umma_f16_acc(tm + (uint32_t)(mb * BN), HcDesc<KC>::make(alo + mb * MBOFF + 2 * k), HcDesc<KC>::make(blo + 2 * k), idesc);
+  }
+}
+
+struct HcTile {
+  int nt, n, w0, q0, hfirst;
+};
+__device__ __forceinline__ HcTile hc_tile(const HcParams& p, long long t) {
+  HcTile r;
+  r.nt = (int)(t % p.n_tiles_n);
+  t /= p.n_tiles_n;
+  const int ti = (int)(t % p.tiles_per_col);
+  t /= p.tiles_per_col;
+  const int ct = (int)(t % p.col_tiles);
+  r.n = (int)(t / p.col_tiles);
+  r.w0 = ct * p.Wt;
+  r.q0 = ti * HC_MT;
+  r.hfirst = r.q0 / p.Wp;
+  return r;
+}
+
+// Accumulators in TMEM (columns), per set: x1: {block 0, block 1}, the two sets alternate per accumulation chunk.
+// x3: {main 0, main 1, cross 0, cross 1}: "main" receives only the hi*hi products and is drained every chunk (short chains:
+// the tensor core adds with truncation, igemm.cu); "cross" receives hi*lo and lo*hi, which are 2^-11 of the result, so its
+// chain may run over the whole tile.  main is drained while the B_lo pass (cross only) runs.  With BN <= 64 two sets fit and
+// alternate per tile; with BN = 128 there is one set and cross is drained while the next tile's first main MMAs wait.
+template <int BN, int KC, bool X3>
+__global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB,
+                                                              const __grid_constant__ HcParams p) {
+  constexpr int ROWB = KC * 2;                                 // bytes per position row
+  constexpr int B_BYTES = BN * ROWB;
+  constexpr int CW = BN / 2;                                   // accumulator columns per epilogue thread
+  constexpr int SETCOLS = (X3 ? 2 : 1) * HC_MB * BN;
+  constexpr int SETS = (2 * SETCOLS <= 512) ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = (SETS * SETCOLS) < 32 ? 32 : (SETS * SETCOLS);
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int MAXB = 32;
+  static_assert(X3 || SETS == 2, "x1 alternates two sets per chunk");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* a_buf = smem;                                        // na buffers of a_buf_bytes
+  uint8_t* b_buf = smem + (size_t)p.na * p.a_buf_bytes;         // nb stages of B_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + (size_t)p.nb * B_BYTES);
+  uint64_t* a_full = bars;            // [4]
+  uint64_t* a_empty = bars + 4;       // [4]
+  uint64_t* b_full = bars + 8;        // [MAXB]
+  uint64_t* b_empty = b_full + MAXB;  // [MAXB]
+  uint64_t* main_full = b_empty + MAXB;    // [2] per set
+  uint64_t* main_drained = main_full + 2;  // [2]
+  uint64_t* cross_full = main_drained + 2; // [2]
+  uint64_t* cross_drained = cross_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cross_drained + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < MAXB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&main_full[i], 1);
+      mbar_init(&main_drained[i], 16);
+      mbar_init(&cross_full[i], 1);
+      mbar_init(&cross_drained[i], 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // A buffer of (step, plane): x3: hi alternates between buffers 0 and 1 (it is read by both passes); lo sits in buffer 2
+  // (released after the B_hi pass, so the next lo tile lands while the B_lo pass runs) or alternates 2/3.  x1: ring of 3.
+  auto hi_buf = [&](uint32_t step) -> int { return X3 ? (int)(step & 1u) : (int)(step % 3u); };
+  auto lo_buf = [&](uint32_t step) -> int { return 2 + (p.lo_double ? (int)(step & 1u) : 0); };
+
+  if (warp == 0) {
+    // ---------------- A producer: one halo tile per (slab, group, plane) ----------------
+    if (lane == 0) {
+      uint32_t eph = 0;                 // bit b: number of loads into buffer b so far, mod 2
+      uint32_t step = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const HcTile tl = hc_tile(p, t);
+        const int wbox = tl.w0 - p.padL, hbox = tl.hfirst - p.padT;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int g = 0; g < p.ngroups; ++g, ++step) {
+            const int hb = hi_buf(step);
+            mbar_wait(&a_empty[hb], ((eph >> hb) & 1u) ^ 1u);
+            eph ^= 1u << hb;
+            mbar_expect_tx(&a_full[hb], p.a_box_bytes);
+            tma_load_4d(a_buf + (size_t)hb * p.a_buf_bytes, &mapA, &a_full[hb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_hi);
+            if (X3) {
+              const int lb = lo_buf(step);
+              mbar_wait(&a_empty[lb], ((eph >> lb) & 1u) ^ 1u);
+              eph ^= 1u << lb;
+              mbar_expect_tx(&a_full[lb], p.a_box_bytes);
+              tma_load_4d(a_buf + (size_t)lb * p.a_buf_bytes, &mapA, &a_full[lb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_lo);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- B producer: one weight stage per (slab, group, pass, tap) ----------------
+    if (lane == 0) {
+      uint32_t bs = 0, bph = 0;
+      const uint32_t nb = (uint32_t)p.nb;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int nt = (int)(t % p.n_tiles_n);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int si = 0; si < p.nsegs; ++si) {
+            const int tb = p.segs[si].tb, te = p.segs[si].te;
+            for (int pass = 0; pass < (X3 ? 2 : 1); ++pass) {
+              for (int tp = tb; tp < te; ++tp) {
+                mbar_wait(&b_empty[bs], bph ^ 1u);
+                mbar_expect_tx(&b_full[bs], B_BYTES);
+                tma_load_2d(b_buf + (size_t)bs * B_BYTES, &mapB, &b_full[bs], kc * KC,
+                            (pass == 0 ? p.taps[tp].brow_hi : p.taps[tp].brow_lo) + nt * BN);
+                if (++bs == nb) { bs = 0; bph ^= 1u; }
+              }
+            }
+          }
+        }
+        if (p.b_resident) break;      // all stages of a tile are resident: loaded once
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer: the whole warp walks the (uniform) loops and waits; one elected lane issues ----------------
+    {
+      uint32_t aph = 0;                 // bit b: number of tiles consumed from A buffer b so far, mod 2
+      uint32_t step = 0, bs = 0, bph = 0, chunk_ctr = 0, tile_ctr = 0;
+      uint32_t nm0 = 0, nm1 = 0, nc0 = 0, nc1 = 0;     // chunks committed so far per set (main / cross)
+      const uint32_t nb = (uint32_t)p.nb;
+      const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
+      const bool resident = p.b_resident != 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
+        const HcTile tl = hc_tile(p, t);
+        const int rel0 = tl.q0 - tl.hfirst * p.Wp;         // position of tile row 0 inside the box (before the tap offset)
+        const uint32_t set_t = (X3 && SETS == 2) ? (tile_ctr & 1u) : 0u;
+        int in_chunk = 0;
+        bool fresh = true;                                 // next main MMA starts an accumulation chunk (overwrites)
+        bool fresh_cross = true;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const bool chunk_ends = (in_chunk + 1 == p.kcs_per_drain) || (kc == p.kchunks - 1);
+          uint32_t a_hi = 0, a_lo = 0;
+          int hb = 0, lb = 0;
+          for (int si = 0; si < p.nsegs; ++si) {
+            const int tb = p.segs[si].tb, te = p.segs[si].te, sflags = p.segs[si].flags;
+            if (sflags & HC_SEG_FIRST) {
+              hb = hi_buf(step);
+              lb = lo_buf(step);
+              mbar_wait(&a_full[hb], (aph >> hb) & 1u);
+              aph ^= 1u << hb;
+              if (X3) {
+                mbar_wait(&a_full[lb], (aph >> lb) & 1u);
+                aph ^= 1u << lb;
+              }
+              a_hi = a_base + (uint32_t)hb * p.a_buf_bytes + (uint32_t)rel0 * (uint32_t)ROWB;
+              a_lo = a_base + (uint32_t)lb * p.a_buf_bytes + (uint32_t)rel0 * (uint32_t)ROWB;
+            }
+            for (int pass = 0; pass < (X3 ? 2 : 1); ++pass) {
+              for (int tp = tb; tp < te; ++tp) {
+                const uint32_t set = X3 ? set_t : (chunk_ctr & 1u);
+                if (pass == 0 && fresh) {                  // this set's main accumulator must have been drained
+                  const uint32_t nm = set ? nm1 : nm0;
+                  if (nm >= 1) mbar_wait(&main_drained[set], (nm - 1u) & 1u);
+                }
+                if (X3 && fresh_cross) {
+                  const uint32_t nc = set_t ? nc1 : nc0;
+                  if (nc >= 1) mbar_wait(&cross_drained[set_t], (nc - 1u) & 1u);
+                }
+                mbar_wait(&b_full[bs], resident ? 0u : bph);
+                tcgen05_fence_after();
+                const uint32_t blo = (b_base + bs * (uint32_t)B_BYTES) >> 4;
+                const uint32_t roff = (uint32_t)p.taps[tp].posoff * (uint32_t)ROWB;
+                if (elect_one()) {
+                  if (pass == 0) hc_issue_tap<BN, KC>(tmem_base + set * (uint32_t)SETCOLS, (a_hi + roff) >> 4, blo, IDESC, fresh ? 0u : 1u);
+                  if (X3)                                  // pass 0: A_lo * B_hi, pass 1: A_hi * B_lo -> cross
+                    hc_issue_tap<BN, KC>(tmem_base + set_t * (uint32_t)SETCOLS + (uint32_t)(HC_MB * BN),
+                                         ((pass == 0 ? a_lo : a_hi) + roff) >> 4, blo, IDESC, fresh_cross ? 0u : 1u);
+                  if (!resident) tcgen05_commit(&b_empty[bs]);
+                }
+                __syncwarp();
+                if (pass == 0) fresh = false;
+                fresh_cross = false;
+                if (++bs == nb) { bs = 0; bph ^= 1u; }
+              }
+              if (X3 && pass == 0) {
+                // main chain complete (mid-slab commit, or the slab-end commit of a chunk): drained while the B_lo pass runs
+                const bool main_done = (sflags & HC_SEG_COMMIT) && (!(sflags & HC_SEG_SLABEND) || chunk_ends);
+                if (elect_one()) {
+                  if (sflags & HC_SEG_LAST) tcgen05_commit(&a_empty[lb]);   // the lo tile is only read by B_hi passes
+                  if (main_done) tcgen05_commit(&main_full[set_t]);
+                }
+                __syncwarp();
+                if (main_done) {
+                  if (set_t) ++nm1; else ++nm0;
+                  fresh = true;
+                }
+              }
+            }
+            if (sflags & HC_SEG_LAST) {
+              if (elect_one()) tcgen05_commit(&a_empty[hb]);
+              __syncwarp();
+              ++step;
+            }
+          }
+          if (chunk_ends) {
+            in_chunk = 0;
+            if (!X3) {
+              const uint32_t set = chunk_ctr & 1u;
+              if (elect_one()) tcgen05_commit(&main_full[set]);
+              __syncwarp();
+              if (set) ++nm1; else ++nm0;
+              ++chunk_ctr;
+              fresh = true;
+            }
+          } else {
+            ++in_chunk;
+          }
+        }
+        if (X3) {
+          if (elect_one()) tcgen05_commit(&cross_full[set_t]);
+          __syncwarp();
+          if (set_t) ++nc1; else ++nc0;
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: thread <-> TMEM lane <-> position ----------------
+    const int ew = warp - 3;
+    const int q = warp & 3;                 // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    const int j = ew >> 2;                  // 0..3 within the quadrant
+    const int mb = j & 1, ch = j >> 1;
+    const int m = mb * 128 + q * 32 + lane;
+    const smc_igemm_epilogue& e = p.epi;
+    const float acc_scale = e.acc_scale != 0.f ? e.acc_scale : 1.f;
+    const int ndrains = p.ndrains;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BN + ch * CW);
+    uint32_t em0 = 0, em1 = 0, ec0 = 0, ec1 = 0, chunk_ctr = 0, tile_ctr = 0;
+    float acc[CW];
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
+      const HcTile tl = hc_tile(p, t);
+      const uint32_t set_t = (X3 && SETS == 2) ? (tile_ctr & 1u) : 0u;
+#pragma unroll
+      for (int i = 0; i < CW; ++i) acc[i] = 0.f;
+      for (int dch = 0; dch < ndrains + (X3 ? 1 : 0); ++dch) {
+        const bool cross = X3 && dch == ndrains;
+        const uint32_t set = X3 ? set_t : (chunk_ctr & 1u);
+        uint64_t* full = cross ? &cross_full[set] : &main_full[set];
+        uint64_t* drained = cross ? &cross_drained[set] : &main_drained[set];
+        uint32_t cnt;
+        if (cross) { cnt = set ? ec1 : ec0; if (set) ++ec1; else ++ec0; }
+        else { cnt = set ? em1 : em0; if (set) ++em1; else ++em0; }
+        if (!X3) ++chunk_ctr;
+        const uint32_t col = set * (uint32_t)SETCOLS + (cross ? (uint32_t)(HC_MB * BN) : 0u);
+        mbar_wait(full, cnt & 1u);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + col + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(drained);
+      }
+      // ---- fused epilogue + stores for this thread's position
+      const int qpos = tl.q0 + m;
+      const int h = qpos / p.Wp, wr = qpos - h * p.Wp;
+      const int w = tl.w0 + wr;
+      const bool valid = (wr < p.Wt) && (w < p.W) && (h < p.H);
+      if (valid) {
+        const int n = tl.n;
+        const int o0 = tl.nt * BN + ch * CW;
+        const long long opix = e.o_off + (long long)n * e.o_sn + (long long)h * e.o_sh + (long long)w * e.o_sw + o0;
+        float nz = 0.f;
+        if (e.noise != nullptr) nz = __ldg(e.noise + (long long)h * e.noise_sh + (long long)w * e.noise_sw);
+        const float* rs = e.row_scale ? e.row_scale + (long long)n * p.n_out + o0 : nullptr;
+        const float* ps = e.post_scale ? e.post_scale + (long long)n * p.n_out + o0 : nullptr;
+        const float* bs = e.bias ? e.bias + o0 : nullptr;
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float x = acc[c0 + i] * acc_scale;
+            if (rs) x *= __ldg(rs + c0 + i);
+            x += nz;
+            if (bs) x += __ldg(bs + c0 + i);
+            if (e.act == 1) x = x > 0.f ? x : x * e.alpha;
+            x *= e.gain;
+            if (e.clamp >= 0.f) x = fminf(fmaxf(x, -e.clamp), e.clamp);
+            v[i] = x;
+          }
+          if (e.out_raw) {
+            const __half2 a0 = __floats2half2_rn(v[0], v[1]), a1 = __floats2half2_rn(v[2], v[3]);
+            const __half2 a2 = __floats2half2_rn(v[4], v[5]), a3 = __floats2half2_rn(v[6], v[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw) + opix + c0) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1),
+                           *reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&a3));
+          }
+          if (ps) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= __ldg(ps + c0 + i);
+          }
+          if (e.residual) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(e.residual + opix + c0));
+            const float4 r1 = __ldg(reinterpret_cast<const float4*>(e.residual + opix + c0 + 4));
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+          }
+          if (e.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(e.out_f32 + opix + c0);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          if (e.out_hi) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const __half2 hh = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+              const float2 hf = __half22float2(hh);
+              const __half2 ll = __floats2half2_rn(v[2 * u] - hf.x, v[2 * u + 1] - hf.y);
+              hi[u] = *reinterpret_cast<const uint32_t*>(&hh);
+              lo[u] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_hi) + opix + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (e.out_lo)
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_lo) + opix + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static int g_hconv_mode = 1;          // 0: never use this kernel, 1: auto, 2: use it whenever the shape is supported
+static int g_hconv_nb = 0;   // 0: by stage size
+static int g_hconv_wt = 0;   // 0: widest that fits (<= 64)
+static int g_hconv_grid = 0;
+static int g_hconv_mask = 7;   // bit 0: single-source convs with > 4 taps, bit 1: <= 4 taps, bit 2: multi-source (up2 dgrad)
+
+void hconv_config(int key, int value) {
+  if (key == 0) g_hconv_mode = value;
+  if (key == 2) g_hconv_nb = value;
+  if (key == 3) g_hconv_wt = value;
+  if (key == 4) g_hconv_grid = value;
+  if (key == 5) g_hconv_mask = value;
+}
+
+template <int BN, int KC, bool X3>
+static int hc_launch(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(hconv_kernel<BN, KC, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  hconv_kernel<BN, KC, X3><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+template <int BN, int KC>
+static int hc_launch_x(bool x3, const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
+  return x3 ? hc_launch<BN, KC, true>(ma, mb, p, grid, smem, st) : hc_launch<BN, KC, false>(ma, mb, p, grid, smem, st);
+}
+
+// Returns SMC_OK when launched, SMC_EUNSUPPORTED when the shape is left to igemm.cu.
+int hconv_try_launch(const smc_igemm_desc* d, cudaStream_t st) {
+  if (g_hconv_mode == 0) return SMC_EUNSUPPORTED;
+  if (d->C % 32 != 0 || d->n_out % 32 != 0 || d->lda % 8 != 0 || d->ldb % 8 != 0) return SMC_EUNSUPPORTED;
+  const int KC = d->C % 64 == 0 ? 64 : 32;
+  if (d->tw > 0) return SMC_EUNSUPPORTED;          // caller pinned the igemm.cu tile shape
+  if (g_hconv_mode == 1 && ((long long)d->H * d->W < 1024 || d->H < 8)) return SMC_EUNSUPPORTED;
+  const int BN = d->n_out % 128 == 0 ? 128 : (d->n_out % 64 == 0 ? 64 : 32);
+
+  // split-precision pattern of gemm.igemm: [T base taps] [same, B rows + b_lo] [same, A planes + a_lo]
+  int T = d->ntaps;
+  bool x3 = false;
+  int a_lo = 0, b_lo = 0;
+  if (d->ntaps % 3 == 0 && d->ntaps >= 3) {
+    const int t3 = d->ntaps / 3;
+    a_lo = d->taps[2 * t3].dn - d->taps[0].dn;
+    b_lo = d->taps[t3].brow - d->taps[0].brow;
+    bool ok = a_lo > 0 && b_lo > 0;
+    for (int i = 0; i < t3 && ok; ++i) {
+      const smc_igemm_tap &a = d->taps[i], &b = d->taps[t3 + i], &c = d->taps[2 * t3 + i];
+      ok = b.dn == a.dn && b.dy == a.dy && b.dx == a.dx && b.brow == a.brow + b_lo && c.dn == a.dn + a_lo && c.dy == a.dy &&
+           c.dx == a.dx && c.brow == a.brow;
+    }
+    if (ok) {
+      x3 = true;
+      T = t3;
+    }
+  }
+  if (T > HC_MAX_TAPS) return SMC_EUNSUPPORTED;
+
+  HcParams p;
+  p.n_img = d->n_img; p.H = d->H; p.W = d->W; p.C = d->C; p.n_out = d->n_out;
+  int min_dx = 0, max_dx = 0, min_dy = 0, max_dy = 0;
+  for (int i = 0; i < T; ++i) {
+    min_dx = d->taps[i].dx < min_dx ? d->taps[i].dx : min_dx;
+    max_dx = d->taps[i].dx > max_dx ? d->taps[i].dx : max_dx;
+    min_dy = d->taps[i].dy < min_dy ? d->taps[i].dy : min_dy;
+    max_dy = d->taps[i].dy > max_dy ? d->taps[i].dy : max_dy;
+    if (d->taps[i].brow < 0 || d->taps[i].brow + (x3 ? b_lo : 0) + d->n_out > d->rowsB) return SMC_EINVAL;
+  }
+  if (max_dx - min_dx > 4 || max_dy - min_dy > 4) return SMC_EUNSUPPORTED;
+  p.padL = -min_dx; p.padT = -min_dy;
+  const int padW = max_dx - min_dx, padH = max_dy - min_dy;
+  // smem plan: weight stages (resident when a tile's whole weight set is small and there is one N tile), then the widest
+  // tile whose A buffers fit (wider = fewer discarded halo positions, but more halo rows fetched per tile)
+  const int passes = x3 ? 2 : 1;
+  const int b_bytes = BN * KC * 2;
+  const int stages_per_tile = (d->C / KC) * T * passes;
+  p.b_resident = (d->n_out == BN && stages_per_tile <= 32 && stages_per_tile * b_bytes <= 96 * 1024) ? 1 : 0;
+  if (p.b_resident) {
+    p.nb = stages_per_tile;
+  } else {
+    p.nb = g_hconv_nb > 0 ? g_hconv_nb : (b_bytes >= 16384 ? 4 : (b_bytes >= 8192 ? 6 : 8));
+    p.nb = p.nb < 2 ? 2 : (p.nb > 32 ? 32 : p.nb);
+  }
+  const size_t smem_fixed = 1024 + (size_t)p.nb * b_bytes + 1024;
+  const int wt_cands[4] = {g_hconv_wt > 0 ? g_hconv_wt : 64, 32, 16, 8};
+  p.Wt = 0;
+  for (int ci = 0; ci < 4 && p.Wt == 0; ++ci) {
+    for (int lod = (x3 && d->C / KC <= 2) ? 1 : 0; lod >= 0 && p.Wt == 0; --lod) {
+      const int wt = d->W < wt_cands[ci] ? d->W : wt_cands[ci];
+      const int wp = wt + padW;
+      const int rb = (HC_MT % wp == 0) ? HC_MT / wp + padH : ceil_div(HC_MT, wp) + 1 + padH;
+      const size_t abuf = ((size_t)(rb * wp + 8) * (size_t)(KC * 2) + 1023u) & ~(size_t)1023u;
+      const int na = x3 ? 3 + lod : 3;
+      if (wp <= 256 && rb <= 256 && smem_fixed + na * abuf <= 227 * 1024) {
+        p.Wt = wt; p.Wp = wp; p.RB = rb; p.lo_double = lod; p.na = na;
+      }
+    }
+  }
+  if (p.Wt == 0) return SMC_EUNSUPPORTED;
+  p.col_tiles = ceil_div(d->W, p.Wt);
+  p.tiles_per_col = (int)ceil_div_ll((long long)d->H * p.Wp, HC_MT);
+  p.n_tiles_n = d->n_out / BN;
+  p.total_tiles = (long long)d->n_img * p.col_tiles * p.tiles_per_col * p.n_tiles_n;
+  p.kchunks = d->C / KC;
+
+  // group the base taps by A source
+  p.ngroups = 0;
+  int ntap = 0;
+  bool used[SMC_IGEMM_MAX_TAPS] = {false};
+  for (int i = 0; i < T; ++i) {
+    if (used[i]) continue;
+    if (p.ngroups == HC_MAX_GROUPS) return SMC_EUNSUPPORTED;
+    HcGroup& g = p.groups[p.ngroups++];
+    g.dn_hi = d->taps[i].dn;
+    g.dn_lo = d->taps[i].dn + a_lo;
+    g.tap_begin = ntap;
+    for (int k = i; k < T; ++k) {
+      if (used[k] || d->taps[k].dn != d->taps[i].dn) continue;
+      used[k] = true;
+      HcTap& tp = p.taps[ntap++];
+      tp.posoff = (d->taps[k].dy + p.padT) * p.Wp + d->taps[k].dx + p.padL;
+      tp.brow_hi = d->taps[k].brow;
+      tp.brow_lo = d->taps[k].brow + b_lo;
+    }
+    g.tap_end = ntap;
+  }
+  {
+    const int kind = p.ngroups > 1 ? 4 : (T > 4 ? 1 : 2);
+    if (!(g_hconv_mask & kind)) return SMC_EUNSUPPORTED;
+    if ((g_hconv_mask & 8) && d->epi.act == 1) return SMC_EUNSUPPORTED;     // diagnostics: keep activated (forward) convs on igemm.cu
+    if ((g_hconv_mask & 16) && d->epi.act != 1) return SMC_EUNSUPPORTED;    // diagnostics: keep linear (dgrad, parity) convs on igemm.cu
+    if ((g_hconv_mask & 32) && d->C % 64 != 0) return SMC_EUNSUPPORTED;
+    if ((g_hconv_mask & 64) && d->C % 64 == 0) return SMC_EUNSUPPORTED;
+  }
+  // accumulation chains: at most max_chain MMAs (K = 16 each) go into the main accumulator between two drains
+  const int mma_per_tap = KC / 16;
+  const int max_chain = d->acc_chunk_k > 0 ? (d->acc_chunk_k / 16 < mma_per_tap ? mma_per_tap : d->acc_chunk_k / 16) : (1 << 30);
+  const int chain_per_slab = T * mma_per_tap;
+  p.nsegs = 0;
+  int mid_commits = 0;
+  if (x3 && chain_per_slab > max_chain) {
+    // split inside the slab: segments of at most max_chain / mma_per_tap taps, greedy commits
+    const int seg_taps = max_chain / mma_per_tap < 1 ? 1 : max_chain / mma_per_tap;
+    int chain = 0;
+    for (int g = 0; g < p.ngroups; ++g) {
+      const int nt_g = p.groups[g].tap_end - p.groups[g].tap_begin;
+      const int nseg = ceil_div(nt_g, seg_taps);
+      const int len = ceil_div(nt_g, nseg);
+      for (int q = 0; q < nseg; ++q) {
+        if (p.nsegs == HC_MAX_SEGS) return SMC_EUNSUPPORTED;
+        HcSeg& sg = p.segs[p.nsegs++];
+        sg.g = g;
+        sg.tb = p.groups[g].tap_begin + q * len;
+        sg.te = sg.tb + len < p.groups[g].tap_end ? sg.tb + len : p.groups[g].tap_end;
+        sg.flags = (q == 0 ? HC_SEG_FIRST : 0) | (q == nseg - 1 ? HC_SEG_LAST : 0);
+        const int add = (sg.te - sg.tb) * mma_per_tap;
+        if (chain > 0 && chain + add > max_chain) {          // commit after the previous segment
+          p.segs[p.nsegs - 2].flags |= HC_SEG_COMMIT;
+          ++mid_commits;
+          chain = 0;
+        }
+        chain += add;
+      }
+    }
+    p.kcs_per_drain = 1;
+  } else {
+    for (int g = 0; g < p.ngroups; ++g) {
+      HcSeg& sg = p.segs[p.nsegs++];
+      sg.g = g; sg.tb = p.groups[g].tap_begin; sg.te = p.groups[g].tap_end; sg.flags = HC_SEG_FIRST | HC_SEG_LAST;
+    }
+    p.kcs_per_drain = d->acc_chunk_k > 0 ? (max_chain / chain_per_slab < 1 ? 1 : max_chain / chain_per_slab) : p.kchunks;
+  }
+  p.segs[p.nsegs - 1].flags |= HC_SEG_COMMIT | HC_SEG_SLABEND;
+  p.ndrains = p.kchunks * mid_commits + ceil_div(p.kchunks, p.kcs_per_drain);
+  p.a_box_bytes = (uint32_t)(p.RB * p.Wp) * (uint32_t)(KC * 2);
+  p.a_buf_bytes = ((uint32_t)(p.RB * p.Wp + 8) * (uint32_t)(KC * 2) + 1023u) & ~1023u;
+  p.epi = d->epi;
+  if (!p.epi.out_f32 && !p.epi.out_hi && !p.epi.out_raw) return SMC_EINVAL;
+  if ((p.epi.o_sn | p.epi.o_sh | p.epi.o_sw | p.epi.o_off) & 7) return SMC_EUNSUPPORTED;
+  const size_t smem = smem_fixed + (size_t)p.na * p.a_buf_bytes;
+  if (smem > 227 * 1024) return SMC_EUNSUPPORTED;
+
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return SMC_EDRIVER;
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->WA, (cuuint64_t)d->HA, (cuuint64_t)d->NA};
+    cuuint64_t strides[3] = {(cuuint64_t)d->lda * 2, (cuuint64_t)d->lda * 2 * d->WA, (cuuint64_t)d->lda * 2 * d->WA * d->HA};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)p.Wp, (cuuint32_t)p.RB, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->A), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return SMC_EDRIVER;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->C, (cuuint64_t)d->rowsB};
+    cuuint64_t strides[1] = {(cuuint64_t)d->ldb * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->B), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return SMC_EDRIVER;
+  }
+  const int max_grid = g_hconv_grid > 0 ? g_hconv_grid : kNumSMs;
+  const int grid = p.total_tiles < max_grid ? (int)p.total_tiles : max_grid;
+  if (KC == 64) {
+    if (BN == 128) return hc_launch_x<128, 64>(x3, ma, mb, p, grid, smem, st);
+    if (BN == 64) return hc_launch_x<64, 64>(x3, ma, mb, p, grid, smem, st);
+    return hc_launch_x<32, 64>(x3, ma, mb, p, grid, smem, st);
+  }
+  if (BN == 128) return hc_launch_x<128, 32>(x3, ma, mb, p, grid, smem, st);
+  if (BN == 64) return hc_launch_x<64, 32>(x3, ma, mb, p, grid, smem, st);
+  return hc_launch_x<32, 32>(x3, ma, mb, p, grid, smem, st);
+}
+
+}  // namespace smc
+
+extern "C" int smc_igemm_config(int key, int value) {
+  smc::hconv_config(key, value);
+  return SMC_OK;
+}

@@ -12,10 +12,7 @@
 //                               fp16 hi (+lo) / fp32 stores
 // Two CTAs fit per SM (<= 3 x 32 KB stages, <= 256 TMEM columns each), so one tile's epilogue overlaps
 // the other's main loop without a persistent scheduler.
-#include <cuda.h>
-
-#include "common.cuh"
-#include "stylemc_b200.h"
+#include "tc.cuh"
 
 namespace smc {
 
@@ -26,76 +23,6 @@ struct IgParams {
   smc_igemm_tap taps[SMC_IGEMM_MAX_TAPS];
   smc_igemm_epilogue epi;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], fp16 x fp16 -> fp32
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major operand tile in smem, rows of SWZ bytes (SWZ = KC * 2 in {64, 128}), hardware swizzle SWZ,
-// 8-row core-matrix groups SWZ*8 bytes apart (cute::UMMA::SmemDescriptor layout, version 1 = sm_100).
-template <int SWZ>
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);                  // start address, bits [0,14)
-  d |= (uint64_t)0 << 16;                                  // leading byte offset: unused for swizzled K-major
-  d |= (uint64_t)(((SWZ * 8) >> 4) & 0x3FFF) << 32;        // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
-  d |= (uint64_t)(SWZ == 128 ? 2 : 4) << 61;               // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
-  return d;
-}
 
 // ---- kernel ---------------------------------------------------------------------------------------
 // ACC = true ("promoted accumulation"): the tensor core adds into its fp32 accumulator with truncation, a bias toward zero that
@@ -324,11 +251,7 @@ __global__ void __launch_bounds__(192, ACC ? 1 : 2) igemm_kernel(const __grid_co
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* ptr = nullptr;
@@ -360,10 +283,17 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const IgPara
   return SMC_OK;
 }
 
+int hconv_try_launch(const smc_igemm_desc* d, cudaStream_t st);   // hconv.cu
+
 int igemm_launch(const smc_igemm_desc* d, cudaStream_t st) {
   if (!d || !d->A || !d->B) return SMC_EINVAL;
   if (d->ntaps < 1 || d->ntaps > SMC_IGEMM_MAX_TAPS) return SMC_EINVAL;
   if (d->n_img < 1 || d->H < 1 || d->W < 1 || d->n_out < 1 || d->C < 1) return SMC_EINVAL;
+  if (((uintptr_t)d->A & 15) || ((uintptr_t)d->B & 15)) return SMC_EINVAL;
+  {
+    const int r = hconv_try_launch(d, st);   // halo-tile kernel for the spatial convolutions it supports
+    if (r != SMC_EUNSUPPORTED) return r;
+  }
   if (d->C % 32 != 0 || d->lda % 8 != 0 || d->ldb % 8 != 0) return SMC_EUNSUPPORTED;
   if (((uintptr_t)d->A & 15) || ((uintptr_t)d->B & 15)) return SMC_EINVAL;
   const int KC = (d->C % 64 == 0) ? 64 : 32;

@@ -1,0 +1,165 @@
+"""GPU checks of the halo-tile tcgen05 convolution kernel (csrc/hconv.cu, reached through smc_igemm) against torch fp64
+references of the same contraction, and against the per-tap kernel (csrc/igemm.cu) on the same inputs.
+Floating point: tolerances are stated per case (max-abs error relative to the largest reference magnitude)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def force_hconv():
+    from stylemc_b200 import _lib
+    _lib.call('smc_igemm_config', 0, 2)      # use hconv.cu whenever the shape is supported
+    yield
+    _lib.call('smc_igemm_config', 0, 1)
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def planes(x_nchw, two):
+    from stylemc_b200 import gemm
+    n, c, h, w = x_nchw.shape
+    return gemm.split_planes(x_nchw.permute(0, 2, 3, 1).contiguous(), two).reshape(-1, h, w, c)
+
+
+def wmat(w_oihw, two, transpose=False):
+    from stylemc_b200 import gemm
+    o, i, kh, kw = w_oihw.shape
+    m = w_oihw.permute(2, 3, 1, 0).reshape(kh * kw * i, o) if transpose else w_oihw.permute(2, 3, 0, 1).reshape(kh * kw * o, i)
+    return gemm.split_planes(m.contiguous(), two).reshape(-1, m.shape[1])
+
+
+CASES = [(2, 64, 64, 32, 32), (1, 128, 128, 48, 40), (2, 64, 128, 64, 64), (1, 192, 64, 33, 70), (1, 32, 32, 64, 64),
+         (2, 64, 32, 40, 40), (1, 32, 64, 37, 129), (1, 256, 256, 32, 32), (3, 96, 96, 32, 32)]
+
+
+@pytest.mark.parametrize('n,c,o,h,w', CASES)
+@pytest.mark.parametrize('x3', [False, True])
+def test_conv3x3(n, c, o, h, w, x3):
+    from stylemc_b200 import gemm
+    g = torch.Generator(device='cuda').manual_seed(2)
+    x = torch.randn(n, c, h, w, device='cuda', generator=g)
+    wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.05
+    if not x3:
+        x, wt = x.half().float(), wt.half().float()
+    out = torch.empty(n, h, w, o, device='cuda')
+    gemm.igemm(planes(x, x3), wmat(wt, x3), n, h, w, o, gemm.TAPS_3X3, precision='x3' if x3 else 'x1', acc_chunk_k=512 if x3 else 0,
+               a_plane_stride_imgs=n, b_rows_per_tap=9 * o, out_f32=out)
+    ref = F.conv2d(x.double(), wt.double(), padding=1).permute(0, 2, 3, 1)
+    assert rel(out, ref) <= (2e-6 if x3 else 1e-5)
+
+
+def test_matches_per_tap_kernel_bitwise_close():
+    """Same inputs through igemm.cu and hconv.cu: both are fp32-accumulated fp16 products, so they agree to accumulation order."""
+    from stylemc_b200 import _lib, gemm
+    g = torch.Generator(device='cuda').manual_seed(7)
+    n, c, o, h, w = 2, 128, 128, 40, 40
+    x = torch.randn(n, c, h, w, device='cuda', generator=g).half().float()
+    wt = (torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.05).half().float()
+    outs = []
+    for mode in (0, 2):
+        _lib.call('smc_igemm_config', 0, mode)
+        out = torch.empty(n, h, w, o, device='cuda')
+        gemm.igemm(planes(x, False), wmat(wt, False), n, h, w, o, gemm.TAPS_3X3, out_f32=out)
+        outs.append(out)
+    assert rel(outs[1], outs[0]) <= 2e-6
+
+
+@pytest.mark.parametrize('x3', [False, True])
+def test_epilogue_all_outputs(x3):
+    from stylemc_b200 import gemm
+    g = torch.Generator(device='cuda').manual_seed(3)
+    n, c, o, h, w = 3, 64, 128, 36, 44
+    x = torch.randn(n, c, h, w, device='cuda', generator=g)
+    wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.1
+    if not x3:
+        x, wt = x.half().float(), wt.half().float()
+    d = torch.rand(n, o, device='cuda', generator=g) + 0.5
+    s = torch.randn(n, o, device='cuda', generator=g)
+    bias = torch.randn(o, device='cuda', generator=g)
+    noise = torch.randn(h, w, device='cuda', generator=g)
+    res = torch.randn(n, h, w, o, device='cuda', generator=g)
+    o32 = torch.empty(n, h, w, o, device='cuda')
+    ohi, olo, oraw = (torch.empty(n, h, w, o, device='cuda', dtype=torch.float16) for _ in range(3))
+    gemm.igemm(planes(x, x3), wmat(wt, x3), n, h, w, o, gemm.TAPS_3X3, precision='x3' if x3 else 'x1', acc_chunk_k=512 if x3 else 0,
+               a_plane_stride_imgs=n, b_rows_per_tap=9 * o, row_scale=d, post_scale=s, bias=bias, noise=noise,
+               noise_strides=(w, 1), act=1, alpha=0.2, gain=2 ** 0.5, clamp=3.0, residual=res, out_f32=o32, out_hi=ohi, out_lo=olo,
+               out_raw=oraw)
+    u = F.conv2d(x.double(), wt.double(), padding=1)
+    z = u * d.double()[:, :, None, None] + noise.double() + bias.double()[None, :, None, None]
+    y = (F.leaky_relu(z, 0.2) * 2 ** 0.5).clamp(-3, 3).permute(0, 2, 3, 1)
+    full = y * s.double()[:, None, None, :] + res.double()
+    assert rel(oraw.float(), y) <= 1e-3
+    assert rel(o32, full) <= 1e-5
+    assert rel(ohi.float() + olo.float(), full) <= 1e-5
+    assert rel(ohi.float(), full) <= 1e-3
+
+
+@pytest.mark.parametrize('n,c,o,h', [(2, 64, 32, 32), (1, 128, 64, 40), (2, 64, 128, 33)])
+@pytest.mark.parametrize('x3', [False, True])
+def test_transposed_stride2_parity_planes_and_dgrad(n, c, o, h, x3):
+    from stylemc_b200 import gemm
+    g = torch.Generator(device='cuda').manual_seed(4)
+    w = h
+    x = torch.randn(n, c, h, w, device='cuda', generator=g)
+    wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.1
+    if not x3:
+        x, wt = x.half().float(), wt.half().float()
+    kw = dict(precision='x3' if x3 else 'x1', acc_chunk_k=512 if x3 else 0)
+    pl = torch.zeros(4, n, h + 1, w + 1, o, device='cuda')
+    for r in (0, 1):
+        for cc in (0, 1):
+            gemm.igemm(planes(x, x3), wmat(wt, x3), n, h + 1, w + 1, o, gemm.up2_parity_taps(r, cc), a_plane_stride_imgs=n,
+                       b_rows_per_tap=9 * o, out_f32=pl[r * 2 + cc], **kw)
+    ref = F.conv_transpose2d(x.double(), wt.double().transpose(0, 1), stride=2)            # [n, o, 2h+1, 2w+1]
+    t = torch.zeros(n, 2 * h + 2, 2 * w + 2, o, device='cuda', dtype=torch.float64)
+    for r in (0, 1):
+        for cc in (0, 1):
+            t[:, r::2, cc::2] = pl[r * 2 + cc].double()
+    assert rel(t[:, :2 * h + 1, :2 * w + 1], ref.permute(0, 2, 3, 1)) <= (2e-6 if x3 else 1e-5)
+    assert t[:, 2 * h + 1].abs().max().item() == 0 and t[:, :, 2 * w + 1].abs().max().item() == 0
+
+    # dgrad of the same conv from gradient parity planes (four A sources)
+    gy = torch.randn(n, o, 2 * h + 1, 2 * w + 1, device='cuda', generator=g)
+    if not x3:
+        gy = gy.half().float()
+    gyl = F.pad(gy, (0, 1, 0, 1))
+    gp32 = torch.stack([gyl[:, :, r::2, cc::2] for r in (0, 1) for cc in (0, 1)])           # [4, n, o, h+1, w+1]
+    gp = gemm.split_planes(gp32.permute(0, 1, 3, 4, 2).contiguous(), x3)                    # [P, 4, n, h+1, w+1, o]
+    gx = torch.empty(n, h, w, c, device='cuda')
+    gemm.igemm(gp.reshape(-1, h + 1, w + 1, o), wmat(wt, x3, transpose=True), n, h, w, c, gemm.up2_dgrad_taps(n), a_plane_stride_imgs=4 * n,
+               b_rows_per_tap=9 * c, out_f32=gx, **kw)
+    xr = x.double().requires_grad_(True)
+    F.conv_transpose2d(xr, wt.double().transpose(0, 1), stride=2).backward(gy.double())
+    assert rel(gx, xr.grad.permute(0, 2, 3, 1)) <= (2e-6 if x3 else 1e-5)
+
+
+def test_conv3x3_dgrad_taps():
+    from stylemc_b200 import gemm
+    g = torch.Generator(device='cuda').manual_seed(5)
+    n, c, o, h, w = 2, 64, 96, 36, 36
+    wt = (torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.1).half().float()
+    gy = torch.randn(n, o, h, w, device='cuda', generator=g).half().float()
+    gx = torch.empty(n, h, w, c, device='cuda')
+    gemm.igemm(planes(gy, False), wmat(wt, False, transpose=True), n, h, w, c, gemm.TAPS_3X3_DGRAD, out_f32=gx)
+    xr = torch.zeros(n, c, h, w, device='cuda', dtype=torch.float64, requires_grad=True)
+    F.conv2d(xr, wt.double(), padding=1).backward(gy.double())
+    assert rel(gx, xr.grad.permute(0, 2, 3, 1)) <= 1e-5
+
+
+def test_promoted_accumulation_is_fp32_grade_on_a_long_chain():
+    """K = 9 * 512 products per output: the main (hi*hi) chain is drained every 64-channel slab, the cross terms never."""
+    from stylemc_b200 import gemm
+    g = torch.Generator(device='cuda').manual_seed(11)
+    n, c, o, h, w = 1, 512, 128, 32, 32
+    x = torch.randn(n, c, h, w, device='cuda', generator=g)
+    wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.02
+    out = torch.empty(n, h, w, o, device='cuda')
+    gemm.igemm(planes(x, True), wmat(wt, True), n, h, w, o, gemm.TAPS_3X3, precision='x3', acc_chunk_k=512, a_plane_stride_imgs=n,
+               b_rows_per_tap=9 * o, out_f32=out)
+    ref = F.conv2d(x.double(), wt.double(), padding=1).permute(0, 2, 3, 1)
+    assert rel(out, ref) <= 1.5e-6
