@@ -51,12 +51,12 @@ struct HcParams {
   int n_img, H, W, C, n_out;
   int Wt, Wp, RB, padL, padT;
   int col_tiles, tiles_per_col, n_tiles_n;
-  long long total_tiles;
+  int total_tiles;
   int ngroups, kchunks, kcs_per_drain, nb;
   int nsegs, ndrains;  // segments per slab; main-accumulator drains per tile
-  int lo_double;     // x3: the lo tile has two buffers (small tiles: the next lo tile must land before the B_lo pass ends)
+  int na_hi, na_lo;  // A buffers: a ring for the hi tiles (read by both passes) and one for the lo tiles (released after the
+                     // B_hi pass); x1 uses the hi ring only.  Small-C layers get deeper rings: their tiles are short.
   int b_resident;    // every weight stage of a tile has its own smem slot and is loaded once per CTA (n_tiles_n == 1)
-  int na;            // number of A buffers
   uint32_t a_box_bytes, a_buf_bytes;
   HcGroup groups[HC_MAX_GROUPS];
   HcSeg segs[HC_MAX_SEGS];
@@ -113,14 +113,14 @@ __device__ __forceinline__ void hc_issue_tap(uint32_t tm, uint32_t alo, uint32_t
 struct HcTile {
   int nt, n, w0, q0, hfirst;
 };
-__device__ __forceinline__ HcTile hc_tile(const HcParams& p, long long t) {
+__device__ __forceinline__ HcTile hc_tile(const HcParams& p, int t) {
   HcTile r;
-  r.nt = (int)(t % p.n_tiles_n);
+  r.nt = t % p.n_tiles_n;
   t /= p.n_tiles_n;
-  const int ti = (int)(t % p.tiles_per_col);
+  const int ti = t % p.tiles_per_col;
   t /= p.tiles_per_col;
-  const int ct = (int)(t % p.col_tiles);
-  r.n = (int)(t / p.col_tiles);
+  const int ct = t % p.col_tiles;
+  r.n = t / p.col_tiles;
   r.w0 = ct * p.Wt;
   r.q0 = ti * HC_MT;
   r.hfirst = r.q0 / p.Wp;
@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* a_buf = smem;                                        // na buffers of a_buf_bytes
-  uint8_t* b_buf = smem + (size_t)p.na * p.a_buf_bytes;         // nb stages of B_BYTES
+  uint8_t* b_buf = smem + (size_t)(p.na_hi + p.na_lo) * p.a_buf_bytes;         // nb stages of B_BYTES
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + (size_t)p.nb * B_BYTES);
-  uint64_t* a_full = bars;            // [4]
-  uint64_t* a_empty = bars + 4;       // [4]
-  uint64_t* b_full = bars + 8;        // [MAXB]
+  uint64_t* a_full = bars;            // [8]
+  uint64_t* a_empty = bars + 8;       // [8]
+  uint64_t* b_full = bars + 16;       // [MAXB]
   uint64_t* b_empty = b_full + MAXB;  // [MAXB]
   uint64_t* main_full = b_empty + MAXB;    // [2] per set
   uint64_t* main_drained = main_full + 2;  // [2]
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
@@ -193,17 +193,17 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // A buffer of (step, plane): x3: hi alternates between buffers 0 and 1 (it is read by both passes); lo sits in buffer 2
-  // (released after the B_hi pass, so the next lo tile lands while the B_lo pass runs) or alternates 2/3.  x1: ring of 3.
-  auto hi_buf = [&](uint32_t step) -> int { return X3 ? (int)(step & 1u) : (int)(step % 3u); };
-  auto lo_buf = [&](uint32_t step) -> int { return 2 + (p.lo_double ? (int)(step & 1u) : 0); };
+  // A buffer of (step, plane): hi tiles cycle through buffers [0, na_hi), lo tiles through [na_hi, na_hi + na_lo)
+  const uint32_t na_hi = (uint32_t)p.na_hi, na_lo = (uint32_t)p.na_lo;
+  auto hi_buf = [&](uint32_t step) -> int { return (int)(step % na_hi); };
+  auto lo_buf = [&](uint32_t step) -> int { return X3 ? (int)(na_hi + step % na_lo) : 0; };
 
   if (warp == 0) {
     // ---------------- A producer: one halo tile per (slab, group, plane) ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t eph = 0;                 // bit b: number of loads into buffer b so far, mod 2
       uint32_t step = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const HcTile tl = hc_tile(p, t);
         const int wbox = tl.w0 - p.padL, hbox = tl.hfirst - p.padT;
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -226,10 +226,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ---------------- B producer: one weight stage per (slab, group, pass, tap) ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t bs = 0, bph = 0;
       const uint32_t nb = (uint32_t)p.nb;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int nt = (int)(t % p.n_tiles_n);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int si = 0; si < p.nsegs; ++si) {
@@ -249,15 +249,17 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       }
     }
   } else if (warp == 2) {
-    // ---------------- MMA issuer: the whole warp walks the (uniform) loops and waits; one elected lane issues ----------------
-    {
+    // ---------------- MMA issuer: ONE elected lane runs the whole role.  elect.sync (rather than lane == 0) tells ptxas
+    // that a single thread is active, so the tcgen05 operands go to uniform registers with one R2UR each instead of a
+    // per-lane waterfall loop (15 instructions per MMA), and the issue loop stays far below the MMA duration.
+    if (elect_one()) {
       uint32_t aph = 0;                 // bit b: number of tiles consumed from A buffer b so far, mod 2
       uint32_t step = 0, bs = 0, bph = 0, chunk_ctr = 0, tile_ctr = 0;
       uint32_t nm0 = 0, nm1 = 0, nc0 = 0, nc1 = 0;     // chunks committed so far per set (main / cross)
       const uint32_t nb = (uint32_t)p.nb;
       const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
       const bool resident = p.b_resident != 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
         const HcTile tl = hc_tile(p, t);
         const int rel0 = tl.q0 - tl.hfirst * p.Wp;         // position of tile row 0 inside the box (before the tap offset)
         const uint32_t set_t = (X3 && SETS == 2) ? (tile_ctr & 1u) : 0u;
@@ -297,14 +299,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
                 tcgen05_fence_after();
                 const uint32_t blo = (b_base + bs * (uint32_t)B_BYTES) >> 4;
                 const uint32_t roff = (uint32_t)p.taps[tp].posoff * (uint32_t)ROWB;
-                if (elect_one()) {
+                {
                   if (pass == 0) hc_issue_tap<BN, KC>(tmem_base + set * (uint32_t)SETCOLS, (a_hi + roff) >> 4, blo, IDESC, fresh ? 0u : 1u);
                   if (X3)                                  // pass 0: A_lo * B_hi, pass 1: A_hi * B_lo -> cross
                     hc_issue_tap<BN, KC>(tmem_base + set_t * (uint32_t)SETCOLS + (uint32_t)(HC_MB * BN),
                                          ((pass == 0 ? a_lo : a_hi) + roff) >> 4, blo, IDESC, fresh_cross ? 0u : 1u);
                   if (!resident) tcgen05_commit(&b_empty[bs]);
                 }
-                __syncwarp();
                 if (pass == 0) fresh = false;
                 fresh_cross = false;
                 if (++bs == nb) { bs = 0; bph ^= 1u; }
@@ -312,11 +313,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
               if (X3 && pass == 0) {
                 // main chain complete (mid-slab commit, or the slab-end commit of a chunk): drained while the B_lo pass runs
                 const bool main_done = (sflags & HC_SEG_COMMIT) && (!(sflags & HC_SEG_SLABEND) || chunk_ends);
-                if (elect_one()) {
-                  if (sflags & HC_SEG_LAST) tcgen05_commit(&a_empty[lb]);   // the lo tile is only read by B_hi passes
-                  if (main_done) tcgen05_commit(&main_full[set_t]);
-                }
-                __syncwarp();
+                if (sflags & HC_SEG_LAST) tcgen05_commit(&a_empty[lb]);   // the lo tile is only read by B_hi passes
+                if (main_done) tcgen05_commit(&main_full[set_t]);
                 if (main_done) {
                   if (set_t) ++nm1; else ++nm0;
                   fresh = true;
@@ -324,8 +322,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
               }
             }
             if (sflags & HC_SEG_LAST) {
-              if (elect_one()) tcgen05_commit(&a_empty[hb]);
-              __syncwarp();
+              tcgen05_commit(&a_empty[hb]);
               ++step;
             }
           }
@@ -333,8 +330,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             in_chunk = 0;
             if (!X3) {
               const uint32_t set = chunk_ctr & 1u;
-              if (elect_one()) tcgen05_commit(&main_full[set]);
-              __syncwarp();
+              tcgen05_commit(&main_full[set]);
               if (set) ++nm1; else ++nm0;
               ++chunk_ctr;
               fresh = true;
@@ -344,8 +340,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
           }
         }
         if (X3) {
-          if (elect_one()) tcgen05_commit(&cross_full[set_t]);
-          __syncwarp();
+          tcgen05_commit(&cross_full[set_t]);
           if (set_t) ++nc1; else ++nc0;
         }
       }
@@ -363,7 +358,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BN + ch * CW);
     uint32_t em0 = 0, em1 = 0, ec0 = 0, ec1 = 0, chunk_ctr = 0, tile_ctr = 0;
     float acc[CW];
-    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
       const HcTile tl = hc_tile(p, t);
       const uint32_t set_t = (X3 && SETS == 2) ? (tile_ctr & 1u) : 0u;
 #pragma unroll
@@ -558,24 +553,36 @@ int hconv_try_launch(const smc_igemm_desc* d, cudaStream_t st) {
   }
   const size_t smem_fixed = 1024 + (size_t)p.nb * b_bytes + 1024;
   const int wt_cands[4] = {g_hconv_wt > 0 ? g_hconv_wt : 64, 32, 16, 8};
+  const bool short_tiles = d->C / KC <= 2;            // few MMAs per tile: prefetch A tiles further ahead
   p.Wt = 0;
   for (int ci = 0; ci < 4 && p.Wt == 0; ++ci) {
-    for (int lod = (x3 && d->C / KC <= 2) ? 1 : 0; lod >= 0 && p.Wt == 0; --lod) {
-      const int wt = d->W < wt_cands[ci] ? d->W : wt_cands[ci];
-      const int wp = wt + padW;
-      const int rb = (HC_MT % wp == 0) ? HC_MT / wp + padH : ceil_div(HC_MT, wp) + 1 + padH;
-      const size_t abuf = ((size_t)(rb * wp + 8) * (size_t)(KC * 2) + 1023u) & ~(size_t)1023u;
-      const int na = x3 ? 3 + lod : 3;
-      if (wp <= 256 && rb <= 256 && smem_fixed + na * abuf <= 227 * 1024) {
-        p.Wt = wt; p.Wp = wp; p.RB = rb; p.lo_double = lod; p.na = na;
-      }
+    const int wt = d->W < wt_cands[ci] ? d->W : wt_cands[ci];
+    const int wp = wt + padW;
+    const int rb = (HC_MT % wp == 0) ? HC_MT / wp + padH : ceil_div(HC_MT, wp) + 1 + padH;
+    const size_t abuf = ((size_t)(rb * wp + 8) * (size_t)(KC * 2) + 1023u) & ~(size_t)1023u;
+    if (wp > 256 || rb > 256) continue;
+    const int nmax = (int)((227 * 1024 - smem_fixed) / abuf);
+    int nh, nl;
+    if (x3) {
+      if (nmax < 3) continue;
+      nl = short_tiles ? (nmax / 2 > 4 ? 4 : nmax / 2) : 1;
+      nh = nmax - nl > (short_tiles ? 4 : 2) ? (short_tiles ? 4 : 2) : nmax - nl;
+    } else {
+      if (nmax < 2) continue;
+      nh = nmax > 4 ? 4 : nmax;
+      nl = 0;
     }
+    p.Wt = wt; p.Wp = wp; p.RB = rb; p.na_hi = nh; p.na_lo = nl;
   }
   if (p.Wt == 0) return SMC_EUNSUPPORTED;
   p.col_tiles = ceil_div(d->W, p.Wt);
   p.tiles_per_col = (int)ceil_div_ll((long long)d->H * p.Wp, HC_MT);
   p.n_tiles_n = d->n_out / BN;
-  p.total_tiles = (long long)d->n_img * p.col_tiles * p.tiles_per_col * p.n_tiles_n;
+  {
+    const long long tt = (long long)d->n_img * p.col_tiles * p.tiles_per_col * p.n_tiles_n;
+    if (tt > 0x7fffffffLL) return SMC_ETOOLARGE;
+    p.total_tiles = (int)tt;
+  }
   p.kchunks = d->C / KC;
 
   // group the base taps by A source
@@ -652,7 +659,7 @@ int hconv_try_launch(const smc_igemm_desc* d, cudaStream_t st) {
   p.epi = d->epi;
   if (!p.epi.out_f32 && !p.epi.out_hi && !p.epi.out_raw) return SMC_EINVAL;
   if ((p.epi.o_sn | p.epi.o_sh | p.epi.o_sw | p.epi.o_off) & 7) return SMC_EUNSUPPORTED;
-  const size_t smem = smem_fixed + (size_t)p.na * p.a_buf_bytes;
+  const size_t smem = smem_fixed + (size_t)(p.na_hi + p.na_lo) * p.a_buf_bytes;
   if (smem > 227 * 1024) return SMC_EUNSUPPORTED;
 
   EncodeTiledFn enc = get_encode_fn();

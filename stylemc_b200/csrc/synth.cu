@@ -569,11 +569,15 @@ __global__ void __launch_bounds__(256) fir_bwd_kernel(const __half* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // ds[n,i] = T1[n,i] - s[n,i] * sum_o q[o,i] * d[n,o]^2 * R[n,o]  (SURVEY.md section 8a style-gradient algebra;
 // R already carries d * dL/dd), summed over the batch into the delta gradient row and unscaled.
+// One CTA = 32 columns i x 8 slices of the o loop (the per-sample sum over o is the long axis: N * cout terms per column);
+// the batch is walked in order so the result is deterministic.
 __global__ void __launch_bounds__(256) sgrad_finish_kernel(const float* __restrict__ T1, const float* __restrict__ R, const float* __restrict__ q,
                                                            const float* __restrict__ d, const float* __restrict__ s, long long s_stride,
                                                            const float* __restrict__ gscale_ptr, float* __restrict__ grad_row, int N, int cin, int cout) {
-  extern __shared__ float coef[];  // [cout] = d^2 * R for the current image
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float coef[];  // [cout] = d^2 * R for the current image, then [8][32] partial sums
+  float* part = coef + cout;
+  const int tx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
   float acc = 0.f;
   for (int n = 0; n < N; ++n) {
     __syncthreads();
@@ -582,13 +586,29 @@ __global__ void __launch_bounds__(256) sgrad_finish_kernel(const float* __restri
       coef[o] = dd * dd * R[(long long)n * cout + o];
     }
     __syncthreads();
+    float t2 = 0.f;
     if (i < cin) {
-      float t2 = 0.f;
-      for (int o = 0; o < cout; ++o) t2 += __ldg(q + (long long)o * cin + i) * coef[o];
-      acc += T1[(long long)n * cin + i] - s[n * s_stride + i] * t2;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int o = sl;
+      for (; o + 24 < cout; o += 32) {
+        a0 += __ldg(q + (long long)o * cin + i) * coef[o];
+        a1 += __ldg(q + (long long)(o + 8) * cin + i) * coef[o + 8];
+        a2 += __ldg(q + (long long)(o + 16) * cin + i) * coef[o + 16];
+        a3 += __ldg(q + (long long)(o + 24) * cin + i) * coef[o + 24];
+      }
+      for (; o < cout; o += 8) a0 += __ldg(q + (long long)o * cin + i) * coef[o];
+      t2 = (a0 + a1) + (a2 + a3);
+    }
+    part[sl * 32 + tx] = t2;
+    __syncthreads();
+    if (sl == 0 && i < cin) {
+      float tt = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tt += part[k * 32 + tx];
+      acc += T1[(long long)n * cin + i] - s[n * s_stride + i] * tt;
     }
   }
-  if (i < cin) grad_row[i] += acc / __ldg(gscale_ptr);
+  if (sl == 0 && i < cin) grad_row[i] += acc / __ldg(gscale_ptr);
 }
 
 // gscale = 2^k with amax(|g|) * gscale in (target/2, target]: keeps the fp16 gradient planes (and their lo halves) in the
@@ -725,7 +745,7 @@ extern "C" int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int 
 extern "C" int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
                                 const float* gscale, float* grad_row, int n, int cin, int cout, void* stream) {
   if (!t1 || !r || !q || !d || !s || !gscale || !grad_row || n < 1 || cin < 1 || cout < 1) return SMC_EINVAL;
-  sgrad_finish_kernel<<<ceil_div(cin, 256), 256, cout * sizeof(float), (cudaStream_t)stream>>>(t1, r, q, d, s, s_stride, gscale, grad_row, n, cin, cout);
+  sgrad_finish_kernel<<<ceil_div(cin, 32), 256, (cout + 256) * sizeof(float), (cudaStream_t)stream>>>(t1, r, q, d, s, s_stride, gscale, grad_row, n, cin, cout);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

@@ -203,3 +203,15 @@ def ab_epilogue():
 
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'abe':
     ab_epilogue()
+
+
+def one(c, o, r, n=16):
+    x, wt, run = conv_case(n, c, o, r, r, True, acc_k=512)
+    cfg(0, 2)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'one':
+    one(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
