@@ -312,6 +312,98 @@ __global__ void __launch_bounds__(256) torgb_kernel(const __half* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------------
+// torgb_kernel for C <= 256 with C/8 a power of two: a block stays inside one image and a lane owns one channel group, so the
+// modulated ToRGB weights and the next block's styles sit in registers; x is streamed once.
+__global__ void __launch_bounds__(256) torgb1_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, int N, int H, int W, int C,
+                                                     const float* __restrict__ w_rgb, const float* __restrict__ s_t, long long st_stride,
+                                                     float wgain, const float* __restrict__ b_rgb, float clamp,
+                                                     const float* __restrict__ img_prev, const float* __restrict__ fk_up, float* __restrict__ img,
+                                                     const float* __restrict__ s_next, long long sn_stride,
+                                                     __half* __restrict__ xs_hi, __half* __restrict__ xs_lo, int lpp, int pix_per_block) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpp;
+  const int groups_per_warp = 32 / lpp;
+  const int warps = blockDim.x >> 5;
+  const int hw = H * W;
+  const int blocks_per_img = ceil_div(hw, pix_per_block);
+  const int n = blockIdx.x / blocks_per_img;
+  const int p_begin = (blockIdx.x % blocks_per_img) * pix_per_block;
+  const int p_end = (p_begin + pix_per_block < hw) ? p_begin + pix_per_block : hw;
+  const int c = sub * 8;
+  float m0[8], m1[8], m2[8], sn[8];
+  {
+    float st[8];
+    ld8f(s_t + n * st_stride + c, st);
+    ld8f(w_rgb + c, m0); ld8f(w_rgb + C + c, m1); ld8f(w_rgb + 2 * C + c, m2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float t = st[e] * wgain; m0[e] *= t; m1[e] *= t; m2[e] *= t; sn[e] = 0.f; }
+    if (xs_hi) ld8f(s_next + n * sn_stride + c, sn);
+  }
+  const float bj = sub < 3 ? __ldg(b_rgb + sub) : 0.f;
+  float fk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) fk[i] = img_prev ? __ldg(fk_up + i) : 0.f;
+  for (int pbase = p_begin + (threadIdx.x >> 5) * groups_per_warp; pbase < p_end; pbase += groups_per_warp * warps) {
+    const int p = pbase + lane / lpp;
+    const bool live = p < p_end;
+    const long long pix = (long long)n * hw + (live ? p : 0);
+    float v[8];
+    h8_to_f(ld_stream(x_hi + pix * C + c), v);
+    if (x_lo) {
+      float l[8];
+      h8_to_f(ld_stream(x_lo + pix * C + c), l);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += l[e];
+    }
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { r0 += m0[e] * v[e]; r1 += m1[e] * v[e]; r2 += m2[e] * v[e]; }
+    if (xs_hi && live) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = v[e] * sn[e];
+      if (xs_lo) {
+        uint4 hi, lo;
+        f_to_h8_split(o, hi, lo);
+        st_stream(xs_hi + pix * C + c, hi);
+        st_stream(xs_lo + pix * C + c, lo);
+      } else {
+        st_stream(xs_hi + pix * C + c, f_to_h8(o));
+      }
+    }
+    for (int o = lpp >> 1; o > 0; o >>= 1) {
+      r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+      r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    if (live && sub < 3) {
+      const int j = sub;
+      float r = (j == 0 ? r0 : (j == 1 ? r1 : r2)) + bj;
+      if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
+      const int yy = p / W, xq = p - yy * W;
+      if (img_prev) {
+        const int h2 = H >> 1, w2 = W >> 1;
+        const float* ip = img_prev + ((long long)n * 3 + j) * h2 * w2;
+        float u = 0.f;
+#pragma unroll
+        for (int fy = 0; fy < 4; ++fy) {
+          const int ay = yy + fy - 2;
+          if (ay < 0 || (ay & 1) || (ay >> 1) >= h2) continue;
+#pragma unroll
+          for (int fx = 0; fx < 4; ++fx) {
+            const int ax = xq + fx - 2;
+            if (ax < 0 || (ax & 1) || (ax >> 1) >= w2) continue;
+            u += fk[fy * 4 + fx] * __ldg(ip + (long long)(ay >> 1) * w2 + (ax >> 1));
+          }
+        }
+        r += u;
+      }
+      img[(((long long)n * 3 + j) * H + yy) * W + xq] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Backward through  y = clamp(lrelu(z) * gain),  z = d * u + noise + b  of one modulated-conv layer whose
 // saved fp16 output is y.  Incoming gradient w.r.t. y:
 //     g_y = s_next[n,c] * g_up[n,p,c]                          (consumer conv's dgrad output, scaled fp16)
@@ -476,6 +568,142 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__
           atomicAdd(&red[C + g * 8 + e], racc[ps][e]);
         }
       }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      if (T1) atomicAdd(T1 + (long long)n * C + i, red[i]);
+      if (R) atomicAdd(R + (long long)n * C + i, red[C + i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// act_bwd for C <= 256 with C/8 a power of two (every layer from 128 px up, where the bytes are): one lane owns ONE channel
+// group for the whole block, so every per-channel parameter (next style, ToRGB weights * style, demodulation, bias) lives in
+// registers and y is read exactly once per pixel (the ToRGB clamp mask is computed from the same registers).
+template <class TG>
+__global__ void __launch_bounds__(256) act_bwd1_kernel(const __half* __restrict__ y, const __half* __restrict__ y_lo, int N, int H, int W, int C,
+                                                       const TG* __restrict__ g_up, const float* __restrict__ s_next, long long sn_stride,
+                                                       const float* __restrict__ g_img, const float* __restrict__ w_rgb,
+                                                       const float* __restrict__ s_t, long long st_stride, float wgain,
+                                                       const float* __restrict__ b_rgb, float rgb_clamp, const float* __restrict__ gscale_ptr,
+                                                       const float* __restrict__ dcoef, const float* __restrict__ noise, const float* __restrict__ bias,
+                                                       float alpha, float gain, float clamp,
+                                                       __half* __restrict__ gd, __half* __restrict__ gd_lo, float* __restrict__ T1, float* __restrict__ R,
+                                                       int lpp, int pix_per_block) {
+  extern __shared__ float red[];  // [2][C] block partials (T1, R)
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpp;
+  const int groups_per_warp = 32 / lpp;
+  const int warps = blockDim.x >> 5;
+  const bool reduce = (T1 != nullptr) || (R != nullptr);
+  const float gscale = gscale_ptr ? __ldg(gscale_ptr) : 1.f;
+  const long long hw = (long long)H * W;
+  const long long blocks_per_img = ceil_div_ll(hw, pix_per_block);
+  const int n = (int)(blockIdx.x / blocks_per_img);
+  const long long p_begin = (blockIdx.x % blocks_per_img) * pix_per_block;
+  const long long p_end = (p_begin + pix_per_block < hw) ? p_begin + pix_per_block : hw;
+  if (reduce) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+  }
+  const int c = sub * 8;
+  float sn[8], m0[8], m1[8], m2[8], dc[8], bs[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sn[e] = 0.f; m0[e] = 0.f; m1[e] = 0.f; m2[e] = 0.f; dc[e] = 1.f; }
+  if (g_up) ld8f(s_next + n * sn_stride + c, sn);
+  if (g_img) {
+    float st[8];
+    ld8f(s_t + n * st_stride + c, st);
+    ld8f(w_rgb + c, m0); ld8f(w_rgb + C + c, m1); ld8f(w_rgb + 2 * C + c, m2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float t = st[e] * wgain; m0[e] *= t; m1[e] *= t; m2[e] *= t; }
+  }
+  if (dcoef) ld8f(dcoef + (long long)n * C + c, dc);
+  ld8f(bias + c, bs);
+  float b3[3] = {0.f, 0.f, 0.f};
+  if (g_img) { b3[0] = __ldg(b_rgb); b3[1] = __ldg(b_rgb + 1); b3[2] = __ldg(b_rgb + 2); }
+  float t1acc[8], racc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { t1acc[e] = 0.f; racc[e] = 0.f; }
+
+  for (long long pbase = p_begin + (threadIdx.x >> 5) * groups_per_warp; pbase < p_end; pbase += (long long)groups_per_warp * warps) {
+    const long long p = pbase + lane / lpp;   // warp-uniform trip count: the shuffles below need all lanes
+    const bool live = p < p_end;
+    const long long pix = (long long)n * hw + (live ? p : 0);
+    float yv[8], gu[8];
+    h8_to_f(ld_stream(y + pix * C + c), yv);
+    if (y_lo) {
+      float l[8];
+      h8_to_f(ld_stream(y_lo + pix * C + c), l);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[e] += l[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gu[e] = 0.f;
+    if (g_up) {
+      if (sizeof(TG) == 2) h8_to_f(ld_stream(g_up + pix * C + c), gu);
+      else {
+        const uint4 a = ld_stream(reinterpret_cast<const float*>(g_up) + pix * C + c), b = ld_stream(reinterpret_cast<const float*>(g_up) + pix * C + c + 4);
+        gu[0] = __uint_as_float(a.x); gu[1] = __uint_as_float(a.y); gu[2] = __uint_as_float(a.z); gu[3] = __uint_as_float(a.w);
+        gu[4] = __uint_as_float(b.x); gu[5] = __uint_as_float(b.y); gu[6] = __uint_as_float(b.z); gu[7] = __uint_as_float(b.w);
+      }
+    }
+    float grgb[3] = {0.f, 0.f, 0.f};
+    if (g_img) {
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      if (rgb_clamp >= 0.f) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { r0 += m0[e] * yv[e]; r1 += m1[e] * yv[e]; r2 += m2[e] * yv[e]; }
+        for (int o = lpp >> 1; o > 0; o >>= 1) {
+          r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+          r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+          r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        }
+      }
+      if (live) {
+        const float rr[3] = {r0 + b3[0], r1 + b3[1], r2 + b3[2]};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const bool pass = (rgb_clamp < 0.f) || (rr[j] > -rgb_clamp && rr[j] < rgb_clamp);
+          grgb[j] = pass ? gscale * __ldg(g_img + ((long long)n * 3 + j) * hw + p) : 0.f;
+        }
+      }
+    }
+    if (!live) continue;
+    const float nz = noise ? __ldg(noise + p) : 0.f;
+    float out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gy = gu[e] * sn[e] + (m0[e] * grgb[0] + m1[e] * grgb[1] + m2[e] * grgb[2]);
+      const float yy = yv[e];
+      const bool pass = (clamp < 0.f) || (yy > -clamp && yy < clamp);
+      const float slope = (yy > 0.f ? 1.f : alpha) * gain;
+      float gz = pass ? gy * slope : 0.f;
+      out[e] = gz * dc[e];
+      if (reduce && gd && !gd_lo) gz = __half2float(__float2half_rn(out[e])) / dc[e];
+      if (reduce) {
+        const float z = yy / slope;
+        racc[e] += gz * (z - nz - bs[e]);
+        t1acc[e] += gu[e] * yy;
+      }
+    }
+    if (gd) {
+      if (gd_lo) {
+        uint4 hi, lo;
+        f_to_h8_split(out, hi, lo);
+        st_stream(gd + pix * C + c, hi);
+        st_stream(gd_lo + pix * C + c, lo);
+      } else {
+        st_stream(gd + pix * C + c, f_to_h8(out));
+      }
+    }
+  }
+  if (reduce) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&red[c + e], t1acc[e]);
+      atomicAdd(&red[C + c + e], racc[e]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -698,6 +926,19 @@ extern "C" int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w
   const int lpp = pick_lpp(c);
   if (lpp < 4) return SMC_EUNSUPPORTED;  // three lanes of a group write r, g, b
   const long long npix = (long long)n * h * w;
+  const int cgn = c >> 3;
+  if (cgn <= 32 && (cgn & (cgn - 1)) == 0 && (long long)h * w < (1 << 30)) {
+    const int hw = h * w;
+    int pix_per_block = 8 * (32 / lpp) * 16;
+    while (pix_per_block > 8 * (32 / lpp) && (long long)ceil_div(hw, pix_per_block) * n < 4 * kNumSMs) pix_per_block >>= 1;
+    const long long blocks = (long long)ceil_div(hw, pix_per_block) * n;
+    if (blocks > 0x7fffffffLL) return SMC_ETOOLARGE;
+    torgb1_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x_hi, (const __half*)x_lo, n, h, w, c, w_rgb, s_t, st_stride, wgain,
+                                                                  b_rgb, clamp, img_prev, fk_up, img, s_next, sn_stride, (__half*)xs_hi, (__half*)xs_lo,
+                                                                  lpp, pix_per_block);
+    SMC_LAUNCH_CHECK();
+    return SMC_OK;
+  }
   const int g = grid_for(npix * lpp, 256);
   torgb_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const __half*)x_hi, (const __half*)x_lo, n, h, w, c, w_rgb, s_t, st_stride, wgain, b_rgb,
                                                      clamp, img_prev, fk_up, img, s_next, sn_stride, (__half*)xs_hi, (__half*)xs_lo, lpp);
@@ -720,6 +961,19 @@ extern "C" int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w,
   while (pix_per_block > 8 * (32 / lpp) && ceil_div_ll(hw, pix_per_block) * n < 2 * kNumSMs) pix_per_block >>= 1;
   const long long blocks = ceil_div_ll(hw, pix_per_block) * n;
   if (blocks > 0x7fffffffLL) return SMC_ETOOLARGE;
+  const int cgn = c >> 3;
+  if (cgn <= 32 && (cgn & (cgn - 1)) == 0) {      // one channel group per lane: parameters in registers, y read once
+    if (g_up_is_f32)
+      act_bwd1_kernel<float><<<(int)blocks, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+          (const __half*)y, (const __half*)y_lo, n, h, w, c, (const float*)g_up, s_next, sn_stride, g_img, w_rgb, s_t, st_stride, wgain, b_rgb,
+          rgb_clamp, gscale, dcoef, noise, bias, alpha, gain, clamp, (__half*)gd, (__half*)gd_lo, t1, r, lpp, pix_per_block);
+    else
+      act_bwd1_kernel<__half><<<(int)blocks, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+          (const __half*)y, (const __half*)y_lo, n, h, w, c, (const __half*)g_up, s_next, sn_stride, g_img, w_rgb, s_t, st_stride, wgain, b_rgb,
+          rgb_clamp, gscale, dcoef, noise, bias, alpha, gain, clamp, (__half*)gd, (__half*)gd_lo, t1, r, lpp, pix_per_block);
+    SMC_LAUNCH_CHECK();
+    return SMC_OK;
+  }
   if (g_up_is_f32)
     act_bwd_kernel<float><<<(int)blocks, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
         (const __half*)y, (const __half*)y_lo, n, h, w, c, (const float*)g_up, s_next, sn_stride, g_img, w_rgb, s_t, st_stride, wgain, b_rgb,
