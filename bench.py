@@ -37,7 +37,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--resolution', type=int, default=1024)
     ap.add_argument('--batch', type=int, default=64, help='seeds per GPU per step (BASELINE configs[3]: 64/GPU)')
-    ap.add_argument('--micro-batch', type=int, default=16, help='seeds per pass through the network inside a step')
+    ap.add_argument('--micro-batch', type=int, default=64, help='seeds per pass through the network inside a step')
     ap.add_argument('--precision', default='x3p', choices=['x1', 'mixed', 'x3', 'x3p'])
     ap.add_argument('--lr', type=float, default=0.05, help='SGD learning rate (reference default 1.5 is tuned for trained weights; random-init nets diverge with it)')
     ap.add_argument('--cpu-sample', type=int, default=1, help='seeds per step of the CPU baseline sample')

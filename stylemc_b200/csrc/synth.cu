@@ -340,65 +340,78 @@ __global__ void __launch_bounds__(256) torgb1_kernel(const __half* __restrict__ 
     if (xs_hi) ld8f(s_next + n * sn_stride + c, sn);
   }
   const float bj = sub < 3 ? __ldg(b_rgb + sub) : 0.f;
-  float fk[16];
+  constexpr int U = 4;                                 // pixels in flight per lane (memory-level parallelism)
+  const int pstride = groups_per_warp * warps;
+  for (int pbase = p_begin + (threadIdx.x >> 5) * groups_per_warp; pbase < p_end; pbase += pstride * U) {
+    uint4 rh[U], rl[U];
+    bool live[U];
+    long long pix[U];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) fk[i] = img_prev ? __ldg(fk_up + i) : 0.f;
-  for (int pbase = p_begin + (threadIdx.x >> 5) * groups_per_warp; pbase < p_end; pbase += groups_per_warp * warps) {
-    const int p = pbase + lane / lpp;
-    const bool live = p < p_end;
-    const long long pix = (long long)n * hw + (live ? p : 0);
-    float v[8];
-    h8_to_f(ld_stream(x_hi + pix * C + c), v);
-    if (x_lo) {
-      float l[8];
-      h8_to_f(ld_stream(x_lo + pix * C + c), l);
+    for (int u = 0; u < U; ++u) {
+      const int p = pbase + u * pstride + lane / lpp;
+      live[u] = p < p_end;
+      pix[u] = (long long)n * hw + (live[u] ? p : p_begin);
+      rh[u] = ld_stream(x_hi + pix[u] * C + c);
+      rl[u] = x_lo ? ld_stream(x_lo + pix[u] * C + c) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pbase + u * pstride >= p_end) break;         // warp-uniform
+      const int p = pbase + u * pstride + lane / lpp;
+      float v[8], l[8];
+      h8_to_f(rh[u], v);
+      h8_to_f(rl[u], l);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += l[e];
-    }
-    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { r0 += m0[e] * v[e]; r1 += m1[e] * v[e]; r2 += m2[e] * v[e]; }
-    if (xs_hi && live) {
-      float o[8];
+      for (int e = 0; e < 8; ++e) { r0 += m0[e] * v[e]; r1 += m1[e] * v[e]; r2 += m2[e] * v[e]; }
+      if (xs_hi && live[u]) {
+        float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = v[e] * sn[e];
-      if (xs_lo) {
-        uint4 hi, lo;
-        f_to_h8_split(o, hi, lo);
-        st_stream(xs_hi + pix * C + c, hi);
-        st_stream(xs_lo + pix * C + c, lo);
-      } else {
-        st_stream(xs_hi + pix * C + c, f_to_h8(o));
-      }
-    }
-    for (int o = lpp >> 1; o > 0; o >>= 1) {
-      r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-      r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-    }
-    if (live && sub < 3) {
-      const int j = sub;
-      float r = (j == 0 ? r0 : (j == 1 ? r1 : r2)) + bj;
-      if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
-      const int yy = p / W, xq = p - yy * W;
-      if (img_prev) {
-        const int h2 = H >> 1, w2 = W >> 1;
-        const float* ip = img_prev + ((long long)n * 3 + j) * h2 * w2;
-        float u = 0.f;
-#pragma unroll
-        for (int fy = 0; fy < 4; ++fy) {
-          const int ay = yy + fy - 2;
-          if (ay < 0 || (ay & 1) || (ay >> 1) >= h2) continue;
-#pragma unroll
-          for (int fx = 0; fx < 4; ++fx) {
-            const int ax = xq + fx - 2;
-            if (ax < 0 || (ax & 1) || (ax >> 1) >= w2) continue;
-            u += fk[fy * 4 + fx] * __ldg(ip + (long long)(ay >> 1) * w2 + (ax >> 1));
-          }
+        for (int e = 0; e < 8; ++e) o[e] = v[e] * sn[e];
+        if (xs_lo) {
+          uint4 hi, lo;
+          f_to_h8_split(o, hi, lo);
+          st_stream(xs_hi + pix[u] * C + c, hi);
+          st_stream(xs_lo + pix[u] * C + c, lo);
+        } else {
+          st_stream(xs_hi + pix[u] * C + c, f_to_h8(o));
         }
-        r += u;
       }
-      img[(((long long)n * 3 + j) * H + yy) * W + xq] = r;
+      for (int o = lpp >> 1; o > 0; o >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      }
+      if (live[u] && sub < 3) {
+        const int j = sub;
+        float r = (j == 0 ? r0 : (j == 1 ? r1 : r2)) + bj;
+        if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
+        const int yy = p / W, xq = p - yy * W;
+        if (img_prev) {
+          // out[y, x] = sum fk[fy][fx] * xup[y + fy - 2, x + fx - 2]; xup is nonzero at even coordinates only, so just the two
+          // rows fy = (y & 1) + {0, 2} and the two columns fx = (x & 1) + {0, 2} contribute
+          const int h2 = H >> 1, w2 = W >> 1;
+          const float* ip = img_prev + ((long long)n * 3 + j) * h2 * w2;
+          const int fy0 = yy & 1, fx0 = xq & 1;
+          const int sy0 = (yy + fy0 - 2) >> 1, sx0 = (xq + fx0 - 2) >> 1;      // source row / column of the first tap (may be -1)
+          float uu = 0.f;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const int sy = sy0 + a;
+            if (sy < 0 || sy >= h2) continue;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int sx = sx0 + b;
+              if (sx < 0 || sx >= w2) continue;
+              uu += __ldg(fk_up + (fy0 + 2 * a) * 4 + fx0 + 2 * b) * __ldg(ip + (long long)sy * w2 + sx);
+            }
+          }
+          r += uu;
+        }
+        img[(((long long)n * 3 + j) * H + yy) * W + xq] = r;
+      }
     }
   }
 }
@@ -582,7 +595,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __half* __restrict__
 // group for the whole block, so every per-channel parameter (next style, ToRGB weights * style, demodulation, bias) lives in
 // registers and y is read exactly once per pixel (the ToRGB clamp mask is computed from the same registers).
 template <class TG>
-__global__ void __launch_bounds__(256) act_bwd1_kernel(const __half* __restrict__ y, const __half* __restrict__ y_lo, int N, int H, int W, int C,
+__global__ void __launch_bounds__(256, 2) act_bwd1_kernel(const __half* __restrict__ y, const __half* __restrict__ y_lo, int N, int H, int W, int C,
                                                        const TG* __restrict__ g_up, const float* __restrict__ s_next, long long sn_stride,
                                                        const float* __restrict__ g_img, const float* __restrict__ w_rgb,
                                                        const float* __restrict__ s_t, long long st_stride, float wgain,
@@ -627,75 +640,96 @@ __global__ void __launch_bounds__(256) act_bwd1_kernel(const __half* __restrict_
 #pragma unroll
   for (int e = 0; e < 8; ++e) { t1acc[e] = 0.f; racc[e] = 0.f; }
 
-  for (long long pbase = p_begin + (threadIdx.x >> 5) * groups_per_warp; pbase < p_end; pbase += (long long)groups_per_warp * warps) {
-    const long long p = pbase + lane / lpp;   // warp-uniform trip count: the shuffles below need all lanes
-    const bool live = p < p_end;
-    const long long pix = (long long)n * hw + (live ? p : 0);
-    float yv[8], gu[8];
-    h8_to_f(ld_stream(y + pix * C + c), yv);
-    if (y_lo) {
-      float l[8];
-      h8_to_f(ld_stream(y_lo + pix * C + c), l);
+  constexpr int U = 2;                                 // pixels in flight per lane (memory-level parallelism)
+  const long long pstride = (long long)groups_per_warp * warps;
+  for (long long pbase = p_begin + (threadIdx.x >> 5) * groups_per_warp; pbase < p_end; pbase += pstride * U) {
+    uint4 ryh[U], ryl[U], rg0[U], rg1[U];
+    float nzv[U], gim[U][3];
+    bool live[U];
+    long long pix[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) yv[e] += l[e];
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) gu[e] = 0.f;
-    if (g_up) {
-      if (sizeof(TG) == 2) h8_to_f(ld_stream(g_up + pix * C + c), gu);
-      else {
-        const uint4 a = ld_stream(reinterpret_cast<const float*>(g_up) + pix * C + c), b = ld_stream(reinterpret_cast<const float*>(g_up) + pix * C + c + 4);
-        gu[0] = __uint_as_float(a.x); gu[1] = __uint_as_float(a.y); gu[2] = __uint_as_float(a.z); gu[3] = __uint_as_float(a.w);
-        gu[4] = __uint_as_float(b.x); gu[5] = __uint_as_float(b.y); gu[6] = __uint_as_float(b.z); gu[7] = __uint_as_float(b.w);
-      }
-    }
-    float grgb[3] = {0.f, 0.f, 0.f};
-    if (g_img) {
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-      if (rgb_clamp >= 0.f) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { r0 += m0[e] * yv[e]; r1 += m1[e] * yv[e]; r2 += m2[e] * yv[e]; }
-        for (int o = lpp >> 1; o > 0; o >>= 1) {
-          r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-          r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-          r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    for (int u = 0; u < U; ++u) {
+      const long long p = pbase + u * pstride + lane / lpp;
+      live[u] = p < p_end;
+      const long long pp = live[u] ? p : p_begin;
+      pix[u] = (long long)n * hw + pp;
+      ryh[u] = ld_stream(y + pix[u] * C + c);
+      ryl[u] = y_lo ? ld_stream(y_lo + pix[u] * C + c) : make_uint4(0, 0, 0, 0);
+      rg0[u] = make_uint4(0, 0, 0, 0);
+      rg1[u] = make_uint4(0, 0, 0, 0);
+      if (g_up) {
+        if (sizeof(TG) == 2) rg0[u] = ld_stream(g_up + pix[u] * C + c);
+        else {
+          rg0[u] = ld_stream(reinterpret_cast<const float*>(g_up) + pix[u] * C + c);
+          rg1[u] = ld_stream(reinterpret_cast<const float*>(g_up) + pix[u] * C + c + 4);
         }
       }
-      if (live) {
+      nzv[u] = noise ? __ldg(noise + pp) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) gim[u][j] = g_img ? __ldg(g_img + ((long long)n * 3 + j) * hw + pp) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pbase + u * pstride >= p_end) break;         // warp-uniform: the shuffles below need all lanes
+      float yv[8], gu[8];
+      h8_to_f(ryh[u], yv);
+      {
+        float l[8];
+        h8_to_f(ryl[u], l);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] += l[e];
+      }
+      if (sizeof(TG) == 2) h8_to_f(rg0[u], gu);
+      else {
+        gu[0] = __uint_as_float(rg0[u].x); gu[1] = __uint_as_float(rg0[u].y); gu[2] = __uint_as_float(rg0[u].z); gu[3] = __uint_as_float(rg0[u].w);
+        gu[4] = __uint_as_float(rg1[u].x); gu[5] = __uint_as_float(rg1[u].y); gu[6] = __uint_as_float(rg1[u].z); gu[7] = __uint_as_float(rg1[u].w);
+      }
+      float grgb[3] = {0.f, 0.f, 0.f};
+      if (g_img) {
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        if (rgb_clamp >= 0.f) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { r0 += m0[e] * yv[e]; r1 += m1[e] * yv[e]; r2 += m2[e] * yv[e]; }
+          for (int o = lpp >> 1; o > 0; o >>= 1) {
+            r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+            r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+            r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+          }
+        }
         const float rr[3] = {r0 + b3[0], r1 + b3[1], r2 + b3[2]};
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const bool pass = (rgb_clamp < 0.f) || (rr[j] > -rgb_clamp && rr[j] < rgb_clamp);
-          grgb[j] = pass ? gscale * __ldg(g_img + ((long long)n * 3 + j) * hw + p) : 0.f;
+          grgb[j] = pass ? gscale * gim[u][j] : 0.f;
         }
       }
-    }
-    if (!live) continue;
-    const float nz = noise ? __ldg(noise + p) : 0.f;
-    float out[8];
+      if (!live[u]) continue;
+      const float nz = nzv[u];
+      float out[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float gy = gu[e] * sn[e] + (m0[e] * grgb[0] + m1[e] * grgb[1] + m2[e] * grgb[2]);
-      const float yy = yv[e];
-      const bool pass = (clamp < 0.f) || (yy > -clamp && yy < clamp);
-      const float slope = (yy > 0.f ? 1.f : alpha) * gain;
-      float gz = pass ? gy * slope : 0.f;
-      out[e] = gz * dc[e];
-      if (reduce && gd && !gd_lo) gz = __half2float(__float2half_rn(out[e])) / dc[e];
-      if (reduce) {
-        const float z = yy / slope;
-        racc[e] += gz * (z - nz - bs[e]);
-        t1acc[e] += gu[e] * yy;
+      for (int e = 0; e < 8; ++e) {
+        const float gy = gu[e] * sn[e] + (m0[e] * grgb[0] + m1[e] * grgb[1] + m2[e] * grgb[2]);
+        const float yy = yv[e];
+        const bool pass = (clamp < 0.f) || (yy > -clamp && yy < clamp);
+        const float slope = (yy > 0.f ? 1.f : alpha) * gain;
+        float gz = pass ? gy * slope : 0.f;
+        out[e] = gz * dc[e];
+        if (reduce && gd && !gd_lo) gz = __half2float(__float2half_rn(out[e])) / dc[e];
+        if (reduce) {
+          const float z = yy / slope;
+          racc[e] += gz * (z - nz - bs[e]);
+          t1acc[e] += gu[e] * yy;
+        }
       }
-    }
-    if (gd) {
-      if (gd_lo) {
-        uint4 hi, lo;
-        f_to_h8_split(out, hi, lo);
-        st_stream(gd + pix * C + c, hi);
-        st_stream(gd_lo + pix * C + c, lo);
-      } else {
-        st_stream(gd + pix * C + c, f_to_h8(out));
+      if (gd) {
+        if (gd_lo) {
+          uint4 hi, lo;
+          f_to_h8_split(out, hi, lo);
+          st_stream(gd + pix[u] * C + c, hi);
+          st_stream(gd_lo + pix[u] * C + c, lo);
+        } else {
+          st_stream(gd + pix[u] * C + c, f_to_h8(out));
+        }
       }
     }
   }
