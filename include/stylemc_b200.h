@@ -96,6 +96,11 @@ typedef struct smc_igemm_epilogue {
   int64_t o_sn, o_sh, o_sw;  // element strides of the output address for (n, h, w); channel stride 1
   int64_t o_off;             // element offset of (0, 0, 0, channel 0)
   float acc_scale;           // applied to the raw accumulator first (undoes a power-of-two pre-scaling of B); 0 means 1
+  // Fused ToRGB (halo-tile conv kernel only; the per-tap kernel returns SMC_EUNSUPPORTED when these are set):
+  void* out_raw_lo;          // fp16: rn(v - out_raw) of the value before post_scale (second plane of the saved activation)
+  const float* rgb_w;        // [n_img, 3, n_out] modulated ToRGB weights (w[j, c] * style[n, c] * weight_gain) or NULL
+  float* rgb_acc;            // fp32, atomically accumulated: rgb_acc[n * rgb_sn + j * rgb_sj + h * rgb_sh + w] += sum_c rgb_w * v
+  int64_t rgb_sn, rgb_sj, rgb_sh;
 } smc_igemm_epilogue;
 
 typedef struct smc_igemm_desc {
@@ -133,6 +138,9 @@ int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, 
 int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* noise,
                 const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
                 void* out_raw, void* out_raw_lo, void* out_hi, void* out_lo, void* stream);
+/* img[n, j, y, x] = clamp(img[n, j, y, x] + b[j]) + upsample2d(img_prev)[n, j, y, x]   (in place; img holds the fused-ToRGB sums of
+ * smc_igemm's rgb_acc; ToRGBLayer bias/clamp and utils.py:45-49; img_prev [N, 3, H/2, W/2] or NULL for the first block). */
+int smc_img_finish(float* img, const float* img_prev, const float* b_rgb, float clamp, const float* fk_up, int n, int h, int w, void* stream);
 int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w, int c, const float* w_rgb, const float* s_t,
               int64_t st_stride, float wgain, const float* b_rgb, float clamp, const float* img_prev, const float* fk_up,
               float* img, const float* s_next, int64_t sn_stride, void* xs_hi, void* xs_lo, void* stream);

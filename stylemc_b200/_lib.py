@@ -32,7 +32,9 @@ class Epilogue(ctypes.Structure):
                 ('residual', ctypes.c_void_p), ('out_f32', ctypes.c_void_p), ('out_hi', ctypes.c_void_p),
                 ('out_lo', ctypes.c_void_p), ('out_raw', ctypes.c_void_p),
                 ('o_sn', ctypes.c_int64), ('o_sh', ctypes.c_int64), ('o_sw', ctypes.c_int64), ('o_off', ctypes.c_int64),
-                ('acc_scale', ctypes.c_float)]
+                ('acc_scale', ctypes.c_float),
+                ('out_raw_lo', ctypes.c_void_p), ('rgb_w', ctypes.c_void_p), ('rgb_acc', ctypes.c_void_p),
+                ('rgb_sn', ctypes.c_int64), ('rgb_sj', ctypes.c_int64), ('rgb_sh', ctypes.c_int64)]
 
 
 class IgemmDesc(ctypes.Structure):
@@ -66,6 +68,7 @@ SIGNATURES = {
     'smc_pack_nhwc': 'p q p q pp iiii p',
     'smc_unpack_nchw': 'p i pp iiii p',
     'smc_fir_act': 'p i iiii ppp fff p q pppp p',
+    'smc_img_finish': 'ppp f p iii p',
     'smc_torgb': 'pp iiii pp q f p f ppp p q pp p',
     'smc_act_bwd': 'pp iiii p i p q ppp q f p f pppp fff pppp p',
     'smc_fir_bwd': 'pp iiii ppp p',

@@ -401,6 +401,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         const float* rs = e.row_scale ? e.row_scale + (long long)n * p.n_out + o0 : nullptr;
         const float* ps = e.post_scale ? e.post_scale + (long long)n * p.n_out + o0 : nullptr;
         const float* bs = e.bias ? e.bias + o0 : nullptr;
+        const float* rw = e.rgb_acc ? e.rgb_w + (long long)n * 3 * p.n_out + o0 : nullptr;
+        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 8) {
           float v[8];
@@ -416,11 +418,26 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             v[i] = x;
           }
           if (e.out_raw) {
-            const __half2 a0 = __floats2half2_rn(v[0], v[1]), a1 = __floats2half2_rn(v[2], v[3]);
-            const __half2 a2 = __floats2half2_rn(v[4], v[5]), a3 = __floats2half2_rn(v[6], v[7]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw) + opix + c0) =
-                make_uint4(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1),
-                           *reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&a3));
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const __half2 hh = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+              const float2 hf = __half22float2(hh);
+              const __half2 ll = __floats2half2_rn(v[2 * u] - hf.x, v[2 * u + 1] - hf.y);
+              hi[u] = *reinterpret_cast<const uint32_t*>(&hh);
+              lo[u] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw) + opix + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (e.out_raw_lo)
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw_lo) + opix + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          if (rw) {                                         // fused ToRGB: partial dot products over this thread's channels
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              rgb0 += __ldg(rw + c0 + i) * v[i];
+              rgb1 += __ldg(rw + p.n_out + c0 + i) * v[i];
+              rgb2 += __ldg(rw + 2 * p.n_out + c0 + i) * v[i];
+            }
           }
           if (ps) {
 #pragma unroll
@@ -451,6 +468,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             if (e.out_lo)
               *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_lo) + opix + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
+        }
+        if (rw) {
+          float* ra = e.rgb_acc + (long long)n * e.rgb_sn + (long long)h * e.rgb_sh + w;
+          atomicAdd(ra, rgb0);
+          atomicAdd(ra + e.rgb_sj, rgb1);
+          atomicAdd(ra + 2 * e.rgb_sj, rgb2);
         }
       }
     }
@@ -657,7 +680,8 @@ int hconv_try_launch(const smc_igemm_desc* d, cudaStream_t st) {
   p.a_box_bytes = (uint32_t)(p.RB * p.Wp) * (uint32_t)(KC * 2);
   p.a_buf_bytes = ((uint32_t)(p.RB * p.Wp + 8) * (uint32_t)(KC * 2) + 1023u) & ~1023u;
   p.epi = d->epi;
-  if (!p.epi.out_f32 && !p.epi.out_hi && !p.epi.out_raw) return SMC_EINVAL;
+  if (!p.epi.out_f32 && !p.epi.out_hi && !p.epi.out_raw && !p.epi.rgb_acc) return SMC_EINVAL;
+  if ((p.epi.rgb_acc != nullptr) != (p.epi.rgb_w != nullptr) || (p.epi.out_raw_lo && !p.epi.out_raw)) return SMC_EINVAL;
   if ((p.epi.o_sn | p.epi.o_sh | p.epi.o_sw | p.epi.o_off) & 7) return SMC_EUNSUPPORTED;
   const size_t smem = smem_fixed + (size_t)(p.na_hi + p.na_lo) * p.a_buf_bytes;
   if (smem > 227 * 1024) return SMC_EUNSUPPORTED;

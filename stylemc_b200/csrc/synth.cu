@@ -312,6 +312,42 @@ __global__ void __launch_bounds__(256) torgb_kernel(const __half* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Tail of the fused ToRGB path (the conv1 epilogue of hconv.cu accumulated the 1x1 modulated conv into img):
+// img = clamp(img + b[j]) + upsample2d(img_prev)   (ToRGBLayer bias_act(clamp) [UPSTREAM]; utils.py:45-49).
+__global__ void __launch_bounds__(256) img_finish_kernel(float* __restrict__ img, const float* __restrict__ img_prev, const float* __restrict__ b_rgb,
+                                                         float clamp, const float* __restrict__ fk_up, int N, int H, int W) {
+  const long long total = (long long)N * 3 * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int xq = (int)(idx % W);
+    const long long t = idx / W;
+    const int yy = (int)(t % H);
+    const long long nj = t / H;
+    float r = img[idx] + __ldg(b_rgb + (int)(nj % 3));
+    if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
+    if (img_prev) {
+      const int h2 = H >> 1, w2 = W >> 1;
+      const float* ip = img_prev + nj * h2 * w2;
+      const int fy0 = yy & 1, fx0 = xq & 1;
+      const int sy0 = (yy + fy0 - 2) >> 1, sx0 = (xq + fx0 - 2) >> 1;
+      float uu = 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int sy = sy0 + a;
+        if (sy < 0 || sy >= h2) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int sx = sx0 + b;
+          if (sx < 0 || sx >= w2) continue;
+          uu += __ldg(fk_up + (fy0 + 2 * a) * 4 + fx0 + 2 * b) * __ldg(ip + (long long)sy * w2 + sx);
+        }
+      }
+      r += uu;
+    }
+    img[idx] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // torgb_kernel for C <= 256 with C/8 a power of two: a block stays inside one image and a lane owns one channel group, so the
 // modulated ToRGB weights and the next block's styles sit in registers; x is streamed once.
 __global__ void __launch_bounds__(256) torgb1_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, int N, int H, int W, int C,
@@ -947,6 +983,15 @@ extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h,
   else
     fir_act_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)planes, n, h, w, c, fk, noise, bias, alpha, gain, clamp, post,
                                                                   post_stride, (__half*)out_raw, (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_img_finish(float* img, const float* img_prev, const float* b_rgb, float clamp, const float* fk_up, int n, int h, int w,
+                              void* stream) {
+  if (!img || !b_rgb || n < 1 || h < 1 || w < 1) return SMC_EINVAL;
+  if (img_prev && (!fk_up || (h & 1) || (w & 1))) return SMC_EINVAL;
+  img_finish_kernel<<<grid_for((long long)n * 3 * h * w, 256), 256, 0, (cudaStream_t)stream>>>(img, img_prev, b_rgb, clamp, fk_up, n, h, w);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

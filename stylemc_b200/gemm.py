@@ -34,7 +34,7 @@ def up2_dgrad_taps(n_img):
 def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=None, b_rows_per_tap=None,
           row_scale=None, post_scale=None, bias=None, noise=None, noise_strides=(0, 0), act=0, alpha=0.2, gain=1.0,
           clamp=-1.0, residual=None, out_f32=None, out_hi=None, out_lo=None, out_raw=None, out_strides=None, out_offset=0,
-          tile=None, acc_scale=1.0, acc_chunk_k=0):
+          tile=None, acc_scale=1.0, acc_chunk_k=0, out_raw_lo=None, rgb_w=None, rgb_acc=None):
     """Launch one implicit GEMM.
 
     A: fp16 tensor viewed as [NA, HA, WA, C] (NA includes the hi/lo planes stacked on the image axis).
@@ -77,6 +77,10 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
     e.o_sn, e.o_sh, e.o_sw = out_strides
     e.o_off = out_offset
     e.acc_scale = acc_scale
+    e.out_raw_lo, e.rgb_w, e.rgb_acc = _lib.ptr(out_raw_lo), _lib.ptr(rgb_w), _lib.ptr(rgb_acc)
+    if rgb_acc is not None:          # NCHW fp32 [n_img, 3, H, W]
+        assert rgb_acc.dtype == torch.float32 and rgb_acc.is_contiguous() and rgb_w is not None and rgb_w.is_contiguous()
+        e.rgb_sn, e.rgb_sj, e.rgb_sh = rgb_acc.stride(0), rgb_acc.stride(1), rgb_acc.stride(2)
     d.acc_chunk_k = acc_chunk_k
     with torch.cuda.device(A.device):
         if _lib.igemm_hook is not None:

@@ -17,6 +17,7 @@ Styles are applied to the activations (the reference's non-fused formulation, id
 checks fused vs non-fused), so the frozen weights are shared by the whole batch.
 """
 import math
+import os
 
 import torch
 
@@ -109,6 +110,7 @@ class SynthesisEngine:
         if precision not in ('x1', 'x3', 'mixed', 'x3p'):
             raise ValueError(precision)
         self.acc_k = 512 if precision == 'x3p' else 0
+        self.fuse_torgb = os.environ.get('STYLEMC_HCONV') != '0'      # the fused epilogue exists in hconv.cu only
         self.precision, self.x3_max_res = ('x3' if precision == 'x3p' else precision), x3_max_res
         # style row of (conv0, conv1, torgb) per block (utils.py:169-185)
         self.rows, r = [], 0
@@ -156,6 +158,30 @@ class SynthesisEngine:
                    noise_strides=(res, 1), act=1, alpha=LRELU_ALPHA, gain=L.gain, clamp=L.clamp,
                    out_hi=y[0], out_lo=y[1] if want_lo else None)
         return y
+
+    @staticmethod
+    def _fusable(L, res):
+        """conv1 layers that run on the halo-tile kernel (csrc/hconv.cu) with a single N tile (cout <= 128: every block from 256 px
+        up in config-f, where the bytes are) take ToRGB and the next style multiply in their epilogue.  With one N tile exactly two
+        threads add into each rgb value, so the atomic accumulation is order-independent (deterministic)."""
+        return res >= 32 and L.cin % 32 == 0 and L.cout % 32 == 0 and L.cout <= 128
+
+    def _conv1_fused(self, L, T, xs, d, noise, styles, rt, row_next, n, res, prec, two, keep_y, next_two):
+        """conv1 with everything that consumes its output fused into the GEMM epilogue: the saved activation y (hi/lo, only when
+        it is needed), xs_next = y * styles[:, row_next] for the next block's conv0, and the ToRGB 1x1 modulated conv accumulated
+        into a zeroed fp32 image (finished by smc_img_finish).  Returns (y or None, xs_next or None, rgb accumulator)."""
+        y = self._planes(n, res, res, L.cout, two) if keep_y else None
+        xn = self._planes(n, res, res, L.cout, next_two) if row_next is not None else None
+        post = styles[:, row_next, :L.cout].contiguous() if row_next is not None else None
+        rgb_w = ((styles[:, rt, :L.cout] * T.wgain).unsqueeze(1) * T.w.unsqueeze(0)).contiguous()        # [n, 3, C]
+        acc = torch.zeros([n, 3, res, res], dtype=torch.float32, device=self.device)
+        gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec, acc_chunk_k=self.acc_k,
+                   a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, bias=L.bias, noise=noise,
+                   noise_strides=(res, 1), act=1, alpha=LRELU_ALPHA, gain=L.gain, clamp=L.clamp,
+                   out_raw=y[0] if keep_y else None, out_raw_lo=y[1] if (keep_y and two) else None,
+                   post_scale=post, out_hi=xn[0] if xn is not None else None, out_lo=xn[1] if (xn is not None and next_two) else None,
+                   rgb_w=rgb_w, rgb_acc=acc)
+        return y, xn, acc
 
     def _conv0(self, L, xs, d, noise, styles, row_next, n, hin, prec, want_lo, save_lo=False):
         """3x3 transposed stride-2 modulated conv + 4x4 FIR + noise + bias + lrelu + clamp.
@@ -211,22 +237,30 @@ class SynthesisEngine:
                     if save:
                         saved.y0[k], saved.d0[k] = y0, d0
                 d1 = self._demod(L1, styles, r1, n)
-                y1 = self._conv1(L1, xs, d1, self._noise(L1, noise_mode, n), n, res, prec, two)
+                T = blk.torgb
+                has_next = k < last
+                nprec_two = has_next and self._prec(self.blocks[k + 1].resolution) == 'x3'
+                if self.fuse_torgb and self._fusable(L1, res):
+                    y1, xs_next, new_img = self._conv1_fused(L1, T, xs, d1, self._noise(L1, noise_mode, n), styles, rt,
+                                                             self.rows[k + 1][0] if has_next else None, n, res, prec, two,
+                                                             keep_y=save or want_xs, next_two=nprec_two)
+                    _lib.call('smc_img_finish', _lib.ptr(new_img), _lib.ptr(img), _lib.ptr(T.bias), T.clamp, _lib.ptr(self.fk4), n, res, res,
+                              _lib.stream())
+                    xs = xs_next
+                else:
+                    y1 = self._conv1(L1, xs, d1, self._noise(L1, noise_mode, n), n, res, prec, two)
+                    # ToRGB + skip + style multiply for the next block's conv0
+                    new_img = torch.empty([n, 3, res, res], dtype=torch.float32, device=self.device)
+                    if has_next:
+                        xs = self._planes(n, res, res, L1.cout, nprec_two)
+                        snp, sns = self._srow(styles, self.rows[k + 1][0])
+                    stp, sts = self._srow(styles, rt)
+                    _lib.call('smc_torgb', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if two else None, n, res, res, L1.cout, _lib.ptr(T.w), stp, sts,
+                              T.wgain, _lib.ptr(T.bias), T.clamp, _lib.ptr(img), _lib.ptr(self.fk4), _lib.ptr(new_img),
+                              snp if has_next else None, sns if has_next else 0, _lib.ptr(xs[0]) if has_next else None,
+                              _lib.ptr(xs[1]) if (has_next and xs.shape[0] == 2) else None, _lib.stream())
                 if save:
                     saved.y1[k], saved.d1[k] = y1, d1
-                # ToRGB + skip + style multiply for the next block's conv0
-                T = blk.torgb
-                new_img = torch.empty([n, 3, res, res], dtype=torch.float32, device=self.device)
-                has_next = k < last
-                if has_next:
-                    nprec = self._prec(self.blocks[k + 1].resolution)
-                    xs = self._planes(n, res, res, L1.cout, nprec == 'x3')
-                    snp, sns = self._srow(styles, self.rows[k + 1][0])
-                stp, sts = self._srow(styles, rt)
-                _lib.call('smc_torgb', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if two else None, n, res, res, L1.cout, _lib.ptr(T.w), stp, sts,
-                          T.wgain, _lib.ptr(T.bias), T.clamp, _lib.ptr(img), _lib.ptr(self.fk4), _lib.ptr(new_img),
-                          snp if has_next else None, sns if has_next else 0, _lib.ptr(xs[0]) if has_next else None,
-                          _lib.ptr(xs[1]) if (has_next and xs.shape[0] == 2) else None, _lib.stream())
                 img = new_img
                 if want_xs:
                     out = torch.empty([n, L1.cout, res, res], dtype=torch.float32, device=self.device)
