@@ -135,7 +135,9 @@ int smc_demod_coefs(const float* q, const float* s, int64_t s_stride, float* d, 
 int smc_pack_nhwc(const float* x, int64_t x_stride_n, const float* s, int64_t s_stride, void* hi, void* lo, int n, int c,
                   int hw, int c_pitch, void* stream);
 int smc_unpack_nchw(const void* x, int x_is_half, float* y, const float* noise, int n, int c, int hw, int c_pitch, void* stream);
-int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* noise,
+/* fsep_host: optional HOST pointer to 8 floats {fy[0..3], fx[0..3]} with fk[fy][fx] == fy[fy] * fx[fx] (separable filter, as the
+ * [1,3,3,1] resample filter is): selects the register-window kernels; NULL = generic 4x4 kernel. */
+int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* fsep_host, const float* noise,
                 const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
                 void* out_raw, void* out_raw_lo, void* out_hi, void* out_lo, void* stream);
 /* img[n, j, y, x] = clamp(img[n, j, y, x] + b[j]) + upsample2d(img_prev)[n, j, y, x]   (in place; img holds the fused-ToRGB sums of
@@ -149,8 +151,8 @@ int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w, int c, con
                 int64_t sn_stride, const float* g_img, const float* w_rgb, const float* s_t, int64_t st_stride, float wgain,
                 const float* b_rgb, float rgb_clamp, const float* gscale, const float* dcoef, const float* noise, const float* bias,
                 float alpha, float gain, float clamp, void* gd, void* gd_lo, float* t1, float* r, void* stream);
-int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int w, int c, const float* fk, void* planes, void* planes_lo,
-                void* stream);
+int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int w, int c, const float* fk, const float* fsep_host, void* planes,
+                void* planes_lo, void* stream);
 int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
                      const float* gscale, float* grad_row, int n, int cin, int cout, void* stream);
 int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_scratch, float* gscale, void* stream);

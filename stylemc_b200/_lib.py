@@ -67,11 +67,11 @@ SIGNATURES = {
     'smc_demod_coefs': 'pp q p iii p',
     'smc_pack_nhwc': 'p q p q pp iiii p',
     'smc_unpack_nchw': 'p i pp iiii p',
-    'smc_fir_act': 'p i iiii ppp fff p q pppp p',
+    'smc_fir_act': 'p i iiii pppp fff p q pppp p',
     'smc_img_finish': 'ppp f p iii p',
     'smc_torgb': 'pp iiii pp q f p f ppp p q pp p',
     'smc_act_bwd': 'pp iiii p i p q ppp q f p f pppp fff pppp p',
-    'smc_fir_bwd': 'pp iiii ppp p',
+    'smc_fir_bwd': 'pp iiii pppp p',
     'smc_sgrad_finish': 'ppppp q pp iii p',
     'smc_grad_scale': 'p q f pp p',
     'smc_resample_fwd': 'pppppp i iii i pp p',

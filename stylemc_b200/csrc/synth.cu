@@ -312,6 +312,214 @@ __global__ void __launch_bounds__(256) torgb_kernel(const __half* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------------
+// fir_act for a SEPARABLE 4x4 filter fk[fy][fx] = fyw[fy] * fxw[fx] (the [1,3,3,1] resample filter is) and fp32 planes.
+// One thread = one quad column x 4 channels, marching down JT quad rows with a 5-row window of horizontally filtered rows
+// in registers: every plane value is loaded once per thread (10 loads per 2x2 quad instead of 25) and the FIR costs
+// 8 + 8 FMAs per output instead of 16.
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  const uint4 u = ld_stream(p);
+  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
+__device__ __forceinline__ uint2 f4_to_h4(const float (&v)[4]) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ void f4_to_h4_split(const float (&v)[4], uint2& hi, uint2& lo) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  const __half2 la = __floats2half2_rn(v[0] - fa.x, v[1] - fa.y), lb = __floats2half2_rn(v[2] - fb.x, v[3] - fb.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+}
+
+template <int JT>
+__global__ void __launch_bounds__(256) fir_act2_kernel(const float* __restrict__ planes, int N, int H, int W, int C, float4 fyw, float4 fxw,
+                                                       const float* __restrict__ noise, const float* __restrict__ bias, float alpha, float gain,
+                                                       float clamp, const float* __restrict__ post, long long post_stride,
+                                                       __half* __restrict__ out_raw, __half* __restrict__ out_raw_lo,
+                                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int cg4 = C >> 2;
+  const int kcols = 256 / cg4;
+  const int g = threadIdx.x % cg4, kl = threadIdx.x / cg4;
+  const int k = blockIdx.x * kcols + kl;
+  if (kl >= kcols || k >= W) return;
+  const int c = g * 4;
+  const int n = blockIdx.z;
+  const int j0 = blockIdx.y * JT;
+  const int j1 = j0 + JT < H ? j0 + JT : H;
+  const long long plane_sz = (long long)N * (H + 1) * (W + 1) * C;
+  const float fy[4] = {fyw.x, fyw.y, fyw.z, fyw.w}, fx[4] = {fxw.x, fxw.y, fxw.z, fxw.w};
+  float bs[4], ps[4];
+  {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+    bs[0] = b4.x; bs[1] = b4.y; bs[2] = b4.z; bs[3] = b4.w;
+    ps[0] = ps[1] = ps[2] = ps[3] = 1.f;
+    if (post) {
+      const float4 p4 = __ldg(reinterpret_cast<const float4*>(post + n * post_stride + c));
+      ps[0] = p4.x; ps[1] = p4.y; ps[2] = p4.z; ps[3] = p4.w;
+    }
+  }
+  // horizontally filtered row ty of t for the two output columns 2k, 2k+1
+  auto hrow = [&](int ty, float (&h)[2][4]) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[b][e] = 0.f;
+    if (ty < 0 || ty > 2 * H) return;
+    const float* rowp = planes + (long long)((ty & 1) * 2) * plane_sz + ((long long)n * (H + 1) + (ty >> 1)) * (W + 1) * C + c;
+    float4 t[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int tx = 2 * k - 1 + i;
+      t[i] = (tx < 0 || tx > 2 * W) ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4_stream(rowp + (long long)(tx & 1) * plane_sz + (long long)(tx >> 1) * C);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        h[b][0] += fx[f] * t[b + f].x; h[b][1] += fx[f] * t[b + f].y; h[b][2] += fx[f] * t[b + f].z; h[b][3] += fx[f] * t[b + f].w;
+      }
+  };
+  float hw[5][2][4];
+  hrow(2 * j0 - 1, hw[0]);
+  hrow(2 * j0, hw[1]);
+  hrow(2 * j0 + 1, hw[2]);
+  for (int j = j0; j < j1; ++j) {
+    hrow(2 * j + 2, hw[3]);
+    hrow(2 * j + 3, hw[4]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int oy = 2 * j + a;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ox = 2 * k + b;
+        const float nz = noise ? __ldg(noise + (long long)oy * (2 * W) + ox) : 0.f;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float t = fy[0] * hw[a][b][e] + fy[1] * hw[a + 1][b][e] + fy[2] * hw[a + 2][b][e] + fy[3] * hw[a + 3][b][e];
+          t += nz + bs[e];
+          t = (t > 0.f ? t : t * alpha) * gain;
+          if (clamp >= 0.f) t = fminf(fmaxf(t, -clamp), clamp);
+          v[e] = t;
+        }
+        const long long o = (((long long)n * (2 * H) + oy) * (2 * W) + ox) * C + c;
+        if (out_raw) {
+          if (out_raw_lo) {
+            uint2 hi, lo;
+            f4_to_h4_split(v, hi, lo);
+            *reinterpret_cast<uint2*>(out_raw + o) = hi;
+            *reinterpret_cast<uint2*>(out_raw_lo + o) = lo;
+          } else {
+            *reinterpret_cast<uint2*>(out_raw + o) = f4_to_h4(v);
+          }
+        }
+        if (out_hi) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] *= ps[e];
+          if (out_lo) {
+            uint2 hi, lo;
+            f4_to_h4_split(v, hi, lo);
+            *reinterpret_cast<uint2*>(out_hi + o) = hi;
+            *reinterpret_cast<uint2*>(out_lo + o) = lo;
+          } else {
+            *reinterpret_cast<uint2*>(out_hi + o) = f4_to_h4(v);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { hw[0][b][e] = hw[2][b][e]; hw[1][b][e] = hw[3][b][e]; hw[2][b][e] = hw[4][b][e]; }
+  }
+}
+
+// Transposed FIR (fir_bwd) for a separable filter, same marching scheme: one thread = one cell column (t columns 2b, 2b+1) x
+// 4 channels, 5-row window of horizontally filtered gd rows.
+template <int JT>
+__global__ void __launch_bounds__(256) fir_bwd2_kernel(const __half* __restrict__ gd, const __half* __restrict__ gd_lo, int N, int H, int W, int C,
+                                                       float4 fyw, float4 fxw, __half* __restrict__ planes, __half* __restrict__ planes_lo) {
+  const int cg4 = C >> 2;
+  const int kcols = 256 / cg4;
+  const int g = threadIdx.x % cg4, kl = threadIdx.x / cg4;
+  const int b = blockIdx.x * kcols + kl;
+  if (kl >= kcols || b > W) return;
+  const int c = g * 4;
+  const int n = blockIdx.z;
+  const int a0 = blockIdx.y * JT;
+  const int a1 = a0 + JT < H + 1 ? a0 + JT : H + 1;
+  const long long plane_sz = (long long)N * (H + 1) * (W + 1) * C;
+  const float fy[4] = {fyw.x, fyw.y, fyw.z, fyw.w}, fx[4] = {fxw.x, fxw.y, fxw.z, fxw.w};
+  // gd row gy filtered horizontally for the two t columns 2b + q: h[q] = sum_wx fx[q + 3 - wx] * gd[gy][2b - 2 + wx]
+  auto hrow = [&](int gy, float (&h)[2][4]) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[q][e] = 0.f;
+    if (gy < 0 || gy >= 2 * H) return;
+    const long long rowo = (((long long)n * 2 * H + gy) * (2 * W)) * C + c;
+    float t[5][4];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int gx = 2 * b - 2 + i;
+      if (gx < 0 || gx >= 2 * W) {
+        t[i][0] = t[i][1] = t[i][2] = t[i][3] = 0.f;
+      } else {
+        const uint2 uh = __ldg(reinterpret_cast<const uint2*>(gd + rowo + (long long)gx * C));
+        const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&uh.x)), x1 = __half22float2(*reinterpret_cast<const __half2*>(&uh.y));
+        t[i][0] = x0.x; t[i][1] = x0.y; t[i][2] = x1.x; t[i][3] = x1.y;
+        if (gd_lo) {
+          const uint2 ul = __ldg(reinterpret_cast<const uint2*>(gd_lo + rowo + (long long)gx * C));
+          const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&ul.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&ul.y));
+          t[i][0] += l0.x; t[i][1] += l0.y; t[i][2] += l1.x; t[i][3] += l1.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int wx = q; wx < q + 4; ++wx)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[q][e] += fx[q + 3 - wx] * t[wx][e];
+  };
+  float hw[5][2][4];
+  hrow(2 * a0 - 2, hw[0]);
+  hrow(2 * a0 - 1, hw[1]);
+  hrow(2 * a0, hw[2]);
+  for (int a = a0; a < a1; ++a) {
+    hrow(2 * a + 1, hw[3]);
+    hrow(2 * a + 2, hw[4]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const bool inside = (2 * a + r <= 2 * H) && (2 * b + q <= 2 * W);
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // t row 2a + r reads gd rows gy = 2a - 2 + wy with fy = r + 3 - wy, wy in [r, r + 3]
+          const float v = fy[3] * hw[r][q][e] + fy[2] * hw[r + 1][q][e] + fy[1] * hw[r + 2][q][e] + fy[0] * hw[r + 3][q][e];
+          o[e] = inside ? v : 0.f;
+        }
+        const long long po = (long long)(r * 2 + q) * plane_sz + (((long long)n * (H + 1) + a) * (W + 1) + b) * C + c;
+        if (planes_lo) {
+          uint2 hi, lo;
+          f4_to_h4_split(o, hi, lo);
+          *reinterpret_cast<uint2*>(planes + po) = hi;
+          *reinterpret_cast<uint2*>(planes_lo + po) = lo;
+        } else {
+          *reinterpret_cast<uint2*>(planes + po) = f4_to_h4(o);
+        }
+      }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { hw[0][q][e] = hw[2][q][e]; hw[1][q][e] = hw[3][q][e]; hw[2][q][e] = hw[4][q][e]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Tail of the fused ToRGB path (the conv1 epilogue of hconv.cu accumulated the 1x1 modulated conv into img):
 // img = clamp(img + b[j]) + upsample2d(img_prev)   (ToRGBLayer bias_act(clamp) [UPSTREAM]; utils.py:45-49).
 __global__ void __launch_bounds__(256) img_finish_kernel(float* __restrict__ img, const float* __restrict__ img_prev, const float* __restrict__ b_rgb,
@@ -970,11 +1178,23 @@ extern "C" int smc_unpack_nchw(const void* x, int x_is_half, float* y, const flo
   return SMC_OK;
 }
 
-extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* noise,
-                           const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
+extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* fsep_host,
+                           const float* noise, const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
                            void* out_raw, void* out_raw_lo, void* out_hi, void* out_lo, void* stream) {
   if (!planes || !fk || !bias || n < 1 || h < 1 || w < 1 || c < 8 || (c & 7)) return SMC_EINVAL;
   if (!out_raw && !out_hi) return SMC_EINVAL;
+  if (fsep_host && !planes_is_half && c <= 1024) {       // separable filter: marching kernel
+    constexpr int JT = 16;
+    const float4 fyw = make_float4(fsep_host[0], fsep_host[1], fsep_host[2], fsep_host[3]);
+    const float4 fxw = make_float4(fsep_host[4], fsep_host[5], fsep_host[6], fsep_host[7]);
+    const int kcols = 256 / (c >> 2);
+    dim3 grid(ceil_div(w, kcols), ceil_div(h, JT), n);
+    if (grid.y > 65535 || grid.z > 65535) return SMC_ETOOLARGE;
+    fir_act2_kernel<JT><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)planes, n, h, w, c, fyw, fxw, noise, bias, alpha, gain, clamp, post,
+                                                                  post_stride, (__half*)out_raw, (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo);
+    SMC_LAUNCH_CHECK();
+    return SMC_OK;
+  }
   const long long items = (long long)n * h * w * (c >> 3);
   const int g = grid_for(items, 256);
   if (planes_is_half)
@@ -1065,9 +1285,21 @@ extern "C" int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w,
   return SMC_OK;
 }
 
-extern "C" int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int w, int c, const float* fk, void* planes, void* planes_lo,
-                           void* stream) {
+extern "C" int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int w, int c, const float* fk, const float* fsep_host,
+                           void* planes, void* planes_lo, void* stream) {
   if (!gd || !fk || !planes || n < 1 || h < 1 || w < 1 || c < 8 || (c & 7)) return SMC_EINVAL;
+  if (fsep_host && c <= 1024) {
+    constexpr int JT = 16;
+    const float4 fyw = make_float4(fsep_host[0], fsep_host[1], fsep_host[2], fsep_host[3]);
+    const float4 fxw = make_float4(fsep_host[4], fsep_host[5], fsep_host[6], fsep_host[7]);
+    const int kcols = 256 / (c >> 2);
+    dim3 grid(ceil_div(w + 1, kcols), ceil_div(h + 1, JT), n);
+    if (grid.y > 65535 || grid.z > 65535) return SMC_ETOOLARGE;
+    fir_bwd2_kernel<JT><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)gd, (const __half*)gd_lo, n, h, w, c, fyw, fxw, (__half*)planes,
+                                                                  (__half*)planes_lo);
+    SMC_LAUNCH_CHECK();
+    return SMC_OK;
+  }
   const long long items = (long long)n * (h + 1) * (w + 1) * (c >> 3);
   fir_bwd_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)gd, (const __half*)gd_lo, n, h, w, c, fk, (__half*)planes,
                                                                                     (__half*)planes_lo);

@@ -16,6 +16,7 @@ as a short chain of hand-written kernels over NHWC fp16 activations that never l
 Styles are applied to the activations (the reference's non-fused formulation, identical maths -- oracle/pin_reference.py
 checks fused vs non-fused), so the frozen weights are shared by the whole batch.
 """
+import ctypes
 import math
 import os
 
@@ -107,6 +108,12 @@ class SynthesisEngine:
         assert f.shape == (4, 4), 'the fused engine implements the 4x4 [1,3,3,1] resample filter'
         self.filter = f
         self.fk4 = (f.flip([0, 1]) * 4.0).contiguous()                 # flipped taps * gain (up=2 -> gain 4)
+        # separable? (the [1,3,3,1] filter is): host copy of the factors fk4[fy][fx] = fy[fy] * fx[fx] for the marching FIR kernels
+        fh = self.fk4.double().cpu()
+        rs, cs, tot = fh.sum(1), fh.sum(0), fh.sum()
+        self.fsep = None
+        if abs(float(tot)) > 1e-20 and float((torch.outer(rs, cs) / tot - fh).abs().max()) <= 1e-6 * float(fh.abs().max()):
+            self.fsep = (ctypes.c_float * 8)(*[float(v) for v in (rs / tot)], *[float(v) for v in cs])
         if precision not in ('x1', 'x3', 'mixed', 'x3p'):
             raise ValueError(precision)
         self.acc_k = 512 if precision == 'x3p' else 0
@@ -127,6 +134,9 @@ class SynthesisEngine:
         if self.precision == 'mixed':
             return 'x3' if res <= self.x3_max_res else 'x1'
         return self.precision
+
+    def _fsep_ptr(self):
+        return ctypes.addressof(self.fsep) if self.fsep is not None else None
 
     @staticmethod
     def _srow(styles, row):
@@ -194,11 +204,12 @@ class SynthesisEngine:
                 gemm.igemm(xs.reshape(-1, hin, hin, L.cin), L.B_fwd, n, hin + 1, hin + 1, L.cout, gemm.up2_parity_taps(r, c),
                            precision=prec, acc_chunk_k=self.acc_k, a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
         res = 2 * hin
-        y = self._planes(n, res, res, L.cout, x3 and save_lo)
+        y = self._planes(n, res, res, L.cout, x3) if save_lo else None     # the raw activation is only needed by the backward pass
         xn = self._planes(n, res, res, L.cout, want_lo)
         sp, ss = self._srow(styles, row_next)
-        _lib.call('smc_fir_act', _lib.ptr(planes), 0 if x3 else 1, n, hin, hin, L.cout, _lib.ptr(self.fk4), _lib.ptr(noise),
-                  _lib.ptr(L.bias), LRELU_ALPHA, L.gain, L.clamp, sp, ss, _lib.ptr(y[0]), _lib.ptr(y[1]) if y.shape[0] == 2 else None,
+        _lib.call('smc_fir_act', _lib.ptr(planes), 0 if x3 else 1, n, hin, hin, L.cout, _lib.ptr(self.fk4), self._fsep_ptr(), _lib.ptr(noise),
+                  _lib.ptr(L.bias), LRELU_ALPHA, L.gain, L.clamp, sp, ss, _lib.ptr(y[0]) if y is not None else None,
+                  _lib.ptr(y[1]) if (y is not None and y.shape[0] == 2) else None,
                   _lib.ptr(xn[0]), _lib.ptr(xn[1]) if want_lo else None, _lib.stream())
         return y, xn
 
@@ -357,7 +368,7 @@ class SynthesisEngine:
                           _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
                 hin = res // 2
                 gp = torch.empty([2 if two else 1, 4 * n, hin + 1, hin + 1, L0.cout], dtype=torch.float16, device=dev)
-                _lib.call('smc_fir_bwd', _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None, n, hin, hin, L0.cout, _lib.ptr(self.fk4),
+                _lib.call('smc_fir_bwd', _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None, n, hin, hin, L0.cout, _lib.ptr(self.fk4), self._fsep_ptr(),
                           _lib.ptr(gp[0]), _lib.ptr(gp[1]) if two else None, _lib.stream())
                 g_up = torch.empty([n, hin, hin, L0.cin], dtype=torch.float32 if two else torch.float16, device=dev)
                 gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=prec, acc_chunk_k=self.acc_k,

@@ -215,3 +215,61 @@ def one(c, o, r, n=16):
 
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'one':
     one(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+
+
+def small_res():
+    """x3p accuracy of the per-tap kernel at tiny spatial sizes (several images per 128-row tile)."""
+    for (n, c, o, r) in [(4, 512, 512, 4), (4, 512, 512, 8), (4, 512, 512, 16), (4, 512, 512, 32)]:
+        for kind in ('fwd', 'dgrad', 'up2dgrad', 'up2fwd'):
+            g = torch.Generator(device='cuda').manual_seed(5)
+            wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.05
+            if kind in ('fwd', 'dgrad'):
+                x = torch.randn(n, c if kind == 'fwd' else o, r, r, device='cuda', generator=g)
+                A = gemm.split_planes(x.permute(0, 2, 3, 1).contiguous(), True).reshape(-1, r, r, x.shape[1])
+                if kind == 'fwd':
+                    B = gemm.split_planes(wt.permute(2, 3, 0, 1).reshape(9 * o, c).contiguous(), True).reshape(-1, c)
+                    ref = F.conv2d(x.double(), wt.double(), padding=1).permute(0, 2, 3, 1)
+                    out = torch.empty(n, r, r, o, device='cuda')
+                    gemm.igemm(A, B, n, r, r, o, gemm.TAPS_3X3, precision='x3', acc_chunk_k=512, a_plane_stride_imgs=n, b_rows_per_tap=9 * o, out_f32=out)
+                else:
+                    B = gemm.split_planes(wt.permute(2, 3, 1, 0).reshape(9 * c, o).contiguous(), True).reshape(-1, o)
+                    xr = torch.zeros(n, c, r, r, device='cuda', dtype=torch.float64, requires_grad=True)
+                    F.conv2d(xr, wt.double(), padding=1).backward(x.double())
+                    ref = xr.grad.permute(0, 2, 3, 1)
+                    out = torch.empty(n, r, r, c, device='cuda')
+                    gemm.igemm(A, B, n, r, r, c, gemm.TAPS_3X3_DGRAD, precision='x3', acc_chunk_k=512, a_plane_stride_imgs=n, b_rows_per_tap=9 * c, out_f32=out)
+            elif kind == 'up2dgrad':
+                h = r
+                gy = torch.randn(n, o, 2 * h + 1, 2 * h + 1, device='cuda', generator=g)
+                gyl = F.pad(gy, (0, 1, 0, 1))
+                gp32 = torch.stack([gyl[:, :, rr::2, cc::2] for rr in (0, 1) for cc in (0, 1)])
+                gp = gemm.split_planes(gp32.permute(0, 1, 3, 4, 2).contiguous(), True)
+                B = gemm.split_planes(wt.permute(2, 3, 1, 0).reshape(9 * c, o).contiguous(), True).reshape(-1, o)
+                out = torch.empty(n, h, h, c, device='cuda')
+                gemm.igemm(gp.reshape(-1, h + 1, h + 1, o), B, n, h, h, c, gemm.up2_dgrad_taps(n), precision='x3', acc_chunk_k=512,
+                           a_plane_stride_imgs=4 * n, b_rows_per_tap=9 * c, out_f32=out)
+                xr = torch.zeros(n, c, h, h, device='cuda', dtype=torch.float64, requires_grad=True)
+                F.conv_transpose2d(xr, wt.double().transpose(0, 1), stride=2).backward(gy.double())
+                ref = xr.grad.permute(0, 2, 3, 1)
+            else:
+                h = r
+                x = torch.randn(n, c, h, h, device='cuda', generator=g)
+                A = gemm.split_planes(x.permute(0, 2, 3, 1).contiguous(), True).reshape(-1, h, h, c)
+                B = gemm.split_planes(wt.permute(2, 3, 0, 1).reshape(9 * o, c).contiguous(), True).reshape(-1, c)
+                pl = torch.zeros(4, n, h + 1, h + 1, o, device='cuda')
+                for rr in (0, 1):
+                    for cc in (0, 1):
+                        gemm.igemm(A, B, n, h + 1, h + 1, o, gemm.up2_parity_taps(rr, cc), precision='x3', acc_chunk_k=512, a_plane_stride_imgs=n,
+                                   b_rows_per_tap=9 * o, out_f32=pl[rr * 2 + cc])
+                t = torch.zeros(n, 2 * h + 2, 2 * h + 2, o, device='cuda', dtype=torch.float64)
+                for rr in (0, 1):
+                    for cc in (0, 1):
+                        t[:, rr::2, cc::2] = pl[rr * 2 + cc].double()
+                out = t[:, :2 * h + 1, :2 * h + 1]
+                ref = F.conv_transpose2d(x.double(), wt.double().transpose(0, 1), stride=2).permute(0, 2, 3, 1)
+            d = out.double() - ref
+            print(f'{kind} c{c} {r}x{r}: rms {(d.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item():.2e}  max {(d.abs().max() / ref.abs().max()).item():.2e}', flush=True)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'small':
+    small_res()
