@@ -520,8 +520,31 @@ static int hc_launch_x(bool x3, const CUtensorMap& ma, const CUtensorMap& mb, co
 }
 
 // Returns SMC_OK when launched, SMC_EUNSUPPORTED when the shape is left to igemm.cu.
+static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st);
+
+// A plain GEMM (one tap, H = 1, M = W rows) is folded into an (M / 64) x 64 "image" so that the same position tiling applies:
+// 256 consecutive rows per tile, no halo.
 int hconv_try_launch(const smc_igemm_desc* d, cudaStream_t st) {
   if (g_hconv_mode == 0) return SMC_EUNSUPPORTED;
+  if (d->H == 1 && d->n_img == 1 && d->HA == 1 && d->WA == d->W && (d->ntaps == 1 || d->ntaps == 3) && !d->epi.noise && !d->epi.rgb_acc &&
+      d->tw == 0 && (g_hconv_mask & 128) == 0) {
+    bool plain = true;
+    for (int i = 0; i < d->ntaps; ++i) plain = plain && d->taps[i].dy == 0 && d->taps[i].dx == 0;
+    int wf = 0;
+    for (int c = 64; c >= 16 && !wf; --c)
+      if (d->W % c == 0) wf = c;
+    if (plain && wf && d->W / wf >= 8 && (g_hconv_mode == 2 || d->W >= 1024)) {
+      smc_igemm_desc f = *d;
+      f.H = f.HA = d->W / wf;
+      f.W = f.WA = wf;
+      f.epi.o_sh = (int64_t)wf * d->epi.o_sw;
+      return hconv_try_launch_impl(&f, st);
+    }
+  }
+  return hconv_try_launch_impl(d, st);
+}
+
+static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   if (d->C % 32 != 0 || d->n_out % 32 != 0 || d->lda % 8 != 0 || d->ldb % 8 != 0) return SMC_EUNSUPPORTED;
   const int KC = d->C % 64 == 0 ? 64 : 32;
   if (d->tw > 0) return SMC_EUNSUPPORTED;          // caller pinned the igemm.cu tile shape
@@ -588,8 +611,12 @@ int hconv_try_launch(const smc_igemm_desc* d, cudaStream_t st) {
     int nh, nl;
     if (x3) {
       if (nmax < 3) continue;
-      nl = short_tiles ? (nmax / 2 > 4 ? 4 : nmax / 2) : 1;
-      nh = nmax - nl > (short_tiles ? 4 : 2) ? (short_tiles ? 4 : 2) : nmax - nl;
+      // short slabs (few taps): the lo buffer is only free during the short B_lo pass, so it needs a second buffer
+      const bool short_slabs = T * (KC / 16) < 16;
+      const int want_h = short_tiles ? 4 : (short_slabs ? 3 : 2), want_l = short_tiles ? 4 : (short_slabs ? 2 : 1);
+      nl = want_l < (nmax / 2 < 1 ? 1 : nmax / 2) ? want_l : (nmax / 2 < 1 ? 1 : nmax / 2);
+      nh = nmax - nl > want_h ? want_h : nmax - nl;
+      if (nh < 2) { nh = 2; nl = nmax - 2; }
     } else {
       if (nmax < 2) continue;
       nh = nmax > 4 ? 4 : nmax;

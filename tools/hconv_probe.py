@@ -273,3 +273,42 @@ def small_res():
 
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'small':
     small_res()
+
+
+def x1_vs_x3():
+    n = 16
+    for (c, o, r) in [(32, 32, 1024), (64, 64, 512), (64, 32, 512), (128, 128, 256)]:
+        for x3 in (True, False):
+            x, wt, run = conv_case(n, c, o, r, r, x3, acc_k=512 if x3 else 0)
+            cfg(0, 2)
+            ms = bench_one(run)
+            print(f'c{c} o{o} {r}x{r} x3={x3}: {ms:.3f} ms', flush=True)
+            del x, wt, run
+            torch.cuda.empty_cache()
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'x1x3':
+    x1_vs_x3()
+
+
+def gemm_probe():
+    for (m, k, nn) in [(6400, 768, 2304), (6400, 768, 768), (6400, 768, 3072), (6400, 3072, 768), (3200, 3072, 768), (1600, 768, 2304)]:
+        g = torch.Generator(device='cuda').manual_seed(1)
+        a = torch.randn(m, k, device='cuda', generator=g)
+        b = torch.randn(nn, k, device='cuda', generator=g) * 0.03
+        A = gemm.split_planes(a, True).view(2, 1, m, k)
+        B = gemm.split_planes(b * 64.0, True).view(2 * nn, k)
+        out = torch.empty(m, nn, device='cuda')
+        ref = a.double() @ b.double().t()
+        row = {}
+        for mode in (0, 1):
+            cfg(0, mode)
+            run = lambda: gemm.igemm(A, B, 1, 1, m, nn, gemm.TAPS_1X1, precision='x3', gain=1.0 / 64.0, acc_chunk_k=512, out_f32=out)
+            ms = bench_one(run, iters=10)
+            err = rel(out, ref)
+            row[mode] = f'{ms * 1e3:.0f} us ({2.0 * m * k * nn / ms / 1e9:.0f} TF/s alg) err {err:.1e}'
+        print(f'gemm {m}x{k}x{nn}: old {row[0]}   new {row[1]}', flush=True)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'gemm':
+    gemm_probe()
