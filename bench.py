@@ -67,6 +67,9 @@ def synth_flops_per_image(blocks, until_k):
     return total
 
 
+# DRAM bytes per launch of the dominant shape, from the committed ncu capture (key = n_img, H, W, Cin, Cout, taps); None when not captured
+TOP_KERNEL_DRAM_BYTES = {}
+
 VIT_FLOPS_FWD = 2 * (49 * 3072 * 768 + 12 * 50 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) + 12 * 12 * 2 * 50 * 50 * 64)   # per image
 
 
@@ -190,7 +193,7 @@ def run_ours(a):
         e0.record()
         yield
         e1.record()
-        records.append((e0, e1, 2.0 * d.n_img * d.H * d.W * d.n_out * d.C * alg_taps))
+        records.append((e0, e1, 2.0 * d.n_img * d.H * d.W * d.n_out * d.C * alg_taps, (d.n_img, d.H, d.W, d.C, d.n_out, alg_taps)))
 
     _lib.igemm_hook = hook
     t0 = torch.cuda.Event(enable_timing=True)
@@ -201,8 +204,13 @@ def run_ours(a):
     t1.record()
     torch.cuda.synchronize()
     _lib.igemm_hook = None
-    ig_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
-    ig_flops = sum(f for _, _, f in records)
+    ig_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in records)
+    ig_flops = sum(f for _, _, f, _ in records)
+    shapes = {}
+    for e0, e1, fl, key in records:
+        t = shapes.setdefault(key, [0.0, 0.0, 0])
+        t[0] += e0.elapsed_time(e1); t[1] += fl; t[2] += 1
+    top_key, top = max(shapes.items(), key=lambda kv: kv[1][0])
     step_ms_hooked = t0.elapsed_time(t1)
 
     if rank != 0:
@@ -215,6 +223,7 @@ def run_ours(a):
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
     achieved = ig_flops / (ig_ms / 1e3) / 1e12
+    mma_per_product = 1 if a.precision == 'x1' else 3
     out = {
         'metric': METRIC, 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': round(ms / a.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -228,9 +237,25 @@ def run_ours(a):
         'e2e': {'value': round(e2e, 3), 'unit': 'images/s', 'ms_per_step': round(ms_e2e / a.steps, 3),
                 'h2d_bytes_per_step': a.batch * 26 * 512 * 4, 'd2h_bytes_per_step': 4, 'losses': [round(v, 6) for v in losses]},
         'gpu_launches': launches,
-        'roofline': {'bound': 'tensor', 'kernel': 'igemm_kernel (tcgen05 implicit GEMM; all launches of one step)', 'achieved': round(achieved, 2),
-                     'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': round(achieved / pk['tflops'], 4), 'traffic': None,
-                     'peak_source': pk['src'], 'launches_per_step': len(records), 'share_of_step': round(ig_ms / step_ms_hooked, 3),
+        # dominant kernel = the smc_igemm shape with the largest summed time in one step (a conv on csrc/hconv.cu).  `achieved` counts
+        # ALGORITHMIC FLOPs (2 * pixels * taps * Cin * Cout per launch); in split precision every algorithmic product
+        # costs three fp16 MMAs, so the tensor pipe does mma_per_product x that work (tensor_pipe_*).
+        'roofline': {'bound': 'tensor',
+                     'kernel': f'hconv_kernel (tcgen05 halo-tile implicit GEMM), heaviest shape of the step: n={top_key[0]} {top_key[1]}x{top_key[2]} '
+                               f'Cin={top_key[3]} Cout={top_key[4]} taps={top_key[5]}',
+                     'achieved': round(top[1] / (top[0] / 1e3) / 1e12, 2), 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                     'frac': round(top[1] / (top[0] / 1e3) / 1e12 / pk['tflops'], 4),
+                     'launches_per_step': top[2], 'avg_launch_ms': round(top[0] / top[2], 4),
+                     'algorithmic_gflop_per_launch': round(top[1] / top[2] / 1e9, 2),
+                     'mma_per_product': mma_per_product,
+                     'tensor_pipe_achieved': round(mma_per_product * top[1] / (top[0] / 1e3) / 1e12, 2),
+                     'tensor_pipe_frac': round(mma_per_product * top[1] / (top[0] / 1e3) / 1e12 / pk['tflops'], 4),
+                     'traffic': TOP_KERNEL_DRAM_BYTES.get(top_key), 'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01c_top_kernel.md',
+                     'peak_source': pk['src'], 'share_of_step': round(top[0] / step_ms_hooked, 3),
+                     'family': {'kernel': 'every smc_igemm launch of one step (hconv_kernel + igemm_kernel: convs, dgrads, CLIP linears)',
+                                'achieved': round(achieved, 2), 'frac': round(achieved / pk['tflops'], 4),
+                                'tensor_pipe_frac': round(mma_per_product * achieved / pk['tflops'], 4),
+                                'launches_per_step': len(records), 'share_of_step': round(ig_ms / step_ms_hooked, 3)},
                      'algorithmic_gflop_per_image': round(alg_flops_img / 1e9, 1),
                      'step_algorithmic_tflops': round(alg_flops_img * a.batch / (ms / a.steps / 1e3) / 1e12, 2)},
     }

@@ -16,14 +16,15 @@ for r in rows:
     tot[n] += us(r); cnt[n] += 1
 T = sum(tot.values())
 out.write(f'# ncu launch list, one find_direction step (tag {tag})\n\n')
-out.write('Command: `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 1 --warmup 1 --batch 16 '
-          '--micro-batch 16 --no-cpu-baseline --profile-step` (one step = one micro-batch of 16 seeds at 1024 px, precision x3p).\n'
+B = os.environ.get('BATCH', '64')
+out.write(f'Command: `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 1 --warmup 1 --batch {B} '
+          f'--micro-batch {B} --no-cpu-baseline --profile-step` (tools/launch_profile.sh; one step of {B} seeds at 1024 px, precision x3p).\n'
           'Per-launch times are cold-cache and serialised: compare SHARES.\n\n')
 out.write(f'{len(rows)} launches, {T/1e3:.2f} ms summed device time\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n')
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
     out.write(f'| `{k[:90]}` | {cnt[k]} | {v:.1f} | {100*v/T:.1f}% |\n')
-ig = sum(v for k, v in tot.items() if 'igemm_kernel' in k)
-out.write(f'\nigemm_kernel family share of the step: {100*ig/T:.1f}% (bench.py roofline.share_of_step must agree).\n')
+ig = sum(v for k, v in tot.items() if 'igemm_kernel' in k or 'hconv_kernel' in k)
+out.write(f'\nsmc_igemm family (hconv_kernel + igemm_kernel) share of the step: {100*ig/T:.1f}% (bench.py roofline.family.share_of_step must agree).\n')
 out.close()
 os.system(f'cp gpurun_out/launches.csv profiles/{tag}_launches.csv')
 if rep:
