@@ -82,3 +82,39 @@ def test_three_step_trajectory_vs_oracle():
         print(f'it {it}: loss {out["loss"].item():.6f} / {r["loss"].item():.6f}  |delta| {delta.norm():.4f}  delta rel diff {d_rel:.2e}')
         assert abs(out['loss'].item() - r['loss'].item()) <= 1e-3 * abs(r['loss'].item())
         assert d_rel <= 2e-3
+
+
+def test_full_size_1024_properties():
+    """BASELINE configs[3] network (1024 px config-f) at full resolution, through size-independent properties -- the CPU oracle needs
+    minutes per image there.  (1) The step is invariant to how the seed batch is cut into micro-batches (the gradient is a sum over
+    seeds): 4 seeds in one pass vs 2 x 2.  (2) The two independent convolution kernels (halo-tile csrc/hconv.cu and per-tap
+    csrc/igemm.cu) produce the same image and the same gradient.  (3) generate_image at until_k truncation returns the running
+    skip image of the full pass (utils.py:169-173)."""
+    from stylemc_b200 import _lib, networks, utils
+    G = networks.make_generator(1024, seed=0)
+    ws = torch.randn(4, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(5))
+    S, shapes = utils.get_styles(G, ws, utils.split_ws(G, ws), 'cpu')
+    delta = 0.05 * torch.randn(1, 8, 512, generator=torch.Generator().manual_seed(6))
+    outs = {}
+    for tag, mb, mode in (('one pass', 4, 1), ('2 x 2', 2, 1), ('per-tap kernel', 4, 0)):
+        _lib.call('smc_igemm_config', 0, mode)
+        f = finder(G, 1024, micro_batch=mb)
+        f.engine.fuse_torgb = mode != 0                      # the fused ToRGB epilogue exists in hconv.cu only
+        f.delta.copy_(delta.cuda())
+        _, img, _ = f.engine.forward(S.cuda() + f.direction(), until_k=f.until_k)
+        out = f.step(S.cuda(), lr=0.0)
+        outs[tag] = (img.cpu(), out['loss'].item(), out['grad'].cpu())
+    _lib.call('smc_igemm_config', 0, 1)
+    img0, loss0, grad0 = outs['one pass']
+    assert img0.shape == (4, 3, 1024, 1024) and torch.isfinite(img0).all() and torch.isfinite(grad0).all()
+    for tag in ('2 x 2', 'per-tap kernel'):
+        img, loss, grad = outs[tag]
+        e_img = (img - img0).abs().max().item()
+        e_grad = ((grad - grad0).norm() / grad0.norm()).item()
+        print(f'{tag}: img max-abs diff {e_img:.2e}, loss diff {abs(loss - loss0):.2e}, grad rel-l2 diff {e_grad:.2e}')
+        assert e_img <= (1e-6 if tag == '2 x 2' else 1e-4)
+        assert abs(loss - loss0) <= 1e-5 * abs(loss0)
+        assert e_grad <= (1e-5 if tag == '2 x 2' else 2e-3)      # kernels differ in rounding: the lrelu-flip sensitivity of DESIGN.md section 5
+    f = finder(G, 1024, micro_batch=4)
+    _, img512, _ = f.engine.forward(S.cuda(), until_k=7)
+    assert img512.shape == (4, 3, 512, 512)

@@ -312,3 +312,44 @@ def gemm_probe():
 
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'gemm':
     gemm_probe()
+
+
+def epilogue_cost():
+    import math
+    n = 16
+    for (c, o, r) in [(128, 128, 256), (64, 64, 512), (32, 32, 1024)]:
+        g = torch.Generator(device='cuda').manual_seed(5)
+        x = torch.randn(n, c, r, r, device='cuda', generator=g)
+        wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.05
+        d = torch.rand(n, o, device='cuda', generator=g) + 0.5
+        ps = torch.rand(n, o, device='cuda', generator=g) + 0.5
+        bias = torch.randn(o, device='cuda', generator=g) * 0.1
+        noise = torch.randn(r, r, device='cuda', generator=g) * 0.1
+        rgb_w = torch.randn(n, 3, o, device='cuda', generator=g) * 0.1
+        A = gemm.split_planes(x.permute(0, 2, 3, 1).contiguous(), True).reshape(-1, r, r, c)
+        B = gemm.split_planes(wt.permute(2, 3, 0, 1).reshape(9 * o, c).contiguous(), True).reshape(-1, c)
+        del x
+        y = torch.zeros(2, n, r, r, o, device='cuda', dtype=torch.float16)
+        xs = torch.zeros(2, n, r, r, o, device='cuda', dtype=torch.float16)
+        o32 = torch.zeros(n, r, r, o, device='cuda')
+        acc = torch.zeros(n, 3, r, r, device='cuda')
+        base = dict(precision='x3', acc_chunk_k=512, a_plane_stride_imgs=n, b_rows_per_tap=9 * o)
+        act = dict(row_scale=d, bias=bias, noise=noise, noise_strides=(r, 1), act=1, alpha=0.2, gain=math.sqrt(2), clamp=256.0)
+        variants = {
+            'f32 only': dict(out_f32=o32),
+            'act + y(hi,lo)': dict(out_hi=y[0], out_lo=y[1], **act),
+            'act + xs(hi,lo) post': dict(out_hi=xs[0], out_lo=xs[1], post_scale=ps, **act),
+            'act + xs + rgb': dict(out_hi=xs[0], out_lo=xs[1], post_scale=ps, rgb_w=rgb_w, rgb_acc=acc, **act),
+            'act + y + xs + rgb (grad fwd)': dict(out_raw=y[0], out_raw_lo=y[1], out_hi=xs[0], out_lo=xs[1], post_scale=ps, rgb_w=rgb_w, rgb_acc=acc, **act),
+            'act + rgb only': dict(rgb_w=rgb_w, rgb_acc=acc, **act),
+        }
+        cfg(0, 2)
+        for name, kw in variants.items():
+            ms = bench_one(lambda: gemm.igemm(A, B, n, r, r, o, gemm.TAPS_3X3, **base, **kw))
+            print(f'c{c} {r}x{r} n{n} {name}: {ms:.3f} ms', flush=True)
+        del A, B, y, xs, o32, acc
+        torch.cuda.empty_cache()
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'epi':
+    epilogue_cost()
