@@ -98,15 +98,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 // one tap of one pass for both 128-row blocks: 2 * KC/16 MMAs; `first` = 0 makes the first MMA of each block overwrite
-template <int BN, int KC>
+// (BLK = TMEM column stride between the two blocks; the MMA's N is in idesc)
+template <int BLK, int KC>
 __device__ __forceinline__ void hc_issue_tap(uint32_t tm, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate_first) {
   constexpr uint32_t MBOFF = (uint32_t)(128 * KC * 2) >> 4;
 #pragma unroll
   for (int mb = 0; mb < HC_MB; ++mb) {
-    umma_f16(tm + (uint32_t)(mb * BN), HcDesc<KC>::make(alo + mb * MBOFF), HcDesc<KC>::make(blo), idesc, accumulate_first);
+    umma_f16(tm + (uint32_t)(mb * BLK), HcDesc<KC>::make(alo + mb * MBOFF), HcDesc<KC>::make(blo), idesc, accumulate_first);
 #pragma unroll
     for (int k = 1; k < KC / 16; ++k)
-      umma_f16_acc(tm + (uint32_t)(mb * BN), HcDesc<KC>::make(alo + mb * MBOFF + 2 * k), HcDesc<KC>::make(blo + 2 * k), idesc);
+      umma_f16_acc(tm + (uint32_t)(mb * BLK), HcDesc<KC>::make(alo + mb * MBOFF + 2 * k), HcDesc<KC>::make(blo + 2 * k), idesc);
   }
 }
 
@@ -132,19 +133,32 @@ __device__ __forceinline__ HcTile hc_tile(const HcParams& p, int t) {
 // the tensor core adds with truncation, igemm.cu); "cross" receives hi*lo and lo*hi, which are 2^-11 of the result, so its
 // chain may run over the whole tile.  main is drained while the B_lo pass (cross only) runs.  With BN <= 64 two sets fit and
 // alternate per tile; with BN = 128 there is one set and cross is drained while the next tile's first main MMAs wait.
-template <int BN, int KC, bool X3>
+// MODE 2 (x3, BN <= 64): with both operands in shared memory an MMA costs ~64 clk for its 128 x 16 A slab whatever N is, so narrow
+// layers are issue-bound on the NUMBER of MMAs.  There the stage of a tap holds [B_hi; B_lo] (2 BN rows) and ONE MMA of N = 2 BN
+// computes A_hi*B_hi (columns [0, BN) = main) and A_hi*B_lo (columns [BN, 2 BN) = cross) together; A_lo*B_hi is a second MMA of
+// N = BN into the cross columns: 2 MMAs per tap and k-step instead of 3.  Both halves are drained per chunk (the first MMA of a
+// chunk overwrites all 2 BN columns); two sets alternate per chunk.
+enum { HC_X1 = 0, HC_X3_TWO_PASS = 1, HC_X3_MERGED = 2 };
+template <int BN, int KC, int MODE>
 __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB,
                                                               const __grid_constant__ HcParams p) {
+  constexpr bool X3 = MODE != HC_X1;
+  constexpr bool TWO_PASS = MODE == HC_X3_TWO_PASS;
+  constexpr bool MERGED = MODE == HC_X3_MERGED;
   constexpr int ROWB = KC * 2;                                 // bytes per position row
-  constexpr int B_BYTES = BN * ROWB;
+  constexpr int B_TILE = BN * ROWB;                            // one weight tile (hi or lo plane of a tap)
+  constexpr int B_BYTES = (MERGED ? 2 : 1) * B_TILE;           // one ring stage
   constexpr int CW = BN / 2;                                   // accumulator columns per epilogue thread
-  constexpr int SETCOLS = (X3 ? 2 : 1) * HC_MB * BN;
+  constexpr int BLK = (MERGED ? 2 : 1) * BN;                   // TMEM columns of one 128-row block
+  constexpr int SETCOLS = (TWO_PASS ? 2 : 1) * HC_MB * BLK;
   constexpr int SETS = (2 * SETCOLS <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (SETS * SETCOLS) < 32 ? 32 : (SETS * SETCOLS);
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   constexpr int MAXB = 32;
-  static_assert(X3 || SETS == 2, "x1 alternates two sets per chunk");
+  static_assert(TWO_PASS || SETS == 2, "x1 / merged alternate two sets per chunk");
+  static_assert(!MERGED || BN <= 64, "merged B needs N = 2 BN <= 128 to pay off");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -234,12 +248,14 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int si = 0; si < p.nsegs; ++si) {
             const int tb = p.segs[si].tb, te = p.segs[si].te;
-            for (int pass = 0; pass < (X3 ? 2 : 1); ++pass) {
+            for (int pass = 0; pass < (TWO_PASS ? 2 : 1); ++pass) {
               for (int tp = tb; tp < te; ++tp) {
                 mbar_wait(&b_empty[bs], bph ^ 1u);
                 mbar_expect_tx(&b_full[bs], B_BYTES);
                 tma_load_2d(b_buf + (size_t)bs * B_BYTES, &mapB, &b_full[bs], kc * KC,
                             (pass == 0 ? p.taps[tp].brow_hi : p.taps[tp].brow_lo) + nt * BN);
+                if (MERGED)
+                  tma_load_2d(b_buf + (size_t)bs * B_BYTES + B_TILE, &mapB, &b_full[bs], kc * KC, p.taps[tp].brow_lo + nt * BN);
                 if (++bs == nb) { bs = 0; bph ^= 1u; }
               }
             }
@@ -262,7 +278,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
         const HcTile tl = hc_tile(p, t);
         const int rel0 = tl.q0 - tl.hfirst * p.Wp;         // position of tile row 0 inside the box (before the tap offset)
-        const uint32_t set_t = (X3 && SETS == 2) ? (tile_ctr & 1u) : 0u;
+        const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
         int in_chunk = 0;
         bool fresh = true;                                 // next main MMA starts an accumulation chunk (overwrites)
         bool fresh_cross = true;
@@ -272,6 +288,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
           int hb = 0, lb = 0;
           for (int si = 0; si < p.nsegs; ++si) {
             const int tb = p.segs[si].tb, te = p.segs[si].te, sflags = p.segs[si].flags;
+            // main chain complete after this segment's B_hi pass (mid-slab commit, or the slab-end commit of a chunk)
+            const bool main_done = (sflags & HC_SEG_COMMIT) && (!(sflags & HC_SEG_SLABEND) || chunk_ends);
             if (sflags & HC_SEG_FIRST) {
               hb = hi_buf(step);
               lb = lo_buf(step);
@@ -284,14 +302,14 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
               a_hi = a_base + (uint32_t)hb * p.a_buf_bytes + (uint32_t)rel0 * (uint32_t)ROWB;
               a_lo = a_base + (uint32_t)lb * p.a_buf_bytes + (uint32_t)rel0 * (uint32_t)ROWB;
             }
-            for (int pass = 0; pass < (X3 ? 2 : 1); ++pass) {
+            for (int pass = 0; pass < (TWO_PASS ? 2 : 1); ++pass) {
               for (int tp = tb; tp < te; ++tp) {
-                const uint32_t set = X3 ? set_t : (chunk_ctr & 1u);
+                const uint32_t set = TWO_PASS ? set_t : (chunk_ctr & 1u);
                 if (pass == 0 && fresh) {                  // this set's main accumulator must have been drained
                   const uint32_t nm = set ? nm1 : nm0;
                   if (nm >= 1) mbar_wait(&main_drained[set], (nm - 1u) & 1u);
                 }
-                if (X3 && fresh_cross) {
+                if (TWO_PASS && fresh_cross) {
                   const uint32_t nc = set_t ? nc1 : nc0;
                   if (nc >= 1) mbar_wait(&cross_drained[set_t], (nc - 1u) & 1u);
                 }
@@ -299,47 +317,46 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
                 tcgen05_fence_after();
                 const uint32_t blo = (b_base + bs * (uint32_t)B_BYTES) >> 4;
                 const uint32_t roff = (uint32_t)p.taps[tp].posoff * (uint32_t)ROWB;
-                {
-                  if (pass == 0) hc_issue_tap<BN, KC>(tmem_base + set * (uint32_t)SETCOLS, (a_hi + roff) >> 4, blo, IDESC, fresh ? 0u : 1u);
-                  if (X3)                                  // pass 0: A_lo * B_hi, pass 1: A_hi * B_lo -> cross
-                    hc_issue_tap<BN, KC>(tmem_base + set_t * (uint32_t)SETCOLS + (uint32_t)(HC_MB * BN),
-                                         ((pass == 0 ? a_lo : a_hi) + roff) >> 4, blo, IDESC, fresh_cross ? 0u : 1u);
-                  if (!resident) tcgen05_commit(&b_empty[bs]);
+                const uint32_t tm = tmem_base + set * (uint32_t)SETCOLS;
+                if (MERGED) {
+                  // A_hi * [B_hi; B_lo] -> (main | cross), then A_lo * B_hi -> cross
+                  hc_issue_tap<BLK, KC>(tm, (a_hi + roff) >> 4, blo, IDESC2, fresh ? 0u : 1u);
+                  hc_issue_tap<BLK, KC>(tm + (uint32_t)BN, (a_lo + roff) >> 4, blo, IDESC, 1u);
+                } else {
+                  if (pass == 0) hc_issue_tap<BLK, KC>(tm, (a_hi + roff) >> 4, blo, IDESC, fresh ? 0u : 1u);
+                  if (TWO_PASS)                            // pass 0: A_lo * B_hi, pass 1: A_hi * B_lo -> cross
+                    hc_issue_tap<BLK, KC>(tm + (uint32_t)(HC_MB * BN), ((pass == 0 ? a_lo : a_hi) + roff) >> 4, blo, IDESC, fresh_cross ? 0u : 1u);
                 }
+                if (!resident) tcgen05_commit(&b_empty[bs]);
                 if (pass == 0) fresh = false;
                 fresh_cross = false;
                 if (++bs == nb) { bs = 0; bph ^= 1u; }
               }
-              if (X3 && pass == 0) {
-                // main chain complete (mid-slab commit, or the slab-end commit of a chunk): drained while the B_lo pass runs
-                const bool main_done = (sflags & HC_SEG_COMMIT) && (!(sflags & HC_SEG_SLABEND) || chunk_ends);
+              if (TWO_PASS && pass == 0) {
                 if (sflags & HC_SEG_LAST) tcgen05_commit(&a_empty[lb]);   // the lo tile is only read by B_hi passes
-                if (main_done) tcgen05_commit(&main_full[set_t]);
-                if (main_done) {
+                if (main_done) {                                          // drained while the B_lo pass runs
+                  tcgen05_commit(&main_full[set_t]);
                   if (set_t) ++nm1; else ++nm0;
                   fresh = true;
                 }
               }
             }
-            if (sflags & HC_SEG_LAST) {
-              tcgen05_commit(&a_empty[hb]);
-              ++step;
-            }
-          }
-          if (chunk_ends) {
-            in_chunk = 0;
-            if (!X3) {
+            if (!TWO_PASS && main_done) {                  // x1 / merged: the two sets alternate per chunk
               const uint32_t set = chunk_ctr & 1u;
               tcgen05_commit(&main_full[set]);
               if (set) ++nm1; else ++nm0;
               ++chunk_ctr;
               fresh = true;
             }
-          } else {
-            ++in_chunk;
+            if (sflags & HC_SEG_LAST) {
+              if (MERGED) tcgen05_commit(&a_empty[lb]);
+              tcgen05_commit(&a_empty[hb]);
+              ++step;
+            }
           }
+          if (chunk_ends) in_chunk = 0; else ++in_chunk;
         }
-        if (X3) {
+        if (TWO_PASS) {
           tcgen05_commit(&cross_full[set_t]);
           if (set_t) ++nc1; else ++nc0;
         }
@@ -355,23 +372,23 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     const smc_igemm_epilogue& e = p.epi;
     const float acc_scale = e.acc_scale != 0.f ? e.acc_scale : 1.f;
     const int ndrains = p.ndrains;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BN + ch * CW);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BLK + ch * CW);
     uint32_t em0 = 0, em1 = 0, ec0 = 0, ec1 = 0, chunk_ctr = 0, tile_ctr = 0;
     float acc[CW];
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
       const HcTile tl = hc_tile(p, t);
-      const uint32_t set_t = (X3 && SETS == 2) ? (tile_ctr & 1u) : 0u;
+      const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
-      for (int dch = 0; dch < ndrains + (X3 ? 1 : 0); ++dch) {
-        const bool cross = X3 && dch == ndrains;
-        const uint32_t set = X3 ? set_t : (chunk_ctr & 1u);
+      for (int dch = 0; dch < ndrains + (TWO_PASS ? 1 : 0); ++dch) {
+        const bool cross = TWO_PASS && dch == ndrains;
+        const uint32_t set = TWO_PASS ? set_t : (chunk_ctr & 1u);
         uint64_t* full = cross ? &cross_full[set] : &main_full[set];
         uint64_t* drained = cross ? &cross_drained[set] : &main_drained[set];
         uint32_t cnt;
         if (cross) { cnt = set ? ec1 : ec0; if (set) ++ec1; else ++ec0; }
         else { cnt = set ? em1 : em0; if (set) ++em1; else ++em0; }
-        if (!X3) ++chunk_ctr;
+        if (!TWO_PASS) ++chunk_ctr;
         const uint32_t col = set * (uint32_t)SETCOLS + (cross ? (uint32_t)(HC_MB * BN) : 0u);
         mbar_wait(full, cnt & 1u);
         tcgen05_fence_after();
@@ -382,6 +399,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+          if (MERGED) {                                     // the cross half of the same block
+            tmem_ld16(lane_addr + col + (uint32_t)(BN + c0), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+          }
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -501,25 +524,28 @@ void hconv_config(int key, int value) {
   if (key == 5) g_hconv_mask = value;
 }
 
-template <int BN, int KC, bool X3>
+template <int BN, int KC, int MODE>
 static int hc_launch(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(hconv_kernel<BN, KC, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(hconv_kernel<BN, KC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  hconv_kernel<BN, KC, X3><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
+  hconv_kernel<BN, KC, MODE><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
 
 template <int BN, int KC>
-static int hc_launch_x(bool x3, const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
-  return x3 ? hc_launch<BN, KC, true>(ma, mb, p, grid, smem, st) : hc_launch<BN, KC, false>(ma, mb, p, grid, smem, st);
+static int hc_launch_x(int mode, const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
+  if (mode == HC_X1) return hc_launch<BN, KC, HC_X1>(ma, mb, p, grid, smem, st);
+  if constexpr (BN <= 64) {
+    if (mode == HC_X3_MERGED) return hc_launch<BN, KC, HC_X3_MERGED>(ma, mb, p, grid, smem, st);
+  }
+  return hc_launch<BN, KC, HC_X3_TWO_PASS>(ma, mb, p, grid, smem, st);
 }
 
-// Returns SMC_OK when launched, SMC_EUNSUPPORTED when the shape is left to igemm.cu.
 static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st);
 
 // A plain GEMM (one tap, H = 1, M = W rows) is folded into an (M / 64) x 64 "image" so that the same position tiling applies:
@@ -587,8 +613,9 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   const int padW = max_dx - min_dx, padH = max_dy - min_dy;
   // smem plan: weight stages (resident when a tile's whole weight set is small and there is one N tile), then the widest
   // tile whose A buffers fit (wider = fewer discarded halo positions, but more halo rows fetched per tile)
-  const int passes = x3 ? 2 : 1;
-  const int b_bytes = BN * KC * 2;
+  const int mode = !x3 ? HC_X1 : ((BN <= 64 && !(g_hconv_mask & 256)) ? HC_X3_MERGED : HC_X3_TWO_PASS);
+  const int passes = mode == HC_X3_TWO_PASS ? 2 : 1;
+  const int b_bytes = BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1);        // one ring stage
   const int stages_per_tile = (d->C / KC) * T * passes;
   p.b_resident = (d->n_out == BN && stages_per_tile <= 32 && stages_per_tile * b_bytes <= 96 * 1024) ? 1 : 0;
   if (p.b_resident) {
@@ -613,7 +640,9 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
       if (nmax < 3) continue;
       // short slabs (few taps): the lo buffer is only free during the short B_lo pass, so it needs a second buffer
       const bool short_slabs = T * (KC / 16) < 16;
-      const int want_h = short_tiles ? 4 : (short_slabs ? 3 : 2), want_l = short_tiles ? 4 : (short_slabs ? 2 : 1);
+      const int want_h = short_tiles ? 4 : (short_slabs ? 3 : 2);
+      // two-pass: the lo tile is released after the B_hi pass; merged: it lives as long as the hi tile
+      const int want_l = mode == HC_X3_MERGED ? want_h : (short_tiles ? 4 : (short_slabs ? 2 : 1));
       nl = want_l < (nmax / 2 < 1 ? 1 : nmax / 2) ? want_l : (nmax / 2 < 1 ? 1 : nmax / 2);
       nh = nmax - nl > want_h ? want_h : nmax - nl;
       if (nh < 2) { nh = 2; nl = nmax - 2; }
@@ -740,13 +769,13 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   const int max_grid = g_hconv_grid > 0 ? g_hconv_grid : kNumSMs;
   const int grid = p.total_tiles < max_grid ? (int)p.total_tiles : max_grid;
   if (KC == 64) {
-    if (BN == 128) return hc_launch_x<128, 64>(x3, ma, mb, p, grid, smem, st);
-    if (BN == 64) return hc_launch_x<64, 64>(x3, ma, mb, p, grid, smem, st);
-    return hc_launch_x<32, 64>(x3, ma, mb, p, grid, smem, st);
+    if (BN == 128) return hc_launch_x<128, 64>(mode, ma, mb, p, grid, smem, st);
+    if (BN == 64) return hc_launch_x<64, 64>(mode, ma, mb, p, grid, smem, st);
+    return hc_launch_x<32, 64>(mode, ma, mb, p, grid, smem, st);
   }
-  if (BN == 128) return hc_launch_x<128, 32>(x3, ma, mb, p, grid, smem, st);
-  if (BN == 64) return hc_launch_x<64, 32>(x3, ma, mb, p, grid, smem, st);
-  return hc_launch_x<32, 32>(x3, ma, mb, p, grid, smem, st);
+  if (BN == 128) return hc_launch_x<128, 32>(mode, ma, mb, p, grid, smem, st);
+  if (BN == 64) return hc_launch_x<64, 32>(mode, ma, mb, p, grid, smem, st);
+  return hc_launch_x<32, 32>(mode, ma, mb, p, grid, smem, st);
 }
 
 }  // namespace smc
