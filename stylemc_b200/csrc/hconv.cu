@@ -133,6 +133,77 @@ __device__ __forceinline__ HcTile hc_tile(const HcParams& p, int t) {
 // the tensor core adds with truncation, igemm.cu); "cross" receives hi*lo and lo*hi, which are 2^-11 of the result, so its
 // chain may run over the whole tile.  main is drained while the B_lo pass (cross only) runs.  With BN <= 64 two sets fit and
 // alternate per tile; with BN = 128 there is one set and cross is drained while the next tile's first main MMAs wait.
+// fp32 x8 -> fp16 hi (and lo = rn(v - hi)) 16-byte vectors
+__device__ __forceinline__ void hc_split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const __half2 hh = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(v[2 * u] - hf.x, v[2 * u + 1] - hf.y);
+    h[u] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[u] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void hc_ld8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// The modulated-conv epilogue (demodulation, noise, bias, leaky ReLU * gain, clamp all present) with the instruction count that
+// matters when a thread owns 64 channels of four output planes: vector parameter loads, one FMA for demod + noise + bias,
+// lrelu(x) * g = max(x g, x g alpha), and the hi/lo splits; the ToRGB partial sums ride along.
+template <int CW>
+__device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], const smc_igemm_epilogue& e, float acc_scale, float nz,
+                                                    const float* __restrict__ rs, const float* __restrict__ bs, const float* __restrict__ ps,
+                                                    const float* __restrict__ rw, int n_out, long long opix, float& rgb0, float& rgb1,
+                                                    float& rgb2) {
+  const float g = e.gain, ga = e.gain * e.alpha, cl = e.clamp;
+#pragma unroll
+  for (int c0 = 0; c0 < CW; c0 += 8) {
+    float v[8], r8[8], b8[8];
+    hc_ld8(rs + c0, r8);
+    hc_ld8(bs + c0, b8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = fmaf(acc[c0 + i], r8[i] * acc_scale, nz + b8[i]);
+      v[i] = fminf(fmaxf(fmaxf(x * g, x * ga), -cl), cl);
+    }
+    if (e.out_raw) {
+      uint4 hi, lo;
+      hc_split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw) + opix + c0) = hi;
+      if (e.out_raw_lo) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw_lo) + opix + c0) = lo;
+    }
+    if (rw) {
+      float w0[8], w1[8], w2[8];
+      hc_ld8(rw + c0, w0);
+      hc_ld8(rw + n_out + c0, w1);
+      hc_ld8(rw + 2 * n_out + c0, w2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rgb0 = fmaf(w0[i], v[i], rgb0);
+        rgb1 = fmaf(w1[i], v[i], rgb1);
+        rgb2 = fmaf(w2[i], v[i], rgb2);
+      }
+    }
+    if (e.out_hi) {
+      if (ps) {
+        float p8[8];
+        hc_ld8(ps + c0, p8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= p8[i];
+      }
+      uint4 hi, lo;
+      hc_split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_hi) + opix + c0) = hi;
+      if (e.out_lo) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_lo) + opix + c0) = lo;
+    }
+  }
+}
+
 // MODE 2 (x3, BN <= 64): with both operands in shared memory an MMA costs ~64 clk for its 128 x 16 A slab whatever N is, so narrow
 // layers are issue-bound on the NUMBER of MMAs.  There the stage of a tap holds [B_hi; B_lo] (2 BN rows) and ONE MMA of N = 2 BN
 // computes A_hi*B_hi (columns [0, BN) = main) and A_hi*B_lo (columns [BN, 2 BN) = cross) together; A_lo*B_hi is a second MMA of
@@ -426,6 +497,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         const float* bs = e.bias ? e.bias + o0 : nullptr;
         const float* rw = e.rgb_acc ? e.rgb_w + (long long)n * 3 * p.n_out + o0 : nullptr;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+        // modulated-conv layers (the bulk of the epilogue work): lean path; alpha < 1 makes max(x, alpha x) the leaky ReLU
+        const bool modconv = rs && bs && e.act == 1 && e.clamp >= 0.f && e.alpha >= 0.f && e.alpha <= 1.f && e.gain > 0.f && !e.residual && !e.out_f32 &&
+                             (((uintptr_t)rs | (uintptr_t)bs | (uintptr_t)ps | (uintptr_t)rw) & 15) == 0;
+        if (modconv) {
+          hc_epilogue_modconv<CW>(acc, e, acc_scale, nz, rs, bs, ps, rw, p.n_out, opix, rgb0, rgb1, rgb2);
+        } else {
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 8) {
           float v[8];
@@ -492,6 +569,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
               *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_lo) + opix + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
+        }   // generic epilogue
         if (rw) {
           float* ra = e.rgb_acc + (long long)n * e.rgb_sn + (long long)h * e.rgb_sh + w;
           atomicAdd(ra, rgb0);

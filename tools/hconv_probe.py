@@ -353,3 +353,30 @@ def epilogue_cost():
 
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'epi':
     epilogue_cost()
+
+
+def one_gradfwd(c, o, r, n=16):
+    import math
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn(n, c, r, r, device='cuda', generator=g)
+    wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.05
+    d = torch.rand(n, o, device='cuda', generator=g) + 0.5
+    ps = torch.rand(n, o, device='cuda', generator=g) + 0.5
+    bias = torch.randn(o, device='cuda', generator=g) * 0.1
+    noise = torch.randn(r, r, device='cuda', generator=g) * 0.1
+    rgb_w = torch.randn(n, 3, o, device='cuda', generator=g) * 0.1
+    A = gemm.split_planes(x.permute(0, 2, 3, 1).contiguous(), True).reshape(-1, r, r, c)
+    B = gemm.split_planes(wt.permute(2, 3, 0, 1).reshape(9 * o, c).contiguous(), True).reshape(-1, c)
+    y = torch.zeros(2, n, r, r, o, device='cuda', dtype=torch.float16)
+    xs = torch.zeros(2, n, r, r, o, device='cuda', dtype=torch.float16)
+    acc = torch.zeros(n, 3, r, r, device='cuda')
+    cfg(0, 2)
+    for _ in range(3):
+        gemm.igemm(A, B, n, r, r, o, gemm.TAPS_3X3, precision='x3', acc_chunk_k=512, a_plane_stride_imgs=n, b_rows_per_tap=9 * o,
+                   row_scale=d, bias=bias, noise=noise, noise_strides=(r, 1), act=1, alpha=0.2, gain=math.sqrt(2), clamp=256.0,
+                   out_raw=y[0], out_raw_lo=y[1], out_hi=xs[0], out_lo=xs[1], post_scale=ps, rgb_w=rgb_w, rgb_acc=acc)
+    torch.cuda.synchronize()
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'onegrad':
+    one_gradfwd(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
