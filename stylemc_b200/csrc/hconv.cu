@@ -152,54 +152,73 @@ __device__ __forceinline__ void hc_ld8(const float* p, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
+// 32-byte store (sm_100 256-bit vector store): one full sector per thread and instruction instead of two half-sector writes
+__device__ __forceinline__ void hc_st32(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w) : "memory");
+}
+
 // The modulated-conv epilogue (demodulation, noise, bias, leaky ReLU * gain, clamp all present) with the instruction count that
 // matters when a thread owns 64 channels of four output planes: vector parameter loads, one FMA for demod + noise + bias,
-// lrelu(x) * g = max(x g, x g alpha), and the hi/lo splits; the ToRGB partial sums ride along.
+// lrelu(x) * g = max(x g, x g alpha), the hi/lo splits and 32-byte stores; the ToRGB partial sums ride along.
 template <int CW>
 __device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], const smc_igemm_epilogue& e, float acc_scale, float nz,
                                                     const float* __restrict__ rs, const float* __restrict__ bs, const float* __restrict__ ps,
                                                     const float* __restrict__ rw, int n_out, long long opix, float& rgb0, float& rgb1,
                                                     float& rgb2) {
   const float g = e.gain, ga = e.gain * e.alpha, cl = e.clamp;
+  static_assert(CW % 16 == 0, "16 channels (32 bytes of fp16) per step");
 #pragma unroll
-  for (int c0 = 0; c0 < CW; c0 += 8) {
-    float v[8], r8[8], b8[8];
-    hc_ld8(rs + c0, r8);
-    hc_ld8(bs + c0, b8);
+  for (int c0 = 0; c0 < CW; c0 += 16) {
+    float v[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float x = fmaf(acc[c0 + i], r8[i] * acc_scale, nz + b8[i]);
-      v[i] = fminf(fmaxf(fmaxf(x * g, x * ga), -cl), cl);
-    }
-    if (e.out_raw) {
-      uint4 hi, lo;
-      hc_split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw) + opix + c0) = hi;
-      if (e.out_raw_lo) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_raw_lo) + opix + c0) = lo;
-    }
-    if (rw) {
-      float w0[8], w1[8], w2[8];
-      hc_ld8(rw + c0, w0);
-      hc_ld8(rw + n_out + c0, w1);
-      hc_ld8(rw + 2 * n_out + c0, w2);
+    for (int hh = 0; hh < 2; ++hh) {
+      float r8[8], b8[8];
+      hc_ld8(rs + c0 + 8 * hh, r8);
+      hc_ld8(bs + c0 + 8 * hh, b8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        rgb0 = fmaf(w0[i], v[i], rgb0);
-        rgb1 = fmaf(w1[i], v[i], rgb1);
-        rgb2 = fmaf(w2[i], v[i], rgb2);
+        const float x = fmaf(acc[c0 + 8 * hh + i], r8[i] * acc_scale, nz + b8[i]);
+        v[8 * hh + i] = fminf(fmaxf(fmaxf(x * g, x * ga), -cl), cl);
+      }
+    }
+    if (e.out_raw) {
+      uint4 h0, l0, h1, l1;
+      hc_split8(reinterpret_cast<const float(&)[8]>(v[0]), h0, l0);
+      hc_split8(reinterpret_cast<const float(&)[8]>(v[8]), h1, l1);
+      hc_st32(reinterpret_cast<__half*>(e.out_raw) + opix + c0, h0, h1);
+      if (e.out_raw_lo) hc_st32(reinterpret_cast<__half*>(e.out_raw_lo) + opix + c0, l0, l1);
+    }
+    if (rw) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float w0[8], w1[8], w2[8];
+        hc_ld8(rw + c0 + 8 * hh, w0);
+        hc_ld8(rw + n_out + c0 + 8 * hh, w1);
+        hc_ld8(rw + 2 * n_out + c0 + 8 * hh, w2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rgb0 = fmaf(w0[i], v[8 * hh + i], rgb0);
+          rgb1 = fmaf(w1[i], v[8 * hh + i], rgb1);
+          rgb2 = fmaf(w2[i], v[8 * hh + i], rgb2);
+        }
       }
     }
     if (e.out_hi) {
       if (ps) {
-        float p8[8];
-        hc_ld8(ps + c0, p8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= p8[i];
+        for (int hh = 0; hh < 2; ++hh) {
+          float p8[8];
+          hc_ld8(ps + c0 + 8 * hh, p8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[8 * hh + i] *= p8[i];
+        }
       }
-      uint4 hi, lo;
-      hc_split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_hi) + opix + c0) = hi;
-      if (e.out_lo) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out_lo) + opix + c0) = lo;
+      uint4 h0, l0, h1, l1;
+      hc_split8(reinterpret_cast<const float(&)[8]>(v[0]), h0, l0);
+      hc_split8(reinterpret_cast<const float(&)[8]>(v[8]), h1, l1);
+      hc_st32(reinterpret_cast<__half*>(e.out_hi) + opix + c0, h0, h1);
+      if (e.out_lo) hc_st32(reinterpret_cast<__half*>(e.out_lo) + opix + c0, l0, l1);
     }
   }
 }
@@ -497,9 +516,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         const float* bs = e.bias ? e.bias + o0 : nullptr;
         const float* rw = e.rgb_acc ? e.rgb_w + (long long)n * 3 * p.n_out + o0 : nullptr;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+        const bool f32_aligned32 = (((uintptr_t)e.out_f32) & 31) == 0;     // element offsets are multiples of 8 floats (checked on the host)
+        const bool out32 = ((((uintptr_t)e.out_raw | (uintptr_t)e.out_raw_lo | (uintptr_t)e.out_hi | (uintptr_t)e.out_lo) & 31) == 0) &&
+                           ((((e.o_sn | e.o_sh | e.o_sw | e.o_off) * 2) & 31) == 0) && (p.n_out % 16 == 0);
         // modulated-conv layers (the bulk of the epilogue work): lean path; alpha < 1 makes max(x, alpha x) the leaky ReLU
         const bool modconv = rs && bs && e.act == 1 && e.clamp >= 0.f && e.alpha >= 0.f && e.alpha <= 1.f && e.gain > 0.f && !e.residual && !e.out_f32 &&
-                             (((uintptr_t)rs | (uintptr_t)bs | (uintptr_t)ps | (uintptr_t)rw) & 15) == 0;
+                             (((uintptr_t)rs | (uintptr_t)bs | (uintptr_t)ps | (uintptr_t)rw) & 15) == 0 && out32;
         if (modconv) {
           hc_epilogue_modconv<CW>(acc, e, acc_scale, nz, rs, bs, ps, rw, p.n_out, opix, rgb0, rgb1, rgb2);
         } else {
@@ -550,9 +572,14 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
           }
           if (e.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(e.out_f32 + opix + c0);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            if (f32_aligned32) {
+              hc_st32(e.out_f32 + opix + c0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                      make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+            } else {
+              float4* dst = reinterpret_cast<float4*>(e.out_f32 + opix + c0);
+              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
           }
           if (e.out_hi) {
             uint32_t hi[4], lo[4];
