@@ -117,6 +117,7 @@ class SynthesisEngine:
         if precision not in ('x1', 'x3', 'mixed', 'x3p'):
             raise ValueError(precision)
         self.acc_k = 512 if precision == 'x3p' else 0
+        self.acc_k_lowres, self.acc_k_lowres_max = 64, 16
         self.fuse_torgb = os.environ.get('STYLEMC_HCONV') != '0'      # the fused epilogue exists in hconv.cu only
         self.precision, self.x3_max_res = ('x3' if precision == 'x3p' else precision), x3_max_res
         # style row of (conv0, conv1, torgb) per block (utils.py:169-185)
@@ -134,6 +135,15 @@ class SynthesisEngine:
         if self.precision == 'mixed':
             return 'x3' if res <= self.x3_max_res else 'x1'
         return self.precision
+
+    def _acc_k(self, res):
+        """K elements per main accumulation chain of a FORWARD conv whose output is res x res.  A leaky-ReLU unit whose pre-activation
+        lies within the forward rounding error of zero takes the wrong slope in the backward pass; at low resolution one such unit
+        moves the style gradient by ~1e-3, and the low-resolution layers cost next to nothing, so they get
+        chains of 4 MMAs (64 K elements): forward error ~1e-7, like the fp32 reference."""
+        if self.acc_k and res <= self.acc_k_lowres_max:
+            return self.acc_k_lowres
+        return self.acc_k
 
     def _fsep_ptr(self):
         return ctypes.addressof(self.fsep) if self.fsep is not None else None
@@ -163,7 +173,7 @@ class SynthesisEngine:
     def _conv1(self, L, xs, d, noise, n, res, prec, want_lo):
         """3x3 modulated conv + noise + bias + lrelu + clamp; returns y planes [P, n, res, res, cout]."""
         y = self._planes(n, res, res, L.cout, want_lo)
-        gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec, acc_chunk_k=self.acc_k,
+        gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec, acc_chunk_k=self._acc_k(res),
                    a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, bias=L.bias, noise=noise,
                    noise_strides=(res, 1), act=1, alpha=LRELU_ALPHA, gain=L.gain, clamp=L.clamp,
                    out_hi=y[0], out_lo=y[1] if want_lo else None)
@@ -185,7 +195,7 @@ class SynthesisEngine:
         post = styles[:, row_next, :L.cout].contiguous() if row_next is not None else None
         rgb_w = ((styles[:, rt, :L.cout] * T.wgain).unsqueeze(1) * T.w.unsqueeze(0)).contiguous()        # [n, 3, C]
         acc = torch.zeros([n, 3, res, res], dtype=torch.float32, device=self.device)
-        gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec, acc_chunk_k=self.acc_k,
+        gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec, acc_chunk_k=self._acc_k(res),
                    a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, bias=L.bias, noise=noise,
                    noise_strides=(res, 1), act=1, alpha=LRELU_ALPHA, gain=L.gain, clamp=L.clamp,
                    out_raw=y[0] if keep_y else None, out_raw_lo=y[1] if (keep_y and two) else None,
@@ -202,7 +212,7 @@ class SynthesisEngine:
             for c in (0, 1):
                 kw = dict(out_f32=planes[r * 2 + c]) if x3 else dict(out_raw=planes[r * 2 + c])
                 gemm.igemm(xs.reshape(-1, hin, hin, L.cin), L.B_fwd, n, hin + 1, hin + 1, L.cout, gemm.up2_parity_taps(r, c),
-                           precision=prec, acc_chunk_k=self.acc_k, a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
+                           precision=prec, acc_chunk_k=self._acc_k(2 * hin), a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
         res = 2 * hin
         y = self._planes(n, res, res, L.cout, x3) if save_lo else None     # the raw activation is only needed by the backward pass
         xn = self._planes(n, res, res, L.cout, want_lo)

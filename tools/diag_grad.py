@@ -67,3 +67,11 @@ for acc_k in (512, 256, 128):
         gr = eng.backward(sv, g_img_ref.cuda(), f.rows, 'const', grad_scale_target=tgt).cpu()
         print(f'acc_k {acc_k} gscale target {tgt}: total {rel(gr, grad_ref):.3e}  rows ' + ' '.join(f'{rel(gr[i], grad_ref[i]):.2e}' for i in range(len(rows))))
 eng.acc_k = 512
+
+print('--- low-resolution chain length (forward convs) ---')
+for lowmax in (0, 16, 32, 64):
+    for lowk in (64, 128):
+        eng.acc_k_lowres, eng.acc_k_lowres_max = lowk, lowmax
+        _, _, sv = eng.forward(s2, f.until_k, 'const', save=True)
+        gr = eng.backward(sv, g_img_ref.cuda(), f.rows, 'const').cpu()
+        print(f'lowres<= {lowmax} acc_k {lowk}: total {rel(gr, grad_ref):.3e}  rows ' + ' '.join(f'{rel(gr[i], grad_ref[i]):.2e}' for i in range(len(rows))))
