@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--lr', type=float, default=0.05, help='SGD learning rate (reference default 1.5 is tuned for trained weights; random-init nets diverge with it)')
     ap.add_argument('--cpu-sample', type=int, default=1, help='seeds per step of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='find_direction', choices=['find_direction', 'generate_fromS'],
+                    help="generate_fromS: forward-only render (BASELINE configs[1], batch 32 at 1024 px); not the headline metric")
     ap.add_argument('--profile-step', action='store_true', help='run warm-up, then ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     return ap.parse_args()
 
@@ -306,9 +308,41 @@ def run_reference(a):
     print(json.dumps(out), flush=True)
 
 
+def run_generate(a):
+    """BASELINE configs[1]: generate_fromS forward-only synthesis from S at 1024 px, batch 32, one B200, no CLIP.  A step renders the
+    original and the edited image of 32 style vectors (generate_fromS.py:137-207) into the uint8 canvas; images/s counts both."""
+    from stylemc_b200 import generate, networks, utils
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    batch = 32
+    G = networks.make_generator(a.resolution, seed=0)
+    ws = torch.randn(batch, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(1000))
+    styles, _ = utils.get_styles(G, ws, utils.split_ws(G, ws), 'cpu')
+    direction = torch.zeros(1, 26, 512)
+    direction[:, [2, 3, 5, 6, 8, 9, 11, 12]] = 0.1 * torch.randn(1, 8, 512, generator=torch.Generator().manual_seed(7))
+    styles_dev = styles.to(dev)
+    for _ in range(a.warmup):
+        generate.generate_fromS(G, styles_dev, direction, 1.0, device=dev, precision=a.precision)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        out = generate.generate_fromS(G, styles_dev, direction, 1.0, device=dev, precision=a.precision)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({'metric': 'generate_fromS forward-only synthesis images/sec @1024px', 'value': round(2 * batch * a.steps / (ms / 1e3), 2),
+                      'unit': 'images/s', 'n_gpus': 1, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': round(ms / a.steps, 3),
+                      'higher_is_better': True, 'dtype': 'f16x3 operands (hi+lo split), f32 accumulate', 'data': 'synthetic',
+                      'config': {'workload': f'generate_fromS {a.resolution}px, 32 styles per step, original + edited -> uint8 canvas (BASELINE configs[1])',
+                                 'precision': a.precision}, 'canvas_shape': list(out.shape)}), flush=True)
+
+
 if __name__ == '__main__':
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'generate_fromS':
+        run_generate(args)
     else:
         run_ours(args)

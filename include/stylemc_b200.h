@@ -186,6 +186,11 @@ int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln, int b, in
 int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
                   float inv_count, float* gscale_out, float gscale_target, void* stream);
 
+/* ---- generate_fromS output stage ---------------------------------------------------------------
+ * out[n, y, x_off + x, j] = uint8(clamp(img[n, j, y, x] * 127.5 + 128, 0, 255))   (generate_fromS.py:174-175; canvas [N, H, canvas_w, 3],
+ * the reference concatenates original | edited along the width, :206). */
+int smc_img_to_uint8(const float* img, unsigned char* out, int n, int h, int w, int canvas_w, int x_off, void* stream);
+
 /* ---- optimiser -----------------------------------------------------------------------------------
  * delta -= lr * (grad * grad_scale + l2_scale * delta)   (SGD, no momentum; L2 term of find_direction.py:190-191) */
 int smc_sgd_step(float* delta, const float* grad, int64_t numel, float lr, float grad_scale, float l2_scale, void* stream);
