@@ -124,7 +124,8 @@ int smc_igemm(const smc_igemm_desc* desc, void* stream);
 /* Tuning / diagnostics knobs of the convolution path (process-global; set before launching, not thread-safe):
  *   key 0: halo-tile kernel (hconv.cu) use: 0 never, 1 auto (default), 2 whenever the shape is supported
  *   key 2: weight-stage ring depth (0 = by stage size)   key 3: tile width Wt in pixels (0 = widest that fits, <= 64)
- *   key 4: persistent grid size (0 = one CTA per SM)      key 5: bit mask of conv kinds routed to hconv.cu (diagnostics) */
+ *   key 4: persistent grid size (0 = one CTA per SM)      key 5: bit mask of conv kinds routed to hconv.cu (diagnostics)
+ *   key 6: smallest H * W the auto mode routes to hconv.cu (default 64) */
 int smc_igemm_config(int key, int value);
 
 /* ---- synthesis glue (synth.cu) -------------------------------------------------------------------

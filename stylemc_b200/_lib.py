@@ -111,7 +111,7 @@ def lib():
         if handle.smc_abi_version() != 1:
             raise RuntimeError('libstylemc_b200.so ABI version mismatch; rebuild')
         _lib = handle
-        for key, env in ((0, 'STYLEMC_HCONV'), (2, 'STYLEMC_HCONV_NB'), (3, 'STYLEMC_HCONV_WT'), (4, 'STYLEMC_HCONV_GRID'), (5, 'STYLEMC_HCONV_MASK')):
+        for key, env in ((0, 'STYLEMC_HCONV'), (2, 'STYLEMC_HCONV_NB'), (3, 'STYLEMC_HCONV_WT'), (4, 'STYLEMC_HCONV_GRID'), (5, 'STYLEMC_HCONV_MASK'), (6, 'STYLEMC_HCONV_MINPOS')):
             if os.environ.get(env):          # diagnostics only: A/B the halo-tile conv kernel against the per-tap kernel
                 handle.smc_igemm_config(key, int(os.environ[env]))
     return _lib

@@ -619,6 +619,7 @@ static int g_hconv_mode = 1;          // 0: never use this kernel, 1: auto, 2: u
 static int g_hconv_nb = 0;   // 0: by stage size
 static int g_hconv_wt = 0;   // 0: widest that fits (<= 64)
 static int g_hconv_grid = 0;
+static int g_hconv_minpos = 64;     // auto mode: smallest H * W routed to this kernel
 static int g_hconv_mask = 7;   // bit 0: single-source convs with > 4 taps, bit 1: <= 4 taps, bit 2: multi-source (up2 dgrad)
 
 void hconv_config(int key, int value) {
@@ -627,6 +628,7 @@ void hconv_config(int key, int value) {
   if (key == 3) g_hconv_wt = value;
   if (key == 4) g_hconv_grid = value;
   if (key == 5) g_hconv_mask = value;
+  if (key == 6) g_hconv_minpos = value;
 }
 
 template <int BN, int KC, int MODE>
@@ -679,7 +681,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   if (d->C % 32 != 0 || d->n_out % 32 != 0 || d->lda % 8 != 0 || d->ldb % 8 != 0) return SMC_EUNSUPPORTED;
   const int KC = d->C % 64 == 0 ? 64 : 32;
   if (d->tw > 0) return SMC_EUNSUPPORTED;          // caller pinned the igemm.cu tile shape
-  if (g_hconv_mode == 1 && ((long long)d->H * d->W < 1024 || d->H < 8)) return SMC_EUNSUPPORTED;
+  if (g_hconv_mode == 1 && ((long long)d->H * d->W < g_hconv_minpos || d->H < 8)) return SMC_EUNSUPPORTED;
   const int BN = d->n_out % 128 == 0 ? 128 : (d->n_out % 64 == 0 ? 64 : 32);
 
   // split-precision pattern of gemm.igemm: [T base taps] [same, B rows + b_lo] [same, A planes + a_lo]
