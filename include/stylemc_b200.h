@@ -61,6 +61,10 @@ typedef struct smc_upfirdn2d_params {
   int64_t f_stride[2];                  /* fp32 filter strides (h, w) */
   int32_t upx, upy, downx, downy, padx0, pady0, flip;
   float gain;
+  /* optional hint for 4x4 filters: f[i][j] == fsep[i] * fsep[4 + j] (rank-1 filter, e.g. setup_filter([1,3,3,1])); the kernels then
+   * filter rows and columns separately.  0 = not known / not separable. */
+  int32_t separable;
+  float fsep[8];
 } smc_upfirdn2d_params;
 int smc_upfirdn2d(const void* x, const float* f, void* y, int dtype, const smc_upfirdn2d_params* p, void* stream);
 

@@ -52,7 +52,8 @@ class UpfirdnParams(ctypes.Structure):
                 ('x_stride', ctypes.c_int64 * 4), ('y_stride', ctypes.c_int64 * 4),
                 ('fH', ctypes.c_int32), ('fW', ctypes.c_int32), ('f_stride', ctypes.c_int64 * 2),
                 ('upx', ctypes.c_int32), ('upy', ctypes.c_int32), ('downx', ctypes.c_int32), ('downy', ctypes.c_int32),
-                ('padx0', ctypes.c_int32), ('pady0', ctypes.c_int32), ('flip', ctypes.c_int32), ('gain', ctypes.c_float)]
+                ('padx0', ctypes.c_int32), ('pady0', ctypes.c_int32), ('flip', ctypes.c_int32), ('gain', ctypes.c_float),
+                ('separable', ctypes.c_int32), ('fsep', ctypes.c_float * 8)]
 
 
 _T = {'p': ctypes.c_void_p, 'i': ctypes.c_int, 'q': ctypes.c_int64, 'f': ctypes.c_float}

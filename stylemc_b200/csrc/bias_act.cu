@@ -28,8 +28,8 @@ struct BiasActArgs {
 };
 
 // One element.  A = activation index (bias_act.py:23-33 cuda_idx), G = derivative order.
-template <class S, int A>
-__device__ __forceinline__ S bias_act_elem(S x, S b, S xref, S yref, S dy, int G, S alpha, S gain, S clamp) {
+template <class S, int A, int G>
+__device__ __forceinline__ S bias_act_elem(S x, S b, S xref, S yref, S dy, S alpha, S gain, S clamp) {
   const S one = (S)1, two = (S)2, range = (S)80, half_range = (S)40;
   const S selu_scale = (S)1.0507009873554804934193349852946, selu_alpha = (S)1.6732632423543772848170429916717;
   const S yy = (gain != (S)0) ? yref / gain : (S)0;
@@ -86,7 +86,7 @@ template <class T, class S> __device__ __forceinline__ T from_s(S v) { return (T
 template <> __device__ __forceinline__ __half from_s<__half, float>(float v) { return __float2half_rn(v); }
 
 // VEC elements per thread per iteration; VEC * sizeof(T) == 16 on the fast path, VEC == 1 otherwise.
-template <class T, int A, int VEC>
+template <class T, int A, int VEC, int G>
 __global__ void __launch_bounds__(256) bias_act_kernel(const BiasActArgs p) {
   typedef typename Compute<T>::type S;
   const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
@@ -112,14 +112,16 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const BiasActArgs p) {
       if (yr) yrv[0] = yr[i0];
       if (dyb) dyv[0] = dyb[i0];
     }
+    // size_x <= INT_MAX (checked by the entry point, as bias_act.cpp:40 does): 32-bit index arithmetic
+    const unsigned i0u = (unsigned)i0, stepu = (unsigned)p.step_b, sizeu = (unsigned)p.size_b;
     S bias0 = 0;
-    if (bb && bias_per_vec) bias0 = to_s<T>(bb[(i0 / p.step_b) % p.size_b]);
+    if (bb && bias_per_vec) bias0 = to_s<T>(bb[(i0u / stepu) % sizeu]);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       S bj = bias0;
-      if (bb && !bias_per_vec) bj = to_s<T>(bb[((i0 + j) / p.step_b) % p.size_b]);
-      out[j] = from_s<T, S>(bias_act_elem<S, A>(to_s<T>(xv[j]), bj, xr ? to_s<T>(xrv[j]) : (S)0, yr ? to_s<T>(yrv[j]) : (S)0,
-                                                 dyb ? to_s<T>(dyv[j]) : (S)1, p.grad, alpha, gain, clamp));
+      if (bb && !bias_per_vec) bj = to_s<T>(bb[((i0u + (unsigned)j) / stepu) % sizeu]);
+      out[j] = from_s<T, S>(bias_act_elem<S, A, G>(to_s<T>(xv[j]), bj, xr ? to_s<T>(xrv[j]) : (S)0, yr ? to_s<T>(yrv[j]) : (S)0,
+                                                    dyb ? to_s<T>(dyv[j]) : (S)1, alpha, gain, clamp));
     }
     if (VEC > 1) st_stream(yb + i0, *reinterpret_cast<uint4*>(out));
     else yb[i0] = out[0];
@@ -129,8 +131,8 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const BiasActArgs p) {
     const long long i = nvec * VEC + threadIdx.x;
     if (i < p.size_x) {
       S bj = bb ? to_s<T>(bb[(i / p.step_b) % p.size_b]) : (S)0;
-      yb[i] = from_s<T, S>(bias_act_elem<S, A>(to_s<T>(xb[i]), bj, xr ? to_s<T>(xr[i]) : (S)0, yr ? to_s<T>(yr[i]) : (S)0,
-                                                dyb ? to_s<T>(dyb[i]) : (S)1, p.grad, alpha, gain, clamp));
+      yb[i] = from_s<T, S>(bias_act_elem<S, A, G>(to_s<T>(xb[i]), bj, xr ? to_s<T>(xr[i]) : (S)0, yr ? to_s<T>(yr[i]) : (S)0,
+                                                   dyb ? to_s<T>(dyb[i]) : (S)1, alpha, gain, clamp));
     }
   }
 }
@@ -142,18 +144,17 @@ static int launch_act(const BiasActArgs& p, int act, cudaStream_t st) {
   const long long cap = (long long)kNumSMs * 16;  // 16 resident 256-thread CTAs fill the 64 warps/SM twice over
   if (blocks > cap) blocks = cap;
   const int g = (int)blocks;
+#define SMC_BA_CASE(A)                                                         \
+  case A:                                                                      \
+    if (p.grad == 0) bias_act_kernel<T, A, VEC, 0><<<g, 256, 0, st>>>(p);      \
+    else if (p.grad == 1) bias_act_kernel<T, A, VEC, 1><<<g, 256, 0, st>>>(p); \
+    else bias_act_kernel<T, A, VEC, 2><<<g, 256, 0, st>>>(p);                  \
+    break;
   switch (act) {
-    case 1: bias_act_kernel<T, 1, VEC><<<g, 256, 0, st>>>(p); break;
-    case 2: bias_act_kernel<T, 2, VEC><<<g, 256, 0, st>>>(p); break;
-    case 3: bias_act_kernel<T, 3, VEC><<<g, 256, 0, st>>>(p); break;
-    case 4: bias_act_kernel<T, 4, VEC><<<g, 256, 0, st>>>(p); break;
-    case 5: bias_act_kernel<T, 5, VEC><<<g, 256, 0, st>>>(p); break;
-    case 6: bias_act_kernel<T, 6, VEC><<<g, 256, 0, st>>>(p); break;
-    case 7: bias_act_kernel<T, 7, VEC><<<g, 256, 0, st>>>(p); break;
-    case 8: bias_act_kernel<T, 8, VEC><<<g, 256, 0, st>>>(p); break;
-    case 9: bias_act_kernel<T, 9, VEC><<<g, 256, 0, st>>>(p); break;
+    SMC_BA_CASE(1) SMC_BA_CASE(2) SMC_BA_CASE(3) SMC_BA_CASE(4) SMC_BA_CASE(5) SMC_BA_CASE(6) SMC_BA_CASE(7) SMC_BA_CASE(8) SMC_BA_CASE(9)
     default: return SMC_EINVAL;
   }
+#undef SMC_BA_CASE
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

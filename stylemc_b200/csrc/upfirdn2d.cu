@@ -23,6 +23,7 @@ struct UpfirdnArgs {
   int fH, fW; long long fs_h, fs_w;
   int upx, upy, downx, downy, padx0, pady0, flip;
   float gain;
+  int separable; float fsy[4], fsx[4];   // f[i][j] == fsy[i] * fsx[j] when separable (host-side hint)
 };
 
 template <class T> struct Acc { typedef float type; };
@@ -110,11 +111,227 @@ __global__ void __launch_bounds__(256) upfirdn2d_direct_kernel(const UpfirdnArgs
   }
 }
 
+// ---- fast path: 4x4 filter, contiguous NCHW, (up, down) in {(1,1), (2,1), (1,2)}, fp32 / fp16 ----------------------------------
+// These are the three cases on the hot path (upfirdn2d.cu:217,252,298 in the reference): the FIR after the
+// transposed conv, upsample2d of the skip image, and its transpose.  One thread = one output column x YB consecutive output rows of
+// one (n, c) plane; lanes run along x, so every load instruction of a warp is one (or two, down = 2) contiguous 128-byte line and
+// the taps' horizontal overlap is served by L1.  The filter (flipped, times gain) sits in registers; trip counts are compile-time.
+template <class T> __device__ __forceinline__ float ldg_f(const T* p) { return (float)__ldg(p); }
+template <> __device__ __forceinline__ float ldg_f<__half>(const __half* p) { return __half2float(__ldg(p)); }
+
+template <class T, int UP, int DOWN, int YB>
+__global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(const UpfirdnArgs p) {
+  constexpr int F = 4;
+  float fk[F][F];                       // fk[ky][kx] = (flip ? f[ky][kx] : f[F-1-ky][F-1-kx]) * gain
+#pragma unroll
+  for (int ky = 0; ky < F; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < F; ++kx) {
+      const int sy = p.flip ? ky : F - 1 - ky, sx = p.flip ? kx : F - 1 - kx;
+      fk[ky][kx] = __ldg(p.f + sy * p.fs_h + sx * p.fs_w) * p.gain;
+    }
+  const int ox = blockIdx.x * 128 + (threadIdx.x & 127);
+  const int oyb = (blockIdx.y * 2 + (threadIdx.x >> 7)) * YB;
+  const long long plane = blockIdx.z;
+  if (ox >= p.outW || oyb >= p.outH) return;
+  const T* __restrict__ xp = reinterpret_cast<const T*>(p.x) + plane * (long long)p.inH * p.inW;
+  T* __restrict__ yp = reinterpret_cast<T*>(p.y) + plane * (long long)p.outH * p.outW;
+  float acc[YB];
+#pragma unroll
+  for (int j = 0; j < YB; ++j) acc[j] = 0.f;
+  if (UP == 1) {
+    // rows r of the input window: iy = oyb * DOWN - pady0 + r feeds output j with tap ky = r - j * DOWN
+    const int ix0 = ox * DOWN - p.padx0, iy0 = oyb * DOWN - p.pady0;
+#pragma unroll
+    for (int r = 0; r < (YB - 1) * DOWN + F; ++r) {
+      const int iy = iy0 + r;
+      float v[F];
+      const bool rowok = iy >= 0 && iy < p.inH;
+#pragma unroll
+      for (int kx = 0; kx < F; ++kx) {
+        const int ix = ix0 + kx;
+        v[kx] = (rowok && ix >= 0 && ix < p.inW) ? ldg_f<T>(xp + (long long)iy * p.inW + ix) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < YB; ++j) {
+        const int ky = r - j * DOWN;
+        if (ky >= 0 && ky < F) {
+#pragma unroll
+          for (int kx = 0; kx < F; ++kx) acc[j] += fk[ky][kx] * v[kx];
+        }
+      }
+    }
+  } else {
+    // zero-insertion up-sampling: only taps with (a + k) % UP == 0 see data; two taps per axis for UP = 2, F = 4
+    const int ax = ox - p.padx0;
+    const int kx0 = pos_mod(-ax, UP);
+#pragma unroll
+    for (int j = 0; j < YB; ++j) {
+      const int ay = oyb + j - p.pady0;
+      const int ky0 = pos_mod(-ay, UP);
+#pragma unroll
+      for (int a = 0; a < F / UP; ++a) {
+        const int iy = (ay + ky0 + a * UP) / UP;       // exact
+        const bool rowok = iy >= 0 && iy < p.inH;
+#pragma unroll
+        for (int b = 0; b < F / UP; ++b) {
+          const int ix = (ax + kx0 + b * UP) / UP;
+          const float v = (rowok && ix >= 0 && ix < p.inW) ? ldg_f<T>(xp + (long long)iy * p.inW + ix) : 0.f;
+          // coefficient fk[ky0 + a UP][kx0 + b UP] with ky0, kx0 in {0, 1}: selected without dynamic indexing
+          const float c0 = kx0 ? fk[a * UP][b * UP + 1] : fk[a * UP][b * UP];
+          const float c1 = kx0 ? fk[a * UP + 1][b * UP + 1] : fk[a * UP + 1][b * UP];
+          acc[j] += (ky0 ? c1 : c0) * v;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < YB; ++j)
+    if (oyb + j < p.outH) st_as<T, float>(yp + (long long)(oyb + j) * p.outW + ox, acc[j]);
+}
+
+// up = 1 (plain / decimating FIR): the input footprint of a 128 x TOH output tile is staged once in shared memory (coalesced loads,
+// zero fill = the padding), then each thread walks YB output rows of one column with a register window: (YB - 1) * DOWN + 4 rows x 4
+// conflict-free LDS for YB outputs, no bounds checks or address arithmetic in the FIR loop.
+template <class T, int DOWN>
+__global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(const UpfirdnArgs p) {
+  constexpr int F = 4, TOW = 128, TOH = DOWN == 1 ? 32 : 16, YB = TOH / 2;
+  constexpr int IW = (TOW - 1) * DOWN + F, IH = (TOH - 1) * DOWN + F;
+  __shared__ float sx[IH * IW];
+  float fk[F][F];
+#pragma unroll
+  for (int ky = 0; ky < F; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < F; ++kx) {
+      const int sy = p.flip ? ky : F - 1 - ky, sxi = p.flip ? kx : F - 1 - kx;
+      fk[ky][kx] = __ldg(p.f + sy * p.fs_h + sxi * p.fs_w) * p.gain;
+    }
+  const int ox0 = blockIdx.x * TOW, oy0 = blockIdx.y * TOH;
+  const long long plane = blockIdx.z;
+  const T* __restrict__ xp = reinterpret_cast<const T*>(p.x) + plane * (long long)p.inH * p.inW;
+  const int ix0 = ox0 * DOWN - p.padx0, iy0 = oy0 * DOWN - p.pady0;
+  {
+    // one warp per input row (8 rows in flight per pass).  Tiles whose whole footprint lies inside the image (most of them) skip
+    // every bounds test; the others test the row once and the column per element.
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const bool interior = iy0 >= 0 && iy0 + IH <= p.inH && ix0 >= 0 && ix0 + IW <= p.inW;
+    if (interior) {
+      const T* src = xp + (long long)(iy0 + wrp) * p.inW + ix0 + lane;
+      float* dst = sx + wrp * IW + lane;
+#pragma unroll
+      for (int r = 0; r < IH; r += 8) {
+        if (r + wrp < IH) {
+#pragma unroll
+          for (int c = 0; c < IW; c += 32)
+            if (c + 32 <= IW || c + lane < IW) dst[r * IW + c] = ldg_f<T>(src + (long long)r * p.inW + c);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int r = wrp; r < IH; r += 8) {
+        const int iy = iy0 + r;
+        const bool rowok = iy >= 0 && iy < p.inH;
+        const T* rowp = xp + (long long)(rowok ? iy : 0) * p.inW;
+        float* srow = sx + r * IW;
+#pragma unroll
+        for (int c = 0; c < IW; c += 32) {
+          const int cc = c + lane, ix = ix0 + cc;
+          if (cc < IW) srow[cc] = (rowok && ix >= 0 && ix < p.inW) ? ldg_f<T>(rowp + ix) : 0.f;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 127, tg = threadIdx.x >> 7;
+  float acc[YB];
+#pragma unroll
+  for (int j = 0; j < YB; ++j) acc[j] = 0.f;
+  const float* base = sx + (tg * YB * DOWN) * IW + tx * DOWN;
+  // rank-1 filter (host hint; e.g. the [1,3,3,1] resample filter): a window row costs 4 FMAs + one per tap row that uses it instead
+  // of 4 per tap row.  fk = flip ? f : rot180(f), times gain: the same index map applies to each factor.
+  float fx[F], fy[F];
+  const bool separable = p.separable != 0;
+#pragma unroll
+  for (int k = 0; k < F; ++k) {
+    fy[k] = p.fsy[p.flip ? k : F - 1 - k] * p.gain;
+    fx[k] = p.fsx[p.flip ? k : F - 1 - k];
+  }
+  if (separable) {
+#pragma unroll
+    for (int r = 0; r < (YB - 1) * DOWN + F; ++r) {
+      float h = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < F; ++kx) h += fx[kx] * base[r * IW + kx];
+#pragma unroll
+      for (int j = 0; j < YB; ++j) {
+        const int ky = r - j * DOWN;
+        if (ky >= 0 && ky < F) acc[j] += fy[ky] * h;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < (YB - 1) * DOWN + F; ++r) {
+      float v[F];
+#pragma unroll
+      for (int kx = 0; kx < F; ++kx) v[kx] = base[r * IW + kx];
+#pragma unroll
+      for (int j = 0; j < YB; ++j) {
+        const int ky = r - j * DOWN;
+        if (ky >= 0 && ky < F) {
+#pragma unroll
+          for (int kx = 0; kx < F; ++kx) acc[j] += fk[ky][kx] * v[kx];
+        }
+      }
+    }
+  }
+  const int ox = ox0 + tx;
+  if (ox < p.outW) {
+    T* __restrict__ yp = reinterpret_cast<T*>(p.y) + plane * (long long)p.outH * p.outW + ox;
+#pragma unroll
+    for (int j = 0; j < YB; ++j) {
+      const int oy = oy0 + tg * YB + j;
+      if (oy < p.outH) st_as<T, float>(yp + (long long)oy * p.outW, acc[j]);
+    }
+  }
+}
+
+template <class T, int DOWN>
+static int launch_tile(const UpfirdnArgs& p, cudaStream_t st) {
+  constexpr int TOH = DOWN == 1 ? 32 : 16;
+  dim3 grid(ceil_div(p.outW, 128), ceil_div(p.outH, TOH), p.N * p.C);
+  if (grid.y > 65535 || grid.z > 65535) return SMC_EUNSUPPORTED;
+  upfirdn2d_tile_kernel<T, DOWN><<<grid, 256, 0, st>>>(p);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+template <class T, int UP, int DOWN, int YB>
+static int launch_fast(const UpfirdnArgs& p, cudaStream_t st) {
+  dim3 grid(ceil_div(p.outW, 128), ceil_div(p.outH, 2 * YB), p.N * p.C);
+  if (grid.y > 65535 || grid.z > 65535) return SMC_EUNSUPPORTED;
+  upfirdn2d_fast_kernel<T, UP, DOWN, YB><<<grid, 256, 0, st>>>(p);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+template <class T> struct FastOk { static constexpr bool value = false; };
+template <> struct FastOk<float> { static constexpr bool value = true; };
+template <> struct FastOk<__half> { static constexpr bool value = true; };
+
 template <class T>
 static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t st) {
   typedef typename Acc<T>::type S;
   const bool x_nchw = p.xs_w == 1 && p.xs_h == p.inW && p.xs_c == (long long)p.inH * p.inW && p.xs_n == p.xs_c * p.C;
   const bool y_nchw = p.ys_w == 1 && p.ys_h == p.outW && p.ys_c == (long long)p.outH * p.outW && p.ys_n == p.ys_c * p.C;
+  if constexpr (FastOk<T>::value) {
+    if (x_nchw && y_nchw && p.fH == 4 && p.fW == 4 && p.upx == p.upy && p.downx == p.downy) {
+      int r = SMC_EUNSUPPORTED;
+      if (p.upx == 1 && p.downx == 1) r = launch_tile<T, 1>(p, st);
+      else if (p.upx == 2 && p.downx == 1) r = launch_fast<T, 2, 1, 4>(p, st);
+      else if (p.upx == 1 && p.downx == 2) r = launch_tile<T, 2>(p, st);
+      if (r != SMC_EUNSUPPORTED) return r;
+    }
+  }
   if (x_nchw && y_nchw && p.fH <= kMaxTaps && p.fW <= kMaxTaps) {
     const int in_tile_h = ((kTileH - 1) * p.downy + p.fH - 1) / p.upy + 2;
     const int in_tile_w = ((kTileW - 1) * p.downx + p.fW - 1) / p.upx + 2;
@@ -155,6 +372,8 @@ extern "C" int smc_upfirdn2d(const void* x, const float* f, void* y, int dtype, 
   p.fH = q->fH; p.fW = q->fW; p.fs_h = q->f_stride[0]; p.fs_w = q->f_stride[1];
   p.upx = q->upx; p.upy = q->upy; p.downx = q->downx; p.downy = q->downy;
   p.padx0 = q->padx0; p.pady0 = q->pady0; p.flip = q->flip ? 1 : 0; p.gain = q->gain;
+  p.separable = (q->separable != 0 && q->fH == 4 && q->fW == 4) ? 1 : 0;
+  for (int i = 0; i < 4; ++i) { p.fsy[i] = q->fsep[i]; p.fsx[i] = q->fsep[4 + i]; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {
     case SMC_F32: return launch_upfirdn<float>(p, st);

@@ -56,6 +56,29 @@ def setup_filter(f, device=torch.device('cpu'), normalize=True, flip_filter=Fals
     return f.to(device=device)
 
 
+_sep_cache = {}
+
+
+def _separable_factors(f):
+    """(fy[0..3], fx[0..3]) with f[i][j] == fy[i] * fx[j] for a rank-1 4x4 filter (setup_filter([1,3,3,1]) is one), else None.
+    The filter lives on the device; the answer is cached per filter tensor so the host copy happens once."""
+    if tuple(f.shape) != (4, 4):
+        return None
+    key = (f.data_ptr(), f._version, f.device)
+    if key not in _sep_cache:
+        fh = f.detach().double().cpu()
+        tot = float(fh.sum())
+        res = None
+        if abs(tot) > 1e-20:
+            fy, fx = fh.sum(1) / tot, fh.sum(0)
+            if float((torch.outer(fy, fx) - fh).abs().max()) <= 1e-6 * float(fh.abs().max()):
+                res = [float(v) for v in fy] + [float(v) for v in fx]
+        if len(_sep_cache) > 64:
+            _sep_cache.clear()
+        _sep_cache[key] = res
+    return _sep_cache[key]
+
+
 def _launch(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
     """One pass; mirrors `_plugin.upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)`."""
     _lib.require_cuda(x, 'x')
@@ -85,6 +108,10 @@ def _launch(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain
     p.fH, p.fW = f.shape
     p.f_stride[:] = list(f.stride())
     p.upx, p.upy, p.downx, p.downy, p.padx0, p.pady0, p.flip, p.gain = upx, upy, downx, downy, padx0, pady0, int(bool(flip)), float(gain)
+    sep = _separable_factors(f)
+    if sep is not None:
+        p.separable = 1
+        p.fsep[:] = sep
     import ctypes
     with torch.cuda.device(x.device):
         _lib.call('smc_upfirdn2d', _lib.ptr(x), _lib.ptr(f), _lib.ptr(y), _lib.DTYPE_CODE[x.dtype], ctypes.addressof(p), _lib.stream())
