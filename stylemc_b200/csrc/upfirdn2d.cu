@@ -295,6 +295,57 @@ __global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(const UpfirdnArgs p
   }
 }
 
+// up = 2, down = 1 (upsample2d: zero insertion + 4x4 FIR): polyphase form, 2 x 2 input taps per output.  The (TOH/2 + 2) x (TOW/2 + 2)
+// input footprint of a 128 x 32 output tile is staged in shared memory; a thread owns one output column (fixed column phase) and
+// 16 rows whose row phase alternates, so its 2 x 4 tap coefficients are selected once.
+template <class T>
+__global__ void __launch_bounds__(256) upfirdn2d_up2_tile_kernel(const UpfirdnArgs p) {
+  constexpr int F = 4, TOW = 128, TOH = 32, YB = TOH / 2, IW = TOW / 2 + 2, IH = TOH / 2 + 2;
+  __shared__ float sx[IH * IW];
+  float fk[F][F];
+#pragma unroll
+  for (int ky = 0; ky < F; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < F; ++kx) {
+      const int sy = p.flip ? ky : F - 1 - ky, sxi = p.flip ? kx : F - 1 - kx;
+      fk[ky][kx] = __ldg(p.f + sy * p.fs_h + sxi * p.fs_w) * p.gain;
+    }
+  const int ox0 = blockIdx.x * TOW, oy0 = blockIdx.y * TOH;
+  const long long plane = blockIdx.z;
+  const T* __restrict__ xp = reinterpret_cast<const T*>(p.x) + plane * (long long)p.inH * p.inW;
+  const int ix0 = floor_div(ox0 - p.padx0 + 1, 2), iy0 = floor_div(oy0 - p.pady0 + 1, 2);   // first input column / row a tap can touch
+  for (int i = threadIdx.x; i < IH * IW; i += 256) {
+    const int r = i / IW, c = i - r * IW;
+    const int iy = iy0 + r, ix = ix0 + c;
+    sx[i] = (iy >= 0 && iy < p.inH && ix >= 0 && ix < p.inW) ? ldg_f<T>(xp + (long long)iy * p.inW + ix) : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 127, tg = threadIdx.x >> 7;
+  const int ox = ox0 + tx;
+  const int ax = ox - p.padx0;
+  const int kx0 = pos_mod(-ax, 2);
+  const int cxb = (ax + kx0) / 2 - ix0;                       // smem column of the first tap (exact division), second tap = +1
+  // coefficients of the two column taps for every filter row, column phase folded in
+  float c0[F], c1[F];
+#pragma unroll
+  for (int ky = 0; ky < F; ++ky) {
+    c0[ky] = kx0 ? fk[ky][1] : fk[ky][0];
+    c1[ky] = kx0 ? fk[ky][3] : fk[ky][2];
+  }
+  T* __restrict__ yp = reinterpret_cast<T*>(p.y) + plane * (long long)p.outH * p.outW + ox;
+#pragma unroll
+  for (int j = 0; j < YB; ++j) {
+    const int oy = oy0 + tg * YB + j;
+    const int ay = oy - p.pady0;
+    const int ky0 = pos_mod(-ay, 2);
+    const float* r0 = sx + ((ay + ky0) / 2 - iy0) * IW + cxb;   // first row tap; second = next smem row
+    const float a00 = ky0 ? c0[1] : c0[0], a01 = ky0 ? c1[1] : c1[0];
+    const float a10 = ky0 ? c0[3] : c0[2], a11 = ky0 ? c1[3] : c1[2];
+    const float v = a00 * r0[0] + a01 * r0[1] + a10 * r0[IW] + a11 * r0[IW + 1];
+    if (ox < p.outW && oy < p.outH) st_as<T, float>(yp + (long long)oy * p.outW, v);
+  }
+}
+
 template <class T, int DOWN>
 static int launch_tile(const UpfirdnArgs& p, cudaStream_t st) {
   constexpr int TOH = DOWN == 1 ? 32 : 16;
@@ -327,7 +378,14 @@ static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t st) {
     if (x_nchw && y_nchw && p.fH == 4 && p.fW == 4 && p.upx == p.upy && p.downx == p.downy) {
       int r = SMC_EUNSUPPORTED;
       if (p.upx == 1 && p.downx == 1) r = launch_tile<T, 1>(p, st);
-      else if (p.upx == 2 && p.downx == 1) r = launch_fast<T, 2, 1, 4>(p, st);
+      else if (p.upx == 2 && p.downx == 1) {
+        dim3 grid(ceil_div(p.outW, 128), ceil_div(p.outH, 32), p.N * p.C);
+        if (grid.y <= 65535 && grid.z <= 65535) {
+          upfirdn2d_up2_tile_kernel<T><<<grid, 256, 0, st>>>(p);
+          SMC_LAUNCH_CHECK();
+          r = SMC_OK;
+        }
+      }
       else if (p.upx == 1 && p.downx == 2) r = launch_tile<T, 2>(p, st);
       if (r != SMC_EUNSUPPORTED) return r;
     }
