@@ -195,7 +195,11 @@ def run_ours(a):
         e0.record()
         yield
         e1.record()
-        records.append((e0, e1, 2.0 * d.n_img * d.H * d.W * d.n_out * d.C * alg_taps, (d.n_img, d.H, d.W, d.C, d.n_out, alg_taps)))
+        planes_a = max(1, d.ntaps // max(1, alg_taps) - 1)                       # x3: hi + lo planes of A are read
+        e = d.epi
+        out_b = (4 if e.out_f32 else 0) + sum(2 for q in (e.out_hi, e.out_lo, e.out_raw, e.out_raw_lo) if q)
+        nbytes = float(d.n_img) * d.H * d.W * (2 * planes_a * d.C + out_b * d.n_out)   # algorithmic HBM bytes: A once, outputs once
+        records.append((e0, e1, 2.0 * d.n_img * d.H * d.W * d.n_out * d.C * alg_taps, (d.n_img, d.H, d.W, d.C, d.n_out, alg_taps), nbytes))
 
     _lib.igemm_hook = hook
     t0 = torch.cuda.Event(enable_timing=True)
@@ -206,12 +210,12 @@ def run_ours(a):
     t1.record()
     torch.cuda.synchronize()
     _lib.igemm_hook = None
-    ig_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in records)
-    ig_flops = sum(f for _, _, f, _ in records)
+    ig_ms = sum(r[0].elapsed_time(r[1]) for r in records)
+    ig_flops = sum(r[2] for r in records)
     shapes = {}
-    for e0, e1, fl, key in records:
-        t = shapes.setdefault(key, [0.0, 0.0, 0])
-        t[0] += e0.elapsed_time(e1); t[1] += fl; t[2] += 1
+    for e0, e1, fl, key, nb in records:
+        t = shapes.setdefault(key, [0.0, 0.0, 0, 0.0])
+        t[0] += e0.elapsed_time(e1); t[1] += fl; t[2] += 1; t[3] += nb
     top_key, top = max(shapes.items(), key=lambda kv: kv[1][0])
     step_ms_hooked = t0.elapsed_time(t1)
 
@@ -226,6 +230,10 @@ def run_ours(a):
     e2e = imgs / (ms_e2e / 1e3)
     achieved = ig_flops / (ig_ms / 1e3) / 1e12
     mma_per_product = 1 if a.precision == 'x1' else 3
+    top_tf = top[1] / (top[0] / 1e3) / 1e12                  # algorithmic TFLOP/s of the heaviest shape
+    top_gbs = top[3] / (top[0] / 1e3) / 1e9                  # algorithmic GB/s of the same launches
+    # the 32/64-channel convs sit below the ridge (288 products per 384 bytes at C = 32): they are HBM-bound
+    top_bound = 'hbm' if top_gbs / pk['hbm'] >= mma_per_product * top_tf / pk['tflops'] else 'tensor'
     out = {
         'metric': METRIC, 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': round(ms / a.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -242,11 +250,14 @@ def run_ours(a):
         # dominant kernel = the smc_igemm shape with the largest summed time in one step (a conv on csrc/hconv.cu).  `achieved` counts
         # ALGORITHMIC FLOPs (2 * pixels * taps * Cin * Cout per launch); in split precision every algorithmic product
         # costs three fp16 MMAs, so the tensor pipe does mma_per_product x that work (tensor_pipe_*).
-        'roofline': {'bound': 'tensor',
+        'roofline': {'bound': top_bound,
                      'kernel': f'hconv_kernel (tcgen05 halo-tile implicit GEMM), heaviest shape of the step: n={top_key[0]} {top_key[1]}x{top_key[2]} '
                                f'Cin={top_key[3]} Cout={top_key[4]} taps={top_key[5]}',
-                     'achieved': round(top[1] / (top[0] / 1e3) / 1e12, 2), 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-                     'frac': round(top[1] / (top[0] / 1e3) / 1e12 / pk['tflops'], 4),
+                     'achieved': round(top_gbs if top_bound == 'hbm' else top_tf, 2), 'peak': pk['hbm'] if top_bound == 'hbm' else pk['tflops'],
+                     'unit': 'GB/s' if top_bound == 'hbm' else 'TFLOP/s',
+                     'frac': round(top_gbs / pk['hbm'] if top_bound == 'hbm' else top_tf / pk['tflops'], 4),
+                     'algorithmic_tflops': round(top_tf, 2), 'algorithmic_gbs': round(top_gbs, 1),
+                     'algorithmic_gbyte_per_launch': round(top[3] / top[2] / 1e9, 2),
                      'launches_per_step': top[2], 'avg_launch_ms': round(top[0] / top[2], 4),
                      'algorithmic_gflop_per_launch': round(top[1] / top[2] / 1e9, 2),
                      'mma_per_product': mma_per_product,
