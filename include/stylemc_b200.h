@@ -105,6 +105,16 @@ typedef struct smc_igemm_epilogue {
   const float* rgb_w;        // [n_img, 3, n_out] modulated ToRGB weights (w[j, c] * style[n, c] * weight_gain) or NULL
   float* rgb_acc;            // fp32, atomically accumulated: rgb_acc[n * rgb_sn + j * rgb_sj + h * rgb_sh + w] += sum_c rgb_w * v
   int64_t rgb_sn, rgb_sj, rgb_sh;
+  // Fused activation backward (halo-tile conv kernel only; used by the dgrad GEMMs, replaces a separate smc_act_bwd pass where no
+  // style-gradient reduction is needed): with y = mask_y (+ mask_y_lo), the saved output of the layer BELOW,
+  //   v = acc * acc_scale * post_scale[n, o] * (y > 0 ? gain : gain * alpha), v = 0 where |y| >= clamp (clamp >= 0);
+  // out_hi / out_lo receive v (bias_act.cu:71-72,136-142 semantics: the gradient uses the saved output, not the input).
+  // row_scale, bias, noise, act, residual, out_f32, out_raw and the ToRGB fields must be unset.  Addressed like the outputs.
+  const void* mask_y;        // fp16 or NULL
+  const void* mask_y_lo;     // fp16 or NULL
+  // ToRGB branch of the same backward step (optional, with mask_y): v gets, before the activation slope,
+  //   + sum_j rgb_w[n, j, o] * mask_grgb[n * rgb_sn + j * rgb_sj + h * rgb_sh + w]   (mask_grgb = masked, loss-scaled dL/drgb, fp32)
+  const float* mask_grgb;
 } smc_igemm_epilogue;
 
 typedef struct smc_igemm_desc {

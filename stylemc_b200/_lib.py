@@ -34,7 +34,8 @@ class Epilogue(ctypes.Structure):
                 ('o_sn', ctypes.c_int64), ('o_sh', ctypes.c_int64), ('o_sw', ctypes.c_int64), ('o_off', ctypes.c_int64),
                 ('acc_scale', ctypes.c_float),
                 ('out_raw_lo', ctypes.c_void_p), ('rgb_w', ctypes.c_void_p), ('rgb_acc', ctypes.c_void_p),
-                ('rgb_sn', ctypes.c_int64), ('rgb_sj', ctypes.c_int64), ('rgb_sh', ctypes.c_int64)]
+                ('rgb_sn', ctypes.c_int64), ('rgb_sj', ctypes.c_int64), ('rgb_sh', ctypes.c_int64),
+                ('mask_y', ctypes.c_void_p), ('mask_y_lo', ctypes.c_void_p), ('mask_grgb', ctypes.c_void_p)]
 
 
 class IgemmDesc(ctypes.Structure):

@@ -223,6 +223,75 @@ __device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], cons
   }
 }
 
+// 32-byte read-only load (sm_100 256-bit vector load): the whole sector in one request
+__device__ __forceinline__ void hc_ld32(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void hc_h8_to_f(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+
+// Activation backward fused into a dgrad GEMM (smc_igemm_epilogue::mask_y): the accumulator is the gradient w.r.t. the modulated input
+// of the consumer conv; multiplied by post = (consumer style) * (demodulation of the layer below) it becomes the gradient w.r.t. that
+// layer's pre-activation once the leaky-ReLU slope and the clamp mask of the SAVED output y are applied (bias_act.cu:71-72,136-142).
+// The optional ToRGB branch adds sum_j rw[j][c] * g_j (g = masked dL/drgb of this pixel) before the slope.
+template <int CW>
+__device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const smc_igemm_epilogue& e, float acc_scale,
+                                                   const float* __restrict__ ps, const float* __restrict__ rw, int n_out, long long opix,
+                                                   float g0, float g1, float g2) {
+  const float g = e.gain, ga = e.gain * e.alpha, cl = e.clamp;
+  const __half* yh = reinterpret_cast<const __half*>(e.mask_y) + opix;
+  const __half* yl = e.mask_y_lo ? reinterpret_cast<const __half*>(e.mask_y_lo) + opix : nullptr;
+#pragma unroll
+  for (int c0 = 0; c0 < CW; c0 += 16) {
+    float y[16], v[16];
+    {
+      uint4 a, b;
+      hc_ld32(yh + c0, a, b);
+      hc_h8_to_f(a, y); hc_h8_to_f(b, y + 8);
+      if (yl) {
+        float l[16];
+        hc_ld32(yl + c0, a, b);
+        hc_h8_to_f(a, l); hc_h8_to_f(b, l + 8);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] += l[i];
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float p8[8];
+      hc_ld8(ps + c0 + 8 * hh, p8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * hh + i] = acc[c0 + 8 * hh + i] * (p8[i] * acc_scale);
+      if (rw) {
+        float w0[8], w1[8], w2[8];
+        hc_ld8(rw + c0 + 8 * hh, w0);
+        hc_ld8(rw + n_out + c0 + 8 * hh, w1);
+        hc_ld8(rw + 2 * n_out + c0 + 8 * hh, w2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * hh + i] += w0[i] * g0 + w1[i] * g1 + w2[i] * g2;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float yy = y[i];
+      const bool pass = (cl < 0.f) || (yy > -cl && yy < cl);
+      v[i] = pass ? v[i] * (yy > 0.f ? g : ga) : 0.f;
+    }
+    uint4 h0, l0, h1, l1;
+    hc_split8(reinterpret_cast<const float(&)[8]>(v[0]), h0, l0);
+    hc_split8(reinterpret_cast<const float(&)[8]>(v[8]), h1, l1);
+    hc_st32(reinterpret_cast<__half*>(e.out_hi) + opix + c0, h0, h1);
+    if (e.out_lo) hc_st32(reinterpret_cast<__half*>(e.out_lo) + opix + c0, l0, l1);
+  }
+}
+
 // MODE 2 (x3, BN <= 64): with both operands in shared memory an MMA costs ~64 clk for its 128 x 16 A slab whatever N is, so narrow
 // layers are issue-bound on the NUMBER of MMAs.  There the stage of a tap holds [B_hi; B_lo] (2 BN rows) and ONE MMA of N = 2 BN
 // computes A_hi*B_hi (columns [0, BN) = main) and A_hi*B_lo (columns [BN, 2 BN) = cross) together; A_lo*B_hi is a second MMA of
@@ -522,7 +591,16 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         // modulated-conv layers (the bulk of the epilogue work): lean path; alpha < 1 makes max(x, alpha x) the leaky ReLU
         const bool modconv = rs && bs && e.act == 1 && e.clamp >= 0.f && e.alpha >= 0.f && e.alpha <= 1.f && e.gain > 0.f && !e.residual && !e.out_f32 &&
                              (((uintptr_t)rs | (uintptr_t)bs | (uintptr_t)ps | (uintptr_t)rw) & 15) == 0 && out32;
-        if (modconv) {
+        if (e.mask_y) {
+          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+          const float* mrw = nullptr;
+          if (e.mask_grgb) {
+            const float* gp = e.mask_grgb + (long long)n * e.rgb_sn + (long long)h * e.rgb_sh + w;
+            g0 = __ldg(gp); g1 = __ldg(gp + e.rgb_sj); g2 = __ldg(gp + 2 * e.rgb_sj);
+            mrw = e.rgb_w + (long long)n * 3 * p.n_out + o0;
+          }
+          hc_epilogue_actbwd<CW>(acc, e, acc_scale, ps, mrw, p.n_out, opix, g0, g1, g2);
+        } else if (modconv) {
           hc_epilogue_modconv<CW>(acc, e, acc_scale, nz, rs, bs, ps, rw, p.n_out, opix, rgb0, rgb1, rgb2);
         } else {
 #pragma unroll
@@ -844,6 +922,18 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   p.a_buf_bytes = ((uint32_t)(p.RB * p.Wp + 8) * (uint32_t)(KC * 2) + 1023u) & ~1023u;
   p.epi = d->epi;
   if (!p.epi.out_f32 && !p.epi.out_hi && !p.epi.out_raw && !p.epi.rgb_acc) return SMC_EINVAL;
+  if (p.epi.mask_y) {
+    // fused activation backward: the lean path needs 32-byte aligned fp16 planes and float4-aligned parameter vectors
+    const smc_igemm_epilogue& e = p.epi;
+    if (!e.post_scale || !e.out_hi || e.row_scale || e.bias || e.noise || e.residual || e.out_f32 || e.out_raw || e.out_raw_lo || e.rgb_acc)
+      return SMC_EINVAL;
+    if ((e.mask_grgb != nullptr) != (e.rgb_w != nullptr)) return SMC_EINVAL;
+    if ((((uintptr_t)e.mask_y | (uintptr_t)e.mask_y_lo | (uintptr_t)e.out_hi | (uintptr_t)e.out_lo) & 31) || (((uintptr_t)e.post_scale | (uintptr_t)e.rgb_w) & 15) ||
+        (((e.o_sn | e.o_sh | e.o_sw | e.o_off) * 2) & 31) || (d->n_out % 16 != 0))
+      return SMC_EUNSUPPORTED;
+  } else if (p.epi.mask_y_lo || p.epi.mask_grgb) {
+    return SMC_EINVAL;
+  } else
   if ((p.epi.rgb_acc != nullptr) != (p.epi.rgb_w != nullptr) || (p.epi.out_raw_lo && !p.epi.out_raw)) return SMC_EINVAL;
   if ((p.epi.o_sn | p.epi.o_sh | p.epi.o_sw | p.epi.o_off) & 7) return SMC_EUNSUPPORTED;
   const size_t smem = smem_fixed + (size_t)(p.na_hi + p.na_lo) * p.a_buf_bytes;

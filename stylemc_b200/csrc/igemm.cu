@@ -296,6 +296,7 @@ int igemm_launch(const smc_igemm_desc* d, cudaStream_t st) {
   }
   if (d->C % 32 != 0 || d->lda % 8 != 0 || d->ldb % 8 != 0) return SMC_EUNSUPPORTED;
   if (d->epi.out_raw_lo || d->epi.rgb_acc || d->epi.rgb_w) return SMC_EUNSUPPORTED;   // fused ToRGB lives in hconv.cu only
+  if (d->epi.mask_y || d->epi.mask_y_lo || d->epi.mask_grgb) return SMC_EUNSUPPORTED;    // so does the fused activation backward
   if (((uintptr_t)d->A & 15) || ((uintptr_t)d->B & 15)) return SMC_EINVAL;
   const int KC = (d->C % 64 == 0) ? 64 : 32;
   int BN = 0;

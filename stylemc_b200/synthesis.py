@@ -119,6 +119,7 @@ class SynthesisEngine:
         self.acc_k = 512 if precision == 'x3p' else 0
         self.acc_k_lowres, self.acc_k_lowres_max = 64, 16
         self.fuse_torgb = os.environ.get('STYLEMC_HCONV') != '0'      # the fused epilogue exists in hconv.cu only
+        self.fuse_act_bwd = os.environ.get('STYLEMC_FUSE_ACT_BWD') != '0'   # also needs fuse_torgb (both live in hconv.cu)
         self.precision, self.x3_max_res = ('x3' if precision == 'x3p' else precision), x3_max_res
         # style row of (conv0, conv1, torgb) per block (utils.py:169-185)
         self.rows, r = [], 0
@@ -144,6 +145,11 @@ class SynthesisEngine:
         if self.acc_k and res <= self.acc_k_lowres_max:
             return self.acc_k_lowres
         return self.acc_k
+
+    @staticmethod
+    def _hconv_shape(res, cin, cout):
+        """Shapes the halo-tile kernel (csrc/hconv.cu) takes in its default routing: the fused epilogues exist there only."""
+        return res >= 32 and cin % 32 == 0 and cout % 32 == 0
 
     def _fsep_ptr(self):
         return ctypes.addressof(self.fsep) if self.fsep is not None else None
@@ -362,20 +368,30 @@ class SynthesisEngine:
                     if r1 in want:
                         raise RuntimeError('trainable style rows in b4 are not implemented (reference trains b8..b64 only)')
                     break
-                gx1 = torch.empty([n, res, res, L1.cin], dtype=torch.float32 if two else torch.float16, device=dev)
-                gemm.igemm(gd1.reshape(-1, res, res, L1.cout), L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, precision=prec, acc_chunk_k=self.acc_k,
-                           a_plane_stride_imgs=n, b_rows_per_tap=9 * L1.cin, **(dict(out_f32=gx1) if two else dict(out_raw=gx1)))
                 L0 = blk.conv0
                 y0, d0 = saved.y0[k], saved.d0[k]
                 t1 = bufs(r1, L1.cin, L1.cout)[0] if r1 in want else None
                 rr = bufs(r0, L0.cin, L0.cout)[1] if r0 in want else None
                 gd0 = self._planes(n, res, res, L0.cout, two)
-                sp, ss = self._srow(styles, r1)
-                noise0 = self._noise(L0, noise_mode, n)
-                _lib.call('smc_act_bwd', _lib.ptr(y0[0]), _lib.ptr(y0[1]) if y0.shape[0] == 2 else None, n, res, res, L0.cout, _lib.ptr(gx1),
-                          int(two), sp, ss, None, None, None, 0, 0.0, None, -1.0, _lib.ptr(gscale), _lib.ptr(d0), _lib.ptr(noise0),
-                          _lib.ptr(L0.bias), LRELU_ALPHA, L0.gain, L0.clamp, _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None,
-                          _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
+                if self.fuse_torgb and self.fuse_act_bwd and t1 is None and rr is None and self._hconv_shape(res, L1.cout, L1.cin):
+                    # no style-gradient reduction wanted from this layer: the activation backward of conv0 (slope and clamp mask of the
+                    # saved y0, conv1's style, conv0's demodulation) is the epilogue of conv1's dgrad GEMM -- no fp32 round trip
+                    post = (styles[:, r1, :L1.cin] * d0).contiguous()
+                    gemm.igemm(gd1.reshape(-1, res, res, L1.cout), L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, precision=prec,
+                               acc_chunk_k=self.acc_k, a_plane_stride_imgs=n, b_rows_per_tap=9 * L1.cin, post_scale=post, alpha=LRELU_ALPHA,
+                               gain=L0.gain, clamp=L0.clamp, mask_y=y0[0], mask_y_lo=y0[1] if y0.shape[0] == 2 else None,
+                               out_hi=gd0[0], out_lo=gd0[1] if two else None)
+                else:
+                    gx1 = torch.empty([n, res, res, L1.cin], dtype=torch.float32 if two else torch.float16, device=dev)
+                    gemm.igemm(gd1.reshape(-1, res, res, L1.cout), L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, precision=prec,
+                               acc_chunk_k=self.acc_k, a_plane_stride_imgs=n, b_rows_per_tap=9 * L1.cin,
+                               **(dict(out_f32=gx1) if two else dict(out_raw=gx1)))
+                    sp, ss = self._srow(styles, r1)
+                    noise0 = self._noise(L0, noise_mode, n)
+                    _lib.call('smc_act_bwd', _lib.ptr(y0[0]), _lib.ptr(y0[1]) if y0.shape[0] == 2 else None, n, res, res, L0.cout, _lib.ptr(gx1),
+                              int(two), sp, ss, None, None, None, 0, 0.0, None, -1.0, _lib.ptr(gscale), _lib.ptr(d0), _lib.ptr(noise0),
+                              _lib.ptr(L0.bias), LRELU_ALPHA, L0.gain, L0.clamp, _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None,
+                              _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
                 hin = res // 2
                 gp = torch.empty([2 if two else 1, 4 * n, hin + 1, hin + 1, L0.cout], dtype=torch.float16, device=dev)
                 _lib.call('smc_fir_bwd', _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None, n, hin, hin, L0.cout, _lib.ptr(self.fk4), self._fsep_ptr(),
