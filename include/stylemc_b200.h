@@ -145,6 +145,8 @@ int smc_igemm_config(int key, int value);
 /* ---- synthesis glue (synth.cu) -------------------------------------------------------------------
  * Activations are NHWC fp16 ("hi" plane, optional "lo" plane = rn(v - hi)); styles are rows of the
  * [N, 26, 512] S tensor addressed as base pointer + n * stride. */
+/* A/B diagnostics (process-global, not thread-safe): key 0 / 1 / 2 = use the newer smc_fir_act / smc_fir_bwd / smc_act_bwd kernels (default 1). */
+int smc_synth_config(int key, int value);
 int smc_demod_coefs(const float* q, const float* s, int64_t s_stride, float* d, int n, int cin, int cout, void* stream);
 /* c_pitch >= c is the channel pitch of the NHWC side (channels c .. c_pitch-1 are left untouched: zero them once). */
 int smc_pack_nhwc(const float* x, int64_t x_stride_n, const float* s, int64_t s_stride, void* hi, void* lo, int n, int c,
@@ -156,8 +158,11 @@ int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int
                 const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
                 void* out_raw, void* out_raw_lo, void* out_hi, void* out_lo, void* stream);
 /* img[n, j, y, x] = clamp(img[n, j, y, x] + b[j]) + upsample2d(img_prev)[n, j, y, x]   (in place; img holds the fused-ToRGB sums of
- * smc_igemm's rgb_acc; ToRGBLayer bias/clamp and utils.py:45-49; img_prev [N, 3, H/2, W/2] or NULL for the first block). */
-int smc_img_finish(float* img, const float* img_prev, const float* b_rgb, float clamp, const float* fk_up, int n, int h, int w, void* stream);
+ * smc_igemm's rgb_acc; ToRGBLayer bias/clamp and utils.py:45-49; img_prev [N, 3, H/2, W/2] or NULL for the first block).
+ * pass_mask (optional, [N, 3, H, W] bytes): 1 where the clamp passes the gradient (|img + b| < clamp, bias_act.cu:136-142), kept for
+ * the backward pass so that it need not recompute the ToRGB output. */
+int smc_img_finish(float* img, const float* img_prev, const float* b_rgb, float clamp, const float* fk_up, int n, int h, int w,
+                   unsigned char* pass_mask, void* stream);
 int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w, int c, const float* w_rgb, const float* s_t,
               int64_t st_stride, float wgain, const float* b_rgb, float clamp, const float* img_prev, const float* fk_up,
               float* img, const float* s_next, int64_t sn_stride, void* xs_hi, void* xs_lo, void* stream);

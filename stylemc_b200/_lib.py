@@ -66,11 +66,12 @@ SIGNATURES = {
     'smc_upfirdn2d': 'ppp i p p',
     'smc_igemm': 'pp',
     'smc_igemm_config': 'ii',
+    'smc_synth_config': 'ii',
     'smc_demod_coefs': 'pp q p iii p',
     'smc_pack_nhwc': 'p q p q pp iiii p',
     'smc_unpack_nchw': 'p i pp iiii p',
     'smc_fir_act': 'p i iiii pppp fff p q pppp p',
-    'smc_img_finish': 'ppp f p iii p',
+    'smc_img_finish': 'ppp f p iii pp',
     'smc_torgb': 'pp iiii pp q f p f ppp p q pp p',
     'smc_act_bwd': 'pp iiii p i p q ppp q f p f pppp fff pppp p',
     'smc_fir_bwd': 'pp iiii pppp p',
@@ -116,6 +117,9 @@ def lib():
         for key, env in ((0, 'STYLEMC_HCONV'), (2, 'STYLEMC_HCONV_NB'), (3, 'STYLEMC_HCONV_WT'), (4, 'STYLEMC_HCONV_GRID'), (5, 'STYLEMC_HCONV_MASK'), (6, 'STYLEMC_HCONV_MINPOS')):
             if os.environ.get(env):          # diagnostics only: A/B the halo-tile conv kernel against the per-tap kernel
                 handle.smc_igemm_config(key, int(os.environ[env]))
+        for key, env in ((0, 'STYLEMC_FIR_ACT3'), (1, 'STYLEMC_FIR_BWD3'), (2, 'STYLEMC_ACT_BWD2')):
+            if os.environ.get(env):          # diagnostics only: A/B the newer glue kernels against the older ones
+                handle.smc_synth_config(key, int(os.environ[env]))
     return _lib
 
 
@@ -142,7 +146,7 @@ def require_cuda(t, name):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
-_LAUNCHES = {'smc_abi_version': 0, 'smc_igemm_config': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2}
+_LAUNCHES = {'smc_abi_version': 0, 'smc_igemm_config': 0, 'smc_synth_config': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2}
 launch_count = 0
 igemm_hook = None      # bench.py installs a callable(desc_addr) -> context manager to time every smc_igemm launch
 

@@ -435,6 +435,170 @@ __global__ void __launch_bounds__(256) fir_act2_kernel(const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// fir_act3: fir_act2 with the instruction count cut roughly in half (ncu on fir_act2: 48 warp instructions per output element, issue
+// slots 46 % busy, DRAM 54 %): channel count and output set are template parameters (plane/pixel offsets become immediates, no
+// pointer tests in the loop), packed fp32x2 FMAs (FFMA2) for both filter passes, gain folded into the vertical taps and the
+// bias (lrelu(x) * g = max(x g, x g alpha) for g > 0, 0 <= alpha <= 1), FMNMX3 for max + clamp, running pointers instead of
+// per-row 64-bit index arithmetic, L1-allocating loads (neighbouring threads share 3 of their 5 input columns).
+// Needs: fp32 planes, split outputs, H % JT == 0, (H + 1) * (W + 1) * C < 2^31.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// two fp32 pairs -> 4 fp16 hi and 4 fp16 lo = rn(v - hi)
+// hi - v in one instruction (sm_100 mixed-precision add: FHADD), hi = one half of a packed pair
+__device__ __forceinline__ void hsubf2(uint32_t hh, float v0, float v1, float& d0, float& d1) {
+  asm("{\n\t"
+      ".reg .b16 h0, h1;\n\t"
+      "mov.b32 {h0, h1}, %2;\n\t"
+      "sub.rn.f32.f16 %0, h0, %3;\n\t"
+      "sub.rn.f32.f16 %1, h1, %4;\n\t"
+      "}" : "=f"(d0), "=f"(d1) : "r"(hh), "f"(v0), "f"(v1));
+}
+__device__ __forceinline__ void split4(float2 p, float2 q, uint2& hi, uint2& lo) {
+  const __half2 a = __floats2half2_rn(p.x, p.y), b = __floats2half2_rn(q.x, q.y);
+  const uint32_t ua = *reinterpret_cast<const uint32_t*>(&a), ub = *reinterpret_cast<const uint32_t*>(&b);
+  float d0, d1, d2, d3;
+  hsubf2(ua, p.x, p.y, d0, d1);
+  hsubf2(ub, q.x, q.y, d2, d3);
+  const __half2 la = __floats2half2_rn(d0, d1), lb = __floats2half2_rn(d2, d3);
+  hi = make_uint2(ua, ub);
+  // lo = rn(v - hi) = -rn(hi - v): flip the two sign bits
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&la) ^ 0x80008000u, *reinterpret_cast<const uint32_t*>(&lb) ^ 0x80008000u);
+}
+
+template <int C, int JT, bool SAVE, bool NOISE>
+__global__ void __launch_bounds__(256, 2) fir_act3_kernel(const float* __restrict__ planes, int N, int H, int W, float4 fyw, float4 fxw,
+                                                          const float* __restrict__ noise, const float* __restrict__ bias, float alpha, float gain,
+                                                          float clamp, const float* __restrict__ post, long long post_stride,
+                                                          __half* __restrict__ out_raw, __half* __restrict__ out_raw_lo,
+                                                          __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  constexpr int CG4 = C / 4, KCOLS = 256 / CG4;
+  const int g = threadIdx.x % CG4, kl = threadIdx.x / CG4;
+  const int k = blockIdx.x * KCOLS + kl;
+  if (k >= W) return;
+  const int c = g * 4;
+  const int n = blockIdx.z;
+  const int j0 = blockIdx.y * JT;
+  const long long plane_sz = (long long)N * (H + 1) * (W + 1) * C;
+  const int pitch = (W + 1) * C;
+  const float2 fx0 = make_float2(fxw.x, fxw.x), fx1 = make_float2(fxw.y, fxw.y), fx2 = make_float2(fxw.z, fxw.z), fx3 = make_float2(fxw.w, fxw.w);
+  const float2 fy0 = make_float2(fyw.x * gain, fyw.x * gain), fy1 = make_float2(fyw.y * gain, fyw.y * gain),
+               fy2 = make_float2(fyw.z * gain, fyw.z * gain), fy3 = make_float2(fyw.w * gain, fyw.w * gain);
+  const float2 gain2 = make_float2(gain, gain), alpha2 = make_float2(alpha, alpha);
+  const float cl = clamp >= 0.f ? clamp : __int_as_float(0x7f800000), ncl = -cl;
+  float2 bsg[2], ps[2];
+  {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+    bsg[0] = make_float2(b4.x * gain, b4.y * gain); bsg[1] = make_float2(b4.z * gain, b4.w * gain);
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(post + n * post_stride + c));
+    ps[0] = make_float2(p4.x, p4.y); ps[1] = make_float2(p4.z, p4.w);
+  }
+  const bool left_ok = k > 0, right_ok = k < W - 1;
+  // column k of plane (row parity 0, column parity 0) / (0, 1) of image n, plane row (j0 - 1) for odd t rows and j0 for even ones;
+  // row-parity-1 planes lie 2 * plane_sz further
+  const float* pe = planes + (long long)n * (H + 1) * pitch + (long long)k * C + c;          // even t rows: plane row = ty / 2
+  const float* pe1 = pe + plane_sz;
+  const float* po = pe + 2 * plane_sz;                                                       // odd t rows: plane row = (ty - 1) / 2
+  const float* po1 = po + plane_sz;
+  auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+  // horizontally filtered row for the two output columns 2k, 2k + 1: h[b][half] (half = channel pair)
+  auto hrow = [&](const float* r0, const float* r1, float2 (&h)[2][2]) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 t0 = left_ok ? ld4(r1 - C) : z;    // t column 2k - 1
+    const float4 t1 = ld4(r0);                      // 2k
+    const float4 t2 = ld4(r1);                      // 2k + 1
+    const float4 t3 = ld4(r0 + C);                  // 2k + 2
+    const float4 t4 = right_ok ? ld4(r1 + C) : z;   // 2k + 3
+    h[0][0] = ffma2(fx3, make_float2(t3.x, t3.y), ffma2(fx2, make_float2(t2.x, t2.y), ffma2(fx1, make_float2(t1.x, t1.y), fmul2(fx0, make_float2(t0.x, t0.y)))));
+    h[0][1] = ffma2(fx3, make_float2(t3.z, t3.w), ffma2(fx2, make_float2(t2.z, t2.w), ffma2(fx1, make_float2(t1.z, t1.w), fmul2(fx0, make_float2(t0.z, t0.w)))));
+    h[1][0] = ffma2(fx3, make_float2(t4.x, t4.y), ffma2(fx2, make_float2(t3.x, t3.y), ffma2(fx1, make_float2(t2.x, t2.y), fmul2(fx0, make_float2(t1.x, t1.y)))));
+    h[1][1] = ffma2(fx3, make_float2(t4.z, t4.w), ffma2(fx2, make_float2(t3.z, t3.w), ffma2(fx1, make_float2(t2.z, t2.w), fmul2(fx0, make_float2(t1.z, t1.w)))));
+  };
+  auto zrow = [](float2 (&h)[2][2]) {
+    h[0][0] = h[0][1] = h[1][0] = h[1][1] = make_float2(0.f, 0.f);
+  };
+  float2 hw[5][2][2];
+  // t rows 2 j0 - 1 (odd, plane row j0 - 1), 2 j0 (even, plane row j0), 2 j0 + 1 (odd, plane row j0)
+  if (j0 > 0) hrow(po + (long long)(j0 - 1) * pitch, po1 + (long long)(j0 - 1) * pitch, hw[0]); else zrow(hw[0]);
+  pe += (long long)j0 * pitch; pe1 += (long long)j0 * pitch; po += (long long)j0 * pitch; po1 += (long long)j0 * pitch;
+  hrow(pe, pe1, hw[1]);
+  hrow(po, po1, hw[2]);
+  const long long orow = (long long)(2 * W) * C;                                             // elements per output row
+  long long o = (((long long)n * (2 * H) + 2 * j0) * (2 * W) + 2 * k) * C + c;
+  const float* nzp = NOISE ? noise + (long long)(2 * j0) * (2 * W) + 2 * k : nullptr;
+#pragma unroll 1
+  for (int j = j0; j < j0 + JT; ++j) {
+    // t rows 2j + 2 (even, plane row j + 1: always inside) and 2j + 3 (odd, plane row j + 1: outside the grid when j == H - 1)
+    pe += pitch; pe1 += pitch; po += pitch; po1 += pitch;
+    hrow(pe, pe1, hw[3]);
+    if (j < H - 1) hrow(po, po1, hw[4]); else zrow(hw[4]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        float2 nb0 = bsg[0], nb1 = bsg[1];
+        if (NOISE) {
+          const float nz = __ldg(nzp + a * (2 * W) + b);
+          nb0 = ffma2(make_float2(nz, nz), gain2, bsg[0]);
+          nb1 = ffma2(make_float2(nz, nz), gain2, bsg[1]);
+        }
+        float2 v0 = ffma2(fy3, hw[a + 3][b][0], ffma2(fy2, hw[a + 2][b][0], ffma2(fy1, hw[a + 1][b][0], ffma2(fy0, hw[a][b][0], nb0))));
+        float2 v1 = ffma2(fy3, hw[a + 3][b][1], ffma2(fy2, hw[a + 2][b][1], ffma2(fy1, hw[a + 1][b][1], ffma2(fy0, hw[a][b][1], nb1))));
+        const float2 m0 = fmul2(v0, alpha2), m1 = fmul2(v1, alpha2);
+        v0.x = fminf(fmax3(v0.x, m0.x, ncl), cl); v0.y = fminf(fmax3(v0.y, m0.y, ncl), cl);
+        v1.x = fminf(fmax3(v1.x, m1.x, ncl), cl); v1.y = fminf(fmax3(v1.y, m1.y, ncl), cl);
+        const long long oo = o + a * orow + b * C;
+        uint2 hi, lo;
+        if (SAVE) {
+          split4(v0, v1, hi, lo);
+          *reinterpret_cast<uint2*>(out_raw + oo) = hi;
+          *reinterpret_cast<uint2*>(out_raw_lo + oo) = lo;
+        }
+        split4(fmul2(v0, ps[0]), fmul2(v1, ps[1]), hi, lo);
+        *reinterpret_cast<uint2*>(out_hi + oo) = hi;
+        *reinterpret_cast<uint2*>(out_lo + oo) = lo;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { hw[0][b][e] = hw[2][b][e]; hw[1][b][e] = hw[3][b][e]; hw[2][b][e] = hw[4][b][e]; }
+    o += 2 * orow;
+    if (NOISE) nzp += 2 * (2 * W);
+  }
+}
+
+template <int C>
+static int launch_fir_act3(const float* planes, int n, int h, int w, float4 fyw, float4 fxw, const float* noise, const float* bias, float alpha,
+                           float gain, float clamp, const float* post, long long post_stride, __half* out_raw, __half* out_raw_lo, __half* out_hi,
+                           __half* out_lo, cudaStream_t st) {
+  constexpr int JT = 16, KCOLS = 256 / (C / 4);
+  dim3 grid(ceil_div(w, KCOLS), h / JT, n);
+  if (grid.y > 65535 || grid.z > 65535) return SMC_ETOOLARGE;
+#define SMC_FA3(SAVE, NOISE)                                                                                                                   \
+  fir_act3_kernel<C, JT, SAVE, NOISE><<<grid, 256, 0, st>>>(planes, n, h, w, fyw, fxw, noise, bias, alpha, gain, clamp, post, post_stride, out_raw, \
+                                                            out_raw_lo, out_hi, out_lo)
+  if (out_raw) { if (noise) SMC_FA3(true, true); else SMC_FA3(true, false); }
+  else { if (noise) SMC_FA3(false, true); else SMC_FA3(false, false); }
+#undef SMC_FA3
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
 // Transposed FIR (fir_bwd) for a separable filter, same marching scheme: one thread = one cell column (t columns 2b, 2b+1) x
 // 4 channels, 5-row window of horizontally filtered gd rows.
 template <int JT>
@@ -523,7 +687,8 @@ __global__ void __launch_bounds__(256) fir_bwd2_kernel(const __half* __restrict_
 // Tail of the fused ToRGB path (the conv1 epilogue of hconv.cu accumulated the 1x1 modulated conv into img):
 // img = clamp(img + b[j]) + upsample2d(img_prev)   (ToRGBLayer bias_act(clamp) [UPSTREAM]; utils.py:45-49).
 __global__ void __launch_bounds__(256) img_finish_kernel(float* __restrict__ img, const float* __restrict__ img_prev, const float* __restrict__ b_rgb,
-                                                         float clamp, const float* __restrict__ fk_up, int N, int H, int W) {
+                                                         float clamp, const float* __restrict__ fk_up, int N, int H, int W,
+                                                         unsigned char* __restrict__ pass_mask) {
   const long long total = (long long)N * 3 * H * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int xq = (int)(idx % W);
@@ -531,6 +696,7 @@ __global__ void __launch_bounds__(256) img_finish_kernel(float* __restrict__ img
     const int yy = (int)(t % H);
     const long long nj = t / H;
     float r = img[idx] + __ldg(b_rgb + (int)(nj % 3));
+    if (pass_mask) pass_mask[idx] = (clamp < 0.f || (r > -clamp && r < clamp)) ? 1 : 0;
     if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
     if (img_prev) {
       const int h2 = H >> 1, w2 = W >> 1;
@@ -1178,6 +1344,18 @@ extern "C" int smc_unpack_nchw(const void* x, int x_is_half, float* y, const flo
   return SMC_OK;
 }
 
+static int g_fir_act3 = 1;   // 0: keep the older marching kernel (A/B diagnostics, smc_synth_config key 0)
+static int g_fir_bwd3 = 1;   // same for smc_fir_bwd (key 1)
+static int g_act_bwd2 = 1;   // same for smc_act_bwd (key 2)
+
+extern "C" int smc_synth_config(int key, int value) {
+  if (key == 0) g_fir_act3 = value;
+  else if (key == 1) g_fir_bwd3 = value;
+  else if (key == 2) g_act_bwd2 = value;
+  else return SMC_EINVAL;
+  return SMC_OK;
+}
+
 extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int c, const float* fk, const float* fsep_host,
                            const float* noise, const float* bias, float alpha, float gain, float clamp, const float* post, int64_t post_stride,
                            void* out_raw, void* out_raw_lo, void* out_hi, void* out_lo, void* stream) {
@@ -1187,6 +1365,22 @@ extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h,
     constexpr int JT = 16;
     const float4 fyw = make_float4(fsep_host[0], fsep_host[1], fsep_host[2], fsep_host[3]);
     const float4 fxw = make_float4(fsep_host[4], fsep_host[5], fsep_host[6], fsep_host[7]);
+    if (g_fir_act3 && out_hi && out_lo && post && (!out_raw || out_raw_lo) && h % JT == 0 && gain > 0.f && alpha >= 0.f && alpha <= 1.f &&
+        (long long)(h + 1) * (w + 1) * c < 0x7fffffffLL && ((((uintptr_t)planes | (uintptr_t)bias | (uintptr_t)post) & 15) == 0) &&
+        (post_stride & 3) == 0) {
+#define SMC_FA3C(CC)                                                                                                                        \
+  case CC: return launch_fir_act3<CC>((const float*)planes, n, h, w, fyw, fxw, noise, bias, alpha, gain, clamp, post, post_stride, (__half*)out_raw, \
+                                      (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo, (cudaStream_t)stream)
+      switch (c) {
+        SMC_FA3C(32);
+        SMC_FA3C(64);
+        SMC_FA3C(128);
+        SMC_FA3C(256);
+        SMC_FA3C(512);
+        default: break;
+      }
+#undef SMC_FA3C
+    }
     const int kcols = 256 / (c >> 2);
     dim3 grid(ceil_div(w, kcols), ceil_div(h, JT), n);
     if (grid.y > 65535 || grid.z > 65535) return SMC_ETOOLARGE;
@@ -1210,7 +1404,8 @@ extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h,
 // img_finish for W % 4 == 0: one thread = 4 consecutive pixels of a row (one float4 read-modify-write); the 2 x 4 source values of
 // the previous image that the 4x4 up-sampling filter touches are loaded once.
 __global__ void __launch_bounds__(256) img_finish4_kernel(float* __restrict__ img, const float* __restrict__ img_prev, const float* __restrict__ b_rgb,
-                                                          float clamp, const float* __restrict__ fk_up, int N, int H, int W) {
+                                                          float clamp, const float* __restrict__ fk_up, int N, int H, int W,
+                                                          unsigned char* __restrict__ pass_mask) {
   const int wq = W >> 2;
   const long long total = (long long)N * 3 * H * wq;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -1222,6 +1417,14 @@ __global__ void __launch_bounds__(256) img_finish4_kernel(float* __restrict__ im
     float4 v = *p4;
     const float b = __ldg(b_rgb + (int)(nj % 3));
     float r[4] = {v.x + b, v.y + b, v.z + b, v.w + b};
+    if (pass_mask) {
+      uchar4 m;
+      m.x = (clamp < 0.f || (r[0] > -clamp && r[0] < clamp)) ? 1 : 0;
+      m.y = (clamp < 0.f || (r[1] > -clamp && r[1] < clamp)) ? 1 : 0;
+      m.z = (clamp < 0.f || (r[2] > -clamp && r[2] < clamp)) ? 1 : 0;
+      m.w = (clamp < 0.f || (r[3] > -clamp && r[3] < clamp)) ? 1 : 0;
+      reinterpret_cast<uchar4*>(pass_mask + (nj * H + yy) * (long long)W)[q] = m;
+    }
     if (clamp >= 0.f) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) r[i] = fminf(fmaxf(r[i], -clamp), clamp);
@@ -1256,13 +1459,14 @@ __global__ void __launch_bounds__(256) img_finish4_kernel(float* __restrict__ im
 }
 
 extern "C" int smc_img_finish(float* img, const float* img_prev, const float* b_rgb, float clamp, const float* fk_up, int n, int h, int w,
-                              void* stream) {
+                              unsigned char* pass_mask, void* stream) {
   if (!img || !b_rgb || n < 1 || h < 1 || w < 1) return SMC_EINVAL;
   if (img_prev && (!fk_up || (h & 1) || (w & 1))) return SMC_EINVAL;
-  if ((w & 3) == 0 && (((uintptr_t)img) & 15) == 0)
-    img_finish4_kernel<<<grid_for((long long)n * 3 * h * (w >> 2), 256), 256, 0, (cudaStream_t)stream>>>(img, img_prev, b_rgb, clamp, fk_up, n, h, w);
+  if ((w & 3) == 0 && (((uintptr_t)img) & 15) == 0 && (((uintptr_t)pass_mask) & 3) == 0)
+    img_finish4_kernel<<<grid_for((long long)n * 3 * h * (w >> 2), 256), 256, 0, (cudaStream_t)stream>>>(img, img_prev, b_rgb, clamp, fk_up, n, h, w,
+                                                                                                        pass_mask);
   else
-    img_finish_kernel<<<grid_for((long long)n * 3 * h * w, 256), 256, 0, (cudaStream_t)stream>>>(img, img_prev, b_rgb, clamp, fk_up, n, h, w);
+    img_finish_kernel<<<grid_for((long long)n * 3 * h * w, 256), 256, 0, (cudaStream_t)stream>>>(img, img_prev, b_rgb, clamp, fk_up, n, h, w, pass_mask);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

@@ -83,6 +83,7 @@ class SavedForward:
 
     def __init__(self):
         self.y0, self.y1, self.d0, self.d1 = {}, {}, {}, {}
+        self.rgb_pass = {}        # block -> [N, 3, H, W] uint8, 1 where the ToRGB clamp passes the gradient (fused-ToRGB blocks only)
         self.styles = None
         self.until_k = None
 
@@ -271,8 +272,11 @@ class SynthesisEngine:
                     y1, xs_next, new_img = self._conv1_fused(L1, T, xs, d1, self._noise(L1, noise_mode, n), styles, rt,
                                                              self.rows[k + 1][0] if has_next else None, n, res, prec, two,
                                                              keep_y=save or want_xs, next_two=nprec_two)
+                    rgb_pass = torch.empty([n, 3, res, res], dtype=torch.uint8, device=self.device) if (save and has_next) else None
                     _lib.call('smc_img_finish', _lib.ptr(new_img), _lib.ptr(img), _lib.ptr(T.bias), T.clamp, _lib.ptr(self.fk4), n, res, res,
-                              _lib.stream())
+                              _lib.ptr(rgb_pass), _lib.stream())
+                    if rgb_pass is not None:
+                        saved.rgb_pass[k] = rgb_pass
                     xs = xs_next
                 else:
                     y1 = self._conv1(L1, xs, d1, self._noise(L1, noise_mode, n), n, res, prec, two)
@@ -337,6 +341,7 @@ class SynthesisEngine:
                 return acc[row]
 
             g_up, up_row, up_f32 = None, None, False   # gradient w.r.t. the modulated input of the consumer conv above, its style row, dtype
+            gd1_fused = None                           # conv1's gd planes already produced by the epilogue of the dgrad GEMM above
             for k in range(last, -1, -1):
                 blk = self.blocks[k]
                 res = blk.resolution
@@ -350,17 +355,20 @@ class SynthesisEngine:
                 t1 = bufs(up_row, L1.cout, self.blocks[k + 1].conv0.cout)[0] if (g_up is not None and up_row in want) else None
                 rr = bufs(r1, L1.cin, L1.cout)[1] if r1 in want else None
                 need_gd = not stop_here
-                if not need_gd and t1 is None:
-                    break
-                gd1 = self._planes(n, res, res, L1.cout, two) if need_gd else None
-                sp, ss = self._srow(styles, up_row) if g_up is not None else (None, 0)
-                stp, sts = self._srow(styles, rt)
-                noise1 = self._noise(L1, noise_mode, n)
-                _lib.call('smc_act_bwd', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if y1.shape[0] == 2 else None, n, res, res, L1.cout,
-                          _lib.ptr(g_up), int(up_f32), sp, ss, _lib.ptr(g_img) if need_gd else None, _lib.ptr(T.w), stp, sts, T.wgain,
-                          _lib.ptr(T.bias), T.clamp, _lib.ptr(gscale), _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA,
-                          L1.gain, L1.clamp, _lib.ptr(gd1[0]) if need_gd else None, _lib.ptr(gd1[1]) if (need_gd and two) else None,
-                          _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
+                if gd1_fused is not None:
+                    gd1, gd1_fused = gd1_fused, None
+                else:
+                    if not need_gd and t1 is None:
+                        break
+                    gd1 = self._planes(n, res, res, L1.cout, two) if need_gd else None
+                    sp, ss = self._srow(styles, up_row) if g_up is not None else (None, 0)
+                    stp, sts = self._srow(styles, rt)
+                    noise1 = self._noise(L1, noise_mode, n)
+                    _lib.call('smc_act_bwd', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if y1.shape[0] == 2 else None, n, res, res, L1.cout,
+                              _lib.ptr(g_up), int(up_f32), sp, ss, _lib.ptr(g_img) if need_gd else None, _lib.ptr(T.w), stp, sts, T.wgain,
+                              _lib.ptr(T.bias), T.clamp, _lib.ptr(gscale), _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA,
+                              L1.gain, L1.clamp, _lib.ptr(gd1[0]) if need_gd else None, _lib.ptr(gd1[1]) if (need_gd and two) else None,
+                              _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
                 if stop_here:
                     break
                 # ---- dgrad conv1 -> gradient w.r.t. (y0 * s1) (or const * s1 for b4)
@@ -396,13 +404,33 @@ class SynthesisEngine:
                 gp = torch.empty([2 if two else 1, 4 * n, hin + 1, hin + 1, L0.cout], dtype=torch.float16, device=dev)
                 _lib.call('smc_fir_bwd', _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None, n, hin, hin, L0.cout, _lib.ptr(self.fk4), self._fsep_ptr(),
                           _lib.ptr(gp[0]), _lib.ptr(gp[1]) if two else None, _lib.stream())
-                g_up = torch.empty([n, hin, hin, L0.cin], dtype=torch.float32 if two else torch.float16, device=dev)
-                gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=prec, acc_chunk_k=self.acc_k,
-                           a_plane_stride_imgs=4 * n, b_rows_per_tap=9 * L0.cin, **(dict(out_f32=g_up) if two else dict(out_raw=g_up)))
-                up_row, up_f32 = r0, two
                 # ---- skip image: transpose of upsample2d (upfirdn2d.py:245-264)
                 if k > 0:
                     g_img = upfirdn2d.upfirdn2d(g_img, self.filter, down=2, padding=[1, 1, 1, 1], flip_filter=True, gain=4)
+                # ---- dgrad conv0 -> gradient w.r.t. (y1 of the block below * s0)
+                Lp, Tp = self.blocks[k - 1].conv1, self.blocks[k - 1].torgb
+                pr1, prt = self.rows[k - 1][1], self.rows[k - 1][2]
+                two_p = self._prec(self.blocks[k - 1].resolution) == 'x3'
+                if (self.fuse_torgb and self.fuse_act_bwd and (k - 1) in saved.rgb_pass and k - 1 >= lowest_k and r0 not in want and pr1 not in want
+                        and two_p == two and self._hconv_shape(hin, L0.cout, L0.cin)):
+                    # the block below needs no style-gradient reduction either: its conv1 activation backward, ToRGB branch included
+                    # (g_rgb masked by the clamp mask saved in the forward pass), is the epilogue of this dgrad GEMM
+                    y1p, d1p = saved.y1[k - 1], saved.d1[k - 1]
+                    grgb = (g_img * saved.rgb_pass[k - 1]) * gscale
+                    post = (styles[:, r0, :L0.cin] * d1p).contiguous()
+                    rgbw = ((styles[:, prt, :Lp.cout] * Tp.wgain * d1p).unsqueeze(1) * Tp.w.unsqueeze(0)).contiguous()      # [n, 3, C]
+                    gd1_fused = self._planes(n, hin, hin, Lp.cout, two)
+                    gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=prec,
+                               acc_chunk_k=self.acc_k, a_plane_stride_imgs=4 * n, b_rows_per_tap=9 * L0.cin, post_scale=post, alpha=LRELU_ALPHA,
+                               gain=Lp.gain, clamp=Lp.clamp, mask_y=y1p[0], mask_y_lo=y1p[1] if y1p.shape[0] == 2 else None, mask_grgb=grgb,
+                               rgb_w=rgbw, out_hi=gd1_fused[0], out_lo=gd1_fused[1] if two else None)
+                    g_up = None
+                else:
+                    g_up = torch.empty([n, hin, hin, L0.cin], dtype=torch.float32 if two else torch.float16, device=dev)
+                    gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=prec,
+                               acc_chunk_k=self.acc_k, a_plane_stride_imgs=4 * n, b_rows_per_tap=9 * L0.cin,
+                               **(dict(out_f32=g_up) if two else dict(out_raw=g_up)))
+                up_row, up_f32 = r0, two
             for i, row in enumerate(trainable_rows):
                 k, which = owner[row]
                 L = self.blocks[k].conv1 if which == 1 else self.blocks[k].conv0
