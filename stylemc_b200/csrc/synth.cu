@@ -480,8 +480,8 @@ __device__ __forceinline__ void split4(float2 p, float2 q, uint2& hi, uint2& lo)
   lo = make_uint2(*reinterpret_cast<const uint32_t*>(&la) ^ 0x80008000u, *reinterpret_cast<const uint32_t*>(&lb) ^ 0x80008000u);
 }
 
-template <int C, int JT, bool SAVE, bool NOISE>
-__global__ void __launch_bounds__(256, 2) fir_act3_kernel(const float* __restrict__ planes, int N, int H, int W, float4 fyw, float4 fxw,
+template <int C, int JT, int SAVE /* 0: no raw output, 1: hi plane only, 2: hi + lo */, bool NOISE, int MINB>
+__global__ void __launch_bounds__(256, MINB) fir_act3_kernel(const float* __restrict__ planes, int N, int H, int W, float4 fyw, float4 fxw,
                                                           const float* __restrict__ noise, const float* __restrict__ bias, float alpha, float gain,
                                                           float clamp, const float* __restrict__ post, long long post_stride,
                                                           __half* __restrict__ out_raw, __half* __restrict__ out_raw_lo,
@@ -563,10 +563,13 @@ __global__ void __launch_bounds__(256, 2) fir_act3_kernel(const float* __restric
         v1.x = fminf(fmax3(v1.x, m1.x, ncl), cl); v1.y = fminf(fmax3(v1.y, m1.y, ncl), cl);
         const long long oo = o + a * orow + b * C;
         uint2 hi, lo;
-        if (SAVE) {
+        if (SAVE == 2) {
           split4(v0, v1, hi, lo);
           *reinterpret_cast<uint2*>(out_raw + oo) = hi;
           *reinterpret_cast<uint2*>(out_raw_lo + oo) = lo;
+        } else if (SAVE == 1) {
+          const __half2 a2 = __floats2half2_rn(v0.x, v0.y), b2 = __floats2half2_rn(v1.x, v1.y);
+          *reinterpret_cast<uint2*>(out_raw + oo) = make_uint2(*reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&b2));
         }
         split4(fmul2(v0, ps[0]), fmul2(v1, ps[1]), hi, lo);
         *reinterpret_cast<uint2*>(out_hi + oo) = hi;
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(256, 2) fir_act3_kernel(const float* __restric
   }
 }
 
-template <int C>
+template <int C, int MINB>
 static int launch_fir_act3(const float* planes, int n, int h, int w, float4 fyw, float4 fxw, const float* noise, const float* bias, float alpha,
                            float gain, float clamp, const float* post, long long post_stride, __half* out_raw, __half* out_raw_lo, __half* out_hi,
                            __half* out_lo, cudaStream_t st) {
@@ -590,10 +593,11 @@ static int launch_fir_act3(const float* planes, int n, int h, int w, float4 fyw,
   dim3 grid(ceil_div(w, KCOLS), h / JT, n);
   if (grid.y > 65535 || grid.z > 65535) return SMC_ETOOLARGE;
 #define SMC_FA3(SAVE, NOISE)                                                                                                                   \
-  fir_act3_kernel<C, JT, SAVE, NOISE><<<grid, 256, 0, st>>>(planes, n, h, w, fyw, fxw, noise, bias, alpha, gain, clamp, post, post_stride, out_raw, \
+  fir_act3_kernel<C, JT, SAVE, NOISE, MINB><<<grid, 256, 0, st>>>(planes, n, h, w, fyw, fxw, noise, bias, alpha, gain, clamp, post, post_stride, out_raw, \
                                                             out_raw_lo, out_hi, out_lo)
-  if (out_raw) { if (noise) SMC_FA3(true, true); else SMC_FA3(true, false); }
-  else { if (noise) SMC_FA3(false, true); else SMC_FA3(false, false); }
+  if (out_raw && out_raw_lo) { if (noise) SMC_FA3(2, true); else SMC_FA3(2, false); }
+  else if (out_raw) { if (noise) SMC_FA3(1, true); else SMC_FA3(1, false); }
+  else { if (noise) SMC_FA3(0, true); else SMC_FA3(0, false); }
 #undef SMC_FA3
   SMC_LAUNCH_CHECK();
   return SMC_OK;
@@ -1344,7 +1348,7 @@ extern "C" int smc_unpack_nchw(const void* x, int x_is_half, float* y, const flo
   return SMC_OK;
 }
 
-static int g_fir_act3 = 1;   // 0: keep the older marching kernel (A/B diagnostics, smc_synth_config key 0)
+static int g_fir_act3 = 3;   // 0: keep the older marching kernel; 2 / 3 / 4: fir_act3 with that many resident blocks per SM (smc_synth_config key 0)
 static int g_fir_bwd3 = 1;   // same for smc_fir_bwd (key 1)
 static int g_act_bwd2 = 1;   // same for smc_act_bwd (key 2)
 
@@ -1365,12 +1369,19 @@ extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h,
     constexpr int JT = 16;
     const float4 fyw = make_float4(fsep_host[0], fsep_host[1], fsep_host[2], fsep_host[3]);
     const float4 fxw = make_float4(fsep_host[4], fsep_host[5], fsep_host[6], fsep_host[7]);
-    if (g_fir_act3 && out_hi && out_lo && post && (!out_raw || out_raw_lo) && h % JT == 0 && gain > 0.f && alpha >= 0.f && alpha <= 1.f &&
+    if (g_fir_act3 && out_hi && out_lo && post && (out_raw || !out_raw_lo) && h % JT == 0 && gain > 0.f && alpha >= 0.f && alpha <= 1.f &&
         (long long)(h + 1) * (w + 1) * c < 0x7fffffffLL && ((((uintptr_t)planes | (uintptr_t)bias | (uintptr_t)post) & 15) == 0) &&
         (post_stride & 3) == 0) {
 #define SMC_FA3C(CC)                                                                                                                        \
-  case CC: return launch_fir_act3<CC>((const float*)planes, n, h, w, fyw, fxw, noise, bias, alpha, gain, clamp, post, post_stride, (__half*)out_raw, \
-                                      (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo, (cudaStream_t)stream)
+  case CC:                                                                                                                                   \
+    if (g_fir_act3 == 2)                                                                                                                     \
+      return launch_fir_act3<CC, 2>((const float*)planes, n, h, w, fyw, fxw, noise, bias, alpha, gain, clamp, post, post_stride, (__half*)out_raw, \
+                                    (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo, (cudaStream_t)stream);                          \
+    if (g_fir_act3 == 4)                                                                                                                     \
+      return launch_fir_act3<CC, 4>((const float*)planes, n, h, w, fyw, fxw, noise, bias, alpha, gain, clamp, post, post_stride, (__half*)out_raw, \
+                                    (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo, (cudaStream_t)stream);                          \
+    return launch_fir_act3<CC, 3>((const float*)planes, n, h, w, fyw, fxw, noise, bias, alpha, gain, clamp, post, post_stride, (__half*)out_raw,  \
+                                  (__half*)out_raw_lo, (__half*)out_hi, (__half*)out_lo, (cudaStream_t)stream)
       switch (c) {
         SMC_FA3C(32);
         SMC_FA3C(64);

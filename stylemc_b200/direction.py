@@ -114,7 +114,7 @@ class DirectionFinder:
         for lo in range(0, n_total, self.micro_batch):
             s = styles[lo:lo + self.micro_batch].to(self.device, torch.float32)
             s2 = s + direction                                                        # find_direction.py:308
-            _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True)                 # :309
+            _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True, grad_rows=self.rows)   # :309
             _, original, _ = eng.forward(s, self.until_k, self.noise_mode, save=False)                # :312
             u_t = resample.unprocess_fwd(img)                                                      # :159-160
             u_s = resample.unprocess_fwd(original)

@@ -193,11 +193,11 @@ class SynthesisEngine:
         threads add into each rgb value, so the atomic accumulation is order-independent (deterministic)."""
         return res >= 32 and L.cin % 32 == 0 and L.cout % 32 == 0 and L.cout <= 128
 
-    def _conv1_fused(self, L, T, xs, d, noise, styles, rt, row_next, n, res, prec, two, keep_y, next_two):
+    def _conv1_fused(self, L, T, xs, d, noise, styles, rt, row_next, n, res, prec, two, keep_y, next_two, y_full=True):
         """conv1 with everything that consumes its output fused into the GEMM epilogue: the saved activation y (hi/lo, only when
         it is needed), xs_next = y * styles[:, row_next] for the next block's conv0, and the ToRGB 1x1 modulated conv accumulated
         into a zeroed fp32 image (finished by smc_img_finish).  Returns (y or None, xs_next or None, rgb accumulator)."""
-        y = self._planes(n, res, res, L.cout, two) if keep_y else None
+        y = self._planes(n, res, res, L.cout, two and y_full) if keep_y else None
         xn = self._planes(n, res, res, L.cout, next_two) if row_next is not None else None
         post = styles[:, row_next, :L.cout].contiguous() if row_next is not None else None
         rgb_w = ((styles[:, rt, :L.cout] * T.wgain).unsqueeze(1) * T.w.unsqueeze(0)).contiguous()        # [n, 3, C]
@@ -205,12 +205,12 @@ class SynthesisEngine:
         gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec, acc_chunk_k=self._acc_k(res),
                    a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, bias=L.bias, noise=noise,
                    noise_strides=(res, 1), act=1, alpha=LRELU_ALPHA, gain=L.gain, clamp=L.clamp,
-                   out_raw=y[0] if keep_y else None, out_raw_lo=y[1] if (keep_y and two) else None,
+                   out_raw=y[0] if keep_y else None, out_raw_lo=y[1] if (keep_y and y.shape[0] == 2) else None,
                    post_scale=post, out_hi=xn[0] if xn is not None else None, out_lo=xn[1] if (xn is not None and next_two) else None,
                    rgb_w=rgb_w, rgb_acc=acc)
         return y, xn, acc
 
-    def _conv0(self, L, xs, d, noise, styles, row_next, n, hin, prec, want_lo, save_lo=False):
+    def _conv0(self, L, xs, d, noise, styles, row_next, n, hin, prec, want_lo, save_lo=False, save_full=True):
         """3x3 transposed stride-2 modulated conv + 4x4 FIR + noise + bias + lrelu + clamp.
         Returns (y planes [P, n, 2h, 2h, cout] (lo only when saving for an x3 backward), xs_next planes = y * styles[:, row_next])."""
         x3 = prec == 'x3'
@@ -221,7 +221,8 @@ class SynthesisEngine:
                 gemm.igemm(xs.reshape(-1, hin, hin, L.cin), L.B_fwd, n, hin + 1, hin + 1, L.cout, gemm.up2_parity_taps(r, c),
                            precision=prec, acc_chunk_k=self._acc_k(2 * hin), a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
         res = 2 * hin
-        y = self._planes(n, res, res, L.cout, x3) if save_lo else None     # the raw activation is only needed by the backward pass
+        # the raw activation is only needed by the backward pass; its lo plane only where a style-gradient reduction reads it
+        y = self._planes(n, res, res, L.cout, x3 and save_full) if save_lo else None
         xn = self._planes(n, res, res, L.cout, want_lo)
         sp, ss = self._srow(styles, row_next)
         _lib.call('smc_fir_act', _lib.ptr(planes), 0 if x3 else 1, n, hin, hin, L.cout, _lib.ptr(self.fk4), self._fsep_ptr(), _lib.ptr(noise),
@@ -231,10 +232,13 @@ class SynthesisEngine:
         return y, xn
 
     # ---- forward -------------------------------------------------------------------------------
-    def forward(self, styles, until_k=100, noise_mode='const', save=False, want_xs=False):
+    def forward(self, styles, until_k=100, noise_mode='const', save=False, want_xs=False, grad_rows=None):
         """styles [N, 26, 512] fp32 CUDA -> (xs list or None, img [N, 3, R, R] fp32, SavedForward or None).
 
-        Mirrors utils.generate_image (utils.py:161-216) without the blending branches."""
+        Mirrors utils.generate_image (utils.py:161-216) without the blending branches.
+        grad_rows (with save=True): the style rows whose gradient ``backward`` will be asked for.  Layers that feed none of their
+        style-gradient reductions keep only the hi plane of their saved activation (the backward pass needs just its sign and
+        clamp mask there); None keeps every plane."""
         _lib.require_cuda(styles, 'styles')
         if styles.ndim != 3 or styles.shape[1] < self.rows[min(until_k, len(self.blocks) - 1)][2] + 1:
             raise RuntimeError(f'styles must be [N, >= {self.rows[-1][2] + 1}, C], got {tuple(styles.shape)}')
@@ -261,7 +265,8 @@ class SynthesisEngine:
                 else:
                     L0 = blk.conv0
                     d0 = self._demod(L0, styles, r0, n)
-                    y0, xs = self._conv0(L0, xs, d0, self._noise(L0, noise_mode, n), styles, r1, n, res // 2, prec, two, save_lo=save)
+                    y0, xs = self._conv0(L0, xs, d0, self._noise(L0, noise_mode, n), styles, r1, n, res // 2, prec, two, save_lo=save,
+                                         save_full=grad_rows is None or r0 in grad_rows or r1 in grad_rows)
                     if save:
                         saved.y0[k], saved.d0[k] = y0, d0
                 d1 = self._demod(L1, styles, r1, n)
@@ -271,7 +276,9 @@ class SynthesisEngine:
                 if self.fuse_torgb and self._fusable(L1, res):
                     y1, xs_next, new_img = self._conv1_fused(L1, T, xs, d1, self._noise(L1, noise_mode, n), styles, rt,
                                                              self.rows[k + 1][0] if has_next else None, n, res, prec, two,
-                                                             keep_y=save or want_xs, next_two=nprec_two)
+                                                             keep_y=save or want_xs, next_two=nprec_two,
+                                                             y_full=want_xs or grad_rows is None or r1 in grad_rows or
+                                                             (has_next and self.rows[k + 1][0] in grad_rows))
                     rgb_pass = torch.empty([n, 3, res, res], dtype=torch.uint8, device=self.device) if (save and has_next) else None
                     _lib.call('smc_img_finish', _lib.ptr(new_img), _lib.ptr(img), _lib.ptr(T.bias), T.clamp, _lib.ptr(self.fk4), n, res, res,
                               _lib.ptr(rgb_pass), _lib.stream())
@@ -296,13 +303,14 @@ class SynthesisEngine:
                 if want_xs:
                     out = torch.empty([n, L1.cout, res, res], dtype=torch.float32, device=self.device)
                     _lib.call('smc_unpack_nchw', _lib.ptr(y1[0]), 1, _lib.ptr(out), None, n, L1.cout, res * res, L1.cout, _lib.stream())
-                    if two:   # add the lo plane so xs carries the full precision that was computed
+                    if y1.shape[0] == 2:   # add the lo plane so xs carries the full precision that was computed
                         lo = torch.empty_like(out)
                         _lib.call('smc_unpack_nchw', _lib.ptr(y1[1]), 1, _lib.ptr(lo), None, n, L1.cout, res * res, L1.cout, _lib.stream())
                         out += lo
                     xs_list.append(out)
         if save:
             saved.styles, saved.until_k = styles, last
+            saved.grad_rows = None if grad_rows is None else set(grad_rows)
         return xs_list, img, saved
 
     # ---- backward ------------------------------------------------------------------------------
@@ -327,6 +335,8 @@ class SynthesisEngine:
                 raise RuntimeError(f'style row {r} is not a conv layer of the blocks that ran (ToRGB rows are not trainable here)')
         lowest_k = min(owner[r][0] for r in trainable_rows)
         want = set(trainable_rows)
+        if getattr(saved, 'grad_rows', None) is not None and not want <= saved.grad_rows:
+            raise RuntimeError(f'the forward pass saved activations for style rows {sorted(saved.grad_rows)} only; asked for {sorted(want)}')
         grad = torch.zeros([len(trainable_rows), STYLE_WIDTH], dtype=torch.float32, device=dev)
         g_img = g_img.float().contiguous()
         with torch.cuda.device(dev):
