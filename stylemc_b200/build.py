@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    if force or procs or not os.path.exists(LIB):
+    if force or procs or not os.path.exists(LIB) or any(_newer(o, LIB) for o in objs):
         subprocess.check_call([nvcc, '-shared', '-o', LIB] + objs + ['-lcudart'])
     return LIB
 

@@ -1348,6 +1348,213 @@ extern "C" int smc_unpack_nchw(const void* x, int x_is_half, float* y, const flo
   return SMC_OK;
 }
 
+namespace smc {
+// fp16 hi (+ lo) quad -> two fp32 pairs
+__device__ __forceinline__ void ld_h4(const __half* hi, const __half* lo, bool has_lo, float2& p, float2& q) {
+  const uint2 uh = __ldg(reinterpret_cast<const uint2*>(hi));
+  p = __half22float2(*reinterpret_cast<const __half2*>(&uh.x));
+  q = __half22float2(*reinterpret_cast<const __half2*>(&uh.y));
+  if (has_lo) {
+    const uint2 ul = __ldg(reinterpret_cast<const uint2*>(lo));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&ul.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&ul.y));
+    p.x += a.x; p.y += a.y; q.x += b.x; q.y += b.y;
+  }
+}
+
+// fir_bwd3: fir_bwd2 on the fir_act3 diet (ncu on fir_bwd2: 52 warp instructions per output element, DRAM 38 %): channel count as a
+// template parameter, packed FFMA2 filter passes, FHADD split, running pointers.  Needs (2H)(2W)C < 2^31 per image.
+template <int C, int JT, bool LO, int MINB>
+__global__ void __launch_bounds__(256, MINB) fir_bwd3_kernel(const __half* __restrict__ gd, const __half* __restrict__ gd_lo, int N, int H, int W,
+                                                             float4 fyw, float4 fxw, __half* __restrict__ planes, __half* __restrict__ planes_lo) {
+  constexpr int CG4 = C / 4, KCOLS = 256 / CG4;
+  const int g = threadIdx.x % CG4, kl = threadIdx.x / CG4;
+  const int b = blockIdx.x * KCOLS + kl;
+  if (b > W) return;
+  const int c = g * 4;
+  const int n = blockIdx.z;
+  const int a0 = blockIdx.y * JT;
+  const int a1 = a0 + JT < H + 1 ? a0 + JT : H + 1;
+  const long long plane_sz = (long long)N * (H + 1) * (W + 1) * C;
+  // t column 2b + q reads gd columns 2b - 2 + wx with tap fx[q + 3 - wx], wx in [q, q + 3]
+  const float2 fx0 = make_float2(fxw.x, fxw.x), fx1 = make_float2(fxw.y, fxw.y), fx2 = make_float2(fxw.z, fxw.z), fx3 = make_float2(fxw.w, fxw.w);
+  const float2 fy0 = make_float2(fyw.x, fyw.x), fy1 = make_float2(fyw.y, fyw.y), fy2 = make_float2(fyw.z, fyw.z), fy3 = make_float2(fyw.w, fyw.w);
+  bool ok[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) ok[i] = (2 * b - 2 + i >= 0) && (2 * b - 2 + i < 2 * W);
+  const int gpitch = 2 * W * C;                                                        // elements per gd row
+  const long long gbase = (long long)n * (2 * H) * gpitch + (long long)(2 * b - 2) * C + c;      // row 0, column 2b - 2 (may point left of the row)
+  auto hrow = [&](int gy, float2 (&h)[2][2]) {
+    if (gy < 0 || gy >= 2 * H) {
+      h[0][0] = h[0][1] = h[1][0] = h[1][1] = make_float2(0.f, 0.f);
+      return;
+    }
+    const __half* rh = gd + gbase + (long long)gy * gpitch;
+    const __half* rl = LO ? gd_lo + gbase + (long long)gy * gpitch : nullptr;
+    float2 t[5][2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      if (ok[i]) ld_h4(rh + i * C, rl + i * C, LO, t[i][0], t[i][1]);
+      else t[i][0] = t[i][1] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      h[0][e] = ffma2(fx0, t[3][e], ffma2(fx1, t[2][e], ffma2(fx2, t[1][e], fmul2(fx3, t[0][e]))));
+      h[1][e] = ffma2(fx0, t[4][e], ffma2(fx1, t[3][e], ffma2(fx2, t[2][e], fmul2(fx3, t[1][e]))));
+    }
+  };
+  float2 hw[5][2][2];
+  hrow(2 * a0 - 2, hw[0]);
+  hrow(2 * a0 - 1, hw[1]);
+  hrow(2 * a0, hw[2]);
+  long long po = (((long long)n * (H + 1) + a0) * (W + 1) + b) * C + c;
+  const bool col1 = 2 * b + 1 <= 2 * W;
+#pragma unroll 1
+  for (int a = a0; a < a1; ++a) {
+    hrow(2 * a + 1, hw[3]);
+    hrow(2 * a + 2, hw[4]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const bool rowok = 2 * a + r <= 2 * H;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        // t row 2a + r reads gd rows 2a - 2 + wy with tap fy[r + 3 - wy], wy in [r, r + 3]
+        float2 v0 = ffma2(fy0, hw[r + 3][q][0], ffma2(fy1, hw[r + 2][q][0], ffma2(fy2, hw[r + 1][q][0], fmul2(fy3, hw[r][q][0]))));
+        float2 v1 = ffma2(fy0, hw[r + 3][q][1], ffma2(fy1, hw[r + 2][q][1], ffma2(fy2, hw[r + 1][q][1], fmul2(fy3, hw[r][q][1]))));
+        if (!(rowok && (q == 0 || col1))) v0 = v1 = make_float2(0.f, 0.f);
+        const long long o = (long long)(r * 2 + q) * plane_sz + po;
+        if (LO) {
+          uint2 hi, lo;
+          split4(v0, v1, hi, lo);
+          *reinterpret_cast<uint2*>(planes + o) = hi;
+          *reinterpret_cast<uint2*>(planes_lo + o) = lo;
+        } else {
+          const __half2 a2 = __floats2half2_rn(v0.x, v0.y), b2 = __floats2half2_rn(v1.x, v1.y);
+          *reinterpret_cast<uint2*>(planes + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&b2));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { hw[0][q][e] = hw[2][q][e]; hw[1][q][e] = hw[3][q][e]; hw[2][q][e] = hw[4][q][e]; }
+    po += (long long)(W + 1) * C;
+  }
+}
+
+template <int C>
+static int launch_fir_bwd3(const __half* gd, const __half* gd_lo, int n, int h, int w, float4 fyw, float4 fxw, __half* planes, __half* planes_lo,
+                           cudaStream_t st) {
+  constexpr int JT = 16, KCOLS = 256 / (C / 4);
+  dim3 grid(ceil_div(w + 1, KCOLS), ceil_div(h + 1, JT), n);
+  if (grid.y > 65535 || grid.z > 65535) return SMC_ETOOLARGE;
+  if (gd_lo) fir_bwd3_kernel<C, JT, true, 3><<<grid, 256, 0, st>>>(gd, gd_lo, n, h, w, fyw, fxw, planes, planes_lo);
+  else fir_bwd3_kernel<C, JT, false, 3><<<grid, 256, 0, st>>>(gd, gd_lo, n, h, w, fyw, fxw, planes, planes_lo);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+// act_bwd for a layer whose only consumer is ToRGB (the last block), without style-gradient reductions and with the ToRGB clamp
+// already applied to the incoming gradient (g = masked, loss-scaled dL/drgb [N, 3, HW]):
+//   gd[n, p, c] = dcoef[n, c] * slope(y) * sum_j m_j[n, c] * g[n, j, p],  m_j = w_rgb[j, c] * s_t[n, c] * wgain,  0 where |y| >= clamp.
+// A lane owns 8 channels of a pixel for the whole block: the 24 products m_j * dcoef sit in registers.  (ncu on the generic
+// act_bwd1 for this layer: 54 warp instructions per element; here ~11.)
+template <int C, bool YLO, bool LO>
+__global__ void __launch_bounds__(256) act_bwd_rgb_kernel(const __half* __restrict__ y, const __half* __restrict__ y_lo, long long HW,
+                                                          const float* __restrict__ g, const float* __restrict__ w_rgb,
+                                                          const float* __restrict__ s_t, long long st_stride, float wgain,
+                                                          const float* __restrict__ dcoef, float alpha, float gain, float clamp,
+                                                          __half* __restrict__ gd, __half* __restrict__ gd_lo, int pix_per_block) {
+  constexpr int LPP = C / 8, PPW = 32 / LPP, U = 4;                  // lanes per pixel, pixels per warp, pixels in flight per lane
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPP, c = sub * 8;
+  const long long blocks_per_img = (HW + pix_per_block - 1) / pix_per_block;
+  const int n = (int)(blockIdx.x / blocks_per_img);
+  const long long p_begin = (blockIdx.x % blocks_per_img) * pix_per_block;
+  const long long p_end = p_begin + pix_per_block < HW ? p_begin + pix_per_block : HW;
+  float2 m0[4], m1[4], m2[4];
+  {
+    float st[8], dc[8], w0[8], w1[8], w2[8];
+    ld8f(s_t + n * st_stride + c, st);
+    ld8f(dcoef + (long long)n * C + c, dc);
+    ld8f(w_rgb + c, w0); ld8f(w_rgb + C + c, w1); ld8f(w_rgb + 2 * C + c, w2);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ta = st[2 * e] * wgain * dc[2 * e], tb = st[2 * e + 1] * wgain * dc[2 * e + 1];
+      m0[e] = make_float2(w0[2 * e] * ta, w0[2 * e + 1] * tb);
+      m1[e] = make_float2(w1[2 * e] * ta, w1[2 * e + 1] * tb);
+      m2[e] = make_float2(w2[2 * e] * ta, w2[2 * e + 1] * tb);
+    }
+  }
+  const float ga = gain * alpha;
+  const float cl = clamp >= 0.f ? clamp : __int_as_float(0x7f800000);
+  const float* gn = g + (long long)n * 3 * HW;
+  const long long ibase = (long long)n * HW;
+  for (long long pb = p_begin + warp * PPW + lane / LPP; pb < p_end; pb += 8 * PPW * U) {
+    uint4 yh[U], yl[U];
+    float g0[U], g1[U], g2[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = pb + u * 8 * PPW;
+      const long long pp = p < p_end ? p : p_begin;
+      yh[u] = ld_stream(y + (ibase + pp) * C + c);
+      if (YLO) yl[u] = ld_stream(y_lo + (ibase + pp) * C + c);
+      g0[u] = __ldg(gn + pp); g1[u] = __ldg(gn + HW + pp); g2[u] = __ldg(gn + 2 * HW + pp);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = pb + u * 8 * PPW;
+      if (p >= p_end) break;
+      float yv[8];
+      h8_to_f(yh[u], yv);
+      if (YLO) {
+        float l[8];
+        h8_to_f(yl[u], l);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] += l[e];
+      }
+      const float2 a0 = make_float2(g0[u], g0[u]), a1 = make_float2(g1[u], g1[u]), a2 = make_float2(g2[u], g2[u]);
+      float2 v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[e] = ffma2(m2[e], a2, ffma2(m1[e], a1, fmul2(m0[e], a0)));
+        const float y0 = yv[2 * e], y1 = yv[2 * e + 1];
+        const float s0 = (fabsf(y0) < cl) ? (y0 > 0.f ? gain : ga) : 0.f, s1 = (fabsf(y1) < cl) ? (y1 > 0.f ? gain : ga) : 0.f;
+        v[e] = fmul2(v[e], make_float2(s0, s1));
+      }
+      const long long o = (ibase + p) * C + c;
+      if (LO) {
+        uint2 h0, l0, h1, l1;
+        split4(v[0], v[1], h0, l0);
+        split4(v[2], v[3], h1, l1);
+        st_stream(gd + o, make_uint4(h0.x, h0.y, h1.x, h1.y));
+        st_stream(gd_lo + o, make_uint4(l0.x, l0.y, l1.x, l1.y));
+      } else {
+        const __half2 q0 = __floats2half2_rn(v[0].x, v[0].y), q1 = __floats2half2_rn(v[1].x, v[1].y), q2 = __floats2half2_rn(v[2].x, v[2].y),
+                      q3 = __floats2half2_rn(v[3].x, v[3].y);
+        st_stream(gd + o, make_uint4(*reinterpret_cast<const uint32_t*>(&q0), *reinterpret_cast<const uint32_t*>(&q1),
+                                     *reinterpret_cast<const uint32_t*>(&q2), *reinterpret_cast<const uint32_t*>(&q3)));
+      }
+    }
+  }
+}
+
+template <int C>
+static int launch_act_bwd_rgb(const __half* y, const __half* y_lo, int n, long long hw, const float* g, const float* w_rgb, const float* s_t,
+                              long long st_stride, float wgain, const float* dcoef, float alpha, float gain, float clamp, __half* gd, __half* gd_lo,
+                              cudaStream_t st) {
+  const int pix_per_block = 8 * (32 / (C / 8)) * 4 * 8;               // 8 passes of the 4-deep pipeline per block
+  const long long blocks = ((hw + pix_per_block - 1) / pix_per_block) * n;
+  if (blocks > 0x7fffffffLL) return SMC_ETOOLARGE;
+#define SMC_ABR(YLO, LO) act_bwd_rgb_kernel<C, YLO, LO><<<(int)blocks, 256, 0, st>>>(y, y_lo, hw, g, w_rgb, s_t, st_stride, wgain, dcoef, alpha, gain, \
+                                                                                      clamp, gd, gd_lo, pix_per_block)
+  if (y_lo) { if (gd_lo) SMC_ABR(true, true); else SMC_ABR(true, false); }
+  else { if (gd_lo) SMC_ABR(false, true); else SMC_ABR(false, false); }
+#undef SMC_ABR
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+}  // namespace smc
+
 static int g_fir_act3 = 3;   // 0: keep the older marching kernel; 2 / 3 / 4: fir_act3 with that many resident blocks per SM (smc_synth_config key 0)
 static int g_fir_bwd3 = 1;   // same for smc_fir_bwd (key 1)
 static int g_act_bwd2 = 1;   // same for smc_act_bwd (key 2)
@@ -1519,8 +1726,23 @@ extern "C" int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w,
   if (!g_up && !g_img) return SMC_EINVAL;
   if (g_up && !s_next) return SMC_EINVAL;
   if (g_img && (!w_rgb || !s_t || !b_rgb)) return SMC_EINVAL;
-  const int lpp = pick_lpp(c);
   const long long hw = (long long)h * w;
+  if (g_act_bwd2 && !g_up && g_img && rgb_clamp < 0.f && !gscale && !t1 && !r && gd && (c == 32 || c == 64 || c == 128) &&
+      ((((uintptr_t)y | (uintptr_t)y_lo | (uintptr_t)gd | (uintptr_t)gd_lo | (uintptr_t)w_rgb | (uintptr_t)s_t | (uintptr_t)dcoef) & 15) == 0) &&
+      (st_stride & 3) == 0) {
+    // last block: the only consumer is ToRGB, its clamp mask and the loss scale are already in g_img
+#define SMC_ABRC(CC)                                                                                                                      \
+  case CC: return launch_act_bwd_rgb<CC>((const __half*)y, (const __half*)y_lo, n, hw, g_img, w_rgb, s_t, st_stride, wgain, dcoef, alpha, gain, \
+                                         clamp, (__half*)gd, (__half*)gd_lo, (cudaStream_t)stream)
+    switch (c) {
+      SMC_ABRC(32);
+      SMC_ABRC(64);
+      SMC_ABRC(128);
+      default: break;
+    }
+#undef SMC_ABRC
+  }
+  const int lpp = pick_lpp(c);
   // enough blocks to fill the machine, few enough that the per-block atomics stay cheap
   int pix_per_block = 8 * (32 / lpp) * 16;
   while (pix_per_block > 8 * (32 / lpp) && ceil_div_ll(hw, pix_per_block) * n < 2 * kNumSMs) pix_per_block >>= 1;
@@ -1558,6 +1780,20 @@ extern "C" int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int 
     constexpr int JT = 16;
     const float4 fyw = make_float4(fsep_host[0], fsep_host[1], fsep_host[2], fsep_host[3]);
     const float4 fxw = make_float4(fsep_host[4], fsep_host[5], fsep_host[6], fsep_host[7]);
+    if (g_fir_bwd3 && (!planes_lo) == (!gd_lo) && (long long)(2 * h) * (2 * w) * c < 0x7fffffffLL &&
+        ((((uintptr_t)gd | (uintptr_t)gd_lo | (uintptr_t)planes | (uintptr_t)planes_lo) & 7) == 0)) {
+#define SMC_FB3C(CC) \
+  case CC: return launch_fir_bwd3<CC>((const __half*)gd, (const __half*)gd_lo, n, h, w, fyw, fxw, (__half*)planes, (__half*)planes_lo, (cudaStream_t)stream)
+      switch (c) {
+        SMC_FB3C(32);
+        SMC_FB3C(64);
+        SMC_FB3C(128);
+        SMC_FB3C(256);
+        SMC_FB3C(512);
+        default: break;
+      }
+#undef SMC_FB3C
+    }
     const int kcols = 256 / (c >> 2);
     dim3 grid(ceil_div(w + 1, kcols), ceil_div(h + 1, JT), n);
     if (grid.y > 65535 || grid.z > 65535) return SMC_ETOOLARGE;

@@ -279,7 +279,7 @@ class SynthesisEngine:
                                                              keep_y=save or want_xs, next_two=nprec_two,
                                                              y_full=want_xs or grad_rows is None or r1 in grad_rows or
                                                              (has_next and self.rows[k + 1][0] in grad_rows))
-                    rgb_pass = torch.empty([n, 3, res, res], dtype=torch.uint8, device=self.device) if (save and has_next) else None
+                    rgb_pass = torch.empty([n, 3, res, res], dtype=torch.uint8, device=self.device) if save else None
                     _lib.call('smc_img_finish', _lib.ptr(new_img), _lib.ptr(img), _lib.ptr(T.bias), T.clamp, _lib.ptr(self.fk4), n, res, res,
                               _lib.ptr(rgb_pass), _lib.stream())
                     if rgb_pass is not None:
@@ -374,9 +374,14 @@ class SynthesisEngine:
                     sp, ss = self._srow(styles, up_row) if g_up is not None else (None, 0)
                     stp, sts = self._srow(styles, rt)
                     noise1 = self._noise(L1, noise_mode, n)
+                    gi, rgb_clamp, gs = (g_img if need_gd else None), T.clamp, gscale
+                    if need_gd and g_up is None and t1 is None and rr is None and k in saved.rgb_pass and self.fuse_act_bwd:
+                        # top block, no reduction wanted: the ToRGB clamp mask saved by the forward pass and the loss scale go into the
+                        # incoming gradient, so the kernel neither recomputes the ToRGB output nor reads the lo plane of y1
+                        gi, rgb_clamp, gs = (g_img * saved.rgb_pass[k]) * gscale, -1.0, None
                     _lib.call('smc_act_bwd', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if y1.shape[0] == 2 else None, n, res, res, L1.cout,
-                              _lib.ptr(g_up), int(up_f32), sp, ss, _lib.ptr(g_img) if need_gd else None, _lib.ptr(T.w), stp, sts, T.wgain,
-                              _lib.ptr(T.bias), T.clamp, _lib.ptr(gscale), _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA,
+                              _lib.ptr(g_up), int(up_f32), sp, ss, _lib.ptr(gi), _lib.ptr(T.w), stp, sts, T.wgain,
+                              _lib.ptr(T.bias), rgb_clamp, _lib.ptr(gs), _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA,
                               L1.gain, L1.clamp, _lib.ptr(gd1[0]) if need_gd else None, _lib.ptr(gd1[1]) if (need_gd and two) else None,
                               _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
                 if stop_here:
