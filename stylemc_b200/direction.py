@@ -9,6 +9,7 @@ Only ``clip_type='small'`` (ViT-B/32) with ``clip_loss_type='default'`` is imple
 the accelerated path.
 """
 import math
+import os
 
 import torch
 
@@ -94,6 +95,10 @@ class DirectionFinder:
         self.group = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.kernel_launches = 0
+        # The original-image branch (find_direction.py:312: no gradient) is independent of the edited one until the loss: it runs on a
+        # second CUDA stream, so its under-filled launches (low-resolution layers, ViT GEMMs with a few dozen tiles) share the SMs
+        self.overlap = os.environ.get('STYLEMC_OVERLAP', '1') != '0'
+        self._side = None
 
     # ---- pieces ----------------------------------------------------------------------------------
     def direction(self):
@@ -114,12 +119,26 @@ class DirectionFinder:
         for lo in range(0, n_total, self.micro_batch):
             s = styles[lo:lo + self.micro_batch].to(self.device, torch.float32)
             s2 = s + direction                                                        # find_direction.py:308
+            if self.overlap:
+                cur = torch.cuda.current_stream(self.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(self.device)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    _, original, _ = eng.forward(s, self.until_k, self.noise_mode, save=False)            # :312
+                    e_s, _ = self.clip.encode_image_fwd(resample.unprocess_fwd(original), save=False)
+                    del original
+                s.record_stream(self._side)
             _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True, grad_rows=self.rows)   # :309
-            _, original, _ = eng.forward(s, self.until_k, self.noise_mode, save=False)                # :312
             u_t = resample.unprocess_fwd(img)                                                      # :159-160
-            u_s = resample.unprocess_fwd(original)
-            e_s, _ = self.clip.encode_image_fwd(u_s, save=False)
+            if not self.overlap:
+                _, original, _ = eng.forward(s, self.until_k, self.noise_mode, save=False)                # :312
+                e_s, _ = self.clip.encode_image_fwd(resample.unprocess_fwd(original), save=False)
+                del original
             e_t, csaved = self.clip.encode_image_fwd(u_t, save=True)
+            if self.overlap:
+                cur.wait_stream(self._side)
+                e_s.record_stream(cur)
             part, d_t, gscale = self.loss_fn.loss_and_grad(e_s, e_t, self.clip_loss_coef, 1.0 / count)
             g224 = self.clip.encode_image_bwd(csaved, d_t)
             g_img = resample.unprocess_bwd(g224, img, unscale=gscale)
