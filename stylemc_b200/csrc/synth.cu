@@ -442,17 +442,6 @@ __global__ void __launch_bounds__(256) fir_act2_kernel(const float* __restrict__
 // bias (lrelu(x) * g = max(x g, x g alpha) for g > 0, 0 <= alpha <= 1), FMNMX3 for max + clamp, running pointers instead of
 // per-row 64-bit index arithmetic, L1-allocating loads (neighbouring threads share 3 of their 5 input columns).
 // Needs: fp32 planes, split outputs, H % JT == 0, (H + 1) * (W + 1) * C < 2^31.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
-                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  return *reinterpret_cast<float2*>(&rd);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  return *reinterpret_cast<float2*>(&rd);
-}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -1559,7 +1548,10 @@ static int g_fir_act3 = 3;   // 0: keep the older marching kernel; 2 / 3 / 4: fi
 static int g_fir_bwd3 = 1;   // same for smc_fir_bwd (key 1)
 static int g_act_bwd2 = 1;   // same for smc_act_bwd (key 2)
 
+namespace smc { extern int g_upfirdn_rows; }   // upfirdn2d.cu
+
 extern "C" int smc_synth_config(int key, int value) {
+  if (key == 3) { smc::g_upfirdn_rows = value; return SMC_OK; }
   if (key == 0) g_fir_act3 = value;
   else if (key == 1) g_fir_bwd3 = value;
   else if (key == 2) g_act_bwd2 = value;

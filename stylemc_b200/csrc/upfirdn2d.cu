@@ -346,6 +346,323 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_tile_kernel(const UpfirdnAr
   }
 }
 
+// ---- warp-row streaming kernels: separable 4x4 filter, contiguous NCHW, (up, down) in {(1,1), (2,1), (1,2)} ---------------------------
+// One WARP owns a strip of output columns of one (n, c) plane and marches down a segment of rows.  An input row is read once with
+// coalesced loads (lane + 32 m), its horizontal neighbours come from warp shuffles (no shared memory, no block barrier, any row
+// alignment: the (2H+1)^2 planes of the conv0 FIR have odd widths), the horizontally filtered row enters a 4-row register window and
+// every output row is one vertical 4-tap (2-tap for up = 2) combination of window rows.  The next input row is prefetched while the
+// current one is filtered.  fk[ky][kx] = fy[ky] * fx[kx] (host hint UpfirdnArgs::separable).
+int g_upfirdn_rows = 1;   // 0: keep the tile kernels (A/B diagnostics, smc_synth_config key 3)
+
+template <class T> __device__ __forceinline__ void st2(T* p, float a, float b, bool ok0, bool ok1, bool vec);
+template <> __device__ __forceinline__ void st2<float>(float* p, float a, float b, bool ok0, bool ok1, bool vec) {
+  if (vec && ok1) { *reinterpret_cast<float2*>(p) = make_float2(a, b); return; }
+  if (ok0) p[0] = a;
+  if (ok1) p[1] = b;
+}
+template <> __device__ __forceinline__ void st2<__half>(__half* p, float a, float b, bool ok0, bool ok1, bool vec) {
+  if (vec && ok1) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); return; }
+  if (ok0) p[0] = __float2half_rn(a);
+  if (ok1) p[1] = __float2half_rn(b);
+}
+
+struct RowsFilter { float fx[4], fy[4]; };
+__device__ __forceinline__ RowsFilter rows_filter(const UpfirdnArgs& p) {
+  RowsFilter f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f.fy[k] = p.fsy[p.flip ? k : 3 - k] * p.gain;
+    f.fx[k] = p.fsx[p.flip ? k : 3 - k];
+  }
+  return f;
+}
+
+template <class T, int NJ> struct StN;
+template <> struct StN<float, 4> {
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct StN<__half, 8> {
+  static __device__ __forceinline__ void st(__half* p, const float (&v)[8]) {
+    const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]), c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                                              *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+  }
+};
+
+// up = down = 1.  A lane owns NJ CONSECUTIVE output columns (one 16-byte store per row).  The input row is read with coalesced scalar
+// loads (any row alignment), staged in a per-warp shared-memory row (double buffered, one __syncwarp per row, no block barrier) and
+// read back as the lane's NJ + 3 consecutive inputs with 16-byte loads.  (A first version took the neighbours from warp shuffles:
+// 27 SHFL + SEL per row made it issue bound at 35 instructions per output.)
+template <class T, int RS, int NJ>
+__global__ void __launch_bounds__(128) upfirdn2d_rows_up1_kernel(const UpfirdnArgs p, int strips, int segs) {
+  constexpr int SW = 32 * NJ, BW = SW + 32;               // strip width, staged row width (NJ + 1 loads per lane)
+  __shared__ __align__(16) float buf[4][2][BW];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  long long task = (long long)blockIdx.x * 4 + wrp;
+  if (task >= (long long)p.N * p.C * strips * segs) return;
+  const int strip = (int)(task % strips); task /= strips;
+  const int seg = (int)(task % segs);
+  const long long plane = task / segs;
+  const int ox0 = strip * SW, oy0 = seg * RS;
+  const T* __restrict__ xp = reinterpret_cast<const T*>(p.x) + plane * (long long)p.inH * p.inW;
+  T* __restrict__ yp = reinterpret_cast<T*>(p.y) + plane * (long long)p.outH * p.outW;
+  const RowsFilter f = rows_filter(p);
+  const int ix0 = ox0 - p.padx0 + lane;
+  bool cok[NJ + 1];
+#pragma unroll
+  for (int m = 0; m <= NJ; ++m) cok[m] = ix0 + 32 * m >= 0 && ix0 + 32 * m < p.inW;
+  auto load_row = [&](int iy, T (&v)[NJ + 1]) {
+    const bool rowok = iy >= 0 && iy < p.inH;
+    const T* row = xp + (long long)(rowok ? iy : 0) * p.inW + ix0;
+#pragma unroll
+    for (int m = 0; m <= NJ; ++m) v[m] = (rowok && cok[m]) ? __ldg(row + 32 * m) : (T)0.f;
+  };
+  const int rows = (p.outH - oy0 < RS ? p.outH - oy0 : RS) + 3;
+  const int iyb = oy0 - p.pady0;
+  const int oxl = ox0 + NJ * lane;
+  const bool vec = (p.outW % NJ) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) && oxl + NJ <= p.outW;
+  float hw[4][NJ];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) hw[u][j] = 0.f;
+  T pf[2][NJ + 1];                                        // two input rows in flight
+  load_row(iyb, pf[0]);
+  load_row(iyb + 1, pf[1]);
+  for (int r0 = 0; r0 < rows; r0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= rows) break;
+      float* b = buf[wrp][u & 1];
+#pragma unroll
+      for (int m = 0; m <= NJ; ++m) b[lane + 32 * m] = (float)pf[u & 1][m];
+      __syncwarp();
+      if (r + 2 < rows) load_row(iyb + r + 2, pf[u & 1]);
+      float win[NJ + 4];
+#pragma unroll
+      for (int q = 0; q < (NJ + 4) / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(b + NJ * lane + 4 * q);
+        win[4 * q] = t.x; win[4 * q + 1] = t.y; win[4 * q + 2] = t.z; win[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) hw[u][j] = f.fx[0] * win[j] + f.fx[1] * win[j + 1] + f.fx[2] * win[j + 2] + f.fx[3] * win[j + 3];
+      if (r >= 3) {
+        const int oy = oy0 + r - 3;
+        T* orow = yp + (long long)oy * p.outW + oxl;
+        float v[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; j += 2) {
+          const float2 t = ffma2(make_float2(f.fy[3], f.fy[3]), make_float2(hw[u][j], hw[u][j + 1]),
+                                 ffma2(make_float2(f.fy[2], f.fy[2]), make_float2(hw[(u + 3) & 3][j], hw[(u + 3) & 3][j + 1]),
+                                       ffma2(make_float2(f.fy[1], f.fy[1]), make_float2(hw[(u + 2) & 3][j], hw[(u + 2) & 3][j + 1]),
+                                             fmul2(make_float2(f.fy[0], f.fy[0]), make_float2(hw[(u + 1) & 3][j], hw[(u + 1) & 3][j + 1])))));
+          v[j] = t.x; v[j + 1] = t.y;
+        }
+        if (vec) StN<T, NJ>::st(orow, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+            if (oxl + j < p.outW) st_as<T, float>(orow + j, v[j]);
+        }
+      }
+    }
+  }
+}
+
+// up = 2 (zero insertion), down = 1: polyphase.  Output column 2b + c reads input columns b + sx[c], b + sx[c] + 1 with taps
+// fx[kx0[c]], fx[kx0[c] + 2]; rows alike.  A lane owns b = b0 + lane + 32 m (m = 0, 1) and stores (2b, 2b + 1) pairs.
+template <class T, int RA>
+__global__ void __launch_bounds__(128) upfirdn2d_rows_up2_kernel(const UpfirdnArgs p, int strips, int segs) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  long long task = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (task >= (long long)p.N * p.C * strips * segs) return;
+  // strips fastest: the warps of a block (and of neighbouring blocks) read adjacent chunks of the same input rows (DRAM page locality)
+  const int strip = (int)(task % strips); task /= strips;
+  const int seg = (int)(task % segs);
+  const long long plane = task / segs;
+  const int b0 = strip * 64, a0 = seg * RA;
+  const T* __restrict__ xp = reinterpret_cast<const T*>(p.x) + plane * (long long)p.inH * p.inW;
+  T* __restrict__ yp = reinterpret_cast<T*>(p.y) + plane * (long long)p.outH * p.outW;
+  const RowsFilter f = rows_filter(p);
+  int sx[2], sy[2];
+  float fxa[2], fxb[2], fya[2], fyb[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int kx0 = pos_mod(p.padx0 - c, 2), ky0 = pos_mod(p.pady0 - c, 2);
+    sx[c] = floor_div(c - p.padx0 + kx0, 2);
+    sy[c] = floor_div(c - p.pady0 + ky0, 2);
+    fxa[c] = kx0 ? f.fx[1] : f.fx[0]; fxb[c] = kx0 ? f.fx[3] : f.fx[2];
+    fya[c] = ky0 ? f.fy[1] : f.fy[0]; fyb[c] = ky0 ? f.fy[3] : f.fy[2];
+  }
+  const int msx = sx[0] < sx[1] ? sx[0] : sx[1], msy = sy[0] < sy[1] ? sy[0] : sy[1], Msy = sy[0] < sy[1] ? sy[1] : sy[0];
+  const bool d0 = sx[0] != msx, d1 = sx[1] != msx;       // column phase c reads the sequence shifted by (dc, dc + 1)
+  const int ix0 = b0 + msx + lane;
+  bool cok[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) cok[m] = ix0 + 32 * m >= 0 && ix0 + 32 * m < p.inW;
+  auto load_row = [&](int iy, float (&v)[3]) {
+    const bool rowok = iy >= 0 && iy < p.inH;
+    const T* row = xp + (long long)(rowok ? iy : 0) * p.inW + ix0;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) v[m] = (rowok && cok[m]) ? ldg_f<T>(row + 32 * m) : 0.f;
+  };
+  const bool vec = (p.outW & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 7) == 0);
+  float hp[2][2];                       // previous filtered row: [column phase][m]
+  hp[0][0] = hp[0][1] = hp[1][0] = hp[1][1] = 0.f;
+  const int i_first = a0 + msy, i_last = a0 + RA + Msy;      // input rows a + sy[r], a + sy[r] + 1 for a in [a0, a0 + RA)
+  float nxt[3];
+  load_row(i_first, nxt);
+  for (int i = i_first; i <= i_last; ++i) {
+    float in[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) in[m] = nxt[m];
+    if (i < i_last) load_row(i + 1, nxt);
+    float s1[3], s2[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { s1[m] = __shfl_sync(full, in[m], (lane + 1) & 31); s2[m] = __shfl_sync(full, in[m], (lane + 2) & 31); }
+    float hn[2][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float x0 = in[m];
+      const float x1 = lane + 1 < 32 ? s1[m] : s1[m + 1];
+      const float x2 = lane + 2 < 32 ? s2[m] : s2[m + 1];
+      hn[0][m] = fxa[0] * (d0 ? x1 : x0) + fxb[0] * (d0 ? x2 : x1);
+      hn[1][m] = fxa[1] * (d1 ? x1 : x0) + fxb[1] * (d1 ? x2 : x1);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int a = i - 1 - sy[r];
+      const int oy = 2 * a + r;
+      if (a >= a0 && a < a0 + RA && oy < p.outH) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const int ox = 2 * (b0 + lane + 32 * m);
+          const float v0 = fya[r] * hp[0][m] + fyb[r] * hn[0][m], v1 = fya[r] * hp[1][m] + fyb[r] * hn[1][m];
+          st2<T>(yp + (long long)oy * p.outW + ox, v0, v1, ox < p.outW, ox + 1 < p.outW, vec);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) { hp[c][0] = hn[c][0]; hp[c][1] = hn[c][1]; }
+  }
+}
+
+// up = 1, down = 2: output column o reads input columns 2 o - px0 + kx.  With px0 = 2 s + e the lanes load (even, odd) input PAIRS
+// q = o - s - e + d (d = 0, 1, 2); e = 0: taps (d0.x, d0.y, d1.x, d1.y), e = 1: (d0.y, d1.x, d1.y, d2.x).  Needs an even input width.
+template <class T> struct Pair;
+template <> struct Pair<float> { typedef float2 type; static __device__ __forceinline__ float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); } };
+template <> struct Pair<__half> {
+  typedef __half2 type;
+  static __device__ __forceinline__ float2 ld(const __half* p) { return __half22float2(__ldg(reinterpret_cast<const __half2*>(p))); }
+};
+
+template <class T, int E, int RS>
+__global__ void __launch_bounds__(128) upfirdn2d_rows_down2_kernel(const UpfirdnArgs p, int strips, int segs) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  long long task = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (task >= (long long)p.N * p.C * strips * segs) return;
+  // strips fastest: the warps of a block (and of neighbouring blocks) read adjacent chunks of the same input rows (DRAM page locality)
+  const int strip = (int)(task % strips); task /= strips;
+  const int seg = (int)(task % segs);
+  const long long plane = task / segs;
+  const int ox0 = strip * 128, oy0 = seg * RS;
+  const T* __restrict__ xp = reinterpret_cast<const T*>(p.x) + plane * (long long)p.inH * p.inW;
+  T* __restrict__ yp = reinterpret_cast<T*>(p.y) + plane * (long long)p.outH * p.outW;
+  const RowsFilter f = rows_filter(p);
+  const int s = floor_div(p.padx0, 2);                    // padx0 = 2 s + E
+  const int q0 = ox0 - s - E + lane;                      // pair index of (lane, m = 0)
+  const int npairs = p.inW >> 1;
+  bool cok[5];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) cok[m] = q0 + 32 * m >= 0 && q0 + 32 * m < npairs;
+  auto load_row = [&](int iy, float2 (&v)[5]) {
+    const bool rowok = iy >= 0 && iy < p.inH;
+    const T* row = xp + (long long)(rowok ? iy : 0) * p.inW + 2 * q0;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) v[m] = (rowok && cok[m]) ? Pair<T>::ld(row + 64 * m) : make_float2(0.f, 0.f);
+  };
+  float hw[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hw[i][j] = 0.f;
+  float2 nxt[5];
+  const int iy0 = 2 * oy0 - p.pady0;
+  load_row(iy0, nxt);
+  const int nout = p.outH - oy0 < RS ? p.outH - oy0 : RS;
+  const int rows = 2 * nout + 2;                          // input rows 0 .. 2 (nout - 1) + 3
+#pragma unroll 2
+  for (int r = 0; r < rows; ++r) {
+    float2 in[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) in[m] = nxt[m];
+    if (r + 1 < rows) load_row(iy0 + r + 1, nxt);
+    float x1[5], y1[5], x2[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      x1[m] = __shfl_sync(full, in[m].x, (lane + 1) & 31);
+      y1[m] = __shfl_sync(full, in[m].y, (lane + 1) & 31);
+      if (E) x2[m] = __shfl_sync(full, in[m].x, (lane + 2) & 31);
+    }
+    const bool w1 = lane + 1 >= 32, w2 = lane + 2 >= 32;
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d1x = w1 ? x1[j + 1] : x1[j], d1y = w1 ? y1[j + 1] : y1[j];
+      if (E) {
+        const float d2x = w2 ? x2[j + 1] : x2[j];
+        h[j] = f.fx[0] * in[j].y + f.fx[1] * d1x + f.fx[2] * d1y + f.fx[3] * d2x;
+      } else {
+        h[j] = f.fx[0] * in[j].x + f.fx[1] * in[j].y + f.fx[2] * d1x + f.fx[3] * d1y;
+      }
+    }
+    if (r >= 3 && (r & 1)) {
+      const int oy = oy0 + ((r - 3) >> 1);
+      T* orow = yp + (long long)oy * p.outW + ox0 + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = f.fy[0] * hw[0][j] + f.fy[1] * hw[1][j] + f.fy[2] * hw[2][j] + f.fy[3] * h[j];
+        if (ox0 + lane + 32 * j < p.outW) st_as<T, float>(orow + 32 * j, v);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { hw[0][j] = hw[1][j]; hw[1][j] = hw[2][j]; hw[2][j] = h[j]; }
+  }
+}
+
+template <class T>
+static int launch_rows(const UpfirdnArgs& p, cudaStream_t st) {
+  const long long planes = (long long)p.N * p.C;
+  if (p.upx == 1 && p.downx == 1) {
+    constexpr int RS = 128, NJ = sizeof(T) == 2 ? 8 : 4;
+    const int strips = ceil_div(p.outW, 32 * NJ), segs = ceil_div(p.outH, RS);
+    const long long blocks = ceil_div_ll(planes * strips * segs, 4);
+    if (blocks > 0x7fffffffLL) return SMC_EUNSUPPORTED;
+    upfirdn2d_rows_up1_kernel<T, RS, NJ><<<(int)blocks, 128, 0, st>>>(p, strips, segs);
+  } else if (p.upx == 2 && p.downx == 1) {
+    constexpr int RA = 32;
+    const int strips = ceil_div(ceil_div(p.outW, 2), 64), segs = ceil_div(ceil_div(p.outH, 2), RA);
+    const long long blocks = ceil_div_ll(planes * strips * segs, 4);
+    if (blocks > 0x7fffffffLL) return SMC_EUNSUPPORTED;
+    upfirdn2d_rows_up2_kernel<T, RA><<<(int)blocks, 128, 0, st>>>(p, strips, segs);
+  } else if (p.upx == 1 && p.downx == 2) {
+    constexpr int RS = 32;
+    if ((p.inW & 1) || (reinterpret_cast<uintptr_t>(p.x) & 7) || p.padx0 < 0) return SMC_EUNSUPPORTED;
+    const int strips = ceil_div(p.outW, 128), segs = ceil_div(p.outH, RS);
+    const long long blocks = ceil_div_ll(planes * strips * segs, 4);
+    if (blocks > 0x7fffffffLL) return SMC_EUNSUPPORTED;
+    if (p.padx0 & 1) upfirdn2d_rows_down2_kernel<T, 1, RS><<<(int)blocks, 128, 0, st>>>(p, strips, segs);
+    else upfirdn2d_rows_down2_kernel<T, 0, RS><<<(int)blocks, 128, 0, st>>>(p, strips, segs);
+  } else {
+    return SMC_EUNSUPPORTED;
+  }
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
 template <class T, int DOWN>
 static int launch_tile(const UpfirdnArgs& p, cudaStream_t st) {
   constexpr int TOH = DOWN == 1 ? 32 : 16;
@@ -377,6 +694,10 @@ static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t st) {
   if constexpr (FastOk<T>::value) {
     if (x_nchw && y_nchw && p.fH == 4 && p.fW == 4 && p.upx == p.upy && p.downx == p.downy) {
       int r = SMC_EUNSUPPORTED;
+      if (g_upfirdn_rows && p.separable) {
+        r = launch_rows<T>(p, st);
+        if (r != SMC_EUNSUPPORTED) return r;
+      }
       if (p.upx == 1 && p.downx == 1) r = launch_tile<T, 1>(p, st);
       else if (p.upx == 2 && p.downx == 1) {
         dim3 grid(ceil_div(p.outW, 128), ceil_div(p.outH, 32), p.N * p.C);
