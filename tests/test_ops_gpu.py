@@ -112,6 +112,29 @@ def test_bias_act_fwd_bwd_vs_oracle(kw, shape):
     assert (xc.grad.cpu() - xr.grad).abs().max().item() <= 2e-6 * max(1.0, xr.grad.abs().max().item())
 
 
+@pytest.mark.parametrize('shape', [(3, 10, 33, 7), (2, 6, 8, 24), (5, 64, 40, 40)])
+def test_bias_act_fp16_vectors(shape):
+    """fp16 fast path: two 8-element vectors per thread and iteration, per-vector or per-element bias lookup (H*W % 8), ragged tail."""
+    from stylemc_b200.ops import bias_act
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(*shape, generator=g) * 3).half()
+    b = torch.randn(shape[1], generator=g).half()
+    dy = torch.randn(*shape, generator=g).half()
+    kw = dict(act='lrelu', gain=2 ** 0.5, clamp=4.0)
+    xr = x.float().requires_grad_(True)
+    yr = o_act.bias_act(xr, b.float(), **kw)
+    yr.backward(dy.float())
+    xc = x.cuda().requires_grad_(True)
+    y = bias_act.bias_act(xc, b.cuda(), **kw)
+    y.backward(dy.cuda())
+    assert y.dtype == torch.float16
+    assert (y.detach().float().cpu() - yr.detach()).abs().max().item() <= 4e-3      # one fp16 rounding of |y| <= 4
+    # the clamp mask is taken on the STORED (fp16-rounded) y, as in the reference plugin: skip outputs within a rounding step of the clamp
+    ok = ~((yr.detach().abs() < 4.0) & (yr.detach().abs() > 4.0 - 4e-3))
+    assert ((xc.grad.float().cpu() - xr.grad).abs() * ok).max().item() <= 4e-3 * max(1.0, xr.grad.abs().max().item())
+    assert ok.float().mean().item() > 0.99
+
+
 def test_bias_act_misc():
     from stylemc_b200.ops import bias_act
     g = torch.Generator().manual_seed(3)
