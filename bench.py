@@ -70,7 +70,7 @@ def synth_flops_per_image(blocks, until_k):
 
 
 # DRAM bytes per launch of the dominant shape, from the committed ncu capture (key = n_img, H, W, Cin, Cout, taps); None when not captured
-TOP_KERNEL_DRAM_BYTES = {(64, 1024, 1024, 32, 32, 9): 15.6e9}    # mean of the 3 launches per step: 19.1 (grad fwd), 10.5 (no-grad fwd), 17.3 GB (dgrad)
+TOP_KERNEL_DRAM_BYTES = {(64, 1024, 1024, 32, 32, 9): 15.7e9}    # mean of the 3 launches per step: 10.6 (no-grad fwd), 15.0 (grad fwd), 21.4 GB (dgrad)
 
 VIT_FLOPS_FWD = 2 * (49 * 3072 * 768 + 12 * 50 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) + 12 * 12 * 2 * 50 * 50 * 64)   # per image
 
@@ -198,7 +198,7 @@ def run_ours(a):
         planes_a = max(1, d.ntaps // max(1, alg_taps) - 1)                       # x3: hi + lo planes of A are read
         e = d.epi
         out_b = (4 if e.out_f32 else 0) + sum(2 for q in (e.out_hi, e.out_lo, e.out_raw, e.out_raw_lo) if q)
-        nbytes = float(d.n_img) * d.H * d.W * (2 * planes_a * d.C + out_b * d.n_out)   # algorithmic HBM bytes: A once, outputs once
+        nbytes = float(d.n_img) * d.H * d.W * (2 * planes_a * d.C + out_b * d.n_out * max(1, d.nprob))   # algorithmic HBM bytes: A once, outputs once
         records.append((e0, e1, 2.0 * d.n_img * d.H * d.W * d.n_out * d.C * alg_taps, (d.n_img, d.H, d.W, d.C, d.n_out, alg_taps), nbytes))
 
     _lib.igemm_hook = hook
@@ -265,7 +265,7 @@ def run_ours(a):
                      'mma_per_product': mma_per_product,
                      'tensor_pipe_achieved': round(mma_per_product * top[1] / (top[0] / 1e3) / 1e12, 2),
                      'tensor_pipe_frac': round(mma_per_product * top[1] / (top[0] / 1e3) / 1e12 / pk['tflops'], 4),
-                     'traffic': TOP_KERNEL_DRAM_BYTES.get(top_key), 'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01c_hconv_launches.md (rows 35, 71, 219) and r01c_top_kernel.md',
+                     'traffic': TOP_KERNEL_DRAM_BYTES.get(top_key), 'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01f_hconv_launches.md (rows 35, 120, 219) and r01f_top_kernel.md',
                      'peak_source': pk['src'], 'share_of_step': round(top[0] / step_ms_hooked, 3),
                      'family': {'kernel': 'every smc_igemm launch of one step (hconv_kernel + igemm_kernel: convs, dgrads, CLIP linears)',
                                 'achieved': round(achieved, 2), 'frac': round(achieved / pk['tflops'], 4),

@@ -132,6 +132,13 @@ typedef struct smc_igemm_desc {
   smc_igemm_epilogue epi;
   int32_t acc_chunk_k;       // 0: one TMEM accumulation chain; > 0: drain the accumulator into fp32 registers every
                              // ~acc_chunk_k K-elements (removes the tensor core's truncation bias on long chains)
+  // Problem group (optional): nprob = 2..4 GEMMs that share A, B, the iteration space and the epilogue but own a run of the base
+  // taps each (prob_ntaps[q] consecutive taps; in a split-precision tap list the runs refer to the first third) and write to
+  // epi.o_off + prob_o_off[q].  The four output parities of the stride-2 transposed conv (conv2d_resample.py:132-139 with up = 2)
+  // are such a group: one launch then fetches every input tile from DRAM once instead of once per parity.  nprob = 0 or 1: one GEMM.
+  int32_t nprob;
+  int32_t prob_ntaps[4];
+  int64_t prob_o_off[4];
 } smc_igemm_desc;
 
 int smc_igemm(const smc_igemm_desc* desc, void* stream);

@@ -44,7 +44,8 @@ class IgemmDesc(ctypes.Structure):
                 ('B', ctypes.c_void_p), ('rowsB', ctypes.c_int32), ('ldb', ctypes.c_int64),
                 ('n_img', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('n_out', ctypes.c_int32),
                 ('tw', ctypes.c_int32), ('th', ctypes.c_int32), ('tn', ctypes.c_int32), ('ntaps', ctypes.c_int32),
-                ('taps', Tap * MAX_TAPS), ('epi', Epilogue), ('acc_chunk_k', ctypes.c_int32)]
+                ('taps', Tap * MAX_TAPS), ('epi', Epilogue), ('acc_chunk_k', ctypes.c_int32),
+                ('nprob', ctypes.c_int32), ('prob_ntaps', ctypes.c_int32 * 4), ('prob_o_off', ctypes.c_int64 * 4)]
 
 
 class UpfirdnParams(ctypes.Structure):

@@ -47,13 +47,26 @@ enum : int32_t { HC_SEG_FIRST = 1, HC_SEG_LAST = 2, HC_SEG_COMMIT = 4, HC_SEG_SL
 struct HcSeg {
   int32_t g, tb, te, flags;   // group, tap range, FIRST / LAST segment of its group, COMMIT main after it, last segment of the slab
 };
+// A launch may hold up to HC_MAX_PROBS "problems" that share the A operand and the iteration space but have their own taps and
+// output plane (the four output parities of a stride-2 transposed conv, gemm.up2_parity_taps).  A CTA walks the problems of one
+// position tile back to back, so the A tile is fetched from DRAM once and served from L2 for the other problems; separate launches
+// read the whole input once each.
+constexpr int HC_MAX_PROBS = 4;
+struct HcProb {
+  int32_t seg_begin, nsegs;     // its segments in HcParams::segs (per slab)
+  int32_t kcs_per_drain, ndrains;   // slabs per main-accumulator chunk; main-accumulator drains per tile
+  int32_t stage_base;           // first resident weight stage (b_resident)
+  int32_t pad_;
+  int64_t o_off;                // element offset of its output plane, added to epi.o_off
+};
 struct HcParams {
   int n_img, H, W, C, n_out;
   int Wt, Wp, RB, padL, padT;
   int col_tiles, tiles_per_col, n_tiles_n;
-  int total_tiles;
-  int ngroups, kchunks, kcs_per_drain, nb;
-  int nsegs, ndrains;  // segments per slab; main-accumulator drains per tile
+  int total_tiles;              // nprob * super_tiles
+  int nprob, super_tiles;
+  int ngroups, kchunks, nb;
+  HcProb probs[HC_MAX_PROBS];
   int na_hi, na_lo;  // A buffers: a ring for the hi tiles (read by both passes) and one for the lo tiles (released after the
                      // B_hi pass); x1 uses the hi ring only.  Small-C layers get deeper rings: their tiles are short.
   int b_resident;    // every weight stage of a tile has its own smem slot and is loaded once per CTA (n_tiles_n == 1)
@@ -112,10 +125,18 @@ __device__ __forceinline__ void hc_issue_tap(uint32_t tm, uint32_t alo, uint32_t
 }
 
 struct HcTile {
-  int nt, n, w0, q0, hfirst;
+  int prob, nt, n, w0, q0, hfirst;
 };
+// tile visited by this CTA in its `it`-th iteration, or -1: the nprob problems of one (position, N) tile are consecutive iterations of
+// the SAME CTA (balanced work per CTA although the problems differ in size; the A tile of problems 1.. hits in L2)
+__device__ __forceinline__ int hc_tile_at(const HcParams& p, int it) {
+  const int sup = (int)blockIdx.x + (it / p.nprob) * (int)gridDim.x;
+  return sup < p.super_tiles ? sup * p.nprob + it % p.nprob : -1;
+}
 __device__ __forceinline__ HcTile hc_tile(const HcParams& p, int t) {
   HcTile r;
+  r.prob = t % p.nprob;
+  t /= p.nprob;
   r.nt = t % p.n_tiles_n;
   t /= p.n_tiles_n;
   const int ti = t % p.tiles_per_col;
@@ -376,7 +397,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     if (elect_one()) {
       uint32_t eph = 0;                 // bit b: number of loads into buffer b so far, mod 2
       uint32_t step = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int it = 0, t = hc_tile_at(p, 0); t >= 0; t = hc_tile_at(p, ++it)) {
         const HcTile tl = hc_tile(p, t);
         const int wbox = tl.w0 - p.padL, hbox = tl.hfirst - p.padT;
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -402,10 +423,21 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     if (elect_one()) {
       uint32_t bs = 0, bph = 0;
       const uint32_t nb = (uint32_t)p.nb;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nt = (int)(t % p.n_tiles_n);
+      // resident weights: the stages of ALL problems are loaded once, problem-major (slot = HcProb::stage_base + running index)
+      for (int it = 0;; ++it) {
+        int t;
+        if (p.b_resident) {
+          if (it >= p.nprob) break;
+          t = it;                                 // tile index = problem index, N tile 0 (n_tiles_n == 1)
+        } else {
+          t = hc_tile_at(p, it);
+          if (t < 0) break;
+        }
+        const HcTile tl = hc_tile(p, t);
+        const int nt = tl.nt;
+        const HcProb& pr = p.probs[tl.prob];
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int si = 0; si < p.nsegs; ++si) {
+          for (int si = pr.seg_begin; si < pr.seg_begin + pr.nsegs; ++si) {
             const int tb = p.segs[si].tb, te = p.segs[si].te;
             for (int pass = 0; pass < (TWO_PASS ? 2 : 1); ++pass) {
               for (int tp = tb; tp < te; ++tp) {
@@ -420,7 +452,6 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             }
           }
         }
-        if (p.b_resident) break;      // all stages of a tile are resident: loaded once
       }
     }
   } else if (warp == 2) {
@@ -434,18 +465,20 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const uint32_t nb = (uint32_t)p.nb;
       const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
       const bool resident = p.b_resident != 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
+      for (int it = 0, t = hc_tile_at(p, 0); t >= 0; t = hc_tile_at(p, ++it), ++tile_ctr) {
         const HcTile tl = hc_tile(p, t);
+        const HcProb& pr = p.probs[tl.prob];
+        if (resident) bs = (uint32_t)pr.stage_base;
         const int rel0 = tl.q0 - tl.hfirst * p.Wp;         // position of tile row 0 inside the box (before the tap offset)
         const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
         int in_chunk = 0;
         bool fresh = true;                                 // next main MMA starts an accumulation chunk (overwrites)
         bool fresh_cross = true;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          const bool chunk_ends = (in_chunk + 1 == p.kcs_per_drain) || (kc == p.kchunks - 1);
+          const bool chunk_ends = (in_chunk + 1 == pr.kcs_per_drain) || (kc == p.kchunks - 1);
           uint32_t a_hi = 0, a_lo = 0;
           int hb = 0, lb = 0;
-          for (int si = 0; si < p.nsegs; ++si) {
+          for (int si = pr.seg_begin; si < pr.seg_begin + pr.nsegs; ++si) {
             const int tb = p.segs[si].tb, te = p.segs[si].te, sflags = p.segs[si].flags;
             // main chain complete after this segment's B_hi pass (mid-slab commit, or the slab-end commit of a chunk)
             const bool main_done = (sflags & HC_SEG_COMMIT) && (!(sflags & HC_SEG_SLABEND) || chunk_ends);
@@ -530,12 +563,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     const int m = mb * 128 + q * 32 + lane;
     const smc_igemm_epilogue& e = p.epi;
     const float acc_scale = e.acc_scale != 0.f ? e.acc_scale : 1.f;
-    const int ndrains = p.ndrains;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BLK + ch * CW);
     uint32_t em0 = 0, em1 = 0, ec0 = 0, ec1 = 0, chunk_ctr = 0, tile_ctr = 0;
     float acc[CW];
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_ctr) {
+    for (int it = 0, t = hc_tile_at(p, 0); t >= 0; t = hc_tile_at(p, ++it), ++tile_ctr) {
       const HcTile tl = hc_tile(p, t);
+      const int ndrains = p.probs[tl.prob].ndrains;
       const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
@@ -577,7 +610,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       if (valid) {
         const int n = tl.n;
         const int o0 = tl.nt * BN + ch * CW;
-        const long long opix = e.o_off + (long long)n * e.o_sn + (long long)h * e.o_sh + (long long)w * e.o_sw + o0;
+        const long long opix = e.o_off + p.probs[tl.prob].o_off + (long long)n * e.o_sn + (long long)h * e.o_sh + (long long)w * e.o_sw + o0;
         float nz = 0.f;
         if (e.noise != nullptr) nz = __ldg(e.noise + (long long)h * e.noise_sh + (long long)w * e.noise_sw);
         const float* rs = e.row_scale ? e.row_scale + (long long)n * p.n_out + o0 : nullptr;
@@ -801,7 +834,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   const int mode = !x3 ? HC_X1 : ((BN <= 64 && !(g_hconv_mask & 256)) ? HC_X3_MERGED : HC_X3_TWO_PASS);
   const int passes = mode == HC_X3_TWO_PASS ? 2 : 1;
   const int b_bytes = BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1);        // one ring stage
-  const int stages_per_tile = (d->C / KC) * T * passes;
+  const int stages_per_tile = (d->C / KC) * T * passes;      // all problems together
   p.b_resident = (d->n_out == BN && stages_per_tile <= 32 && stages_per_tile * b_bytes <= 96 * 1024) ? 1 : 0;
   if (p.b_resident) {
     p.nb = stages_per_tile;
@@ -824,7 +857,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     if (x3) {
       if (nmax < 3) continue;
       // short slabs (few taps): the lo buffer is only free during the short B_lo pass, so it needs a second buffer
-      const bool short_slabs = T * (KC / 16) < 16;
+      const bool short_slabs = T * (KC / 16) < 16 || d->nprob > 1;   // problems of a parity group have 1-4 taps each
       const int want_h = short_tiles ? 4 : (short_slabs ? 3 : 2);
       // two-pass: the lo tile is released after the B_hi pass; merged: it lives as long as the hi tile
       const int want_l = mode == HC_X3_MERGED ? want_h : (short_tiles ? 4 : (short_slabs ? 2 : 1));
@@ -842,10 +875,13 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   p.col_tiles = ceil_div(d->W, p.Wt);
   p.tiles_per_col = (int)ceil_div_ll((long long)d->H * p.Wp, HC_MT);
   p.n_tiles_n = d->n_out / BN;
+  p.nprob = d->nprob > 1 ? d->nprob : 1;
+  if (p.nprob > HC_MAX_PROBS) return SMC_EINVAL;
   {
     const long long tt = (long long)d->n_img * p.col_tiles * p.tiles_per_col * p.n_tiles_n;
-    if (tt > 0x7fffffffLL) return SMC_ETOOLARGE;
-    p.total_tiles = (int)tt;
+    if (tt * p.nprob > 0x7fffffffLL) return SMC_ETOOLARGE;
+    p.super_tiles = (int)tt;
+    p.total_tiles = (int)tt * p.nprob;
   }
   p.kchunks = d->C / KC;
 
@@ -881,43 +917,74 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   // accumulation chains: at most max_chain MMAs (K = 16 each) go into the main accumulator between two drains
   const int mma_per_tap = KC / 16;
   const int max_chain = d->acc_chunk_k > 0 ? (d->acc_chunk_k / 16 < mma_per_tap ? mma_per_tap : d->acc_chunk_k / 16) : (1 << 30);
-  const int chain_per_slab = T * mma_per_tap;
-  p.nsegs = 0;
-  int mid_commits = 0;
-  if (x3 && chain_per_slab > max_chain) {
-    // split inside the slab: segments of at most max_chain / mma_per_tap taps, greedy commits
-    const int seg_taps = max_chain / mma_per_tap < 1 ? 1 : max_chain / mma_per_tap;
-    int chain = 0;
-    for (int g = 0; g < p.ngroups; ++g) {
-      const int nt_g = p.groups[g].tap_end - p.groups[g].tap_begin;
-      const int nseg = ceil_div(nt_g, seg_taps);
-      const int len = ceil_div(nt_g, nseg);
-      for (int q = 0; q < nseg; ++q) {
-        if (p.nsegs == HC_MAX_SEGS) return SMC_EUNSUPPORTED;
-        HcSeg& sg = p.segs[p.nsegs++];
-        sg.g = g;
-        sg.tb = p.groups[g].tap_begin + q * len;
-        sg.te = sg.tb + len < p.groups[g].tap_end ? sg.tb + len : p.groups[g].tap_end;
-        sg.flags = (q == 0 ? HC_SEG_FIRST : 0) | (q == nseg - 1 ? HC_SEG_LAST : 0);
-        const int add = (sg.te - sg.tb) * mma_per_tap;
-        if (chain > 0 && chain + add > max_chain) {          // commit after the previous segment
-          p.segs[p.nsegs - 2].flags |= HC_SEG_COMMIT;
-          ++mid_commits;
-          chain = 0;
-        }
-        chain += add;
-      }
+  // problems: one (all groups) by default; with nprob > 1 the base taps of the single group are split into consecutive runs
+  if (p.nprob > 1) {
+    if (p.ngroups != 1) return SMC_EUNSUPPORTED;
+    int sum = 0;
+    for (int q = 0; q < p.nprob; ++q) {
+      if (d->prob_ntaps[q] < 1) return SMC_EINVAL;
+      sum += d->prob_ntaps[q];
     }
-    p.kcs_per_drain = 1;
-  } else {
-    for (int g = 0; g < p.ngroups; ++g) {
-      HcSeg& sg = p.segs[p.nsegs++];
-      sg.g = g; sg.tb = p.groups[g].tap_begin; sg.te = p.groups[g].tap_end; sg.flags = HC_SEG_FIRST | HC_SEG_LAST;
-    }
-    p.kcs_per_drain = d->acc_chunk_k > 0 ? (max_chain / chain_per_slab < 1 ? 1 : max_chain / chain_per_slab) : p.kchunks;
+    if (sum != T) return SMC_EINVAL;
   }
-  p.segs[p.nsegs - 1].flags |= HC_SEG_COMMIT | HC_SEG_SLABEND;
-  p.ndrains = p.kchunks * mid_commits + ceil_div(p.kchunks, p.kcs_per_drain);
+  int nsegs_total = 0, tap_cursor = 0, stage_cursor = 0;
+  for (int q = 0; q < p.nprob; ++q) {
+    HcProb& pr = p.probs[q];
+    // the tap ranges this problem covers: (group, begin, end)
+    int rg[HC_MAX_GROUPS], rb[HC_MAX_GROUPS], re[HC_MAX_GROUPS], nr = 0;
+    if (p.nprob > 1) {
+      rg[0] = 0; rb[0] = tap_cursor; re[0] = tap_cursor + d->prob_ntaps[q]; nr = 1;
+      tap_cursor = re[0];
+    } else {
+      for (int g = 0; g < p.ngroups; ++g) { rg[nr] = g; rb[nr] = p.groups[g].tap_begin; re[nr] = p.groups[g].tap_end; ++nr; }
+    }
+    int Tq = 0;
+    for (int i = 0; i < nr; ++i) Tq += re[i] - rb[i];
+    const int chain_per_slab = Tq * mma_per_tap;
+    pr.seg_begin = nsegs_total;
+    pr.stage_base = stage_cursor;
+    pr.pad_ = 0;
+    pr.o_off = p.nprob > 1 ? d->prob_o_off[q] : 0;
+    stage_cursor += (d->C / KC) * Tq * passes;
+    int mid_commits = 0;
+    if (x3 && chain_per_slab > max_chain) {
+      // split inside the slab: segments of at most max_chain / mma_per_tap taps, greedy commits
+      const int seg_taps = max_chain / mma_per_tap < 1 ? 1 : max_chain / mma_per_tap;
+      int chain = 0;
+      for (int i = 0; i < nr; ++i) {
+        const int nt_g = re[i] - rb[i];
+        const int nseg = ceil_div(nt_g, seg_taps);
+        const int len = ceil_div(nt_g, nseg);
+        for (int qs = 0; qs < nseg; ++qs) {
+          if (nsegs_total == HC_MAX_SEGS) return SMC_EUNSUPPORTED;
+          HcSeg& sg = p.segs[nsegs_total++];
+          sg.g = rg[i];
+          sg.tb = rb[i] + qs * len;
+          sg.te = sg.tb + len < re[i] ? sg.tb + len : re[i];
+          sg.flags = (qs == 0 ? HC_SEG_FIRST : 0) | (qs == nseg - 1 ? HC_SEG_LAST : 0);
+          const int add = (sg.te - sg.tb) * mma_per_tap;
+          if (chain > 0 && chain + add > max_chain) {          // commit after the previous segment
+            p.segs[nsegs_total - 2].flags |= HC_SEG_COMMIT;
+            ++mid_commits;
+            chain = 0;
+          }
+          chain += add;
+        }
+      }
+      pr.kcs_per_drain = 1;
+    } else {
+      for (int i = 0; i < nr; ++i) {
+        if (nsegs_total == HC_MAX_SEGS) return SMC_EUNSUPPORTED;
+        HcSeg& sg = p.segs[nsegs_total++];
+        sg.g = rg[i]; sg.tb = rb[i]; sg.te = re[i]; sg.flags = HC_SEG_FIRST | HC_SEG_LAST;
+      }
+      pr.kcs_per_drain = d->acc_chunk_k > 0 ? (max_chain / chain_per_slab < 1 ? 1 : max_chain / chain_per_slab) : p.kchunks;
+    }
+    pr.nsegs = nsegs_total - pr.seg_begin;
+    p.segs[nsegs_total - 1].flags |= HC_SEG_COMMIT | HC_SEG_SLABEND;
+    pr.ndrains = p.kchunks * mid_commits + ceil_div(p.kchunks, pr.kcs_per_drain);
+  }
+  for (int q = p.nprob; q < HC_MAX_PROBS; ++q) p.probs[q] = p.probs[0];
   p.a_box_bytes = (uint32_t)(p.RB * p.Wp) * (uint32_t)(KC * 2);
   p.a_buf_bytes = ((uint32_t)(p.RB * p.Wp + 8) * (uint32_t)(KC * 2) + 1023u) & ~1023u;
   p.epi = d->epi;
@@ -964,7 +1031,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     if (r != CUDA_SUCCESS) return SMC_EDRIVER;
   }
   const int max_grid = g_hconv_grid > 0 ? g_hconv_grid : kNumSMs;
-  const int grid = p.total_tiles < max_grid ? (int)p.total_tiles : max_grid;
+  const int grid = p.super_tiles < max_grid ? (int)p.super_tiles : max_grid;
   if (KC == 64) {
     if (BN == 128) return hc_launch_x<128, 64>(mode, ma, mb, p, grid, smem, st);
     if (BN == 64) return hc_launch_x<64, 64>(mode, ma, mb, p, grid, smem, st);

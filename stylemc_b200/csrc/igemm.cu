@@ -290,9 +290,33 @@ int igemm_launch(const smc_igemm_desc* d, cudaStream_t st) {
   if (d->ntaps < 1 || d->ntaps > SMC_IGEMM_MAX_TAPS) return SMC_EINVAL;
   if (d->n_img < 1 || d->H < 1 || d->W < 1 || d->n_out < 1 || d->C < 1) return SMC_EINVAL;
   if (((uintptr_t)d->A & 15) || ((uintptr_t)d->B & 15)) return SMC_EINVAL;
+  if (d->nprob < 0 || d->nprob > 4) return SMC_EINVAL;
   {
     const int r = hconv_try_launch(d, st);   // halo-tile kernel for the spatial convolutions it supports
     if (r != SMC_EUNSUPPORTED) return r;
+  }
+  if (d->nprob > 1) {
+    // problem group not taken as one launch: run its GEMMs one by one (same results, the input is read once per problem)
+    int sum = 0;
+    for (int q = 0; q < d->nprob; ++q) {
+      if (d->prob_ntaps[q] < 1) return SMC_EINVAL;
+      sum += d->prob_ntaps[q];
+    }
+    const int reps = d->ntaps == sum ? 1 : (d->ntaps == 3 * sum ? 3 : 0);
+    if (reps == 0) return SMC_EINVAL;
+    int t0 = 0;
+    for (int q = 0; q < d->nprob; ++q) {
+      smc_igemm_desc s = *d;
+      s.nprob = 0;
+      s.ntaps = reps * d->prob_ntaps[q];
+      for (int r = 0; r < reps; ++r)
+        for (int i = 0; i < d->prob_ntaps[q]; ++i) s.taps[r * d->prob_ntaps[q] + i] = d->taps[r * sum + t0 + i];
+      s.epi.o_off = d->epi.o_off + d->prob_o_off[q];
+      const int rc = igemm_launch(&s, st);
+      if (rc != SMC_OK) return rc;
+      t0 += d->prob_ntaps[q];
+    }
+    return SMC_OK;
   }
   if (d->C % 32 != 0 || d->lda % 8 != 0 || d->ldb % 8 != 0) return SMC_EUNSUPPORTED;
   if (d->epi.out_raw_lo || d->epi.rgb_acc || d->epi.rgb_w) return SMC_EUNSUPPORTED;   // fused ToRGB lives in hconv.cu only

@@ -34,13 +34,16 @@ def up2_dgrad_taps(n_img):
 def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=None, b_rows_per_tap=None,
           row_scale=None, post_scale=None, bias=None, noise=None, noise_strides=(0, 0), act=0, alpha=0.2, gain=1.0,
           clamp=-1.0, residual=None, out_f32=None, out_hi=None, out_lo=None, out_raw=None, out_strides=None, out_offset=0,
-          tile=None, acc_scale=1.0, acc_chunk_k=0, out_raw_lo=None, rgb_w=None, rgb_acc=None, mask_y=None, mask_y_lo=None, mask_grgb=None):
+          tile=None, acc_scale=1.0, acc_chunk_k=0, out_raw_lo=None, rgb_w=None, rgb_acc=None, mask_y=None, mask_y_lo=None, mask_grgb=None,
+          problems=None):
     """Launch one implicit GEMM.
 
     A: fp16 tensor viewed as [NA, HA, WA, C] (NA includes the hi/lo planes stacked on the image axis).
     B: fp16 tensor [rowsB, C]; ``taps`` entries are (dn, dy, dx, tap_index) or (dy, dx, tap_index);
        tap_index selects rows tap_index * n_out .. of the hi block, the lo block follows ``b_lo_row`` rows later.
     out_strides: (sn, sh, sw) element strides of the output; default dense NHWC [n_img, H, W, n_out].
+    problems: optional [(ntaps, out_offset), ...] (2..4 entries): a problem group (smc_igemm_desc::nprob) -- ``taps`` is the concatenation of
+       the problems' tap lists, problem q writes to ``out_offset + problems[q][1]`` (elements).  One launch, the input is read once.
     mask_y (+ mask_y_lo): fused activation backward (smc_igemm_epilogue::mask_y): out = acc * post_scale * lrelu'(mask_y) * clamp mask,
        optionally + rgb_w . mask_grgb (fp32 NCHW [n_img, 3, H, W]) before the slope.
     """
@@ -88,6 +91,12 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
         assert mask_grgb.dtype == torch.float32 and mask_grgb.is_contiguous() and rgb_w is not None and rgb_w.is_contiguous() and rgb_acc is None
         e.rgb_sn, e.rgb_sj, e.rgb_sh = mask_grgb.stride(0), mask_grgb.stride(1), mask_grgb.stride(2)
     d.acc_chunk_k = acc_chunk_k
+    if problems is not None:
+        if not 2 <= len(problems) <= 4 or sum(nt for nt, _ in problems) != len(taps):
+            raise RuntimeError('problems must be 2..4 (ntaps, out_offset) pairs covering the tap list')
+        d.nprob = len(problems)
+        for q, (nt, off) in enumerate(problems):
+            d.prob_ntaps[q], d.prob_o_off[q] = nt, off
     with torch.cuda.device(A.device):
         if _lib.igemm_hook is not None:
             with _lib.igemm_hook(d, len(full) // (3 if precision == 'x3' else 1)):

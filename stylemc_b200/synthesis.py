@@ -120,6 +120,7 @@ class SynthesisEngine:
         self.acc_k = 512 if precision == 'x3p' else 0
         self.acc_k_lowres, self.acc_k_lowres_max = 64, 16
         self.fuse_torgb = os.environ.get('STYLEMC_HCONV') != '0'      # the fused epilogue exists in hconv.cu only
+        self.group_parities = os.environ.get('STYLEMC_CONV0_GROUP') != '0'  # conv0: the four parity GEMMs as one problem-group launch
         self.fuse_act_bwd = os.environ.get('STYLEMC_FUSE_ACT_BWD') != '0'   # also needs fuse_torgb (both live in hconv.cu)
         self.precision, self.x3_max_res = ('x3' if precision == 'x3p' else precision), x3_max_res
         # style row of (conv0, conv1, torgb) per block (utils.py:169-185)
@@ -215,11 +216,22 @@ class SynthesisEngine:
         Returns (y planes [P, n, 2h, 2h, cout] (lo only when saving for an x3 backward), xs_next planes = y * styles[:, row_next])."""
         x3 = prec == 'x3'
         planes = torch.empty([4, n, hin + 1, hin + 1, L.cout], dtype=torch.float32 if x3 else torch.float16, device=self.device)
-        for r in (0, 1):
-            for c in (0, 1):
-                kw = dict(out_f32=planes[r * 2 + c]) if x3 else dict(out_raw=planes[r * 2 + c])
-                gemm.igemm(xs.reshape(-1, hin, hin, L.cin), L.B_fwd, n, hin + 1, hin + 1, L.cout, gemm.up2_parity_taps(r, c),
-                           precision=prec, acc_chunk_k=self._acc_k(2 * hin), a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
+        if self.group_parities:
+            # one launch for the four output parities (problem group): every input tile comes from DRAM once
+            taps, problems = [], []
+            for q, (r, c) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                t = gemm.up2_parity_taps(r, c)
+                taps += t
+                problems.append((len(t), q * planes[0].numel()))
+            kw = dict(out_f32=planes[0]) if x3 else dict(out_raw=planes[0])
+            gemm.igemm(xs.reshape(-1, hin, hin, L.cin), L.B_fwd, n, hin + 1, hin + 1, L.cout, taps, precision=prec, acc_chunk_k=self._acc_k(2 * hin),
+                       a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, problems=problems, **kw)
+        else:
+            for r in (0, 1):
+                for c in (0, 1):
+                    kw = dict(out_f32=planes[r * 2 + c]) if x3 else dict(out_raw=planes[r * 2 + c])
+                    gemm.igemm(xs.reshape(-1, hin, hin, L.cin), L.B_fwd, n, hin + 1, hin + 1, L.cout, gemm.up2_parity_taps(r, c),
+                               precision=prec, acc_chunk_k=self._acc_k(2 * hin), a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, **kw)
         res = 2 * hin
         # the raw activation is only needed by the backward pass; its lo plane only where a style-gradient reduction reads it
         y = self._planes(n, res, res, L.cout, x3 and save_full) if save_lo else None

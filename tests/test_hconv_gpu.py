@@ -138,6 +138,37 @@ def test_transposed_stride2_parity_planes_and_dgrad(n, c, o, h, x3):
     assert rel(gx, xr.grad.permute(0, 2, 3, 1)) <= (2e-6 if x3 else 1e-5)
 
 
+@pytest.mark.parametrize('n,c,o,h,chunk', [(2, 64, 32, 32, 512), (3, 128, 64, 40, 512), (2, 64, 128, 33, 512), (2, 256, 128, 16, 64), (5, 64, 32, 70, 512),
+                                           (2, 64, 32, 4, 512)])
+@pytest.mark.parametrize('x3', [False, True])
+def test_parity_problem_group_equals_separate_launches(n, c, o, h, chunk, x3):
+    """smc_igemm_desc::nprob: the four parity GEMMs of the stride-2 transposed conv as ONE launch give bit-identical planes (same taps,
+    same accumulation chains per problem); the h = 4 case pins the per-tap kernel and exercises the one-by-one fallback."""
+    from stylemc_b200 import gemm
+    g = torch.Generator(device='cuda').manual_seed(6)
+    x = torch.randn(n, c, h, h, device='cuda', generator=g)
+    wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.1
+    if not x3:
+        x, wt = x.half().float(), wt.half().float()
+    d = torch.rand(n, o, device='cuda', generator=g) + 0.5
+    kw = dict(precision='x3' if x3 else 'x1', acc_chunk_k=chunk if x3 else 0, a_plane_stride_imgs=n, b_rows_per_tap=9 * o, row_scale=d)
+    if h == 4:
+        kw['tile'] = (8, 8, 2)            # a pinned per-tap tile shape keeps the call on csrc/igemm.cu
+    A, B = planes(x, x3), wmat(wt, x3)
+    sep = torch.zeros(4, n, h + 1, h + 1, o, device='cuda')
+    taps, problems = [], []
+    for q, (r, cc) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        t = gemm.up2_parity_taps(r, cc)
+        gemm.igemm(A, B, n, h + 1, h + 1, o, t, out_f32=sep[q], **kw)
+        taps += t
+        problems.append((len(t), q * sep[0].numel()))
+    grp = torch.full_like(sep, float('nan'))
+    gemm.igemm(A, B, n, h + 1, h + 1, o, taps, out_f32=grp[0], problems=problems, **kw)
+    assert torch.equal(grp, sep)
+    with pytest.raises(RuntimeError):
+        gemm.igemm(A, B, n, h + 1, h + 1, o, taps, out_f32=grp[0], problems=problems[:3], **kw)
+
+
 def test_conv3x3_dgrad_taps():
     from stylemc_b200 import gemm
     g = torch.Generator(device='cuda').manual_seed(5)
