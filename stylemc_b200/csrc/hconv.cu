@@ -52,6 +52,21 @@ struct HcSeg {
 // position tile back to back, so the A tile is fetched from DRAM once and served from L2 for the other problems; separate launches
 // read the whole input once each.
 constexpr int HC_MAX_PROBS = 4;
+// n / d for n < 2^31 as one multiply-high, one add and one shift (round-up method): the tile decode runs in the single-thread
+// roles between two tiles, and a hardware-less integer division is ~25 dependent instructions there.
+struct HcDiv {
+  uint32_t mul, shift;
+};
+static HcDiv hc_make_div(uint32_t d) {
+  HcDiv f{0u, 0u};
+  if (d <= 1) return f;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.shift = s;
+  f.mul = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1ull);
+  return f;
+}
+__device__ __forceinline__ int hc_div(int n, HcDiv f) { return (int)((__umulhi((uint32_t)n, f.mul) + (uint32_t)n) >> f.shift); }
 struct HcProb {
   int32_t seg_begin, nsegs;     // its segments in HcParams::segs (per slab)
   int32_t kcs_per_drain, ndrains;   // slabs per main-accumulator chunk; main-accumulator drains per tile
@@ -65,11 +80,13 @@ struct HcParams {
   int col_tiles, tiles_per_col, n_tiles_n;
   int total_tiles;              // nprob * super_tiles
   int nprob, super_tiles;
+  HcDiv div_ntn, div_tpc, div_ct, div_wp;   // n_tiles_n, tiles_per_col, col_tiles, Wp
   int ngroups, kchunks, nb;
   HcProb probs[HC_MAX_PROBS];
   int na_hi, na_lo;  // A buffers: a ring for the hi tiles (read by both passes) and one for the lo tiles (released after the
                      // B_hi pass); x1 uses the hi ring only.  Small-C layers get deeper rings: their tiles are short.
   int b_resident;    // every weight stage of a tile has its own smem slot and is loaded once per CTA (n_tiles_n == 1)
+  int a_share;       // problem group with a single slab: the A tile loaded for problem 0 stays in shared memory for the other problems
   uint32_t a_box_bytes, a_buf_bytes;
   HcGroup groups[HC_MAX_GROUPS];
   HcSeg segs[HC_MAX_SEGS];
@@ -127,25 +144,33 @@ __device__ __forceinline__ void hc_issue_tap(uint32_t tm, uint32_t alo, uint32_t
 struct HcTile {
   int prob, nt, n, w0, q0, hfirst;
 };
-// tile visited by this CTA in its `it`-th iteration, or -1: the nprob problems of one (position, N) tile are consecutive iterations of
-// the SAME CTA (balanced work per CTA although the problems differ in size; the A tile of problems 1.. hits in L2)
-__device__ __forceinline__ int hc_tile_at(const HcParams& p, int it) {
-  const int sup = (int)blockIdx.x + (it / p.nprob) * (int)gridDim.x;
-  return sup < p.super_tiles ? sup * p.nprob + it % p.nprob : -1;
+// Tile walk of one CTA: (position, N) tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the nprob problems of a tile are consecutive
+// iterations of the SAME CTA (balanced work per CTA although the problems differ in size; the A tile of problems 1.. hits in L2 or
+// stays in shared memory).  Counters only: the single-thread roles run this between two tiles, on the MMA issue path (a version
+// with two more integer divisions per tile slowed the 1024-px conv1 down by 12 %).
+struct HcWalk {
+  int sup, prob;
+};
+__device__ __forceinline__ HcWalk hc_walk_begin() { return HcWalk{(int)blockIdx.x, 0}; }
+__device__ __forceinline__ void hc_walk_next(const HcParams& p, HcWalk& w) {
+  if (++w.prob == p.nprob) { w.prob = 0; w.sup += (int)gridDim.x; }
 }
-__device__ __forceinline__ HcTile hc_tile(const HcParams& p, int t) {
+__device__ __forceinline__ HcTile hc_tile(const HcParams& p, const HcWalk& w) {
   HcTile r;
-  r.prob = t % p.nprob;
-  t /= p.nprob;
-  r.nt = t % p.n_tiles_n;
-  t /= p.n_tiles_n;
-  const int ti = t % p.tiles_per_col;
-  t /= p.tiles_per_col;
-  const int ct = t % p.col_tiles;
-  r.n = t / p.col_tiles;
+  int t = w.sup;
+  r.prob = w.prob;
+  int q = hc_div(t, p.div_ntn);
+  r.nt = t - q * p.n_tiles_n;
+  t = q;
+  q = hc_div(t, p.div_tpc);
+  const int ti = t - q * p.tiles_per_col;
+  t = q;
+  q = hc_div(t, p.div_ct);
+  const int ct = t - q * p.col_tiles;
+  r.n = q;
   r.w0 = ct * p.Wt;
   r.q0 = ti * HC_MT;
-  r.hfirst = r.q0 / p.Wp;
+  r.hfirst = hc_div(r.q0, p.div_wp);
   return r;
 }
 
@@ -397,8 +422,9 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     if (elect_one()) {
       uint32_t eph = 0;                 // bit b: number of loads into buffer b so far, mod 2
       uint32_t step = 0;
-      for (int it = 0, t = hc_tile_at(p, 0); t >= 0; t = hc_tile_at(p, ++it)) {
-        const HcTile tl = hc_tile(p, t);
+      for (HcWalk wk = hc_walk_begin(); wk.sup < p.super_tiles; hc_walk_next(p, wk)) {
+        if (p.a_share && wk.prob > 0) continue;            // same position tile as problem 0: its buffers are reused
+        const HcTile tl = hc_tile(p, wk);
         const int wbox = tl.w0 - p.padL, hbox = tl.hfirst - p.padT;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int g = 0; g < p.ngroups; ++g, ++step) {
@@ -424,18 +450,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       uint32_t bs = 0, bph = 0;
       const uint32_t nb = (uint32_t)p.nb;
       // resident weights: the stages of ALL problems are loaded once, problem-major (slot = HcProb::stage_base + running index)
-      for (int it = 0;; ++it) {
-        int t;
-        if (p.b_resident) {
-          if (it >= p.nprob) break;
-          t = it;                                 // tile index = problem index, N tile 0 (n_tiles_n == 1)
-        } else {
-          t = hc_tile_at(p, it);
-          if (t < 0) break;
-        }
-        const HcTile tl = hc_tile(p, t);
-        const int nt = tl.nt;
-        const HcProb& pr = p.probs[tl.prob];
+      for (HcWalk wk = hc_walk_begin(); wk.sup < p.super_tiles; hc_walk_next(p, wk)) {
+        if (p.b_resident && wk.sup != (int)blockIdx.x) break;       // resident: one pass over the problems (n_tiles_n == 1)
+        const int nt = wk.sup - hc_div(wk.sup, p.div_ntn) * p.n_tiles_n;
+        const HcProb& pr = p.probs[wk.prob];
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int si = pr.seg_begin; si < pr.seg_begin + pr.nsegs; ++si) {
             const int tb = p.segs[si].tb, te = p.segs[si].te;
@@ -465,9 +483,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const uint32_t nb = (uint32_t)p.nb;
       const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
       const bool resident = p.b_resident != 0;
-      for (int it = 0, t = hc_tile_at(p, 0); t >= 0; t = hc_tile_at(p, ++it), ++tile_ctr) {
-        const HcTile tl = hc_tile(p, t);
+      uint32_t a_hi = 0, a_lo = 0;                         // live across the problems of a tile when the A tile is shared
+      int hb = 0, lb = 0;
+      for (HcWalk wk = hc_walk_begin(); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
+        const HcTile tl = hc_tile(p, wk);
         const HcProb& pr = p.probs[tl.prob];
+        const bool a_load = !(p.a_share && tl.prob > 0);              // this tile waits for its own A buffers
+        const bool a_free = !(p.a_share && tl.prob + 1 < p.nprob);    // and releases them
         if (resident) bs = (uint32_t)pr.stage_base;
         const int rel0 = tl.q0 - tl.hfirst * p.Wp;         // position of tile row 0 inside the box (before the tap offset)
         const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
@@ -476,13 +498,11 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         bool fresh_cross = true;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           const bool chunk_ends = (in_chunk + 1 == pr.kcs_per_drain) || (kc == p.kchunks - 1);
-          uint32_t a_hi = 0, a_lo = 0;
-          int hb = 0, lb = 0;
           for (int si = pr.seg_begin; si < pr.seg_begin + pr.nsegs; ++si) {
             const int tb = p.segs[si].tb, te = p.segs[si].te, sflags = p.segs[si].flags;
             // main chain complete after this segment's B_hi pass (mid-slab commit, or the slab-end commit of a chunk)
             const bool main_done = (sflags & HC_SEG_COMMIT) && (!(sflags & HC_SEG_SLABEND) || chunk_ends);
-            if (sflags & HC_SEG_FIRST) {
+            if ((sflags & HC_SEG_FIRST) && a_load) {
               hb = hi_buf(step);
               lb = lo_buf(step);
               mbar_wait(&a_full[hb], (aph >> hb) & 1u);
@@ -540,7 +560,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
               ++chunk_ctr;
               fresh = true;
             }
-            if (sflags & HC_SEG_LAST) {
+            if ((sflags & HC_SEG_LAST) && a_free) {
               if (MERGED) tcgen05_commit(&a_empty[lb]);
               tcgen05_commit(&a_empty[hb]);
               ++step;
@@ -566,8 +586,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BLK + ch * CW);
     uint32_t em0 = 0, em1 = 0, ec0 = 0, ec1 = 0, chunk_ctr = 0, tile_ctr = 0;
     float acc[CW];
-    for (int it = 0, t = hc_tile_at(p, 0); t >= 0; t = hc_tile_at(p, ++it), ++tile_ctr) {
-      const HcTile tl = hc_tile(p, t);
+    for (HcWalk wk = hc_walk_begin(); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
+      const HcTile tl = hc_tile(p, wk);
       const int ndrains = p.probs[tl.prob].ndrains;
       const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
 #pragma unroll
@@ -604,7 +624,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       }
       // ---- fused epilogue + stores for this thread's position
       const int qpos = tl.q0 + m;
-      const int h = qpos / p.Wp, wr = qpos - h * p.Wp;
+      const int h = hc_div(qpos, p.div_wp), wr = qpos - h * p.Wp;
       const int w = tl.w0 + wr;
       const bool valid = (wr < p.Wt) && (w < p.W) && (h < p.H);
       if (valid) {
@@ -884,6 +904,10 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     p.total_tiles = (int)tt * p.nprob;
   }
   p.kchunks = d->C / KC;
+  p.div_ntn = hc_make_div((uint32_t)p.n_tiles_n);
+  p.div_tpc = hc_make_div((uint32_t)p.tiles_per_col);
+  p.div_ct = hc_make_div((uint32_t)p.col_tiles);
+  p.div_wp = hc_make_div((uint32_t)p.Wp);
 
   // group the base taps by A source
   p.ngroups = 0;
@@ -985,6 +1009,8 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     pr.ndrains = p.kchunks * mid_commits + ceil_div(p.kchunks, pr.kcs_per_drain);
   }
   for (int q = p.nprob; q < HC_MAX_PROBS; ++q) p.probs[q] = p.probs[0];
+  // (two-pass mode releases the lo tile after each B_hi pass, so it keeps one load per problem)
+  p.a_share = (p.nprob > 1 && p.kchunks == 1 && mode != HC_X3_TWO_PASS && !(g_hconv_mask & 512)) ? 1 : 0;
   p.a_box_bytes = (uint32_t)(p.RB * p.Wp) * (uint32_t)(KC * 2);
   p.a_buf_bytes = ((uint32_t)(p.RB * p.Wp + 8) * (uint32_t)(KC * 2) + 1023u) & ~1023u;
   p.epi = d->epi;
