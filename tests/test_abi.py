@@ -59,6 +59,33 @@ def test_struct_layouts_match_header():
     assert f'#define SMC_IGEMM_MAX_TAPS {_lib.MAX_TAPS}' in src
 
 
+def test_struct_offsets_match_a_c_compiler(tmp_path):
+    """Every field of the three structs that cross the boundary sits where gcc puts it for include/stylemc_b200.h (sizeof + offsetof
+    printed by a tiny C program); catches a ctypes mirror that drifts from the header."""
+    import shutil
+    import subprocess
+    from stylemc_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('no C compiler')
+    structs = {'smc_igemm_epilogue': _lib.Epilogue, 'smc_igemm_desc': _lib.IgemmDesc, 'smc_upfirdn2d_params': _lib.UpfirdnParams,
+               'smc_igemm_tap': _lib.Tap}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "stylemc_b200.h"', 'int main(void) {']
+    for cname, st in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, st in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(st), (cname, got[cname], ctypes.sizeof(st))
+        for fname, _ in st._fields_:
+            assert int(got[f'{cname}.{fname}']) == getattr(st, fname).offset, (cname, fname)
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, 'stylemc_b200')
     for dirpath, _, files in os.walk(pkg):
