@@ -153,7 +153,8 @@ int smc_igemm_config(int key, int value);
  * Activations are NHWC fp16 ("hi" plane, optional "lo" plane = rn(v - hi)); styles are rows of the
  * [N, 26, 512] S tensor addressed as base pointer + n * stride. */
 /* A/B diagnostics (process-global, not thread-safe): key 0 / 1 / 2 = use the newer smc_fir_act / smc_fir_bwd / smc_act_bwd kernels,
- * key 3 = the warp-row streaming smc_upfirdn2d kernels (all default on; 0 selects the older kernel). */
+ * key 3 = the warp-row streaming smc_upfirdn2d kernels (all default on; 0 selects the older kernel);
+ * key 4 = smc_resample_fwd/bwd run the vertical pass first for >= 2x down-sampling. */
 int smc_synth_config(int key, int value);
 int smc_demod_coefs(const float* q, const float* s, int64_t s_stride, float* d, int n, int cin, int cout, void* stream);
 /* c_pitch >= c is the channel pitch of the NHWC side (channels c .. c_pitch-1 are left untouched: zero them once). */

@@ -59,7 +59,7 @@ def test_encode_image_input_gradient(model, params):
     assert r <= 1e-3
 
 
-@pytest.mark.parametrize('res', [64, 256, 1024])
+@pytest.mark.parametrize('res', [64, 256, 512, 1024])
 def test_unprocess_fwd_bwd(res):
     from stylemc_b200 import resample
     gen = torch.Generator().manual_seed(6)
