@@ -142,6 +142,19 @@ typedef struct smc_igemm_desc {
 } smc_igemm_desc;
 
 int smc_igemm(const smc_igemm_desc* desc, void* stream);
+/* Diagnostics (host only, no CUDA call, not thread-safe): the plan csrc/hconv.cu would launch `desc` with.  Returns SMC_EUNSUPPORTED
+ * (and kernel = 0) when the call would be served by the per-tap kernel csrc/igemm.cu instead. */
+typedef struct smc_igemm_plan_info {
+  int32_t kernel;                 /* 1: halo-tile kernel */
+  int32_t bn, kc, mode;           /* template arguments: N tile, K slab, 0 x1 / 1 split two-pass / 2 split merged-B */
+  int32_t Wt, Wp, RB;             /* tile width, pitch with halo, rows of the TMA box */
+  int32_t na_hi, na_lo, nb;       /* A buffers (hi / lo ring), weight stages */
+  int32_t b_resident, a_share, nprob, kchunks;
+  int32_t super_tiles, grid;      /* (position, N) tiles; CTAs */
+  int32_t smem_bytes, tmem_cols;
+  int32_t prob_ntaps[4], prob_nsegs[4], prob_ndrains[4], prob_commits[4], prob_stages[4];
+} smc_igemm_plan_info;
+int smc_igemm_plan(const smc_igemm_desc* desc, smc_igemm_plan_info* out);
 /* Tuning / diagnostics knobs of the convolution path (process-global; set before launching, not thread-safe):
  *   key 0: halo-tile kernel (hconv.cu) use: 0 never, 1 auto (default), 2 whenever the shape is supported
  *   key 2: weight-stage ring depth (0 = by stage size)   key 3: tile width Wt in pixels (0 = widest that fits, <= 64)

@@ -48,6 +48,12 @@ class IgemmDesc(ctypes.Structure):
                 ('nprob', ctypes.c_int32), ('prob_ntaps', ctypes.c_int32 * 4), ('prob_o_off', ctypes.c_int64 * 4)]
 
 
+class IgemmPlanInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('kernel', 'bn', 'kc', 'mode', 'Wt', 'Wp', 'RB', 'na_hi', 'na_lo', 'nb', 'b_resident', 'a_share', 'nprob',
+                                              'kchunks', 'super_tiles', 'grid', 'smem_bytes', 'tmem_cols')] + \
+               [(n, ctypes.c_int32 * 4) for n in ('prob_ntaps', 'prob_nsegs', 'prob_ndrains', 'prob_commits', 'prob_stages')]
+
+
 class UpfirdnParams(ctypes.Structure):
     _fields_ = [('N', ctypes.c_int32), ('C', ctypes.c_int32), ('inH', ctypes.c_int32), ('inW', ctypes.c_int32),
                 ('outH', ctypes.c_int32), ('outW', ctypes.c_int32),
@@ -66,6 +72,7 @@ SIGNATURES = {
     'smc_bias_act': 'pppppp iqiq ii fff p',
     'smc_upfirdn2d': 'ppp i p p',
     'smc_igemm': 'pp',
+    'smc_igemm_plan': 'pp',
     'smc_igemm_config': 'ii',
     'smc_synth_config': 'ii',
     'smc_demod_coefs': 'pp q p iii p',
@@ -147,7 +154,7 @@ def require_cuda(t, name):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
-_LAUNCHES = {'smc_abi_version': 0, 'smc_igemm_config': 0, 'smc_synth_config': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2}
+_LAUNCHES = {'smc_abi_version': 0, 'smc_igemm_config': 0, 'smc_igemm_plan': 0, 'smc_synth_config': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2}
 launch_count = 0
 igemm_hook = None      # bench.py installs a callable(desc_addr) -> context manager to time every smc_igemm launch
 

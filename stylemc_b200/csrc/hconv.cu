@@ -753,6 +753,8 @@ static int g_hconv_grid = 0;
 static int g_hconv_minpos = 64;     // auto mode: smallest H * W routed to this kernel
 static int g_hconv_mask = 7;   // bit 0: single-source convs with > 4 taps, bit 1: <= 4 taps, bit 2: multi-source (up2 dgrad)
 
+static smc_igemm_plan_info* g_plan_out = nullptr;   // set only inside smc_igemm_plan (diagnostics, not thread-safe)
+
 void hconv_config(int key, int value) {
   if (key == 0) g_hconv_mode = value;
   if (key == 2) g_hconv_nb = value;
@@ -1032,6 +1034,43 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   const size_t smem = smem_fixed + (size_t)(p.na_hi + p.na_lo) * p.a_buf_bytes;
   if (smem > 227 * 1024) return SMC_EUNSUPPORTED;
 
+  if (g_plan_out) {                    // smc_igemm_plan: report the launch plan instead of launching (host only, no CUDA call)
+    smc_igemm_plan_info& o = *g_plan_out;
+    o.kernel = 1; o.bn = BN; o.kc = KC; o.mode = mode;
+    o.Wt = p.Wt; o.Wp = p.Wp; o.RB = p.RB; o.na_hi = p.na_hi; o.na_lo = p.na_lo; o.nb = p.nb;
+    o.b_resident = p.b_resident; o.a_share = p.a_share; o.nprob = p.nprob; o.kchunks = p.kchunks;
+    o.super_tiles = p.super_tiles;
+    o.grid = p.super_tiles < (g_hconv_grid > 0 ? g_hconv_grid : kNumSMs) ? p.super_tiles : (g_hconv_grid > 0 ? g_hconv_grid : kNumSMs);
+    o.smem_bytes = (int32_t)smem;
+    {                                  // TMEM columns exactly as hconv_kernel derives them from <BN, MODE>
+      const int blk = (mode == HC_X3_MERGED ? 2 : 1) * BN;
+      const int setcols = (mode == HC_X3_TWO_PASS ? 2 : 1) * HC_MB * blk;
+      const int sets = 2 * setcols <= 512 ? 2 : 1;
+      o.tmem_cols = sets * setcols < 32 ? 32 : sets * setcols;
+    }
+    for (int q = 0; q < HC_MAX_PROBS; ++q) {
+      const HcProb& pr = p.probs[q < p.nprob ? q : 0];
+      o.prob_nsegs[q] = q < p.nprob ? pr.nsegs : 0;
+      o.prob_ndrains[q] = q < p.nprob ? pr.ndrains : 0;
+      o.prob_stages[q] = 0;
+      // main-accumulator commits per tile as the MMA issuer's loop makes them (must equal the drains the epilogue waits for)
+      int commits = 0, in_chunk = 0, ntap = 0;
+      for (int kc = 0; kc < p.kchunks && q < p.nprob; ++kc) {
+        const bool chunk_ends = (in_chunk + 1 == pr.kcs_per_drain) || (kc == p.kchunks - 1);
+        for (int si = pr.seg_begin; si < pr.seg_begin + pr.nsegs; ++si) {
+          const int f = p.segs[si].flags;
+          if ((f & HC_SEG_COMMIT) && (!(f & HC_SEG_SLABEND) || chunk_ends)) ++commits;
+          if (kc == 0) ntap += p.segs[si].te - p.segs[si].tb;
+        }
+        in_chunk = chunk_ends ? 0 : in_chunk + 1;
+      }
+      o.prob_commits[q] = commits;
+      o.prob_ntaps[q] = ntap;
+      if (q < p.nprob) o.prob_stages[q] = pr.stage_base;
+    }
+    return SMC_OK;
+  }
+
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return SMC_EDRIVER;
   const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1069,6 +1108,18 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
 }
 
 }  // namespace smc
+
+// The launch plan the halo-tile kernel would use for a descriptor (tile shape, shared-memory and TMEM budget, problem table), without
+// touching the GPU: lets the CPU test-suite check the planner on every layer shape of the benchmark networks.
+extern "C" int smc_igemm_plan(const smc_igemm_desc* desc, smc_igemm_plan_info* out) {
+  if (!desc || !out) return SMC_EINVAL;
+  if (desc->nprob < 0 || desc->nprob > 4 || desc->ntaps < 1 || desc->ntaps > SMC_IGEMM_MAX_TAPS) return SMC_EINVAL;
+  *out = smc_igemm_plan_info{};
+  smc::g_plan_out = out;
+  const int r = smc::hconv_try_launch(desc, nullptr);
+  smc::g_plan_out = nullptr;
+  return r;               // SMC_EUNSUPPORTED: the call would go to the per-tap kernel (out->kernel stays 0)
+}
 
 extern "C" int smc_igemm_config(int key, int value) {
   smc::hconv_config(key, value);
