@@ -152,3 +152,25 @@ def test_setup_filter_matches_oracle():
     from stylemc_b200.ops import upfirdn2d
     for taps, kw in (([1, 3, 3, 1], {}), ([1, 2, 3, 4, 4, 3, 2, 1], {}), ([1, 2, 1], dict(gain=3, flip_filter=True)), (None, {})):
         assert torch.equal(upfirdn2d.setup_filter(taps, **kw), fir.setup_filter(taps, **kw))
+
+
+def test_bench_flop_accounting_matches_survey_8d():
+    """bench.py's algorithmic work per image (the numerator of roofline.achieved) against SURVEY.md section 8(d): synthesis forward
+    148.13 GFLOP at 1024 px, 90.14 GFLOP for the 256-px truncation, ViT-B/32 forward 8.82 GFLOP."""
+    import importlib.util
+    import os
+    from types import SimpleNamespace as NS
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_module', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ch = lambda r: min(32768 // r, 512)
+    blocks = []
+    for k, r in enumerate([4, 8, 16, 32, 64, 128, 256, 512, 1024]):
+        conv0 = None if k == 0 else NS(cin=ch(r // 2), cout=ch(r))
+        blocks.append(NS(resolution=r, conv0=conv0, conv1=NS(cin=ch(r), cout=ch(r)), torgb=NS(cin=ch(r))))
+    assert abs(bench.synth_flops_per_image(blocks, 8) / 1e9 - 148.13) < 0.4          # + ToRGB 0.39 GFLOP
+    assert abs(bench.synth_flops_per_image(blocks, 6) / 1e9 - 90.14) < 0.2
+    assert abs(bench.VIT_FLOPS_FWD / 1e9 - 8.82) < 0.1
+    p = bench.peaks()
+    assert p['hbm'] > 1000 and p['tflops'] > 100
