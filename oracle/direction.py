@@ -1,6 +1,6 @@
 """Oracle: one find_direction optimisation step  (TEST INFRASTRUCTURE ONLY).
 
-Restates, for clip_type='small' / clip_loss_type='default' / identity = landmarks = 0:
+Restates, for clip_type='small' or 'double' / clip_loss_type='default' / identity = landmarks = 0:
 ``find_direction.py:38-41`` (trainable S rows), ``:49-52`` (unprocess), ``:148-169``
 (compute_clip_loss), ``:190-191`` (L2 term), ``:298-339`` (cosine LR, delta insertion, two
 synthesis passes, backward, SGD) and ``clip_loss.py:8-34`` (directional CLIP loss).
@@ -45,6 +45,17 @@ class CLIPLoss:
         e = e / e.norm(dim=1, keepdim=True)                                            # :28
         cos = F.cosine_similarity(e, self.text_features)                               # :29-32
         return (len(src_image) - cos.sum()) / len(src_image)                           # :34
+
+
+class DoubleCLIPLoss:
+    """clip_type='double' (the CLI default, find_direction.py:216): ``init_clip_loss`` builds one CLIPLoss on ViT-B/32 and one
+    on ViT-B/16 (:117-119), ``compute_clip_loss`` adds them as ``loss32 + 0.5 * loss16`` (:160-164)."""
+
+    def __init__(self, loss_small, loss_large):
+        self.loss_small, self.loss_large = loss_small, loss_large
+
+    def __call__(self, src_image, tgt_image):
+        return self.loss_small(src_image, tgt_image) + 0.5 * self.loss_large(src_image, tgt_image)
 
 
 def cosine_lr(base_lr, it, total):

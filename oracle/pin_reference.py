@@ -215,9 +215,9 @@ def pin_driver(R, out):
     return G_ref, G_ora, S_r, shapes_r
 
 
-def pin_clip(R, out):
-    print('clip: restated ViT-B/32 vs transformers.CLIPModel (weight copy)')
-    model = vit.CLIP(seed=0)
+def pin_clip(R, out, cfg=vit.VIT_B32, seed=0, name='ViT-B/32'):
+    print(f'clip: restated {name} vs transformers.CLIPModel (weight copy)')
+    model = vit.CLIP(seed=seed, cfg=cfg)
     g = torch.Generator().manual_seed(3)
     images = torch.randn(2, 3, 224, 224, generator=g)
     toks = torch.cat([vit.synthetic_tokens('pos'), vit.synthetic_tokens('neg')])
@@ -225,9 +225,10 @@ def pin_clip(R, out):
         ei, et = model.encode_image(images), model.encode_text(toks)
     try:
         from transformers import CLIPConfig, CLIPModel
-        cfg = CLIPConfig()  # defaults are ViT-B/32 with quick_gelu
-        cfg.vision_config.attn_implementation = cfg.text_config.attn_implementation = 'eager'
-        hf = CLIPModel(cfg).eval()
+        hcfg = CLIPConfig()  # defaults are ViT-B/32 with quick_gelu
+        hcfg.vision_config.patch_size = cfg['vision_patch_size']
+        hcfg.vision_config.attn_implementation = hcfg.text_config.attn_implementation = 'eager'
+        hf = CLIPModel(hcfg).eval()
         sd = hf.state_dict()
         p = model.p
 
@@ -274,8 +275,8 @@ def pin_clip(R, out):
     return model
 
 
-def install_stub_clip(R, model):
-    R.clip.load = lambda name, device=None: (model, None)
+def install_stub_clip(R, model, model_b16=None):
+    R.clip.load = lambda name, device=None: ({'ViT-B/32': model, 'ViT-B/16': model_b16}[name], None)
     R.clip.tokenize = lambda texts: vit.synthetic_tokens('pos' if 'woman' in texts[0] else 'neg')
 
 
@@ -324,6 +325,45 @@ def pin_step(R, model, G_ref, G_ora, S, shapes, out):
     out['styles'] = S.numpy()
 
 
+def pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, out):
+    """clip_type='double' (the CLI default, find_direction.py:216): the reference's own init_clip_loss / compute_clip_loss
+    (find_direction.py:100-122,148-169) on two stub towers vs oracle.direction.DoubleCLIPLoss."""
+    print('step (double): reference init_clip_loss + compute_clip_loss with clip_type="double" vs the oracle (64-px net)')
+    from torchvision.transforms import CenterCrop, Compose, Resize
+    from PIL import Image
+    install_stub_clip(R, model, model_b16)
+    dev = torch.device('cpu')
+    mean, std = R.utils.get_mean_std(dev)
+    transf = Compose([Resize(224, interpolation=Image.BICUBIC), CenterCrop(224)])
+    T = R.fd.S_TRAINABLE_SPACE_CHANNELS
+    l1, l2 = R.fd.init_clip_loss('default', 'double', dev, POS_TEXT, NEG_TEXT)
+    assert l1.model is model and l2.model is model_b16
+    delta0 = 0.1 * torch.randn(1, 8, 512, generator=torch.Generator().manual_seed(4))      # same delta as step64.npz
+    delta = delta0.clone().requires_grad_(True)
+    styles_direction = torch.zeros(1, R.fd.N_STYLE_CHANNELS, 512)
+    styles_direction[:, T] = delta
+    styles2 = S + styles_direction
+    _, img = R.utils.generate_image(G_ref, 100, styles2, shapes, 'const', dev)
+    _, original = R.utils.generate_image(G_ref, 100, S, shapes, 'const', dev)
+    clip_term = R.fd.compute_clip_loss(img, original, 'default', 'double', 1.0, l1, l2, transf, mean, std, dev, POS_TEXT, NEG_TEXT)
+    reg = 0.1 * torch.nn.functional.mse_loss(styles2[:, T], S[:, T])
+    loss = clip_term + reg
+    loss.backward()
+    pos, neg = vit.synthetic_tokens('pos'), vit.synthetic_tokens('neg')
+    loss_fn = direction.DoubleCLIPLoss(direction.CLIPLoss(model, pos, neg), direction.CLIPLoss(model_b16, pos, neg))
+    o = direction.direction_step(G_ora, shapes, loss_fn, S, delta0, 100)
+    close(o['loss'], loss.detach(), 1e-6, 'double step loss')
+    rel = ((o['grad'] - delta.grad).norm() / delta.grad.norm()).item()
+    print(f'  grad rel-l2 {rel:.3e}, |grad| {delta.grad.norm():.3e}')
+    assert rel < 1e-5
+    out['loss'], out['clip_loss'], out['l2_loss'], out['grad'] = (loss.detach().numpy(), clip_term.detach().numpy(), reg.detach().numpy(),
+                                                                   delta.grad.numpy())
+    out['b16_seed'] = np.array(B16_SEED)     # styles, delta and images are those of step64.npz
+
+
+B16_SEED = 7
+
+
 def pin_config1(R, model, out):
     print('config 1: FFHQ-256 config-f net, batch 4, one find_direction step through the reference (CPU)')
     G_ref = synthesis.make_generator(256, seed=0)
@@ -352,17 +392,22 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--check', action='store_true', help='verify only, do not write fixtures')
     ap.add_argument('--skip-config1', action='store_true')
+    ap.add_argument('--only-double', action='store_true', help='(re)write only clip_b16.npz and step64_double.npz')
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     R = import_reference()
-    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'step64', 'config1')}
+    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'config1')}
     pin_ops(R, fx['ops'])
     pin_modconv_e4e(R, fx['ops'])
     G_ref, G_ora, S, shapes = pin_driver(R, fx['synth64'])
     model = pin_clip(R, fx['clip'])
+    model_b16 = pin_clip(R, fx['clip_b16'], vit.VIT_B16, B16_SEED, 'ViT-B/16')
     pin_step(R, model, G_ref, G_ora, S, shapes, fx['step64'])
-    if not args.skip_config1:
+    pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, fx['step64_double'])
+    if not args.skip_config1 and not args.only_double:
         pin_config1(R, model, fx['config1'])
+    if args.only_double:
+        fx = {k: fx[k] for k in ('clip_b16', 'step64_double')}
     if not args.check:
         os.makedirs(GOLD, exist_ok=True)
         for name, d in fx.items():

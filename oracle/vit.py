@@ -1,4 +1,4 @@
-"""Oracle: CLIP ViT-B/32 image tower + text tower  (TEST INFRASTRUCTURE ONLY).
+"""Oracle: CLIP ViT-B/32 (and ViT-B/16) image tower + text tower  (TEST INFRASTRUCTURE ONLY).
 
 Restates openai/CLIP ``clip/model.py`` (VisionTransformer, Transformer, ResidualAttentionBlock,
 fp32-internal LayerNorm, QuickGELU = x*sigmoid(1.702x), CLIP.encode_image / encode_text).  The
@@ -18,6 +18,9 @@ import torch.nn.functional as F
 VIT_B32 = dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768, vision_patch_size=32,
                context_length=77, vocab_size=49408, transformer_width=512, transformer_heads=8,
                transformer_layers=12)
+# "ViT-B/16" (clip_loss.py:12-13, the second tower of clip_type='double'): 16-px patches -> 14 x 14 + 1 = 197 tokens; the
+# rest of the architecture is identical
+VIT_B16 = dict(VIT_B32, vision_patch_size=16)
 
 
 def _block_params(g, prefix, width, layers, p):

@@ -80,3 +80,28 @@ def test_step_golden(golden):
     assert abs(o['loss'].item() - float(g['loss'])) <= 1e-6
     assert ((o['grad'] - T(g['grad'])).norm() / T(g['grad']).norm()).item() <= 1e-4
     assert (direction.unprocess(T(g['original_img']))[:1] - T(g['unprocessed'])).abs().max().item() <= 1e-5
+
+
+def test_clip_b16_golden(golden):
+    """ViT-B/16 (197 tokens), the second tower of clip_type='double' (clip_loss.py:12-13)."""
+    g = golden('clip_b16')
+    model = vit.CLIP(seed=int(golden('step64_double')['b16_seed']), cfg=vit.VIT_B16)
+    images = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        assert (model.encode_image(images) - T(g['image_features'])).abs().max().item() <= 1e-5
+        assert (model.encode_text(T(g['tokens'])) - T(g['text_features'])).abs().max().item() <= 1e-5
+
+
+def test_step_double_golden(golden):
+    """clip_type='double': loss32 + 0.5 * loss16 as the reference's init_clip_loss / compute_clip_loss computed it
+    (find_direction.py:117-119,160-164); styles and delta are those of step64.npz."""
+    g, gd = golden('step64'), golden('step64_double')
+    G = synthesis.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    shapes = synthesis.get_temp_shapes(G)
+    pos, neg = vit.synthetic_tokens('pos'), vit.synthetic_tokens('neg')
+    loss_fn = direction.DoubleCLIPLoss(direction.CLIPLoss(vit.CLIP(seed=0), pos, neg),
+                                       direction.CLIPLoss(vit.CLIP(seed=int(gd['b16_seed']), cfg=vit.VIT_B16), pos, neg))
+    o = direction.direction_step(G, shapes, loss_fn, T(g['styles']), T(g['delta']), 100)
+    assert abs(o['loss'].item() - float(gd['loss'])) <= 1e-6
+    assert abs(o['clip_loss'].item() - float(gd['clip_loss'])) <= 1e-6
+    assert ((o['grad'] - T(gd['grad'])).norm() / T(gd['grad']).norm()).item() <= 1e-4
