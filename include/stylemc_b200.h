@@ -217,6 +217,11 @@ int smc_layernorm_bwd(const float* dy, const float* x, int64_t in_row_stride, in
 int smc_attention_fwd(const float* qkv, void* ohi, void* olo, float* o32, int b, int t, int wd, int heads, int causal, void* stream);
 int smc_attention_bwd(const float* qkv, const float* d_o, void* ghi, void* glo, int b, int t, int wd, int heads, int causal,
                       void* stream);
+/* Sequences longer than the whole-sequence kernels hold in shared memory (ViT-B/16, clip_loss.py:12-13: 197 tokens): smc_attention_fwd
+   switches to query-row blocks by itself; the backward pass is this entry point (two launches: dQ per query-row block, dK/dV per key-row
+   block).  stats: caller-allocated fp32 scratch, 2 * b * heads * t words.  head_dim 64 only. */
+int smc_attention_bwd_tiled(const float* qkv, const float* d_o, void* ghi, void* glo, float* stats, int b, int t, int wd, int heads,
+                            int causal, void* stream);
 int smc_quickgelu_fwd(const float* h, void* hi, void* lo, int64_t n, void* stream);
 int smc_quickgelu_bwd(const float* dg, const float* h, void* hi, void* lo, int64_t n, void* stream);
 int smc_split_rows(const float* x, void* hi, void* lo, int64_t rows, int wd, int rows_per_group, int group_stride, int group_offset,

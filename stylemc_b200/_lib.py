@@ -95,6 +95,7 @@ SIGNATURES = {
     'smc_layernorm_bwd': 'pp qq ppp p q ii p',
     'smc_attention_fwd': 'pppp iiiii p',
     'smc_attention_bwd': 'pppp iiiii p',
+    'smc_attention_bwd_tiled': 'ppppp iiiii p',
     'smc_quickgelu_fwd': 'ppp q p',
     'smc_quickgelu_bwd': 'pppp q p',
     'smc_split_rows': 'ppp q iiii p',
@@ -125,7 +126,8 @@ def lib():
         for key, env in ((0, 'STYLEMC_HCONV'), (2, 'STYLEMC_HCONV_NB'), (3, 'STYLEMC_HCONV_WT'), (4, 'STYLEMC_HCONV_GRID'), (5, 'STYLEMC_HCONV_MASK'), (6, 'STYLEMC_HCONV_MINPOS')):
             if os.environ.get(env):          # diagnostics only: A/B the halo-tile conv kernel against the per-tap kernel
                 handle.smc_igemm_config(key, int(os.environ[env]))
-        for key, env in ((0, 'STYLEMC_FIR_ACT3'), (1, 'STYLEMC_FIR_BWD3'), (2, 'STYLEMC_ACT_BWD2'), (3, 'STYLEMC_UPFIRDN_ROWS'), (4, 'STYLEMC_RESAMPLE_VFIRST')):
+        for key, env in ((0, 'STYLEMC_FIR_ACT3'), (1, 'STYLEMC_FIR_BWD3'), (2, 'STYLEMC_ACT_BWD2'), (3, 'STYLEMC_UPFIRDN_ROWS'), (4, 'STYLEMC_RESAMPLE_VFIRST'),
+                         (5, 'STYLEMC_ATTENTION_TILED')):
             if os.environ.get(env):          # diagnostics only: A/B the newer glue kernels against the older ones
                 handle.smc_synth_config(key, int(os.environ[env]))
     return _lib
@@ -154,7 +156,8 @@ def require_cuda(t, name):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
-_LAUNCHES = {'smc_abi_version': 0, 'smc_igemm_config': 0, 'smc_igemm_plan': 0, 'smc_synth_config': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2}
+_LAUNCHES = {'smc_abi_version': 0, 'smc_igemm_config': 0, 'smc_igemm_plan': 0, 'smc_synth_config': 0, 'smc_resample_fwd': 2, 'smc_resample_bwd': 2, 'smc_grad_scale': 2,
+             'smc_attention_bwd_tiled': 2}
 launch_count = 0
 igemm_hook = None      # bench.py installs a callable(desc_addr) -> context manager to time every smc_igemm launch
 

@@ -1,19 +1,29 @@
-"""CLIP ViT-B/32 image tower (forward + backward to the pixels) and text tower (forward) on hand-written kernels.
+"""CLIP ViT-B/32 (and ViT-B/16) image tower (forward + backward to the pixels) and text tower (forward) on hand-written kernels.
 
 Stands in for the object ``clip.load(...)`` returns at clip_loss.py:11: ``encode_image(x[N,3,224,224]) -> [N,512]``,
 ``encode_text(tokens[B,77]) -> [B,512]``, ``dtype`` (openai/CLIP clip/model.py VisionTransformer / Transformer /
 ResidualAttentionBlock / QuickGELU; parameter names are the openai state-dict keys).  Every linear layer is one launch of the
-tcgen05 implicit GEMM (``smc_igemm``) with bias and residual add in its epilogue; LayerNorm, the 50-token attention core and
-QuickGELU are small fused kernels that emit the next GEMM's fp16 operand planes directly.  The residual stream and all
+tcgen05 implicit GEMM (``smc_igemm``) with bias and residual add in its epilogue; LayerNorm, the attention core (50 tokens for
+ViT-B/32 and 77 for the text tower in one CTA per head; 197 tokens for ViT-B/16 in row blocks) and QuickGELU are small fused kernels that emit the next GEMM's fp16 operand planes directly.  The residual stream and all
 statistics stay fp32.  Weights are frozen: the backward pass produces the gradient w.r.t. the input pixels only (the
 reference accumulates 88 M unused weight gradients per step).
 """
+import os
+
 import torch
 
 from . import _lib, gemm
 
 VIT_B32 = dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768, vision_patch_size=32,
                context_length=77, vocab_size=49408, transformer_width=512, transformer_heads=8, transformer_layers=12)
+# clip.load("ViT-B/16") (clip_loss.py:12-13), the second tower of clip_type='double': 16-px patches, 14 * 14 + 1 = 197 tokens
+VIT_B16 = dict(VIT_B32, vision_patch_size=16)
+
+
+def whole_sequence_attention_bwd_fits(t, head_dim):
+    """smc_attention_bwd keeps q, k, v, dO and two [t, t+1] score matrices of one head in shared memory (200 KB budget, vit.cu); longer
+    sequences take smc_attention_bwd_tiled."""
+    return (4 * t * (head_dim + 1) + 2 * t * (t + 1)) * 4 <= 200 * 1024
 
 
 class _Linear:
@@ -155,6 +165,8 @@ class CLIPModel:
             d_feat = d_feat.float().contiguous()
             dln = torch.empty([b, wd], dtype=torch.float32, device=self.device)
             _lib.call('smc_head_proj_bwd', _lib.ptr(d_feat), _lib.ptr(self.vproj), _lib.ptr(dln), b, wd, cfg['embed_dim'], _lib.stream())
+            tiled = not whole_sequence_attention_bwd_fits(t, wd // tw.heads) or bool(int(os.environ.get('STYLEMC_ATTENTION_TILED', '0')))
+            stats = torch.empty([2, b * tw.heads * t], dtype=torch.float32, device=self.device) if tiled else None
             dx = torch.zeros([rows, wd], dtype=torch.float32, device=self.device)
             _lib.call('smc_layernorm_bwd', _lib.ptr(dln), _lib.ptr(saved['xl']), t, 0, _lib.ptr(self.ln_post[0]), _lib.ptr(saved['mp']),
                       _lib.ptr(saved['rp']), _lib.ptr(dx), b, wd, 0, _lib.stream())
@@ -172,8 +184,12 @@ class CLIPModel:
                 _lib.call('smc_split_rows', _lib.ptr(dx), _lib.ptr(dxp[0]), self._lo(dxp), rows, wd, rows, 0, 0, _lib.stream())
                 do = self._linear(dxp, blk['out'], rows, bwd=True)
                 dqkv = self._planes(rows, 3 * wd)
-                _lib.call('smc_attention_bwd', _lib.ptr(sv['qkv']), _lib.ptr(do), _lib.ptr(dqkv[0]), self._lo(dqkv), b, t, wd, tw.heads, 0,
-                          _lib.stream())
+                if tiled:
+                    _lib.call('smc_attention_bwd_tiled', _lib.ptr(sv['qkv']), _lib.ptr(do), _lib.ptr(dqkv[0]), self._lo(dqkv), _lib.ptr(stats), b, t,
+                              wd, tw.heads, 0, _lib.stream())
+                else:
+                    _lib.call('smc_attention_bwd', _lib.ptr(sv['qkv']), _lib.ptr(do), _lib.ptr(dqkv[0]), self._lo(dqkv), b, t, wd, tw.heads, 0,
+                              _lib.stream())
                 dln1 = self._linear(dqkv, blk['qkv'], rows, bwd=True)
                 _lib.call('smc_layernorm_bwd', _lib.ptr(dln1), _lib.ptr(sv['x_in']), 1, 0, _lib.ptr(blk['ln1'][0]), _lib.ptr(sv['m1']),
                           _lib.ptr(sv['r1']), _lib.ptr(dx), rows, wd, 1, _lib.stream())

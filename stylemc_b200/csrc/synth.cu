@@ -1548,11 +1548,12 @@ static int g_fir_act3 = 3;   // 0: keep the older marching kernel; 2 / 3 / 4: fi
 static int g_fir_bwd3 = 1;   // same for smc_fir_bwd (key 1)
 static int g_act_bwd2 = 1;   // same for smc_act_bwd (key 2)
 
-namespace smc { extern int g_upfirdn_rows; extern int g_resample_vfirst; }   // upfirdn2d.cu, vit.cu
+namespace smc { extern int g_upfirdn_rows; extern int g_resample_vfirst; extern int g_attention_tiled; }   // upfirdn2d.cu, vit.cu
 
 extern "C" int smc_synth_config(int key, int value) {
   if (key == 3) { smc::g_upfirdn_rows = value; return SMC_OK; }
   if (key == 4) { smc::g_resample_vfirst = value; return SMC_OK; }
+  if (key == 5) { smc::g_attention_tiled = value; return SMC_OK; }
   if (key == 0) g_fir_act3 = value;
   else if (key == 1) g_fir_bwd3 = value;
   else if (key == 2) g_act_bwd2 = value;

@@ -606,6 +606,358 @@ __global__ void __launch_bounds__(256) attention_bwd2_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Long sequences (ViT-B/16, the second tower of clip_type='double', clip_loss.py:12-13: 14 x 14 + 1 = 197 tokens).  The whole-sequence
+// kernels above keep T x (T+1) score words per CTA (310 KB forward, 517 KB backward at T = 197), more than an SM has.  Here a CTA owns a
+// block of QB query rows (forward and dQ) or KB key rows (dK, dV) of one (sequence, head); the other operand stays whole in shared memory
+// (2 x 51 KB at T = 197) and the score block is [QB][T+1].  Same 4 x 4 interleaved register tiles as above, head_dim 64 only.
+//   forward      : S = (q*scale) k^T, P = softmax(S), O = P v                                   for the CTA's query rows
+//   backward (q) : recompute P rows; dP = dO v^T; dot = rowsum(P*dP); dS = P*(dP-dot)*scale; dQ = dS k; also stores per row
+//                  lse = max + log(sum) and dot in ``stats`` [2][B*heads][T] for the second kernel
+//   backward (kv): P^T, dS^T for the CTA's key rows from lse/dot (P = exp(s*scale - lse)); dK = dS^T q, dV = P^T dO
+__global__ void __launch_bounds__(256) attention_fwd_rows_kernel(const float* __restrict__ qkv, __half* __restrict__ ohi, __half* __restrict__ olo,
+                                                                 float* __restrict__ o32, int T, int Wd, int heads, int causal, int QB, int nqb) {
+  extern __shared__ float sm[];
+  constexpr int hd = 64, ld = hd + 1;
+  const int qb = blockIdx.x % nqb, bh = blockIdx.x / nqb;
+  const int b = bh / heads, h = bh % heads;
+  const int r0 = qb * QB, R = min(QB, T - r0);
+  float* k = sm;                  // [T][ld]
+  float* v = k + T * ld;          // [T][ld]
+  float* q = v + T * ld;          // [QB][ld]
+  float* S = q + QB * ld;         // [QB][T+1]
+  const float scale = rsqrtf((float)hd);
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    const float* row = qkv + ((long long)b * T + t) * 3 * Wd + h * hd + d;
+    k[t * ld + d] = row[Wd];
+    v[t * ld + d] = row[2 * Wd];
+  }
+  for (int i = threadIdx.x; i < R * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    q[t * ld + d] = qkv[((long long)b * T + r0 + t) * 3 * Wd + h * hd + d] * scale;
+  }
+  __syncthreads();
+  const int TRr = (R + 3) >> 2, TRc = (T + 3) >> 2;
+  for (int tile = threadIdx.x; tile < TRr * TRc; tile += blockDim.x) {
+    const int tr = tile / TRc, tc = tile - tr * TRc;
+    const float *qp[4], *kp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = tr + TRr * i, c = tc + TRc * i;
+      qp[i] = q + (r < R ? r : R - 1) * ld;
+      kp[i] = k + (c < T ? c : T - 1) * ld;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < hd; ++d) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = qp[i][d]; bb[i] = kp[i][d]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bb[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = tr + TRr * i;
+      if (r >= R) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = tc + TRc * j;
+        if (c < T) S[r * (T + 1) + c] = (causal && c > r0 + r) ? -INFINITY : acc[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += blockDim.x >> 5) {
+    float m = -INFINITY;
+    for (int c = lane; c < T; c += 32) m = fmaxf(m, S[r * (T + 1) + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < T; c += 32) { const float e = expf(S[r * (T + 1) + c] - m); S[r * (T + 1) + c] = e; s += e; }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int c = lane; c < T; c += 32) S[r * (T + 1) + c] *= inv;
+  }
+  __syncthreads();
+  for (int tile = threadIdx.x; tile < TRr * 16; tile += blockDim.x) {
+    const int tt = tile >> 4, td = tile & 15;
+    const float* sp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = tt + TRr * i;
+      sp[i] = S + (t < R ? t : R - 1) * (T + 1);
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < T; ++c) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sp[i][c]; bb[i] = v[c * ld + td + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * bb[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = tt + TRr * i;
+      if (t >= R) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long o = ((long long)b * T + r0 + t) * Wd + h * hd + td + 16 * j;
+        if (ohi) store_split(ohi, olo, o, acc[i][j]);
+        if (o32) o32[o] = acc[i][j];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) attention_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, __half* __restrict__ ghi,
+                                                              __half* __restrict__ glo, float* __restrict__ stats, int T, int Wd, int heads, int causal,
+                                                              int QB, int nqb) {
+  extern __shared__ float sm[];
+  constexpr int hd = 64, ld = hd + 1;
+  const int qb = blockIdx.x % nqb, bh = blockIdx.x / nqb;
+  const int b = bh / heads, h = bh % heads;
+  const int r0 = qb * QB, R = min(QB, T - r0);
+  float* k = sm;                  // [T][ld]
+  float* v = k + T * ld;          // [T][ld]
+  float* q = v + T * ld;          // [QB][ld]
+  float* go = q + QB * ld;        // [QB][ld]
+  float* P = go + QB * ld;        // [QB][T+1]
+  float* dS = P + QB * (T + 1);   // [QB][T+1]
+  const float scale = rsqrtf((float)hd);
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    const float* row = qkv + ((long long)b * T + t) * 3 * Wd + h * hd + d;
+    k[t * ld + d] = row[Wd];
+    v[t * ld + d] = row[2 * Wd];
+  }
+  for (int i = threadIdx.x; i < R * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    q[t * ld + d] = qkv[((long long)b * T + r0 + t) * 3 * Wd + h * hd + d];
+    go[t * ld + d] = dO[((long long)b * T + r0 + t) * Wd + h * hd + d];
+  }
+  __syncthreads();
+  const int TRr = (R + 3) >> 2, TRc = (T + 3) >> 2;
+  for (int tile = threadIdx.x; tile < TRr * TRc; tile += blockDim.x) {
+    const int tr = tile / TRc, tc = tile - tr * TRc;
+    int ro[4], co[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = tr + TRr * i, c = tc + TRc * i;
+      ro[i] = (r < R ? r : R - 1) * ld;
+      co[i] = (c < T ? c : T - 1) * ld;
+    }
+    float as[4][4], ap[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { as[i][j] = 0.f; ap[i][j] = 0.f; }
+#pragma unroll 2
+    for (int d = 0; d < hd; ++d) {
+      float a[4], bb[4], g[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = q[ro[i] + d]; bb[i] = k[co[i] + d]; g[i] = go[ro[i] + d]; w[i] = v[co[i] + d]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { as[i][j] += a[i] * bb[j]; ap[i][j] += g[i] * w[j]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = tr + TRr * i;
+      if (r >= R) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = tc + TRc * j;
+        if (c < T) {
+          P[r * (T + 1) + c] = (causal && c > r0 + r) ? -INFINITY : as[i][j] * scale;
+          dS[r * (T + 1) + c] = ap[i][j];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_rows = (long long)(gridDim.x / nqb) * T;      // B * heads * T
+  for (int r = warp; r < R; r += blockDim.x >> 5) {
+    float m = -INFINITY;
+    for (int c = lane; c < T; c += 32) m = fmaxf(m, P[r * (T + 1) + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < T; c += 32) { const float e = expf(P[r * (T + 1) + c] - m); P[r * (T + 1) + c] = e; s += e; }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    float dot = 0.f;
+    for (int c = lane; c < T; c += 32) { const float pp = P[r * (T + 1) + c] * inv; P[r * (T + 1) + c] = pp; dot += pp * dS[r * (T + 1) + c]; }
+    dot = warp_sum(dot);
+    for (int c = lane; c < T; c += 32) dS[r * (T + 1) + c] = P[r * (T + 1) + c] * (dS[r * (T + 1) + c] - dot) * scale;
+    if (lane == 0) {
+      stats[(long long)bh * T + r0 + r] = m + logf(s);
+      stats[n_rows + (long long)bh * T + r0 + r] = dot;
+    }
+  }
+  __syncthreads();
+  for (int tile = threadIdx.x; tile < TRr * 16; tile += blockDim.x) {
+    const int tt = tile >> 4, td = tile & 15;
+    int tv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int t = tt + TRr * i; tv[i] = (t < R ? t : R - 1) * (T + 1); }
+    float aq[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) aq[i][j] = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < T; ++c) {
+      float s1[4], kk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s1[i] = dS[tv[i] + c]; kk[i] = k[c * ld + td + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) aq[i][j] += s1[i] * kk[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = tt + TRr * i;
+      if (t >= R) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        store_split(ghi, glo, ((long long)b * T + r0 + t) * 3 * Wd + h * hd + td + 16 * j, aq[i][j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) attention_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, __half* __restrict__ ghi,
+                                                               __half* __restrict__ glo, const float* __restrict__ stats, int T, int Wd, int heads,
+                                                               int causal, int KB, int nkb) {
+  extern __shared__ float sm[];
+  constexpr int hd = 64, ld = hd + 1;
+  const int kb = blockIdx.x % nkb, bh = blockIdx.x / nkb;
+  const int b = bh / heads, h = bh % heads;
+  const int c0 = kb * KB, C = min(KB, T - c0);
+  float* q = sm;                  // [T][ld]
+  float* go = q + T * ld;         // [T][ld]
+  float* k = go + T * ld;         // [KB][ld]
+  float* v = k + KB * ld;         // [KB][ld]
+  float* PT = v + KB * ld;        // [KB][T+1]   P transposed: PT[c][r]
+  float* dST = PT + KB * (T + 1); // [KB][T+1]
+  float* lse = dST + KB * (T + 1);// [T]
+  float* dt = lse + T;            // [T]
+  const float scale = rsqrtf((float)hd);
+  const long long n_rows = (long long)(gridDim.x / nkb) * T;
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    q[t * ld + d] = qkv[((long long)b * T + t) * 3 * Wd + h * hd + d];
+    go[t * ld + d] = dO[((long long)b * T + t) * Wd + h * hd + d];
+  }
+  for (int i = threadIdx.x; i < C * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    const float* row = qkv + ((long long)b * T + c0 + t) * 3 * Wd + h * hd + d;
+    k[t * ld + d] = row[Wd];
+    v[t * ld + d] = row[2 * Wd];
+  }
+  for (int r = threadIdx.x; r < T; r += blockDim.x) {
+    lse[r] = stats[(long long)bh * T + r];
+    dt[r] = stats[n_rows + (long long)bh * T + r];
+  }
+  __syncthreads();
+  const int TRr = (C + 3) >> 2, TRc = (T + 3) >> 2;
+  for (int tile = threadIdx.x; tile < TRr * TRc; tile += blockDim.x) {
+    const int tr = tile / TRc, tc = tile - tr * TRc;
+    int co[4], ro[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tr + TRr * i, r = tc + TRc * i;
+      co[i] = (c < C ? c : C - 1) * ld;
+      ro[i] = (r < T ? r : T - 1) * ld;
+    }
+    float as[4][4], ap[4][4];     // [key i][query j]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { as[i][j] = 0.f; ap[i][j] = 0.f; }
+#pragma unroll 2
+    for (int d = 0; d < hd; ++d) {
+      float a[4], bb[4], g[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { bb[i] = k[co[i] + d]; w[i] = v[co[i] + d]; a[i] = q[ro[i] + d]; g[i] = go[ro[i] + d]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { as[i][j] += bb[i] * a[j]; ap[i][j] += w[i] * g[j]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tr + TRr * i;
+      if (c >= C) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = tc + TRc * j;
+        if (r < T) {
+          const float p = (causal && c0 + c > r) ? 0.f : expf(as[i][j] * scale - lse[r]);
+          PT[c * (T + 1) + r] = p;
+          dST[c * (T + 1) + r] = p * (ap[i][j] - dt[r]) * scale;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int tile = threadIdx.x; tile < TRr * 16; tile += blockDim.x) {
+    const int tt = tile >> 4, td = tile & 15;
+    int cv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int c = tt + TRr * i; cv[i] = (c < C ? c : C - 1) * (T + 1); }
+    float ak[4][4], av[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ak[i][j] = 0.f; av[i][j] = 0.f; }
+#pragma unroll 2
+    for (int r = 0; r < T; ++r) {
+      float s2[4], p2[4], qq[4], gg[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s2[i] = dST[cv[i] + r];
+        p2[i] = PT[cv[i] + r];
+        qq[i] = q[r * ld + td + 16 * i];
+        gg[i] = go[r * ld + td + 16 * i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ak[i][j] += s2[i] * qq[j]; av[i][j] += p2[i] * gg[j]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tt + TRr * i;
+      if (c >= C) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long o = ((long long)b * T + c0 + c) * 3 * Wd + h * hd + td + 16 * j;
+        store_split(ghi, glo, o + Wd, ak[i][j]);
+        store_split(ghi, glo, o + 2 * Wd, av[i][j]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // QuickGELU (x * sigmoid(1.702 x)) forward to fp16 operand planes, and backward dh = dg * gelu'(h).
 __global__ void __launch_bounds__(256) quickgelu_fwd_kernel(const float* __restrict__ h, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -724,6 +1076,8 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
   }
 }
 
+int g_attention_tiled = 0;   // 0: tiled attention only where the whole-sequence kernel does not fit; 1: always; >= 4: always, rows per CTA capped
+                             // at that value (smc_synth_config key 5; tests exercise several row blocks at 50 tokens this way)
 int g_resample_vfirst = 0;   // unprocess: vertical pass first for >= 2x down-sampling (smc_synth_config key 4)
 
 static int grid1d(long long items) {
@@ -831,11 +1185,34 @@ extern "C" int smc_layernorm_bwd(const float* dy, const float* x, int64_t in_row
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
+// Rows per CTA of the tiled attention kernels: the fewest blocks whose shared memory (whole[T][65] x 2 + per-row words) stays under 200 KB.
+// per_row = words that scale with the block (operand rows + score rows), extra = fixed words.  Returns 0 when even 4 rows do not fit.
+static int attention_block_rows(int t, int per_row, int extra, size_t* smem) {
+  const int cap = smc::g_attention_tiled >= 4 ? smc::g_attention_tiled : t;
+  for (int nb = 1; nb <= t; ++nb) {
+    int rows = (((t + nb - 1) / nb) + 3) & ~3;
+    if (rows > ((cap + 3) & ~3)) continue;
+    *smem = ((size_t)2 * t * 65 + (size_t)rows * per_row + extra) * sizeof(float);
+    if (*smem <= 200 * 1024) return rows;
+  }
+  return 0;
+}
 extern "C" int smc_attention_fwd(const float* qkv, void* ohi, void* olo, float* o32, int b, int t, int wd, int heads, int causal, void* stream) {
   if (!qkv || (!ohi && !o32) || b < 1 || t < 1 || heads < 1 || wd % heads) return SMC_EINVAL;
   const int hd = wd / heads;
   const size_t smem = (size_t)(3 * t * (hd + 1) + t * (t + 1)) * sizeof(float);
-  if (smem > 200 * 1024) return SMC_EUNSUPPORTED;
+  if (smem > 200 * 1024 || smc::g_attention_tiled) {       // long sequences (ViT-B/16: 197 tokens): query-row blocks
+    if (hd != 64) return SMC_EUNSUPPORTED;
+    size_t sm2 = 0;
+    const int qb = attention_block_rows(t, 65 + t + 1, 0, &sm2);
+    if (!qb) return SMC_EUNSUPPORTED;
+    const int nqb = (t + qb - 1) / qb;
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    if (e != cudaSuccess) return (int)e;
+    attention_fwd_rows_kernel<<<b * heads * nqb, 256, sm2, ST>>>(qkv, (__half*)ohi, (__half*)olo, o32, t, wd, heads, causal, qb, nqb);
+    SMC_LAUNCH_CHECK();
+    return SMC_OK;
+  }
   cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   if (hd == 64) {
@@ -865,6 +1242,26 @@ extern "C" int smc_attention_bwd(const float* qkv, const float* d_o, void* ghi, 
     return SMC_OK;
   }
   attention_bwd_kernel<<<b * heads, 256, smem, ST>>>(qkv, d_o, (__half*)ghi, (__half*)glo, t, wd, heads, causal);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+// Backward for sequences the whole-sequence kernel cannot hold (see attention_bwd_q_kernel): two launches, dQ per query-row block, then
+// dK/dV per key-row block.  stats: caller-allocated fp32 scratch of 2 * b * heads * t words (row log-sum-exp and rowsum(P * dP)).
+extern "C" int smc_attention_bwd_tiled(const float* qkv, const float* d_o, void* ghi, void* glo, float* stats, int b, int t, int wd, int heads,
+                                       int causal, void* stream) {
+  if (!qkv || !d_o || !ghi || !stats || b < 1 || t < 1 || heads < 1 || wd % heads) return SMC_EINVAL;
+  if (wd / heads != 64) return SMC_EUNSUPPORTED;
+  size_t smem = 0;
+  const int rb = attention_block_rows(t, 2 * 65 + 2 * (t + 1), 2 * t, &smem);
+  if (!rb) return SMC_EUNSUPPORTED;
+  const int nb = (t + rb - 1) / rb;
+  cudaError_t e = cudaFuncSetAttribute(attention_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(attention_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  attention_bwd_q_kernel<<<b * heads * nb, 256, smem, ST>>>(qkv, d_o, (__half*)ghi, (__half*)glo, stats, t, wd, heads, causal, rb, nb);
+  SMC_LAUNCH_CHECK();
+  attention_bwd_kv_kernel<<<b * heads * nb, 256, smem, ST>>>(qkv, d_o, (__half*)ghi, (__half*)glo, stats, t, wd, heads, causal, rb, nb);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

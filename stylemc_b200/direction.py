@@ -5,8 +5,9 @@ CLIP loss (clip_loss.py:24-34), the backward pass CLIP -> unprocess -> synthesis
 gradient of the L2 term (find_direction.py:190-191) and one SGD update (:285,339).  Across GPUs the seed batch is sharded by
 rows; the only exchange is an all-reduce of the ``[8, 512]`` gradient (16 KiB) and of the loss scalars.
 
-Only ``clip_type='small'`` (ViT-B/32) with ``clip_loss_type='default'`` is implemented; identity and landmark terms are outside
-the accelerated path.
+``clip_loss_type='default'`` with ``clip_type='small'`` (one ViT-B/32 tower, the benchmark configuration) or ``'double'`` (ViT-B/32 +
+0.5 * ViT-B/16, find_direction.py:117-119,160-164: pass both models); identity and landmark terms are outside the accelerated path
+(SURVEY.md section 2).
 """
 import math
 import os
@@ -18,6 +19,7 @@ from . import _lib, resample, synthesis, utils
 S_TRAINABLE_SPACE_CHANNELS = [2, 3, 5, 6, 8, 9, 11, 12]     # find_direction.py:41
 N_STYLE_CHANNELS = 26                                       # find_direction.py:38
 RESOLUTION_DICT = {256: 6, 512: 7, 1024: 8}                 # find_direction.py:263
+DOUBLE_CLIP_WEIGHTS = (1.0, 0.5)                            # find_direction.py:164: clip1 + 0.5 * clip2 (ViT-B/32, ViT-B/16)
 
 
 class CLIPLoss:
@@ -73,7 +75,8 @@ def cosine_lr(base_lr, it, total):
 class DirectionFinder:
     """State and step function of the S-space direction search for one prompt pair.
 
-    G: frozen generator (attribute structure of the unpickled network); clip_model: stylemc_b200.clip.CLIPModel;
+    G: frozen generator (attribute structure of the unpickled network); clip_model: stylemc_b200.clip.CLIPModel (clip_type='small'),
+    or the pair (ViT-B/32 model, ViT-B/16 model) for clip_type='double' (weights 1 and 0.5, find_direction.py:164);
     resolution: 256 / 512 / 1024 -> until_k per find_direction.py:263 (the network is truncated after that block).
     precision: synthesis engine mode; 'x3p' reproduces the fp32 reference's gradient to <= 1e-3, 'x1' is the fast fp16-operand
     mode (images <= 1e-2, loss <= 1e-3, gradient ~1e-2: the lrelu kinks amplify forward rounding, DESIGN.md "Numerics").
@@ -86,8 +89,11 @@ class DirectionFinder:
         self.engine = utils.engine_for(G, self.device, precision)
         self.until_k = RESOLUTION_DICT[resolution] if resolution in RESOLUTION_DICT else int(math.log2(resolution)) - 2
         self.until_k = min(self.until_k, len(self.engine.blocks) - 1)
-        self.clip = clip_model
-        self.loss_fn = CLIPLoss(clip_model, pos_tokens, neg_tokens)
+        models = list(clip_model) if isinstance(clip_model, (tuple, list)) else [clip_model]
+        if len(models) > len(DOUBLE_CLIP_WEIGHTS):
+            raise ValueError('clip_model: one model (clip_type small) or two (clip_type double)')
+        self.clips = [(m, CLIPLoss(m, pos_tokens, neg_tokens), w) for m, w in zip(models, DOUBLE_CLIP_WEIGHTS)]
+        self.clip, self.loss_fn = self.clips[0][0], self.clips[0][1]
         self.lr, self.clip_loss_coef, self.l2_reg_coef = learning_rate, clip_loss_coef, l2_reg_coef
         self.noise_mode, self.micro_batch = noise_mode, micro_batch
         self.rows = list(trainable_rows)
@@ -107,6 +113,13 @@ class DirectionFinder:
         d[:, self.rows] = self.delta
         return d
 
+    def _encode_original(self, s):
+        """CLIP embeddings of the un-edited images (find_direction.py:312: no gradient), one per tower."""
+        _, original, _ = self.engine.forward(s, self.until_k, self.noise_mode, save=False)
+        u_s = resample.unprocess_fwd(original)
+        del original
+        return [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
+
     def loss_and_grad(self, styles, global_count=None):
         """styles [n, 26, 512] (this rank's shard, device) -> (grad [8, 512] summed over the shard, clip-loss partial sum).
         ``global_count`` is the number of seeds in the whole step (all ranks); the CLIP loss is their mean (clip_loss.py:34)."""
@@ -125,25 +138,27 @@ class DirectionFinder:
                     self._side = torch.cuda.Stream(self.device)
                 self._side.wait_stream(cur)
                 with torch.cuda.stream(self._side):
-                    _, original, _ = eng.forward(s, self.until_k, self.noise_mode, save=False)            # :312
-                    e_s, _ = self.clip.encode_image_fwd(resample.unprocess_fwd(original), save=False)
-                    del original
+                    e_s = self._encode_original(s)
                 s.record_stream(self._side)
             _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True, grad_rows=self.rows)   # :309
             u_t = resample.unprocess_fwd(img)                                                      # :159-160
             if not self.overlap:
-                _, original, _ = eng.forward(s, self.until_k, self.noise_mode, save=False)                # :312
-                e_s, _ = self.clip.encode_image_fwd(resample.unprocess_fwd(original), save=False)
-                del original
-            e_t, csaved = self.clip.encode_image_fwd(u_t, save=True)
-            if self.overlap:
-                cur.wait_stream(self._side)
-                e_s.record_stream(cur)
-            part, d_t, gscale = self.loss_fn.loss_and_grad(e_s, e_t, self.clip_loss_coef, 1.0 / count)
-            g224 = self.clip.encode_image_bwd(csaved, d_t)
+                e_s = self._encode_original(s)
+            g224 = gscale = None
+            for i, (model, loss_fn, weight) in enumerate(self.clips):
+                e_t, csaved = model.encode_image_fwd(u_t, save=True)
+                if self.overlap and i == 0:
+                    cur.wait_stream(self._side)
+                    for e in e_s:
+                        e.record_stream(cur)
+                part, d_t, gs = loss_fn.loss_and_grad(e_s[i], e_t, self.clip_loss_coef * weight, 1.0 / count)
+                g = model.encode_image_bwd(csaved, d_t)
+                del csaved
+                # every tower's pixel gradient carries its own power-of-two loss scale: bring the later ones to the first one's
+                g224, gscale = (g, gs) if g224 is None else (g224 + g * (gscale / gs), gscale)
+                part_sum += part
             g_img = resample.unprocess_bwd(g224, img, unscale=gscale)
             grad += eng.backward(saved, g_img, self.rows, self.noise_mode)
-            part_sum += part
         return grad, part_sum
 
     def step(self, styles, lr=None, global_count=None):
@@ -155,7 +170,7 @@ class DirectionFinder:
             grad, part = allreduce_step(grad, part, self.group)
         numel = self.delta.numel()
         l2 = self.l2_reg_coef * self.delta.square().mean()                            # find_direction.py:190-191 (batch independent)
-        clip_loss = self.clip_loss_coef + part                                        # coef * (count - sum cos) / count
+        clip_loss = self.clip_loss_coef * sum(w for _, _, w in self.clips) + part     # sum over towers of w * coef * (count - sum cos) / count
         l2_scale = 2.0 * self.l2_reg_coef / numel
         grad_total = grad + l2_scale * self.delta[0]
         with torch.cuda.device(self.device):

@@ -1,0 +1,70 @@
+// Minimal CPU stand-in for the CUDA execution model, enough to run a shared-memory / warp-shuffle kernel of csrc/ unchanged on host
+// threads: one std::thread per CUDA thread of a block, blocks one after another.  TEST INFRASTRUCTURE ONLY (tests/test_attention_emu.py):
+// it checks index arithmetic and data flow of kernels on a machine without a GPU; it says nothing about launch limits or speed.
+#pragma once
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct emu_block {
+  explicit emu_block(int threads) : bar(threads), shfl(threads) {
+    for (int w = 0; w < (threads + 31) / 32; ++w) warp_bar.emplace_back(new std::barrier<>(std::min(32, threads - 32 * w)));
+  }
+  std::barrier<> bar;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+  std::vector<float> shfl;
+};
+static thread_local emu_dim3 threadIdx, blockIdx;
+static emu_dim3 blockDim, gridDim;
+static thread_local float* emu_smem;
+static thread_local emu_block* emu_ctx;
+
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+typedef _Float16 __half;
+static inline __half __float2half_rn(float v) { return (__half)v; }
+static inline float __half2float(__half h) { return (float)h; }
+static inline float rsqrtf(float v) { return 1.0f / std::sqrt(v); }
+using std::min;
+using std::max;
+
+static inline void __syncthreads() { emu_ctx->bar.arrive_and_wait(); }
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  const int t = (int)threadIdx.x;
+  emu_ctx->shfl[t] = v;
+  emu_ctx->warp_bar[t >> 5]->arrive_and_wait();
+  const float r = emu_ctx->shfl[t ^ lane_mask];
+  emu_ctx->warp_bar[t >> 5]->arrive_and_wait();
+  return r;
+}
+
+// kernel<<<grid, block, smem>>>(args...)  ->  emu_launch(grid, block, smem, [&] { kernel(args...); })
+static void emu_launch(int grid, int block, size_t smem_bytes, const std::function<void()>& body) {
+  gridDim.x = grid;
+  blockDim.x = block;
+  std::vector<float> smem((smem_bytes + 3) / 4);
+  for (int b = 0; b < grid; ++b) {
+    std::fill(smem.begin(), smem.end(), NAN);      // reads of never-written shared memory poison the result
+    emu_block ctx(block);
+    std::vector<std::thread> th;
+    for (int t = 0; t < block; ++t)
+      th.emplace_back([&, t] {
+        threadIdx.x = t;
+        blockIdx.x = b;
+        emu_smem = smem.data();
+        emu_ctx = &ctx;
+        body();
+      });
+    for (auto& x : th) x.join();
+  }
+}

@@ -174,3 +174,63 @@ def test_bench_flop_accounting_matches_survey_8d():
     assert abs(bench.VIT_FLOPS_FWD / 1e9 - 8.82) < 0.1
     p = bench.peaks()
     assert p['hbm'] > 1000 and p['tflops'] > 100
+
+
+@pytest.mark.parametrize('towers', [1, 2])
+def test_direction_finder_combines_towers_and_loss_scales(towers, monkeypatch):
+    """Host logic of DirectionFinder.loss_and_grad with stand-in engines on the CPU (linear synthesis, linear towers): for
+    clip_type='double' the loss is loss1 + 0.5 * loss2 (find_direction.py:164) and the pixel gradients of the two towers, each
+    carrying its own power-of-two loss scale, are reconciled before the synthesis backward."""
+    from stylemc_b200 import direction
+    gen = torch.Generator().manual_seed(9)
+    n, rows, coef = 3, direction.S_TRAINABLE_SPACE_CHANNELS, 0.7
+    A = torch.randn(26 * 512, 3 * 8 * 8, generator=gen, dtype=torch.float64) * 0.02
+    text = torch.nn.functional.normalize(torch.randn(1, 16, generator=gen, dtype=torch.float64), dim=1)
+
+    class Engine:
+        def forward(self, s, until_k, noise_mode, save, grad_rows=None):
+            return None, (s.double().reshape(len(s), -1) @ A).reshape(len(s), 3, 8, 8), s
+
+        def backward(self, saved, g_img, rows_, noise_mode):
+            return (g_img.reshape(len(g_img), -1) @ A.t()).reshape(len(g_img), 26, 512)[:, rows_].sum(0)
+
+    class Tower:
+        def __init__(self, scale):
+            self.w, self.scale = torch.randn(3 * 8 * 8, 16, generator=gen, dtype=torch.float64), scale
+
+        def encode_image_fwd(self, u, save):
+            return u.flatten(1) @ self.w, (u.shape if save else None)
+
+        def encode_image_bwd(self, saved, d):
+            return (d @ self.w.t()).reshape(saved)
+
+    class Loss:
+        def __init__(self, scale):
+            self.scale = scale
+
+        def loss_and_grad(self, e_s, e_t, c, inv_count):
+            e_t = e_t.detach().requires_grad_(True)
+            part = -c * inv_count * torch.nn.functional.cosine_similarity(e_t - e_s, text).sum()
+            d, = torch.autograd.grad(part, e_t)
+            return part.detach().reshape(1), d * self.scale, torch.tensor([self.scale], dtype=torch.float64)
+
+    monkeypatch.setattr(direction.resample, 'unprocess_fwd', lambda img: 2.0 * img)
+    monkeypatch.setattr(direction.resample, 'unprocess_bwd', lambda g, img, unscale=None: 2.0 * g / unscale)
+    f = object.__new__(direction.DirectionFinder)
+    f.device, f.engine, f.until_k, f.noise_mode, f.micro_batch, f.rows = torch.device('cpu'), Engine(), 3, 'const', 2, rows
+    f.clip_loss_coef, f.overlap, f._side = coef, False, None
+    f.clips = [(Tower(s), Loss(s), w) for s, w in zip((64.0, 4096.0), direction.DOUBLE_CLIP_WEIGHTS)][:towers]
+    f.delta = 0.1 * torch.randn(1, 8, 512, generator=gen)
+    styles = torch.randn(n, 26, 512, generator=gen)
+    grad, part = f.loss_and_grad(styles, global_count=n)
+
+    delta = f.delta.double().clone().requires_grad_(True)
+    d = torch.zeros(1, 26, 512, dtype=torch.float64).index_put((torch.tensor([0]).view(1, 1), torch.tensor(rows).view(1, -1)), delta)
+    img = lambda s: 2.0 * (s.reshape(n, -1) @ A)
+    want = 0
+    for tower, _, w in f.clips:
+        e = img(styles.double() + d) @ tower.w - img(styles.double()) @ tower.w
+        want = want - w * coef / n * torch.nn.functional.cosine_similarity(e, text).sum()
+    g_want, = torch.autograd.grad(want, delta)
+    assert abs(part.item() - want.item()) <= 1e-5 * abs(want.item())      # part_sum is a float32 accumulator
+    assert ((grad.double() - g_want[0]).norm() / g_want.norm()).item() <= 1e-5
