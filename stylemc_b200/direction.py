@@ -113,6 +113,13 @@ class DirectionFinder:
         d[:, self.rows] = self.delta
         return d
 
+    def load_direction(self, styles_direction):
+        """Resume from a saved direction [1, 26, 512] (find_direction.py:266-270: the trainable rows are selected out of it)."""
+        d = torch.as_tensor(styles_direction, dtype=torch.float32)
+        if tuple(d.shape) != (1, N_STYLE_CHANNELS, synthesis.STYLE_WIDTH):
+            raise RuntimeError(f'direction must be [1, {N_STYLE_CHANNELS}, {synthesis.STYLE_WIDTH}], got {tuple(d.shape)}')
+        self.delta.copy_(d[:, self.rows].to(self.device))
+
     def _encode_original(self, s):
         """CLIP embeddings of the un-edited images (find_direction.py:312: no gradient), one per tower."""
         _, original, _ = self.engine.forward(s, self.until_k, self.noise_mode, save=False)

@@ -1,0 +1,91 @@
+"""The reference's on-disk formats either side of the hot path and its optimisation loop.
+
+All files are ``np.savez`` archives with one key:
+  ``w``  [M, num_ws, 512] fp32   W+ latents             written by generate_w.py:50-51, read by w_s_converter.py:75
+  ``s``  [M, 26, 512] fp32       zero-padded S tensor   written by w_s_converter.py:81-82, read by find_direction.py:260 and
+                                                        generate_fromS.py:114
+  ``s``  [1, 26, 512] fp32       S-space direction      written by find_direction.py:334 (``direction_last.npz`` checkpoints) and :349-351
+                                                        (``direction_<prompt>.npz``), read by generate_fromS.py:125 and ``--resume`` (:266-268)
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+N_STYLE_ROWS, STYLE_WIDTH = 26, 512
+
+
+def _check(a, key, path, lead=None):
+    if a.ndim != 3 or a.shape[2] != STYLE_WIDTH or (key == 's' and a.shape[1] != N_STYLE_ROWS) or (lead is not None and a.shape[0] != lead):
+        raise RuntimeError(f'{path}: unexpected shape {tuple(a.shape)} for key {key!r}')
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+
+def load_w(path):
+    return _check(np.load(path)['w'], 'w', path)
+
+
+def save_w(path, ws):
+    np.savez(path, w=torch.as_tensor(ws).detach().cpu().float().numpy())
+
+
+def load_styles(path, n=None):
+    """[M, 26, 512] fp32 host tensor (generate_fromS.py:114 takes the first ``n`` rows)."""
+    s = _check(np.load(path)['s'], 's', path)
+    return s if n is None else s[:n]
+
+
+def save_styles(path, styles):
+    np.savez(path, s=torch.as_tensor(styles).detach().cpu().float().numpy())
+
+
+def direction_path(outdir, text_prompt):
+    """find_direction.py:350 / generate_fromS.py:125."""
+    return os.path.join(outdir, f'direction_{text_prompt.replace(" ", "_")}.npz')
+
+
+def load_direction(path):
+    return _check(np.load(path)['s'], 's', path, lead=1)
+
+
+def save_direction(path, styles_direction):
+    d = torch.as_tensor(styles_direction).detach().cpu().float()
+    if tuple(d.shape) != (1, N_STYLE_ROWS, STYLE_WIDTH):
+        raise RuntimeError(f'direction must be [1, {N_STYLE_ROWS}, {STYLE_WIDTH}], got {tuple(d.shape)}')
+    np.savez(path, s=d.numpy())
+
+
+def find_direction(finder, styles_array, batch_size, n_epochs, outdir=None, text_prompt=None, resume=None, seed=0, checkpoint_every=1000,
+                   log=None):
+    """The loop of find_direction.py:285-351 around ``DirectionFinder.step``: ``ceil(M / batch) * n_epochs`` iterations, a random
+    batch per iteration (:303-304), cosine learning rate (:298-301), ``direction_last.npz`` every ``checkpoint_every`` iterations
+    (:333-334), ``direction_<prompt>.npz`` at the end (:349-351); ``resume`` loads a saved direction (:266-270).
+
+    The batch index is drawn from ``np.random.RandomState(seed)``, not the global generator the reference uses: in a data-parallel run
+    every rank must draw the same index.  With several ranks each one takes its rows of the batch (``direction.shard_rows``) and only
+    rank 0 writes files.  Returns the final direction [1, 26, 512] (host)."""
+    from . import direction as smc_dir
+    n_items = styles_array.shape[0]
+    num_batches = math.ceil(n_items / batch_size)
+    total = num_batches * n_epochs
+    rng = np.random.RandomState(seed)
+    rank = torch.distributed.get_rank(finder.group) if finder.world > 1 else 0
+    if resume is not None:
+        finder.load_direction(load_direction(resume))
+    if outdir is not None and rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+    for it in range(1, total + 1):
+        lr = smc_dir.cosine_lr(finder.lr, it, total)
+        i = rng.randint(0, num_batches)
+        batch = styles_array[i * batch_size:(i + 1) * batch_size]
+        lo, hi = smc_dir.shard_rows(batch.shape[0], rank, finder.world)
+        out = finder.step(batch[lo:hi], lr=lr, global_count=batch.shape[0])
+        if outdir is not None and rank == 0 and it % checkpoint_every == checkpoint_every - 1:
+            save_direction(os.path.join(outdir, 'direction_last.npz'), finder.direction())
+        if log is not None and it % 10 == 0:
+            log(it, lr, out)
+    final = finder.direction().detach().cpu()
+    if outdir is not None and rank == 0:
+        save_direction(direction_path(outdir, text_prompt) if text_prompt else os.path.join(outdir, 'direction_last.npz'), final)
+    return final

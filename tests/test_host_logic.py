@@ -1,6 +1,7 @@
 """CPU: host-side logic of the product (no kernel launches): resampling tap tables, implicit-GEMM tap tables (checked by
 emulating the smc_igemm contract with plain torch), S-space bookkeeping, network parameter naming, schedules."""
 import math
+import os
 
 import pytest
 import torch
@@ -234,3 +235,55 @@ def test_direction_finder_combines_towers_and_loss_scales(towers, monkeypatch):
     g_want, = torch.autograd.grad(want, delta)
     assert abs(part.item() - want.item()) <= 1e-5 * abs(want.item())      # part_sum is a float32 accumulator
     assert ((grad.double() - g_want[0]).norm() / g_want.norm()).item() <= 1e-5
+
+
+def test_npz_formats_and_find_direction_loop(tmp_path):
+    """the w / s / direction npz layouts (generate_w.py:51, w_s_converter.py:82, find_direction.py:260,334,351,
+    generate_fromS.py:114,125) and the optimisation loop's bookkeeping (iteration count, cosine LR, batch slices, checkpoints,
+    final file, resume) with a stand-in step function."""
+    import numpy as np
+    from stylemc_b200 import direction, io
+    gen = torch.Generator().manual_seed(1)
+    S = torch.randn(11, 26, 512, generator=gen)
+    io.save_styles(tmp_path / 's.npz', S)
+    assert list(np.load(tmp_path / 's.npz').keys()) == ['s'] and np.load(tmp_path / 's.npz')['s'].dtype == np.float32
+    assert torch.equal(io.load_styles(tmp_path / 's.npz'), S) and io.load_styles(tmp_path / 's.npz', n=4).shape[0] == 4
+    ws = torch.randn(3, 18, 512, generator=gen)
+    io.save_w(tmp_path / 'w.npz', ws)
+    assert torch.equal(io.load_w(tmp_path / 'w.npz'), ws)
+    with pytest.raises(RuntimeError):
+        io.save_direction(tmp_path / 'bad.npz', torch.zeros(2, 26, 512))
+    np.savez(tmp_path / 'bad_s.npz', s=np.zeros((3, 20, 512), np.float32))
+    with pytest.raises(RuntimeError):
+        io.load_styles(tmp_path / 'bad_s.npz')
+    assert io.direction_path('out', 'a happy face') == os.path.join('out', 'direction_a_happy_face.npz')
+
+    f = object.__new__(direction.DirectionFinder)
+    f.device, f.rows, f.lr, f.world, f.group = torch.device('cpu'), direction.S_TRAINABLE_SPACE_CHANNELS, 1.5, 1, None
+    f.delta = torch.zeros(1, 8, 512)
+    calls = []
+
+    def step(styles, lr=None, global_count=None):
+        calls.append((styles.shape[0], lr, global_count, styles[0, 0, 0].item()))
+        f.delta += 1.0
+        return dict(loss=torch.tensor(0.0))
+    f.step = step
+    out = tmp_path / 'run'
+    final = io.find_direction(f, S, batch_size=4, n_epochs=5, outdir=str(out), text_prompt='a happy face', seed=3, checkpoint_every=6)
+    total = math.ceil(11 / 4) * 5                                                     # find_direction.py:286-287
+    assert len(calls) == total
+    rng = np.random.RandomState(3)
+    for it, (n, lr, count, first) in enumerate(calls, 1):
+        i = rng.randint(0, 3)
+        assert n == count == min(4, 11 - 4 * i) and first == S[4 * i, 0, 0].item()   # :303-304, ragged last batch
+        assert abs(lr - o_dir.cosine_lr(1.5, it, total)) < 1e-12                      # :298-299
+    want = torch.zeros(1, 26, 512)
+    want[:, f.rows] = float(total)
+    assert torch.equal(final, want) and torch.equal(io.load_direction(io.direction_path(str(out), 'a happy face')), want)
+    last = io.load_direction(out / 'direction_last.npz')                              # written at iterations 5 and 11 (it % 6 == 5, as :333)
+    assert last[0, f.rows[0], 0].item() == 11.0 and last[0, 0].abs().max().item() == 0.0
+    # resume (:266-270): the trainable rows of the saved direction become delta
+    f.delta.zero_()
+    calls.clear()
+    io.find_direction(f, S, batch_size=11, n_epochs=1, resume=str(out / 'direction_last.npz'))
+    assert len(calls) == 1 and f.delta[0, 0, 0].item() == 12.0
