@@ -89,3 +89,18 @@ def find_direction(finder, styles_array, batch_size, n_epochs, outdir=None, text
     if outdir is not None and rank == 0:
         save_direction(direction_path(outdir, text_prompt) if text_prompt else os.path.join(outdir, 'direction_last.npz'), final)
     return final
+
+
+def save_canvases(canvases, outdir, text_prompt, first_index=0):
+    """generate_fromS.py:205-206: one ``<prompt>_<i:03d>.jpeg`` (quality 95) per row of the uint8 ``original | edited`` canvas
+    [M, R, 2 R, 3] that ``generate.generate_fromS`` returns.  Returns the file paths."""
+    from PIL import Image
+    arr = torch.as_tensor(canvases).detach().cpu().numpy()
+    if arr.dtype != np.uint8 or arr.ndim != 4 or arr.shape[3] != 3:
+        raise RuntimeError(f'canvases must be uint8 [M, H, W, 3], got {arr.dtype} {tuple(arr.shape)}')
+    os.makedirs(outdir, exist_ok=True)
+    paths = []
+    for i, a in enumerate(arr, first_index):
+        paths.append(os.path.join(outdir, f'{text_prompt.replace(" ", "_")}_{i:03d}.jpeg'))
+        Image.fromarray(a, 'RGB').save(paths[-1], quality=95)
+    return paths

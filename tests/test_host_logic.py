@@ -287,3 +287,14 @@ def test_npz_formats_and_find_direction_loop(tmp_path):
     calls.clear()
     io.find_direction(f, S, batch_size=11, n_epochs=1, resume=str(out / 'direction_last.npz'))
     assert len(calls) == 1 and f.delta[0, 0, 0].item() == 12.0
+
+
+def test_save_canvases_writes_the_reference_file_names(tmp_path):
+    from PIL import Image
+    from stylemc_b200 import io
+    canv = torch.randint(0, 256, (2, 16, 32, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(2))
+    paths = io.save_canvases(canv, str(tmp_path), 'a happy face', first_index=7)
+    assert [os.path.basename(p) for p in paths] == ['a_happy_face_007.jpeg', 'a_happy_face_008.jpeg']     # generate_fromS.py:205
+    assert Image.open(paths[0]).size == (32, 16)
+    with pytest.raises(RuntimeError):
+        io.save_canvases(canv.float(), str(tmp_path), 'x')
