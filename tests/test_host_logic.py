@@ -177,12 +177,23 @@ def test_bench_flop_accounting_matches_survey_8d():
     assert p['hbm'] > 1000 and p['tflops'] > 100
 
 
-@pytest.mark.parametrize('towers', [1, 2])
-def test_direction_finder_combines_towers_and_loss_scales(towers, monkeypatch):
+@pytest.mark.parametrize('towers,overlap', [(1, False), (2, False), (1, True), (2, True)])
+def test_direction_finder_combines_towers_and_loss_scales(towers, overlap, monkeypatch):
     """Host logic of DirectionFinder.loss_and_grad with stand-in engines on the CPU (linear synthesis, linear towers): for
     clip_type='double' the loss is loss1 + 0.5 * loss2 (find_direction.py:164) and the pixel gradients of the two towers, each
-    carrying its own power-of-two loss scale, are reconciled before the synthesis backward."""
+    carrying its own power-of-two loss scale, are reconciled before the synthesis backward.  overlap=True walks the two-stream
+    branch (the benchmark's default) with the CUDA stream calls replaced by no-ops."""
+    import contextlib
     from stylemc_b200 import direction
+
+    class FakeStream:
+        def wait_stream(self, other):
+            pass
+    if overlap:
+        monkeypatch.setattr(torch.cuda, 'current_stream', lambda device=None: FakeStream())
+        monkeypatch.setattr(torch.cuda, 'Stream', lambda device=None: FakeStream())
+        monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())
+        monkeypatch.setattr(torch.Tensor, 'record_stream', lambda self, s: None)
     gen = torch.Generator().manual_seed(9)
     n, rows, coef = 3, direction.S_TRAINABLE_SPACE_CHANNELS, 0.7
     A = torch.randn(26 * 512, 3 * 8 * 8, generator=gen, dtype=torch.float64) * 0.02
@@ -219,7 +230,7 @@ def test_direction_finder_combines_towers_and_loss_scales(towers, monkeypatch):
     monkeypatch.setattr(direction.resample, 'unprocess_bwd', lambda g, img, unscale=None: 2.0 * g / unscale)
     f = object.__new__(direction.DirectionFinder)
     f.device, f.engine, f.until_k, f.noise_mode, f.micro_batch, f.rows = torch.device('cpu'), Engine(), 3, 'const', 2, rows
-    f.clip_loss_coef, f.overlap, f._side = coef, False, None
+    f.clip_loss_coef, f.overlap, f._side = coef, overlap, None
     f.clips = [(Tower(s), Loss(s), w) for s, w in zip((64.0, 4096.0), direction.DOUBLE_CLIP_WEIGHTS)][:towers]
     f.delta = 0.1 * torch.randn(1, 8, 512, generator=gen)
     styles = torch.randn(n, 26, 512, generator=gen)
