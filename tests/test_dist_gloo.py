@@ -77,3 +77,48 @@ def test_two_rank_allreduce_equals_full_batch(tmp_path):
     assert got['span'] == (0, 3)
     assert ((got['grad'] - grad).norm() / grad.norm()).item() <= 1e-5
     assert abs(got['part'].item() - part.item()) <= 1e-6
+
+
+def loop_worker(rank, world, port, outdir):
+    """io.find_direction on two ranks with a stand-in step: every rank must draw the same batch and take disjoint rows of it."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.distributed.init_process_group('gloo', rank=rank, world_size=world)
+    from stylemc_b200 import direction, io
+    group = torch.distributed.group.WORLD
+    S = torch.arange(11, dtype=torch.float32).view(11, 1, 1).expand(11, 26, 512).contiguous()      # row id in every element
+    f = object.__new__(direction.DirectionFinder)
+    f.device, f.rows, f.lr, f.world, f.group = torch.device('cpu'), direction.S_TRAINABLE_SPACE_CHANNELS, 1.0, world, group
+    f.delta = torch.zeros(1, 8, 512)
+    log = []
+
+    def step(styles, lr=None, global_count=None):
+        ids = styles[:, 0, 0].tolist()
+        rows = torch.zeros(11)
+        rows[[int(i) for i in ids]] = 1
+        torch.distributed.all_reduce(rows, group=group)                     # union of the shards of this iteration
+        assert rows.max().item() == 1, 'two ranks processed the same seed'
+        assert rows.sum().item() == global_count, 'the shards do not cover the batch every rank was told about'
+        log.append(rows.nonzero().flatten().tolist())
+        f.delta += rows.sum()
+        return dict(loss=torch.tensor(0.0))
+    f.step = step
+    final = io.find_direction(f, S, batch_size=4, n_epochs=2, outdir=outdir, text_prompt='p', seed=5)
+    if rank == 0:
+        torch.save(dict(log=log, final=final), os.path.join(outdir, 'log.pt'))
+    else:
+        assert not os.path.exists(os.path.join(outdir, 'rank1_wrote_something'))
+    torch.distributed.destroy_process_group()
+
+
+def test_two_rank_loop_draws_one_batch_and_shards_it(tmp_path):
+    import numpy as np
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(loop_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(tmp_path / 'log.pt')
+    rng = np.random.RandomState(5)
+    want = [list(range(4 * i, min(4 * i + 4, 11))) for i in (rng.randint(0, 3) for _ in range(6))]
+    assert got['log'] == want                                                 # contiguous batches (find_direction.py:303-304), incl. the ragged one
+    assert sorted(os.listdir(tmp_path)) == ['direction_p.npz', 'log.pt']      # only rank 0 writes
+    assert got['final'][0, 2, 0].item() == sum(len(w) for w in want)

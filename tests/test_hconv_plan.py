@@ -114,7 +114,7 @@ def test_every_synthesis_gemm_of_the_1024_network_has_a_plan(n, x3):
             check(o, 9, x3, halo=1)
 
 
-@pytest.mark.parametrize('rows', [64 * 50, 2 * 64 * 50, 64 * 49])
+@pytest.mark.parametrize('rows', [64 * 50, 2 * 64 * 50, 64 * 49, 64 * 197, 64 * 196, 3 * 197])      # ViT-B/32 and ViT-B/16 token / patch rows
 def test_clip_linears_have_a_plan(rows):
     for k, n_out in ((768, 2304), (768, 768), (768, 3072), (3072, 768)):
         rc, o = plan(make_desc(1, 1, rows, k, n_out, gemm.TAPS_1X1, True, 512, rows_b=n_out))
