@@ -83,3 +83,41 @@ def generate_image(G, until_k, styles, temp_shapes, noise_mode, device, use_blen
                 raise RuntimeError(f'temp_shapes[{k}] = {tuple(temp_shapes[k])} does not match the network {want}')
     xs, img, _ = eng.forward(styles.to(device), until_k=until_k, noise_mode=noise_mode, want_xs=True)
     return xs, img
+
+
+def style_layer_names(G):
+    """Layer name of every used row of the S tensor, in row order (utils.py:133-155 walks the blocks the same way):
+    ``['b4.conv1', 'b4.torgb', 'b8.conv0', 'b8.conv1', 'b8.torgb', ...]`` (26 names for the 1024-px network, 20 for 256 px)."""
+    names = []
+    for res in G.synthesis.block_resolutions:
+        block = getattr(G.synthesis, f'b{res}')
+        names += [f'b{res}.{n}' for n in (('conv1', 'torgb') if block.in_channels == 0 else ('conv0', 'conv1', 'torgb'))]
+    return names
+
+
+def styles_dict(G, styles, temp_shapes):
+    """Per-layer view of the S tensor: ``{'b4.conv1': styles[:, 0, :512], ...}`` (views, no copies).  The reference's container stays the
+    zero-padded ``[N, 26, 512]`` tensor plus ``temp_shapes`` (utils.py:123-158); this is the "styles dict" reading of the same data."""
+    widths = [c for shape, res in zip(temp_shapes, G.synthesis.block_resolutions)
+              for c in (shape[1:] if getattr(G.synthesis, f'b{res}').in_channels == 0 else shape)]
+    names = style_layer_names(G)
+    if len(widths) != len(names) or len(names) > styles.shape[1]:
+        raise RuntimeError('temp_shapes does not match the network')
+    return {name: styles[:, row, :c] for row, (name, c) in enumerate(zip(names, widths))}
+
+
+def styles_from_dict(G, per_layer, temp_shapes=None):
+    """Inverse of ``styles_dict``: the zero-padded ``[N, 26, 512]`` tensor from per-layer style vectors."""
+    names = style_layer_names(G)
+    if set(per_layer) != set(names):
+        raise RuntimeError(f'expected styles for {names}, got {sorted(per_layer)}')
+    first = per_layer[names[0]]
+    styles = torch.zeros(first.shape[0], synthesis.N_STYLE_ROWS, synthesis.STYLE_WIDTH, dtype=torch.float32, device=first.device)
+    for row, name in enumerate(names):
+        s = per_layer[name]
+        styles[:, row, :s.shape[1]] = s
+    if temp_shapes is not None:
+        for name, view in styles_dict(G, styles, temp_shapes).items():
+            if view.shape[1] != per_layer[name].shape[1]:
+                raise RuntimeError(f'{name}: {per_layer[name].shape[1]} style channels, the network has {view.shape[1]}')
+    return styles

@@ -309,3 +309,19 @@ def test_save_canvases_writes_the_reference_file_names(tmp_path):
     assert Image.open(paths[0]).size == (32, 16)
     with pytest.raises(RuntimeError):
         io.save_canvases(canv.float(), str(tmp_path), 'x')
+
+
+def test_styles_dict_view_round_trip():
+    """BASELINE.json's "per-layer styles dict": a named view of the reference's [N, 26, 512] S tensor (SURVEY.md 8a naming note)."""
+    from stylemc_b200 import utils
+    G = o_syn.make_generator(32, seed=1, channel_base=1024, channel_max=64)
+    ws = torch.randn(3, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(2))
+    S, shapes = o_syn.get_styles(G, ws, o_syn.split_ws(G, ws))
+    d = utils.styles_dict(G, S, shapes)
+    assert list(d) == ['b4.conv1', 'b4.torgb', 'b8.conv0', 'b8.conv1', 'b8.torgb', 'b16.conv0', 'b16.conv1', 'b16.torgb',
+                       'b32.conv0', 'b32.conv1', 'b32.torgb']
+    assert d['b8.conv0'].shape == (3, shapes[1][0]) and d['b8.conv0'].data_ptr() == S[:, 2].data_ptr()       # a view of row 2
+    assert d['b4.torgb'].shape[1] == shapes[0][2]
+    assert torch.equal(utils.styles_from_dict(G, d, shapes), S)
+    with pytest.raises(RuntimeError):
+        utils.styles_from_dict(G, {k: v for k, v in d.items() if k != 'b8.torgb'})
