@@ -2,7 +2,9 @@
 attention_bwd_q_kernel, attention_bwd_kv_kernel) executed UNCHANGED on host threads by a small CUDA execution-model shim
 (tests/emu/cuda_emu.h) and compared with a float64 softmax attention and its gradient.  The kernel text is cut out of vit.cu at
 test time, so this checks the index arithmetic and data flow of the code that ships, without a GPU; the whole-sequence kernels
-that the GPU tests already verify run through the same shim as a check of the shim itself."""
+that the GPU tests already verify run through the same shim as a check of the shim itself.  The same binary is also built with
+AddressSanitizer + UBSan (out-of-bounds global / shared-memory accesses: memcheck's job on a device) and with ThreadSanitizer (a missing
+``__syncthreads`` is a data race between host threads: racecheck's job)."""
 import os
 import re
 import shutil
@@ -35,15 +37,28 @@ def extract(vit_cu, common_cuh):
     return '\n'.join(parts) + '\n'
 
 
+SANITIZERS = {'plain': ['-O2'],
+              # heap bounds of every global AND shared-memory access (the shim's shared memory is a heap block of exactly the launcher's size)
+              'address': ['-O1', '-g', '-fsanitize=address,undefined', '-fno-sanitize-recover=undefined'],
+              # the shim's barriers are the only synchronisation, so a missing __syncthreads shows up as a data race (checked by removing one)
+              'thread': ['-O1', '-g', '-fsanitize=thread']}
+
+
 @pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
-def test_tiled_attention_kernels_on_the_cpu_shim(tmp_path):
+@pytest.mark.parametrize('sanitizer', list(SANITIZERS))
+def test_tiled_attention_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     csrc = os.path.join(ROOT, 'stylemc_b200', 'csrc')
     inc = extract(open(os.path.join(csrc, 'vit.cu')).read(), open(os.path.join(csrc, 'common.cuh')).read())
     (tmp_path / 'kernels_extracted.inc').write_text(inc)
     exe = str(tmp_path / 'attention_emu')
-    subprocess.check_call(['g++', '-std=c++20', '-O2', '-pthread', '-Wno-unknown-pragmas', '-I', str(tmp_path), '-I', EMU,
-                           os.path.join(EMU, 'attention_main.cpp'), '-o', exe])
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
-    print(r.stdout, r.stderr)
-    assert r.returncode == 0, r.stdout + r.stderr
+    cc = subprocess.run(['g++', '-std=c++20', '-pthread', '-Wno-unknown-pragmas'] + SANITIZERS[sanitizer] +
+                        ['-I', str(tmp_path), '-I', EMU, os.path.join(EMU, 'attention_main.cpp'), '-o', exe], capture_output=True, text=True)
+    if cc.returncode != 0 and sanitizer != 'plain':
+        pytest.skip(f'-fsanitize={sanitizer} runtime not available: {cc.stderr[-200:]}')
+    assert cc.returncode == 0, cc.stderr
+    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=0 exitcode=66', ASAN_OPTIONS='detect_leaks=0')
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    print(r.stdout, r.stderr[-3000:])
+    assert r.returncode == 0, r.stdout + r.stderr[-3000:]
     assert r.stdout.count('ok  ') == 5 and 'FAIL' not in r.stdout
+    assert 'ThreadSanitizer' not in r.stderr and 'AddressSanitizer' not in r.stderr and 'runtime error' not in r.stderr
