@@ -325,3 +325,24 @@ def test_styles_dict_view_round_trip():
     assert torch.equal(utils.styles_from_dict(G, d, shapes), S)
     with pytest.raises(RuntimeError):
         utils.styles_from_dict(G, {k: v for k, v in d.items() if k != 'b8.torgb'})
+
+
+def test_plugin_boundary_is_registered_as_torch_library_ops():
+    """torch.ops.stylemc_b200.bias_act / .upfirdn2d carry the argument lists of the reference's pybind plugin functions
+    (bias_act.cpp:32, upfirdn2d.cpp:16), have fake (meta) implementations for tracing and no CPU kernel."""
+    import stylemc_b200.ops  # noqa: F401
+    s = str(torch.ops.stylemc_b200.bias_act.default._schema)
+    assert [a.split()[-1] for a in s[s.index('(') + 1:s.index(')')].split(', ')] == ['x', 'b', 'xref', 'yref', 'dy', 'grad', 'dim', 'act', 'alpha',
+                                                                                   'gain', 'clamp']
+    s = str(torch.ops.stylemc_b200.upfirdn2d.default._schema)
+    assert [a.split()[-1] for a in s[s.index('(') + 1:s.index(')')].split(', ')] == ['x', 'f', 'upx', 'upy', 'downx', 'downy', 'padx0', 'padx1', 'pady0',
+                                                                                   'pady1', 'flip', 'gain']
+    x, f = torch.empty(2, 3, 8, 8, device='meta'), torch.empty(4, 4, device='meta')
+    assert torch.ops.stylemc_b200.upfirdn2d(x, f, 2, 2, 1, 1, 2, 1, 2, 1, False, 4.0).shape == (2, 3, 16, 16)        # upsample2d
+    assert torch.ops.stylemc_b200.upfirdn2d(x, f, 1, 1, 2, 2, 1, 1, 1, 1, False, 1.0).shape == (2, 3, 4, 4)          # downsample2d
+    xl = torch.empty(2, 8, 9, 9, device='meta').to(memory_format=torch.channels_last)
+    y = torch.ops.stylemc_b200.upfirdn2d(xl, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0)                                  # the conv0 FIR: (2H+1)^2 -> (2H)^2
+    assert y.shape == (2, 8, 8, 8) and y.stride(1) == 1
+    assert torch.ops.stylemc_b200.bias_act(x, None, None, None, None, 0, 1, 3, 0.2, 2 ** 0.5, 256.0).shape == x.shape
+    with pytest.raises(NotImplementedError):                                     # no CPU kernel, no fallback
+        torch.ops.stylemc_b200.bias_act(torch.zeros(2, 3), None, None, None, None, 0, 1, 3, 0.2, 1.0, -1.0)

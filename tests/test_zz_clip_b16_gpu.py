@@ -128,3 +128,17 @@ def test_step_double_64px_golden(golden, model_b16):
     clip_rel = abs(out['clip_loss'].item() - float(gd['clip_loss'])) / abs(float(gd['clip_loss']))
     print(f'double: loss rel {loss_rel:.2e}, clip rel {clip_rel:.2e}, grad rel-l2 {grad_rel:.3e}')
     assert loss_rel <= 1e-3 and clip_rel <= 1e-3 and grad_rel <= 1e-3
+
+
+def test_torch_library_plugin_ops_match_the_op_api():
+    """torch.ops.stylemc_b200.bias_act / .upfirdn2d (stylemc_b200/ops/custom_ops.py) launch the same kernels as the op-level API."""
+    from stylemc_b200.ops import bias_act, upfirdn2d
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 8, 17, 17, generator=gen).cuda()
+    b = torch.randn(8, generator=gen).cuda()
+    y = torch.ops.stylemc_b200.bias_act(x, b, None, None, None, 0, 1, bias_act.activation_funcs['lrelu'].cuda_idx, 0.2, 2 ** 0.5, 256.0)
+    assert torch.equal(y, bias_act.bias_act(x, b, act='lrelu', clamp=256))
+    f = upfirdn2d.setup_filter([1, 3, 3, 1], device=x.device)
+    z = torch.ops.stylemc_b200.upfirdn2d(x, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0)
+    assert z.shape == (2, 8, 16, 16)
+    assert (z - upfirdn2d.upfirdn2d(x, f, padding=1, gain=4)).abs().max().item() <= 1e-5       # the op API splits separable filters into two passes
