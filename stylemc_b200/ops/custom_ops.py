@@ -4,7 +4,7 @@ The reference reaches its two native plugins through pybind modules built by ``t
 ``_plugin.bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp) -> Tensor`` (bias_act.cpp:32; callers bias_act.py:153,182,201)
 and ``_plugin.upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain) -> Tensor`` (upfirdn2d.cpp:16; caller
 upfirdn2d.py:237-240).  Here the same two calls are ``torch.ops.stylemc_b200.bias_act`` / ``torch.ops.stylemc_b200.upfirdn2d``: same
-argument lists (an absent tensor is ``None`` instead of the reference's empty ``_null_tensor``, bias_act.py:39), CUDA implementation =
+argument lists (an absent tensor is ``None`` or, as in the reference, an empty tensor: ``_null_tensor``, bias_act.py:39), CUDA implementation =
 one launch through the C ABI (``smc_bias_act`` / ``smc_upfirdn2d``), a fake (meta) implementation for tracing, and no CPU kernel -- a
 CPU tensor raises.  Like the pybind functions they carry no autograd formula: differentiation lives one level up, in the
 ``autograd.Function`` pairs of ``ops/bias_act.py`` and ``ops/upfirdn2d.py`` (as in the reference, bias_act.py:129-210, upfirdn2d.py:214-268),
@@ -27,7 +27,9 @@ def bias_act(x: torch.Tensor, b: Optional[torch.Tensor], xref: Optional[torch.Te
         raise RuntimeError(f'bias_act: unknown activation index {act}')
     if grad not in (0, 1, 2):
         raise RuntimeError('grad must be 0, 1 or 2')                               # bias_act.cpp:44
-    return _bias_act._launch(x, b, xref, yref, dy, grad, dim, _SPEC_BY_IDX[act], float(alpha), float(gain), float(clamp))
+    present = lambda t: t if (t is not None and t.numel() > 0) else None        # the reference passes an empty tensor for "absent" (bias_act.py:39)
+    return _bias_act._launch(x, present(b), present(xref), present(yref), present(dy), grad, dim, _SPEC_BY_IDX[act], float(alpha), float(gain),
+                             float(clamp))
 
 
 @bias_act.register_fake
