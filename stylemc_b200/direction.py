@@ -9,6 +9,7 @@ rows; the only exchange is an all-reduce of the ``[8, 512]`` gradient (16 KiB) a
 0.5 * ViT-B/16, find_direction.py:117-119,160-164: pass both models); identity and landmark terms are outside the accelerated path
 (SURVEY.md section 2).
 """
+import contextlib
 import math
 import os
 
@@ -20,6 +21,15 @@ S_TRAINABLE_SPACE_CHANNELS = [2, 3, 5, 6, 8, 9, 11, 12]     # find_direction.py:
 N_STYLE_CHANNELS = 26                                       # find_direction.py:38
 RESOLUTION_DICT = {256: 6, 512: 7, 1024: 8}                 # find_direction.py:263
 DOUBLE_CLIP_WEIGHTS = (1.0, 0.5)                            # find_direction.py:164: clip1 + 0.5 * clip2 (ViT-B/32, ViT-B/16)
+
+
+_NVTX = os.environ.get('STYLEMC_NVTX', '0') != '0'
+
+
+def _phase(name):
+    """NVTX range around a phase of the step when STYLEMC_NVTX=1 (the reference's only tracing hook is ``misc.profiled_function`` ->
+    ``torch.autograd.profiler.record_function``, misc.py:98-103); a no-op otherwise."""
+    return torch.cuda.nvtx.range(name) if _NVTX else contextlib.nullcontext()
 
 
 class CLIPLoss:
@@ -122,10 +132,11 @@ class DirectionFinder:
 
     def _encode_original(self, s):
         """CLIP embeddings of the un-edited images (find_direction.py:312: no gradient), one per tower."""
-        _, original, _ = self.engine.forward(s, self.until_k, self.noise_mode, save=False)
-        u_s = resample.unprocess_fwd(original)
-        del original
-        return [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
+        with _phase('original_branch'):
+            _, original, _ = self.engine.forward(s, self.until_k, self.noise_mode, save=False)
+            u_s = resample.unprocess_fwd(original)
+            del original
+            return [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
 
     def loss_and_grad(self, styles, global_count=None):
         """styles [n, 26, 512] (this rank's shard, device) -> (grad [8, 512] summed over the shard, clip-loss partial sum).
@@ -147,25 +158,31 @@ class DirectionFinder:
                 with torch.cuda.stream(self._side):
                     e_s = self._encode_original(s)
                 s.record_stream(self._side)
-            _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True, grad_rows=self.rows)   # :309
-            u_t = resample.unprocess_fwd(img)                                                      # :159-160
+            with _phase('synthesis_fwd'):
+                _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True, grad_rows=self.rows)   # :309
+            with _phase('unprocess_fwd'):
+                u_t = resample.unprocess_fwd(img)                                                  # :159-160
             if not self.overlap:
                 e_s = self._encode_original(s)
             g224 = gscale = None
             for i, (model, loss_fn, weight) in enumerate(self.clips):
-                e_t, csaved = model.encode_image_fwd(u_t, save=True)
+                with _phase('clip_fwd'):
+                    e_t, csaved = model.encode_image_fwd(u_t, save=True)
                 if self.overlap and i == 0:
                     cur.wait_stream(self._side)
                     for e in e_s:
                         e.record_stream(cur)
                 part, d_t, gs = loss_fn.loss_and_grad(e_s[i], e_t, self.clip_loss_coef * weight, 1.0 / count)
-                g = model.encode_image_bwd(csaved, d_t)
+                with _phase('clip_bwd'):
+                    g = model.encode_image_bwd(csaved, d_t)
                 del csaved
                 # every tower's pixel gradient carries its own power-of-two loss scale: bring the later ones to the first one's
                 g224, gscale = (g, gs) if g224 is None else (g224 + g * (gscale / gs), gscale)
                 part_sum += part
-            g_img = resample.unprocess_bwd(g224, img, unscale=gscale)
-            grad += eng.backward(saved, g_img, self.rows, self.noise_mode)
+            with _phase('unprocess_bwd'):
+                g_img = resample.unprocess_bwd(g224, img, unscale=gscale)
+            with _phase('synthesis_bwd'):
+                grad += eng.backward(saved, g_img, self.rows, self.noise_mode)
         return grad, part_sum
 
     def step(self, styles, lr=None, global_count=None):
