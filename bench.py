@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='find_direction', choices=['find_direction', 'generate_fromS'],
                     help="generate_fromS: forward-only render (BASELINE configs[1], batch 32 at 1024 px); not the headline metric")
+    ap.add_argument('--clip-type', default='small', choices=['small', 'double'],
+                    help="double: ViT-B/32 + 0.5 * ViT-B/16 (the reference CLI's default, find_direction.py:216); not the headline metric (BASELINE fixes ViT-B/32)")
     ap.add_argument('--profile-step', action='store_true', help='run warm-up, then ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     return ap.parse_args()
 
@@ -73,6 +75,7 @@ def synth_flops_per_image(blocks, until_k):
 TOP_KERNEL_DRAM_BYTES = {(64, 1024, 1024, 32, 32, 9): 15.7e9}    # mean of the 3 launches per step: 10.6 (no-grad fwd), 15.0 (grad fwd), 21.4 GB (dgrad)
 
 VIT_FLOPS_FWD = 2 * (49 * 3072 * 768 + 12 * 50 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) + 12 * 12 * 2 * 50 * 50 * 64)   # per image
+VIT_B16_FLOPS_FWD = 2 * (196 * 768 * 768 + 12 * 197 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) + 12 * 12 * 2 * 197 * 197 * 64)   # 35.2 GFLOP
 
 
 class ClockSampler:
@@ -133,7 +136,10 @@ def run_ours(a):
     ws = torch.randn(pool, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(1000 + rank))
     styles_host, shapes = utils.get_styles(G, ws, utils.split_ws(G, ws), 'cpu')
     styles_host = styles_host.pin_memory()
-    model = clip.CLIPModel(clip.random_params(seed=0), dev, precision='x3p' if a.precision == 'x3p' else ('x3' if a.precision != 'x1' else 'x1'))
+    clip_precision = 'x3p' if a.precision == 'x3p' else ('x3' if a.precision != 'x1' else 'x1')
+    model = clip.CLIPModel(clip.random_params(seed=0), dev, precision=clip_precision)
+    if a.clip_type == 'double':
+        model = (model, clip.CLIPModel(clip.random_params(seed=1, cfg=clip.VIT_B16), dev, precision=clip_precision, cfg=clip.VIT_B16))
     finder = direction.DirectionFinder(G, model, clip.placeholder_tokens(POS_BODY), clip.placeholder_tokens(NEG_BODY), a.resolution, device=dev,
                                        precision=a.precision, micro_batch=a.micro_batch, process_group=group, learning_rate=a.lr)
     # delta == 0 makes edited == original and the directional loss 0/0 (NaN in the reference): start from a small random direction
@@ -227,6 +233,8 @@ def run_ours(a):
     eng = finder.engine
     sf = synth_flops_per_image(eng.blocks, finder.until_k)
     alg_flops_img = 3 * sf + 3 * VIT_FLOPS_FWD                # 2 fwd + dgrad bwd of synthesis, 2 fwd + input-grad bwd of the ViT
+    if a.clip_type == 'double':
+        alg_flops_img += 3 * VIT_B16_FLOPS_FWD
     imgs = a.batch * world * a.steps
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
@@ -247,6 +255,7 @@ def run_ours(a):
         'data': 'synthetic (random-init StyleGAN2 config-f + random-init CLIP ViT-B/32, S from randn W)',
         'config': {'workload': f'find_direction {a.resolution}px, batch {a.batch}/GPU (BASELINE configs[3]), fwd+bwd to delta-S [1,8,512]',
                    'resolution': a.resolution, 'batch_per_gpu': a.batch, 'global_batch': a.batch * world, 'micro_batch': a.micro_batch,
+                   'clip_type': a.clip_type + (' (ViT-B/32 + 0.5 * ViT-B/16: NOT the headline configuration)' if a.clip_type == 'double' else ' (ViT-B/32)'),
                    'precision': a.precision, 'learning_rate': a.lr, 'parallelism': f'dp{world} (seed shards; all-reduce of the 16 KiB gradient)',
                    'l2_flush': 'none needed: each step streams >10 GB of activations, far larger than the 126 MB L2'},
         'clocks': clocks,

@@ -11,3 +11,4 @@ leg() { echo "== [$(( $(date +%s) - T0 ))s] $*"; }
 (timeout 600 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_zz_clip_b16_gpu.py -m gpu -q --no-header -p no:cacheprovider \
    -k "attention_197" 2>&1) > gpurun_out/r2_racecheck.log; leg "racecheck: $(tail -n 1 gpurun_out/r2_racecheck.log)"
 (timeout 900 python -m pytest tests -m gpu -q -x --no-header -p no:cacheprovider 2>&1) > gpurun_out/r2_tests.log; leg "whole suite: $(tail -n 1 gpurun_out/r2_tests.log)"
+(timeout 400 python bench.py --clip-type double --no-cpu-baseline > gpurun_out/r2_bench_double.json 2> gpurun_out/r2_bench_double.err); leg "bench clip_type=double: $(cut -c1-200 gpurun_out/r2_bench_double.json)"
