@@ -3,7 +3,7 @@ usage (GPU): python tools/diag_clip_prec.py [x3p x3 x1]"""
 import os, sys
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import synthesis as o_syn, vit as o_vit
 from stylemc_b200 import clip, direction
 

@@ -1,7 +1,7 @@
 """Dev diagnostic (GPU box): where does the config-1 delta-S gradient error come from?  Splits it into the CLIP/unprocess backward
 (gradient w.r.t. the image) and the synthesis backward, using the CPU oracle's own image gradient as the hand-over."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import torch.nn.functional as F
 from oracle import synthesis as o_syn, vit as o_vit, direction as o_dir

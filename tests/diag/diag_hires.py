@@ -1,7 +1,7 @@
 """Dev diagnostic (GPU box): how much precision do the HIGH-resolution blocks need?  1024-px config-f network, 2 seeds, CPU oracle
 (fp32) as reference; our step with split precision everywhere vs fp16 operands (x1) from a given resolution up."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import synthesis as o_syn, vit as o_vit, direction as o_dir
 from stylemc_b200 import clip, direction

@@ -1,6 +1,6 @@
 """Dev diagnostic: config-1 step gradient error for each engine precision (run on the GPU box)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import synthesis as o_syn, vit as o_vit
 from stylemc_b200 import clip, direction
