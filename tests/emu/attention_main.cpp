@@ -1,5 +1,5 @@
 // Driver of the emulated attention kernels (see cuda_emu.h).  kernels_extracted.inc is cut out of stylemc_b200/csrc/vit.cu by
-// tests/test_attention_emu.py (store_split, warp_sum, the attention kernels and attention_block_rows, verbatim except for the
+// tests/test_kernels_emu.py (store_split, warp_sum, the attention kernels and attention_block_rows, verbatim except for the
 // `extern __shared__` line).  Compares against a float64 restatement of softmax attention and its gradient.
 #include "cuda_emu.h"
 namespace smc { int g_attention_tiled = 0; }

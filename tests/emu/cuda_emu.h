@@ -1,5 +1,5 @@
 // Minimal CPU stand-in for the CUDA execution model, enough to run a shared-memory / warp-shuffle kernel of csrc/ unchanged on host
-// threads: one std::thread per CUDA thread of a block, blocks one after another.  TEST INFRASTRUCTURE ONLY (tests/test_attention_emu.py):
+// threads: one std::thread per CUDA thread of a block, blocks one after another.  TEST INFRASTRUCTURE ONLY (tests/test_kernels_emu.py):
 // it checks index arithmetic and data flow of kernels on a machine without a GPU; it says nothing about launch limits or speed.
 #pragma once
 #include <algorithm>
@@ -37,6 +37,9 @@ static inline float __half2float(__half h) { return (float)h; }
 static inline float rsqrtf(float v) { return 1.0f / std::sqrt(v); }
 using std::min;
 using std::max;
+using std::isfinite;
+#define __shared__ static          /* statically sized shared arrays: blocks run one after another, so one copy per process is one per block */
+template <class T> static inline T __ldg(const T* p) { return *p; }
 
 static inline void __syncthreads() { emu_ctx->bar.arrive_and_wait(); }
 static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {

@@ -25,15 +25,21 @@ def _cut(text, start_pattern):
     return text[m.start():end]
 
 
-def extract(vit_cu, common_cuh):
+GLUE_KERNELS = ['layernorm_fwd_kernel', 'layernorm_bwd_kernel', 'quickgelu_fwd_kernel', 'quickgelu_bwd_kernel', 'split_rows_kernel', 'head_proj_kernel',
+                'head_proj_bwd_kernel', 'clip_loss_kernel']
+
+
+def extract(vit_cu, common_cuh, kernels=KERNELS, host_functions=('attention_block_rows',)):
     parts = ['namespace smc {', _cut(common_cuh, r'^__device__ __forceinline__ float warp_sum\('),
              _cut(vit_cu, r'^__device__ __forceinline__ void store_split\(')]
-    for k in KERNELS:
-        body = _cut(vit_cu, r'^__global__ void __launch_bounds__\(256\) ' + k + r'\(')
-        assert body.count('extern __shared__ float sm[];') == 1
-        parts.append(body.replace('extern __shared__ float sm[];', 'float* sm = emu_smem;'))
+    for k in kernels:
+        body = _cut(vit_cu, r'^__global__ void __launch_bounds__\(\d+\) ' + k + r'\(')
+        body, n = re.subn(r'extern __shared__ float (\w+)\[\];', r'float* \1 = emu_smem;', body)
+        assert n <= 1
+        parts.append(body)
     parts.append('}  // namespace smc')
-    parts.append(_cut(vit_cu, r'^static int attention_block_rows\('))
+    for f in host_functions:
+        parts.append(_cut(vit_cu, r'^static int ' + f + r'\('))
     return '\n'.join(parts) + '\n'
 
 
@@ -44,15 +50,13 @@ SANITIZERS = {'plain': ['-O2'],
               'thread': ['-O1', '-g', '-fsanitize=thread']}
 
 
-@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
-@pytest.mark.parametrize('sanitizer', list(SANITIZERS))
-def test_tiled_attention_kernels_on_the_cpu_shim(tmp_path, sanitizer):
+def build_and_run(tmp_path, sanitizer, main_cpp, kernels, host_functions):
     csrc = os.path.join(ROOT, 'stylemc_b200', 'csrc')
-    inc = extract(open(os.path.join(csrc, 'vit.cu')).read(), open(os.path.join(csrc, 'common.cuh')).read())
+    inc = extract(open(os.path.join(csrc, 'vit.cu')).read(), open(os.path.join(csrc, 'common.cuh')).read(), kernels, host_functions)
     (tmp_path / 'kernels_extracted.inc').write_text(inc)
-    exe = str(tmp_path / 'attention_emu')
+    exe = str(tmp_path / 'emu')
     cc = subprocess.run(['g++', '-std=c++20', '-pthread', '-Wno-unknown-pragmas'] + SANITIZERS[sanitizer] +
-                        ['-I', str(tmp_path), '-I', EMU, os.path.join(EMU, 'attention_main.cpp'), '-o', exe], capture_output=True, text=True)
+                        ['-I', str(tmp_path), '-I', EMU, os.path.join(EMU, main_cpp), '-o', exe], capture_output=True, text=True)
     if cc.returncode != 0 and sanitizer != 'plain':
         pytest.skip(f'-fsanitize={sanitizer} runtime not available: {cc.stderr[-200:]}')
     assert cc.returncode == 0, cc.stderr
@@ -60,5 +64,22 @@ def test_tiled_attention_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
     print(r.stdout, r.stderr[-3000:])
     assert r.returncode == 0, r.stdout + r.stderr[-3000:]
-    assert r.stdout.count('ok  ') == 5 and 'FAIL' not in r.stdout
+    assert 'FAIL' not in r.stdout
     assert 'ThreadSanitizer' not in r.stderr and 'AddressSanitizer' not in r.stderr and 'runtime error' not in r.stderr
+    return r.stdout
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', list(SANITIZERS))
+def test_tiled_attention_kernels_on_the_cpu_shim(tmp_path, sanitizer):
+    out = build_and_run(tmp_path, sanitizer, 'attention_main.cpp', KERNELS, ('attention_block_rows',))
+    assert out.count('ok  ') == 5
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', list(SANITIZERS))
+def test_vit_glue_kernels_on_the_cpu_shim(tmp_path, sanitizer):
+    """LayerNorm forward / backward, the embedding head and its transpose, QuickGELU, split_rows and the directional CLIP loss kernel (the
+    one with the most barriers in vit.cu) of the measured ViT-B/32 path, same shim, same sanitizers."""
+    out = build_and_run(tmp_path, sanitizer, 'vit_glue_main.cpp', GLUE_KERNELS, ())
+    assert out.count('ok  ') == 14

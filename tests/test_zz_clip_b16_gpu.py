@@ -2,7 +2,7 @@
 (find_direction.py:117-119,160-164: loss32 + 0.5 * loss16), against tests/golden/clip_b16.npz and step64_double.npz (written by
 oracle/pin_reference.py from the reference's own init_clip_loss / compute_clip_loss) and against the whole-sequence attention
 kernels.  The kernels these tests exercise (attention_fwd_rows_kernel, attention_bwd_q_kernel, attention_bwd_kv_kernel) were
-written after the round-1 GPU budget was spent: on the CPU they run under tests/test_attention_emu.py; this file is their first
+written after the round-1 GPU budget was spent: on the CPU they run under tests/test_kernels_emu.py; this file is their first
 run on a device (named test_zz_* so it runs after the files that cover the measured path)."""
 import pytest
 import torch
