@@ -140,16 +140,56 @@ class SynthesisNetwork(torch.nn.Module):
             setattr(self, f'b{r}', blk)
 
 
-class Generator(torch.nn.Module):
-    """Minimal stand-in for the unpickled G_ema: only ``.synthesis`` is on the hot path."""
+class MappingNetwork(torch.nn.Module):
+    """[UPSTREAM MappingNetwork, c_dim = 0] z -> W+: second-moment normalisation, ``num_layers`` FullyConnectedLayers (lrelu, gain
+    sqrt 2, lr multiplier 0.01), broadcast to ``num_ws`` rows, truncation ``w_avg.lerp(w, psi)``.  Constructor kwargs as
+    ``legacy.py:129-136`` (mapping_layers 8, mapping_lrmul 0.01); attribute names ``fc{i}`` / ``w_avg`` as ``legacy.py:175-181``.
+    Called once per seed set by generate_w.py:48-50."""
 
-    def __init__(self, **synthesis_kwargs):
+    def __init__(self, z_dim=512, w_dim=512, num_ws=18, num_layers=8, lr_multiplier=0.01):
+        super().__init__()
+        self.z_dim, self.w_dim, self.num_ws, self.num_layers = z_dim, w_dim, num_ws, num_layers
+        for i in range(num_layers):
+            setattr(self, f'fc{i}', FullyConnectedLayer(z_dim if i == 0 else w_dim, w_dim, activation='lrelu', lr_multiplier=lr_multiplier))
+        self.register_buffer('w_avg', torch.zeros([w_dim]))
+
+    def forward(self, z, c=None, truncation_psi=1, truncation_cutoff=None):
+        x = z.to(self.w_avg.dtype)
+        x = x * (x.square().mean(dim=1, keepdim=True) + 1e-8).rsqrt()
+        for i in range(self.num_layers):
+            x = getattr(self, f'fc{i}')(x)
+        x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            if truncation_cutoff is None:
+                x = self.w_avg.lerp(x, truncation_psi)
+            else:
+                x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+        return x
+
+
+class Generator(torch.nn.Module):
+    """Minimal stand-in for the unpickled G_ema: ``.synthesis`` is the hot path; ``.mapping`` (built AFTER the synthesis network, as
+    upstream, so the synthesis weights of a seed do not depend on it) only when asked for."""
+
+    def __init__(self, mapping=False, **synthesis_kwargs):
         super().__init__()
         self.synthesis = SynthesisNetwork(**synthesis_kwargs)
+        self.z_dim, self.c_dim, self.w_dim = 512, 0, self.synthesis.w_dim
+        if mapping:
+            self.mapping = MappingNetwork(z_dim=self.z_dim, w_dim=self.w_dim, num_ws=self.synthesis.num_ws)
+
+
+def generate_w(G, seeds, truncation_psi=1.0):
+    """generate_w.py:46-50: one ``np.random.RandomState(seed).randn(1, z_dim)`` per seed -> ``G.mapping`` -> W+ [M, num_ws, 512]."""
+    import numpy as np
+    zs = torch.cat([torch.from_numpy(np.random.RandomState(seed).randn(1, G.z_dim)) for seed in seeds])
+    p = next(G.mapping.parameters())
+    with torch.no_grad():
+        return G.mapping(zs.to(p.device, p.dtype), None, truncation_psi=truncation_psi)
 
 
 def make_generator(img_resolution, seed=0, channel_base=32768, channel_max=512, conv_clamp=256,
-                   noise_strength=0.1, torgb_scale=0.25, dtype=torch.float32):
+                   noise_strength=0.1, torgb_scale=0.25, dtype=torch.float32, mapping=False):
     """Random-init config-f style generator (BASELINE.json config 1/2/4).
 
     Upstream init (weights ~N(0,1), bias 0, affine bias 1, noise_strength 0) with two documented
@@ -161,8 +201,10 @@ def make_generator(img_resolution, seed=0, channel_base=32768, channel_max=512, 
     state = torch.random.get_rng_state()
     torch.random.set_rng_state(gen.get_state())
     try:
-        G = Generator(w_dim=512, img_resolution=img_resolution, img_channels=3, channel_base=channel_base,
+        G = Generator(mapping=mapping, w_dim=512, img_resolution=img_resolution, img_channels=3, channel_base=channel_base,
                       channel_max=channel_max, num_fp16_res=0, conv_clamp=conv_clamp)
+        if mapping:
+            G.mapping.w_avg.copy_(0.1 * torch.randn(512))       # a trained network carries the running mean of W here
     finally:
         torch.random.set_rng_state(state)
     with torch.no_grad():

@@ -30,6 +30,16 @@ def save_w(path, ws):
     np.savez(path, w=torch.as_tensor(ws).detach().cpu().float().numpy())
 
 
+def generate_w(G, seeds, truncation_psi=1.0, device='cuda'):
+    """generate_w.py:46-51: ``z = RandomState(seed).randn(1, z_dim)`` per seed -> ``G.mapping(z, label, truncation_psi)`` -> W+
+    [M, num_ws, 512] (what ``save_w`` writes under the key ``w``).  ``G.mapping`` runs on ``device`` (the lrelu layers use the
+    bias_act kernel: CUDA only)."""
+    zs = torch.cat([torch.from_numpy(np.random.RandomState(seed).randn(1, G.z_dim)) for seed in seeds])
+    G.mapping.to(device)
+    with torch.no_grad():
+        return G.mapping(zs.to(device, torch.float32), None, truncation_psi=truncation_psi)
+
+
 def load_styles(path, n=None):
     """[M, 26, 512] fp32 host tensor (generate_fromS.py:114 takes the first ``n`` rows)."""
     s = _check(np.load(path)['s'], 's', path)

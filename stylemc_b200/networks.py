@@ -190,24 +190,56 @@ class SynthesisNetwork(torch.nn.Module):
         return img
 
 
-class Generator(torch.nn.Module):
-    """Stand-in for the unpickled ``G_ema``: only ``.synthesis`` is on the accelerated path (the mapping network runs once per
-    seed set, generate_w.py:48-51, and is out of scope)."""
+class MappingNetwork(torch.nn.Module):
+    """[UPSTREAM MappingNetwork, c_dim = 0] z -> W+ (generate_w.py:48-50, once per seed set): second-moment normalisation, 8
+    FullyConnectedLayers (lrelu through the ``bias_act`` kernel, lr multiplier 0.01; kwargs of legacy.py:129-136), broadcast to
+    ``num_ws`` rows, truncation ``w_avg.lerp(w, psi)``.  Attribute names ``fc{i}`` / ``w_avg`` as legacy.py:175-181."""
 
-    def __init__(self, **synthesis_kwargs):
+    def __init__(self, z_dim=512, w_dim=512, num_ws=18, num_layers=8, lr_multiplier=0.01):
+        super().__init__()
+        self.z_dim, self.w_dim, self.num_ws, self.num_layers = z_dim, w_dim, num_ws, num_layers
+        for i in range(num_layers):
+            setattr(self, f'fc{i}', FullyConnectedLayer(z_dim if i == 0 else w_dim, w_dim, activation='lrelu', lr_multiplier=lr_multiplier))
+        self.register_buffer('w_avg', torch.zeros([w_dim]))
+
+    def forward(self, z, c=None, truncation_psi=1, truncation_cutoff=None):
+        x = z.to(torch.float32)
+        x = x * (x.square().mean(dim=1, keepdim=True) + 1e-8).rsqrt()
+        for i in range(self.num_layers):
+            x = getattr(self, f'fc{i}')(x)
+        x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            if truncation_cutoff is None:
+                x = self.w_avg.lerp(x, truncation_psi)
+            else:
+                x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+        return x
+
+
+class Generator(torch.nn.Module):
+    """Stand-in for the unpickled ``G_ema``: ``.synthesis`` is the accelerated path; ``.mapping`` (z -> W+, once per seed set,
+    generate_w.py:48-51) is built after it, as upstream, and only when asked for."""
+
+    def __init__(self, mapping=False, **synthesis_kwargs):
         super().__init__()
         self.synthesis = SynthesisNetwork(**synthesis_kwargs)
+        self.z_dim, self.c_dim, self.w_dim = 512, 0, self.synthesis.w_dim
+        if mapping:
+            self.mapping = MappingNetwork(z_dim=self.z_dim, w_dim=self.w_dim, num_ws=self.synthesis.num_ws)
 
 
 def make_generator(img_resolution, seed=0, channel_base=32768, channel_max=512, conv_clamp=256, noise_strength=0.1,
-                   torgb_scale=0.25):
+                   torgb_scale=0.25, mapping=False):
     """Random-init FFHQ config-f style generator (BASELINE.json: random-init weights; upstream init N(0,1) weights, zero biases,
     affine bias 1) with the noise path switched on (noise_strength) and ToRGB weights scaled so images mostly lie in [-1, 1]."""
     state = torch.random.get_rng_state()
     torch.manual_seed(seed)
     try:
-        G = Generator(w_dim=512, img_resolution=img_resolution, img_channels=3, channel_base=channel_base, channel_max=channel_max,
-                      num_fp16_res=0, conv_clamp=conv_clamp)
+        G = Generator(mapping=mapping, w_dim=512, img_resolution=img_resolution, img_channels=3, channel_base=channel_base,
+                      channel_max=channel_max, num_fp16_res=0, conv_clamp=conv_clamp)
+        if mapping:
+            with torch.no_grad():
+                G.mapping.w_avg.copy_(0.1 * torch.randn(512))       # a trained network carries the running mean of W here
     finally:
         torch.random.set_rng_state(state)
     with torch.no_grad():

@@ -346,3 +346,36 @@ def test_plugin_boundary_is_registered_as_torch_library_ops():
     assert torch.ops.stylemc_b200.bias_act(x, None, None, None, None, 0, 1, 3, 0.2, 2 ** 0.5, 256.0).shape == x.shape
     with pytest.raises(NotImplementedError):                                     # no CPU kernel, no fallback
         torch.ops.stylemc_b200.bias_act(torch.zeros(2, 3), None, None, None, None, 0, 1, 3, 0.2, 1.0, -1.0)
+
+
+def test_mapping_network_and_generate_w():
+    """SURVEY.md 8(f) row 1, z -> W+ (generate_w.py:46-51; upstream MappingNetwork with legacy.py:129-136 kwargs): the oracle against an
+    independent float64 evaluation, the invariances of the architecture, parameter names of legacy.py:175-181, and identical weights in
+    the product's module (whose forward needs the bias_act kernel: tests/test_zz_clip_b16_gpu.py)."""
+    import numpy as np
+    from stylemc_b200 import networks
+    G = o_syn.make_generator(32, seed=1, channel_base=1024, channel_max=64, mapping=True)
+    plain = o_syn.make_generator(32, seed=1, channel_base=1024, channel_max=64)
+    assert all(torch.equal(v, G.state_dict()[k]) for k, v in plain.state_dict().items())       # the mapping network does not move the synthesis weights
+    names = [k for k in G.state_dict() if k.startswith('mapping.')]
+    assert names == ['mapping.w_avg'] + [f'mapping.fc{i}.{p}' for i in range(8) for p in ('weight', 'bias')]
+    seeds = [1, 2, 5]
+    ws = o_syn.generate_w(G, seeds, truncation_psi=0.7)
+    assert ws.shape == (3, G.synthesis.num_ws, 512) and all(torch.equal(ws[:, 0], ws[:, j]) for j in range(ws.shape[1]))
+    # float64, written out: z / rms(z) -> 8 x lrelu(x W^T * 0.01 / sqrt(512) + 0.01 b) * sqrt(2) -> w_avg + psi (w - w_avg)
+    x = np.concatenate([np.random.RandomState(s).randn(1, 512) for s in seeds])
+    x = x / np.sqrt((x * x).mean(1, keepdims=True) + 1e-8)
+    for i in range(8):
+        fc = getattr(G.mapping, f'fc{i}')
+        x = x @ (fc.weight.double().numpy().T * (0.01 / math.sqrt(512))) + fc.bias.double().numpy() * 0.01
+        x = np.where(x > 0, x, 0.2 * x) * math.sqrt(2)
+    avg = G.mapping.w_avg.double().numpy()
+    want = avg + 0.7 * (x - avg)
+    assert np.abs(ws[:, 0].double().numpy() - want).max() <= 1e-5
+    z = torch.randn(2, 512, generator=torch.Generator().manual_seed(3))
+    assert torch.allclose(G.mapping(z), G.mapping(3.0 * z), atol=1e-5)                        # second-moment normalisation
+    cut = G.mapping(z, truncation_psi=0.5, truncation_cutoff=2)
+    full = G.mapping(z)
+    assert torch.equal(cut[:, 2:], full[:, 2:]) and torch.allclose(cut[:, :2], G.mapping.w_avg.lerp(full[:, :2], 0.5))
+    Gp = networks.make_generator(32, seed=1, channel_base=1024, channel_max=64, mapping=True)
+    assert all(torch.equal(v, Gp.state_dict()[k]) for k, v in G.state_dict().items())

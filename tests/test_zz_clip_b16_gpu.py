@@ -142,3 +142,12 @@ def test_torch_library_plugin_ops_match_the_op_api():
     z = torch.ops.stylemc_b200.upfirdn2d(x, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0)
     assert z.shape == (2, 8, 16, 16)
     assert (z - upfirdn2d.upfirdn2d(x, f, padding=1, gain=4)).abs().max().item() <= 1e-5       # the op API splits separable filters into two passes
+
+
+def test_generate_w_matches_oracle():
+    """z -> W+ (generate_w.py:46-51) on the device: cuBLAS matmuls + the bias_act kernel for the 8 lrelu layers, against the CPU oracle."""
+    from stylemc_b200 import io, networks
+    kw = dict(seed=1, channel_base=1024, channel_max=64, mapping=True)
+    ws = io.generate_w(networks.make_generator(32, **kw), [1, 2, 5], truncation_psi=0.7)
+    ref = o_syn.generate_w(o_syn.make_generator(32, **kw), [1, 2, 5], truncation_psi=0.7)
+    assert ws.shape == ref.shape and (ws.cpu() - ref).abs().max().item() <= 2e-5
