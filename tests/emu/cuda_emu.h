@@ -51,23 +51,30 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   return r;
 }
 
-// kernel<<<grid, block, smem>>>(args...)  ->  emu_launch(grid, block, smem, [&] { kernel(args...); })
-static void emu_launch(int grid, int block, size_t smem_bytes, const std::function<void()>& body) {
-  gridDim.x = grid;
+// kernel<<<grid, block, smem>>>(args...)  ->  emu_launch(grid, block, smem, [&] { kernel(args...); })   (grid: int or emu_dim3)
+static void emu_launch(emu_dim3 grid, int block, size_t smem_bytes, const std::function<void()>& body) {
+  gridDim = grid;
   blockDim.x = block;
   std::vector<float> smem((smem_bytes + 3) / 4);
-  for (int b = 0; b < grid; ++b) {
-    std::fill(smem.begin(), smem.end(), NAN);      // reads of never-written shared memory poison the result
-    emu_block ctx(block);
-    std::vector<std::thread> th;
-    for (int t = 0; t < block; ++t)
-      th.emplace_back([&, t] {
-        threadIdx.x = t;
-        blockIdx.x = b;
-        emu_smem = smem.data();
-        emu_ctx = &ctx;
-        body();
-      });
-    for (auto& x : th) x.join();
-  }
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        std::fill(smem.begin(), smem.end(), NAN);      // reads of never-written shared memory poison the result
+        emu_block ctx(block);
+        std::vector<std::thread> th;
+        for (int t = 0; t < block; ++t)
+          th.emplace_back([&, t] {
+            threadIdx.x = t;
+            blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+            emu_smem = smem.data();
+            emu_ctx = &ctx;
+            body();
+          });
+        for (auto& x : th) x.join();
+      }
+}
+static void emu_launch(int grid, int block, size_t smem_bytes, const std::function<void()>& body) {
+  emu_dim3 g;
+  g.x = grid;
+  emu_launch(g, block, smem_bytes, body);
 }

@@ -29,17 +29,22 @@ GLUE_KERNELS = ['layernorm_fwd_kernel', 'layernorm_bwd_kernel', 'quickgelu_fwd_k
                 'head_proj_bwd_kernel', 'clip_loss_kernel']
 
 
-def extract(vit_cu, common_cuh, kernels=KERNELS, host_functions=('attention_block_rows',)):
-    parts = ['namespace smc {', _cut(common_cuh, r'^__device__ __forceinline__ float warp_sum\('),
-             _cut(vit_cu, r'^__device__ __forceinline__ void store_split\(')]
+SYNTH_KERNELS = ['demod_kernel', 'pack_nhwc_kernel', ('unpack_nchw_kernel', 'template <class T>'), 'sgrad_finish_kernel']
+
+
+def extract(cu, common_cuh, kernels=KERNELS, host_functions=('attention_block_rows',)):
+    parts = ['namespace smc {', _cut(common_cuh, r'^__device__ __forceinline__ float warp_sum\(')]
+    if '__forceinline__ void store_split(' in cu:
+        parts.append(_cut(cu, r'^__device__ __forceinline__ void store_split\('))
     for k in kernels:
-        body = _cut(vit_cu, r'^__global__ void __launch_bounds__\(\d+\) ' + k + r'\(')
+        k, prefix = k if isinstance(k, tuple) else (k, '')
+        body = _cut(cu, r'^__global__ void __launch_bounds__\(\d+\) ' + k + r'\(')
         body, n = re.subn(r'extern __shared__ float (\w+)\[\];', r'float* \1 = emu_smem;', body)
         assert n <= 1
-        parts.append(body)
+        parts.append(prefix + '\n' + body)
     parts.append('}  // namespace smc')
     for f in host_functions:
-        parts.append(_cut(vit_cu, r'^static int ' + f + r'\('))
+        parts.append(_cut(cu, r'^static int ' + f + r'\('))
     return '\n'.join(parts) + '\n'
 
 
@@ -50,9 +55,9 @@ SANITIZERS = {'plain': ['-O2'],
               'thread': ['-O1', '-g', '-fsanitize=thread']}
 
 
-def build_and_run(tmp_path, sanitizer, main_cpp, kernels, host_functions):
+def build_and_run(tmp_path, sanitizer, main_cpp, kernels, host_functions, source='vit.cu'):
     csrc = os.path.join(ROOT, 'stylemc_b200', 'csrc')
-    inc = extract(open(os.path.join(csrc, 'vit.cu')).read(), open(os.path.join(csrc, 'common.cuh')).read(), kernels, host_functions)
+    inc = extract(open(os.path.join(csrc, source)).read(), open(os.path.join(csrc, 'common.cuh')).read(), kernels, host_functions)
     (tmp_path / 'kernels_extracted.inc').write_text(inc)
     exe = str(tmp_path / 'emu')
     cc = subprocess.run(['g++', '-std=c++20', '-pthread', '-Wno-unknown-pragmas'] + SANITIZERS[sanitizer] +
@@ -83,3 +88,12 @@ def test_vit_glue_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     one with the most barriers in vit.cu) of the measured ViT-B/32 path, same shim, same sanitizers."""
     out = build_and_run(tmp_path, sanitizer, 'vit_glue_main.cpp', GLUE_KERNELS, ())
     assert out.count('ok  ') == 14
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', list(SANITIZERS))
+def test_synthesis_glue_kernels_on_the_cpu_shim(tmp_path, sanitizer):
+    """Shared-memory glue kernels of csrc/synth.cu on the measured path: demodulation coefficients, the final style-gradient assembly
+    (SURVEY.md 8a algebra) and the NCHW <-> NHWC tile transposes, launched with the grids the C layer uses."""
+    out = build_and_run(tmp_path, sanitizer, 'synth_glue_main.cpp', SYNTH_KERNELS, (), source='synth.cu')
+    assert out.count('ok  ') == 7
