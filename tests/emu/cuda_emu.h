@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <barrier>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
@@ -40,6 +41,22 @@ using std::max;
 using std::isfinite;
 #define __shared__ static          /* statically sized shared arrays: blocks run one after another, so one copy per process is one per block */
 template <class T> static inline T __ldg(const T* p) { return *p; }
+
+// vector types with CUDA's alignment, so that UBSan checks the alignment assumptions of 8- and 16-byte loads / stores
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(4) __half2 { __half x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline __half2 __floats2half2_rn(float a, float b) { return __half2{(__half)a, (__half)b}; }
+static inline float2 __half22float2(__half2 h) { return float2{(float)h.x, (float)h.y}; }
+static inline float __int_as_float(int i) { float f; __builtin_memcpy(&f, &i, 4); return f; }
+// packed fp32x2 arithmetic of common.cuh (inline PTX there): one rounding per component, like fma.rn.f32x2 / mul.rn.f32x2
+static inline float2 ffma2(float2 a, float2 b, float2 c) { return float2{std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)}; }
+static inline float2 fmul2(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
 
 static inline void __syncthreads() { emu_ctx->bar.arrive_and_wait(); }
 static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {

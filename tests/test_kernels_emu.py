@@ -38,7 +38,10 @@ def extract(cu, common_cuh, kernels=KERNELS, host_functions=('attention_block_ro
         parts.append(_cut(cu, r'^__device__ __forceinline__ void store_split\('))
     for k in kernels:
         k, prefix = k if isinstance(k, tuple) else (k, '')
-        body = _cut(cu, r'^__global__ void __launch_bounds__\(\d+\) ' + k + r'\(')
+        if k.startswith('@'):                      # a __device__ helper the kernels call
+            parts.append(_cut(cu, r'^__device__ __forceinline__ \w+ ' + k[1:] + r'\('))
+            continue
+        body = _cut(cu, r'^__global__ void __launch_bounds__\([^)]*\) ' + k + r'\(')
         body, n = re.subn(r'extern __shared__ float (\w+)\[\];', r'float* \1 = emu_smem;', body)
         assert n <= 1
         parts.append(prefix + '\n' + body)
@@ -97,3 +100,16 @@ def test_synthesis_glue_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     (SURVEY.md 8a algebra) and the NCHW <-> NHWC tile transposes, launched with the grids the C layer uses."""
     out = build_and_run(tmp_path, sanitizer, 'synth_glue_main.cpp', SYNTH_KERNELS, (), source='synth.cu')
     assert out.count('ok  ') == 7
+
+
+FIR_KERNELS = ['@split4', ('fir_act3_kernel', 'template <int C, int JT, int SAVE, bool NOISE, int MINB>')]
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', ['plain', 'address'])
+def test_fir_act3_kernel_on_the_cpu_shim(tmp_path, sanitizer):
+    """The conv0 tail of the fused synthesis path (csrc/synth.cu fir_act3_kernel: the heaviest HBM-bound kernel of a step) against a
+    float64 upfirdn2d + bias_act over the transposed-conv output.  Plane entries outside that output are NaN, the run under
+    AddressSanitizer + UBSan checks the bounds and the 8 / 16-byte alignment of every vector access.  (No barriers: no TSan leg.)"""
+    out = build_and_run(tmp_path, sanitizer, 'fir_act3_main.cpp', FIR_KERNELS, (), source='synth.cu')
+    assert out.count('ok  ') == 3
