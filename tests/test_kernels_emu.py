@@ -59,7 +59,7 @@ SANITIZERS = {'plain': ['-O2'],
               'thread': ['-O1', '-g', '-fsanitize=thread']}
 
 
-def build_and_run(tmp_path, sanitizer, main_cpp, kernels, host_functions, source='vit.cu'):
+def build_and_run(tmp_path, sanitizer, main_cpp, kernels, host_functions, source='vit.cu', argv=()):
     csrc = os.path.join(ROOT, 'stylemc_b200', 'csrc')
     inc = extract(open(os.path.join(csrc, source)).read(), open(os.path.join(csrc, 'common.cuh')).read(), kernels, host_functions)
     (tmp_path / 'kernels_extracted.inc').write_text(inc)
@@ -70,7 +70,7 @@ def build_and_run(tmp_path, sanitizer, main_cpp, kernels, host_functions, source
         pytest.skip(f'-fsanitize={sanitizer} runtime not available: {cc.stderr[-200:]}')
     assert cc.returncode == 0, cc.stderr
     env = dict(os.environ, TSAN_OPTIONS='halt_on_error=0 exitcode=66', ASAN_OPTIONS='detect_leaks=0')
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    r = subprocess.run([exe] + list(argv), capture_output=True, text=True, timeout=900, env=env)
     print(r.stdout, r.stderr[-3000:])
     assert r.returncode == 0, r.stdout + r.stderr[-3000:]
     assert 'FAIL' not in r.stdout
@@ -126,3 +126,40 @@ def test_fir_bwd3_kernel_on_the_cpu_shim(tmp_path, sanitizer):
     rows / columns of the planes outside the transposed-conv grid; bounds and vector alignment under AddressSanitizer + UBSan."""
     out = build_and_run(tmp_path, sanitizer, 'fir_bwd3_main.cpp', FIR_BWD_KERNELS, (), source='synth.cu')
     assert out.count('ok  ') == 3
+
+
+RESAMPLE_KERNELS = ['resample_h_kernel', 'resample_v_kernel', 'resample_vT_kernel', 'resample_hT_kernel']
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('in_size,out_size,sanitizer', [(80, 36, 'plain'), (80, 36, 'address'), (20, 36, 'plain')])
+def test_unprocess_kernels_on_the_cpu_shim(tmp_path, in_size, out_size, sanitizer):
+    """``unprocess`` (find_direction.py:49-52) end to end on the CPU: the shipped resample kernels, launched in the C layer's order on the
+    tables stylemc_b200/resample.py builds, against the oracle's F.interpolate(bicubic, antialias) forward and its autograd -- a
+    down-sampling case (the benchmark's 1024 -> 224 regime: wide windows) and an up-sampling one (the 64-px tests)."""
+    import numpy as np
+    import torch
+    from oracle import direction as o_dir
+    from stylemc_b200 import resample
+    gen = torch.Generator().manual_seed(4)
+    planes = 3
+    x = 0.7 * torch.randn(1, 3, in_size, in_size, generator=gen)                 # ~15 % of the pixels hit the clamp(0, 255)
+    g = torch.randn(1, 3, out_size, out_size, generator=gen)
+    unscale = 64.0
+    start, count, wgt, taps = resample.aa_tables(in_size, out_size)
+    oidx, count_t, wgt_t, taps_t = resample.transpose_tables(start, count, wgt, in_size)
+    with open(tmp_path / 'in.bin', 'wb') as f:
+        f.write(np.array([planes, in_size, out_size, taps, taps_t], np.int32).tobytes())
+        for a, dt in ((x.numpy(), np.float32), (start, np.int32), (count, np.int32), (wgt, np.float32), (oidx, np.int32), (count_t, np.int32),
+                      (wgt_t, np.float32), ((g * unscale).numpy(), np.float32),
+                      (np.array(list(resample.CLIP_MEAN) + list(resample.CLIP_STD) + [unscale]), np.float32)):
+            f.write(np.ascontiguousarray(a, dtype=dt).tobytes())
+    build_and_run(tmp_path, sanitizer, 'unprocess_main.cpp', RESAMPLE_KERNELS, (), argv=[str(tmp_path / 'in.bin'), str(tmp_path / 'out.bin')])
+    out = np.fromfile(tmp_path / 'out.bin', np.float32)
+    y = torch.from_numpy(out[:planes * out_size * out_size]).reshape(1, 3, out_size, out_size)
+    gx = torch.from_numpy(out[planes * out_size * out_size:]).reshape(1, 3, in_size, in_size)
+    x64 = x.double().requires_grad_(True)
+    y64 = o_dir.unprocess(x64, size=out_size)
+    y64.backward(g.double())
+    assert (y.double() - y64.detach()).abs().max().item() <= 2e-5
+    assert ((gx.double() - x64.grad).norm() / x64.grad.norm()).item() <= 1e-5
