@@ -3,6 +3,7 @@
 // it checks index arithmetic and data flow of kernels on a machine without a GPU; it says nothing about launch limits or speed.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -57,6 +58,13 @@ static inline float __int_as_float(int i) { float f; __builtin_memcpy(&f, &i, 4)
 // packed fp32x2 arithmetic of common.cuh (inline PTX there): one rounding per component, like fma.rn.f32x2 / mul.rn.f32x2
 static inline float2 ffma2(float2 a, float2 b, float2 c) { return float2{std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)}; }
 static inline float2 fmul2(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+static inline float __uint_as_float(unsigned u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
+// 16-byte streaming load / store of common.cuh (inline PTX there); the cast keeps CUDA's 16-byte alignment requirement visible to UBSan
+static inline uint4 ld_stream(const void* p) { return *static_cast<const uint4*>(p); }
+static inline void st_stream(void* p, const uint4& v) { *static_cast<uint4*>(p) = v; }
+static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 
 static inline void __syncthreads() { emu_ctx->bar.arrive_and_wait(); }
 static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {

@@ -163,3 +163,16 @@ def test_unprocess_kernels_on_the_cpu_shim(tmp_path, in_size, out_size, sanitize
     y64.backward(g.double())
     assert (y.double() - y64.detach()).abs().max().item() <= 2e-5
     assert ((gx.double() - x64.grad).norm() / x64.grad.norm()).item() <= 1e-5
+
+
+ACT_BWD_KERNELS = ['@h8_to_f', '@f_to_h8', '@f_to_h8_split', '@ld8f', ('act_bwd1_kernel', 'template <class TG>')]
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', list(SANITIZERS))
+def test_act_bwd1_kernel_on_the_cpu_shim(tmp_path, sanitizer):
+    """The activation backward + style-gradient reductions of the fused synthesis path (csrc/synth.cu act_bwd1_kernel: shared-memory and
+    global atomics, partial-warp shuffles) against a float64 restatement, with the launch configuration of smc_act_bwd; ThreadSanitizer
+    covers the reductions, AddressSanitizer + UBSan the 16-byte streaming loads and stores."""
+    out = build_and_run(tmp_path, sanitizer, 'act_bwd_main.cpp', ACT_BWD_KERNELS, (), source='synth.cu')
+    assert out.count('ok  ') == 3
