@@ -1691,6 +1691,7 @@ extern "C" int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w
   if (xs_hi && !s_next) return SMC_EINVAL;
   const int lpp = pick_lpp(c);
   if (lpp < 4) return SMC_EUNSUPPORTED;  // three lanes of a group write r, g, b
+  if (32 % lpp) return SMC_EUNSUPPORTED; // lane groups must tile a warp (C / 8 = 12, 20, ... would let the lanes left over redo a neighbour's pixel)
   const long long npix = (long long)n * h * w;
   const int cgn = c >> 3;
   if (cgn <= 32 && (cgn & (cgn - 1)) == 0 && (long long)h * w < (1 << 30)) {
@@ -1737,6 +1738,9 @@ extern "C" int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w,
 #undef SMC_ABRC
   }
   const int lpp = pick_lpp(c);
+  // lane groups must tile a warp: with C / 8 = 12, 20, ... the lanes left over would process a neighbour's pixel a second time and the T1 / R
+  // reductions would count it twice (found by tests/test_kernels_emu.py; no layer of the config-f networks has such a channel count)
+  if (32 % lpp) return SMC_EUNSUPPORTED;
   // enough blocks to fill the machine, few enough that the per-block atomics stay cheap
   int pix_per_block = 8 * (32 / lpp) * 16;
   while (pix_per_block > 8 * (32 / lpp) && ceil_div_ll(hw, pix_per_block) * n < 2 * kNumSMs) pix_per_block >>= 1;

@@ -1,4 +1,4 @@
-// Driver of the emulated act_bwd1_kernel of stylemc_b200/csrc/synth.cu (see cuda_emu.h): the activation backward of a modulated-conv layer
+// Driver of the emulated act_bwd1_kernel and act_bwd_kernel of stylemc_b200/csrc/synth.cu (see cuda_emu.h): the activation backward of a modulated-conv layer
 // on the fused synthesis path, which also accumulates the two reductions of the style gradient (SURVEY.md 8a algebra) with shared-memory
 // and global atomics -- the kernel where a race would hide.  Reference (float64), per pixel p of image n and channel c, y = saved activation:
 //   m_j[c]  = w_rgb[j,c] * s_t[n,c] * wgain                      ToRGB weights times its styles
@@ -19,7 +19,7 @@ static std::vector<float> rnd(size_t n, double scale = 1.0, double shift = 0.0) 
   return v;
 }
 
-template <class TG>
+template <class TG, bool GENERIC = false>
 static int run(int N, int H, int W, int C, bool with_rgb, bool with_up, bool gd_lo_plane, float clamp, float rgb_clamp) {
   const long long hw = (long long)H * W;
   const size_t ne = (size_t)N * hw * C;
@@ -47,9 +47,10 @@ static int run(int N, int H, int W, int C, bool with_rgb, bool with_up, bool gd_
   while (pix_per_block > 8 * (32 / lpp) && ceil_div_ll(hw, pix_per_block) * N < 2 * 148) pix_per_block >>= 1;
   const int blocks = (int)(ceil_div_ll(hw, pix_per_block) * N);
   emu_launch(blocks, 256, 2 * C * sizeof(float), [&] {
-    act_bwd1_kernel<TG>(yh.data(), yl.data(), N, H, W, C, with_up ? g_up.data() : nullptr, s_next.data(), sn_stride, with_rgb ? g_img.data() : nullptr,
-                        w_rgb.data(), s_t.data(), st_stride, wgain, b_rgb.data(), rgb_clamp, &gscale, dcoef.data(), noise.data(), bias.data(), alpha, gain,
-                        clamp, gd.data(), gd_lo_plane ? gdl.data() : nullptr, T1.data(), R.data(), lpp, pix_per_block);
+    auto kernel = GENERIC ? act_bwd_kernel<TG> : act_bwd1_kernel<TG>;      // same arguments; smc_act_bwd picks by C / 8 being a power of two <= 32
+    kernel(yh.data(), yl.data(), N, H, W, C, with_up ? g_up.data() : nullptr, s_next.data(), sn_stride, with_rgb ? g_img.data() : nullptr, w_rgb.data(),
+           s_t.data(), st_stride, wgain, b_rgb.data(), rgb_clamp, &gscale, dcoef.data(), noise.data(), bias.data(), alpha, gain, clamp, gd.data(),
+           gd_lo_plane ? gdl.data() : nullptr, T1.data(), R.data(), lpp, pix_per_block);
   });
   double e_gd = 0, m_gd = 0, e_t1 = 0, e_r = 0, m_t1 = 0, m_r = 0;
   int masked = 0, rgb_masked = 0;
@@ -89,8 +90,8 @@ static int run(int N, int H, int W, int C, bool with_rgb, bool with_up, bool gd_
   const double tol_gd = gd_lo_plane ? 3e-6 : 6e-4, tol_r = gd_lo_plane ? 2e-5 : 2e-3;
   const bool ok = e_gd <= tol_gd * m_gd && e_t1 <= 2e-5 * std::max(m_t1, 1.0) && e_r <= tol_r * std::max(m_r, 1.0) && (clamp < 0 || clamp > 2 || masked > 0) &&
                   (!with_rgb || rgb_clamp < 0 || rgb_masked > 0);      // a small clamp must bite
-  printf("%s act_bwd1<%s> N=%d HW=%lld C=%d rgb=%d up=%d lo=%d blocks=%d lpp=%d: gd err %.2e (max %.2f), T1 err %.2e (max %.1f), R err %.2e (max %.1f), %d + %d masked\n",
-         ok ? "ok  " : "FAIL", sizeof(TG) == 2 ? "half" : "float", N, hw, C, (int)with_rgb, (int)with_up, (int)gd_lo_plane, blocks, lpp, e_gd, m_gd, e_t1, m_t1, e_r,
+  printf("%s act_bwd%s<%s> N=%d HW=%lld C=%d rgb=%d up=%d lo=%d blocks=%d lpp=%d: gd err %.2e (max %.2f), T1 err %.2e (max %.1f), R err %.2e (max %.1f), %d + %d masked\n",
+         ok ? "ok  " : "FAIL", GENERIC ? "" : "1", sizeof(TG) == 2 ? "half" : "float", N, hw, C, (int)with_rgb, (int)with_up, (int)gd_lo_plane, blocks, lpp, e_gd, m_gd, e_t1, m_t1, e_r,
          m_r, masked, rgb_masked);
   return ok ? 0 : 1;
 }
@@ -101,5 +102,7 @@ int main() {
   bad += run<float>(2, 13, 11, 64, true, true, true, 1.0f, 0.05f);     // both gradient sources, both clamps bite, ragged pixel count
   bad += run<__half>(1, 9, 7, 128, false, true, false, -1.0f, -1.0f);  // fp16 incoming gradient, hi-only gd, no ToRGB branch, no clamp
   bad += run<float>(1, 8, 8, 32, true, false, true, 256.0f, -1.0f);    // ToRGB gradient only (g_up absent), 4 lanes per pixel
+  bad += run<float, true>(1, 5, 7, 512, true, true, true, 1.0f, 0.1f);  // the 512-channel layers: generic kernel, two channel groups per lane
+  bad += run<__half, true>(1, 6, 6, 320, false, true, false, -1.0f, -1.0f); // C / 8 = 40: not a power of two, lane groups still tile a warp (lpp = 32)
   return bad ? 1 : 0;
 }

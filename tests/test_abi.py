@@ -102,3 +102,14 @@ def test_cpu_tensors_are_refused():
         bias_act.bias_act(torch.zeros(1, 2, 3, 3), torch.zeros(2), act='lrelu')
     with pytest.raises(RuntimeError):
         upfirdn2d.upfirdn2d(torch.zeros(1, 2, 4, 4), upfirdn2d.setup_filter([1, 3, 3, 1]))
+
+
+def test_act_bwd_refuses_channel_counts_whose_lane_groups_do_not_tile_a_warp():
+    """C / 8 = 12 lanes per pixel leave 8 lanes of a warp over; they would redo a neighbour's pixel and the style-gradient reductions would
+    count it twice (found with tests/test_kernels_emu.py).  The C layer refuses such shapes before any launch: no device needed."""
+    from stylemc_b200 import _lib
+    fake = 0x1000                                        # never dereferenced on the host
+    args = lambda c: (fake, fake, 1, 8, 8, c, fake, 1, fake, 512, None, None, None, 0, 1.0, None, -1.0, fake, fake, fake, fake, 0.2, 1.4, 256.0,
+                      fake, fake, fake, fake, None)
+    assert _lib.lib().smc_act_bwd(*args(96)) == -2       # SMC_EUNSUPPORTED
+    assert _lib.lib().smc_act_bwd(*args(24)) == -1       # below 32 channels: invalid argument, as before

@@ -64,7 +64,8 @@ def build_and_run(tmp_path, sanitizer, main_cpp, kernels, host_functions, source
     inc = extract(open(os.path.join(csrc, source)).read(), open(os.path.join(csrc, 'common.cuh')).read(), kernels, host_functions)
     (tmp_path / 'kernels_extracted.inc').write_text(inc)
     exe = str(tmp_path / 'emu')
-    cc = subprocess.run(['g++', '-std=c++20', '-pthread', '-Wno-unknown-pragmas'] + SANITIZERS[sanitizer] +
+    # -fno-strict-aliasing: CUDA code type-puns vector registers (uint4 <-> __half2[4]); g++ -O2 miscompiles that under its aliasing rules
+    cc = subprocess.run(['g++', '-std=c++20', '-pthread', '-Wno-unknown-pragmas', '-fno-strict-aliasing'] + SANITIZERS[sanitizer] +
                         ['-I', str(tmp_path), '-I', EMU, os.path.join(EMU, main_cpp), '-o', exe], capture_output=True, text=True)
     if cc.returncode != 0 and sanitizer != 'plain':
         pytest.skip(f'-fsanitize={sanitizer} runtime not available: {cc.stderr[-200:]}')
@@ -165,14 +166,14 @@ def test_unprocess_kernels_on_the_cpu_shim(tmp_path, in_size, out_size, sanitize
     assert ((gx.double() - x64.grad).norm() / x64.grad.norm()).item() <= 1e-5
 
 
-ACT_BWD_KERNELS = ['@h8_to_f', '@f_to_h8', '@f_to_h8_split', '@ld8f', ('act_bwd1_kernel', 'template <class TG>')]
+ACT_BWD_KERNELS = ['@h8_to_f', '@f_to_h8', '@f_to_h8_split', '@ld8f', ('act_bwd_kernel', 'template <class TG>'), ('act_bwd1_kernel', 'template <class TG>')]
 
 
 @pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
 @pytest.mark.parametrize('sanitizer', list(SANITIZERS))
-def test_act_bwd1_kernel_on_the_cpu_shim(tmp_path, sanitizer):
-    """The activation backward + style-gradient reductions of the fused synthesis path (csrc/synth.cu act_bwd1_kernel: shared-memory and
+def test_act_bwd_kernels_on_the_cpu_shim(tmp_path, sanitizer):
+    """The activation backward + style-gradient reductions of the fused synthesis path (csrc/synth.cu act_bwd1_kernel and the generic act_bwd_kernel of the 512-channel layers: shared-memory and
     global atomics, partial-warp shuffles) against a float64 restatement, with the launch configuration of smc_act_bwd; ThreadSanitizer
     covers the reductions, AddressSanitizer + UBSan the 16-byte streaming loads and stores."""
     out = build_and_run(tmp_path, sanitizer, 'act_bwd_main.cpp', ACT_BWD_KERNELS, (), source='synth.cu')
-    assert out.count('ok  ') == 3
+    assert out.count('ok  ') == 5
