@@ -177,3 +177,15 @@ def test_act_bwd_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     covers the reductions, AddressSanitizer + UBSan the 16-byte streaming loads and stores."""
     out = build_and_run(tmp_path, sanitizer, 'act_bwd_main.cpp', ACT_BWD_KERNELS, (), source='synth.cu')
     assert out.count('ok  ') == 5
+
+
+TORGB_KERNELS = ['@h8_to_f', '@f_to_h8', '@f_to_h8_split', '@ld8f', 'torgb_kernel', 'torgb1_kernel']
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', list(SANITIZERS))
+def test_torgb_kernels_on_the_cpu_shim(tmp_path, sanitizer):
+    """ToRGB + skip-image upsample + next-layer style multiply (csrc/synth.cu torgb1_kernel and the generic torgb_kernel; utils.py:45-49)
+    against a float64 restatement, with the launch configurations of smc_torgb."""
+    out = build_and_run(tmp_path, sanitizer, 'torgb_main.cpp', TORGB_KERNELS, (), source='synth.cu')
+    assert out.count('ok  ') == 5
