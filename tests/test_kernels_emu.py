@@ -189,3 +189,15 @@ def test_torgb_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     against a float64 restatement, with the launch configurations of smc_torgb."""
     out = build_and_run(tmp_path, sanitizer, 'torgb_main.cpp', TORGB_KERNELS, (), source='synth.cu')
     assert out.count('ok  ') == 5
+
+
+ACT_BWD_RGB_KERNELS = ['@h8_to_f', '@ld8f', '@split4', ('act_bwd_rgb_kernel', 'template <int C, bool YLO, bool LO>')]
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', ['plain', 'address'])
+def test_act_bwd_rgb_kernel_on_the_cpu_shim(tmp_path, sanitizer):
+    """The activation backward of the last block (csrc/synth.cu act_bwd_rgb_kernel: at 1024 px the largest activation of a step) against
+    a float64 restatement with the launch configuration of launch_act_bwd_rgb.  (No shared memory or shuffles: no TSan leg.)"""
+    out = build_and_run(tmp_path, sanitizer, 'act_bwd_rgb_main.cpp', ACT_BWD_RGB_KERNELS, (), source='synth.cu')
+    assert out.count('ok  ') == 3
