@@ -201,3 +201,12 @@ def test_act_bwd_rgb_kernel_on_the_cpu_shim(tmp_path, sanitizer):
     a float64 restatement with the launch configuration of launch_act_bwd_rgb.  (No shared memory or shuffles: no TSan leg.)"""
     out = build_and_run(tmp_path, sanitizer, 'act_bwd_rgb_main.cpp', ACT_BWD_RGB_KERNELS, (), source='synth.cu')
     assert out.count('ok  ') == 3
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', ['plain', 'address'])
+def test_img_finish_kernels_on_the_cpu_shim(tmp_path, sanitizer):
+    """The tail of the fused ToRGB path (csrc/synth.cu img_finish4_kernel / img_finish_kernel: bias, clamp + saved mask, skip-image
+    upsample) against a float64 restatement; the kernel is picked as smc_img_finish picks it."""
+    out = build_and_run(tmp_path, sanitizer, 'img_finish_main.cpp', ['img_finish_kernel', 'img_finish4_kernel'], (), source='synth.cu')
+    assert out.count('ok  ') == 4
