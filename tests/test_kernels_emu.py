@@ -54,9 +54,9 @@ def extract(cu, common_cuh, kernels=KERNELS, host_functions=('attention_block_ro
 SANITIZERS = {'plain': ['-O2'],
               # pointer-overflow is off: kernels form `nullptr + offset` for an absent lo plane and never dereference it (fine on a device)
               # heap bounds of every global AND shared-memory access (the shim's shared memory is a heap block of exactly the launcher's size)
-              'address': ['-O1', '-g', '-fsanitize=address,undefined', '-fno-sanitize=pointer-overflow', '-fno-sanitize-recover=undefined'],
+              'address': ['-O2', '-g', '-fsanitize=address,undefined', '-fno-sanitize=pointer-overflow', '-fno-sanitize-recover=undefined'],
               # the shim's barriers are the only synchronisation, so a missing __syncthreads shows up as a data race (checked by removing one)
-              'thread': ['-O1', '-g', '-fsanitize=thread']}
+              'thread': ['-O2', '-g', '-fsanitize=thread']}
 
 
 def build_and_run(tmp_path, sanitizer, main_cpp, kernels, host_functions, source='vit.cu', argv=()):
@@ -133,7 +133,7 @@ RESAMPLE_KERNELS = ['resample_h_kernel', 'resample_v_kernel', 'resample_vT_kerne
 
 
 @pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
-@pytest.mark.parametrize('in_size,out_size,sanitizer', [(80, 36, 'plain'), (80, 36, 'address'), (20, 36, 'plain')])
+@pytest.mark.parametrize('in_size,out_size,sanitizer', [(80, 36, 'plain'), (40, 18, 'address'), (20, 36, 'plain')])
 def test_unprocess_kernels_on_the_cpu_shim(tmp_path, in_size, out_size, sanitizer):
     """``unprocess`` (find_direction.py:49-52) end to end on the CPU: the shipped resample kernels, launched in the C layer's order on the
     tables stylemc_b200/resample.py builds, against the oracle's F.interpolate(bicubic, antialias) forward and its autograd -- a
@@ -183,7 +183,7 @@ TORGB_KERNELS = ['@h8_to_f', '@f_to_h8', '@f_to_h8_split', '@ld8f', 'torgb_kerne
 
 
 @pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
-@pytest.mark.parametrize('sanitizer', list(SANITIZERS))
+@pytest.mark.parametrize('sanitizer', ['plain', 'address'])
 def test_torgb_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     """ToRGB + skip-image upsample + next-layer style multiply (csrc/synth.cu torgb1_kernel and the generic torgb_kernel; utils.py:45-49)
     against a float64 restatement, with the launch configurations of smc_torgb."""
