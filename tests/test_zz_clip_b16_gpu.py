@@ -3,7 +3,8 @@
 oracle/pin_reference.py from the reference's own init_clip_loss / compute_clip_loss) and against the whole-sequence attention
 kernels.  The kernels these tests exercise (attention_fwd_rows_kernel, attention_bwd_q_kernel, attention_bwd_kv_kernel) were
 written after the round-1 GPU budget was spent: on the CPU they run under tests/test_kernels_emu.py; this file is their first
-run on a device (named test_zz_* so it runs after the files that cover the measured path)."""
+run on a device (named test_zz_* so it runs after the files that cover the measured path).  The last two tests cover the other pieces
+added in the same window: the torch.library plugin operators and the mapping network (io.generate_w)."""
 import pytest
 import torch
 
