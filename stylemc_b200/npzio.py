@@ -1,4 +1,6 @@
-"""The reference's on-disk formats either side of the hot path and its optimisation loop.
+"""(Named npzio, not io: a module called io on sys.path would shadow the standard library when a script of this directory is run directly.)
+
+The reference's on-disk formats either side of the hot path and its optimisation loop.
 
 All files are ``np.savez`` archives with one key:
   ``w``  [M, num_ws, 512] fp32   W+ latents             written by generate_w.py:50-51, read by w_s_converter.py:75

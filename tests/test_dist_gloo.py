@@ -80,10 +80,10 @@ def test_two_rank_allreduce_equals_full_batch(tmp_path):
 
 
 def loop_worker(rank, world, port, outdir):
-    """io.find_direction on two ranks with a stand-in step: every rank must draw the same batch and take disjoint rows of it."""
+    """npzio.find_direction on two ranks with a stand-in step: every rank must draw the same batch and take disjoint rows of it."""
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.distributed.init_process_group('gloo', rank=rank, world_size=world)
-    from stylemc_b200 import direction, io
+    from stylemc_b200 import direction, npzio as io
     group = torch.distributed.group.WORLD
     S = torch.arange(11, dtype=torch.float32).view(11, 1, 1).expand(11, 26, 512).contiguous()      # row id in every element
     f = object.__new__(direction.DirectionFinder)

@@ -253,7 +253,7 @@ def test_npz_formats_and_find_direction_loop(tmp_path):
     generate_fromS.py:114,125) and the optimisation loop's bookkeeping (iteration count, cosine LR, batch slices, checkpoints,
     final file, resume) with a stand-in step function."""
     import numpy as np
-    from stylemc_b200 import direction, io
+    from stylemc_b200 import direction, npzio as io
     gen = torch.Generator().manual_seed(1)
     S = torch.randn(11, 26, 512, generator=gen)
     io.save_styles(tmp_path / 's.npz', S)
@@ -302,7 +302,7 @@ def test_npz_formats_and_find_direction_loop(tmp_path):
 
 def test_save_canvases_writes_the_reference_file_names(tmp_path):
     from PIL import Image
-    from stylemc_b200 import io
+    from stylemc_b200 import npzio as io
     canv = torch.randint(0, 256, (2, 16, 32, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(2))
     paths = io.save_canvases(canv, str(tmp_path), 'a happy face', first_index=7)
     assert [os.path.basename(p) for p in paths] == ['a_happy_face_007.jpeg', 'a_happy_face_008.jpeg']     # generate_fromS.py:205

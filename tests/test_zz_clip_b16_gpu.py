@@ -4,7 +4,7 @@ oracle/pin_reference.py from the reference's own init_clip_loss / compute_clip_l
 kernels.  The kernels these tests exercise (attention_fwd_rows_kernel, attention_bwd_q_kernel, attention_bwd_kv_kernel) were
 written after the round-1 GPU budget was spent: on the CPU they run under tests/test_kernels_emu.py; this file is their first
 run on a device (named test_zz_* so it runs after the files that cover the measured path).  The last two tests cover the other pieces
-added in the same window: the torch.library plugin operators and the mapping network (io.generate_w)."""
+added in the same window: the torch.library plugin operators and the mapping network (npzio.generate_w)."""
 import pytest
 import torch
 
@@ -147,7 +147,7 @@ def test_torch_library_plugin_ops_match_the_op_api():
 
 def test_generate_w_matches_oracle():
     """z -> W+ (generate_w.py:46-51) on the device: cuBLAS matmuls + the bias_act kernel for the 8 lrelu layers, against the CPU oracle."""
-    from stylemc_b200 import io, networks
+    from stylemc_b200 import networks, npzio as io
     kw = dict(seed=1, channel_base=1024, channel_max=64, mapping=True)
     ws = io.generate_w(networks.make_generator(32, **kw), [1, 2, 5], truncation_psi=0.7)
     ref = o_syn.generate_w(o_syn.make_generator(32, **kw), [1, 2, 5], truncation_psi=0.7)
