@@ -210,3 +210,11 @@ def test_img_finish_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     upsample) against a float64 restatement; the kernel is picked as smc_img_finish picks it."""
     out = build_and_run(tmp_path, sanitizer, 'img_finish_main.cpp', ['img_finish_kernel', 'img_finish4_kernel'], (), source='synth.cu')
     assert out.count('ok  ') == 4
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
+@pytest.mark.parametrize('sanitizer', ['plain', 'address'])
+def test_vit_token_kernels_on_the_cpu_shim(tmp_path, sanitizer):
+    """patchify / unpatchify for patch sizes 32, 16 (the ViT-B/16 tower) and 8, class-token assembly and the text embedding lookup."""
+    out = build_and_run(tmp_path, sanitizer, 'vit_tokens_main.cpp', ['patchify_kernel', 'unpatchify_kernel', 'assemble_tokens_kernel', 'embed_text_kernel'], ())
+    assert out.count('ok  ') == 4
