@@ -388,15 +388,84 @@ def pin_config1(R, model, out):
     out['img_down'] = torch.nn.functional.avg_pool2d(r['img'], 8).numpy()
 
 
+CONFIG4_BATCH = 3        # odd on purpose: micro_batch=2 on the GPU side is then a ragged 2 + 1 split
+
+
+def pin_config4(R, model, out):
+    """BASELINE configs[3] (the benchmarked network): FFHQ-1024 config-f net, one find_direction step through the reference's real
+    ``utils.generate_image`` + ``compute_clip_loss`` (find_direction.py:306-336), plus the oracle's float64 gradient as the
+    reference's own error bar.  Images are stored as 64x64 centre crops and 8x average pools (the full fp32 images are 38 MB)."""
+    print(f'config 4: FFHQ-1024 config-f net, batch {CONFIG4_BATCH}, one find_direction step through the reference (CPU)')
+    G_ref = synthesis.make_generator(1024, seed=0)
+    G_ora = synthesis.make_generator(1024, seed=0)
+    ws = torch.randn(CONFIG4_BATCH, G_ref.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(40))
+    S, shapes = R.utils.get_styles(G_ref, ws, R.utils.split_ws(G_ref, ws), torch.device('cpu'))
+    synthesis.get_temp_shapes(G_ora)
+    delta = 0.1 * torch.randn(1, 8, 512, generator=torch.Generator().manual_seed(41))
+    k = direction.RESOLUTION_TO_K[1024]
+    r = reference_step(R, G_ref, shapes, S, delta, k)
+    loss_fn = direction.CLIPLoss(model, vit.synthetic_tokens('pos'), vit.synthetic_tokens('neg'))
+    o = direction.direction_step(G_ora, shapes, loss_fn, S, delta, k)
+    close(o['img'], r['img'], 0, 'config4 img')
+    close(o['loss'], r['loss'], 1e-6, 'config4 loss')
+    rel = ((o['grad'] - r['grad']).norm() / r['grad'].norm()).item()
+    print(f'  grad rel-l2 {rel:.3e}, |grad| {r["grad"].norm():.3e}; img std {r["img"].std():.3f} '
+          f'frac |img|>1: {(r["img"].abs() > 1).float().mean():.4f}')
+    assert rel < 1e-5
+    # float64 run of the oracle: how far the fp32 reference itself is from the exact gradient
+    G64 = synthesis.make_generator(1024, seed=0).double()
+    synthesis.get_temp_shapes(G64)
+    m64 = vit.CLIP(params=model.p, cfg=model.cfg, dtype=torch.float64)
+    if True:
+        l64 = direction.CLIPLoss(m64, vit.synthetic_tokens('pos'), vit.synthetic_tokens('neg'))
+        o64 = direction.direction_step(G64, shapes, l64, S.double(), delta.double(), k)
+        bar = ((r['grad'].double() - o64['grad']).norm() / o64['grad'].norm()).item()
+        print(f'  fp32 reference vs float64 oracle: grad rel-l2 {bar:.3e}, loss rel {abs(r["loss"].item() - o64["loss"].item()) / abs(o64["loss"].item()):.3e}')
+        out['grad_fp64'], out['loss_fp64'] = o64['grad'].numpy(), o64['loss'].numpy()
+    out['ws'], out['delta'], out['loss'], out['clip_loss'] = ws.numpy(), delta.numpy(), r['loss'].numpy(), r['clip_loss'].numpy()
+    out['grad'] = r['grad'].numpy()
+    for tag, im in (('img', r['img']), ('original', r['original_img'])):
+        out[tag + '_crop'] = im[:, :, 480:544, 480:544].numpy()
+        out[tag + '_down'] = torch.nn.functional.avg_pool2d(im, 8).numpy()
+        out[tag + '_mean_std'] = np.array([im.mean().item(), im.std().item()])
+    # generate_fromS.py:147-175,206 on the same network: uint8 canvas original | edited of the first two styles, change_power 2.5,
+    # stored as a 16-strided sample plus a 128-row x 256-column full-resolution window around the seam
+    styles_direction = torch.zeros(1, R.fd.N_STYLE_CHANNELS, 512)
+    styles_direction[:, R.fd.S_TRAINABLE_SPACE_CHANNELS] = delta
+    canv = []
+    with torch.no_grad():
+        for i in range(2):
+            halves = []
+            for g in (0, 2.5):
+                _, img = R.utils.generate_image(G_ref, 100, S[[i]] + styles_direction * g, shapes, 'const', torch.device('cpu'))
+                halves.append((img.permute(0, 2, 3, 1) * 127.5 + 128).clamp(0, 255)[0].to(torch.uint8))
+            canv.append(torch.cat(halves, dim=1))
+    canv = torch.stack(canv)                    # [2, 1024, 2048, 3]
+    out['canvas_power'] = np.array(2.5)
+    out['canvas_strided'] = canv[:, ::16, ::16].numpy()
+    out['canvas_window'] = canv[:, 448:576, 896:1152].numpy()
+    out['canvas_sum'] = canv.long().sum(dim=(1, 2)).numpy()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--check', action='store_true', help='verify only, do not write fixtures')
     ap.add_argument('--skip-config1', action='store_true')
+    ap.add_argument('--skip-config4', action='store_true')
+    ap.add_argument('--only-config4', action='store_true', help='(re)write only config4.npz')
     ap.add_argument('--only-double', action='store_true', help='(re)write only clip_b16.npz and step64_double.npz')
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     R = import_reference()
-    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'config1')}
+    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'config1', 'config4')}
+    if args.only_config4:
+        model = vit.CLIP(seed=0, cfg=vit.VIT_B32)
+        install_stub_clip(R, model)
+        pin_config4(R, model, fx['config4'])
+        if not args.check:
+            np.savez_compressed(os.path.join(GOLD, 'config4.npz'), **fx['config4'])
+            print('wrote config4.npz', f'{os.path.getsize(os.path.join(GOLD, "config4.npz")) / 1e6:.2f} MB')
+        return
     pin_ops(R, fx['ops'])
     pin_modconv_e4e(R, fx['ops'])
     G_ref, G_ora, S, shapes = pin_driver(R, fx['synth64'])
@@ -406,6 +475,8 @@ def main():
     pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, fx['step64_double'])
     if not args.skip_config1 and not args.only_double:
         pin_config1(R, model, fx['config1'])
+    if not args.skip_config4 and not args.only_double:
+        pin_config4(R, model, fx['config4'])
     if args.only_double:
         fx = {k: fx[k] for k in ('clip_b16', 'step64_double')}
     if not args.check:

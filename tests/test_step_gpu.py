@@ -61,6 +61,35 @@ def test_step_config1_256px_golden(golden):
     check_step(f, g, S, 'config1')
 
 
+@pytest.mark.parametrize('mode', ['micro_batch_2', 'one_pass_overlap', 'one_pass_serial'])
+def test_step_config4_1024px_golden(golden, mode):
+    """BASELINE.json configs[3], the benchmarked network: FFHQ-1024 config-f, 3 seeds, one step against the reference's own loop body
+    (tests/golden/config4.npz, oracle/pin_reference.py::pin_config4: real utils.generate_image + compute_clip_loss on the CPU).
+    Once cut into micro-batches (ragged 2 + 1), once as bench.py runs it (one pass, original-image branch on the side stream), once
+    with both branches on one stream.  The fp32 reference itself sits 3.3e-4 from the float64 gradient (``grad_fp64``)."""
+    g = golden('config4')
+    G = o_syn.make_generator(1024, seed=0)
+    ws = torch.as_tensor(g['ws'])
+    S, shapes = o_syn.get_styles(G, ws, o_syn.split_ws(G, ws))
+    f = finder(G, 1024, micro_batch=2 if mode == 'micro_batch_2' else 64)
+    f.overlap = mode != 'one_pass_serial'
+    f.delta.copy_(torch.as_tensor(g['delta']).cuda())
+    for tag, styles in (('img', S.cuda() + f.direction()), ('original', S.cuda())):
+        _, img, _ = f.engine.forward(styles, until_k=f.until_k)
+        assert img.shape == (3, 3, 1024, 1024)
+        e_crop = (img[:, :, 480:544, 480:544].cpu() - torch.as_tensor(g[tag + '_crop'])).abs().max().item()
+        e_down = (torch.nn.functional.avg_pool2d(img, 8).cpu() - torch.as_tensor(g[tag + '_down'])).abs().max().item()
+        mean, std = float(g[tag + '_mean_std'][0]), float(g[tag + '_mean_std'][1])
+        print(f'config4 {tag}: crop max-abs err {e_crop:.2e}, 8x-pooled max-abs err {e_down:.2e}')
+        assert e_crop <= 1e-2 and e_down <= 1e-2
+        assert abs(img.mean().item() - mean) <= 1e-4 and abs(img.std().item() - std) <= 1e-4
+        del img
+    check_step(f, g, S, f'config4 {mode}')
+    g64 = torch.as_tensor(g['grad_fp64'])[0].float()
+    ref_bar = ((torch.as_tensor(g['grad'])[0] - g64).norm() / g64.norm()).item()
+    print(f'config4: fp32 reference vs float64 oracle grad rel-l2 {ref_bar:.2e}')
+
+
 def test_three_step_trajectory_vs_oracle():
     """Three consecutive optimisation steps (cosine LR, SGD) on the 64-px network track the CPU oracle's trajectory."""
     from oracle import direction as o_dir
