@@ -20,7 +20,39 @@
 
 namespace smc {
 
-constexpr int kNumSMs = 148;
+constexpr int kNumSMs = 148;          // B200; grid-size heuristics of the streaming kernels (caps, not correctness)
+constexpr int kMaxDevices = 64;
+
+// SM count of the CURRENT device (persistent-kernel grids), queried once per device.
+inline int sm_count() {
+  static int cached[kMaxDevices] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return kNumSMs;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : kNumSMs;
+  }
+  return cached[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember what each device has been configured with
+// (one table per kernel instantiation: `state` is a function-local static of the launcher).
+struct SmemOptIn {
+  size_t configured[kMaxDevices] = {0};
+};
+template <typename K>
+inline cudaError_t smem_opt_in(SmemOptIn& state, K kernel, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (bytes > state.configured[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    state.configured[dev] = bytes;
+  }
+  return cudaSuccess;
+}
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -766,12 +766,8 @@ void hconv_config(int key, int value) {
 
 template <int BN, int KC, int MODE>
 static int hc_launch(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(hconv_kernel<BN, KC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
+  static SmemOptIn opt_in;
+  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE>, smem); e != cudaSuccess) return (int)e;
   hconv_kernel<BN, KC, MODE><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
@@ -1095,7 +1091,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return SMC_EDRIVER;
   }
-  const int max_grid = g_hconv_grid > 0 ? g_hconv_grid : kNumSMs;
+  const int max_grid = g_hconv_grid > 0 ? g_hconv_grid : sm_count();
   const int grid = p.super_tiles < max_grid ? (int)p.super_tiles : max_grid;
   if (KC == 64) {
     if (BN == 128) return hc_launch_x<128, 64>(mode, ma, mb, p, grid, smem, st);

@@ -272,12 +272,8 @@ static int pow2_ceil(int v) {
 template <int BN, int KC, int STAGES, bool ACC>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const IgParams& p, int grid, cudaStream_t st) {
   constexpr int SMEM = STAGES * (128 * KC * 2 + BN * KC * 2) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, KC, STAGES, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static SmemOptIn opt_in;
+  if (cudaError_t e = smem_opt_in(opt_in, igemm_kernel<BN, KC, STAGES, ACC>, SMEM); e != cudaSuccess) return (int)e;
   igemm_kernel<BN, KC, STAGES, ACC><<<grid, 192, SMEM, st>>>(ma, mb, p);
   SMC_LAUNCH_CHECK();
   return SMC_OK;

@@ -68,12 +68,17 @@ def shard_rows(n_total, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def allreduce_step(grad, part, group):
+def allreduce_step(grad, part, group, local_rows=None):
     """Sum the shard gradients [rows, 512] and the loss partial sums over the ranks in ONE collective (16 KiB + 4 B).  Because
     every rank divides by the GLOBAL seed count (loss_and_grad's ``global_count``), the sum is exactly the full-batch mean
-    gradient of clip_loss.py:34, also for ragged shards."""
-    buf = torch.cat([grad.reshape(-1), part.reshape(-1)])
+    gradient of clip_loss.py:34, also for ragged shards.  When the caller does not know the global count, ``local_rows`` (this
+    rank's row count) rides in the same buffer: ``grad`` / ``part`` must then be UN-normalised sums (count 1) and the result is
+    divided by the all-reduced row count on the device -- ragged or empty shards included, no guess, no host sync."""
+    tail = [] if local_rows is None else [torch.full([1], float(local_rows), dtype=grad.dtype, device=grad.device)]
+    buf = torch.cat([grad.reshape(-1), part.reshape(-1)] + tail)
     torch.distributed.all_reduce(buf, op=torch.distributed.ReduceOp.SUM, group=group)
+    if local_rows is not None:
+        buf = buf[:-1] / buf[-1]
     return buf[:grad.numel()].reshape(grad.shape), buf[grad.numel():]
 
 
@@ -129,6 +134,16 @@ class DirectionFinder:
         if tuple(d.shape) != (1, N_STYLE_CHANNELS, synthesis.STYLE_WIDTH):
             raise RuntimeError(f'direction must be [1, {N_STYLE_CHANNELS}, {synthesis.STYLE_WIDTH}], got {tuple(d.shape)}')
         self.delta.copy_(d[:, self.rows].to(self.device))
+
+    def seed_delta(self, scale=1e-2, seed=0):
+        """Replace an all-zero delta by ``scale * N(0, 1)`` drawn from a seeded HOST generator (identical on every rank).
+
+        At delta == 0 (find_direction.py:270, the default start) the edited and the original image are the same tensor, so
+        ``tgt - src`` is exactly 0 and the reference's loss is 0/0 = NaN (clip_loss.py:27-28); it only gets off the ground where
+        cuDNN's non-determinism makes the two passes differ in the last bit.  ``smc_clip_loss`` gives such a sample cos = 0 and a
+        zero gradient, and the L2 gradient is 0 too, so SGD would stay at 0 forever: the loop driver calls this instead."""
+        g = torch.Generator().manual_seed(seed)
+        self.delta.copy_((scale * torch.randn(self.delta.shape, generator=g)).to(self.device))
 
     def _encode_original(self, s):
         """CLIP embeddings of the un-edited images (find_direction.py:312: no gradient), one per tower."""
@@ -188,10 +203,14 @@ class DirectionFinder:
     def step(self, styles, lr=None, global_count=None):
         """One optimisation step on this rank's shard.  Returns a dict of device scalars (loss, clip_loss, l2_loss, grad_norm)."""
         lr = self.lr if lr is None else lr
-        count = styles.shape[0] * self.world if global_count is None else global_count
-        grad, part = self.loss_and_grad(styles, count)
-        if self.world > 1:
-            grad, part = allreduce_step(grad, part, self.group)
+        if self.world > 1 and global_count is None:
+            # shard sizes of the other ranks are unknown (ragged / empty shards): sum un-normalised, divide by the all-reduced count
+            grad, part = self.loss_and_grad(styles, 1)
+            grad, part = allreduce_step(grad, part, self.group, local_rows=styles.shape[0])
+        else:
+            grad, part = self.loss_and_grad(styles, styles.shape[0] if global_count is None else global_count)
+            if self.world > 1:
+                grad, part = allreduce_step(grad, part, self.group)
         numel = self.delta.numel()
         l2 = self.l2_reg_coef * self.delta.square().mean()                            # find_direction.py:190-191 (batch independent)
         clip_loss = self.clip_loss_coef * sum(w for _, _, w in self.clips) + part     # sum over towers of w * coef * (count - sum cos) / count

@@ -11,6 +11,7 @@ All files are ``np.savez`` archives with one key:
 """
 import math
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -69,14 +70,18 @@ def save_direction(path, styles_direction):
 
 
 def find_direction(finder, styles_array, batch_size, n_epochs, outdir=None, text_prompt=None, resume=None, seed=0, checkpoint_every=1000,
-                   log=None):
+                   log=None, zero_init='perturb'):
     """The loop of find_direction.py:285-351 around ``DirectionFinder.step``: ``ceil(M / batch) * n_epochs`` iterations, a random
     batch per iteration (:303-304), cosine learning rate (:298-301), ``direction_last.npz`` every ``checkpoint_every`` iterations
     (:333-334), ``direction_<prompt>.npz`` at the end (:349-351); ``resume`` loads a saved direction (:266-270).
 
     The batch index is drawn from ``np.random.RandomState(seed)``, not the global generator the reference uses: in a data-parallel run
     every rank must draw the same index.  With several ranks each one takes its rows of the batch (``direction.shard_rows``) and only
-    rank 0 writes files.  Returns the final direction [1, 26, 512] (host)."""
+    rank 0 writes files.  Returns the final direction [1, 26, 512] (host).
+
+    ``zero_init``: what to do when the run would start from delta == 0 (no ``resume``), where the directional loss is 0/0 -- NaN in the
+    reference (clip_loss.py:27-28), cos = 0 with a zero gradient here, i.e. a run that never moves: ``'perturb'`` (default) seeds
+    delta with ``DirectionFinder.seed_delta`` and warns, ``'raise'`` raises, ``'keep'`` runs as is."""
     from . import direction as smc_dir
     n_items = styles_array.shape[0]
     num_batches = math.ceil(n_items / batch_size)
@@ -85,6 +90,15 @@ def find_direction(finder, styles_array, batch_size, n_epochs, outdir=None, text
     rank = torch.distributed.get_rank(finder.group) if finder.world > 1 else 0
     if resume is not None:
         finder.load_direction(load_direction(resume))
+    if zero_init not in ('perturb', 'raise', 'keep'):
+        raise ValueError("zero_init must be 'perturb', 'raise' or 'keep'")
+    if zero_init != 'keep' and total > 0 and not bool(finder.delta.any()):
+        msg = ('find_direction starts from delta == 0: the edited and the original image are identical, the directional CLIP loss is '
+               '0/0 (NaN in the reference, clip_loss.py:27-28) and its gradient here is 0, so the direction would never move')
+        if zero_init == 'raise':
+            raise RuntimeError(msg + "; pass resume=... or zero_init='perturb'")
+        warnings.warn(msg + '; seeding delta with DirectionFinder.seed_delta()')
+        finder.seed_delta()
     if outdir is not None and rank == 0:
         os.makedirs(outdir, exist_ok=True)
     for it in range(1, total + 1):

@@ -105,6 +105,7 @@ def _functions(dim, act, alpha, gain, clamp):
                 dy = _dense(dy)
             else:
                 dy = dy.contiguous(memory_format=torch.channels_last) if (ref.ndim > 2 and ref.stride(1) == 1) else dy.contiguous()
+            ctx.memory_format = torch.channels_last if (dy.ndim > 2 and dy.stride(1) == 1) else torch.contiguous_format   # bias_act.py:171
             dx = _launch(dy, b, x, y, None, 1, dim, spec, alpha, gain, clamp)
             ctx.save_for_backward(dy if spec.has_2nd_grad else None, x, b, y)
             return dx
@@ -112,7 +113,7 @@ def _functions(dim, act, alpha, gain, clamp):
         @staticmethod
         def backward(ctx, d_dx):
             dy, x, b, y = ctx.saved_tensors
-            d_dx = d_dx.contiguous()
+            d_dx = d_dx.contiguous(memory_format=ctx.memory_format)          # bias_act.py:184: the layout of the saved x / y
             d_dy = d_x = d_b = None
             if ctx.needs_input_grad[0]:
                 d_dy = BiasActGrad.apply(d_dx, x, b, y)

@@ -18,8 +18,10 @@ def no_weight_gradients():
     global weight_gradients_disabled
     old = weight_gradients_disabled
     weight_gradients_disabled = True
-    yield
-    weight_gradients_disabled = old
+    try:
+        yield
+    finally:                          # an exception inside the block must not leave the switch stuck
+        weight_gradients_disabled = old
 
 
 def _pair(v):

@@ -61,7 +61,9 @@ _sep_cache = {}
 
 def _separable_factors(f):
     """(fy[0..3], fx[0..3]) with f[i][j] == fy[i] * fx[j] for a rank-1 4x4 filter (setup_filter([1,3,3,1]) is one), else None.
-    The filter lives on the device; the answer is cached per filter tensor so the host copy happens once."""
+    The filter lives on the device; the answer is cached per filter tensor so the host copy happens once.  The cache entry keeps
+    the filter tensor alive: its address can then not be handed to another filter by the caching allocator (a freed 4x4 filter's
+    address is what the next 4x4 filter gets, with ``_version`` 0 again), and an in-place change bumps ``_version``."""
     if tuple(f.shape) != (4, 4):
         return None
     key = (f.data_ptr(), f._version, f.device)
@@ -75,8 +77,8 @@ def _separable_factors(f):
                 res = [float(v) for v in fy] + [float(v) for v in fx]
         if len(_sep_cache) > 64:
             _sep_cache.clear()
-        _sep_cache[key] = res
-    return _sep_cache[key]
+        _sep_cache[key] = (res, f)
+    return _sep_cache[key][0]
 
 
 def _launch(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):

@@ -59,9 +59,11 @@ def worker(rank, world, port, out):
     G, shapes, loss_fn, S, delta = make()
     lo, hi = direction.shard_rows(S.shape[0], rank, world)              # 5 seeds over 2 ranks: 3 + 2 (ragged)
     grad, part = shard_loss_and_grad(G, shapes, loss_fn, S[lo:hi], delta, S.shape[0])
+    # global count unknown to the ranks (DirectionFinder.step without global_count): un-normalised sums + the row count in the same buffer
+    grad_u, part_u = direction.allreduce_step(grad * S.shape[0], part * S.shape[0], torch.distributed.group.WORLD, local_rows=hi - lo)
     grad, part = direction.allreduce_step(grad, part, torch.distributed.group.WORLD)
     if rank == 0:
-        torch.save(dict(grad=grad, part=part, span=(lo, hi)), out)
+        torch.save(dict(grad=grad, part=part, span=(lo, hi), grad_u=grad_u, part_u=part_u), out)
     torch.distributed.destroy_process_group()
 
 
@@ -77,6 +79,8 @@ def test_two_rank_allreduce_equals_full_batch(tmp_path):
     assert got['span'] == (0, 3)
     assert ((got['grad'] - grad).norm() / grad.norm()).item() <= 1e-5
     assert abs(got['part'].item() - part.item()) <= 1e-6
+    assert ((got['grad_u'] - grad).norm() / grad.norm()).item() <= 1e-5        # ragged 3 + 2 shards, count all-reduced with the data
+    assert abs(got['part_u'].item() - part.item()) <= 1e-6
 
 
 def loop_worker(rank, world, port, outdir):
@@ -102,7 +106,7 @@ def loop_worker(rank, world, port, outdir):
         f.delta += rows.sum()
         return dict(loss=torch.tensor(0.0))
     f.step = step
-    final = io.find_direction(f, S, batch_size=4, n_epochs=2, outdir=outdir, text_prompt='p', seed=5)
+    final = io.find_direction(f, S, batch_size=4, n_epochs=2, outdir=outdir, text_prompt='p', seed=5, zero_init='keep')
     if rank == 0:
         torch.save(dict(log=log, final=final), os.path.join(outdir, 'log.pt'))
     else:

@@ -280,7 +280,7 @@ def test_npz_formats_and_find_direction_loop(tmp_path):
         return dict(loss=torch.tensor(0.0))
     f.step = step
     out = tmp_path / 'run'
-    final = io.find_direction(f, S, batch_size=4, n_epochs=5, outdir=str(out), text_prompt='a happy face', seed=3, checkpoint_every=6)
+    final = io.find_direction(f, S, batch_size=4, n_epochs=5, outdir=str(out), text_prompt='a happy face', seed=3, checkpoint_every=6, zero_init='keep')
     total = math.ceil(11 / 4) * 5                                                     # find_direction.py:286-287
     assert len(calls) == total
     rng = np.random.RandomState(3)
@@ -298,6 +298,24 @@ def test_npz_formats_and_find_direction_loop(tmp_path):
     calls.clear()
     io.find_direction(f, S, batch_size=11, n_epochs=1, resume=str(out / 'direction_last.npz'))
     assert len(calls) == 1 and f.delta[0, 0, 0].item() == 12.0
+    # start from delta == 0 (find_direction.py:270): the directional loss is 0/0 there (NaN in the reference, clip_loss.py:27-28; zero
+    # gradient in smc_clip_loss), so the loop seeds delta -- or raises / keeps it when asked to
+    f.delta.zero_()
+    calls.clear()
+    with pytest.raises(RuntimeError, match='delta == 0'):
+        io.find_direction(f, S, batch_size=11, n_epochs=1, zero_init='raise')
+    assert not calls
+    seen = []
+    f.step = lambda styles, lr=None, global_count=None: seen.append(f.delta.clone()) or dict(loss=torch.tensor(0.0))
+    with pytest.warns(UserWarning, match='delta == 0'):
+        io.find_direction(f, S, batch_size=11, n_epochs=1)
+    assert len(seen) == 1 and seen[0].abs().min().item() > 0 and 0.005 < seen[0].std().item() < 0.02
+    g = object.__new__(direction.DirectionFinder)
+    g.device, g.delta = torch.device('cpu'), torch.zeros(1, 8, 512)
+    g.seed_delta()
+    assert torch.equal(g.delta, seen[0])                                              # seeded on the host: the same on every rank
+    with pytest.raises(ValueError):
+        io.find_direction(f, S, batch_size=11, n_epochs=1, zero_init='maybe')
 
 
 def test_save_canvases_writes_the_reference_file_names(tmp_path):

@@ -113,6 +113,34 @@ def test_three_step_trajectory_vs_oracle():
         assert d_rel <= 2e-3
 
 
+def test_delta_zero_is_degenerate_and_the_loop_leaves_it():
+    """delta == 0 (the reference's default start, find_direction.py:270): edited == original, so tgt - src == 0 and the reference's
+    loss is 0/0 = NaN (clip_loss.py:27-28) -- pinned here through the oracle.  smc_clip_loss defines such a sample as cos = 0 with a
+    zero gradient (finite, but SGD would never leave 0), so npzio.find_direction seeds delta (DirectionFinder.seed_delta) and a
+    run from the default init moves."""
+    import warnings
+    from oracle import direction as o_dir
+    from stylemc_b200 import npzio
+    G = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    ws = torch.randn(4, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(21))
+    S, shapes = o_syn.get_styles(G, ws, o_syn.split_ws(G, ws))
+    loss_fn = o_dir.CLIPLoss(o_vit.CLIP(o_vit.random_clip_params(seed=0)), o_vit.synthetic_tokens('pos'), o_vit.synthetic_tokens('neg'))
+    r = o_dir.direction_step(G, shapes, loss_fn, S[:2], torch.zeros(1, 8, 512), 100)
+    assert torch.isnan(r['loss']) and torch.isnan(r['grad']).all()                  # the reference's behaviour
+    f = finder(G, 64)
+    out = f.step(S.cuda(), lr=1.0)
+    assert out['clip_loss'].item() == 1.0 and out['grad'].abs().max().item() == 0.0 and f.delta.abs().max().item() == 0.0
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        final = npzio.find_direction(f, S, batch_size=4, n_epochs=3, seed=0)
+    assert any('delta == 0' in str(x.message) for x in w)
+    seeded = finder(G, 64)
+    seeded.seed_delta()
+    moved = (final[0, f.rows] - seeded.delta.cpu()[0]).norm().item()
+    print(f'|delta| after 3 iterations from the seeded start: {final.norm().item():.3f} (moved by {moved:.3f})')
+    assert torch.isfinite(final).all() and moved > 1e-2
+
+
 def test_full_size_1024_properties():
     """BASELINE configs[3] network (1024 px config-f) at full resolution, through size-independent properties -- the CPU oracle needs
     minutes per image there.  (1) The step is invariant to how the seed batch is cut into micro-batches (the gradient is a sum over
