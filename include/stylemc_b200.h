@@ -238,6 +238,16 @@ int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, flo
  * the reference concatenates original | edited along the width, :206). */
 int smc_img_to_uint8(const float* img, unsigned char* out, int n, int h, int w, int canvas_w, int x_off, void* stream);
 
+/* ---- fma.py:15-58 as a stand-alone op (on the fused path the multiply-add is the GEMM epilogue) -----------------------
+ * smc_fma: out = a * b + c over the broadcast index space `shape` (4 sizes, leading 1s for lower ranks); stride_* are ELEMENT strides
+ * of each operand viewed in that space, 0 on the axes it is broadcast along (fma.py:22, torch.addcmul); out is contiguous.
+ * smc_fma_reduce: the "un-broadcast" of the backward (fma.py:36-43,49-58): out[kept] = sum over the reduced axes of x * y (y may be
+ * NULL: plain sum); `shape` is the full space, stride_out is 0 exactly on the axes that are summed.  Host pointers for the arrays. */
+int smc_fma(const void* a, const void* b, const void* c, void* out, int dtype, const int64_t* shape, const int64_t* stride_a,
+            const int64_t* stride_b, const int64_t* stride_c, void* stream);
+int smc_fma_reduce(const void* x, const void* y, void* out, int dtype, const int64_t* shape, const int64_t* stride_x,
+                   const int64_t* stride_y, const int64_t* stride_out, void* stream);
+
 /* ---- optimiser -----------------------------------------------------------------------------------
  * delta -= lr * (grad * grad_scale + l2_scale * delta)   (SGD, no momentum; L2 term of find_direction.py:190-191) */
 int smc_sgd_step(float* delta, const float* grad, int64_t numel, float lr, float grad_scale, float l2_scale, void* stream);

@@ -132,6 +132,25 @@ def pin_ops(R, out):
         out[name + '.x'], out[name + '.w'], out[name + '.y'] = x.numpy(), w.numpy(), yr.numpy()
     a, bb, cc = torch.randn(2, 3, 4, 4, generator=g), torch.randn(2, 3, 1, 1, generator=g), torch.randn(4, 4, generator=g)
     close(conv.fma(a, bb, cc), R.fma.fma(a, bb, cc), 0, 'fma')
+    # fma.py:15-58 forward + broadcast-aware backward through the reference's own autograd.Function
+    ar, br, cr = (t.clone().requires_grad_(True) for t in (a, bb, cc))
+    dy = torch.randn(2, 3, 4, 4, generator=g)
+    yr = R.fma.fma(ar, br, cr)
+    yr.backward(dy)
+    out['fma.a'], out['fma.b'], out['fma.c'], out['fma.dy'], out['fma.y'] = a.numpy(), bb.numpy(), cc.numpy(), dy.numpy(), yr.detach().numpy()
+    out['fma.da'], out['fma.db'], out['fma.dc'] = ar.grad.numpy(), br.grad.numpy(), cr.grad.numpy()
+    # the conv2d_gradfix entry points (conv2d_gradfix.py:35-43; pass-through to F.conv2d / F.conv_transpose2d on this torch)
+    from torch_utils.ops import conv2d_gradfix as ref_gradfix
+    xg, wg, bg = torch.randn(2, 32, 9, 9, generator=g), torch.randn(32, 32, 3, 3, generator=g), torch.randn(32, generator=g)
+    out['gradfix.x'], out['gradfix.w'], out['gradfix.bias'] = xg.numpy(), wg.numpy(), bg.numpy()
+    out['gradfix.conv2d'] = ref_gradfix.conv2d(xg, wg, bias=bg, padding=1).numpy()
+    wt = torch.randn(32, 32, 3, 3, generator=g)                       # conv_transpose2d weight: [in, out, kh, kw]
+    out['gradfix.wt'] = wt.numpy()
+    out['gradfix.conv_transpose2d'] = ref_gradfix.conv_transpose2d(xg, wt, stride=2).numpy()
+    xr_ = xg.clone().requires_grad_(True)
+    dyc = torch.randn(2, 32, 9, 9, generator=g)
+    ref_gradfix.conv2d(xr_, wg, padding=1).backward(dyc)
+    out['gradfix.dy'], out['gradfix.dx'] = dyc.numpy(), xr_.grad.numpy()
 
     # modulated_conv2d: upstream absent; self-consistency fused vs non-fused (7e-7)
     x = torch.randn(3, 8, 6, 6, generator=g)
@@ -453,6 +472,7 @@ def main():
     ap.add_argument('--skip-config1', action='store_true')
     ap.add_argument('--skip-config4', action='store_true')
     ap.add_argument('--only-config4', action='store_true', help='(re)write only config4.npz')
+    ap.add_argument('--only-ops', action='store_true', help='(re)write only ops.npz')
     ap.add_argument('--only-double', action='store_true', help='(re)write only clip_b16.npz and step64_double.npz')
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
@@ -468,6 +488,11 @@ def main():
         return
     pin_ops(R, fx['ops'])
     pin_modconv_e4e(R, fx['ops'])
+    if args.only_ops:
+        if not args.check:
+            np.savez_compressed(os.path.join(GOLD, 'ops.npz'), **fx['ops'])
+            print('wrote ops.npz')
+        return
     G_ref, G_ora, S, shapes = pin_driver(R, fx['synth64'])
     model = pin_clip(R, fx['clip'])
     model_b16 = pin_clip(R, fx['clip_b16'], vit.VIT_B16, B16_SEED, 'ViT-B/16')

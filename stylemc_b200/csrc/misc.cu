@@ -28,13 +28,177 @@ __global__ void __launch_bounds__(256) img_to_uint8_kernel(const float* __restri
     }
   }
 }
+// Same, four pixels per thread: one 16-byte load per colour plane, twelve output bytes as three aligned 32-bit stores
+// (needs W % 4 == 0, canvas_w % 4 == 0, x_off % 4 == 0 and 16-byte aligned planes; a warp then writes 384 contiguous bytes).
+__device__ __forceinline__ unsigned img_u8(float v) { return (unsigned)fminf(fmaxf(fmaf(v, 127.5f, 128.f), 0.f), 255.f); }
+__global__ void __launch_bounds__(256) img_to_uint8_v4_kernel(const float* __restrict__ img, unsigned char* __restrict__ out, int N, int H, int W4,
+                                                              int canvas_w, int x_off) {
+  const long long total = (long long)N * H * W4;
+  const long long plane = (long long)H * W4;          // in float4 units
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x4 = (int)(i % W4);
+    const long long t = i / W4;
+    const int y = (int)(t % H);
+    const long long n = t / H;
+    const float4* src = reinterpret_cast<const float4*>(img) + (n * 3 * H + y) * (long long)W4 + x4;
+    const uint4 ur = ld_stream(src), ug = ld_stream(src + plane), ub = ld_stream(src + 2 * plane);
+    const float r[4] = {__uint_as_float(ur.x), __uint_as_float(ur.y), __uint_as_float(ur.z), __uint_as_float(ur.w)};
+    const float g[4] = {__uint_as_float(ug.x), __uint_as_float(ug.y), __uint_as_float(ug.z), __uint_as_float(ug.w)};
+    const float b[4] = {__uint_as_float(ub.x), __uint_as_float(ub.y), __uint_as_float(ub.z), __uint_as_float(ub.w)};
+    unsigned by[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { by[3 * k] = img_u8(r[k]); by[3 * k + 1] = img_u8(g[k]); by[3 * k + 2] = img_u8(b[k]); }
+    unsigned* o = reinterpret_cast<unsigned*>(out + ((n * H + y) * (long long)canvas_w + x_off + 4 * x4) * 3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = by[4 * k] | (by[4 * k + 1] << 8) | (by[4 * k + 2] << 16) | (by[4 * k + 3] << 24);
+  }
+}
+
+// ---- fma.py:15-58 as stand-alone kernels: out = a * b + c over a broadcast 4-D index space, and the "un-broadcast" of its
+// backward (sum of x * y over the axes broadcasting expanded).  Element strides; 0 marks a broadcast / reduced axis.
+struct FmaDims {
+  long long size[4];
+  long long sa[4], sb[4], sc[4];
+};
+template <typename T, typename ACC>
+__global__ void __launch_bounds__(256) fma_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, T* __restrict__ out,
+                                                      FmaDims d, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const long long i3 = t % d.size[3]; t /= d.size[3];
+    const long long i2 = t % d.size[2]; t /= d.size[2];
+    const long long i1 = t % d.size[1];
+    const long long i0 = t / d.size[1];
+    const ACC va = (ACC)a[i0 * d.sa[0] + i1 * d.sa[1] + i2 * d.sa[2] + i3 * d.sa[3]];
+    const ACC vb = (ACC)b[i0 * d.sb[0] + i1 * d.sb[1] + i2 * d.sb[2] + i3 * d.sb[3]];
+    const ACC vc = (ACC)c[i0 * d.sc[0] + i1 * d.sc[1] + i2 * d.sc[2] + i3 * d.sc[3]];
+    out[i] = (T)(va * vb + vc);           // contracted to one FMA (torch.addcmul rounds the product for fp32; the difference is < 1 ulp)
+  }
+}
+// out[kept index] = sum over the reduced axes of x * y (y optional).  size = full shape, sa = x strides, sb = y strides,
+// sc = out strides (0 on reduced axes).  One block per output element when the reduction is long, else one thread.
+template <typename T, typename ACC, bool BLOCK>
+__global__ void __launch_bounds__(256) fma_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ out, FmaDims d,
+                                                         long long n_out, long long n_red) {
+  __shared__ ACC red[8];
+  long long ksz[4], rsz[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool reduced = d.sc[k] == 0 && d.size[k] > 1;
+    ksz[k] = reduced ? 1 : d.size[k];
+    rsz[k] = reduced ? d.size[k] : 1;
+  }
+  const long long first = BLOCK ? (long long)blockIdx.x : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = BLOCK ? (long long)gridDim.x : (long long)gridDim.x * blockDim.x;
+  for (long long o = first; o < n_out; o += stride) {
+    long long t = o;
+    const long long k3 = t % ksz[3]; t /= ksz[3];
+    const long long k2 = t % ksz[2]; t /= ksz[2];
+    const long long k1 = t % ksz[1];
+    const long long k0 = t / ksz[1];
+    const long long xo = k0 * d.sa[0] + k1 * d.sa[1] + k2 * d.sa[2] + k3 * d.sa[3];
+    const long long yo = k0 * d.sb[0] + k1 * d.sb[1] + k2 * d.sb[2] + k3 * d.sb[3];
+    ACC acc = (ACC)0;
+    for (long long r = BLOCK ? threadIdx.x : 0; r < n_red; r += BLOCK ? blockDim.x : 1) {
+      long long u = r;
+      const long long r3 = u % rsz[3]; u /= rsz[3];
+      const long long r2 = u % rsz[2]; u /= rsz[2];
+      const long long r1 = u % rsz[1];
+      const long long r0 = u / rsz[1];
+      const ACC vx = (ACC)x[xo + r0 * d.sa[0] + r1 * d.sa[1] + r2 * d.sa[2] + r3 * d.sa[3]];
+      acc += y ? vx * (ACC)y[yo + r0 * d.sb[0] + r1 * d.sb[1] + r2 * d.sb[2] + r3 * d.sb[3]] : vx;
+    }
+    if (BLOCK) {
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      __syncthreads();                                   // red[] of the previous output has been read
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        ACC tot = (ACC)0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        out[k0 * d.sc[0] + k1 * d.sc[1] + k2 * d.sc[2] + k3 * d.sc[3]] = (T)tot;
+      }
+    } else {
+      out[k0 * d.sc[0] + k1 * d.sc[1] + k2 * d.sc[2] + k3 * d.sc[3]] = (T)acc;
+    }
+  }
+}
+
+static bool fma_dims(FmaDims& d, const int64_t* shape, const int64_t* sa, const int64_t* sb, const int64_t* sc, long long* total) {
+  long long n = 1;
+  for (int k = 0; k < 4; ++k) {
+    if (shape[k] < 1) return false;
+    d.size[k] = shape[k];
+    d.sa[k] = sa ? sa[k] : 0; d.sb[k] = sb ? sb[k] : 0; d.sc[k] = sc ? sc[k] : 0;
+    n *= shape[k];
+    if (n > 0x7fffffffLL) return false;
+  }
+  *total = n;
+  return true;
+}
+template <typename T, typename ACC>
+static int fma_launch(const void* a, const void* b, const void* c, void* out, const FmaDims& d, long long total, cudaStream_t st) {
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  fma_fwd_kernel<T, ACC><<<(int)blocks, 256, 0, st>>>((const T*)a, (const T*)b, (const T*)c, (T*)out, d, total);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+template <typename T, typename ACC>
+static int fma_reduce_launch(const void* x, const void* y, void* out, const FmaDims& d, long long n_out, long long n_red, cudaStream_t st) {
+  if (n_red >= 128) {
+    const long long blocks = n_out < (long long)kNumSMs * 16 ? n_out : (long long)kNumSMs * 16;
+    fma_reduce_kernel<T, ACC, true><<<(int)blocks, 256, 0, st>>>((const T*)x, (const T*)y, (T*)out, d, n_out, n_red);
+  } else {
+    long long blocks = ceil_div_ll(n_out, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    fma_reduce_kernel<T, ACC, false><<<(int)blocks, 256, 0, st>>>((const T*)x, (const T*)y, (T*)out, d, n_out, n_red);
+  }
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
 }  // namespace smc
+
+extern "C" int smc_fma(const void* a, const void* b, const void* c, void* out, int dtype, const int64_t* shape, const int64_t* stride_a,
+                       const int64_t* stride_b, const int64_t* stride_c, void* stream) {
+  if (!a || !b || !c || !out || !shape || !stride_a || !stride_b || !stride_c) return SMC_EINVAL;
+  smc::FmaDims d;
+  long long total = 0;
+  if (!smc::fma_dims(d, shape, stride_a, stride_b, stride_c, &total)) return SMC_ETOOLARGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMC_F32) return smc::fma_launch<float, float>(a, b, c, out, d, total, st);
+  if (dtype == SMC_F16) return smc::fma_launch<__half, float>(a, b, c, out, d, total, st);
+  if (dtype == SMC_F64) return smc::fma_launch<double, double>(a, b, c, out, d, total, st);
+  return SMC_EINVAL;
+}
+
+extern "C" int smc_fma_reduce(const void* x, const void* y, void* out, int dtype, const int64_t* shape, const int64_t* stride_x,
+                              const int64_t* stride_y, const int64_t* stride_out, void* stream) {
+  if (!x || !out || !shape || !stride_x || !stride_out || (y && !stride_y)) return SMC_EINVAL;
+  smc::FmaDims d;
+  long long total = 0;
+  if (!smc::fma_dims(d, shape, stride_x, stride_y, stride_out, &total)) return SMC_ETOOLARGE;
+  long long n_red = 1;
+  for (int k = 0; k < 4; ++k)
+    if (stride_out[k] == 0 && shape[k] > 1) n_red *= shape[k];
+  const long long n_out = total / n_red;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMC_F32) return smc::fma_reduce_launch<float, float>(x, y, out, d, n_out, n_red, st);
+  if (dtype == SMC_F16) return smc::fma_reduce_launch<__half, float>(x, y, out, d, n_out, n_red, st);
+  if (dtype == SMC_F64) return smc::fma_reduce_launch<double, double>(x, y, out, d, n_out, n_red, st);
+  return SMC_EINVAL;
+}
 
 extern "C" int smc_img_to_uint8(const float* img, unsigned char* out, int n, int h, int w, int canvas_w, int x_off, void* stream) {
   if (!img || !out || n < 1 || h < 1 || w < 1 || x_off < 0 || x_off + w > canvas_w) return SMC_EINVAL;
-  long long blocks = smc::ceil_div_ll((long long)n * h * w, 256);
+  const bool v4 = w % 4 == 0 && canvas_w % 4 == 0 && x_off % 4 == 0 && ((uintptr_t)img & 15) == 0 && ((uintptr_t)out & 3) == 0;
+  long long blocks = smc::ceil_div_ll((long long)n * h * (v4 ? w / 4 : w), 256);
   if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
-  smc::img_to_uint8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, out, n, h, w, canvas_w, x_off);
+  if (v4)
+    smc::img_to_uint8_v4_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, out, n, h, w / 4, canvas_w, x_off);
+  else
+    smc::img_to_uint8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, out, n, h, w, canvas_w, x_off);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

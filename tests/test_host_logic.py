@@ -134,18 +134,19 @@ def test_schedules_and_sharding():
         assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
 
 
-def test_fma_backward_unbroadcasts():
+def test_fma_has_no_cpu_path_and_plans_broadcast_strides():
+    """ops.fma runs on repo kernels only (smc_fma / smc_fma_reduce): CPU tensors raise; the host-side broadcast bookkeeping (the role
+    of fma.py:49-58 `_unbroadcast`) is checked here, the numbers on the GPU (tests/test_ops_gpu.py::test_fma_golden)."""
     from stylemc_b200.ops import fma
-    g = torch.Generator().manual_seed(3)
-    a = torch.randn(2, 3, 4, 4, generator=g, requires_grad=True)
-    b = torch.randn(2, 3, 1, 1, generator=g, requires_grad=True)
-    c = torch.randn(4, 4, generator=g, requires_grad=True)
-    dy = torch.randn(2, 3, 4, 4, generator=g)
-    fma.fma(a, b, c).backward(dy)
-    a2, b2, c2 = (t.detach().clone().requires_grad_(True) for t in (a, b, c))
-    (a2 * b2 + c2).backward(dy)
-    for x, y in ((a, a2), (b, b2), (c, c2)):
-        assert torch.allclose(x.grad, y.grad, atol=1e-6)
+    a, b, c = torch.zeros(2, 3, 4, 4), torch.zeros(2, 3, 1, 1), torch.zeros(4, 4)
+    with pytest.raises(RuntimeError):
+        fma.fma(a, b, c)
+    space = fma._space(a, b, c)
+    assert space == (2, 3, 4, 4)
+    assert fma._strides(a, space) == [48, 16, 4, 1] and fma._strides(b, space) == [3, 1, 0, 0] and fma._strides(c, space) == [0, 0, 4, 1]
+    assert fma._space(torch.zeros(5), torch.zeros(3, 1)) == (1, 1, 3, 5)
+    with pytest.raises(RuntimeError):
+        fma._space(torch.zeros(1, 1, 1, 1, 2))
 
 
 def test_setup_filter_matches_oracle():

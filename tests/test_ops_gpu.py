@@ -183,3 +183,75 @@ def test_conv2d_resample_input_grad():
             y.backward(dy.cuda())
         assert (y.detach().cpu() - yr.detach()).abs().max().item() <= 2e-5 * yr.abs().max().item()
         assert (xc.grad.cpu() - xr.grad).abs().max().item() <= 2e-5 * xr.grad.abs().max().item()
+
+
+def test_fma_golden(golden):
+    """ops.fma (smc_fma / smc_fma_reduce) against the reference's own autograd.Function run on the CPU (fma.py:15-58): forward and the
+    three broadcast-aware input gradients."""
+    from stylemc_b200.ops import fma
+    g = golden('ops')
+    a, b, c = (dev(g['fma.' + k]).requires_grad_(True) for k in 'abc')
+    y = fma.fma(a, b, c)
+    assert (y.detach().cpu() - torch.as_tensor(g['fma.y'])).abs().max().item() <= 1e-6
+    y.backward(dev(g['fma.dy']))
+    for t, k in ((a, 'da'), (b, 'db'), (c, 'dc')):
+        ref = torch.as_tensor(g['fma.' + k])
+        assert t.grad.shape == ref.shape
+        assert (t.grad.cpu() - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item()), k
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.float64])
+def test_fma_vs_oracle_shapes_and_second_order(dtype):
+    """Long reductions (block-per-output kernel), scalars and rank < 4 operands; fp16 / fp64; gradient of the gradient."""
+    gen = torch.Generator().manual_seed(11)
+    from stylemc_b200.ops import fma
+    tol = {torch.float32: 2e-6, torch.float16: 2e-3, torch.float64: 1e-12}[dtype]
+    for sa, sb, sc in (((3, 5, 40, 40), (3, 5, 1, 1), (40, 40)), ((2, 1, 7), (4, 1), (1,)), ((6,), (), (6,)), ((2, 3, 4, 4), (2, 3, 4, 4), (1, 3, 1, 1))):
+        ta, tb, tc = (torch.randn(*s, generator=gen, dtype=torch.float64) for s in (sa, sb, sc))
+        ra, rb, rc = (t.clone().requires_grad_(True) for t in (ta, tb, tc))
+        yr = o_conv.fma(ra, rb, rc)
+        dy = torch.randn(yr.shape, generator=gen, dtype=torch.float64)
+        gr = torch.autograd.grad(yr, (ra, rb, rc), dy)
+        xa, xb, xc = (t.to(dtype).cuda().requires_grad_(True) for t in (ta, tb, tc))
+        y = fma.fma(xa, xb, xc)
+        assert y.dtype == dtype and y.shape == yr.shape
+        assert (y.detach().cpu().double() - yr.detach()).abs().max().item() <= tol * max(1.0, yr.abs().max().item())
+        gx = torch.autograd.grad(y, (xa, xb, xc), dy.to(dtype).cuda(), create_graph=True)
+        for got, want in zip(gx, gr):
+            assert got.shape == want.shape
+            assert (got.detach().cpu().double() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item()) * 40
+        if dtype == torch.float64:                      # d/da of sum(d y/d b * v) = v broadcast * dy: second order through _FmaReduce.backward
+            v = torch.randn(tb.shape, generator=gen, dtype=torch.float64)
+            ga2, = torch.autograd.grad((gx[1] * v.cuda()).sum(), xa)
+            ra2 = ta.clone().requires_grad_(True)
+            gb_ref, = torch.autograd.grad(o_conv.fma(ra2, rb, rc), rb, dy, create_graph=True)
+            want, = torch.autograd.grad((gb_ref * v).sum(), ra2)
+            assert (ga2.cpu() - want).abs().max().item() <= 1e-10
+
+
+def test_conv2d_gradfix_entry_points_golden(golden):
+    """conv2d_gradfix.conv2d / conv_transpose2d (conv2d_gradfix.py:35-43) against the reference's own functions run on the CPU
+    (F.conv2d / F.conv_transpose2d with bias), forward and the input gradient; weight gradients are refused outside
+    no_weight_gradients() and the switch is restored when the block raises."""
+    from stylemc_b200.ops import conv2d_gradfix
+    g = golden('ops')
+    x, w, b, wt = dev(g['gradfix.x']), dev(g['gradfix.w']), dev(g['gradfix.bias']), dev(g['gradfix.wt'])
+    for got, key in ((conv2d_gradfix.conv2d(x, w, bias=b, padding=1), 'gradfix.conv2d'),
+                     (conv2d_gradfix.conv_transpose2d(x, wt, stride=2), 'gradfix.conv_transpose2d')):
+        ref = torch.as_tensor(g[key])
+        assert got.shape == ref.shape
+        assert (got.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), key
+    xg = x.clone().requires_grad_(True)
+    with conv2d_gradfix.no_weight_gradients():
+        conv2d_gradfix.conv2d(xg, w, padding=1).backward(dev(g['gradfix.dy']))
+    ref = torch.as_tensor(g['gradfix.dx'])
+    assert (xg.grad.cpu() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    wg = w.clone().requires_grad_(True)
+    with pytest.raises(RuntimeError):
+        conv2d_gradfix.conv2d(x, wg, padding=1).sum().backward()          # weight gradient outside no_weight_gradients()
+    with pytest.raises(ZeroDivisionError):
+        with conv2d_gradfix.no_weight_gradients():
+            1 / 0
+    assert conv2d_gradfix.weight_gradients_disabled is False
+    with pytest.raises(RuntimeError):
+        conv2d_gradfix.conv2d(x, w, stride=2)
