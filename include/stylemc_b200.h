@@ -238,6 +238,15 @@ int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, flo
  * the reference concatenates original | edited along the width, :206). */
 int smc_img_to_uint8(const float* img, unsigned char* out, int n, int h, int w, int canvas_w, int x_off, void* stream);
 
+/* ---- one-off preparation of frozen weights (what the reference does implicitly per call in modulated_conv2d: w.flip / transpose /
+ * square().sum(), [UPSTREAM] training/networks.py; conv2d_resample.py:125-147) ------------------------------------------------
+ * w [n_out, n_in, ntaps] fp32 -> K-major tap matrices as fp16 hi (+ lo = rn(v - hi)) planes: forward [ntaps * n_out_padded, n_in_padded]
+ * (row t * n_out_padded + o, column i), dgrad [ntaps * n_in_padded, n_out_padded] (row t * n_in_padded + i, column o), zero padded; and
+ * q[o, i] = sum_t w[o, i, t]^2 (un-padded, un-scaled) for smc_demod_coefs.  Any of the three outputs may be NULL.  scale: optional DEVICE
+ * scalar multiplied into the planes (a power of two from smc_grad_scale). */
+int smc_prepare_weights(const float* w, int n_out, int n_in, int ntaps, int n_out_padded, int n_in_padded, const float* scale,
+                        void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo, float* q, void* stream);
+
 /* ---- fma.py:15-58 as a stand-alone op (on the fused path the multiply-add is the GEMM epilogue) -----------------------
  * smc_fma: out = a * b + c over the broadcast index space `shape` (4 sizes, leading 1s for lower ranks); stride_* are ELEMENT strides
  * of each operand viewed in that space, 0 on the axes it is broadcast along (fma.py:22, torch.addcmul); out is contiguous.

@@ -103,6 +103,7 @@ SIGNATURES = {
     'smc_head_proj_bwd': 'ppp iii p',
     'smc_clip_loss': 'ppppp ii ff p f p',
     'smc_img_to_uint8': 'pp iiiii p',
+    'smc_prepare_weights': 'p iiiii p pppp p p',
     'smc_fma': 'pppp i pppp p',
     'smc_fma_reduce': 'ppp i pppp p',
     'smc_sgd_step': 'pp q fff p',

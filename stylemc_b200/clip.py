@@ -32,10 +32,8 @@ class _Linear:
     def __init__(self, w, b, device, two, need_bwd):
         w = w.detach().to(device=device, dtype=torch.float32)
         self.out_f, self.in_f = w.shape
-        k = gemm.pow2_prescale(w)
-        self.inv = 1.0 / k
-        self.fwd = gemm.split_planes(w * k, two).reshape(-1, self.in_f)                       # [P*out, in]
-        self.bwd = gemm.split_planes((w * k).t().contiguous(), two).reshape(-1, self.out_f) if need_bwd else None   # [P*in, out]
+        # [P*out, in] (y = x @ W.T) and [P*in, out] (dx = dy @ W) planes, pre-scaled by a power of two, in one kernel
+        self.fwd, self.bwd, _, self.inv = gemm.prepare_weights(w, two=two, fwd=True, bwd=need_bwd, prescale=True)
         self.bias = b.detach().to(device=device, dtype=torch.float32).contiguous() if b is not None else None
 
 

@@ -54,6 +54,50 @@ __global__ void __launch_bounds__(256) img_to_uint8_v4_kernel(const float* __res
   }
 }
 
+// ---- one-off weight preparation (frozen G / CLIP): [O, I, T] fp32 conv or linear weights -> the K-major tap matrices of the implicit
+// GEMM as fp16 hi / lo planes, forward [T * Op, Ip] (row t * Op + o, column i) and dgrad [T * Ip, Op] (row t * Ip + i, column o), plus
+// q[o, i] = sum_t w^2 for the demodulation coefficients.  Replaces ~15 ATen launches per layer (permute / contiguous / half / sub /
+// stack / square / sum).  `scale` (device scalar, optional) is a power of two multiplied in before the split (small CLIP weights: keeps the
+// lo plane out of the fp16 subnormals; the GEMM undoes it with acc_scale).
+struct PrepW {
+  const float* w;
+  const float* scale;
+  __half *fwd_hi, *fwd_lo, *bwd_hi, *bwd_lo;
+  float* q;
+  int O, I, T, Op, Ip;
+  long long n_fwd, n_bwd, n_q;
+};
+__global__ void __launch_bounds__(256) prepare_weights_kernel(PrepW p) {
+  const float k = p.scale ? __ldg(p.scale) : 1.f;
+  const long long total = p.n_fwd + p.n_bwd + p.n_q;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    if (idx < p.n_fwd + p.n_bwd) {
+      const bool bwd = idx >= p.n_fwd;
+      long long r = bwd ? idx - p.n_fwd : idx;
+      const int inner = bwd ? p.Op : p.Ip, mid = bwd ? p.Ip : p.Op;
+      const int c = (int)(r % inner); r /= inner;
+      const int m = (int)(r % mid);
+      const int t = (int)(r / mid);
+      const int o = bwd ? c : m, i = bwd ? m : c;
+      float v = 0.f;
+      if (o < p.O && i < p.I) v = __ldg(p.w + ((long long)o * p.I + i) * p.T + t) * k;
+      __half hi, lo;
+      split_half(v, hi, lo);
+      __half* dh = bwd ? p.bwd_hi : p.fwd_hi;
+      __half* dl = bwd ? p.bwd_lo : p.fwd_lo;
+      const long long at = bwd ? idx - p.n_fwd : idx;
+      dh[at] = hi;
+      if (dl) dl[at] = lo;
+    } else {
+      const long long r = idx - p.n_fwd - p.n_bwd;          // (o, i) of the un-padded weight
+      const float* src = p.w + r * p.T;
+      float acc = 0.f;
+      for (int t = 0; t < p.T; ++t) { const float v = __ldg(src + t); acc = fmaf(v, v, acc); }
+      p.q[r] = acc;
+    }
+  }
+}
+
 // ---- fma.py:15-58 as stand-alone kernels: out = a * b + c over a broadcast 4-D index space, and the "un-broadcast" of its
 // backward (sum of x * y over the axes broadcasting expanded).  Element strides; 0 marks a broadcast / reduced axis.
 struct FmaDims {
@@ -159,6 +203,26 @@ static int fma_reduce_launch(const void* x, const void* y, void* out, const FmaD
   return SMC_OK;
 }
 }  // namespace smc
+
+extern "C" int smc_prepare_weights(const float* w, int n_out, int n_in, int ntaps, int n_out_padded, int n_in_padded, const float* scale,
+                                   void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo, float* q, void* stream) {
+  if (!w || n_out < 1 || n_in < 1 || ntaps < 1 || n_out_padded < n_out || n_in_padded < n_in) return SMC_EINVAL;
+  if ((!fwd_hi && fwd_lo) || (!bwd_hi && bwd_lo) || (!fwd_hi && !bwd_hi && !q)) return SMC_EINVAL;
+  smc::PrepW p;
+  p.w = w; p.scale = scale;
+  p.fwd_hi = (__half*)fwd_hi; p.fwd_lo = (__half*)fwd_lo; p.bwd_hi = (__half*)bwd_hi; p.bwd_lo = (__half*)bwd_lo; p.q = q;
+  p.O = n_out; p.I = n_in; p.T = ntaps; p.Op = n_out_padded; p.Ip = n_in_padded;
+  const long long plane = (long long)ntaps * n_out_padded * n_in_padded;
+  if (plane > 0x7fffffffLL) return SMC_ETOOLARGE;
+  p.n_fwd = fwd_hi ? plane : 0;
+  p.n_bwd = bwd_hi ? plane : 0;
+  p.n_q = q ? (long long)n_out * n_in : 0;
+  long long blocks = smc::ceil_div_ll(p.n_fwd + p.n_bwd + p.n_q, 256);
+  if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
+  smc::prepare_weights_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
 
 extern "C" int smc_fma(const void* a, const void* b, const void* c, void* out, int dtype, const int64_t* shape, const int64_t* stride_a,
                        const int64_t* stride_b, const int64_t* stride_c, void* stream) {

@@ -115,6 +115,36 @@ def pow2_prescale(x, target=256.0):
     return 2.0 ** (math.floor(math.log2(target / amax)))
 
 
+def prepare_weights(w, two=True, fwd=True, bwd=False, q=False, prescale=False, pad_to=1):
+    """Frozen conv / linear weights -> the operand layouts of ``igemm`` in ONE kernel (``smc_prepare_weights``).
+
+    w: [O, I, kh, kw] or [O, I] fp32 CUDA tensor.  Returns (B_fwd [P * T * Op, Ip] or None, B_bwd [P * T * Ip, Op] or None,
+    q [O, I] fp32 or None, inv_scale): P = 2 hi/lo planes when ``two``; Op / Ip = channel counts rounded up to ``pad_to``;
+    ``prescale`` multiplies the planes by the power of two that brings max|w| into [128, 256) (``pow2_prescale``, found on the device
+    by ``smc_grad_scale``) and returns its inverse for ``acc_scale`` -- the one host read of this function."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.ndim in (2, 4)
+    w = w.contiguous()
+    o, i = w.shape[:2]
+    t = w.shape[2] * w.shape[3] if w.ndim == 4 else 1
+    op, ip = -(-o // pad_to) * pad_to, -(-i // pad_to) * pad_to
+    planes = 2 if two else 1
+    dev = w.device
+    Bf = torch.empty([planes, t * op, ip], dtype=torch.float16, device=dev) if fwd else None
+    Bb = torch.empty([planes, t * ip, op], dtype=torch.float16, device=dev) if bwd else None
+    qq = torch.empty([o, i], dtype=torch.float32, device=dev) if q else None
+    lo = lambda b: _lib.ptr(b[1]) if (b is not None and two) else None
+    with torch.cuda.device(dev):
+        scale = None
+        if prescale:
+            amax = torch.zeros(1, dtype=torch.int32, device=dev)
+            scale = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.call('smc_grad_scale', _lib.ptr(w), w.numel(), 256.0, _lib.ptr(amax), _lib.ptr(scale), _lib.stream())
+        _lib.call('smc_prepare_weights', _lib.ptr(w), o, i, t, op, ip, _lib.ptr(scale), _lib.ptr(Bf), lo(Bf), _lib.ptr(Bb), lo(Bb), _lib.ptr(qq),
+                  _lib.stream())
+    inv = 1.0 / float(scale) if prescale else 1.0
+    return (Bf.reshape(-1, ip) if fwd else None), (Bb.reshape(-1, op) if bwd else None), qq, inv
+
+
 def split_planes(x, two):
     """fp32 tensor -> stacked fp16 planes [P, ...] (setup-time helper for frozen weights)."""
     hi = x.to(torch.float16)

@@ -45,14 +45,9 @@ def _unpack(y_nhwc, c, dtype):
 
 def _weight_matrix(w, planes, transpose_io=False):
     """[O, I, kh, kw] -> K-major tap matrix planes [P * kh*kw*Op, Ip]: row (t*Op + o), col i.  With transpose_io the roles
-    of O and I are swapped (dgrad: contraction over the output channels)."""
-    if transpose_io:
-        w = w.transpose(0, 1)
-    o, i, kh, kw = w.shape
-    op, ip = _ceil32(o), _ceil32(i)
-    m = torch.zeros([kh * kw, op, ip], dtype=torch.float32, device=w.device)
-    m[:, :o, :i] = w.float().permute(2, 3, 0, 1).reshape(kh * kw, o, i)
-    return gemm.split_planes(m.reshape(kh * kw * op, ip), planes == 2).reshape(-1, ip), op
+    of O and I are swapped (dgrad: contraction over the output channels).  One ``smc_prepare_weights`` launch."""
+    Bf, Bb, _, _ = gemm.prepare_weights(w.float(), two=planes == 2, fwd=not transpose_io, bwd=transpose_io, pad_to=32)
+    return (Bb, _ceil32(w.shape[1])) if transpose_io else (Bf, _ceil32(w.shape[0]))
 
 
 def _conv_fwd_raw(x, w, padding, transpose):

@@ -43,11 +43,8 @@ class _Layer:
         self.cout, self.cin = w.shape[:2]
         self.up = up
         self.resolution = int(mod.resolution)
-        taps_fwd = w.permute(2, 3, 0, 1).reshape(9 * self.cout, self.cin)      # row t*O + o, col i
-        taps_bwd = w.permute(2, 3, 1, 0).reshape(9 * self.cin, self.cout)      # row t*I + i, col o (dgrad)
-        self.B_fwd = gemm.split_planes(taps_fwd, True).reshape(2 * 9 * self.cout, self.cin)
-        self.B_bwd = gemm.split_planes(taps_bwd, True).reshape(2 * 9 * self.cin, self.cout)
-        self.q = w.square().sum(dim=[2, 3]).contiguous()               # [O, I]
+        # one kernel: hi/lo planes of the tap matrices, forward (row t*O + o, col i) and dgrad (row t*I + i, col o), and q = sum_t w^2
+        self.B_fwd, self.B_bwd, self.q, _ = gemm.prepare_weights(w, two=True, fwd=True, bwd=True, q=True)
         self.bias = _f32(mod.bias, device)
         strength = float(mod.noise_strength) if getattr(mod, 'use_noise', True) else 0.0
         self.noise_const = (_f32(mod.noise_const, device) * strength).contiguous() if getattr(mod, 'use_noise', True) else None

@@ -140,3 +140,26 @@ def test_argument_errors():
     b = torch.zeros(32, 48, device='cuda', dtype=torch.float16)
     with pytest.raises(RuntimeError):
         gemm.igemm(a, b, 1, 1, 128, 32, gemm.TAPS_1X1, out_f32=torch.empty(128, 32, device='cuda'))
+
+
+@pytest.mark.parametrize('shape,pad', [((64, 32, 3, 3), 1), ((33, 40, 3, 3), 32), ((3, 6, 1, 1), 32), ((768, 3072), 1), ((512, 512, 3, 3), 1)])
+def test_prepare_weights_matches_the_torch_formulation_bitwise(shape, pad):
+    """smc_prepare_weights (one launch) against the ATen chain it replaces: permute -> reshape -> half / sub / half (gemm.split_planes),
+    square().sum(); planes bit-identical, q to fp32 rounding; with the device-side power-of-two prescale of the CLIP linears."""
+    from stylemc_b200 import gemm
+    w = (torch.randn(*shape, generator=torch.Generator().manual_seed(5)) * 0.03).cuda()
+    o, i = shape[:2]
+    t = shape[2] * shape[3] if len(shape) == 4 else 1
+    op, ip = -(-o // pad) * pad, -(-i // pad) * pad
+    for prescale in (False, True):
+        Bf, Bb, q, inv = gemm.prepare_weights(w, two=True, fwd=True, bwd=True, q=True, prescale=prescale, pad_to=pad)
+        k = gemm.pow2_prescale(w) if prescale else 1.0
+        assert inv == 1.0 / k
+        m = torch.zeros([t, op, ip], device='cuda')
+        m[:, :o, :i] = (w * k).reshape(o, i, t).permute(2, 0, 1)
+        assert torch.equal(Bf, gemm.split_planes(m.reshape(t * op, ip), True).reshape(-1, ip))
+        assert torch.equal(Bb, gemm.split_planes(m.permute(0, 2, 1).reshape(t * ip, op).contiguous(), True).reshape(-1, op))
+        qr = w.reshape(o, i, t).double().square().sum(2)
+        assert ((q.double() - qr).abs() <= 1e-6 * qr.abs().max()).all()
+    B1, none_b, none_q, _ = gemm.prepare_weights(w, two=False)
+    assert none_b is None and none_q is None and torch.equal(B1, gemm.prepare_weights(w, two=True)[0][:t * o])     # hi plane alone
