@@ -27,8 +27,8 @@ def unprocess(img, size=224):
     """find_direction.py:49-52: [-1,1]-ish image -> CLIP-normalised 224x224."""
     x = (img * 127.5 + 128).clamp(0, 255)
     x = F.interpolate(x, size=(size, size), mode='bicubic', antialias=True, align_corners=False)
-    mean = torch.tensor(CLIP_MEAN, dtype=img.dtype).view(1, 3, 1, 1)
-    std = torch.tensor(CLIP_STD, dtype=img.dtype).view(1, 3, 1, 1)
+    mean = torch.tensor(CLIP_MEAN, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
     return (x / 255 - mean) / std
 
 
@@ -71,8 +71,8 @@ def direction_step(G, temp_shapes, clip_loss, styles, delta, until_k, clip_loss_
     original_img).  grad is d loss / d delta, [1,8,512].
     """
     delta = delta.detach().clone().requires_grad_(True)
-    direction = torch.zeros(1, synthesis.N_STYLE_ROWS, synthesis.STYLE_WIDTH, dtype=styles.dtype)
-    direction = direction.index_put((torch.tensor([0]).view(1, 1), torch.tensor(S_TRAINABLE_ROWS).view(1, -1)),
+    direction = torch.zeros(1, synthesis.N_STYLE_ROWS, synthesis.STYLE_WIDTH, dtype=styles.dtype, device=styles.device)
+    direction = direction.index_put((torch.tensor([0], device=styles.device).view(1, 1), torch.tensor(S_TRAINABLE_ROWS, device=styles.device).view(1, -1)),
                                     delta)                                          # :307
     styles2 = styles + direction                                                   # :308
     _, img = synthesis.generate_image(G, until_k, styles2, temp_shapes, noise_mode)   # :309

@@ -248,7 +248,7 @@ def get_temp_shapes(G):
 
 def get_styles(G, ws, block_ws):
     """utils.py:123-158: S [M,26,512] zero padded, row j = affine_j(w); affines replaced by Identity."""
-    styles = torch.zeros(ws.shape[0], N_STYLE_ROWS, STYLE_WIDTH, dtype=ws.dtype)
+    styles = torch.zeros(ws.shape[0], N_STYLE_ROWS, STYLE_WIDTH, dtype=ws.dtype, device=ws.device)
     shapes, row = [], 0
     with torch.no_grad():
         for r, cur in zip(G.synthesis.block_resolutions, block_ws):

@@ -130,11 +130,11 @@ class CLIP:
         c, p = self.cfg, self.p
         T = text.shape[1]
         x = p['token_embedding.weight'][text] + p['positional_embedding'][:T]
-        mask = torch.full((T, T), float('-inf'), dtype=self.dtype).triu_(1)
+        mask = torch.full((T, T), float('-inf'), dtype=self.dtype, device=x.device).triu_(1)
         for i in range(c['transformer_layers']):
             x = _resblock(x, p, f'transformer.resblocks.{i}.', c['transformer_heads'], mask)
         x = _ln(x, p['ln_final.weight'], p['ln_final.bias'])
-        return x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ p['text_projection']
+        return x[torch.arange(x.shape[0], device=x.device), text.argmax(dim=-1)] @ p['text_projection']
 
 
 FLOPS_PER_IMAGE_FWD = None  # filled by bench from the GEMM shapes; see SURVEY.md section 8d

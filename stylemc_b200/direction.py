@@ -99,9 +99,12 @@ class DirectionFinder:
 
     def __init__(self, G, clip_model, pos_tokens, neg_tokens, resolution, device='cuda', learning_rate=1.5, clip_loss_coef=1.0,
                  l2_reg_coef=0.1, noise_mode='const', precision='x3p', micro_batch=16, process_group=None,
-                 trainable_rows=S_TRAINABLE_SPACE_CHANNELS):
+                 trainable_rows=S_TRAINABLE_SPACE_CHANNELS, original_precision=None):
         self.device = torch.device(device)
         self.engine = utils.engine_for(G, self.device, precision)
+        # the original-image branch carries no gradient (find_direction.py:312); it may run in another engine mode (diagnostics:
+        # tests/diag/diag_original_branch.py measures what that does to the loss and the gradient).  Default: the same engine.
+        self.engine_original = self.engine if original_precision in (None, precision) else utils.engine_for(G, self.device, original_precision)
         self.until_k = RESOLUTION_DICT[resolution] if resolution in RESOLUTION_DICT else int(math.log2(resolution)) - 2
         self.until_k = min(self.until_k, len(self.engine.blocks) - 1)
         models = list(clip_model) if isinstance(clip_model, (tuple, list)) else [clip_model]
@@ -148,7 +151,7 @@ class DirectionFinder:
     def _encode_original(self, s):
         """CLIP embeddings of the un-edited images (find_direction.py:312: no gradient), one per tower."""
         with _phase('original_branch'):
-            _, original, _ = self.engine.forward(s, self.until_k, self.noise_mode, save=False)
+            _, original, _ = self.engine_original.forward(s, self.until_k, self.noise_mode, save=False)
             u_s = resample.unprocess_fwd(original)
             del original
             return [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
