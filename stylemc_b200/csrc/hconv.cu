@@ -29,6 +29,10 @@ constexpr int HC_MT = 128 * HC_MB;  // positions per tile
 constexpr int HC_MAX_GROUPS = 4;
 constexpr int HC_MAX_TAPS = 16;
 constexpr int HC_THREADS = 32 * (3 + 16);
+constexpr int HC_EPI_THREADS = 32 * 16;
+constexpr int HC_BAR_BYTES = 1024;                 // mbarriers + TMEM slot
+constexpr int HC_PSTAGE_VECS = 6;                  // staged epilogue vectors per tile (hconv_kernel::pstage)
+static constexpr int hc_pstage_bytes(int bn) { return 2 * HC_PSTAGE_VECS * bn * 4; }
 
 struct HcTap {
   int32_t posoff;            // (dy + padT) * Wp + dx + padL
@@ -204,13 +208,21 @@ __device__ __forceinline__ void hc_st32(void* p, const uint4& a, const uint4& b)
                "r"(b.z), "r"(b.w) : "memory");
 }
 
+// 8 consecutive floats of a per-tile parameter vector staged in shared memory (32-bit shared address): every lane of a warp reads the
+// same address (one broadcast wavefront), latency ~25 clk instead of a global-load round trip per 8 channels
+__device__ __forceinline__ void hc_lds8(uint32_t saddr, float (&f)[8]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(saddr));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(saddr + 16u));
+}
+
 // The modulated-conv epilogue (demodulation, noise, bias, leaky ReLU * gain, clamp all present) with the instruction count that
 // matters when a thread owns 64 channels of four output planes: vector parameter loads, one FMA for demod + noise + bias,
 // lrelu(x) * g = max(x g, x g alpha), the hi/lo splits and 32-byte stores; the ToRGB partial sums ride along.
+// rs / bs / ps / rw: SHARED-memory addresses of this thread's slice of the staged vectors (rs already multiplied by acc_scale; ps / rw
+// 0 = absent; the three rgb rows are rw_stride bytes apart).
 template <int CW>
-__device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], const smc_igemm_epilogue& e, float acc_scale, float nz,
-                                                    const float* __restrict__ rs, const float* __restrict__ bs, const float* __restrict__ ps,
-                                                    const float* __restrict__ rw, int n_out, long long opix, float& rgb0, float& rgb1,
+__device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], const smc_igemm_epilogue& e, float nz, uint32_t rs, uint32_t bs,
+                                                    uint32_t ps, uint32_t rw, uint32_t rw_stride, long long opix, float& rgb0, float& rgb1,
                                                     float& rgb2) {
   const float g = e.gain, ga = e.gain * e.alpha, cl = e.clamp;
   static_assert(CW % 16 == 0, "16 channels (32 bytes of fp16) per step");
@@ -220,11 +232,11 @@ __device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], cons
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float r8[8], b8[8];
-      hc_ld8(rs + c0 + 8 * hh, r8);
-      hc_ld8(bs + c0 + 8 * hh, b8);
+      hc_lds8(rs + 4u * (uint32_t)(c0 + 8 * hh), r8);
+      hc_lds8(bs + 4u * (uint32_t)(c0 + 8 * hh), b8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float x = fmaf(acc[c0 + 8 * hh + i], r8[i] * acc_scale, nz + b8[i]);
+        const float x = fmaf(acc[c0 + 8 * hh + i], r8[i], nz + b8[i]);
         v[8 * hh + i] = fminf(fmaxf(fmaxf(x * g, x * ga), -cl), cl);
       }
     }
@@ -239,9 +251,9 @@ __device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], cons
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float w0[8], w1[8], w2[8];
-        hc_ld8(rw + c0 + 8 * hh, w0);
-        hc_ld8(rw + n_out + c0 + 8 * hh, w1);
-        hc_ld8(rw + 2 * n_out + c0 + 8 * hh, w2);
+        hc_lds8(rw + 4u * (uint32_t)(c0 + 8 * hh), w0);
+        hc_lds8(rw + rw_stride + 4u * (uint32_t)(c0 + 8 * hh), w1);
+        hc_lds8(rw + 2u * rw_stride + 4u * (uint32_t)(c0 + 8 * hh), w2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           rgb0 = fmaf(w0[i], v[8 * hh + i], rgb0);
@@ -255,7 +267,7 @@ __device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], cons
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float p8[8];
-          hc_ld8(ps + c0 + 8 * hh, p8);
+          hc_lds8(ps + 4u * (uint32_t)(c0 + 8 * hh), p8);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[8 * hh + i] *= p8[i];
         }
@@ -288,9 +300,8 @@ __device__ __forceinline__ void hc_h8_to_f(const uint4& u, float* f) {
 // layer's pre-activation once the leaky-ReLU slope and the clamp mask of the SAVED output y are applied (bias_act.cu:71-72,136-142).
 // The optional ToRGB branch adds sum_j rw[j][c] * g_j (g = masked dL/drgb of this pixel) before the slope.
 template <int CW>
-__device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const smc_igemm_epilogue& e, float acc_scale,
-                                                   const float* __restrict__ ps, const float* __restrict__ rw, int n_out, long long opix,
-                                                   float g0, float g1, float g2) {
+__device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const smc_igemm_epilogue& e, float acc_scale, uint32_t ps, uint32_t rw,
+                                                   uint32_t rw_stride, long long opix, float g0, float g1, float g2) {
   const float g = e.gain, ga = e.gain * e.alpha, cl = e.clamp;
   const __half* yh = reinterpret_cast<const __half*>(e.mask_y) + opix;
   const __half* yl = e.mask_y_lo ? reinterpret_cast<const __half*>(e.mask_y_lo) + opix : nullptr;
@@ -312,14 +323,14 @@ __device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float p8[8];
-      hc_ld8(ps + c0 + 8 * hh, p8);
+      hc_lds8(ps + 4u * (uint32_t)(c0 + 8 * hh), p8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[8 * hh + i] = acc[c0 + 8 * hh + i] * (p8[i] * acc_scale);
       if (rw) {
         float w0[8], w1[8], w2[8];
-        hc_ld8(rw + c0 + 8 * hh, w0);
-        hc_ld8(rw + n_out + c0 + 8 * hh, w1);
-        hc_ld8(rw + 2 * n_out + c0 + 8 * hh, w2);
+        hc_lds8(rw + 4u * (uint32_t)(c0 + 8 * hh), w0);
+        hc_lds8(rw + rw_stride + 4u * (uint32_t)(c0 + 8 * hh), w1);
+        hc_lds8(rw + 2u * rw_stride + 4u * (uint32_t)(c0 + 8 * hh), w2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[8 * hh + i] += w0[i] * g0 + w1[i] * g1 + w2[i] * g2;
       }
@@ -380,6 +391,9 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
   uint64_t* cross_full = main_drained + 2; // [2]
   uint64_t* cross_drained = cross_full + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cross_drained + 2);
+  // per-tile parameter vectors of the fused epilogues, staged by the epilogue warps (two buffers, alternating per tile):
+  // [row_scale * acc_scale | bias | post_scale | rgb_w row 0 | row 1 | row 2] x BN floats
+  float* pstage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + HC_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -590,6 +604,55 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const HcTile tl = hc_tile(p, wk);
       const int ndrains = p.probs[tl.prob].ndrains;
       const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
+      // ---- while the tensor core works on this tile: this thread's position, the lean-path decision, the per-tile parameter vectors
+      // into shared memory (one coalesced pass of the 512 epilogue threads instead of ~100 global loads per thread after the drain),
+      // the per-pixel operands (noise, ToRGB gradient) and an L2 prefetch of the saved activation the fused activation backward reads
+      const int qpos = tl.q0 + m;
+      const int h = hc_div(qpos, p.div_wp), wr = qpos - h * p.Wp;
+      const int w = tl.w0 + wr;
+      const bool valid = (wr < p.Wt) && (w < p.W) && (h < p.H);
+      const int o0 = tl.nt * BN + ch * CW;
+      const long long opix = e.o_off + p.probs[tl.prob].o_off + (long long)tl.n * e.o_sn + (long long)h * e.o_sh + (long long)w * e.o_sw + o0;
+      const bool out32 = ((((uintptr_t)e.out_raw | (uintptr_t)e.out_raw_lo | (uintptr_t)e.out_hi | (uintptr_t)e.out_lo) & 31) == 0) &&
+                         ((((e.o_sn | e.o_sh | e.o_sw | e.o_off) * 2) & 31) == 0) && (p.n_out % 16 == 0);
+      // modulated-conv layers (the bulk of the epilogue work): lean path; alpha < 1 makes max(x, alpha x) the leaky ReLU
+      const bool modconv = e.row_scale && e.bias && e.act == 1 && e.clamp >= 0.f && e.alpha >= 0.f && e.alpha <= 1.f && e.gain > 0.f && !e.residual &&
+                           !e.out_f32 && !e.mask_y && out32;
+      const bool staged = modconv || e.mask_y != nullptr;
+      float* pst = pstage + (tile_ctr & 1u) * (uint32_t)(HC_PSTAGE_VECS * BN);
+      if (staged) {
+        const int et = (int)threadIdx.x - 96;
+        const long long nb_off = (long long)tl.n * p.n_out + tl.nt * BN;
+        for (int i = et; i < HC_PSTAGE_VECS * BN; i += HC_EPI_THREADS) {
+          const int which = i / BN, c = i - which * BN;
+          float v = 0.f;
+          if (which == 0) { if (e.row_scale) v = __ldg(e.row_scale + nb_off + c) * acc_scale; }
+          else if (which == 1) { if (e.bias) v = __ldg(e.bias + tl.nt * BN + c); }
+          else if (which == 2) { if (e.post_scale) v = __ldg(e.post_scale + nb_off + c); }
+          else if (e.rgb_w) v = __ldg(e.rgb_w + ((long long)tl.n * 3 + (which - 3)) * p.n_out + tl.nt * BN + c);
+          pst[i] = v;
+        }
+      }
+      float nz = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+      if (valid) {
+        if (e.noise != nullptr) nz = __ldg(e.noise + (long long)h * e.noise_sh + (long long)w * e.noise_sw);
+        if (e.mask_y) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y) + opix));
+          if (CW > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y) + opix + 64));
+          if (e.mask_y_lo) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y_lo) + opix));
+            if (CW > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y_lo) + opix + 64));
+          }
+          if (e.mask_grgb) {
+            const float* gp = e.mask_grgb + (long long)tl.n * e.rgb_sn + (long long)h * e.rgb_sh + w;
+            g0 = __ldg(gp); g1 = __ldg(gp + e.rgb_sj); g2 = __ldg(gp + 2 * e.rgb_sj);
+          }
+        }
+      }
+      // every epilogue warp has left the previous tile (whose buffer is the other one) and this tile's vectors are visible
+      asm volatile("bar.sync 1, %0;" ::"n"(HC_EPI_THREADS) : "memory");
+      const uint32_t pst_s = smem_u32(pst) + 4u * (uint32_t)(ch * CW);
+      constexpr uint32_t VEC = 4u * (uint32_t)BN;                    // bytes between two staged vectors
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
       for (int dch = 0; dch < ndrains + (TWO_PASS ? 1 : 0); ++dch) {
@@ -622,39 +685,20 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(drained);
       }
-      // ---- fused epilogue + stores for this thread's position
-      const int qpos = tl.q0 + m;
-      const int h = hc_div(qpos, p.div_wp), wr = qpos - h * p.Wp;
-      const int w = tl.w0 + wr;
-      const bool valid = (wr < p.Wt) && (w < p.W) && (h < p.H);
+      // ---- fused epilogue + stores for this thread's position (everything that does not need the accumulators was set up above)
       if (valid) {
         const int n = tl.n;
-        const int o0 = tl.nt * BN + ch * CW;
-        const long long opix = e.o_off + p.probs[tl.prob].o_off + (long long)n * e.o_sn + (long long)h * e.o_sh + (long long)w * e.o_sw + o0;
-        float nz = 0.f;
-        if (e.noise != nullptr) nz = __ldg(e.noise + (long long)h * e.noise_sh + (long long)w * e.noise_sw);
-        const float* rs = e.row_scale ? e.row_scale + (long long)n * p.n_out + o0 : nullptr;
+        const float* rs = e.row_scale ? e.row_scale + (long long)n * p.n_out + o0 : nullptr;      // generic path only (global)
         const float* ps = e.post_scale ? e.post_scale + (long long)n * p.n_out + o0 : nullptr;
         const float* bs = e.bias ? e.bias + o0 : nullptr;
         const float* rw = e.rgb_acc ? e.rgb_w + (long long)n * 3 * p.n_out + o0 : nullptr;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
         const bool f32_aligned32 = (((uintptr_t)e.out_f32) & 31) == 0;     // element offsets are multiples of 8 floats (checked on the host)
-        const bool out32 = ((((uintptr_t)e.out_raw | (uintptr_t)e.out_raw_lo | (uintptr_t)e.out_hi | (uintptr_t)e.out_lo) & 31) == 0) &&
-                           ((((e.o_sn | e.o_sh | e.o_sw | e.o_off) * 2) & 31) == 0) && (p.n_out % 16 == 0);
-        // modulated-conv layers (the bulk of the epilogue work): lean path; alpha < 1 makes max(x, alpha x) the leaky ReLU
-        const bool modconv = rs && bs && e.act == 1 && e.clamp >= 0.f && e.alpha >= 0.f && e.alpha <= 1.f && e.gain > 0.f && !e.residual && !e.out_f32 &&
-                             (((uintptr_t)rs | (uintptr_t)bs | (uintptr_t)ps | (uintptr_t)rw) & 15) == 0 && out32;
         if (e.mask_y) {
-          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-          const float* mrw = nullptr;
-          if (e.mask_grgb) {
-            const float* gp = e.mask_grgb + (long long)n * e.rgb_sn + (long long)h * e.rgb_sh + w;
-            g0 = __ldg(gp); g1 = __ldg(gp + e.rgb_sj); g2 = __ldg(gp + 2 * e.rgb_sj);
-            mrw = e.rgb_w + (long long)n * 3 * p.n_out + o0;
-          }
-          hc_epilogue_actbwd<CW>(acc, e, acc_scale, ps, mrw, p.n_out, opix, g0, g1, g2);
+          hc_epilogue_actbwd<CW>(acc, e, acc_scale, pst_s + 2u * VEC, e.mask_grgb ? pst_s + 3u * VEC : 0u, VEC, opix, g0, g1, g2);
         } else if (modconv) {
-          hc_epilogue_modconv<CW>(acc, e, acc_scale, nz, rs, bs, ps, rw, p.n_out, opix, rgb0, rgb1, rgb2);
+          hc_epilogue_modconv<CW>(acc, e, nz, pst_s, pst_s + VEC, e.post_scale ? pst_s + 2u * VEC : 0u, e.rgb_acc ? pst_s + 3u * VEC : 0u, VEC, opix,
+                                  rgb0, rgb1, rgb2);
         } else {
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 8) {
@@ -728,7 +772,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
           }
         }
         }   // generic epilogue
-        if (rw) {
+        if (e.rgb_acc) {
           float* ra = e.rgb_acc + (long long)n * e.rgb_sn + (long long)h * e.rgb_sh + w;
           atomicAdd(ra, rgb0);
           atomicAdd(ra + e.rgb_sj, rgb1);
@@ -860,7 +904,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     p.nb = g_hconv_nb > 0 ? g_hconv_nb : (b_bytes >= 16384 ? 4 : (b_bytes >= 8192 ? 6 : 8));
     p.nb = p.nb < 2 ? 2 : (p.nb > 32 ? 32 : p.nb);
   }
-  const size_t smem_fixed = 1024 + (size_t)p.nb * b_bytes + 1024;
+  const size_t smem_fixed = 1024 + (size_t)p.nb * b_bytes + HC_BAR_BYTES + (size_t)hc_pstage_bytes(BN);
   const int wt_cands[4] = {g_hconv_wt > 0 ? g_hconv_wt : 64, 32, 16, 8};
   const bool short_tiles = d->C / KC <= 2;            // few MMAs per tile: prefetch A tiles further ahead
   p.Wt = 0;

@@ -46,10 +46,11 @@ def _forward(a, b, c):
     out = torch.empty(torch.broadcast_shapes(a.shape, b.shape, c.shape), dtype=a.dtype, device=a.device)
     if out.numel() == 0:
         return out
+    # the four host arrays must outlive the call: keep them in locals (ctypes.addressof of a temporary dangles)
+    shape, sa, sb, sc = _I64x4(*space), _I64x4(*_strides(a, space)), _I64x4(*_strides(b, space)), _I64x4(*_strides(c, space))
     with torch.cuda.device(a.device):
         _lib.call('smc_fma', _lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(out), _lib.DTYPE_CODE[a.dtype],
-                  ctypes.addressof(_I64x4(*space)), ctypes.addressof(_I64x4(*_strides(a, space))),
-                  ctypes.addressof(_I64x4(*_strides(b, space))), ctypes.addressof(_I64x4(*_strides(c, space))), _lib.stream())
+                  ctypes.addressof(shape), ctypes.addressof(sa), ctypes.addressof(sb), ctypes.addressof(sc), _lib.stream())
     return out
 
 
@@ -64,11 +65,11 @@ def _reduce_to(x, y, shape):
         return out.zero_()
     out_view = out.reshape((1,) * (_RANK - out.ndim) + tuple(out.shape))
     so = [0 if (out_view.shape[k] == 1 and space[k] > 1) else out_view.stride(k) for k in range(_RANK)]
+    shape, sx, sout = _I64x4(*space), _I64x4(*_strides(x, space)), _I64x4(*so)          # kept alive across the call
     sy = None if y is None else _I64x4(*_strides(y, space))
     with torch.cuda.device(x.device):
-        _lib.call('smc_fma_reduce', _lib.ptr(x), _lib.ptr(y), _lib.ptr(out), _lib.DTYPE_CODE[x.dtype], ctypes.addressof(_I64x4(*space)),
-                  ctypes.addressof(_I64x4(*_strides(x, space))), None if sy is None else ctypes.addressof(sy),
-                  ctypes.addressof(_I64x4(*so)), _lib.stream())
+        _lib.call('smc_fma_reduce', _lib.ptr(x), _lib.ptr(y), _lib.ptr(out), _lib.DTYPE_CODE[x.dtype], ctypes.addressof(shape),
+                  ctypes.addressof(sx), None if sy is None else ctypes.addressof(sy), ctypes.addressof(sout), _lib.stream())
     return out
 
 
