@@ -153,13 +153,15 @@ typedef struct smc_igemm_plan_info {
   int32_t super_tiles, grid;      /* (position, N) tiles; CTAs */
   int32_t smem_bytes, tmem_cols;
   int32_t prob_ntaps[4], prob_nsegs[4], prob_ndrains[4], prob_commits[4], prob_stages[4];
+  int32_t pair;                   /* 1: CTA-pair launch (cta_group::2, clusters of 2): super_tiles counts PAIRS of images, grid = 2 x clusters */
 } smc_igemm_plan_info;
 int smc_igemm_plan(const smc_igemm_desc* desc, smc_igemm_plan_info* out);
 /* Tuning / diagnostics knobs of the convolution path (process-global; set before launching, not thread-safe):
  *   key 0: halo-tile kernel (hconv.cu) use: 0 never, 1 auto (default), 2 whenever the shape is supported
  *   key 2: weight-stage ring depth (0 = by stage size)   key 3: tile width Wt in pixels (0 = widest that fits, <= 64)
  *   key 4: persistent grid size (0 = one CTA per SM)      key 5: bit mask of conv kinds routed to hconv.cu (diagnostics)
- *   key 6: smallest H * W the auto mode routes to hconv.cu (default 64) */
+ *   key 6: smallest H * W the auto mode routes to hconv.cu (default 64)
+ *   key 7: CTA-pair launches (tcgen05 cta_group::2) for 128-wide N tiles over an even number of images: 1 on (default), 0 off */
 int smc_igemm_config(int key, int value);
 
 /* ---- synthesis glue (synth.cu) -------------------------------------------------------------------

@@ -51,7 +51,7 @@ class IgemmDesc(ctypes.Structure):
 class IgemmPlanInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ('kernel', 'bn', 'kc', 'mode', 'Wt', 'Wp', 'RB', 'na_hi', 'na_lo', 'nb', 'b_resident', 'a_share', 'nprob',
                                               'kchunks', 'super_tiles', 'grid', 'smem_bytes', 'tmem_cols')] + \
-               [(n, ctypes.c_int32 * 4) for n in ('prob_ntaps', 'prob_nsegs', 'prob_ndrains', 'prob_commits', 'prob_stages')]
+               [(n, ctypes.c_int32 * 4) for n in ('prob_ntaps', 'prob_nsegs', 'prob_ndrains', 'prob_commits', 'prob_stages')] + [('pair', ctypes.c_int32)]
 
 
 class UpfirdnParams(ctypes.Structure):
@@ -126,7 +126,8 @@ def lib():
         if handle.smc_abi_version() != 1:
             raise RuntimeError('libstylemc_b200.so ABI version mismatch; rebuild')
         _lib = handle
-        for key, env in ((0, 'STYLEMC_HCONV'), (2, 'STYLEMC_HCONV_NB'), (3, 'STYLEMC_HCONV_WT'), (4, 'STYLEMC_HCONV_GRID'), (5, 'STYLEMC_HCONV_MASK'), (6, 'STYLEMC_HCONV_MINPOS')):
+        for key, env in ((0, 'STYLEMC_HCONV'), (2, 'STYLEMC_HCONV_NB'), (3, 'STYLEMC_HCONV_WT'), (4, 'STYLEMC_HCONV_GRID'), (5, 'STYLEMC_HCONV_MASK'), (6, 'STYLEMC_HCONV_MINPOS'),
+                         (7, 'STYLEMC_HCONV_PAIR')):
             if os.environ.get(env):          # diagnostics only: A/B the halo-tile conv kernel against the per-tap kernel
                 handle.smc_igemm_config(key, int(os.environ[env]))
         for key, env in ((0, 'STYLEMC_FIR_ACT3'), (1, 'STYLEMC_FIR_BWD3'), (2, 'STYLEMC_ACT_BWD2'), (3, 'STYLEMC_UPFIRDN_ROWS'), (4, 'STYLEMC_RESAMPLE_VFIRST'),

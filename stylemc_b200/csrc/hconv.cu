@@ -84,6 +84,7 @@ struct HcParams {
   int col_tiles, tiles_per_col, n_tiles_n;
   int total_tiles;              // nprob * super_tiles
   int nprob, super_tiles;
+  int pair;                     // CTA-pair launch (cta_group::2): super tiles are pairs of images (2 q + cluster rank)
   HcDiv div_ntn, div_tpc, div_ct, div_wp;   // n_tiles_n, tiles_per_col, col_tiles, Wp
   int ngroups, kchunks, nb;
   HcProb probs[HC_MAX_PROBS];
@@ -133,16 +134,29 @@ __device__ __forceinline__ bool elect_one() {
 }
 // one tap of one pass for both 128-row blocks: 2 * KC/16 MMAs; `first` = 0 makes the first MMA of each block overwrite
 // (BLK = TMEM column stride between the two blocks; the MMA's N is in idesc)
-template <int BLK, int KC>
+template <int BLK, int KC, bool PAIR = false>
 __device__ __forceinline__ void hc_issue_tap(uint32_t tm, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate_first) {
   constexpr uint32_t MBOFF = (uint32_t)(128 * KC * 2) >> 4;
 #pragma unroll
   for (int mb = 0; mb < HC_MB; ++mb) {
-    umma_f16(tm + (uint32_t)(mb * BLK), HcDesc<KC>::make(alo + mb * MBOFF), HcDesc<KC>::make(blo), idesc, accumulate_first);
+    if (PAIR) {
+      umma_f16_2sm(tm + (uint32_t)(mb * BLK), HcDesc<KC>::make(alo + mb * MBOFF), HcDesc<KC>::make(blo), idesc, accumulate_first);
 #pragma unroll
-    for (int k = 1; k < KC / 16; ++k)
-      umma_f16_acc(tm + (uint32_t)(mb * BLK), HcDesc<KC>::make(alo + mb * MBOFF + 2 * k), HcDesc<KC>::make(blo + 2 * k), idesc);
+      for (int k = 1; k < KC / 16; ++k)
+        umma_f16_2sm(tm + (uint32_t)(mb * BLK), HcDesc<KC>::make(alo + mb * MBOFF + 2 * k), HcDesc<KC>::make(blo + 2 * k), idesc, 1u);
+    } else {
+      umma_f16(tm + (uint32_t)(mb * BLK), HcDesc<KC>::make(alo + mb * MBOFF), HcDesc<KC>::make(blo), idesc, accumulate_first);
+#pragma unroll
+      for (int k = 1; k < KC / 16; ++k)
+        umma_f16_acc(tm + (uint32_t)(mb * BLK), HcDesc<KC>::make(alo + mb * MBOFF + 2 * k), HcDesc<KC>::make(blo + 2 * k), idesc);
+    }
   }
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void hc_commit(uint64_t* bar) {
+  if (PAIR) tcgen05_commit_2sm(bar);
+  else tcgen05_commit(bar);
 }
 
 struct HcTile {
@@ -155,9 +169,10 @@ struct HcTile {
 struct HcWalk {
   int sup, prob;
 };
-__device__ __forceinline__ HcWalk hc_walk_begin() { return HcWalk{(int)blockIdx.x, 0}; }
+// a CTA pair walks the list together: cluster id and cluster count take the place of block id and grid size
+__device__ __forceinline__ HcWalk hc_walk_begin(const HcParams& p) { return HcWalk{(int)(p.pair ? blockIdx.x >> 1 : blockIdx.x), 0}; }
 __device__ __forceinline__ void hc_walk_next(const HcParams& p, HcWalk& w) {
-  if (++w.prob == p.nprob) { w.prob = 0; w.sup += (int)gridDim.x; }
+  if (++w.prob == p.nprob) { w.prob = 0; w.sup += (int)(p.pair ? gridDim.x >> 1 : gridDim.x); }
 }
 __device__ __forceinline__ HcTile hc_tile(const HcParams& p, const HcWalk& w) {
   HcTile r;
@@ -171,7 +186,7 @@ __device__ __forceinline__ HcTile hc_tile(const HcParams& p, const HcWalk& w) {
   t = q;
   q = hc_div(t, p.div_ct);
   const int ct = t - q * p.col_tiles;
-  r.n = q;
+  r.n = p.pair ? 2 * q + (int)(blockIdx.x & 1u) : q;     // pair: the even CTA takes image 2q, the odd one 2q + 1 (same tile geometry)
   r.w0 = ct * p.Wt;
   r.q0 = ti * HC_MT;
   r.hfirst = hc_div(r.q0, p.div_wp);
@@ -355,7 +370,7 @@ __device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const
 // N = BN into the cross columns: 2 MMAs per tap and k-step instead of 3.  Both halves are drained per chunk (the first MMA of a
 // chunk overwrites all 2 BN columns); two sets alternate per chunk.
 enum { HC_X1 = 0, HC_X3_TWO_PASS = 1, HC_X3_MERGED = 2 };
-template <int BN, int KC, int MODE>
+template <int BN, int KC, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB,
                                                               const __grid_constant__ HcParams p) {
@@ -363,15 +378,18 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
   constexpr bool TWO_PASS = MODE == HC_X3_TWO_PASS;
   constexpr bool MERGED = MODE == HC_X3_MERGED;
   constexpr int ROWB = KC * 2;                                 // bytes per position row
-  constexpr int B_TILE = BN * ROWB;                            // one weight tile (hi or lo plane of a tap)
-  constexpr int B_BYTES = (MERGED ? 2 : 1) * B_TILE;           // one ring stage
+  constexpr int B_TILE = (PAIR ? BN / 2 : BN) * ROWB;          // one weight tile (hi or lo plane of a tap); a pair holds half each
+  constexpr int B_BYTES = (MERGED ? 2 : 1) * B_TILE;           // one ring stage (per CTA)
+  constexpr uint32_t B_TX = (PAIR ? 2u : 1u) * (uint32_t)B_BYTES;   // bytes arriving on the (leader's) full barrier of a stage
+  static_assert(!PAIR || !MERGED, "merged weight stages put B_hi and B_lo in different halves of N: not split across a CTA pair");
   constexpr int CW = BN / 2;                                   // accumulator columns per epilogue thread
   constexpr int BLK = (MERGED ? 2 : 1) * BN;                   // TMEM columns of one 128-row block
   constexpr int SETCOLS = (TWO_PASS ? 2 : 1) * HC_MB * BLK;
   constexpr int SETS = (2 * SETCOLS <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (SETS * SETCOLS) < 32 ? 32 : (SETS * SETCOLS);
-  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t MMA_M = PAIR ? 256 : 128;                 // cta_group::2: 128 rows from each CTA of the pair
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
   constexpr int MAXB = 32;
   static_assert(TWO_PASS || SETS == 2, "x1 / merged alternate two sets per chunk");
   static_assert(!MERGED || BN <= 64, "merged B needs N = 2 BN <= 128 to pay off");
@@ -411,20 +429,27 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&main_full[i], 1);
-      mbar_init(&main_drained[i], 16);
+      mbar_init(&main_drained[i], PAIR ? 32 : 16);       // the leader's copy collects the epilogue warps of both CTAs
       mbar_init(&cross_full[i], 1);
-      mbar_init(&cross_drained[i], 16);
+      mbar_init(&cross_drained[i], PAIR ? 32 : 16);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {          // the same warp of both CTAs allocates; both receive the same column address
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();          // barriers of BOTH CTAs are initialised before any remote arrival / TMA transaction
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool leader = !PAIR || (blockIdx.x & 1u) == 0;     // cluster dims (2, 1, 1): rank in the pair = blockIdx.x & 1
 
   // A buffer of (step, plane): hi tiles cycle through buffers [0, na_hi), lo tiles through [na_hi, na_hi + na_lo)
   const uint32_t na_hi = (uint32_t)p.na_hi, na_lo = (uint32_t)p.na_lo;
@@ -436,23 +461,26 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     if (elect_one()) {
       uint32_t eph = 0;                 // bit b: number of loads into buffer b so far, mod 2
       uint32_t step = 0;
-      for (HcWalk wk = hc_walk_begin(); wk.sup < p.super_tiles; hc_walk_next(p, wk)) {
+      for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk)) {
         if (p.a_share && wk.prob > 0) continue;            // same position tile as problem 0: its buffers are reused
         const HcTile tl = hc_tile(p, wk);
         const int wbox = tl.w0 - p.padL, hbox = tl.hfirst - p.padT;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int g = 0; g < p.ngroups; ++g, ++step) {
+            // pair: each CTA loads the tile of its own image into its own buffer; both transactions land on the LEADER's full barrier
             const int hb = hi_buf(step);
             mbar_wait(&a_empty[hb], ((eph >> hb) & 1u) ^ 1u);
             eph ^= 1u << hb;
-            mbar_expect_tx(&a_full[hb], p.a_box_bytes);
-            tma_load_4d(a_buf + (size_t)hb * p.a_buf_bytes, &mapA, &a_full[hb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_hi);
+            if (leader) mbar_expect_tx(&a_full[hb], (PAIR ? 2u : 1u) * p.a_box_bytes);
+            if (PAIR) tma_load_4d_2sm(a_buf + (size_t)hb * p.a_buf_bytes, &mapA, &a_full[hb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_hi);
+            else tma_load_4d(a_buf + (size_t)hb * p.a_buf_bytes, &mapA, &a_full[hb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_hi);
             if (X3) {
               const int lb = lo_buf(step);
               mbar_wait(&a_empty[lb], ((eph >> lb) & 1u) ^ 1u);
               eph ^= 1u << lb;
-              mbar_expect_tx(&a_full[lb], p.a_box_bytes);
-              tma_load_4d(a_buf + (size_t)lb * p.a_buf_bytes, &mapA, &a_full[lb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_lo);
+              if (leader) mbar_expect_tx(&a_full[lb], (PAIR ? 2u : 1u) * p.a_box_bytes);
+              if (PAIR) tma_load_4d_2sm(a_buf + (size_t)lb * p.a_buf_bytes, &mapA, &a_full[lb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_lo);
+              else tma_load_4d(a_buf + (size_t)lb * p.a_buf_bytes, &mapA, &a_full[lb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_lo);
             }
           }
         }
@@ -464,8 +492,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       uint32_t bs = 0, bph = 0;
       const uint32_t nb = (uint32_t)p.nb;
       // resident weights: the stages of ALL problems are loaded once, problem-major (slot = HcProb::stage_base + running index)
-      for (HcWalk wk = hc_walk_begin(); wk.sup < p.super_tiles; hc_walk_next(p, wk)) {
-        if (p.b_resident && wk.sup != (int)blockIdx.x) break;       // resident: one pass over the problems (n_tiles_n == 1)
+      for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk)) {
+        if (p.b_resident && wk.sup != (int)blockIdx.x) break;   // (never combined with pair launches)       // resident: one pass over the problems (n_tiles_n == 1)
         const int nt = wk.sup - hc_div(wk.sup, p.div_ntn) * p.n_tiles_n;
         const HcProb& pr = p.probs[wk.prob];
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -474,7 +502,11 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             for (int pass = 0; pass < (TWO_PASS ? 2 : 1); ++pass) {
               for (int tp = tb; tp < te; ++tp) {
                 mbar_wait(&b_empty[bs], bph ^ 1u);
-                mbar_expect_tx(&b_full[bs], B_BYTES);
+                if (leader) mbar_expect_tx(&b_full[bs], B_TX);
+                if (PAIR)       // each CTA fetches its half of the tile's BN weight rows
+                  tma_load_2d_2sm(b_buf + (size_t)bs * B_BYTES, &mapB, &b_full[bs], kc * KC,
+                                  (pass == 0 ? p.taps[tp].brow_hi : p.taps[tp].brow_lo) + nt * BN + (int)(blockIdx.x & 1u) * (BN / 2));
+                else
                 tma_load_2d(b_buf + (size_t)bs * B_BYTES, &mapB, &b_full[bs], kc * KC,
                             (pass == 0 ? p.taps[tp].brow_hi : p.taps[tp].brow_lo) + nt * BN);
                 if (MERGED)
@@ -490,7 +522,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     // ---------------- MMA issuer: ONE elected lane runs the whole role.  elect.sync (rather than lane == 0) tells ptxas
     // that a single thread is active, so the tcgen05 operands go to uniform registers with one R2UR each instead of a
     // per-lane waterfall loop (15 instructions per MMA), and the issue loop stays far below the MMA duration.
-    if (elect_one()) {
+    if (leader && elect_one()) {
       uint32_t aph = 0;                 // bit b: number of tiles consumed from A buffer b so far, mod 2
       uint32_t step = 0, bs = 0, bph = 0, chunk_ctr = 0, tile_ctr = 0;
       uint32_t nm0 = 0, nm1 = 0, nc0 = 0, nc1 = 0;     // chunks committed so far per set (main / cross)
@@ -499,7 +531,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const bool resident = p.b_resident != 0;
       uint32_t a_hi = 0, a_lo = 0;                         // live across the problems of a tile when the A tile is shared
       int hb = 0, lb = 0;
-      for (HcWalk wk = hc_walk_begin(); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
+      for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
         const HcTile tl = hc_tile(p, wk);
         const HcProb& pr = p.probs[tl.prob];
         const bool a_load = !(p.a_share && tl.prob > 0);              // this tile waits for its own A buffers
@@ -546,22 +578,22 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
                 const uint32_t tm = tmem_base + set * (uint32_t)SETCOLS;
                 if (MERGED) {
                   // A_hi * [B_hi; B_lo] -> (main | cross), then A_lo * B_hi -> cross
-                  hc_issue_tap<BLK, KC>(tm, (a_hi + roff) >> 4, blo, IDESC2, fresh ? 0u : 1u);
-                  hc_issue_tap<BLK, KC>(tm + (uint32_t)BN, (a_lo + roff) >> 4, blo, IDESC, 1u);
+                  hc_issue_tap<BLK, KC, PAIR>(tm, (a_hi + roff) >> 4, blo, IDESC2, fresh ? 0u : 1u);
+                  hc_issue_tap<BLK, KC, PAIR>(tm + (uint32_t)BN, (a_lo + roff) >> 4, blo, IDESC, 1u);
                 } else {
-                  if (pass == 0) hc_issue_tap<BLK, KC>(tm, (a_hi + roff) >> 4, blo, IDESC, fresh ? 0u : 1u);
+                  if (pass == 0) hc_issue_tap<BLK, KC, PAIR>(tm, (a_hi + roff) >> 4, blo, IDESC, fresh ? 0u : 1u);
                   if (TWO_PASS)                            // pass 0: A_lo * B_hi, pass 1: A_hi * B_lo -> cross
-                    hc_issue_tap<BLK, KC>(tm + (uint32_t)(HC_MB * BN), ((pass == 0 ? a_lo : a_hi) + roff) >> 4, blo, IDESC, fresh_cross ? 0u : 1u);
+                    hc_issue_tap<BLK, KC, PAIR>(tm + (uint32_t)(HC_MB * BN), ((pass == 0 ? a_lo : a_hi) + roff) >> 4, blo, IDESC, fresh_cross ? 0u : 1u);
                 }
-                if (!resident) tcgen05_commit(&b_empty[bs]);
+                if (!resident) hc_commit<PAIR>(&b_empty[bs]);
                 if (pass == 0) fresh = false;
                 fresh_cross = false;
                 if (++bs == nb) { bs = 0; bph ^= 1u; }
               }
               if (TWO_PASS && pass == 0) {
-                if (sflags & HC_SEG_LAST) tcgen05_commit(&a_empty[lb]);   // the lo tile is only read by B_hi passes
+                if (sflags & HC_SEG_LAST) hc_commit<PAIR>(&a_empty[lb]);   // the lo tile is only read by B_hi passes
                 if (main_done) {                                          // drained while the B_lo pass runs
-                  tcgen05_commit(&main_full[set_t]);
+                  hc_commit<PAIR>(&main_full[set_t]);
                   if (set_t) ++nm1; else ++nm0;
                   fresh = true;
                 }
@@ -569,21 +601,21 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             }
             if (!TWO_PASS && main_done) {                  // x1 / merged: the two sets alternate per chunk
               const uint32_t set = chunk_ctr & 1u;
-              tcgen05_commit(&main_full[set]);
+              hc_commit<PAIR>(&main_full[set]);
               if (set) ++nm1; else ++nm0;
               ++chunk_ctr;
               fresh = true;
             }
             if ((sflags & HC_SEG_LAST) && a_free) {
-              if (MERGED) tcgen05_commit(&a_empty[lb]);
-              tcgen05_commit(&a_empty[hb]);
+              if (MERGED) hc_commit<PAIR>(&a_empty[lb]);
+              hc_commit<PAIR>(&a_empty[hb]);
               ++step;
             }
           }
           if (chunk_ends) in_chunk = 0; else ++in_chunk;
         }
         if (TWO_PASS) {
-          tcgen05_commit(&cross_full[set_t]);
+          hc_commit<PAIR>(&cross_full[set_t]);
           if (set_t) ++nc1; else ++nc0;
         }
       }
@@ -599,8 +631,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     const float acc_scale = e.acc_scale != 0.f ? e.acc_scale : 1.f;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BLK + ch * CW);
     uint32_t em0 = 0, em1 = 0, ec0 = 0, ec1 = 0, chunk_ctr = 0, tile_ctr = 0;
+    int st_n = -1, st_nt = -1;               // (image, N tile) whose parameter vectors are staged in pstage[st_buf]
+    uint32_t st_buf = 0;
     float acc[CW];
-    for (HcWalk wk = hc_walk_begin(); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
+    for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
       const HcTile tl = hc_tile(p, wk);
       const int ndrains = p.probs[tl.prob].ndrains;
       const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
@@ -619,8 +653,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const bool modconv = e.row_scale && e.bias && e.act == 1 && e.clamp >= 0.f && e.alpha >= 0.f && e.alpha <= 1.f && e.gain > 0.f && !e.residual &&
                            !e.out_f32 && !e.mask_y && out32;
       const bool staged = modconv || e.mask_y != nullptr;
-      float* pst = pstage + (tile_ctr & 1u) * (uint32_t)(HC_PSTAGE_VECS * BN);
-      if (staged) {
+      // the vectors depend on (image, N tile) only: consecutive tiles of a CTA mostly share them (always at 512 / 1024 px), so they are
+      // re-staged -- into the other buffer, followed by one barrier of the 16 epilogue warps -- only when that pair changes; every
+      // epilogue warp walks the same tile list, so all of them take this branch together
+      if (staged && (tl.n != st_n || tl.nt != st_nt)) {
+        st_n = tl.n; st_nt = tl.nt; st_buf ^= 1u;
+        float* pst = pstage + st_buf * (uint32_t)(HC_PSTAGE_VECS * BN);
         const int et = (int)threadIdx.x - 96;
         const long long nb_off = (long long)tl.n * p.n_out + tl.nt * BN;
         for (int i = et; i < HC_PSTAGE_VECS * BN; i += HC_EPI_THREADS) {
@@ -632,6 +670,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
           else if (e.rgb_w) v = __ldg(e.rgb_w + ((long long)tl.n * 3 + (which - 3)) * p.n_out + tl.nt * BN + c);
           pst[i] = v;
         }
+        // all 16 warps have left the tiles that used the buffer being replaced next time, and this buffer is visible to all of them
+        asm volatile("bar.sync 1, %0;" ::"n"(HC_EPI_THREADS) : "memory");
       }
       float nz = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
       if (valid) {
@@ -649,9 +689,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
           }
         }
       }
-      // every epilogue warp has left the previous tile (whose buffer is the other one) and this tile's vectors are visible
-      asm volatile("bar.sync 1, %0;" ::"n"(HC_EPI_THREADS) : "memory");
-      const uint32_t pst_s = smem_u32(pst) + 4u * (uint32_t)(ch * CW);
+      const uint32_t pst_s = smem_u32(pstage + st_buf * (uint32_t)(HC_PSTAGE_VECS * BN)) + 4u * (uint32_t)(ch * CW);
       constexpr uint32_t VEC = 4u * (uint32_t)BN;                    // bytes between two staged vectors
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
@@ -683,7 +721,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(drained);
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(drained); else mbar_arrive(drained); }
       }
       // ---- fused epilogue + stores for this thread's position (everything that does not need the accumulators was set up above)
       if (valid) {
@@ -782,10 +820,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();          // neither CTA leaves while the other may still read its operands or signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -796,6 +836,7 @@ static int g_hconv_wt = 0;   // 0: widest that fits (<= 64)
 static int g_hconv_grid = 0;
 static int g_hconv_minpos = 64;     // auto mode: smallest H * W routed to this kernel
 static int g_hconv_mask = 7;   // bit 0: single-source convs with > 4 taps, bit 1: <= 4 taps, bit 2: multi-source (up2 dgrad)
+static int g_hconv_pair = 1;   // CTA-pair (cta_group::2) launches for 128-wide N tiles over an even number of images
 
 static smc_igemm_plan_info* g_plan_out = nullptr;   // set only inside smc_igemm_plan (diagnostics, not thread-safe)
 
@@ -806,6 +847,7 @@ void hconv_config(int key, int value) {
   if (key == 4) g_hconv_grid = value;
   if (key == 5) g_hconv_mask = value;
   if (key == 6) g_hconv_minpos = value;
+  if (key == 7) g_hconv_pair = value;
 }
 
 template <int BN, int KC, int MODE>
@@ -813,6 +855,26 @@ static int hc_launch(const CUtensorMap& ma, const CUtensorMap& mb, const HcParam
   static SmemOptIn opt_in;
   if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE>, smem); e != cudaSuccess) return (int)e;
   hconv_kernel<BN, KC, MODE><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+// CTA-pair launch: clusters of two CTAs (the two SMs of a TPC), grid = 2 x clusters
+template <int BN, int KC, int MODE>
+static int hc_launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
+  static SmemOptIn opt_in;
+  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE, true>, smem); e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(HC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hconv_kernel<BN, KC, MODE, true>, ma, mb, p);
+  if (e != cudaSuccess) return (int)e;
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
@@ -895,9 +957,12 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   // tile whose A buffers fit (wider = fewer discarded halo positions, but more halo rows fetched per tile)
   const int mode = !x3 ? HC_X1 : ((BN <= 64 && !(g_hconv_mask & 256)) ? HC_X3_MERGED : HC_X3_TWO_PASS);
   const int passes = mode == HC_X3_TWO_PASS ? 2 : 1;
-  const int b_bytes = BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1);        // one ring stage
   const int stages_per_tile = (d->C / KC) * T * passes;      // all problems together
-  p.b_resident = (d->n_out == BN && stages_per_tile <= 32 && stages_per_tile * b_bytes <= 96 * 1024) ? 1 : 0;
+  p.b_resident = (d->n_out == BN && stages_per_tile <= 32 && stages_per_tile * (BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1)) <= 96 * 1024) ? 1 : 0;
+  // CTA pair (cta_group::2): the 128-wide N tiles are bound by the shared-memory operand fetch of the MMAs (8 KB per 128 x 128 x 16
+  // instruction); a pair reads the weight tile once for 2 x 128 rows.  The two CTAs take the same tile of two consecutive images.
+  p.pair = (g_hconv_pair && BN == 128 && mode != HC_X3_MERGED && d->n_img % 2 == 0 && !p.b_resident) ? 1 : 0;
+  const int b_bytes = BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1) / (p.pair ? 2 : 1);        // one ring stage (per CTA)
   if (p.b_resident) {
     p.nb = stages_per_tile;
   } else {
@@ -940,7 +1005,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   p.nprob = d->nprob > 1 ? d->nprob : 1;
   if (p.nprob > HC_MAX_PROBS) return SMC_EINVAL;
   {
-    const long long tt = (long long)d->n_img * p.col_tiles * p.tiles_per_col * p.n_tiles_n;
+    const long long tt = (long long)(p.pair ? d->n_img / 2 : d->n_img) * p.col_tiles * p.tiles_per_col * p.n_tiles_n;
     if (tt * p.nprob > 0x7fffffffLL) return SMC_ETOOLARGE;
     p.super_tiles = (int)tt;
     p.total_tiles = (int)tt * p.nprob;
@@ -1052,7 +1117,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   }
   for (int q = p.nprob; q < HC_MAX_PROBS; ++q) p.probs[q] = p.probs[0];
   // (two-pass mode releases the lo tile after each B_hi pass, so it keeps one load per problem)
-  p.a_share = (p.nprob > 1 && p.kchunks == 1 && mode != HC_X3_TWO_PASS && !(g_hconv_mask & 512)) ? 1 : 0;
+  p.a_share = (p.nprob > 1 && p.kchunks == 1 && mode != HC_X3_TWO_PASS && !(g_hconv_mask & 512) && !p.pair) ? 1 : 0;
   p.a_box_bytes = (uint32_t)(p.RB * p.Wp) * (uint32_t)(KC * 2);
   p.a_buf_bytes = ((uint32_t)(p.RB * p.Wp + 8) * (uint32_t)(KC * 2) + 1023u) & ~1023u;
   p.epi = d->epi;
@@ -1080,7 +1145,9 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     o.Wt = p.Wt; o.Wp = p.Wp; o.RB = p.RB; o.na_hi = p.na_hi; o.na_lo = p.na_lo; o.nb = p.nb;
     o.b_resident = p.b_resident; o.a_share = p.a_share; o.nprob = p.nprob; o.kchunks = p.kchunks;
     o.super_tiles = p.super_tiles;
+    o.pair = p.pair;
     o.grid = p.super_tiles < (g_hconv_grid > 0 ? g_hconv_grid : kNumSMs) ? p.super_tiles : (g_hconv_grid > 0 ? g_hconv_grid : kNumSMs);
+    if (p.pair) o.grid = 2 * (p.super_tiles < kNumSMs / 2 ? p.super_tiles : kNumSMs / 2);
     o.smem_bytes = (int32_t)smem;
     {                                  // TMEM columns exactly as hconv_kernel derives them from <BN, MODE>
       const int blk = (mode == HC_X3_MERGED ? 2 : 1) * BN;
@@ -1128,7 +1195,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->C, (cuuint64_t)d->rowsB};
     cuuint64_t strides[1] = {(cuuint64_t)d->ldb * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(p.pair ? BN / 2 : BN)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->B), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1136,6 +1203,14 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     if (r != CUDA_SUCCESS) return SMC_EDRIVER;
   }
   const int max_grid = g_hconv_grid > 0 ? g_hconv_grid : sm_count();
+  if (p.pair) {
+    const int max_clusters = max_grid / 2;
+    const int grid2 = 2 * (p.super_tiles < max_clusters ? (int)p.super_tiles : max_clusters);
+    if (KC == 64) return mode == HC_X1 ? hc_launch_pair<128, 64, HC_X1>(ma, mb, p, grid2, smem, st)
+                                       : hc_launch_pair<128, 64, HC_X3_TWO_PASS>(ma, mb, p, grid2, smem, st);
+    return mode == HC_X1 ? hc_launch_pair<128, 32, HC_X1>(ma, mb, p, grid2, smem, st)
+                         : hc_launch_pair<128, 32, HC_X3_TWO_PASS>(ma, mb, p, grid2, smem, st);
+  }
   const int grid = p.super_tiles < max_grid ? (int)p.super_tiles : max_grid;
   if (KC == 64) {
     if (BN == 128) return hc_launch_x<128, 64>(mode, ma, mb, p, grid, smem, st);

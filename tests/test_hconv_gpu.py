@@ -194,3 +194,31 @@ def test_promoted_accumulation_is_fp32_grade_on_a_long_chain():
                b_rows_per_tap=9 * o, out_f32=out)
     ref = F.conv2d(x.double(), wt.double(), padding=1).permute(0, 2, 3, 1)
     assert rel(out, ref) <= 1.5e-6
+
+
+@pytest.mark.parametrize('x3', [True, False])
+@pytest.mark.parametrize('n,c,o,h,w', [(2, 128, 128, 40, 40), (4, 64, 256, 32, 32), (6, 256, 128, 16, 24), (2, 128, 128, 64, 64)])
+def test_cta_pair_launch_equals_single_cta_kernel_bitwise(n, c, o, h, w, x3):
+    """CTA-pair launches (tcgen05 cta_group::2: two CTAs of a cluster share every weight tile, one image each; smc_igemm_config key 7)
+    run the same MMAs in the same order as the single-CTA kernel: identical bits, and both match fp64."""
+    from stylemc_b200 import _lib, gemm
+    g = torch.Generator(device='cuda').manual_seed(7)
+    x = torch.randn(n, c, h, w, device='cuda', generator=g)
+    wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.05
+    if not x3:
+        x, wt = x.half().float(), wt.half().float()
+    A, B = planes(x, x3), wmat(wt, x3)
+    outs = []
+    try:
+        for pair in (0, 1):
+            _lib.call('smc_igemm_config', 7, pair)
+            out = torch.empty(n, h, w, o, device='cuda')
+            gemm.igemm(A, B, n, h, w, o, gemm.TAPS_3X3, precision='x3' if x3 else 'x1', acc_chunk_k=512 if x3 else 0,
+                       a_plane_stride_imgs=n, b_rows_per_tap=9 * o, out_f32=out)
+            outs.append(out)
+    finally:
+        _lib.call('smc_igemm_config', 7, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    ref = F.conv2d(x.double(), wt.double(), padding=1).permute(0, 2, 3, 1)
+    assert rel(outs[1], ref) <= (2e-6 if x3 else 1e-5)

@@ -60,7 +60,11 @@ def check(o, base_taps, x3, halo):
     assert o.kernel == 1
     assert o.smem_bytes <= 227 * 1024
     assert 32 <= o.tmem_cols <= 512 and o.tmem_cols & (o.tmem_cols - 1) == 0
-    assert 1 <= o.grid <= 148 and o.grid <= o.super_tiles
+    if o.pair:       # CTA-pair launch (cta_group::2): clusters of two CTAs over pairs of images, 128-wide N tiles, never the merged-B mode
+        assert o.bn == 128 and o.mode != 2 and not o.b_resident and not o.a_share
+        assert 2 <= o.grid <= 148 and o.grid % 2 == 0 and o.grid // 2 <= o.super_tiles
+    else:
+        assert 1 <= o.grid <= 148 and o.grid <= o.super_tiles
     assert o.Wp - o.Wt == halo and o.Wt <= 64
     assert o.na_hi >= 2 and (o.na_lo >= 1 if x3 else o.na_lo == 0)
     assert sum(o.prob_ntaps[q] for q in range(o.nprob)) == base_taps
@@ -89,6 +93,7 @@ def test_every_synthesis_gemm_of_the_1024_network_has_a_plan(n, x3):
                 continue
             assert rc == 0, (res, rc)
             check(o, 9, x3, halo=2)
+            assert bool(o.pair) == (c >= 128 and n % 2 == 0)         # image pairs: an odd batch keeps the single-CTA kernel
             assert (o.mode == 0) == (not x3)
             if x3:
                 assert o.mode == (2 if c <= 64 else 1)                  # merged-B below 128 output channels

@@ -207,7 +207,7 @@ def test_fma_vs_oracle_shapes_and_second_order(dtype):
     from stylemc_b200.ops import fma
     tol = {torch.float32: 2e-6, torch.float16: 2e-3, torch.float64: 1e-12}[dtype]
     for sa, sb, sc in (((3, 5, 40, 40), (3, 5, 1, 1), (40, 40)), ((2, 1, 7), (4, 1), (1,)), ((6,), (), (6,)), ((2, 3, 4, 4), (2, 3, 4, 4), (1, 3, 1, 1))):
-        ta, tb, tc = (torch.randn(*s, generator=gen, dtype=torch.float64) for s in (sa, sb, sc))
+        ta, tb, tc = (torch.randn(s, generator=gen, dtype=torch.float64) for s in (sa, sb, sc))
         ra, rb, rc = (t.clone().requires_grad_(True) for t in (ta, tb, tc))
         yr = o_conv.fma(ra, rb, rc)
         dy = torch.randn(yr.shape, generator=gen, dtype=torch.float64)
