@@ -84,6 +84,7 @@ struct HcParams {
   int col_tiles, tiles_per_col, n_tiles_n;
   int total_tiles;              // nprob * super_tiles
   int nprob, super_tiles;
+  int a_lo_term;                // split precision: 1 = A_lo * B_hi is computed (three terms), 0 = the A operand has a hi plane only (two terms)
   int pair;                     // CTA-pair launch (cta_group::2): super tiles are pairs of images (2 q + cluster rank)
   HcDiv div_ntn, div_tpc, div_ct, div_wp;   // n_tiles_n, tiles_per_col, col_tiles, Wp
   int ngroups, kchunks, nb;
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             if (leader) mbar_expect_tx(&a_full[hb], (PAIR ? 2u : 1u) * p.a_box_bytes);
             if (PAIR) tma_load_4d_2sm(a_buf + (size_t)hb * p.a_buf_bytes, &mapA, &a_full[hb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_hi);
             else tma_load_4d(a_buf + (size_t)hb * p.a_buf_bytes, &mapA, &a_full[hb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_hi);
-            if (X3) {
+            if (X3 && p.a_lo_term) {
               const int lb = lo_buf(step);
               mbar_wait(&a_empty[lb], ((eph >> lb) & 1u) ^ 1u);
               eph ^= 1u << lb;
@@ -529,6 +530,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const uint32_t nb = (uint32_t)p.nb;
       const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
       const bool resident = p.b_resident != 0;
+      const bool alo = X3 && p.a_lo_term != 0;             // the A operand has a lo plane (A_lo * B_hi is computed)
       uint32_t a_hi = 0, a_lo = 0;                         // live across the problems of a tile when the A tile is shared
       int hb = 0, lb = 0;
       for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
@@ -550,15 +552,15 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             const bool main_done = (sflags & HC_SEG_COMMIT) && (!(sflags & HC_SEG_SLABEND) || chunk_ends);
             if ((sflags & HC_SEG_FIRST) && a_load) {
               hb = hi_buf(step);
-              lb = lo_buf(step);
               mbar_wait(&a_full[hb], (aph >> hb) & 1u);
               aph ^= 1u << hb;
-              if (X3) {
+              if (alo) {
+                lb = lo_buf(step);
                 mbar_wait(&a_full[lb], (aph >> lb) & 1u);
                 aph ^= 1u << lb;
+                a_lo = a_base + (uint32_t)lb * p.a_buf_bytes + (uint32_t)rel0 * (uint32_t)ROWB;
               }
               a_hi = a_base + (uint32_t)hb * p.a_buf_bytes + (uint32_t)rel0 * (uint32_t)ROWB;
-              a_lo = a_base + (uint32_t)lb * p.a_buf_bytes + (uint32_t)rel0 * (uint32_t)ROWB;
             }
             for (int pass = 0; pass < (TWO_PASS ? 2 : 1); ++pass) {
               for (int tp = tb; tp < te; ++tp) {
@@ -579,19 +581,20 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
                 if (MERGED) {
                   // A_hi * [B_hi; B_lo] -> (main | cross), then A_lo * B_hi -> cross
                   hc_issue_tap<BLK, KC, PAIR>(tm, (a_hi + roff) >> 4, blo, IDESC2, fresh ? 0u : 1u);
-                  hc_issue_tap<BLK, KC, PAIR>(tm + (uint32_t)BN, (a_lo + roff) >> 4, blo, IDESC, 1u);
+                  if (alo) hc_issue_tap<BLK, KC, PAIR>(tm + (uint32_t)BN, (a_lo + roff) >> 4, blo, IDESC, 1u);
                 } else {
                   if (pass == 0) hc_issue_tap<BLK, KC, PAIR>(tm, (a_hi + roff) >> 4, blo, IDESC, fresh ? 0u : 1u);
-                  if (TWO_PASS)                            // pass 0: A_lo * B_hi, pass 1: A_hi * B_lo -> cross
+                  if (TWO_PASS && (pass == 1 || alo)) {    // pass 0: A_lo * B_hi (three-term split only), pass 1: A_hi * B_lo -> cross
                     hc_issue_tap<BLK, KC, PAIR>(tm + (uint32_t)(HC_MB * BN), ((pass == 0 ? a_lo : a_hi) + roff) >> 4, blo, IDESC, fresh_cross ? 0u : 1u);
+                    fresh_cross = false;
+                  }
                 }
                 if (!resident) hc_commit<PAIR>(&b_empty[bs]);
                 if (pass == 0) fresh = false;
-                fresh_cross = false;
                 if (++bs == nb) { bs = 0; bph ^= 1u; }
               }
               if (TWO_PASS && pass == 0) {
-                if (sflags & HC_SEG_LAST) hc_commit<PAIR>(&a_empty[lb]);   // the lo tile is only read by B_hi passes
+                if ((sflags & HC_SEG_LAST) && alo) hc_commit<PAIR>(&a_empty[lb]);   // the lo tile is only read by B_hi passes
                 if (main_done) {                                          // drained while the B_lo pass runs
                   hc_commit<PAIR>(&main_full[set_t]);
                   if (set_t) ++nm1; else ++nm0;
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
               fresh = true;
             }
             if ((sflags & HC_SEG_LAST) && a_free) {
-              if (MERGED) hc_commit<PAIR>(&a_empty[lb]);
+              if (MERGED && alo) hc_commit<PAIR>(&a_empty[lb]);
               hc_commit<PAIR>(&a_empty[hb]);
               ++step;
             }
@@ -938,9 +941,28 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
       T = t3;
     }
   }
+  // two-term split (gemm.igemm precision 'x2'): [T base taps] [same, B rows + b_lo] -- the A operand has a hi plane only
+  bool a_lo_term = x3;
+  if (!x3 && d->ntaps % 2 == 0 && d->ntaps >= 2) {
+    const int t2 = d->ntaps / 2;
+    b_lo = d->taps[t2].brow - d->taps[0].brow;
+    bool ok = b_lo > 0;
+    for (int i = 0; i < t2 && ok; ++i) {
+      const smc_igemm_tap &a = d->taps[i], &b = d->taps[t2 + i];
+      ok = b.dn == a.dn && b.dy == a.dy && b.dx == a.dx && b.brow == a.brow + b_lo;
+    }
+    if (ok) {
+      x3 = true;
+      T = t2;
+      a_lo = 0;
+    } else {
+      b_lo = 0;
+    }
+  }
   if (T > HC_MAX_TAPS) return SMC_EUNSUPPORTED;
 
   HcParams p;
+  p.a_lo_term = a_lo_term ? 1 : 0;
   p.n_img = d->n_img; p.H = d->H; p.W = d->W; p.C = d->C; p.n_out = d->n_out;
   int min_dx = 0, max_dx = 0, min_dy = 0, max_dy = 0;
   for (int i = 0; i < T; ++i) {
@@ -981,7 +1003,7 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     if (wp > 256 || rb > 256) continue;
     const int nmax = (int)((227 * 1024 - smem_fixed) / abuf);
     int nh, nl;
-    if (x3) {
+    if (x3 && a_lo_term) {
       if (nmax < 3) continue;
       // short slabs (few taps): the lo buffer is only free during the short B_lo pass, so it needs a second buffer
       const bool short_slabs = T * (KC / 16) < 16 || d->nprob > 1;   // problems of a parity group have 1-4 taps each

@@ -4,7 +4,8 @@ include/stylemc_b200.h from torch tensors.  Operands are fp16 "planes" tensors:
   A : [P, N, H, W, C]   P = 1 (hi only) or 2 (hi, lo) planes of an NHWC activation
   B : [P, rows, C]      P planes of a K-major weight matrix (rows = taps * n_out)
 
-``precision='x1'`` multiplies hi*hi; ``'x3'`` adds hi*lo and lo*hi as extra taps (~21 mantissa bits).
+``precision='x1'`` multiplies hi*hi; ``'x3'`` adds hi*lo and lo*hi as extra taps (~21 mantissa bits); ``'x2'`` is the split for an A
+operand that has a hi plane only (A_hi*B_hi + A_hi*B_lo): used by the backward GEMMs, whose A operand is a loss-scaled gradient.
 """
 import ctypes
 
@@ -64,6 +65,9 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
         a_lo = a_plane_stride_imgs if a_plane_stride_imgs is not None else NA // 2
         b_lo = b_rows_per_tap if b_rows_per_tap is not None else B.shape[0] // 2
         full = full + [(dn, dy, dx, br + b_lo) for dn, dy, dx, br in full] + [(dn + a_lo, dy, dx, br) for dn, dy, dx, br in full]
+    elif precision == 'x2':
+        b_lo = b_rows_per_tap if b_rows_per_tap is not None else B.shape[0] // 2
+        full = full + [(dn, dy, dx, br + b_lo) for dn, dy, dx, br in full]
     elif precision != 'x1':
         raise ValueError(precision)
     if len(full) > _lib.MAX_TAPS:
@@ -99,7 +103,7 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
             d.prob_ntaps[q], d.prob_o_off[q] = nt, off
     with torch.cuda.device(A.device):
         if _lib.igemm_hook is not None:
-            with _lib.igemm_hook(d, len(full) // (3 if precision == 'x3' else 1)):
+            with _lib.igemm_hook(d, len(full) // {'x3': 3, 'x2': 2}.get(precision, 1)):
                 _lib.call('smc_igemm', ctypes.addressof(d), _lib.stream())
         else:
             _lib.call('smc_igemm', ctypes.addressof(d), _lib.stream())

@@ -119,6 +119,9 @@ class SynthesisEngine:
         self.fuse_torgb = os.environ.get('STYLEMC_HCONV') != '0'      # the fused epilogue exists in hconv.cu only
         self.group_parities = os.environ.get('STYLEMC_CONV0_GROUP') != '0'  # conv0: the four parity GEMMs as one problem-group launch
         self.fuse_act_bwd = os.environ.get('STYLEMC_FUSE_ACT_BWD') != '0'   # also needs fuse_torgb (both live in hconv.cu)
+        # backward pass: hi + lo planes for the activation GRADIENTS too (3 MMAs per product) instead of a hi plane (2 MMAs); measured
+        # identical style gradients to the 4th digit (tests/diag/diag_grad_planes.py), so off by default
+        self.grad_lo = os.environ.get('STYLEMC_GRAD_LO', '0') != '0'
         self.precision, self.x3_max_res = ('x3' if precision == 'x3p' else precision), x3_max_res
         # style row of (conv0, conv1, torgb) per block (utils.py:169-185)
         self.rows, r = [], 0
@@ -369,6 +372,10 @@ class SynthesisEngine:
                 y1, d1 = saved.y1[k], saved.d1[k]
                 prec = self._prec(res)
                 two = prec == 'x3'             # split-precision backward for the blocks whose forward was split-precision
+                # gradient operands: the weights keep both planes; the activation gradients (loss-scaled, zero-mean rounding that averages
+                # out in the style-gradient sums) carry a lo plane only when asked to (2 MMAs per product, not 3)
+                gtwo = two and self.grad_lo
+                gprec = prec if (gtwo or not two) else 'x2'
                 stop_here = (k < lowest_k)       # below the lowest trainable block only T1 of the consumer is needed
                 # ---- conv1 output: consumers are ToRGB (g_img) and the next block's conv0 (g_up)
                 t1 = bufs(up_row, L1.cout, self.blocks[k + 1].conv0.cout)[0] if (g_up is not None and up_row in want) else None
@@ -379,7 +386,7 @@ class SynthesisEngine:
                 else:
                     if not need_gd and t1 is None:
                         break
-                    gd1 = self._planes(n, res, res, L1.cout, two) if need_gd else None
+                    gd1 = self._planes(n, res, res, L1.cout, gtwo) if need_gd else None
                     sp, ss = self._srow(styles, up_row) if g_up is not None else (None, 0)
                     stp, sts = self._srow(styles, rt)
                     noise1 = self._noise(L1, noise_mode, n)
@@ -391,7 +398,7 @@ class SynthesisEngine:
                     _lib.call('smc_act_bwd', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if y1.shape[0] == 2 else None, n, res, res, L1.cout,
                               _lib.ptr(g_up), int(up_f32), sp, ss, _lib.ptr(gi), _lib.ptr(T.w), stp, sts, T.wgain,
                               _lib.ptr(T.bias), rgb_clamp, _lib.ptr(gs), _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA,
-                              L1.gain, L1.clamp, _lib.ptr(gd1[0]) if need_gd else None, _lib.ptr(gd1[1]) if (need_gd and two) else None,
+                              L1.gain, L1.clamp, _lib.ptr(gd1[0]) if need_gd else None, _lib.ptr(gd1[1]) if (need_gd and gtwo) else None,
                               _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
                 if stop_here:
                     break
@@ -404,30 +411,30 @@ class SynthesisEngine:
                 y0, d0 = saved.y0[k], saved.d0[k]
                 t1 = bufs(r1, L1.cin, L1.cout)[0] if r1 in want else None
                 rr = bufs(r0, L0.cin, L0.cout)[1] if r0 in want else None
-                gd0 = self._planes(n, res, res, L0.cout, two)
+                gd0 = self._planes(n, res, res, L0.cout, gtwo)
                 if self.fuse_torgb and self.fuse_act_bwd and t1 is None and rr is None and self._hconv_shape(res, L1.cout, L1.cin):
                     # no style-gradient reduction wanted from this layer: the activation backward of conv0 (slope and clamp mask of the
                     # saved y0, conv1's style, conv0's demodulation) is the epilogue of conv1's dgrad GEMM -- no fp32 round trip
                     post = (styles[:, r1, :L1.cin] * d0).contiguous()
-                    gemm.igemm(gd1.reshape(-1, res, res, L1.cout), L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, precision=prec,
+                    gemm.igemm(gd1.reshape(-1, res, res, L1.cout), L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, precision=gprec,
                                acc_chunk_k=self.acc_k, a_plane_stride_imgs=n, b_rows_per_tap=9 * L1.cin, post_scale=post, alpha=LRELU_ALPHA,
                                gain=L0.gain, clamp=L0.clamp, mask_y=y0[0], mask_y_lo=y0[1] if y0.shape[0] == 2 else None,
-                               out_hi=gd0[0], out_lo=gd0[1] if two else None)
+                               out_hi=gd0[0], out_lo=gd0[1] if gtwo else None)
                 else:
                     gx1 = torch.empty([n, res, res, L1.cin], dtype=torch.float32 if two else torch.float16, device=dev)
-                    gemm.igemm(gd1.reshape(-1, res, res, L1.cout), L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, precision=prec,
+                    gemm.igemm(gd1.reshape(-1, res, res, L1.cout), L1.B_bwd, n, res, res, L1.cin, gemm.TAPS_3X3_DGRAD, precision=gprec,
                                acc_chunk_k=self.acc_k, a_plane_stride_imgs=n, b_rows_per_tap=9 * L1.cin,
                                **(dict(out_f32=gx1) if two else dict(out_raw=gx1)))
                     sp, ss = self._srow(styles, r1)
                     noise0 = self._noise(L0, noise_mode, n)
                     _lib.call('smc_act_bwd', _lib.ptr(y0[0]), _lib.ptr(y0[1]) if y0.shape[0] == 2 else None, n, res, res, L0.cout, _lib.ptr(gx1),
                               int(two), sp, ss, None, None, None, 0, 0.0, None, -1.0, _lib.ptr(gscale), _lib.ptr(d0), _lib.ptr(noise0),
-                              _lib.ptr(L0.bias), LRELU_ALPHA, L0.gain, L0.clamp, _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None,
+                              _lib.ptr(L0.bias), LRELU_ALPHA, L0.gain, L0.clamp, _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if gtwo else None,
                               _lib.ptr(t1), _lib.ptr(rr), _lib.stream())
                 hin = res // 2
-                gp = torch.empty([2 if two else 1, 4 * n, hin + 1, hin + 1, L0.cout], dtype=torch.float16, device=dev)
-                _lib.call('smc_fir_bwd', _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if two else None, n, hin, hin, L0.cout, _lib.ptr(self.fk4), self._fsep_ptr(),
-                          _lib.ptr(gp[0]), _lib.ptr(gp[1]) if two else None, _lib.stream())
+                gp = torch.empty([2 if gtwo else 1, 4 * n, hin + 1, hin + 1, L0.cout], dtype=torch.float16, device=dev)
+                _lib.call('smc_fir_bwd', _lib.ptr(gd0[0]), _lib.ptr(gd0[1]) if gtwo else None, n, hin, hin, L0.cout, _lib.ptr(self.fk4), self._fsep_ptr(),
+                          _lib.ptr(gp[0]), _lib.ptr(gp[1]) if gtwo else None, _lib.stream())
                 # ---- skip image: transpose of upsample2d (upfirdn2d.py:245-264)
                 if k > 0:
                     g_img = upfirdn2d.upfirdn2d(g_img, self.filter, down=2, padding=[1, 1, 1, 1], flip_filter=True, gain=4)
@@ -443,15 +450,15 @@ class SynthesisEngine:
                     grgb = (g_img * saved.rgb_pass[k - 1]) * gscale
                     post = (styles[:, r0, :L0.cin] * d1p).contiguous()
                     rgbw = ((styles[:, prt, :Lp.cout] * Tp.wgain * d1p).unsqueeze(1) * Tp.w.unsqueeze(0)).contiguous()      # [n, 3, C]
-                    gd1_fused = self._planes(n, hin, hin, Lp.cout, two)
-                    gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=prec,
+                    gd1_fused = self._planes(n, hin, hin, Lp.cout, gtwo)
+                    gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=gprec,
                                acc_chunk_k=self.acc_k, a_plane_stride_imgs=4 * n, b_rows_per_tap=9 * L0.cin, post_scale=post, alpha=LRELU_ALPHA,
                                gain=Lp.gain, clamp=Lp.clamp, mask_y=y1p[0], mask_y_lo=y1p[1] if y1p.shape[0] == 2 else None, mask_grgb=grgb,
-                               rgb_w=rgbw, out_hi=gd1_fused[0], out_lo=gd1_fused[1] if two else None)
+                               rgb_w=rgbw, out_hi=gd1_fused[0], out_lo=gd1_fused[1] if gtwo else None)
                     g_up = None
                 else:
                     g_up = torch.empty([n, hin, hin, L0.cin], dtype=torch.float32 if two else torch.float16, device=dev)
-                    gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=prec,
+                    gemm.igemm(gp.reshape(-1, hin + 1, hin + 1, L0.cout), L0.B_bwd, n, hin, hin, L0.cin, gemm.up2_dgrad_taps(n), precision=gprec,
                                acc_chunk_k=self.acc_k, a_plane_stride_imgs=4 * n, b_rows_per_tap=9 * L0.cin,
                                **(dict(out_f32=g_up) if two else dict(out_raw=g_up)))
                 up_row, up_f32 = r0, two
