@@ -63,6 +63,10 @@ class CLIPModel:
         precision = 'x3' if precision == 'x3p' else precision
         self.cfg, self.device, self.precision = cfg, torch.device(device), precision
         self.two = precision == 'x3'
+        # backward GEMMs: the gradient operand carries a lo plane (3 MMAs per product) only when asked to; by default it is a hi plane and the
+        # frozen weights keep both (gemm precision 'x2', 2 MMAs): zero-mean rounding of a loss-scaled gradient, DESIGN.md section 5
+        self.grad_lo = os.environ.get('STYLEMC_GRAD_LO', '0') != '0'
+        self.bwd_prec = os.environ.get('STYLEMC_BWD_PREC', 'x2')
         self.dtype = torch.float32
         dev, two = self.device, self.two
         f = lambda k: params[k].detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -83,7 +87,11 @@ class CLIPModel:
         return torch.empty([2 if self.two else 1, rows, width], dtype=torch.float16, device=self.device)
 
     def _lo(self, planes):
-        return _lib.ptr(planes[1]) if self.two else None
+        return _lib.ptr(planes[1]) if (self.two and planes.shape[0] == 2) else None
+
+    def _gplanes(self, rows, width):
+        """Operand planes of a backward GEMM (gradient): hi (+ lo only with ``grad_lo``)."""
+        return torch.empty([2 if (self.two and self.grad_lo) else 1, rows, width], dtype=torch.float16, device=self.device)
 
     def _linear(self, a_planes, lin, rows, bwd=False, residual=None, out=None):
         """out[rows, n_out] = A @ B.T (+ bias) (+ residual), fp32."""
@@ -91,7 +99,8 @@ class CLIPModel:
         n_out, k = (lin.in_f, lin.out_f) if bwd else (lin.out_f, lin.in_f)
         if out is None:
             out = torch.empty([rows, n_out], dtype=torch.float32, device=self.device)
-        gemm.igemm(a_planes.reshape(-1, 1, rows, k), B, 1, 1, rows, n_out, gemm.TAPS_1X1, precision=self.precision,
+        precision = self.bwd_prec if (self.two and a_planes.shape[0] == 1) else self.precision      # hi-only A operand: two-term split
+        gemm.igemm(a_planes.reshape(-1, 1, rows, k), B, 1, 1, rows, n_out, gemm.TAPS_1X1, precision=precision,
                    a_plane_stride_imgs=1, b_rows_per_tap=n_out, bias=None if bwd else lin.bias, residual=residual, out_f32=out,
                    acc_scale=lin.inv, acc_chunk_k=self.acc_k)
         return out
@@ -170,10 +179,10 @@ class CLIPModel:
                       _lib.ptr(saved['rp']), _lib.ptr(dx), b, wd, 0, _lib.stream())
             for blk, sv in zip(reversed(tw.blocks), reversed(saved['blocks'])):
                 # MLP branch
-                dxp = self._planes(rows, wd)
+                dxp = self._gplanes(rows, wd)
                 _lib.call('smc_split_rows', _lib.ptr(dx), _lib.ptr(dxp[0]), self._lo(dxp), rows, wd, rows, 0, 0, _lib.stream())
                 dg = self._linear(dxp, blk['proj'], rows, bwd=True)
-                dh = self._planes(rows, 4 * wd)
+                dh = self._gplanes(rows, 4 * wd)
                 _lib.call('smc_quickgelu_bwd', _lib.ptr(dg), _lib.ptr(sv['hfc']), _lib.ptr(dh[0]), self._lo(dh), rows * 4 * wd, _lib.stream())
                 dln2 = self._linear(dh, blk['fc'], rows, bwd=True)
                 _lib.call('smc_layernorm_bwd', _lib.ptr(dln2), _lib.ptr(sv['x_mid']), 1, 0, _lib.ptr(blk['ln2'][0]), _lib.ptr(sv['m2']),
@@ -181,7 +190,7 @@ class CLIPModel:
                 # attention branch
                 _lib.call('smc_split_rows', _lib.ptr(dx), _lib.ptr(dxp[0]), self._lo(dxp), rows, wd, rows, 0, 0, _lib.stream())
                 do = self._linear(dxp, blk['out'], rows, bwd=True)
-                dqkv = self._planes(rows, 3 * wd)
+                dqkv = self._gplanes(rows, 3 * wd)
                 if tiled:
                     _lib.call('smc_attention_bwd_tiled', _lib.ptr(sv['qkv']), _lib.ptr(do), _lib.ptr(dqkv[0]), self._lo(dqkv), _lib.ptr(stats), b, t,
                               wd, tw.heads, 0, _lib.stream())
@@ -195,7 +204,7 @@ class CLIPModel:
             _lib.call('smc_layernorm_bwd', _lib.ptr(dx), _lib.ptr(saved['x0']), 1, 0, _lib.ptr(self.ln_pre[0]), _lib.ptr(saved['m0']),
                       _lib.ptr(saved['r0']), _lib.ptr(dx0), rows, wd, 0, _lib.stream())
             prow = b * grid * grid
-            dpp = self._planes(prow, wd)
+            dpp = self._gplanes(prow, wd)
             _lib.call('smc_split_rows', _lib.ptr(dx0), _lib.ptr(dpp[0]), self._lo(dpp), prow, wd, t - 1, t, 1, _lib.stream())
             dcols = self._linear(dpp, self.conv1, prow, bwd=True)
             dimg = torch.empty([b, 3, res, res], dtype=torch.float32, device=self.device)

@@ -122,6 +122,7 @@ class SynthesisEngine:
         # backward pass: hi + lo planes for the activation GRADIENTS too (3 MMAs per product) instead of a hi plane (2 MMAs); measured
         # identical style gradients to the 4th digit (tests/diag/diag_grad_planes.py), so off by default
         self.grad_lo = os.environ.get('STYLEMC_GRAD_LO', '0') != '0'
+        self.bwd_prec = os.environ.get('STYLEMC_BWD_PREC', 'x2')           # 'x1' (weights hi plane only) is a diagnostic: diag_grad_planes.py
         self.precision, self.x3_max_res = ('x3' if precision == 'x3p' else precision), x3_max_res
         # style row of (conv0, conv1, torgb) per block (utils.py:169-185)
         self.rows, r = [], 0
@@ -375,7 +376,7 @@ class SynthesisEngine:
                 # gradient operands: the weights keep both planes; the activation gradients (loss-scaled, zero-mean rounding that averages
                 # out in the style-gradient sums) carry a lo plane only when asked to (2 MMAs per product, not 3)
                 gtwo = two and self.grad_lo
-                gprec = prec if (gtwo or not two) else 'x2'
+                gprec = prec if (gtwo or not two) else self.bwd_prec
                 stop_here = (k < lowest_k)       # below the lowest trainable block only T1 of the consumer is needed
                 # ---- conv1 output: consumers are ToRGB (g_img) and the next block's conv0 (g_up)
                 t1 = bufs(up_row, L1.cout, self.blocks[k + 1].conv0.cout)[0] if (g_up is not None and up_row in want) else None

@@ -171,7 +171,10 @@ def test_full_size_1024_properties():
         print(f'{tag}: img max-abs diff {e_img:.2e}, loss diff {abs(loss - loss0):.2e}, grad rel-l2 diff {e_grad:.2e}')
         assert e_img <= (1e-6 if tag == '2 x 2' else 1e-4)
         assert abs(loss - loss0) <= 1e-5 * abs(loss0)
-        assert e_grad <= (1e-5 if tag == '2 x 2' else 2e-3)      # kernels differ in rounding: the lrelu-flip sensitivity of DESIGN.md section 5
+        # 2 x 2: the activation gradients are fp16 planes under a per-pass power-of-two loss scale (hi plane only by default): two passes
+        # quantise them differently, 1e-4 measured (1e-5 with STYLEMC_GRAD_LO=1), both 5e-4 from the reference (config4 golden above);
+        # per-tap kernel: different rounding, the lrelu-flip sensitivity of DESIGN.md section 5
+        assert e_grad <= (3e-4 if tag == '2 x 2' else 2e-3)
     f = finder(G, 1024, micro_batch=4)
     _, img512, _ = f.engine.forward(S.cuda(), until_k=7)
     assert img512.shape == (4, 3, 512, 512)
