@@ -63,9 +63,10 @@ class CLIPModel:
         precision = 'x3' if precision == 'x3p' else precision
         self.cfg, self.device, self.precision = cfg, torch.device(device), precision
         self.two = precision == 'x3'
-        # backward GEMMs: the gradient operand carries a lo plane (3 MMAs per product) only when asked to; by default it is a hi plane and the
-        # frozen weights keep both (gemm precision 'x2', 2 MMAs): zero-mean rounding of a loss-scaled gradient, DESIGN.md section 5
-        self.grad_lo = os.environ.get('STYLEMC_GRAD_LO', '0') != '0'
+        # backward GEMMs: the gradient operand keeps its lo plane here (3 MMAs per product).  The synthesis engine drops it (2 MMAs, +8 %
+        # images/s); in the ViT the same switch (STYLEMC_CLIP_GRAD_LO=0) gains nothing measurable (the tower is 5 % of the step) and costs
+        # 1.5e-4 of gradient accuracy on the 1024-px golden, so it stays on
+        self.grad_lo = os.environ.get('STYLEMC_CLIP_GRAD_LO', '1') != '0'
         self.bwd_prec = os.environ.get('STYLEMC_BWD_PREC', 'x2')
         self.dtype = torch.float32
         dev, two = self.device, self.two

@@ -30,14 +30,14 @@ for name, res, kw in (('step64', 64, dict(seed=1, channel_base=2048, channel_max
             r = o_dir.direction_step(G, shapes, o_dir.CLIPLoss(o_vit.CLIP(o_vit.random_clip_params(seed=0)), pos, neg), S, delta, o_dir.RESOLUTION_TO_K.get(res, 100))
             ref_grad = r['grad'][0]
         base = None
-        for lo, bprec in ((True, 'x2'), (False, 'x2'), (False, 'x1')):
+        for lo, clo, bprec in ((True, True, 'x2'), (False, True, 'x2'), (False, False, 'x2'), (False, False, 'x1')):
             f = direction.DirectionFinder(G, model, pos, neg, res, precision='x3p', micro_batch=4)
-            f.engine.grad_lo = model.grad_lo = lo
+            f.engine.grad_lo, model.grad_lo = lo, clo
             f.engine.bwd_prec = model.bwd_prec = bprec
             f.delta.copy_(delta.cuda())
             grad = f.step(S.cuda(), lr=0.0)['grad'].cpu()
             base = grad if base is None else base
-            msg = f'{name} delta x{scale}: gradient planes {"hi+lo" if lo else "hi only"}, weights {"hi+lo" if bprec == "x2" else "hi only"}:'
+            msg = f'{name} delta x{scale}: gradient planes synthesis {"hi+lo" if lo else "hi only"} / ViT {"hi+lo" if clo else "hi only"}, weights {"hi+lo" if bprec == "x2" else "hi only"}:'
             if ref_grad is not None:
                 msg += f' grad rel-l2 vs reference {((grad - ref_grad).norm() / ref_grad.norm()).item():.3e};'
             print(msg + f' vs hi+lo {((grad - base).norm() / base.norm()).item():.3e}', flush=True)
