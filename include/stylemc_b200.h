@@ -203,11 +203,14 @@ int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_s
 
 /* ---- unprocess + CLIP glue (vit.cu) --------------------------------------------------------------
  * mean3 / std3 are HOST arrays of 3 floats; all other pointers are device pointers. */
+/* denorm_normalize: 0 plain resample; 1 `unprocess` of find_direction.py:49-52 (clamp(x * 127.5 + 128, 0, 255) -> resize -> / 255 -> normalise);
+ * 2 the NADA preprocessing of clip_loss_nada.py:86-89 ((x + 1) / 2 without a clamp -> resize -> normalise). */
 int smc_resample_fwd(const float* x, float* tmp, float* y, const int* start, const int* count, const float* wgt, int taps,
                      int planes, int in_size, int out_size, int denorm_normalize, const float* mean3, const float* std3, void* stream);
-/* unscale: optional DEVICE pointer to the loss scale S carried by g (see smc_clip_loss); gx = d/dx of the unscaled loss. */
+/* mode: 1 / 2 as denorm_normalize above.  unscale: optional DEVICE pointer to the loss scale S carried by g (see smc_clip_loss);
+ * gx = d/dx of the unscaled loss. */
 int smc_resample_bwd(const float* g, const float* x, float* tmp, float* gx, const int* oidx, const int* count, const float* wgt,
-                     int taps, int planes, int in_size, int out_size, const float* std3, const float* unscale, void* stream);
+                     int taps, int planes, int in_size, int out_size, int mode, const float* std3, const float* unscale, void* stream);
 int smc_patchify(const float* img, void* hi, void* lo, int b, int res, int ps, void* stream);
 int smc_unpatchify(const float* gp, float* gimg, int b, int res, int ps, void* stream);
 int smc_assemble_tokens(const float* patch, const float* cls, const float* pos, float* x0, int b, int t, int wd, void* stream);
@@ -232,8 +235,11 @@ int smc_head_proj(const float* ln, const float* proj, float* out, int b, int wd,
 int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln, int b, int wd, int e, void* stream);
 /* gscale_out (optional, device): d_tgt is multiplied by S = 2^k, max|d_tgt| * S in [target/2, target), and S is stored there
  * (loss scaling for the fp16-operand backward GEMMs; smc_resample_bwd divides it out again). */
+/* normalize != 0: the NADA directional form (clip_loss_nada.py:162-168,206-218): e = tgt/|tgt| - src/|src| instead of tgt - src, gradient taken
+ * through the normalisation of tgt.  The "global" NADA term (clip_loss_nada.py:220-229) is this entry point with e_src = 0, text = the prompt
+ * embedding and coef multiplied by exp(logit_scale) / 100. */
 int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
-                  float inv_count, float* gscale_out, float gscale_target, void* stream);
+                  float inv_count, float* gscale_out, float gscale_target, int normalize, void* stream);
 
 /* ---- generate_fromS output stage ---------------------------------------------------------------
  * out[n, y, x_off + x, j] = uint8(clamp(img[n, j, y, x] * 127.5 + 128, 0, 255))   (generate_fromS.py:174-175; canvas [N, H, canvas_w, 3],

@@ -58,13 +58,75 @@ class DoubleCLIPLoss:
         return self.loss_small(src_image, tgt_image) + 0.5 * self.loss_large(src_image, tgt_image)
 
 
+# clip_loss_nada.py:12-40 (the prompt-engineering templates every class string is composed with)
+NADA_TEMPLATES = [
+    'a photo of a {}.', 'a rendering of a {}.', 'a cropped photo of the {}.', 'the photo of a {}.', 'a photo of a clean {}.', 'a photo of a dirty {}.',
+    'a dark photo of the {}.', 'a photo of my {}.', 'a photo of the cool {}.', 'a close-up photo of a {}.', 'a bright photo of the {}.',
+    'a cropped photo of a {}.', 'a photo of the {}.', 'a good photo of the {}.', 'a photo of one {}.', 'a close-up photo of the {}.',
+    'a rendition of the {}.', 'a photo of the clean {}.', 'a rendition of a {}.', 'a photo of a nice {}.', 'a good photo of a {}.',
+    'a photo of the nice {}.', 'a photo of the small {}.', 'a photo of the weird {}.', 'a photo of the large {}.', 'a photo of a cool {}.',
+    'a photo of a small {}.']
+
+
+def nada_preprocess(img, size=224):
+    """``CLIPLoss.preprocess`` of clip_loss_nada.py:86-89 on a square tensor: Normalize(mean -1, std 2) (GAN output -> [0, 1], NO clamp),
+    Resize(224, BICUBIC) + CenterCrop(224) (``clip_preprocess.transforms[:2]``), Normalize(CLIP mean, std) (``transforms[4:]``)."""
+    x = (img + 1.0) / 2.0
+    x = F.interpolate(x, size=(size, size), mode='bicubic', antialias=True, align_corners=False)
+    mean = torch.tensor(CLIP_MEAN, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+class CLIPLossNADA:
+    """clip_loss_nada.py:66-345 for the two configurations find_direction.py:101-114 builds: ``lambda_direction=1`` (clip_loss_type 'nada':
+    ``clip_directional_loss``, :206-218) or ``lambda_global=1, lambda_direction=0`` ('nada_global': ``global_clip_loss``, :220-229).  Called
+    as the reference calls it (find_direction.py:151-158): ``loss(original, negative_prompt, generated, prompt)`` on raw GAN outputs."""
+
+    def __init__(self, model, tokenize, lambda_direction=1.0, lambda_global=0.0):
+        self.model, self.tokenize = model, tokenize
+        self.lambda_direction, self.lambda_global = lambda_direction, lambda_global
+        self.target_direction = None
+
+    def get_text_features(self, class_str):                                     # :129-140
+        f = self.model.encode_text(self.tokenize([t.format(class_str) for t in NADA_TEMPLATES])).detach()
+        return f / f.norm(dim=-1, keepdim=True)
+
+    def get_image_features(self, img):                                          # :142-148
+        f = self.model.encode_image(nada_preprocess(img))
+        return f / f.norm(dim=-1, keepdim=True)
+
+    def compute_text_direction(self, source_class, target_class):               # :150-157
+        d = (self.get_text_features(target_class) - self.get_text_features(source_class)).mean(dim=0, keepdim=True)
+        return d / d.norm(dim=-1, keepdim=True)
+
+    def clip_directional_loss(self, src_img, source_class, target_img, target_class):    # :206-218
+        if self.target_direction is None:
+            self.target_direction = self.compute_text_direction(source_class, target_class)
+        e = self.get_image_features(target_img) - self.get_image_features(src_img)
+        e = e / e.norm(dim=-1, keepdim=True)
+        return (1.0 - F.cosine_similarity(e, self.target_direction)).mean()
+
+    def global_clip_loss(self, img, text):                                      # :220-229
+        logits_per_image, _ = self.model(nada_preprocess(img), self.tokenize(text))
+        return (1.0 - logits_per_image / 100).mean()
+
+    def __call__(self, src_img, source_class, target_img, target_class):        # :325-345
+        loss = 0.0
+        if self.lambda_global:
+            loss = loss + self.lambda_global * self.global_clip_loss(target_img, [f'a {target_class}'])
+        if self.lambda_direction:
+            loss = loss + self.lambda_direction * self.clip_directional_loss(src_img, source_class, target_img, target_class)
+        return loss
+
+
 def cosine_lr(base_lr, it, total):
     """find_direction.py:298-299 (``it`` is 1-based)."""
     return math.cos(math.pi * it / total) * base_lr * 0.5 + base_lr * 0.5
 
 
 def direction_step(G, temp_shapes, clip_loss, styles, delta, until_k, clip_loss_coef=1.0, l2_reg_coef=0.1,
-                   noise_mode='const'):
+                   noise_mode='const', nada_prompts=None):
     """One loss/gradient evaluation of find_direction.py:306-336.
 
     styles [N,26,512]; delta [1,8,512] (leaf).  Returns dict(loss, clip_loss, l2_loss, grad, img,
@@ -78,7 +140,10 @@ def direction_step(G, temp_shapes, clip_loss, styles, delta, until_k, clip_loss_
     _, img = synthesis.generate_image(G, until_k, styles2, temp_shapes, noise_mode)   # :309
     with torch.no_grad():
         _, original = synthesis.generate_image(G, until_k, styles, temp_shapes, noise_mode)  # :312
-    clip_term = clip_loss_coef * clip_loss(unprocess(original), unprocess(img))   # :159-169
+    if nada_prompts is not None:       # find_direction.py:150-158: the NADA losses take the raw images and the (negative, positive) prompts
+        clip_term = clip_loss_coef * clip_loss(original, nada_prompts[0], img, nada_prompts[1])
+    else:
+        clip_term = clip_loss_coef * clip_loss(unprocess(original), unprocess(img))   # :159-169
     l2_term = l2_reg_coef * F.mse_loss(styles2[:, S_TRAINABLE_ROWS], styles[:, S_TRAINABLE_ROWS])  # :190-191
     loss = clip_term + l2_term
     grad, = torch.autograd.grad(loss, delta)

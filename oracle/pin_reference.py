@@ -383,6 +383,48 @@ def pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, out):
 B16_SEED = 7
 
 
+def pin_step_nada(R, model, G_ref, G_ora, S, shapes, out):
+    """clip_loss_type 'nada' and 'nada_global' (find_direction.py:101-114,150-158): the reference's REAL clip_loss_nada.CLIPLoss
+    (clip_loss_nada.py:66-345) driven by its own init_clip_loss / compute_clip_loss, on a stub ``clip`` module (oracle ViT-B/32,
+    synthetic tokenizer, the five-transform preprocessing pipeline of clip.load) vs oracle.direction.CLIPLossNADA; 64-px net, the
+    styles and delta of step64.npz."""
+    print('step (nada): reference clip_loss_nada.CLIPLoss through init_clip_loss / compute_clip_loss vs the oracle (64-px net)')
+    from torchvision.transforms import CenterCrop, Compose, Normalize, Resize, ToTensor
+    from PIL import Image
+    pre = Compose([Resize(224, interpolation=Image.BICUBIC), CenterCrop(224), lambda im: im.convert('RGB'), ToTensor(),
+                   Normalize(direction.CLIP_MEAN, direction.CLIP_STD)])
+    dummy = types.SimpleNamespace(encode_image=None)
+    R.clip.load = lambda name, device=None: ((model if name == 'ViT-B/32' else dummy), pre)
+    R.clip.tokenize = lambda texts: vit.synthetic_tokenize(texts)
+    dev = torch.device('cpu')
+    T = R.fd.S_TRAINABLE_SPACE_CHANNELS
+    delta0 = 0.1 * torch.randn(1, 8, 512, generator=torch.Generator().manual_seed(4))      # same delta as step64.npz
+    for kind in ('nada', 'nada_global'):
+        l1, l2 = R.fd.init_clip_loss(kind, 'small', dev, POS_TEXT, NEG_TEXT)
+        assert l2 is None and l1.model is model
+        delta = delta0.clone().requires_grad_(True)
+        styles_direction = torch.zeros(1, R.fd.N_STYLE_CHANNELS, 512)
+        styles_direction[:, T] = delta
+        styles2 = S + styles_direction
+        _, img = R.utils.generate_image(G_ref, 100, styles2, shapes, 'const', dev)
+        _, original = R.utils.generate_image(G_ref, 100, S, shapes, 'const', dev)
+        clip_term = R.fd.compute_clip_loss(img, original, kind, 'small', 1.0, l1, None, None, None, None, dev, POS_TEXT, NEG_TEXT)
+        reg = 0.1 * torch.nn.functional.mse_loss(styles2[:, T], S[:, T])
+        loss = clip_term + reg
+        loss.backward()
+        kw = dict(lambda_direction=0.0, lambda_global=1.0) if kind == 'nada_global' else {}
+        o = direction.direction_step(G_ora, shapes, direction.CLIPLossNADA(model, vit.synthetic_tokenize, **kw), S, delta0, 100,
+                                     nada_prompts=(NEG_TEXT, POS_TEXT))
+        close(o['loss'], loss.detach(), 1e-6, f'{kind} step loss')
+        rel = ((o['grad'] - delta.grad).norm() / delta.grad.norm()).item()
+        print(f'  {kind}: loss {loss.item():.6f} grad rel-l2 {rel:.3e}, |grad| {delta.grad.norm():.3e}')
+        assert rel < 1e-5
+        out[kind + '.loss'], out[kind + '.clip_loss'], out[kind + '.grad'] = loss.detach().numpy(), clip_term.detach().numpy(), delta.grad.numpy()
+    out['pos_text'], out['neg_text'] = np.array(POS_TEXT), np.array(NEG_TEXT)
+    close(direction.nada_preprocess(original), l1.preprocess(original), 2e-6, 'nada_preprocess vs the reference transform pipeline')
+    out['preprocessed'] = l1.preprocess(original)[:1].detach().numpy()
+
+
 def pin_config1(R, model, out):
     print('config 1: FFHQ-256 config-f net, batch 4, one find_direction step through the reference (CPU)')
     G_ref = synthesis.make_generator(256, seed=0)
@@ -472,12 +514,13 @@ def main():
     ap.add_argument('--skip-config1', action='store_true')
     ap.add_argument('--skip-config4', action='store_true')
     ap.add_argument('--only-config4', action='store_true', help='(re)write only config4.npz')
+    ap.add_argument('--only-nada', action='store_true', help='(re)write only step64_nada.npz')
     ap.add_argument('--only-ops', action='store_true', help='(re)write only ops.npz')
     ap.add_argument('--only-double', action='store_true', help='(re)write only clip_b16.npz and step64_double.npz')
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     R = import_reference()
-    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'config1', 'config4')}
+    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'step64_nada', 'config1', 'config4')}
     if args.only_config4:
         model = vit.CLIP(seed=0, cfg=vit.VIT_B32)
         install_stub_clip(R, model)
@@ -485,6 +528,14 @@ def main():
         if not args.check:
             np.savez_compressed(os.path.join(GOLD, 'config4.npz'), **fx['config4'])
             print('wrote config4.npz', f'{os.path.getsize(os.path.join(GOLD, "config4.npz")) / 1e6:.2f} MB')
+        return
+    if args.only_nada:
+        G_ref, G_ora, S, shapes = pin_driver(R, fx['synth64'])
+        model = vit.CLIP(seed=0, cfg=vit.VIT_B32)
+        pin_step_nada(R, model, G_ref, G_ora, S, shapes, fx['step64_nada'])
+        if not args.check:
+            np.savez_compressed(os.path.join(GOLD, 'step64_nada.npz'), **fx['step64_nada'])
+            print('wrote step64_nada.npz')
         return
     pin_ops(R, fx['ops'])
     pin_modconv_e4e(R, fx['ops'])
@@ -498,6 +549,7 @@ def main():
     model_b16 = pin_clip(R, fx['clip_b16'], vit.VIT_B16, B16_SEED, 'ViT-B/16')
     pin_step(R, model, G_ref, G_ora, S, shapes, fx['step64'])
     pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, fx['step64_double'])
+    pin_step_nada(R, model, G_ref, G_ora, S, shapes, fx['step64_nada'])
     if not args.skip_config1 and not args.only_double:
         pin_config1(R, model, fx['config1'])
     if not args.skip_config4 and not args.only_double:

@@ -68,6 +68,7 @@ def random_clip_params(seed=0, cfg=VIT_B32):
     p['ln_final.weight'] = 1 + 0.1 * torch.randn(tw, generator=g)
     p['ln_final.bias'] = 0.1 * torch.randn(tw, generator=g)
     p['text_projection'] = tw ** -0.5 * torch.randn(tw, cfg['embed_dim'], generator=g)
+    p['logit_scale'] = torch.tensor(math.log(1 / 0.07))       # clip/model.py CLIP.__init__ (no random draw: the other parameters are unchanged)
     return p
 
 
@@ -80,6 +81,17 @@ def synthetic_tokens(which, context_length=77):
     ids = [49406] + body + [49407]
     t[0, :len(ids)] = torch.tensor(ids)
     return t
+
+
+def synthetic_tokenize(texts, context_length=77):
+    """Stand-in for ``clip.tokenize(list of strings)`` (clip_loss_nada.py:117,131,224): one deterministic row per string, SOT, one id in
+    [1000, 41000) per whitespace-separated word (crc32 of the word), EOT (the unique maximum, so ``argmax`` finds it), zero padding."""
+    import zlib
+    out = torch.zeros(len(texts), context_length, dtype=torch.int64)
+    for r, text in enumerate(texts):
+        ids = [49406] + [1000 + zlib.crc32(w.encode()) % 40000 for w in text.split()][:context_length - 2] + [49407]
+        out[r, :len(ids)] = torch.tensor(ids)
+    return out
 
 
 def _ln(x, w, b):
@@ -135,6 +147,14 @@ class CLIP:
             x = _resblock(x, p, f'transformer.resblocks.{i}.', c['transformer_heads'], mask)
         x = _ln(x, p['ln_final.weight'], p['ln_final.bias'])
         return x[torch.arange(x.shape[0], device=x.device), text.argmax(dim=-1)] @ p['text_projection']
+
+
+    def __call__(self, image, text):
+        """clip/model.py CLIP.forward: (logits_per_image, logits_per_text) = exp(logit_scale) * cosine similarities."""
+        i, t = self.encode_image(image), self.encode_text(text)
+        i, t = i / i.norm(dim=1, keepdim=True), t / t.norm(dim=1, keepdim=True)
+        logits = self.p['logit_scale'].exp() * i @ t.t()
+        return logits, logits.t()
 
 
 FLOPS_PER_IMAGE_FWD = None  # filled by bench from the GEMM shapes; see SURVEY.md section 8d

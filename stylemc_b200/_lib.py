@@ -86,7 +86,7 @@ SIGNATURES = {
     'smc_sgrad_finish': 'ppppp q pp iii p',
     'smc_grad_scale': 'p q f pp p',
     'smc_resample_fwd': 'pppppp i iii i pp p',
-    'smc_resample_bwd': 'ppppppp i iii p p p',
+    'smc_resample_bwd': 'ppppppp i iii i p p p',
     'smc_patchify': 'ppp iii p',
     'smc_unpatchify': 'pp iii p',
     'smc_assemble_tokens': 'pppp iii p',
@@ -101,7 +101,7 @@ SIGNATURES = {
     'smc_split_rows': 'ppp q iiii p',
     'smc_head_proj': 'ppp iii p',
     'smc_head_proj_bwd': 'ppp iii p',
-    'smc_clip_loss': 'ppppp ii ff p f p',
+    'smc_clip_loss': 'ppppp ii ff p f i p',
     'smc_img_to_uint8': 'pp iiiii p',
     'smc_prepare_weights': 'p iiiii p pppp p p',
     'smc_fma': 'pppp i pppp p',

@@ -81,6 +81,7 @@ class CLIPModel:
         self.tok_emb, self.tpos = f('token_embedding.weight'), f('positional_embedding')
         self.ln_final = (f('ln_final.weight'), f('ln_final.bias'))
         self.tproj = f('text_projection')
+        self.logit_scale = float(params['logit_scale']) if 'logit_scale' in params else 4.605170185988092 - 1.9459101090932196   # ln(1 / 0.07)
         self.text = _Tower(params, 'transformer', cfg['transformer_width'], cfg['transformer_layers'], cfg['transformer_heads'], dev, two, False)
 
     # ---- kernels ---------------------------------------------------------------------------------
@@ -286,6 +287,7 @@ def random_params(seed=0, cfg=VIT_B32):
     tower('transformer', tw, cfg['transformer_layers'])
     p['ln_final.weight'], p['ln_final.bias'] = 1 + 0.1 * rn(tw), 0.1 * rn(tw)
     p['text_projection'] = tw ** -0.5 * rn(tw, cfg['embed_dim'])
+    p['logit_scale'] = torch.tensor(2.6592600369327783)        # ln(1 / 0.07), CLIP.__init__
     return p
 
 

@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(256) resample_h_kernel(const float* __restrict
     float acc = 0.f;
     for (int k = 0; k < cnt; ++k) {
       float v = __ldg(src + k);
-      if (denorm) v = fminf(fmaxf(v * 127.5f + 128.f, 0.f), 255.f);
+      if (denorm == 1) v = fminf(fmaxf(v * 127.5f + 128.f, 0.f), 255.f);        // find_direction.py:50
+      else if (denorm == 2) v = fmaf(v, 0.5f, 0.5f);                            // clip_loss_nada.py:86-87: Normalize(mean -1, std 2), no clamp
       acc += __ldg(w + k) * v;
     }
     if (norm_rows > 0) {                 // second pass of the vertical-first order: rows per plane = norm_rows, channel = plane % 3
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(256) resample_vfirst_kernel(const float* __res
       const int y = yb + u;
       if (y >= y1) break;
       float v = v4[u];
-      if (denorm) v = fminf(fmaxf(v * 127.5f + 128.f, 0.f), 255.f);
+      if (denorm == 1) v = fminf(fmaxf(v * 127.5f + 128.f, 0.f), 255.f);
+      else if (denorm == 2) v = fmaf(v, 0.5f, 0.5f);
       while (o_hi < o1 && __ldg(start + o_hi) <= y) ++o_hi;
       for (int o = o_lo; o < o_hi; ++o) {
         const int k = y - __ldg(start + o);
@@ -118,23 +120,25 @@ __global__ void __launch_bounds__(256) resample_v_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) resample_vT_kernel(const float* __restrict__ g, float* __restrict__ gt, const int* __restrict__ oidx,
                                                           const int* __restrict__ count, const float* __restrict__ wgt, int taps, int planes,
                                                           int in_h, int out_h, int w, float s0, float s1, float s2, const float* __restrict__ x,
-                                                          const float* __restrict__ unscale) {
+                                                          const float* __restrict__ unscale, int mode = 1) {
+  // mode 1: unprocess (slope 127.5, clamp mask, 1 / (255 std)); mode 2: the NADA preprocessing (slope 0.5, no clamp, 1 / std)
   const long long total = (long long)planes * in_h * w;
-  const float k127 = x ? 127.5f / (unscale ? __ldg(unscale) : 1.f) : 1.f;
+  const float k127 = x ? (mode == 2 ? 0.5f : 127.5f) / (unscale ? __ldg(unscale) : 1.f) : 1.f;
+  const float k255 = mode == 2 ? 1.f : 255.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(i % w);
     long long r = i / w;
     const int iy = (int)(r % in_h);
     const int pl = (int)(r / in_h);
     const int c = pl % 3;
-    const float k0 = 1.f / (255.f * (c == 0 ? s0 : (c == 1 ? s1 : s2)));
+    const float k0 = 1.f / (k255 * (c == 0 ? s0 : (c == 1 ? s1 : s2)));
     const float* src = g + (long long)pl * out_h * w + ox;
     float acc = 0.f;
     const int cnt = count[iy];
     for (int k = 0; k < cnt; ++k) acc += __ldg(wgt + (long long)iy * taps + k) * __ldg(src + (long long)oidx[(long long)iy * taps + k] * w);
     acc *= k0;
     if (x) {                             // last pass of the vertical-first order: the clamp mask and 127.5 / loss scale live here
-      const float v = x[i] * 127.5f + 128.f;
+      const float v = mode == 2 ? 1.f : x[i] * 127.5f + 128.f;
       acc = (v > 0.f && v < 255.f) ? acc * k127 : 0.f;
     }
     gt[i] = acc;
@@ -143,13 +147,14 @@ __global__ void __launch_bounds__(256) resample_vT_kernel(const float* __restric
 // gx[b,c,y,ix] = 127.5 * [0 < x*127.5+128 < 255] * sum_k wT[ix][k] * gt[b,c,y,oT[ix][k]]
 __global__ void __launch_bounds__(256) resample_hT_kernel(const float* __restrict__ gt, const float* __restrict__ x, float* __restrict__ gx,
                                                           const int* __restrict__ oidx, const int* __restrict__ count, const float* __restrict__ wgt,
-                                                          int taps, long long rows, int in_w, int out_w, const float* __restrict__ unscale) {
+                                                          int taps, long long rows, int in_w, int out_w, const float* __restrict__ unscale,
+                                                          int mode = 1) {
   const long long total = rows * in_w;
-  const float k127 = x ? 127.5f / (unscale ? __ldg(unscale) : 1.f) : 1.f;
+  const float k127 = x ? (mode == 2 ? 0.5f : 127.5f) / (unscale ? __ldg(unscale) : 1.f) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ix = (int)(i % in_w);
     const long long r = i / in_w;
-    const float v = x ? x[i] * 127.5f + 128.f : 1.f;
+    const float v = (x && mode != 2) ? x[i] * 127.5f + 128.f : 1.f;
     float acc = 0.f;
     if (v > 0.f && v < 255.f) {   // torch clamp backward passes gradient on [min, max] inclusive; measure-zero difference
       const float* src = gt + r * out_w;
@@ -1020,28 +1025,49 @@ __global__ void __launch_bounds__(256) head_proj_bwd_kernel(const float* __restr
 // loss = coef * (count - sum_n cos_n) / count  with count = global batch (inv_count = 1 / count).
 // One block; writes loss_part (this rank's sum of -cos * coef * inv_count; the constant coef is added by
 // the caller) and dE_tgt[n,:] = -coef * inv_count * (t/|t| - cos * e/|e|) / |e|.
+// normalize != 0: the NADA form (clip_loss_nada.py:162-168,206-218): both embeddings are L2-normalised before the difference,
+// e = tgt/|tgt| - src/|src|, and the gradient is taken through the normalisation of tgt: d = (g - (g . a) a) / |tgt| with a = tgt/|tgt|.
 __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict__ e_src, const float* __restrict__ e_tgt, const float* __restrict__ text,
                                                         float* __restrict__ loss_part, float* __restrict__ d_tgt, int N, int E, float coef,
-                                                        float inv_count, float* __restrict__ gscale_out, float gscale_target) {
-  __shared__ float red[3][16];
-  __shared__ float bc[3];
+                                                        float inv_count, float* __restrict__ gscale_out, float gscale_target, int normalize) {
+  __shared__ float red[5][16];
+  __shared__ float bc[5];
   float dmax = 0.f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float total = 0.f;
   for (int n = 0; n < N; ++n) {
-    float ee = 0.f, et = 0.f, tt = 0.f;
-    for (int j = threadIdx.x; j < E; j += blockDim.x) {
-      const float e = e_tgt[(long long)n * E + j] - e_src[(long long)n * E + j], t = text[j];
-      ee += e * e; et += e * t; tt += t * t;
+    const float* a = e_tgt + (long long)n * E;
+    const float* b = e_src + (long long)n * E;
+    float ia = 1.f, ib = 1.f;                      // 1 / |tgt|, 1 / |src| (normalize), else 1
+    if (normalize) {
+      float aa = 0.f, bb = 0.f;
+      for (int j = threadIdx.x; j < E; j += blockDim.x) { aa += a[j] * a[j]; bb += b[j] * b[j]; }
+      aa = warp_sum(aa); bb = warp_sum(bb);
+      __syncthreads();
+      if (lane == 0) { red[0][warp] = aa; red[1][warp] = bb; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int w = 0; w < nw; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
+        bc[0] = s0; bc[1] = s1;
+      }
+      __syncthreads();
+      ia = 1.f / fmaxf(sqrtf(bc[0]), 1e-20f);
+      ib = 1.f / fmaxf(sqrtf(bc[1]), 1e-20f);
     }
-    ee = warp_sum(ee); et = warp_sum(et); tt = warp_sum(tt);
+    float ee = 0.f, et = 0.f, tt = 0.f, ta = 0.f, ea = 0.f;
+    for (int j = threadIdx.x; j < E; j += blockDim.x) {
+      const float ah = a[j] * ia, e = ah - b[j] * ib, t = text[j];
+      ee += e * e; et += e * t; tt += t * t; ta += t * ah; ea += e * ah;
+    }
+    ee = warp_sum(ee); et = warp_sum(et); tt = warp_sum(tt); ta = warp_sum(ta); ea = warp_sum(ea);
     __syncthreads();
-    if (lane == 0) { red[0][warp] = ee; red[1][warp] = et; red[2][warp] = tt; }
+    if (lane == 0) { red[0][warp] = ee; red[1][warp] = et; red[2][warp] = tt; red[3][warp] = ta; red[4][warp] = ea; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      float a = 0.f, b2 = 0.f, c = 0.f;
-      for (int w = 0; w < nw; ++w) { a += red[0][w]; b2 += red[1][w]; c += red[2][w]; }
-      bc[0] = a; bc[1] = b2; bc[2] = c;
+    if (threadIdx.x < 5) {
+      float s = 0.f;
+      for (int w = 0; w < nw; ++w) s += red[threadIdx.x][w];
+      bc[threadIdx.x] = s;
     }
     __syncthreads();
     // e == 0 (edited image identical to the original, i.e. delta == 0): the direction is undefined -- the reference divides
@@ -1051,13 +1077,18 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
     const float cosv = degenerate ? 0.f : bc[1] / (ne * nt);
     total -= cosv;
     if (d_tgt) {
+      const float k = -coef * inv_count / ne;
+      const float gdot = normalize ? k * (bc[3] / nt - cosv * bc[4] / ne) : 0.f;       // g . a
       for (int j = threadIdx.x; j < E; j += blockDim.x) {
-        const float e = e_tgt[(long long)n * E + j] - e_src[(long long)n * E + j];
-        const float dv = degenerate ? 0.f : -coef * inv_count * (text[j] / nt - cosv * e / ne) / ne;
+        const float ah = a[j] * ia, e = ah - b[j] * ib;
+        float dv = k * (text[j] / nt - cosv * e / ne);
+        if (normalize) dv = (dv - gdot * ah) * ia;
+        if (degenerate) dv = 0.f;
         d_tgt[(long long)n * E + j] = dv;
         dmax = fmaxf(dmax, fabsf(dv));
       }
     }
+    __syncthreads();                               // bc[] is rewritten by the next sample
   }
   if (threadIdx.x == 0) *loss_part = coef * inv_count * total;
   if (d_tgt && gscale_out) {
@@ -1094,7 +1125,9 @@ using namespace smc;
 
 extern "C" int smc_resample_fwd(const float* x, float* tmp, float* y, const int* start, const int* count, const float* wgt, int taps,
                                 int planes, int in_size, int out_size, int denorm_normalize, const float* mean3, const float* std3, void* stream) {
-  if (!x || !tmp || !y || !start || !count || !wgt || taps < 1 || planes < 1 || in_size < 1 || out_size < 1) return SMC_EINVAL;
+  if (!x || !tmp || !y || !start || !count || !wgt || taps < 1 || planes < 1 || in_size < 1 || out_size < 1 || denorm_normalize < 0 ||
+      denorm_normalize > 2)
+    return SMC_EINVAL;
   float m[3] = {0, 0, 0}, s[3] = {1, 1, 1};
   if (denorm_normalize) {
     if (!mean3 || !std3) return SMC_EINVAL;
@@ -1111,7 +1144,8 @@ extern "C" int smc_resample_fwd(const float* x, float* tmp, float* y, const int*
                                                                                             in_size, nseg, 7, denorm_normalize);
       const long long rows2 = (long long)planes * out_size;
       resample_h_kernel<<<grid1d(rows2 * out_size), 256, 0, ST>>>(tmp, y, start, count, wgt, taps, rows2, in_size, out_size, 0,
-                                                                  denorm_normalize ? out_size : 0, 1.f / 255.f, m[0], m[1], m[2], s[0], s[1], s[2]);
+                                                                  denorm_normalize ? out_size : 0, denorm_normalize == 2 ? 1.f : 1.f / 255.f, m[0], m[1], m[2],
+                                                                  s[0], s[1], s[2]);
       SMC_LAUNCH_CHECK();
       return SMC_OK;
     }
@@ -1120,29 +1154,29 @@ extern "C" int smc_resample_fwd(const float* x, float* tmp, float* y, const int*
   resample_h_kernel<<<grid1d(rows * out_size), 256, 0, ST>>>(x, tmp, start, count, wgt, taps, rows, in_size, out_size, denorm_normalize, 0, 1.f, 0.f,
                                                              0.f, 0.f, 1.f, 1.f, 1.f);
   resample_v_kernel<<<grid1d((long long)planes * out_size * out_size), 256, 0, ST>>>(tmp, y, start, count, wgt, taps, planes, in_size, out_size,
-                                                                                      out_size, 1.f / 255.f, m[0], m[1], m[2], s[0], s[1], s[2],
-                                                                                      denorm_normalize);
+                                                                                      out_size, denorm_normalize == 2 ? 1.f : 1.f / 255.f, m[0], m[1], m[2],
+                                                                                      s[0], s[1], s[2], denorm_normalize);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
 
 extern "C" int smc_resample_bwd(const float* g, const float* x, float* tmp, float* gx, const int* oidx, const int* count, const float* wgt,
-                                int taps, int planes, int in_size, int out_size, const float* std3, const float* unscale, void* stream) {
-  if (!g || !x || !tmp || !gx || !oidx || !count || !wgt || !std3 || taps < 1 || planes < 1) return SMC_EINVAL;
+                                int taps, int planes, int in_size, int out_size, int mode, const float* std3, const float* unscale, void* stream) {
+  if (!g || !x || !tmp || !gx || !oidx || !count || !wgt || !std3 || taps < 1 || planes < 1 || mode < 1 || mode > 2) return SMC_EINVAL;
   if (g_resample_vfirst && in_size >= 2 * out_size) {
     // transpose of the vertical-first order: expand the columns on the small [planes, out, .] tensor first, then the rows at full
     // width (coalesced along x) together with the clamp mask and the scale factors
     const long long rows1 = (long long)planes * out_size;
     resample_hT_kernel<<<grid1d(rows1 * in_size), 256, 0, ST>>>(g, nullptr, tmp, oidx, count, wgt, taps, rows1, in_size, out_size, nullptr);
     resample_vT_kernel<<<grid1d((long long)planes * in_size * in_size), 256, 0, ST>>>(tmp, gx, oidx, count, wgt, taps, planes, in_size, out_size,
-                                                                                       in_size, std3[0], std3[1], std3[2], x, unscale);
+                                                                                       in_size, std3[0], std3[1], std3[2], x, unscale, mode);
     SMC_LAUNCH_CHECK();
     return SMC_OK;
   }
   resample_vT_kernel<<<grid1d((long long)planes * in_size * out_size), 256, 0, ST>>>(g, tmp, oidx, count, wgt, taps, planes, in_size, out_size,
-                                                                                      out_size, std3[0], std3[1], std3[2], nullptr, nullptr);
+                                                                                      out_size, std3[0], std3[1], std3[2], nullptr, nullptr, mode);
   const long long rows = (long long)planes * in_size;
-  resample_hT_kernel<<<grid1d(rows * in_size), 256, 0, ST>>>(tmp, x, gx, oidx, count, wgt, taps, rows, in_size, out_size, unscale);
+  resample_hT_kernel<<<grid1d(rows * in_size), 256, 0, ST>>>(tmp, x, gx, oidx, count, wgt, taps, rows, in_size, out_size, unscale, mode);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
@@ -1297,9 +1331,9 @@ extern "C" int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln
   return SMC_OK;
 }
 extern "C" int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
-                             float inv_count, float* gscale_out, float gscale_target, void* stream) {
+                             float inv_count, float* gscale_out, float gscale_target, int normalize, void* stream) {
   if (!e_src || !e_tgt || !text || !loss_part || n < 1 || e < 1) return SMC_EINVAL;
-  clip_loss_kernel<<<1, 512, 0, ST>>>(e_src, e_tgt, text, loss_part, d_tgt, n, e, coef, inv_count, gscale_out, gscale_target);
+  clip_loss_kernel<<<1, 512, 0, ST>>>(e_src, e_tgt, text, loss_part, d_tgt, n, e, coef, inv_count, gscale_out, gscale_target, normalize);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

@@ -36,6 +36,10 @@ class CLIPLoss:
     """clip_loss.CLIPLoss (clip_loss.py:8-34) with the model and the token ids injected (``clip.load`` / ``clip.tokenize`` are
     external).  ``__call__`` is the differentiable drop-in; ``loss_and_grad`` is the fused kernel used by the step."""
 
+    normalize_features = False          # clip_loss.py:25-27: the difference of the raw embeddings
+    preprocess = 'unprocess'            # find_direction.py:49-52 ahead of the towers
+    needs_source = True                 # the original image's embedding enters the loss
+
     def __init__(self, model, pos_tokens, neg_tokens):
         self.model = model
         t = model.encode_text(pos_tokens) - model.encode_text(neg_tokens)            # clip_loss.py:15-17
@@ -57,8 +61,71 @@ class CLIPLoss:
         gscale = torch.ones(1, dtype=torch.float32, device=dev) if want_grad else None
         with torch.cuda.device(dev):
             _lib.call('smc_clip_loss', _lib.ptr(e_src), _lib.ptr(e_tgt), _lib.ptr(self.text_features), _lib.ptr(part), _lib.ptr(d_tgt), n, e,
-                      float(coef), float(inv_count), _lib.ptr(gscale), float(gscale_target), _lib.stream())
+                      float(coef), float(inv_count), _lib.ptr(gscale), float(gscale_target), int(self.normalize_features), _lib.stream())
         return part, d_tgt, gscale
+
+
+# clip_loss_nada.py:12-40: every class string is embedded through these 27 prompt templates (data of the loss definition)
+NADA_TEMPLATES = [
+    'a photo of a {}.', 'a rendering of a {}.', 'a cropped photo of the {}.', 'the photo of a {}.', 'a photo of a clean {}.', 'a photo of a dirty {}.',
+    'a dark photo of the {}.', 'a photo of my {}.', 'a photo of the cool {}.', 'a close-up photo of a {}.', 'a bright photo of the {}.',
+    'a cropped photo of a {}.', 'a photo of the {}.', 'a good photo of the {}.', 'a photo of one {}.', 'a close-up photo of the {}.',
+    'a rendition of the {}.', 'a photo of the clean {}.', 'a rendition of a {}.', 'a photo of a nice {}.', 'a good photo of a {}.',
+    'a photo of the nice {}.', 'a photo of the small {}.', 'a photo of the weird {}.', 'a photo of the large {}.', 'a photo of a cool {}.',
+    'a photo of a small {}.']
+
+
+def nada_template_texts(class_str):
+    """clip_loss_nada.py:203-204 ``compose_text_with_templates``: the strings to hand to the tokenizer."""
+    return [t.format(class_str) for t in NADA_TEMPLATES]
+
+
+class CLIPLossNADA(CLIPLoss):
+    """``clip_loss_type='nada'`` (find_direction.py:101-107; clip_loss_nada.py:206-218 ``clip_directional_loss``): the text direction is the
+    normalised mean over the prompt templates of (target - source) of the NORMALISED text embeddings (:150-157), both image embeddings are
+    normalised before the difference (:142-148), and the images go through the NADA preprocessing (:86-89: no clamp) instead of
+    ``unprocess``.  ``source_tokens`` / ``target_tokens``: the tokenised ``nada_template_texts`` of the negative / positive prompt, [27, 77]."""
+    normalize_features = True
+    preprocess = 'nada'
+
+    def __init__(self, model, source_tokens, target_tokens):
+        self.model = model
+        s, t = model.encode_text(source_tokens), model.encode_text(target_tokens)
+        s, t = s / s.norm(dim=-1, keepdim=True), t / t.norm(dim=-1, keepdim=True)          # get_text_features(norm=True), :129-140
+        d = (t - s).mean(dim=0, keepdim=True)                                               # :154
+        self.text_features = (d / d.norm(dim=-1, keepdim=True)).contiguous()                # :155, [1, 512]
+
+    def __call__(self, src_image, tgt_image):
+        """Differentiable drop-in on raw GAN outputs (what find_direction.py:151-158 passes)."""
+        a = self.model.encode_image(resample.nada_preprocess(tgt_image))
+        b = self.model.encode_image(resample.nada_preprocess(src_image))
+        e = a / a.norm(dim=-1, keepdim=True) - b / b.norm(dim=-1, keepdim=True)
+        e = e / e.norm(dim=-1, keepdim=True)
+        return (1.0 - torch.nn.functional.cosine_similarity(e, self.text_features)).mean()
+
+
+class CLIPLossNADAGlobal(CLIPLoss):
+    """``clip_loss_type='nada_global'`` (find_direction.py:108-114; clip_loss_nada.py:220-229 ``global_clip_loss``):
+    ``mean(1 - logits_per_image / 100)`` with ``logits = exp(logit_scale) * cos(image, text)`` for the single prompt ``f'a {target_class}'``
+    (:326-327).  The original image does not enter this loss.  ``text_tokens`` [1, 77]."""
+    preprocess = 'nada'
+    needs_source = False
+
+    def __init__(self, model, text_tokens):
+        self.model = model
+        t = model.encode_text(text_tokens)
+        if t.shape[0] != 1:
+            raise RuntimeError('nada_global: one prompt (find_direction.py passes [f"a {target_class}"])')
+        self.text_features = (t / t.norm(dim=-1, keepdim=True)).contiguous()
+        self.logit_gain = math.exp(model.logit_scale) / 100.0
+
+    def __call__(self, src_image, tgt_image):
+        a = self.model.encode_image(resample.nada_preprocess(tgt_image))
+        return (1.0 - self.logit_gain * torch.nn.functional.cosine_similarity(a, self.text_features)).mean()
+
+    def loss_and_grad(self, e_src, e_tgt, coef, inv_count, want_grad=True, gscale_target=64.0):
+        """cos(e_tgt, text) is the directional kernel with a zero source embedding; the logit gain rides in the coefficient."""
+        return super().loss_and_grad(torch.zeros_like(e_tgt), e_tgt, coef * self.logit_gain, inv_count, want_grad, gscale_target)
 
 
 def shard_rows(n_total, rank, world):
@@ -99,7 +166,7 @@ class DirectionFinder:
 
     def __init__(self, G, clip_model, pos_tokens, neg_tokens, resolution, device='cuda', learning_rate=1.5, clip_loss_coef=1.0,
                  l2_reg_coef=0.1, noise_mode='const', precision='x3p', micro_batch=16, process_group=None,
-                 trainable_rows=S_TRAINABLE_SPACE_CHANNELS, original_precision=None):
+                 trainable_rows=S_TRAINABLE_SPACE_CHANNELS, original_precision=None, clip_loss_type='default'):
         self.device = torch.device(device)
         self.engine = utils.engine_for(G, self.device, precision)
         # the original-image branch carries no gradient (find_direction.py:312); it may run in another engine mode (diagnostics:
@@ -110,7 +177,18 @@ class DirectionFinder:
         models = list(clip_model) if isinstance(clip_model, (tuple, list)) else [clip_model]
         if len(models) > len(DOUBLE_CLIP_WEIGHTS):
             raise ValueError('clip_model: one model (clip_type small) or two (clip_type double)')
-        self.clips = [(m, CLIPLoss(m, pos_tokens, neg_tokens), w) for m, w in zip(models, DOUBLE_CLIP_WEIGHTS)]
+        # find_direction.py:100-122 ``init_clip_loss``.  'default': pos / neg = the tokenised prompt and negative prompt; 'nada': the tokenised
+        # ``nada_template_texts`` of the prompt / negative prompt ([27, 77] each); 'nada_global': pos = tokenised f'a {prompt}' (neg unused)
+        if clip_loss_type == 'default':
+            make = lambda m: CLIPLoss(m, pos_tokens, neg_tokens)
+        elif clip_loss_type == 'nada':
+            make = lambda m: CLIPLossNADA(m, neg_tokens, pos_tokens)
+        elif clip_loss_type == 'nada_global':
+            make = lambda m: CLIPLossNADAGlobal(m, pos_tokens)
+        else:
+            raise ValueError("clip_loss_type must be 'default', 'nada' or 'nada_global'")
+        self.clip_loss_type = clip_loss_type
+        self.clips = [(m, make(m), w) for m, w in zip(models, DOUBLE_CLIP_WEIGHTS)]
         self.clip, self.loss_fn = self.clips[0][0], self.clips[0][1]
         self.lr, self.clip_loss_coef, self.l2_reg_coef = learning_rate, clip_loss_coef, l2_reg_coef
         self.noise_mode, self.micro_batch = noise_mode, micro_batch
@@ -152,7 +230,7 @@ class DirectionFinder:
         """CLIP embeddings of the un-edited images (find_direction.py:312: no gradient), one per tower."""
         with _phase('original_branch'):
             _, original, _ = self.engine_original.forward(s, self.until_k, self.noise_mode, save=False)
-            u_s = resample.unprocess_fwd(original)
+            u_s = resample.unprocess_fwd(original, mode=self.loss_fn.preprocess)
             del original
             return [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
 
@@ -165,10 +243,13 @@ class DirectionFinder:
         part_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
         direction = self.direction()
         eng = self.engine
+        pre = self.loss_fn.preprocess                  # 'unprocess' (find_direction.py:49-52) or the NADA preprocessing (clip_loss_nada.py:86-89)
+        need_src = self.loss_fn.needs_source           # nada_global never looks at the original image: that branch is not computed
         for lo in range(0, n_total, self.micro_batch):
             s = styles[lo:lo + self.micro_batch].to(self.device, torch.float32)
             s2 = s + direction                                                        # find_direction.py:308
-            if self.overlap:
+            e_s = [None] * len(self.clips)
+            if self.overlap and need_src:
                 cur = torch.cuda.current_stream(self.device)
                 if self._side is None:
                     self._side = torch.cuda.Stream(self.device)
@@ -179,14 +260,14 @@ class DirectionFinder:
             with _phase('synthesis_fwd'):
                 _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True, grad_rows=self.rows)   # :309
             with _phase('unprocess_fwd'):
-                u_t = resample.unprocess_fwd(img)                                                  # :159-160
-            if not self.overlap:
+                u_t = resample.unprocess_fwd(img, mode=pre)                                        # :159-160
+            if not self.overlap and need_src:
                 e_s = self._encode_original(s)
             g224 = gscale = None
             for i, (model, loss_fn, weight) in enumerate(self.clips):
                 with _phase('clip_fwd'):
                     e_t, csaved = model.encode_image_fwd(u_t, save=True)
-                if self.overlap and i == 0:
+                if self.overlap and need_src and i == 0:
                     cur.wait_stream(self._side)
                     for e in e_s:
                         e.record_stream(cur)
@@ -198,7 +279,7 @@ class DirectionFinder:
                 g224, gscale = (g, gs) if g224 is None else (g224 + g * (gscale / gs), gscale)
                 part_sum += part
             with _phase('unprocess_bwd'):
-                g_img = resample.unprocess_bwd(g224, img, unscale=gscale)
+                g_img = resample.unprocess_bwd(g224, img, unscale=gscale, mode=pre)
             with _phase('synthesis_bwd'):
                 grad += eng.backward(saved, g_img, self.rows, self.noise_mode)
         return grad, part_sum

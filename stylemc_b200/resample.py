@@ -90,7 +90,10 @@ _F3 = ctypes.c_float * 3
 _MEAN, _STD = _F3(*CLIP_MEAN), _F3(*CLIP_STD)
 
 
-def unprocess_fwd(img, size=224):
+MODES = {'unprocess': 1, 'nada': 2}     # find_direction.py:49-52 | clip_loss_nada.py:86-89 ((x + 1) / 2, no clamp, no / 255)
+
+
+def unprocess_fwd(img, size=224, mode='unprocess'):
     """img [N, 3, R, R] fp32 CUDA ([-1, 1]-ish) -> CLIP-normalised [N, 3, size, size] fp32."""
     _lib.require_cuda(img, 'img')
     n, c, h, w = img.shape
@@ -102,11 +105,11 @@ def unprocess_fwd(img, size=224):
     out = torch.empty([n, 3, size, size], dtype=torch.float32, device=img.device)
     with torch.cuda.device(img.device):
         _lib.call('smc_resample_fwd', _lib.ptr(img), _lib.ptr(tmp), _lib.ptr(out), _lib.ptr(tb['start']), _lib.ptr(tb['count']),
-                  _lib.ptr(tb['wgt']), tb['taps'], n * 3, h, size, 1, ctypes.addressof(_MEAN), ctypes.addressof(_STD), _lib.stream())
+                  _lib.ptr(tb['wgt']), tb['taps'], n * 3, h, size, MODES[mode], ctypes.addressof(_MEAN), ctypes.addressof(_STD), _lib.stream())
     return out
 
 
-def unprocess_bwd(g_out, img, unscale=None):
+def unprocess_bwd(g_out, img, unscale=None, mode='unprocess'):
     """Transpose of unprocess_fwd: g_out [N, 3, S, S] -> gradient w.r.t. img [N, 3, R, R].  ``unscale`` is an optional device
     scalar S: the result is divided by it (loss scale carried by g_out)."""
     n, c, size, _ = g_out.shape
@@ -117,23 +120,30 @@ def unprocess_bwd(g_out, img, unscale=None):
     gx = torch.empty_like(img)
     with torch.cuda.device(img.device):
         _lib.call('smc_resample_bwd', _lib.ptr(g_out), _lib.ptr(img), _lib.ptr(tmp), _lib.ptr(gx), _lib.ptr(tb['oidx']), _lib.ptr(tb['count_t']),
-                  _lib.ptr(tb['wgt_t']), tb['taps_t'], n * 3, h, size, ctypes.addressof(_STD), _lib.ptr(unscale), _lib.stream())
+                  _lib.ptr(tb['wgt_t']), tb['taps_t'], n * 3, h, size, MODES[mode], ctypes.addressof(_STD), _lib.ptr(unscale), _lib.stream())
     return gx
 
 
 class _Unprocess(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, size):
+    def forward(ctx, img, size, mode='unprocess'):
         ctx.save_for_backward(img)
-        return unprocess_fwd(img, size)
+        ctx.mode = mode
+        return unprocess_fwd(img, size, mode)
 
     @staticmethod
     def backward(ctx, g):
         img, = ctx.saved_tensors
-        return unprocess_bwd(g, img.float().contiguous()), None
+        return unprocess_bwd(g, img.float().contiguous(), mode=ctx.mode), None, None
 
 
 def unprocess(img, transf=None, mean=None, std=None, size=224):
     """Drop-in for find_direction.unprocess(img, transf, mean, std): the transform, mean and std arguments are accepted for
     signature compatibility; the kernel implements Resize(224, BICUBIC)+CenterCrop(224) on square inputs with CLIP's constants."""
     return _Unprocess.apply(img, size)
+
+
+def nada_preprocess(img, size=224):
+    """``CLIPLoss.preprocess`` of clip_loss_nada.py:86-89 on a square GAN output: Normalize(mean -1, std 2) (no clamp), Resize(224, BICUBIC) +
+    CenterCrop(224), Normalize(CLIP mean, std).  Differentiable."""
+    return _Unprocess.apply(img, size, 'nada')

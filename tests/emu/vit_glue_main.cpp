@@ -102,39 +102,55 @@ static int test_elementwise() {
   return report("quickgelu_fwd", e1, 4.0, 1e-6) + report("quickgelu_bwd", e2, 1.2, 1e-6) + report("split_rows", e3, 1.0, 1e-6);
 }
 
-static int test_clip_loss() {
+static int test_clip_loss_mode(int normalize) {
   const int N = 5, E = 700;            // E not a multiple of the block size; sample 3 is degenerate (edited == original)
   auto es = rnd((size_t)N * E), et = rnd((size_t)N * E), text = rnd(E);
   for (int j = 0; j < E; ++j) et[(size_t)3 * E + j] = es[(size_t)3 * E + j];
   const float coef = 0.7f, inv_count = 1.0f / 9.0f, target = 64.0f;
   std::vector<float> d((size_t)N * E, NAN);
   float part = NAN, gs = NAN;
-  emu_launch(1, 512, 0, [&] { clip_loss_kernel(es.data(), et.data(), text.data(), &part, d.data(), N, E, coef, inv_count, &gs, target); });
+  emu_launch(1, 512, 0, [&] { clip_loss_kernel(es.data(), et.data(), text.data(), &part, d.data(), N, E, coef, inv_count, &gs, target, normalize); });
   std::vector<double> want((size_t)N * E, 0.0);
   double total = 0, tt = 0, dmax = 0;
   for (int j = 0; j < E; ++j) tt += (double)text[j] * text[j];
   const double nt = std::sqrt(tt);
   for (int n = 0; n < N; ++n) {
+    // normalize: e = a/|a| - b/|b| (clip_loss_nada.py:162-168,213-216), gradient through the normalisation of a
+    double na = 1, nb = 1;
+    if (normalize) {
+      double aa = 0, bb = 0;
+      for (int j = 0; j < E; ++j) { aa += (double)et[(size_t)n * E + j] * et[(size_t)n * E + j]; bb += (double)es[(size_t)n * E + j] * es[(size_t)n * E + j]; }
+      na = std::sqrt(aa); nb = std::sqrt(bb);
+    }
+    std::vector<double> e(E), ah(E);
     double ee = 0, ed = 0;
-    for (int j = 0; j < E; ++j) { const double e = (double)et[(size_t)n * E + j] - es[(size_t)n * E + j]; ee += e * e; ed += e * text[j]; }
+    for (int j = 0; j < E; ++j) {
+      ah[j] = et[(size_t)n * E + j] / na;
+      e[j] = ah[j] - es[(size_t)n * E + j] / nb;
+      ee += e[j] * e[j]; ed += e[j] * text[j];
+    }
     if (!(ee > 0)) continue;
     const double ne = std::sqrt(ee), c = ed / (ne * nt);
     total -= c;
+    std::vector<double> g(E);
+    double gdot = 0;
+    for (int j = 0; j < E; ++j) { g[j] = -coef * inv_count * (text[j] / nt - c * e[j] / ne) / ne; gdot += g[j] * ah[j]; }
     for (int j = 0; j < E; ++j) {
-      const double e = (double)et[(size_t)n * E + j] - es[(size_t)n * E + j];
-      want[(size_t)n * E + j] = -coef * inv_count * (text[j] / nt - c * e / ne) / ne;
+      want[(size_t)n * E + j] = normalize ? (g[j] - gdot * ah[j]) / na : g[j];
       dmax = std::max(dmax, std::fabs(want[(size_t)n * E + j]));
     }
   }
   const double S = std::exp2(std::floor(std::log2(target / dmax)));
   double err = 0;
   for (size_t i = 0; i < want.size(); ++i) err = std::max(err, std::fabs(d[i] - S * want[i]));
-  int bad = report("clip_loss: loss partial sum", std::fabs(part - coef * inv_count * total), std::fabs(coef * inv_count * total), 4e-6);
-  bad += report("clip_loss: d_tgt * scale", err, S * dmax, 4e-6);
+  int bad = report(normalize ? "clip_loss (normalised): loss partial sum" : "clip_loss: loss partial sum", std::fabs(part - coef * inv_count * total),
+                   std::fabs(coef * inv_count * total), 4e-6);
+  bad += report("clip_loss: d_tgt * scale", err, S * dmax, 2e-5);
   bad += report("clip_loss: loss scale", std::fabs(gs - S), S, 0.0);
   bad += report("clip_loss: scaled max in range", (S * dmax >= target / 2 && S * dmax < target) ? 0.0 : 1.0, 1.0, 0.0);
   return bad;
 }
+static int test_clip_loss() { return test_clip_loss_mode(0) + test_clip_loss_mode(1); }
 
 int main() {
   srand(11);

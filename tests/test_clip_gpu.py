@@ -120,3 +120,42 @@ def test_clip_loss_kernel_and_drop_in(model, params):
     assert abs((1.0 + part.item()) - ref.item()) <= 1e-5
     assert rel(d_t / gs, etr.grad) <= 1e-5
     assert 32.0 <= (d_t.abs().max()).item() < 64.0
+
+
+@pytest.mark.parametrize('kind', ['nada', 'nada_global'])
+def test_step_nada_losses_64px_golden(golden, params, kind):
+    """clip_loss_type 'nada' / 'nada_global' (find_direction.py:101-114,150-158) against the reference's real clip_loss_nada.CLIPLoss driven by
+    its own init_clip_loss / compute_clip_loss (tests/golden/step64_nada.npz, oracle/pin_reference.py::pin_step_nada): loss and delta-S
+    gradient of one step on the 64-px network, BASELINE tolerances; and the preprocessing (no clamp, (x + 1) / 2) against the reference's
+    transform pipeline."""
+    from oracle import direction as o_dir
+    from oracle import synthesis as o_syn
+    from stylemc_b200 import clip, direction, resample
+    g, g64 = golden('step64_nada'), golden('step64')
+    pos_text, neg_text = str(g['pos_text']), str(g['neg_text'])
+    G = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    o_syn.get_temp_shapes(G)
+    model = clip.CLIPModel(params, 'cuda', precision='x3p')
+    if kind == 'nada':
+        pos = o_vit.synthetic_tokenize(direction.nada_template_texts(pos_text))
+        neg = o_vit.synthetic_tokenize(direction.nada_template_texts(neg_text))
+        assert direction.NADA_TEMPLATES == o_dir.NADA_TEMPLATES and pos.shape == (27, 77)
+    else:
+        pos, neg = o_vit.synthetic_tokenize([f'a {pos_text}']), None
+    f = direction.DirectionFinder(G, model, pos, neg, 64, clip_loss_type=kind)
+    styles = torch.as_tensor(g64['styles']).cuda()
+    f.delta.copy_(torch.as_tensor(g64['delta']).cuda())
+    out = f.step(styles, lr=0.0)
+    ref_grad = torch.as_tensor(g[kind + '.grad'])[0]
+    loss_rel = abs(out['loss'].item() - float(g[kind + '.loss'])) / abs(float(g[kind + '.loss']))
+    clip_rel = abs(out['clip_loss'].item() - float(g[kind + '.clip_loss'])) / abs(float(g[kind + '.clip_loss']))
+    grad_rel = ((out['grad'].cpu() - ref_grad).norm() / ref_grad.norm()).item()
+    print(f'{kind}: loss {out["loss"].item():.6f} ref {float(g[kind + ".loss"]):.6f} rel {loss_rel:.2e}; clip rel {clip_rel:.2e}; grad rel-l2 {grad_rel:.3e}')
+    assert loss_rel <= 1e-3 and clip_rel <= 1e-3 and grad_rel <= 1e-3
+    # the differentiable drop-in (autograd through resample.nada_preprocess and CLIPModel.encode_image) gives the same loss
+    _, img, _ = f.engine.forward(styles + f.direction(), until_k=100)
+    _, orig, _ = f.engine.forward(styles, until_k=100)
+    drop_in = f.loss_fn(orig, img).item()
+    assert abs(drop_in - out['clip_loss'].item()) <= 1e-5 * abs(drop_in)
+    pre = resample.nada_preprocess(orig[:1]).cpu()
+    assert (pre - torch.as_tensor(g['preprocessed'])).abs().max().item() <= 2e-4

@@ -105,3 +105,18 @@ def test_step_double_golden(golden):
     assert abs(o['loss'].item() - float(gd['loss'])) <= 1e-6
     assert abs(o['clip_loss'].item() - float(gd['clip_loss'])) <= 1e-6
     assert ((o['grad'] - T(gd['grad'])).norm() / T(gd['grad']).norm()).item() <= 1e-4
+
+
+@pytest.mark.parametrize('kind', ['nada', 'nada_global'])
+def test_step_nada_golden(golden, kind):
+    """clip_loss_type 'nada' / 'nada_global': the reference's real clip_loss_nada.CLIPLoss through init_clip_loss / compute_clip_loss
+    (find_direction.py:101-114,150-158; tests/golden/step64_nada.npz) vs oracle.direction.CLIPLossNADA; styles and delta of step64.npz."""
+    g, gn = golden('step64'), golden('step64_nada')
+    G = synthesis.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    shapes = synthesis.get_temp_shapes(G)
+    kw = dict(lambda_direction=0.0, lambda_global=1.0) if kind == 'nada_global' else {}
+    loss_fn = direction.CLIPLossNADA(vit.CLIP(seed=0), vit.synthetic_tokenize, **kw)
+    o = direction.direction_step(G, shapes, loss_fn, T(g['styles']), T(g['delta']), 100, nada_prompts=(str(gn['neg_text']), str(gn['pos_text'])))
+    assert abs(o['loss'].item() - float(gn[kind + '.loss'])) <= 1e-6
+    assert ((o['grad'] - T(gn[kind + '.grad'])).norm() / T(gn[kind + '.grad']).norm()).item() <= 1e-4
+    assert (direction.nada_preprocess(o['original_img'])[:1] - T(gn['preprocessed'])).abs().max().item() <= 1e-5
