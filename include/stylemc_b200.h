@@ -237,9 +237,10 @@ int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln, int b, in
  * (loss scaling for the fp16-operand backward GEMMs; smc_resample_bwd divides it out again). */
 /* normalize != 0: the NADA directional form (clip_loss_nada.py:162-168,206-218): e = tgt/|tgt| - src/|src| instead of tgt - src, gradient taken
  * through the normalisation of tgt.  The "global" NADA term (clip_loss_nada.py:220-229) is this entry point with e_src = 0, text = the prompt
- * embedding and coef multiplied by exp(logit_scale) / 100. */
+ * embedding and coef multiplied by exp(logit_scale) / 100.  text_stride: 0 = one text vector for the batch; e = one target vector PER SAMPLE
+ * (the identity loss 1 - <f(edited) / |.|, f(original) / |.|>, id_loss.py:26-39, is this entry point with e_src = 0 and text = f(original)). */
 int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
-                  float inv_count, float* gscale_out, float gscale_target, int normalize, void* stream);
+                  float inv_count, float* gscale_out, float gscale_target, int normalize, int text_stride, void* stream);
 
 /* ---- generate_fromS output stage ---------------------------------------------------------------
  * out[n, y, x_off + x, j] = uint8(clamp(img[n, j, y, x] * 127.5 + 128, 0, 255))   (generate_fromS.py:174-175; canvas [N, H, canvas_w, 3],
@@ -254,6 +255,14 @@ int smc_img_to_uint8(const float* img, unsigned char* out, int n, int h, int w, 
  * scalar multiplied into the planes (a power of two from smc_grad_scale). */
 int smc_prepare_weights(const float* w, int n_out, int n_in, int ntaps, int n_out_padded, int n_in_padded, const float* scale,
                         void* fwd_hi, void* fwd_lo, void* bwd_hi, void* bwd_lo, float* q, void* stream);
+
+/* ---- identity-loss glue (id_loss/id_loss.py:18-24, id_loss/helpers.py:58-119) ------------------------------------
+ * smc_prelu: y = x > 0 ? x : alpha[c] * x on NCHW fp32 (torch.nn.PReLU(C)); with dy != NULL the input gradient dy * (x > 0 ? 1 : alpha[c]).
+ * smc_adaptive_avg_pool: torch.nn.AdaptiveAvgPool2d((oh, ow)) of the window [y0, y0 + hc) x [x0, x0 + wc) of every [h, w] plane
+ * (id_loss.py:12-13,19-22: pool to 256, crop [35:223, 32:220], pool to 112); backward != 0: x is dy [planes, oh, ow], y is dx [planes, h, w]. */
+int smc_prelu(const float* x, const float* dy, const float* alpha, float* y, int64_t numel, int hw, int c, void* stream);
+int smc_adaptive_avg_pool(const float* x, float* y, int64_t planes, int h, int w, int y0, int x0, int hc, int wc, int oh, int ow,
+                          int backward, void* stream);
 
 /* ---- fma.py:15-58 as a stand-alone op (on the fused path the multiply-add is the GEMM epilogue) -----------------------
  * smc_fma: out = a * b + c over the broadcast index space `shape` (4 sizes, leading 1s for lower ranks); stride_* are ELEMENT strides

@@ -28,7 +28,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = '/root/reference'
 sys.path.insert(0, REPO)
 
-from oracle import act, conv, direction, fir, synthesis, vit  # noqa: E402
+from oracle import act, conv, direction, fir, idloss, synthesis, vit  # noqa: E402
 
 GOLD = os.path.join(REPO, 'tests', 'golden')
 
@@ -383,6 +383,49 @@ def pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, out):
 B16_SEED = 7
 
 
+def pin_idloss(R, out):
+    """The identity loss (find_direction.py:179-180): the reference's REAL id_loss.model_irse.Backbone (IR-SE50, eval mode) loaded (strict)
+    with oracle.idloss.random_irse50_params, and the REAL IDLoss.extract_feats / IDLoss.forward run on an instance built without the
+    checkpoint file (id_loss/model_ir_se50.pth is not in the tree), vs oracle.idloss; 256-px and 1024-px shaped inputs."""
+    print('idloss: reference id_loss.IDLoss / model_irse.Backbone vs oracle.idloss (random IR-SE50 parameters)')
+    sys.path.insert(0, REF)
+    from id_loss.id_loss import IDLoss
+    from id_loss.model_irse import Backbone
+    p = idloss.random_irse50_params(seed=0)
+    net = Backbone(input_size=112, num_layers=50, drop_ratio=0.6, mode='ir_se')
+    net.load_state_dict(p, strict=True)                      # key names and shapes of the restated parameter dict
+    net.eval()
+    ref = IDLoss.__new__(IDLoss)                             # IDLoss.__init__ insists on the checkpoint file: build the same object by hand
+    torch.nn.Module.__init__(ref)
+    ref.facenet, ref.pool, ref.face_pool = net, torch.nn.AdaptiveAvgPool2d((256, 256)), torch.nn.AdaptiveAvgPool2d((112, 112))
+    g = torch.Generator().manual_seed(9)
+    for tag, res in (('256', 256), ('512', 512)):
+        base = torch.nn.functional.interpolate(torch.randn(2, 3, res // 8, res // 8, generator=g), size=res, mode='bicubic', align_corners=False) * 0.6
+        y = base.clone()
+        y_hat = (base + 0.15 * torch.nn.functional.interpolate(torch.randn(2, 3, res // 16, res // 16, generator=g), size=res, mode='bicubic',
+                                                                 align_corners=False)).requires_grad_(True)
+        with torch.no_grad():
+            fr = ref.extract_feats(y)
+        close(idloss.extract_feats(p, y), fr, 1e-5, f'extract_feats {tag} px')
+        loss_r, _ = ref(y_hat, y)
+        loss_r.backward()
+        yh2 = y_hat.detach().clone().requires_grad_(True)
+        loss_o = idloss.id_loss(p, yh2, y)
+        g_o, = torch.autograd.grad(loss_o, yh2)
+        close(loss_o.detach(), loss_r.detach(), 1e-6, f'id loss {tag} px')
+        rel = ((g_o - y_hat.grad).norm() / y_hat.grad.norm()).item()
+        print(f'  {tag} px: loss {loss_r.item():.6f}, image-gradient rel-l2 {rel:.2e}, |grad| {y_hat.grad.norm():.3e}')
+        assert rel < 1e-4
+        if res == 256:
+            out['y'], out['y_hat'] = y.numpy(), y_hat.detach().numpy()
+            out['feats_y'], out['loss'], out['grad'] = fr.numpy(), loss_r.detach().numpy(), y_hat.grad.numpy()
+            out['crop112'] = idloss.face_crop(y)[:1].numpy()
+        else:
+            out['y512_seed'] = np.array(9)
+            out['loss512'], out['grad512_norm'] = loss_r.detach().numpy(), y_hat.grad.norm().numpy()
+            out['grad512_down'] = torch.nn.functional.avg_pool2d(y_hat.grad, 8).numpy()
+
+
 def pin_step_nada(R, model, G_ref, G_ora, S, shapes, out):
     """clip_loss_type 'nada' and 'nada_global' (find_direction.py:101-114,150-158): the reference's REAL clip_loss_nada.CLIPLoss
     (clip_loss_nada.py:66-345) driven by its own init_clip_loss / compute_clip_loss, on a stub ``clip`` module (oracle ViT-B/32,
@@ -514,13 +557,14 @@ def main():
     ap.add_argument('--skip-config1', action='store_true')
     ap.add_argument('--skip-config4', action='store_true')
     ap.add_argument('--only-config4', action='store_true', help='(re)write only config4.npz')
+    ap.add_argument('--only-idloss', action='store_true', help='(re)write only idloss.npz')
     ap.add_argument('--only-nada', action='store_true', help='(re)write only step64_nada.npz')
     ap.add_argument('--only-ops', action='store_true', help='(re)write only ops.npz')
     ap.add_argument('--only-double', action='store_true', help='(re)write only clip_b16.npz and step64_double.npz')
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     R = import_reference()
-    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'step64_nada', 'config1', 'config4')}
+    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'step64_nada', 'idloss', 'config1', 'config4')}
     if args.only_config4:
         model = vit.CLIP(seed=0, cfg=vit.VIT_B32)
         install_stub_clip(R, model)
@@ -528,6 +572,12 @@ def main():
         if not args.check:
             np.savez_compressed(os.path.join(GOLD, 'config4.npz'), **fx['config4'])
             print('wrote config4.npz', f'{os.path.getsize(os.path.join(GOLD, "config4.npz")) / 1e6:.2f} MB')
+        return
+    if args.only_idloss:
+        pin_idloss(R, fx['idloss'])
+        if not args.check:
+            np.savez_compressed(os.path.join(GOLD, 'idloss.npz'), **fx['idloss'])
+            print('wrote idloss.npz', f'{os.path.getsize(os.path.join(GOLD, "idloss.npz")) / 1e6:.2f} MB')
         return
     if args.only_nada:
         G_ref, G_ora, S, shapes = pin_driver(R, fx['synth64'])
@@ -550,6 +600,7 @@ def main():
     pin_step(R, model, G_ref, G_ora, S, shapes, fx['step64'])
     pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, fx['step64_double'])
     pin_step_nada(R, model, G_ref, G_ora, S, shapes, fx['step64_nada'])
+    pin_idloss(R, fx['idloss'])
     if not args.skip_config1 and not args.only_double:
         pin_config1(R, model, fx['config1'])
     if not args.skip_config4 and not args.only_double:

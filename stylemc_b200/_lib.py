@@ -101,9 +101,11 @@ SIGNATURES = {
     'smc_split_rows': 'ppp q iiii p',
     'smc_head_proj': 'ppp iii p',
     'smc_head_proj_bwd': 'ppp iii p',
-    'smc_clip_loss': 'ppppp ii ff p f i p',
+    'smc_clip_loss': 'ppppp ii ff p f ii p',
     'smc_img_to_uint8': 'pp iiiii p',
     'smc_prepare_weights': 'p iiiii p pppp p p',
+    'smc_prelu': 'pppp q ii p',
+    'smc_adaptive_avg_pool': 'pp q iiiiiiii i p',
     'smc_fma': 'pppp i pppp p',
     'smc_fma_reduce': 'ppp i pppp p',
     'smc_sgd_step': 'pp q fff p',

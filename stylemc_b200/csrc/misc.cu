@@ -98,6 +98,59 @@ __global__ void __launch_bounds__(256) prepare_weights_kernel(PrepW p) {
   }
 }
 
+// ---- identity-loss glue (id_loss/id_loss.py:18-24, id_loss/helpers.py): per-channel PReLU and adaptive average pooling of a cropped window
+// y = x > 0 ? x : alpha[c] * x on NCHW (channel = (i / hw) % C); grad != 0: y = dy * (x > 0 ? 1 : alpha[c])
+__global__ void __launch_bounds__(256) prelu_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ alpha,
+                                                    float* __restrict__ y, long long total, int hw, int C) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i], a = __ldg(alpha + (int)((i / hw) % C));
+    y[i] = dy ? dy[i] * (v > 0.f ? 1.f : a) : (v > 0.f ? v : a * v);
+  }
+}
+// torch.nn.AdaptiveAvgPool2d over the window [y0, y0 + hc) x [x0, x0 + wc) of every plane: output (oy, ox) averages rows
+// floor(oy * hc / OH) .. ceil((oy + 1) * hc / OH) - 1 of the window (and the same for columns).
+__device__ __forceinline__ int ap_start(int o, int in, int out) { return (int)(((long long)o * in) / out); }
+__device__ __forceinline__ int ap_end(int o, int in, int out) { return (int)((((long long)(o + 1)) * in + out - 1) / out); }
+__global__ void __launch_bounds__(256) adaptive_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int H, int W,
+                                                                int y0, int x0, int hc, int wc, int OH, int OW) {
+  const long long total = planes * OH * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW), oy = (int)((i / OW) % OH);
+    const long long pl = i / ((long long)OW * OH);
+    const int ys = ap_start(oy, hc, OH), ye = ap_end(oy, hc, OH), xs = ap_start(ox, wc, OW), xe = ap_end(ox, wc, OW);
+    const float* src = x + pl * H * W;
+    float acc = 0.f;
+    for (int yy = ys; yy < ye; ++yy)
+      for (int xx = xs; xx < xe; ++xx) acc += __ldg(src + (long long)(y0 + yy) * W + x0 + xx);
+    y[i] = acc / (float)((ye - ys) * (xe - xs));
+  }
+}
+// transpose: every input pixel gathers dy / window size from the (few) outputs whose window contains it; pixels outside the crop get 0
+__global__ void __launch_bounds__(256) adaptive_pool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long planes, int H, int W,
+                                                                int y0, int x0, int hc, int wc, int OH, int OW) {
+  const long long total = planes * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W) - x0, yy = (int)((i / W) % H) - y0;
+    const long long pl = i / ((long long)W * H);
+    float acc = 0.f;
+    if (yy >= 0 && yy < hc && xx >= 0 && xx < wc) {
+      const int oy_lo = max(0, (int)(((long long)yy * OH) / hc) - 1), oy_hi = min(OH - 1, (int)(((long long)(yy + 1) * OH + hc - 1) / hc));
+      const int ox_lo = max(0, (int)(((long long)xx * OW) / wc) - 1), ox_hi = min(OW - 1, (int)(((long long)(xx + 1) * OW + wc - 1) / wc));
+      const float* g = dy + pl * OH * OW;
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        const int ys = ap_start(oy, hc, OH), ye = ap_end(oy, hc, OH);
+        if (yy < ys || yy >= ye) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          const int xs = ap_start(ox, wc, OW), xe = ap_end(ox, wc, OW);
+          if (xx < xs || xx >= xe) continue;
+          acc += __ldg(g + (long long)oy * OW + ox) / (float)((ye - ys) * (xe - xs));
+        }
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
 // ---- fma.py:15-58 as stand-alone kernels: out = a * b + c over a broadcast 4-D index space, and the "un-broadcast" of its
 // backward (sum of x * y over the axes broadcasting expanded).  Element strides; 0 marks a broadcast / reduced axis.
 struct FmaDims {
@@ -220,6 +273,29 @@ extern "C" int smc_prepare_weights(const float* w, int n_out, int n_in, int ntap
   long long blocks = smc::ceil_div_ll(p.n_fwd + p.n_bwd + p.n_q, 256);
   if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
   smc::prepare_weights_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_prelu(const float* x, const float* dy, const float* alpha, float* y, int64_t numel, int hw, int c, void* stream) {
+  if (!x || !alpha || !y || numel < 1 || hw < 1 || c < 1) return SMC_EINVAL;
+  long long blocks = smc::ceil_div_ll(numel, 256);
+  if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
+  smc::prelu_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, dy, alpha, y, numel, hw, c);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_adaptive_avg_pool(const float* x, float* y, int64_t planes, int h, int w, int y0, int x0, int hc, int wc, int oh, int ow,
+                                     int backward, void* stream) {
+  if (!x || !y || planes < 1 || h < 1 || w < 1 || oh < 1 || ow < 1 || y0 < 0 || x0 < 0 || hc < 1 || wc < 1 || y0 + hc > h || x0 + wc > w)
+    return SMC_EINVAL;
+  const long long total = planes * (backward ? (long long)h * w : (long long)oh * ow);
+  if (total > 0x7fffffffLL * 4) return SMC_ETOOLARGE;
+  long long blocks = smc::ceil_div_ll(total, 256);
+  if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
+  if (backward) smc::adaptive_pool_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, planes, h, w, y0, x0, hc, wc, oh, ow);
+  else smc::adaptive_pool_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, planes, h, w, y0, x0, hc, wc, oh, ow);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

@@ -1029,7 +1029,7 @@ __global__ void __launch_bounds__(256) head_proj_bwd_kernel(const float* __restr
 // e = tgt/|tgt| - src/|src|, and the gradient is taken through the normalisation of tgt: d = (g - (g . a) a) / |tgt| with a = tgt/|tgt|.
 __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict__ e_src, const float* __restrict__ e_tgt, const float* __restrict__ text,
                                                         float* __restrict__ loss_part, float* __restrict__ d_tgt, int N, int E, float coef,
-                                                        float inv_count, float* __restrict__ gscale_out, float gscale_target, int normalize) {
+                                                        float inv_count, float* __restrict__ gscale_out, float gscale_target, int normalize, int text_stride = 0) {
   __shared__ float red[5][16];
   __shared__ float bc[5];
   float dmax = 0.f;
@@ -1038,6 +1038,7 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
   for (int n = 0; n < N; ++n) {
     const float* a = e_tgt + (long long)n * E;
     const float* b = e_src + (long long)n * E;
+    const float* tx = text + (long long)n * text_stride;          // text_stride = E: one target vector per sample (identity loss)
     float ia = 1.f, ib = 1.f;                      // 1 / |tgt|, 1 / |src| (normalize), else 1
     if (normalize) {
       float aa = 0.f, bb = 0.f;
@@ -1057,7 +1058,7 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
     }
     float ee = 0.f, et = 0.f, tt = 0.f, ta = 0.f, ea = 0.f;
     for (int j = threadIdx.x; j < E; j += blockDim.x) {
-      const float ah = a[j] * ia, e = ah - b[j] * ib, t = text[j];
+      const float ah = a[j] * ia, e = ah - b[j] * ib, t = tx[j];
       ee += e * e; et += e * t; tt += t * t; ta += t * ah; ea += e * ah;
     }
     ee = warp_sum(ee); et = warp_sum(et); tt = warp_sum(tt); ta = warp_sum(ta); ea = warp_sum(ea);
@@ -1081,7 +1082,7 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
       const float gdot = normalize ? k * (bc[3] / nt - cosv * bc[4] / ne) : 0.f;       // g . a
       for (int j = threadIdx.x; j < E; j += blockDim.x) {
         const float ah = a[j] * ia, e = ah - b[j] * ib;
-        float dv = k * (text[j] / nt - cosv * e / ne);
+        float dv = k * (tx[j] / nt - cosv * e / ne);
         if (normalize) dv = (dv - gdot * ah) * ia;
         if (degenerate) dv = 0.f;
         d_tgt[(long long)n * E + j] = dv;
@@ -1109,7 +1110,7 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
 
 int g_attention_tiled = 0;   // 0: tiled attention only where the whole-sequence kernel does not fit; 1: always; >= 4: always, rows per CTA capped
                              // at that value (smc_synth_config key 5; tests exercise several row blocks at 50 tokens this way)
-int g_resample_vfirst = 0;   // unprocess: vertical pass first for >= 2x down-sampling (smc_synth_config key 4)
+int g_resample_vfirst = 1;   // unprocess: vertical pass first for >= 2x down-sampling (smc_synth_config key 4; 0 = horizontal first)
 
 static int grid1d(long long items) {
   long long b = ceil_div_ll(items, 256);
@@ -1331,9 +1332,9 @@ extern "C" int smc_head_proj_bwd(const float* d_e, const float* proj, float* dln
   return SMC_OK;
 }
 extern "C" int smc_clip_loss(const float* e_src, const float* e_tgt, const float* text, float* loss_part, float* d_tgt, int n, int e, float coef,
-                             float inv_count, float* gscale_out, float gscale_target, int normalize, void* stream) {
-  if (!e_src || !e_tgt || !text || !loss_part || n < 1 || e < 1) return SMC_EINVAL;
-  clip_loss_kernel<<<1, 512, 0, ST>>>(e_src, e_tgt, text, loss_part, d_tgt, n, e, coef, inv_count, gscale_out, gscale_target, normalize);
+                             float inv_count, float* gscale_out, float gscale_target, int normalize, int text_stride, void* stream) {
+  if (!e_src || !e_tgt || !text || !loss_part || n < 1 || e < 1 || (text_stride != 0 && text_stride < e)) return SMC_EINVAL;
+  clip_loss_kernel<<<1, 512, 0, ST>>>(e_src, e_tgt, text, loss_part, d_tgt, n, e, coef, inv_count, gscale_out, gscale_target, normalize, text_stride);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

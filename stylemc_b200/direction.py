@@ -61,7 +61,8 @@ class CLIPLoss:
         gscale = torch.ones(1, dtype=torch.float32, device=dev) if want_grad else None
         with torch.cuda.device(dev):
             _lib.call('smc_clip_loss', _lib.ptr(e_src), _lib.ptr(e_tgt), _lib.ptr(self.text_features), _lib.ptr(part), _lib.ptr(d_tgt), n, e,
-                      float(coef), float(inv_count), _lib.ptr(gscale), float(gscale_target), int(self.normalize_features), _lib.stream())
+                      float(coef), float(inv_count), _lib.ptr(gscale), float(gscale_target), int(self.normalize_features),
+                      e if self.text_features.shape[0] > 1 else 0, _lib.stream())
         return part, d_tgt, gscale
 
 
@@ -166,7 +167,8 @@ class DirectionFinder:
 
     def __init__(self, G, clip_model, pos_tokens, neg_tokens, resolution, device='cuda', learning_rate=1.5, clip_loss_coef=1.0,
                  l2_reg_coef=0.1, noise_mode='const', precision='x3p', micro_batch=16, process_group=None,
-                 trainable_rows=S_TRAINABLE_SPACE_CHANNELS, original_precision=None, clip_loss_type='default'):
+                 trainable_rows=S_TRAINABLE_SPACE_CHANNELS, original_precision=None, clip_loss_type='default', id_loss=None,
+                 identity_loss_coef=0.0):
         self.device = torch.device(device)
         self.engine = utils.engine_for(G, self.device, precision)
         # the original-image branch carries no gradient (find_direction.py:312); it may run in another engine mode (diagnostics:
@@ -188,6 +190,11 @@ class DirectionFinder:
         else:
             raise ValueError("clip_loss_type must be 'default', 'nada' or 'nada_global'")
         self.clip_loss_type = clip_loss_type
+        # identity term (find_direction.py:179-180,193): ``id_loss`` = stylemc_b200.idloss.IDLoss; its coefficient defaults to 0 here (the
+        # benchmark objective is the CLIP + L2 terms), the reference CLI's default is 0.6 (find_direction.py:225)
+        self.id_loss, self.identity_loss_coef = id_loss, float(identity_loss_coef)
+        if self.identity_loss_coef != 0.0 and id_loss is None:
+            raise ValueError('identity_loss_coef != 0 needs id_loss (stylemc_b200.idloss.IDLoss)')
         self.clips = [(m, make(m), w) for m, w in zip(models, DOUBLE_CLIP_WEIGHTS)]
         self.clip, self.loss_fn = self.clips[0][0], self.clips[0][1]
         self.lr, self.clip_loss_coef, self.l2_reg_coef = learning_rate, clip_loss_coef, l2_reg_coef
@@ -231,8 +238,11 @@ class DirectionFinder:
         with _phase('original_branch'):
             _, original, _ = self.engine_original.forward(s, self.until_k, self.noise_mode, save=False)
             u_s = resample.unprocess_fwd(original, mode=self.loss_fn.preprocess)
-            del original
-            return [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
+            e_s = [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
+            return e_s + [original] if self._use_id() else e_s
+
+    def _use_id(self):
+        return self.id_loss is not None and self.identity_loss_coef != 0.0
 
     def loss_and_grad(self, styles, global_count=None):
         """styles [n, 26, 512] (this rank's shard, device) -> (grad [8, 512] summed over the shard, clip-loss partial sum).
@@ -241,10 +251,11 @@ class DirectionFinder:
         count = n_total if global_count is None else global_count
         grad = torch.zeros([len(self.rows), synthesis.STYLE_WIDTH], dtype=torch.float32, device=self.device)
         part_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._id_part = torch.zeros(1, dtype=torch.float32, device=self.device)
         direction = self.direction()
         eng = self.engine
         pre = self.loss_fn.preprocess                  # 'unprocess' (find_direction.py:49-52) or the NADA preprocessing (clip_loss_nada.py:86-89)
-        need_src = self.loss_fn.needs_source           # nada_global never looks at the original image: that branch is not computed
+        need_src = self.loss_fn.needs_source or self._use_id()     # nada_global alone never looks at the original image
         for lo in range(0, n_total, self.micro_batch):
             s = styles[lo:lo + self.micro_batch].to(self.device, torch.float32)
             s2 = s + direction                                                        # find_direction.py:308
@@ -280,9 +291,15 @@ class DirectionFinder:
                 part_sum += part
             with _phase('unprocess_bwd'):
                 g_img = resample.unprocess_bwd(g224, img, unscale=gscale, mode=pre)
+            if self._use_id():
+                with _phase('identity_loss'):       # id_loss.py:26-39 on (generated, original): adds its image gradient and its partial sum
+                    part_id, g_id = self.id_loss.loss_and_grad(img, e_s[len(self.clips)], self.identity_loss_coef, 1.0 / count)
+                    g_img = g_img + g_id
+                    self._id_part += part_id
             with _phase('synthesis_bwd'):
                 grad += eng.backward(saved, g_img, self.rows, self.noise_mode)
-        return grad, part_sum
+        # with the identity term the partial sums travel together: [clip, identity] (one all-reduce either way)
+        return grad, (torch.cat([part_sum, self._id_part]) if self._use_id() else part_sum)
 
     def step(self, styles, lr=None, global_count=None):
         """One optimisation step on this rank's shard.  Returns a dict of device scalars (loss, clip_loss, l2_loss, grad_norm)."""
@@ -297,9 +314,14 @@ class DirectionFinder:
                 grad, part = allreduce_step(grad, part, self.group)
         numel = self.delta.numel()
         l2 = self.l2_reg_coef * self.delta.square().mean()                            # find_direction.py:190-191 (batch independent)
-        clip_loss = self.clip_loss_coef * sum(w for _, _, w in self.clips) + part     # sum over towers of w * coef * (count - sum cos) / count
+        clip_loss = self.clip_loss_coef * sum(w for _, _, w in self.clips) + part[:1]     # sum over towers of w * coef * (count - sum cos) / count
+        id_loss = (self.identity_loss_coef + part[1:2]) if self._use_id() else None      # coef * (count - sum <f_hat, f>) / count, id_loss.py:33-39
         l2_scale = 2.0 * self.l2_reg_coef / numel
         grad_total = grad + l2_scale * self.delta[0]
         with torch.cuda.device(self.device):
             _lib.call('smc_sgd_step', _lib.ptr(self.delta), _lib.ptr(grad), numel, float(lr), 1.0, float(l2_scale), _lib.stream())   # :339
-        return dict(loss=clip_loss + l2, clip_loss=clip_loss, l2_loss=l2, grad=grad_total, grad_norm=grad_total.norm())
+        out = dict(loss=clip_loss + l2, clip_loss=clip_loss, l2_loss=l2, grad=grad_total, grad_norm=grad_total.norm())
+        if id_loss is not None:
+            out['identity_loss'] = id_loss
+            out['loss'] = out['loss'] + id_loss                                       # find_direction.py:193
+        return out

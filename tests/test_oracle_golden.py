@@ -120,3 +120,19 @@ def test_step_nada_golden(golden, kind):
     assert abs(o['loss'].item() - float(gn[kind + '.loss'])) <= 1e-6
     assert ((o['grad'] - T(gn[kind + '.grad'])).norm() / T(gn[kind + '.grad']).norm()).item() <= 1e-4
     assert (direction.nada_preprocess(o['original_img'])[:1] - T(gn['preprocessed'])).abs().max().item() <= 1e-5
+
+
+def test_idloss_golden(golden):
+    """oracle.idloss (IR-SE50 + IDLoss restatement) against the reference's real id_loss.IDLoss / model_irse.Backbone outputs
+    (tests/golden/idloss.npz): features, loss, image gradient at 256 px, and the loss at 512 px (exercises the pool to 256)."""
+    from oracle import idloss
+    g = golden('idloss')
+    p = idloss.random_irse50_params(seed=0)
+    y, y_hat = T(g['y']), T(g['y_hat']).requires_grad_(True)
+    with torch.no_grad():
+        assert (idloss.extract_feats(p, y) - T(g['feats_y'])).abs().max().item() <= 1e-6
+        assert (idloss.face_crop(y)[:1] - T(g['crop112'])).abs().max().item() <= 1e-6
+    loss = idloss.id_loss(p, y_hat, y)
+    grad, = torch.autograd.grad(loss, y_hat)
+    assert abs(loss.item() - float(g['loss'])) <= 1e-6
+    assert ((grad - T(g['grad'])).norm() / T(g['grad']).norm()).item() <= 1e-4
