@@ -172,7 +172,7 @@ class IRSE50:
             r = fma.fma(U['conv2'](r), *U['bn1'])
             inv_hw = torch.full([], 1.0 / (r.shape[2] * r.shape[3]), dtype=torch.float32, device=self.device)
             s = fma.fma(fma._FmaReduce.apply(r, None, torch.Size([r.shape[0], r.shape[1], 1, 1])), inv_hw, self.zero)   # SEModule: global mean
-            s = bias_act.bias_act(U['fc1'](s), act='relu')
+            s = bias_act.bias_act(U['fc1'](s), act='relu', gain=1)                      # torch.nn.ReLU: bias_act's relu defaults to gain sqrt(2)
             s = bias_act.bias_act(U['fc2'](s), act='sigmoid')
             x = fma.fma(r, s, shortcut)                                                           # gate and residual add in one kernel (strided shortcut read)
         x = fma.fma(x, *self.bn_out)
