@@ -33,18 +33,20 @@ class _FrozenConv:
         self.cout, self.cin, self.k = w.shape[0], w.shape[1], w.shape[2]
         self.stride = stride
         self.cin_p, self.cout_p = -(-self.cin // 32) * 32, -(-self.cout // 32) * 32
-        self.B_fwd, self.B_bwd, _, _ = gemm.prepare_weights(w, two=True, fwd=True, bwd=True, pad_to=32)
+        # the planes carry a power-of-two prescale (max |w| -> [128, 256), undone by acc_scale): He-scaled weights of 0.006 .. 0.06 would put
+        # the lo plane into the fp16 subnormals (absolute error 3e-8 = 5e-6 of a weight of the final Linear)
+        self.B_fwd, self.B_bwd, _, self.inv = gemm.prepare_weights(w, two=True, fwd=True, bwd=True, pad_to=32, prescale=True)
 
     def __call__(self, x):
         return _ConvFn.apply(x, self)
 
 
-def _igemm_nchw(x, B, n_out_p, n_out, taps, acc_chunk_k):
+def _igemm_nchw(x, B, n_out_p, n_out, taps, acc_chunk_k, acc_scale):
     """NCHW fp32 -> NCHW fp32 through one split-precision implicit GEMM (A planes packed NHWC, output unpacked)."""
     n, c, h, w = x.shape
     A = _pack(x, 2)
     y = torch.empty([n, h, w, n_out_p], dtype=torch.float32, device=x.device)
-    gemm.igemm(A, B, n, h, w, n_out_p, taps, precision='x3', acc_chunk_k=acc_chunk_k, out_f32=y)
+    gemm.igemm(A, B, n, h, w, n_out_p, taps, precision='x3', acc_chunk_k=acc_chunk_k, out_f32=y, acc_scale=acc_scale)
     return _unpack(y, n_out, torch.float32)
 
 
@@ -61,7 +63,7 @@ class _ConvFn(torch.autograd.Function):
         x = x.float()
         if L.stride == 2 and L.k == 1:
             x = x[:, :, ::2, ::2]                                   # a strided 1x1 conv reads the even pixels only
-        y = _igemm_nchw(x.contiguous(), L.B_fwd, L.cout_p, L.cout, TAPS[L.k], ACC_K_FWD)
+        y = _igemm_nchw(x.contiguous(), L.B_fwd, L.cout_p, L.cout, TAPS[L.k], ACC_K_FWD, L.inv)
         if L.stride == 2 and L.k == 3:
             y = y[:, :, ::2, ::2].contiguous()                      # padding 1, stride 2: the even positions of the stride-1 result
         return y
@@ -75,7 +77,7 @@ class _ConvFn(torch.autograd.Function):
             full = torch.zeros([gy.shape[0], gy.shape[1], h, w], dtype=torch.float32, device=gy.device)
             full[:, :, ::2, ::2] = gy
             gy = full
-        gx = _igemm_nchw(gy.contiguous(), L.B_bwd, L.cin_p, L.cin, TAPS_DGRAD[L.k], ACC_K_BWD)
+        gx = _igemm_nchw(gy.contiguous(), L.B_bwd, L.cin_p, L.cin, TAPS_DGRAD[L.k], ACC_K_BWD, L.inv)
         if L.stride == 2 and L.k == 1:
             full = torch.zeros([gx.shape[0], gx.shape[1], h, w], dtype=torch.float32, device=gx.device)
             full[:, :, ::2, ::2] = gx
