@@ -170,11 +170,15 @@ struct HcTile {
 struct HcWalk {
   int sup, prob;
 };
-// a CTA pair walks the list together: cluster id and cluster count take the place of block id and grid size
-__device__ __forceinline__ HcWalk hc_walk_begin(const HcParams& p) { return HcWalk{(int)(p.pair ? blockIdx.x >> 1 : blockIdx.x), 0}; }
+// a CTA pair walks the list together: cluster id and cluster count take the place of block id and grid size (compile-time switch: the
+// walk runs on the MMA issue path between two tiles)
+template <bool PAIR>
+__device__ __forceinline__ HcWalk hc_walk_begin() { return HcWalk{(int)(PAIR ? blockIdx.x >> 1 : blockIdx.x), 0}; }
+template <bool PAIR>
 __device__ __forceinline__ void hc_walk_next(const HcParams& p, HcWalk& w) {
-  if (++w.prob == p.nprob) { w.prob = 0; w.sup += (int)(p.pair ? gridDim.x >> 1 : gridDim.x); }
+  if (++w.prob == p.nprob) { w.prob = 0; w.sup += (int)(PAIR ? gridDim.x >> 1 : gridDim.x); }
 }
+template <bool PAIR>
 __device__ __forceinline__ HcTile hc_tile(const HcParams& p, const HcWalk& w) {
   HcTile r;
   int t = w.sup;
@@ -187,7 +191,7 @@ __device__ __forceinline__ HcTile hc_tile(const HcParams& p, const HcWalk& w) {
   t = q;
   q = hc_div(t, p.div_ct);
   const int ct = t - q * p.col_tiles;
-  r.n = p.pair ? 2 * q + (int)(blockIdx.x & 1u) : q;     // pair: the even CTA takes image 2q, the odd one 2q + 1 (same tile geometry)
+  r.n = PAIR ? 2 * q + (int)(blockIdx.x & 1u) : q;       // pair: the even CTA takes image 2q, the odd one 2q + 1 (same tile geometry)
   r.w0 = ct * p.Wt;
   r.q0 = ti * HC_MT;
   r.hfirst = hc_div(r.q0, p.div_wp);
@@ -462,9 +466,9 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     if (elect_one()) {
       uint32_t eph = 0;                 // bit b: number of loads into buffer b so far, mod 2
       uint32_t step = 0;
-      for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk)) {
+      for (HcWalk wk = hc_walk_begin<PAIR>(); wk.sup < p.super_tiles; hc_walk_next<PAIR>(p, wk)) {
         if (p.a_share && wk.prob > 0) continue;            // same position tile as problem 0: its buffers are reused
-        const HcTile tl = hc_tile(p, wk);
+        const HcTile tl = hc_tile<PAIR>(p, wk);
         const int wbox = tl.w0 - p.padL, hbox = tl.hfirst - p.padT;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int g = 0; g < p.ngroups; ++g, ++step) {
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       uint32_t bs = 0, bph = 0;
       const uint32_t nb = (uint32_t)p.nb;
       // resident weights: the stages of ALL problems are loaded once, problem-major (slot = HcProb::stage_base + running index)
-      for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk)) {
+      for (HcWalk wk = hc_walk_begin<PAIR>(); wk.sup < p.super_tiles; hc_walk_next<PAIR>(p, wk)) {
         if (p.b_resident && wk.sup != (int)blockIdx.x) break;   // (never combined with pair launches)       // resident: one pass over the problems (n_tiles_n == 1)
         const int nt = wk.sup - hc_div(wk.sup, p.div_ntn) * p.n_tiles_n;
         const HcProb& pr = p.probs[wk.prob];
@@ -533,8 +537,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const bool alo = X3 && p.a_lo_term != 0;             // the A operand has a lo plane (A_lo * B_hi is computed)
       uint32_t a_hi = 0, a_lo = 0;                         // live across the problems of a tile when the A tile is shared
       int hb = 0, lb = 0;
-      for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
-        const HcTile tl = hc_tile(p, wk);
+      for (HcWalk wk = hc_walk_begin<PAIR>(); wk.sup < p.super_tiles; hc_walk_next<PAIR>(p, wk), ++tile_ctr) {
+        const HcTile tl = hc_tile<PAIR>(p, wk);
         const HcProb& pr = p.probs[tl.prob];
         const bool a_load = !(p.a_share && tl.prob > 0);              // this tile waits for its own A buffers
         const bool a_free = !(p.a_share && tl.prob + 1 < p.nprob);    // and releases them
@@ -637,8 +641,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
     int st_n = -1, st_nt = -1;               // (image, N tile) whose parameter vectors are staged in pstage[st_buf]
     uint32_t st_buf = 0;
     float acc[CW];
-    for (HcWalk wk = hc_walk_begin(p); wk.sup < p.super_tiles; hc_walk_next(p, wk), ++tile_ctr) {
-      const HcTile tl = hc_tile(p, wk);
+    for (HcWalk wk = hc_walk_begin<PAIR>(); wk.sup < p.super_tiles; hc_walk_next<PAIR>(p, wk), ++tile_ctr) {
+      const HcTile tl = hc_tile<PAIR>(p, wk);
       const int ndrains = p.probs[tl.prob].ndrains;
       const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
       // ---- while the tensor core works on this tile: this thread's position, the lean-path decision, the per-tile parameter vectors
