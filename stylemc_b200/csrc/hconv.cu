@@ -235,15 +235,35 @@ __device__ __forceinline__ void hc_lds8(uint32_t saddr, float (&f)[8]) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(saddr + 16u));
 }
 
+// Per-channel parameter vector of the fused epilogues: staged in shared memory (N tiles of 64 channels and more, where a thread reads ~100
+// vectors per tile) or read from global memory as before (32-channel tiles: their tiles last ~5k clocks and a thread owns 16 channels, so
+// the staging pass and its barrier cost more than they save -- measured +9..17 % on the 1024-px convs).
+template <bool STAGE>
+struct HcVec;
+template <>
+struct HcVec<true> {
+  uint32_t a;                                     // shared address of this thread's first channel, 0 = absent
+  __device__ __forceinline__ bool ok() const { return a != 0u; }
+  __device__ __forceinline__ void ld8(int off, float (&f)[8]) const { hc_lds8(a + 4u * (uint32_t)off, f); }
+  __device__ __forceinline__ HcVec row(int k, uint32_t stride_bytes, int) const { return HcVec{a + (uint32_t)k * stride_bytes}; }
+};
+template <>
+struct HcVec<false> {
+  const float* p;
+  __device__ __forceinline__ bool ok() const { return p != nullptr; }
+  __device__ __forceinline__ void ld8(int off, float (&f)[8]) const { hc_ld8(p + off, f); }
+  __device__ __forceinline__ HcVec row(int k, uint32_t, int n_out) const { return HcVec{p + (long long)k * n_out}; }
+};
+
 // The modulated-conv epilogue (demodulation, noise, bias, leaky ReLU * gain, clamp all present) with the instruction count that
 // matters when a thread owns 64 channels of four output planes: vector parameter loads, one FMA for demod + noise + bias,
 // lrelu(x) * g = max(x g, x g alpha), the hi/lo splits and 32-byte stores; the ToRGB partial sums ride along.
-// rs / bs / ps / rw: SHARED-memory addresses of this thread's slice of the staged vectors (rs already multiplied by acc_scale; ps / rw
-// 0 = absent; the three rgb rows are rw_stride bytes apart).
-template <int CW>
-__device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], const smc_igemm_epilogue& e, float nz, uint32_t rs, uint32_t bs,
-                                                    uint32_t ps, uint32_t rw, uint32_t rw_stride, long long opix, float& rgb0, float& rgb1,
-                                                    float& rgb2) {
+// rs / bs / ps / rw: this thread's slice of the vectors (staged: rs already multiplied by acc_scale, rs_scale = 1; ps / rw may be absent; the
+// three rgb rows are rw_stride bytes (staged) or n_out floats (global) apart).
+template <int CW, bool STAGE>
+__device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], const smc_igemm_epilogue& e, float nz, float rs_scale, HcVec<STAGE> rs,
+                                                    HcVec<STAGE> bs, HcVec<STAGE> ps, HcVec<STAGE> rw, uint32_t rw_stride, int n_out, long long opix,
+                                                    float& rgb0, float& rgb1, float& rgb2) {
   const float g = e.gain, ga = e.gain * e.alpha, cl = e.clamp;
   static_assert(CW % 16 == 0, "16 channels (32 bytes of fp16) per step");
 #pragma unroll
@@ -252,11 +272,11 @@ __device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], cons
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float r8[8], b8[8];
-      hc_lds8(rs + 4u * (uint32_t)(c0 + 8 * hh), r8);
-      hc_lds8(bs + 4u * (uint32_t)(c0 + 8 * hh), b8);
+      rs.ld8(c0 + 8 * hh, r8);
+      bs.ld8(c0 + 8 * hh, b8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float x = fmaf(acc[c0 + 8 * hh + i], r8[i], nz + b8[i]);
+        const float x = fmaf(acc[c0 + 8 * hh + i], STAGE ? r8[i] : r8[i] * rs_scale, nz + b8[i]);
         v[8 * hh + i] = fminf(fmaxf(fmaxf(x * g, x * ga), -cl), cl);
       }
     }
@@ -267,13 +287,13 @@ __device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], cons
       hc_st32(reinterpret_cast<__half*>(e.out_raw) + opix + c0, h0, h1);
       if (e.out_raw_lo) hc_st32(reinterpret_cast<__half*>(e.out_raw_lo) + opix + c0, l0, l1);
     }
-    if (rw) {
+    if (rw.ok()) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float w0[8], w1[8], w2[8];
-        hc_lds8(rw + 4u * (uint32_t)(c0 + 8 * hh), w0);
-        hc_lds8(rw + rw_stride + 4u * (uint32_t)(c0 + 8 * hh), w1);
-        hc_lds8(rw + 2u * rw_stride + 4u * (uint32_t)(c0 + 8 * hh), w2);
+        rw.ld8(c0 + 8 * hh, w0);
+        rw.row(1, rw_stride, n_out).ld8(c0 + 8 * hh, w1);
+        rw.row(2, rw_stride, n_out).ld8(c0 + 8 * hh, w2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           rgb0 = fmaf(w0[i], v[8 * hh + i], rgb0);
@@ -283,11 +303,11 @@ __device__ __forceinline__ void hc_epilogue_modconv(const float (&acc)[CW], cons
       }
     }
     if (e.out_hi) {
-      if (ps) {
+      if (ps.ok()) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float p8[8];
-          hc_lds8(ps + 4u * (uint32_t)(c0 + 8 * hh), p8);
+          ps.ld8(c0 + 8 * hh, p8);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[8 * hh + i] *= p8[i];
         }
@@ -319,9 +339,9 @@ __device__ __forceinline__ void hc_h8_to_f(const uint4& u, float* f) {
 // of the consumer conv; multiplied by post = (consumer style) * (demodulation of the layer below) it becomes the gradient w.r.t. that
 // layer's pre-activation once the leaky-ReLU slope and the clamp mask of the SAVED output y are applied (bias_act.cu:71-72,136-142).
 // The optional ToRGB branch adds sum_j rw[j][c] * g_j (g = masked dL/drgb of this pixel) before the slope.
-template <int CW>
-__device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const smc_igemm_epilogue& e, float acc_scale, uint32_t ps, uint32_t rw,
-                                                   uint32_t rw_stride, long long opix, float g0, float g1, float g2) {
+template <int CW, bool STAGE>
+__device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const smc_igemm_epilogue& e, float acc_scale, HcVec<STAGE> ps, HcVec<STAGE> rw,
+                                                   uint32_t rw_stride, int n_out, long long opix, float g0, float g1, float g2) {
   const float g = e.gain, ga = e.gain * e.alpha, cl = e.clamp;
   const __half* yh = reinterpret_cast<const __half*>(e.mask_y) + opix;
   const __half* yl = e.mask_y_lo ? reinterpret_cast<const __half*>(e.mask_y_lo) + opix : nullptr;
@@ -343,14 +363,14 @@ __device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float p8[8];
-      hc_lds8(ps + 4u * (uint32_t)(c0 + 8 * hh), p8);
+      ps.ld8(c0 + 8 * hh, p8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[8 * hh + i] = acc[c0 + 8 * hh + i] * (p8[i] * acc_scale);
-      if (rw) {
+      if (rw.ok()) {
         float w0[8], w1[8], w2[8];
-        hc_lds8(rw + 4u * (uint32_t)(c0 + 8 * hh), w0);
-        hc_lds8(rw + rw_stride + 4u * (uint32_t)(c0 + 8 * hh), w1);
-        hc_lds8(rw + 2u * rw_stride + 4u * (uint32_t)(c0 + 8 * hh), w2);
+        rw.ld8(c0 + 8 * hh, w0);
+        rw.row(1, rw_stride, n_out).ld8(c0 + 8 * hh, w1);
+        rw.row(2, rw_stride, n_out).ld8(c0 + 8 * hh, w2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[8 * hh + i] += w0[i] * g0 + w1[i] * g1 + w2[i] * g2;
       }
@@ -392,6 +412,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
   constexpr int SETCOLS = (TWO_PASS ? 2 : 1) * HC_MB * BLK;
   constexpr int SETS = (2 * SETCOLS <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (SETS * SETCOLS) < 32 ? 32 : (SETS * SETCOLS);
+  constexpr bool STAGE = BN >= 64;                             // epilogue parameter vectors staged in shared memory (HcVec)
   constexpr uint32_t MMA_M = PAIR ? 256 : 128;                 // cta_group::2: 128 rows from each CTA of the pair
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
   constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
@@ -645,59 +666,63 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const HcTile tl = hc_tile<PAIR>(p, wk);
       const int ndrains = p.probs[tl.prob].ndrains;
       const uint32_t set_t = (TWO_PASS && SETS == 2) ? (tile_ctr & 1u) : 0u;
-      // ---- while the tensor core works on this tile: this thread's position, the lean-path decision, the per-tile parameter vectors
-      // into shared memory (one coalesced pass of the 512 epilogue threads instead of ~100 global loads per thread after the drain),
-      // the per-pixel operands (noise, ToRGB gradient) and an L2 prefetch of the saved activation the fused activation backward reads
-      const int qpos = tl.q0 + m;
-      const int h = hc_div(qpos, p.div_wp), wr = qpos - h * p.Wp;
-      const int w = tl.w0 + wr;
-      const bool valid = (wr < p.Wt) && (w < p.W) && (h < p.H);
-      const int o0 = tl.nt * BN + ch * CW;
-      const long long opix = e.o_off + p.probs[tl.prob].o_off + (long long)tl.n * e.o_sn + (long long)h * e.o_sh + (long long)w * e.o_sw + o0;
-      const bool out32 = ((((uintptr_t)e.out_raw | (uintptr_t)e.out_raw_lo | (uintptr_t)e.out_hi | (uintptr_t)e.out_lo) & 31) == 0) &&
-                         ((((e.o_sn | e.o_sh | e.o_sw | e.o_off) * 2) & 31) == 0) && (p.n_out % 16 == 0);
-      // modulated-conv layers (the bulk of the epilogue work): lean path; alpha < 1 makes max(x, alpha x) the leaky ReLU
-      const bool modconv = e.row_scale && e.bias && e.act == 1 && e.clamp >= 0.f && e.alpha >= 0.f && e.alpha <= 1.f && e.gain > 0.f && !e.residual &&
-                           !e.out_f32 && !e.mask_y && out32;
-      const bool staged = modconv || e.mask_y != nullptr;
-      // the vectors depend on (image, N tile) only: consecutive tiles of a CTA mostly share them (always at 512 / 1024 px), so they are
-      // re-staged -- into the other buffer, followed by one barrier of the 16 epilogue warps -- only when that pair changes; every
-      // epilogue warp walks the same tile list, so all of them take this branch together
-      if (staged && (tl.n != st_n || tl.nt != st_nt)) {
-        st_n = tl.n; st_nt = tl.nt; st_buf ^= 1u;
-        float* pst = pstage + st_buf * (uint32_t)(HC_PSTAGE_VECS * BN);
-        const int et = (int)threadIdx.x - 96;
-        const long long nb_off = (long long)tl.n * p.n_out + tl.nt * BN;
-        for (int i = et; i < HC_PSTAGE_VECS * BN; i += HC_EPI_THREADS) {
-          const int which = i / BN, c = i - which * BN;
-          float v = 0.f;
-          if (which == 0) { if (e.row_scale) v = __ldg(e.row_scale + nb_off + c) * acc_scale; }
-          else if (which == 1) { if (e.bias) v = __ldg(e.bias + tl.nt * BN + c); }
-          else if (which == 2) { if (e.post_scale) v = __ldg(e.post_scale + nb_off + c); }
-          else if (e.rgb_w) v = __ldg(e.rgb_w + ((long long)tl.n * 3 + (which - 3)) * p.n_out + tl.nt * BN + c);
-          pst[i] = v;
-        }
-        // all 16 warps have left the tiles that used the buffer being replaced next time, and this buffer is visible to all of them
-        asm volatile("bar.sync 1, %0;" ::"n"(HC_EPI_THREADS) : "memory");
-      }
+      // ---- this thread's position, the lean-path decision and the per-pixel operands.  STAGE (N tiles of 64+ channels): all of it runs
+      // here, while the tensor core works on the tile, together with the staging of the per-tile parameter vectors in shared memory (one
+      // coalesced pass of the 512 epilogue threads instead of ~100 global loads per thread after the drain) and an L2 prefetch of the saved
+      // activation the fused activation backward reads.  32-channel tiles (short, 16 channels per thread) keep the lean order: after the drain.
+      int h = 0, w = 0, o0 = 0;
+      bool valid = false, modconv = false;
+      long long opix = 0;
       float nz = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      if (valid) {
-        if (e.noise != nullptr) nz = __ldg(e.noise + (long long)h * e.noise_sh + (long long)w * e.noise_sw);
-        if (e.mask_y) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y) + opix));
-          if (CW > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y) + opix + 64));
-          if (e.mask_y_lo) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y_lo) + opix));
-            if (CW > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y_lo) + opix + 64));
-          }
-          if (e.mask_grgb) {
+      auto locate = [&]() {
+        const int qpos = tl.q0 + m;
+        h = hc_div(qpos, p.div_wp);
+        const int wr = qpos - h * p.Wp;
+        w = tl.w0 + wr;
+        valid = (wr < p.Wt) && (w < p.W) && (h < p.H);
+        o0 = tl.nt * BN + ch * CW;
+        opix = e.o_off + p.probs[tl.prob].o_off + (long long)tl.n * e.o_sn + (long long)h * e.o_sh + (long long)w * e.o_sw + o0;
+        const bool out32 = ((((uintptr_t)e.out_raw | (uintptr_t)e.out_raw_lo | (uintptr_t)e.out_hi | (uintptr_t)e.out_lo) & 31) == 0) &&
+                           ((((e.o_sn | e.o_sh | e.o_sw | e.o_off) * 2) & 31) == 0) && (p.n_out % 16 == 0);
+        // modulated-conv layers (the bulk of the epilogue work): lean path; alpha < 1 makes max(x, alpha x) the leaky ReLU
+        modconv = e.row_scale && e.bias && e.act == 1 && e.clamp >= 0.f && e.alpha >= 0.f && e.alpha <= 1.f && e.gain > 0.f && !e.residual &&
+                  !e.out_f32 && !e.mask_y && out32 &&
+                  (STAGE || (((uintptr_t)e.row_scale | (uintptr_t)e.bias | (uintptr_t)e.post_scale | (uintptr_t)e.rgb_w) & 15) == 0);
+        if (valid) {
+          if (e.noise != nullptr) nz = __ldg(e.noise + (long long)h * e.noise_sh + (long long)w * e.noise_sw);
+          if (e.mask_y && e.mask_grgb) {
             const float* gp = e.mask_grgb + (long long)tl.n * e.rgb_sn + (long long)h * e.rgb_sh + w;
             g0 = __ldg(gp); g1 = __ldg(gp + e.rgb_sj); g2 = __ldg(gp + 2 * e.rgb_sj);
           }
         }
+      };
+      if (STAGE) {
+        locate();
+        // the vectors depend on (image, N tile) only: consecutive tiles of a CTA mostly share them (always at 512 / 1024 px), so they are
+        // re-staged -- into the other buffer, followed by one barrier of the 16 epilogue warps -- only when that pair changes; every
+        // epilogue warp walks the same tile list, so all of them take this branch together
+        if ((modconv || e.mask_y != nullptr) && (tl.n != st_n || tl.nt != st_nt)) {
+          st_n = tl.n; st_nt = tl.nt; st_buf ^= 1u;
+          float* pst = pstage + st_buf * (uint32_t)(HC_PSTAGE_VECS * BN);
+          const int et = (int)threadIdx.x - 96;
+          const long long nb_off = (long long)tl.n * p.n_out + tl.nt * BN;
+          for (int i = et; i < HC_PSTAGE_VECS * BN; i += HC_EPI_THREADS) {
+            const int which = i / BN, c = i - which * BN;
+            float v = 0.f;
+            if (which == 0) { if (e.row_scale) v = __ldg(e.row_scale + nb_off + c) * acc_scale; }
+            else if (which == 1) { if (e.bias) v = __ldg(e.bias + tl.nt * BN + c); }
+            else if (which == 2) { if (e.post_scale) v = __ldg(e.post_scale + nb_off + c); }
+            else if (e.rgb_w) v = __ldg(e.rgb_w + ((long long)tl.n * 3 + (which - 3)) * p.n_out + tl.nt * BN + c);
+            pst[i] = v;
+          }
+          // all 16 warps have left the tiles that used the buffer being replaced next time, and this buffer is visible to all of them
+          asm volatile("bar.sync 1, %0;" ::"n"(HC_EPI_THREADS) : "memory");
+        }
+        if (valid && e.mask_y) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y) + opix));
+          if (e.mask_y_lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __half*>(e.mask_y_lo) + opix));
+        }
       }
-      const uint32_t pst_s = smem_u32(pstage + st_buf * (uint32_t)(HC_PSTAGE_VECS * BN)) + 4u * (uint32_t)(ch * CW);
-      constexpr uint32_t VEC = 4u * (uint32_t)BN;                    // bytes between two staged vectors
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
       for (int dch = 0; dch < ndrains + (TWO_PASS ? 1 : 0); ++dch) {
@@ -730,20 +755,34 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(drained); else mbar_arrive(drained); }
       }
-      // ---- fused epilogue + stores for this thread's position (everything that does not need the accumulators was set up above)
+      // ---- fused epilogue + stores for this thread's position
+      if (!STAGE) locate();
       if (valid) {
         const int n = tl.n;
-        const float* rs = e.row_scale ? e.row_scale + (long long)n * p.n_out + o0 : nullptr;      // generic path only (global)
+        const float* rs = e.row_scale ? e.row_scale + (long long)n * p.n_out + o0 : nullptr;
         const float* ps = e.post_scale ? e.post_scale + (long long)n * p.n_out + o0 : nullptr;
         const float* bs = e.bias ? e.bias + o0 : nullptr;
         const float* rw = e.rgb_acc ? e.rgb_w + (long long)n * 3 * p.n_out + o0 : nullptr;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
         const bool f32_aligned32 = (((uintptr_t)e.out_f32) & 31) == 0;     // element offsets are multiples of 8 floats (checked on the host)
+        constexpr uint32_t VEC = 4u * (uint32_t)BN;                        // bytes between two staged vectors
+        const uint32_t pst_s = STAGE ? smem_u32(pstage + st_buf * (uint32_t)(HC_PSTAGE_VECS * BN)) + 4u * (uint32_t)(ch * CW) : 0u;
         if (e.mask_y) {
-          hc_epilogue_actbwd<CW>(acc, e, acc_scale, pst_s + 2u * VEC, e.mask_grgb ? pst_s + 3u * VEC : 0u, VEC, opix, g0, g1, g2);
+          if constexpr (STAGE) {
+            hc_epilogue_actbwd<CW, true>(acc, e, acc_scale, HcVec<true>{pst_s + 2u * VEC}, HcVec<true>{e.mask_grgb ? pst_s + 3u * VEC : 0u}, VEC,
+                                         p.n_out, opix, g0, g1, g2);
+          } else {
+            hc_epilogue_actbwd<CW, false>(acc, e, acc_scale, HcVec<false>{ps},
+                                          HcVec<false>{e.mask_grgb ? e.rgb_w + (long long)n * 3 * p.n_out + o0 : nullptr}, 0u, p.n_out, opix, g0, g1, g2);
+          }
         } else if (modconv) {
-          hc_epilogue_modconv<CW>(acc, e, nz, pst_s, pst_s + VEC, e.post_scale ? pst_s + 2u * VEC : 0u, e.rgb_acc ? pst_s + 3u * VEC : 0u, VEC, opix,
-                                  rgb0, rgb1, rgb2);
+          if constexpr (STAGE) {
+            hc_epilogue_modconv<CW, true>(acc, e, nz, 1.f, HcVec<true>{pst_s}, HcVec<true>{pst_s + VEC}, HcVec<true>{e.post_scale ? pst_s + 2u * VEC : 0u},
+                                          HcVec<true>{e.rgb_acc ? pst_s + 3u * VEC : 0u}, VEC, p.n_out, opix, rgb0, rgb1, rgb2);
+          } else {
+            hc_epilogue_modconv<CW, false>(acc, e, nz, acc_scale, HcVec<false>{rs}, HcVec<false>{bs}, HcVec<false>{ps}, HcVec<false>{rw}, 0u, p.n_out, opix,
+                                           rgb0, rgb1, rgb2);
+          }
         } else {
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 8) {
