@@ -395,7 +395,9 @@ __device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const
 // N = BN into the cross columns: 2 MMAs per tap and k-step instead of 3.  Both halves are drained per chunk (the first MMA of a
 // chunk overwrites all 2 BN columns); two sets alternate per chunk.
 enum { HC_X1 = 0, HC_X3_TWO_PASS = 1, HC_X3_MERGED = 2 };
-template <int BN, int KC, int MODE, bool PAIR = false>
+// ALO: the A operand has a lo plane (three-term split); false = two-term split (hi plane only).  A template parameter, not a field of
+// HcParams: the flag sits inside the MMA issue loop, and a run-time branch there cost the 32-channel layers 10-15 %.
+template <int BN, int KC, int MODE, bool PAIR = false, bool ALO = true>
 __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB,
                                                               const __grid_constant__ HcParams p) {
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             if (leader) mbar_expect_tx(&a_full[hb], (PAIR ? 2u : 1u) * p.a_box_bytes);
             if (PAIR) tma_load_4d_2sm(a_buf + (size_t)hb * p.a_buf_bytes, &mapA, &a_full[hb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_hi);
             else tma_load_4d(a_buf + (size_t)hb * p.a_buf_bytes, &mapA, &a_full[hb], kc * KC, wbox, hbox, tl.n + p.groups[g].dn_hi);
-            if (X3 && p.a_lo_term) {
+            if (X3 && ALO) {
               const int lb = lo_buf(step);
               mbar_wait(&a_empty[lb], ((eph >> lb) & 1u) ^ 1u);
               eph ^= 1u << lb;
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
       const uint32_t nb = (uint32_t)p.nb;
       const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
       const bool resident = p.b_resident != 0;
-      const bool alo = X3 && p.a_lo_term != 0;             // the A operand has a lo plane (A_lo * B_hi is computed)
+      constexpr bool alo = X3 && ALO;                      // the A operand has a lo plane (A_lo * B_hi is computed)
       uint32_t a_hi = 0, a_lo = 0;                         // live across the problems of a tile when the A tile is shared
       int hb = 0, lb = 0;
       for (HcWalk wk = hc_walk_begin<PAIR>(); wk.sup < p.super_tiles; hc_walk_next<PAIR>(p, wk), ++tile_ctr) {
@@ -896,19 +898,29 @@ void hconv_config(int key, int value) {
   if (key == 7) g_hconv_pair = value;
 }
 
-template <int BN, int KC, int MODE>
-static int hc_launch(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
+template <int BN, int KC, int MODE, bool ALO>
+static int hc_launch_a(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
   static SmemOptIn opt_in;
-  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE>, smem); e != cudaSuccess) return (int)e;
-  hconv_kernel<BN, KC, MODE><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
+  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE, false, ALO>, smem); e != cudaSuccess) return (int)e;
+  hconv_kernel<BN, KC, MODE, false, ALO><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
-// CTA-pair launch: clusters of two CTAs (the two SMs of a TPC), grid = 2 x clusters
 template <int BN, int KC, int MODE>
+static int hc_launch(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
+  if constexpr (MODE != HC_X1) {
+    if (!p.a_lo_term) return hc_launch_a<BN, KC, MODE, false>(ma, mb, p, grid, smem, st);
+  }
+  return hc_launch_a<BN, KC, MODE, true>(ma, mb, p, grid, smem, st);
+}
+// CTA-pair launch: clusters of two CTAs (the two SMs of a TPC), grid = 2 x clusters
+template <int BN, int KC, int MODE, bool ALO = true>
 static int hc_launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
+  if constexpr (MODE != HC_X1 && ALO) {
+    if (!p.a_lo_term) return hc_launch_pair<BN, KC, MODE, false>(ma, mb, p, grid, smem, st);
+  }
   static SmemOptIn opt_in;
-  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE, true>, smem); e != cudaSuccess) return (int)e;
+  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE, true, ALO>, smem); e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
   cfg.blockDim = dim3(HC_THREADS, 1, 1);
@@ -919,7 +931,7 @@ static int hc_launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const Hc
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, hconv_kernel<BN, KC, MODE, true>, ma, mb, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hconv_kernel<BN, KC, MODE, true, ALO>, ma, mb, p);
   if (e != cudaSuccess) return (int)e;
   SMC_LAUNCH_CHECK();
   return SMC_OK;
