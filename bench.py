@@ -137,7 +137,8 @@ def hooked_step(fn):
         e = d.epi
         out_b = (4 if e.out_f32 else 0) + sum(2 for q in (e.out_hi, e.out_lo, e.out_raw, e.out_raw_lo) if q)
         nbytes = float(d.n_img) * d.H * d.W * (2 * planes_a * d.C + out_b * d.n_out * max(1, d.nprob))   # algorithmic HBM bytes: A once, outputs once
-        records.append((e0, e1, 2.0 * d.n_img * d.H * d.W * d.n_out * d.C * alg_taps, (d.n_img, d.H, d.W, d.C, d.n_out, alg_taps), nbytes))
+        terms = max(1, d.ntaps // max(1, alg_taps))            # fp16 MMAs per algorithmic product: 3 (hi/lo split), 2 (hi-only A operand), 1
+        records.append((e0, e1, 2.0 * d.n_img * d.H * d.W * d.n_out * d.C * alg_taps, (d.n_img, d.H, d.W, d.C, d.n_out, alg_taps), nbytes, terms))
 
     _lib.igemm_hook = hook
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -153,18 +154,20 @@ def hooked_step(fn):
 
 
 def summarize_records(records):
-    """(summed ms, summed FLOPs, key of the shape with the largest summed time, [ms, flops, launches, bytes] of that shape)."""
+    """(summed ms, summed FLOPs, key of the shape with the largest summed time, [ms, flops, launches, bytes, MMA flops] of that shape,
+    summed MMA flops).  MMA flops = algorithmic flops x the fp16 MMAs issued per product in that launch."""
     ig_ms = sum(r[0].elapsed_time(r[1]) for r in records)
     ig_flops = sum(r[2] for r in records)
+    ig_mma = sum(r[2] * r[5] for r in records)
     shapes = {}
-    for e0, e1, fl, key, nb in records:
-        t = shapes.setdefault(key, [0.0, 0.0, 0, 0.0])
-        t[0] += e0.elapsed_time(e1); t[1] += fl; t[2] += 1; t[3] += nb
+    for e0, e1, fl, key, nb, terms in records:
+        t = shapes.setdefault(key, [0.0, 0.0, 0, 0.0, 0.0])
+        t[0] += e0.elapsed_time(e1); t[1] += fl; t[2] += 1; t[3] += nb; t[4] += fl * terms
     top_key, top = max(shapes.items(), key=lambda kv: kv[1][0])
-    return ig_ms, ig_flops, top_key, top
+    return ig_ms, ig_flops, top_key, top, ig_mma
 
 
-def top_kernel_roofline(pk, top_key, top, step_ms, mma_per_product):
+def top_kernel_roofline(pk, top_key, top, step_ms):
     """roofline object of the heaviest smc_igemm shape: SURVEY.md 8d's max(flops / peak_flops, bytes / peak_bw) of the ALGORITHMIC work."""
     top_tf = top[1] / (top[0] / 1e3) / 1e12
     top_gbs = top[3] / (top[0] / 1e3) / 1e9
@@ -181,9 +184,9 @@ def top_kernel_roofline(pk, top_key, top, step_ms, mma_per_product):
             'algorithmic_gbyte_per_launch': round(top[3] / top[2] / 1e9, 2),
             'launches_per_step': top[2], 'avg_launch_ms': round(top[0] / top[2], 4),
             'algorithmic_gflop_per_launch': round(top[1] / top[2] / 1e9, 2),
-            'mma_per_product': mma_per_product,
-            'tensor_pipe_achieved': round(mma_per_product * top_tf, 2),
-            'tensor_pipe_frac': round(mma_per_product * top_tf / pk['tflops'], 4),
+            'mma_per_product': round(top[4] / top[1], 2),                 # mean over the shape's launches: 3 forward (hi/lo split), 2 backward
+            'tensor_pipe_achieved': round(top[4] / (top[0] / 1e3) / 1e12, 2),
+            'tensor_pipe_frac': round(top[4] / (top[0] / 1e3) / 1e12 / pk['tflops'], 4),
             'traffic': TOP_KERNEL_DRAM_BYTES.get(top_key), 'traffic_source': TRAFFIC_SOURCE if top_key in TOP_KERNEL_DRAM_BYTES else None,
             'peak_source': pk['src'], 'share_of_step': round(top[0] / step_ms, 3)}
 
@@ -279,7 +282,7 @@ def run_ours(a):
     overlap, finder.overlap = finder.overlap, False       # per-launch timing: keep the two image branches on one stream for this step
     records, step_ms_hooked = hooked_step(lambda: step_resident(0))
     finder.overlap = overlap
-    ig_ms, ig_flops, top_key, top = summarize_records(records)
+    ig_ms, ig_flops, top_key, top, ig_mma = summarize_records(records)
 
     if rank != 0:
         return
@@ -293,21 +296,21 @@ def run_ours(a):
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
     achieved = ig_flops / (ig_ms / 1e3) / 1e12
-    mma_per_product = 1 if a.precision == 'x1' else 3
     # every layer is reported against max(flops / peak_flops, bytes / peak_bw) of its ALGORITHMIC work; the 32/64-channel convs
     # sit below the ridge (b1024.conv1: ~100-144 FLOP/B against ~216 FLOP/B): their bound is HBM.  tensor_pipe_frac is the same launch
     # seen from the tensor pipe, which executes mma_per_product fp16 MMAs per algorithmic product in split precision.
-    roof = top_kernel_roofline(pk, top_key, top, step_ms_hooked, mma_per_product)
+    roof = top_kernel_roofline(pk, top_key, top, step_ms_hooked)
     roof.update({'family': {'kernel': 'every smc_igemm launch of one step (hconv_kernel + igemm_kernel: convs, dgrads, CLIP linears)',
                             'achieved': round(achieved, 2), 'frac': round(achieved / pk['tflops'], 4),
-                            'tensor_pipe_frac': round(mma_per_product * achieved / pk['tflops'], 4),
+                            'mma_per_product': round(ig_mma / ig_flops, 2),
+                            'tensor_pipe_frac': round(ig_mma / (ig_ms / 1e3) / 1e12 / pk['tflops'], 4),
                             'launches_per_step': len(records), 'share_of_step': round(ig_ms / step_ms_hooked, 3)},
                  'algorithmic_gflop_per_image': round(alg_flops_img / 1e9, 1),
                  'step_algorithmic_tflops': round(alg_flops_img * global_n / world / (ms / a.steps / 1e3) / 1e12, 2)})
     out = {
         'metric': METRIC, 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': round(ms / a.steps, 3), 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
-        'dtype': 'f16x3 operands (hi+lo split), f32 accumulate' if a.precision != 'x1' else 'f16 operands, f32 accumulate',
+        'dtype': 'f16 hi+lo split operands (3 MMAs per product forward, 2 backward), f32 accumulate' if a.precision != 'x1' else 'f16 operands, f32 accumulate',
         'data': 'synthetic (random-init StyleGAN2 config-f + random-init CLIP ViT-B/32, S from randn W)',
         'config': {'workload': (f'find_direction {a.resolution}px, {global_n} seeds per step sharded over {world} GPU(s) (BASELINE configs[2] when 256px / 129), '
                                 f'fwd+bwd to delta-S [1,8,512]') if strong else
@@ -465,12 +468,11 @@ def run_generate(a):
     ms_e2e = timed(step_e2e)
     clocks = sampler.stop()
     records, step_ms = hooked_step(lambda: render(styles_dev))
-    ig_ms, ig_flops, top_key, top = summarize_records(records)
+    ig_ms, ig_flops, top_key, top, ig_mma = summarize_records(records)
     pk = peaks()
-    mma = 1 if a.precision == 'x1' else 3
-    roof = top_kernel_roofline(pk, top_key, top, step_ms, mma)
+    roof = top_kernel_roofline(pk, top_key, top, step_ms)
     roof['family'] = {'kernel': 'every smc_igemm launch of one step', 'achieved': round(ig_flops / (ig_ms / 1e3) / 1e12, 2),
-                      'tensor_pipe_frac': round(mma * ig_flops / (ig_ms / 1e3) / 1e12 / pk['tflops'], 4), 'launches_per_step': len(records),
+                      'tensor_pipe_frac': round(ig_mma / (ig_ms / 1e3) / 1e12 / pk['tflops'], 4), 'launches_per_step': len(records),
                       'share_of_step': round(ig_ms / step_ms, 3)}
     imgs = 2 * batch * a.steps
     print(json.dumps({'metric': 'generate_fromS forward-only synthesis images/sec @1024px', 'value': round(imgs / (ms / 1e3), 2),
