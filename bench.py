@@ -52,6 +52,8 @@ def parse():
     ap.add_argument('--gpu-library-baseline', action='store_true',
                     help="also time the reference's GPU formulation (oracle modules = ATen / cuDNN / cuBLAS fp32 on cuda:0, TF32 off and on) for one step; "
                          'reported as gpu_library_baseline next to cpu_baseline (BASELINE.md section 3, second bar)')
+    ap.add_argument('--cuda-graph', type=int, default=-1, help='replay the step from a CUDA graph (DirectionFinder.step_graph): 1 on, 0 off, '
+                    '-1 = on for strong-scaling runs (--global-seeds), off otherwise')
     ap.add_argument('--profile-step', action='store_true', help='run warm-up, then ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     return ap.parse_args()
 
@@ -251,16 +253,19 @@ def run_ours(a):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return ms.item()
 
+    use_graph = a.cuda_graph == 1 or (a.cuda_graph == -1 and strong)
+    do_step = finder.step_graph if use_graph else finder.step
+
     def step_resident(i):
         lr = direction.cosine_lr(finder.lr, i + 1, total_steps)
-        finder.step(styles_dev[(i % 2) * local_n:(i % 2 + 1) * local_n], lr=lr, global_count=global_n)
+        do_step(styles_dev[(i % 2) * local_n:(i % 2 + 1) * local_n], lr=lr, global_count=global_n)
 
     losses = []
 
     def step_e2e(i):
         lr = direction.cosine_lr(finder.lr, i + 1, total_steps)
         s = styles_host[(i % 2) * local_n:(i % 2 + 1) * local_n].to(dev, non_blocking=True)      # H2D from pinned memory
-        losses.append(finder.step(s, lr=lr, global_count=global_n)['loss'].item())                # D2H of the step's loss
+        losses.append(do_step(s, lr=lr, global_count=global_n)['loss'].item())                    # D2H of the step's loss
 
     for i in range(a.warmup):
         step_resident(i)
@@ -280,7 +285,7 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel family (smc_igemm): every launch of ONE extra step bracketed by CUDA events
     overlap, finder.overlap = finder.overlap, False       # per-launch timing: keep the two image branches on one stream for this step
-    records, step_ms_hooked = hooked_step(lambda: step_resident(0))
+    records, step_ms_hooked = hooked_step(lambda: finder.step(styles_dev[:local_n], lr=0.0, global_count=global_n))
     finder.overlap = overlap
     ig_ms, ig_flops, top_key, top, ig_mma = summarize_records(records)
 
@@ -317,7 +322,7 @@ def run_ours(a):
                                f'find_direction {a.resolution}px, batch {a.batch}/GPU (BASELINE configs[3]), fwd+bwd to delta-S [1,8,512]',
                    'resolution': a.resolution, 'batch_per_gpu': local_n, 'global_batch': global_n, 'micro_batch': a.micro_batch,
                    'clip_type': a.clip_type + (' (ViT-B/32 + 0.5 * ViT-B/16: NOT the headline configuration)' if a.clip_type == 'double' else ' (ViT-B/32)'),
-                   'precision': a.precision, 'learning_rate': a.lr, 'parallelism': f'dp{world} (seed shards; all-reduce of the 16 KiB gradient)',
+                   'precision': a.precision, 'learning_rate': a.lr, 'cuda_graph': bool(use_graph), 'parallelism': f'dp{world} (seed shards; all-reduce of the 16 KiB gradient)',
                    'l2_flush': 'none needed: each step streams >10 GB of activations, far larger than the 126 MB L2'},
         'clocks': clocks,
         'e2e': {'value': round(e2e, 3), 'unit': 'images/s', 'ms_per_step': round(ms_e2e / a.steps, 3),

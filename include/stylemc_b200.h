@@ -277,6 +277,9 @@ int smc_fma_reduce(const void* x, const void* y, void* out, int dtype, const int
 /* ---- optimiser -----------------------------------------------------------------------------------
  * delta -= lr * (grad * grad_scale + l2_scale * delta)   (SGD, no momentum; L2 term of find_direction.py:190-191) */
 int smc_sgd_step(float* delta, const float* grad, int64_t numel, float lr, float grad_scale, float l2_scale, void* stream);
+/* the same update with the learning rate read from DEVICE memory: the step can be captured once in a CUDA graph and replayed under the cosine
+ * schedule of find_direction.py:298-301 */
+int smc_sgd_step_dev(float* delta, const float* grad, int64_t numel, const float* lr_dev, float grad_scale, float l2_scale, void* stream);
 
 #ifdef __cplusplus
 }  /* extern "C" */

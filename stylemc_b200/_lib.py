@@ -109,6 +109,7 @@ SIGNATURES = {
     'smc_fma': 'pppp i pppp p',
     'smc_fma_reduce': 'ppp i pppp p',
     'smc_sgd_step': 'pp q fff p',
+    'smc_sgd_step_dev': 'pp q p ff p',
 }
 
 _lib = None

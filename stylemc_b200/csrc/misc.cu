@@ -4,7 +4,8 @@
 
 namespace smc {
 __global__ void sgd_step_kernel(float* __restrict__ delta, const float* __restrict__ grad, long long n, float lr, float grad_scale,
-                                float l2_scale) {
+                                float l2_scale, const float* __restrict__ lr_dev = nullptr) {
+  if (lr_dev) lr = __ldg(lr_dev);          // learning rate from device memory: a captured CUDA graph replays with this step's value
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float d = delta[i];
     delta[i] = d - lr * (grad[i] * grad_scale + l2_scale * d);
@@ -350,6 +351,15 @@ extern "C" int smc_sgd_step(float* delta, const float* grad, int64_t numel, floa
   long long blocks = smc::ceil_div_ll(numel, 256);
   if (blocks > smc::kNumSMs * 8) blocks = smc::kNumSMs * 8;
   smc::sgd_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(delta, grad, numel, lr, grad_scale, l2_scale);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_sgd_step_dev(float* delta, const float* grad, int64_t numel, const float* lr_dev, float grad_scale, float l2_scale, void* stream) {
+  if (!delta || !grad || !lr_dev || numel < 1) return SMC_EINVAL;
+  long long blocks = smc::ceil_div_ll(numel, 256);
+  if (blocks > smc::kNumSMs * 8) blocks = smc::kNumSMs * 8;
+  smc::sgd_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(delta, grad, numel, 0.f, grad_scale, l2_scale, lr_dev);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

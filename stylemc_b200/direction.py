@@ -301,6 +301,37 @@ class DirectionFinder:
         # with the identity term the partial sums travel together: [clip, identity] (one all-reduce either way)
         return grad, (torch.cat([part_sum, self._id_part]) if self._use_id() else part_sum)
 
+    def step_graph(self, styles, lr=None, global_count=None):
+        """``step`` replayed from a CUDA graph: the ~500 launches of a step (two streams, the NCCL all-reduce included) are captured once per
+        (shard size, global count) and replayed with one ``cudaGraphLaunch``; the S batch and the learning rate are copied into static
+        device buffers first.  Worth it where a step is short (BASELINE configs[2]: 17 seeds per GPU at 256 px = 25 ms, half of it launch
+        gaps); the returned tensors are the graph's static outputs, overwritten by the next replay."""
+        lr = self.lr if lr is None else lr
+        styles = styles.to(self.device, torch.float32)
+        key = (tuple(styles.shape), global_count)
+        if not hasattr(self, '_graphs'):
+            self._graphs = {}
+        if key not in self._graphs:
+            static_s, static_lr = styles.clone(), torch.zeros(1, dtype=torch.float32, device=self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                  # warm-up outside the capture (allocator, smem opt-ins, side stream); lr 0: delta unchanged
+                for _ in range(2):
+                    self.step(static_s, lr=static_lr, global_count=global_count)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count
+            with torch.cuda.graph(graph):
+                out = self.step(static_s, lr=static_lr, global_count=global_count)
+            self._graphs[key] = (graph, static_s, static_lr, out, _lib.launch_count - n0)
+        graph, static_s, static_lr, out, launches = self._graphs[key]
+        static_s.copy_(styles, non_blocking=True)
+        static_lr.fill_(float(lr))
+        graph.replay()
+        _lib.launch_count += launches            # kernels of this library inside the replayed graph (bench.py's gpu_launches claim)
+        return out
+
     def step(self, styles, lr=None, global_count=None):
         """One optimisation step on this rank's shard.  Returns a dict of device scalars (loss, clip_loss, l2_loss, grad_norm)."""
         lr = self.lr if lr is None else lr
@@ -319,7 +350,10 @@ class DirectionFinder:
         l2_scale = 2.0 * self.l2_reg_coef / numel
         grad_total = grad + l2_scale * self.delta[0]
         with torch.cuda.device(self.device):
-            _lib.call('smc_sgd_step', _lib.ptr(self.delta), _lib.ptr(grad), numel, float(lr), 1.0, float(l2_scale), _lib.stream())   # :339
+            if torch.is_tensor(lr):     # device scalar (graph replay)
+                _lib.call('smc_sgd_step_dev', _lib.ptr(self.delta), _lib.ptr(grad), numel, _lib.ptr(lr), 1.0, float(l2_scale), _lib.stream())
+            else:
+                _lib.call('smc_sgd_step', _lib.ptr(self.delta), _lib.ptr(grad), numel, float(lr), 1.0, float(l2_scale), _lib.stream())   # :339
         out = dict(loss=clip_loss + l2, clip_loss=clip_loss, l2_loss=l2, grad=grad_total, grad_norm=grad_total.norm())
         if id_loss is not None:
             out['identity_loss'] = id_loss

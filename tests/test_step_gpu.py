@@ -141,6 +141,31 @@ def test_delta_zero_is_degenerate_and_the_loop_leaves_it():
     assert torch.isfinite(final).all() and moved > 1e-2
 
 
+def test_step_graph_replay_equals_eager_steps():
+    """DirectionFinder.step_graph (one CUDA graph per shard shape, S batch and learning rate in static buffers) follows the same trajectory as
+    eager steps: three steps with a cosine learning rate and two different S batches on the 64-px network."""
+    from stylemc_b200 import direction
+    G = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    ws = torch.randn(8, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(21))
+    S, shapes = o_syn.get_styles(G, ws, o_syn.split_ws(G, ws))
+    delta = 0.05 * torch.randn(1, 8, 512, generator=torch.Generator().manual_seed(22))
+    runs = []
+    for graphed in (False, True):
+        f = finder(G, 64)
+        f.delta.copy_(delta.cuda())
+        losses = []
+        for it in range(1, 4):
+            lr = direction.cosine_lr(1.0, it, 3)
+            batch = S[(it % 2) * 4:(it % 2) * 4 + 4].cuda()
+            out = (f.step_graph if graphed else f.step)(batch, lr=lr)
+            losses.append(out['loss'].item())
+        runs.append((losses, f.delta.cpu().clone()))
+    (l0, d0), (l1, d1) = runs
+    print('eager', l0, 'graph', l1, 'delta rel diff', ((d0 - d1).norm() / d0.norm()).item())
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(l0, l1))
+    assert ((d0 - d1).norm() / d0.norm()).item() <= 1e-4
+
+
 def test_full_size_1024_properties():
     """BASELINE configs[3] network (1024 px config-f) at full resolution, through size-independent properties -- the CPU oracle needs
     minutes per image there.  (1) The step is invariant to how the seed batch is cut into micro-batches (the gradient is a sum over
