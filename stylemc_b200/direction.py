@@ -213,8 +213,9 @@ class DirectionFinder:
     def direction(self):
         """styles_direction [1, 26, 512] (find_direction.py:306-307; the tensor saved as direction_*.npz, :349-351)."""
         d = torch.zeros([1, N_STYLE_CHANNELS, synthesis.STYLE_WIDTH], dtype=torch.float32, device=self.device)
-        d[:, self.rows] = self.delta
-        return d
+        if getattr(self, '_rows_idx', None) is None:         # device-side row indices: no host-to-device copy inside a step (graph capture)
+            self._rows_idx = torch.tensor(self.rows, dtype=torch.int64, device=self.device)
+        return d.index_copy_(1, self._rows_idx, self.delta)
 
     def load_direction(self, styles_direction):
         """Resume from a saved direction [1, 26, 512] (find_direction.py:266-270: the trainable rows are selected out of it)."""
