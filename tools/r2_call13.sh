@@ -2,7 +2,7 @@ mkdir -p gpurun_out
 T0=$(date +%s)
 leg() { echo "== [$(( $(date +%s) - T0 ))s] $*"; }
 PT="timeout 900 python -m pytest -m gpu -q --no-header -p no:cacheprovider"
-($PT tests/test_step_gpu.py -k graph -s 2>&1) > gpurun_out/c13_graph.log; leg "graph test: $(tail -n 1 gpurun_out/c13_graph.log)"; grep -E "^eager|Error|^E  " gpurun_out/c13_graph.log | head
+
 for g in 0 1 0 1; do
   (timeout 300 python bench.py --no-cpu-baseline --cuda-graph $g > gpurun_out/c13_bench_g$g.json 2> gpurun_out/c13_bench_g$g.err); leg "bench 1024 graph=$g: $(cut -c1-170 gpurun_out/c13_bench_g$g.json)"
 done
