@@ -53,7 +53,7 @@ def parse():
                     help="also time the reference's GPU formulation (oracle modules = ATen / cuDNN / cuBLAS fp32 on cuda:0, TF32 off and on) for one step; "
                          'reported as gpu_library_baseline next to cpu_baseline (BASELINE.md section 3, second bar)')
     ap.add_argument('--cuda-graph', type=int, default=-1, help='replay the step from a CUDA graph (DirectionFinder.step_graph): 1 on, 0 off, '
-                    '-1 = on for strong-scaling runs (--global-seeds), off otherwise')
+                    '-1 = on for single-GPU --global-seeds runs, off otherwise')
     ap.add_argument('--profile-step', action='store_true', help='run warm-up, then ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     return ap.parse_args()
 
@@ -253,7 +253,9 @@ def run_ours(a):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return ms.item()
 
-    use_graph = a.cuda_graph == 1 or (a.cuda_graph == -1 and strong)
+    # graph replay pays where a step is short and there is no per-step host sync around an NCCL collective: on one GPU it is +3.7 % at 17 seeds;
+    # on 8 GPUs +1.9 % resident, but the e2e loop (loss read back every step) ran at HALF speed with the all-reduce inside the graph
+    use_graph = a.cuda_graph == 1 or (a.cuda_graph == -1 and strong and world == 1)
     do_step = finder.step_graph if use_graph else finder.step
 
     def step_resident(i):
