@@ -1110,7 +1110,8 @@ __global__ void __launch_bounds__(512) clip_loss_kernel(const float* __restrict_
 
 int g_attention_tiled = 0;   // 0: tiled attention only where the whole-sequence kernel does not fit; 1: always; >= 4: always, rows per CTA capped
                              // at that value (smc_synth_config key 5; tests exercise several row blocks at 50 tokens this way)
-int g_resample_vfirst = 1;   // unprocess: vertical pass first for >= 2x down-sampling (smc_synth_config key 4; 0 = horizontal first)
+int g_resample_vfirst = 0;   // unprocess: vertical pass first for >= 2x down-sampling (smc_synth_config key 4).  Off: under ncu the marching kernel is slower
+                             // (1.34 ms at 0.7 TB/s against 0.88 + 0.17 ms, profiles/r02_glue_launches.md); the bench A/B was inside the noise (+0.4 %)
 
 static int grid1d(long long items) {
   long long b = ceil_div_ll(items, 256);
