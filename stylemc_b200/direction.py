@@ -237,13 +237,13 @@ class DirectionFinder:
     def _encode_original(self, s):
         """CLIP embeddings of the un-edited images (find_direction.py:312: no gradient), one per tower."""
         with _phase('original_branch'):
-            _, original, _ = self.engine_original.forward(s, self.until_k, self.noise_mode, save=False)
-            u_s = resample.unprocess_fwd(original, mode=self.loss_fn.preprocess)
+            _, original, _ = getattr(self, 'engine_original', self.engine).forward(s, self.until_k, self.noise_mode, save=False)
+            u_s = resample.unprocess_fwd(original, mode=getattr(self.clips[0][1], 'preprocess', 'unprocess'))
             e_s = [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
             return e_s + [original] if self._use_id() else e_s
 
     def _use_id(self):
-        return self.id_loss is not None and self.identity_loss_coef != 0.0
+        return getattr(self, 'id_loss', None) is not None and self.identity_loss_coef != 0.0
 
     def loss_and_grad(self, styles, global_count=None):
         """styles [n, 26, 512] (this rank's shard, device) -> (grad [8, 512] summed over the shard, clip-loss partial sum).
@@ -255,8 +255,9 @@ class DirectionFinder:
         self._id_part = torch.zeros(1, dtype=torch.float32, device=self.device)
         direction = self.direction()
         eng = self.engine
-        pre = self.loss_fn.preprocess                  # 'unprocess' (find_direction.py:49-52) or the NADA preprocessing (clip_loss_nada.py:86-89)
-        need_src = self.loss_fn.needs_source or self._use_id()     # nada_global alone never looks at the original image
+        loss0 = self.clips[0][1]
+        pre = getattr(loss0, 'preprocess', 'unprocess')    # find_direction.py:49-52, or the NADA preprocessing (clip_loss_nada.py:86-89)
+        need_src = getattr(loss0, 'needs_source', True) or self._use_id()     # nada_global alone never looks at the original image
         for lo in range(0, n_total, self.micro_batch):
             s = styles[lo:lo + self.micro_batch].to(self.device, torch.float32)
             s2 = s + direction                                                        # find_direction.py:308

@@ -227,8 +227,8 @@ def test_direction_finder_combines_towers_and_loss_scales(towers, overlap, monke
             d, = torch.autograd.grad(part, e_t)
             return part.detach().reshape(1), d * self.scale, torch.tensor([self.scale], dtype=torch.float64)
 
-    monkeypatch.setattr(direction.resample, 'unprocess_fwd', lambda img: 2.0 * img)
-    monkeypatch.setattr(direction.resample, 'unprocess_bwd', lambda g, img, unscale=None: 2.0 * g / unscale)
+    monkeypatch.setattr(direction.resample, 'unprocess_fwd', lambda img, mode='unprocess': 2.0 * img)
+    monkeypatch.setattr(direction.resample, 'unprocess_bwd', lambda g, img, unscale=None, mode='unprocess': 2.0 * g / unscale)
     f = object.__new__(direction.DirectionFinder)
     f.device, f.engine, f.until_k, f.noise_mode, f.micro_batch, f.rows = torch.device('cpu'), Engine(), 3, 'const', 2, rows
     f.clip_loss_coef, f.overlap, f._side = coef, overlap, None
