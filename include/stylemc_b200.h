@@ -197,8 +197,9 @@ int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w, int c, con
                 float alpha, float gain, float clamp, void* gd, void* gd_lo, float* t1, float* r, void* stream);
 int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int w, int c, const float* fk, const float* fsep_host, void* planes,
                 void* planes_lo, void* stream);
+/* grad_samples (optional): also writes the per-sample style gradient ds[n, 0..cin) at grad_samples + n * gs_stride (latent mapper). */
 int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
-                     const float* gscale, float* grad_row, int n, int cin, int cout, void* stream);
+                     const float* gscale, float* grad_row, int n, int cin, int cout, float* grad_samples, int64_t gs_stride, void* stream);
 int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_scratch, float* gscale, void* stream);
 
 /* ---- unprocess + CLIP glue (vit.cu) --------------------------------------------------------------
@@ -263,6 +264,13 @@ int smc_prepare_weights(const float* w, int n_out, int n_in, int ntaps, int n_ou
 int smc_prelu(const float* x, const float* dy, const float* alpha, float* y, int64_t numel, int hw, int c, void* stream);
 int smc_adaptive_avg_pool(const float* x, float* y, int64_t planes, int h, int w, int y0, int x0, int hc, int wc, int oh, int ow,
                           int backward, void* stream);
+
+/* ---- latent-mapper glue (latent_mappers.py:12-93, train_latent_mapper.py:131) ----------------------------------------------------------------
+ * smc_pixelnorm: PixelNorm over dim 1 of x [b, l, c] (encoder4editing/models/stylegan2/model.py:14-15); dy != NULL: the input gradient.
+ * smc_adam_step: torch.optim.Adam without weight decay; bc1 = 1 - beta1^t and bc2_sqrt = sqrt(1 - beta2^t) are computed by the host. */
+int smc_pixelnorm(const float* x, const float* dy, float* y, int b, int l, int c, void* stream);
+int smc_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1, float beta2, float eps, float bc1,
+                  float bc2_sqrt, void* stream);
 
 /* ---- fma.py:15-58 as a stand-alone op (on the fused path the multiply-add is the GEMM epilogue) -----------------------
  * smc_fma: out = a * b + c over the broadcast index space `shape` (4 sizes, leading 1s for lower ranks); stride_* are ELEMENT strides

@@ -28,7 +28,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = '/root/reference'
 sys.path.insert(0, REPO)
 
-from oracle import act, conv, direction, fir, idloss, synthesis, vit  # noqa: E402
+from oracle import act, conv, direction, fir, idloss, mapper, synthesis, vit  # noqa: E402
 
 GOLD = os.path.join(REPO, 'tests', 'golden')
 
@@ -383,6 +383,72 @@ def pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, out):
 B16_SEED = 7
 
 
+def pin_mapper(R, model, G_ref, G_ora, S, shapes, out):
+    """The latent mapper (latent_mappers.py:68-93) and one train_latent_mapper.py:150-190 step: the reference's REAL ``Mapper`` loaded (strict) with
+    oracle.mapper.random_mapper_params, its REAL ``find_direction.compute_loss`` (CLIP term through the stub clip module, identity term through the
+    hand-built IDLoss of pin_idloss with coefficient 0.6, landmarks coefficient 0, L2 0.1) and autograd down to the mapper's weights, vs
+    oracle.mapper on the 64-px network with the styles of step64.npz."""
+    print('mapper: reference latent_mappers.Mapper + compute_loss vs oracle.mapper (64-px net)')
+    from torchvision.transforms import CenterCrop, Compose, Resize
+    from PIL import Image
+    op = types.ModuleType('encoder4editing.models.stylegan2.op')          # CUDA-only fused ops: not used by the Mapper (only EqualLinear / PixelNorm names are imported)
+    op.FusedLeakyReLU, op.fused_leaky_relu, op.upfirdn2d = torch.nn.Identity, (lambda x, b=None, *a, **k: x), None
+    sys.modules.setdefault('encoder4editing.models.stylegan2.op', op)
+    sys.path.insert(0, REF)
+    from latent_mappers import Mapper
+    from id_loss.id_loss import IDLoss
+    from id_loss.model_irse import Backbone
+    install_stub_clip(R, model)
+    dev = torch.device('cpu')
+    p = mapper.random_mapper_params(seed=3)
+    ref = Mapper(neg_slope=0.01)
+    ref.load_state_dict(p, strict=True)
+    x = S[:, R.fd.S_TRAINABLE_SPACE_CHANNELS]
+    with torch.no_grad():
+        close(mapper.mapper_forward(p, x), ref(x), 1e-6, 'Mapper.forward')
+    # the reference's objects for compute_loss
+    idp = idloss.random_irse50_params(seed=0)
+    net = Backbone(input_size=112, num_layers=50, drop_ratio=0.6, mode='ir_se')
+    net.load_state_dict(idp, strict=True)
+    net.eval()
+    id_ref = IDLoss.__new__(IDLoss)
+    torch.nn.Module.__init__(id_ref)
+    id_ref.facenet, id_ref.pool, id_ref.face_pool = net, torch.nn.AdaptiveAvgPool2d((256, 256)), torch.nn.AdaptiveAvgPool2d((112, 112))
+    mean, std = R.utils.get_mean_std(dev)
+    transf = Compose([Resize(224, interpolation=Image.BICUBIC), CenterCrop(224)])
+    l1, _ = R.fd.init_clip_loss('default', 'small', dev, POS_TEXT, NEG_TEXT)
+    T = R.fd.S_TRAINABLE_SPACE_CHANNELS
+    styles = S[:2]
+    delta = ref(styles[:, T])                                            # train_latent_mapper.py:155-158
+    styles2 = styles.clone()
+    styles2[:, T] += delta
+    _, img = R.utils.generate_image(G_ref, 100, styles2, shapes, 'const', dev)
+    _, original = R.utils.generate_image(G_ref, 100, styles, shapes, 'const', dev)
+    loss, ld = R.fd.compute_loss(img, original, transf, mean, std, dev, 'default', 'small', 1.0, l1, None, POS_TEXT, NEG_TEXT, id_ref, 0.6,
+                                 None, 0.0, None, 224, styles, styles2, 0.1)
+    loss.backward()
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    loss_fn = direction.CLIPLoss(model, vit.synthetic_tokens('pos'), vit.synthetic_tokens('neg'))
+    o = mapper.mapper_step_loss(G_ora, shapes, loss_fn, pr, styles, 100, id_params=idp, identity_loss_coef=0.6)
+    grads = torch.autograd.grad(o['loss'], list(pr.values()))
+    close(o['loss'].detach(), loss.detach(), 1e-6, 'mapper step loss')
+    close(o['identity_loss'].detach(), ld['identity_loss'].detach(), 1e-6, 'mapper step identity term')
+    worst = 0.0
+    for (k, _), g in zip(pr.items(), grads):
+        gr = dict(ref.named_parameters())[k].grad
+        worst = max(worst, ((g - gr).norm() / gr.norm()).item())
+    print(f'  loss {loss.item():.6f} (clip {ld["clip_loss"].item():.6f}, identity {ld["identity_loss"].item():.6f}, l2 {ld["l2_loss"].item():.6f}); '
+          f'worst parameter-gradient rel-l2 {worst:.2e}')
+    assert worst < 1e-4
+    out['x'], out['delta'] = x.numpy(), ref(x).detach().numpy()
+    out['loss'], out['clip_loss'], out['identity_loss'], out['l2_loss'] = (loss.detach().numpy(), ld['clip_loss'].detach().numpy(),
+                                                                           ld['identity_loss'].detach().numpy(), ld['l2_loss'].detach().numpy())
+    for k, v in ref.named_parameters():          # full gradients of the biases and of the first / last weight; norms of the other weights (fixture size)
+        if k.endswith('bias') or k in ('course_mapping.modulation_module_list.0.fc.weight', 'medium_mapping.modulation_module_list.4.fc.weight'):
+            out['grad.' + k] = v.grad.numpy()
+        out['gradnorm.' + k] = v.grad.norm().numpy()
+
+
 def pin_idloss(R, out):
     """The identity loss (find_direction.py:179-180): the reference's REAL id_loss.model_irse.Backbone (IR-SE50, eval mode) loaded (strict)
     with oracle.idloss.random_irse50_params, and the REAL IDLoss.extract_feats / IDLoss.forward run on an instance built without the
@@ -557,6 +623,7 @@ def main():
     ap.add_argument('--skip-config1', action='store_true')
     ap.add_argument('--skip-config4', action='store_true')
     ap.add_argument('--only-config4', action='store_true', help='(re)write only config4.npz')
+    ap.add_argument('--only-mapper', action='store_true', help='(re)write only mapper64.npz')
     ap.add_argument('--only-idloss', action='store_true', help='(re)write only idloss.npz')
     ap.add_argument('--only-nada', action='store_true', help='(re)write only step64_nada.npz')
     ap.add_argument('--only-ops', action='store_true', help='(re)write only ops.npz')
@@ -564,7 +631,7 @@ def main():
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     R = import_reference()
-    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'step64_nada', 'idloss', 'config1', 'config4')}
+    fx = {k: {} for k in ('ops', 'synth64', 'clip', 'clip_b16', 'step64', 'step64_double', 'step64_nada', 'idloss', 'mapper64', 'config1', 'config4')}
     if args.only_config4:
         model = vit.CLIP(seed=0, cfg=vit.VIT_B32)
         install_stub_clip(R, model)
@@ -572,6 +639,14 @@ def main():
         if not args.check:
             np.savez_compressed(os.path.join(GOLD, 'config4.npz'), **fx['config4'])
             print('wrote config4.npz', f'{os.path.getsize(os.path.join(GOLD, "config4.npz")) / 1e6:.2f} MB')
+        return
+    if args.only_mapper:
+        G_ref, G_ora, S, shapes = pin_driver(R, fx['synth64'])
+        model = vit.CLIP(seed=0, cfg=vit.VIT_B32)
+        pin_mapper(R, model, G_ref, G_ora, S, shapes, fx['mapper64'])
+        if not args.check:
+            np.savez_compressed(os.path.join(GOLD, 'mapper64.npz'), **fx['mapper64'])
+            print('wrote mapper64.npz', f'{os.path.getsize(os.path.join(GOLD, "mapper64.npz")) / 1e6:.2f} MB')
         return
     if args.only_idloss:
         pin_idloss(R, fx['idloss'])
@@ -601,6 +676,7 @@ def main():
     pin_step_double(R, model, model_b16, G_ref, G_ora, S, shapes, fx['step64_double'])
     pin_step_nada(R, model, G_ref, G_ora, S, shapes, fx['step64_nada'])
     pin_idloss(R, fx['idloss'])
+    pin_mapper(R, model, G_ref, G_ora, S, shapes, fx['mapper64'])
     if not args.skip_config1 and not args.only_double:
         pin_config1(R, model, fx['config1'])
     if not args.skip_config4 and not args.only_double:

@@ -83,7 +83,7 @@ SIGNATURES = {
     'smc_torgb': 'pp iiii pp q f p f ppp p q pp p',
     'smc_act_bwd': 'pp iiii p i p q ppp q f p f pppp fff pppp p',
     'smc_fir_bwd': 'pp iiii pppp p',
-    'smc_sgrad_finish': 'ppppp q pp iii p',
+    'smc_sgrad_finish': 'ppppp q pp iii p q p',
     'smc_grad_scale': 'p q f pp p',
     'smc_resample_fwd': 'pppppp i iii i pp p',
     'smc_resample_bwd': 'ppppppp i iii i p p p',
@@ -106,6 +106,8 @@ SIGNATURES = {
     'smc_prepare_weights': 'p iiiii p pppp p p',
     'smc_prelu': 'pppp q ii p',
     'smc_adaptive_avg_pool': 'pp q iiiiiiii i p',
+    'smc_pixelnorm': 'ppp iii p',
+    'smc_adam_step': 'pppp q ffffff p',
     'smc_fma': 'pppp i pppp p',
     'smc_fma_reduce': 'ppp i pppp p',
     'smc_sgd_step': 'pp q fff p',

@@ -152,6 +152,40 @@ __global__ void __launch_bounds__(256) adaptive_pool_bwd_kernel(const float* __r
   }
 }
 
+// ---- latent-mapper glue (latent_mappers.py:12-93, train_latent_mapper.py:131,150-196)
+// PixelNorm over dim 1 of x [B, L, C] (encoder4editing/models/stylegan2/model.py:14-15): y = x * rsqrt(mean_l x^2 + 1e-8); one thread per (b, c).
+// dy != NULL: the input gradient dx_l = r dy_l - x_l r^3 mean_k(dy_k x_k).
+__global__ void __launch_bounds__(256) pixelnorm_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ y, int B, int L, int C) {
+  const long long total = (long long)B * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long base = (i / C) * L * C + c;
+    float ss = 0.f, dot = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float v = x[base + (long long)l * C];
+      ss += v * v;
+      if (dy) dot += dy[base + (long long)l * C] * v;
+    }
+    const float r = rsqrtf(ss / L + 1e-8f);
+    const float k = dy ? r * r * r * dot / L : 0.f;
+    for (int l = 0; l < L; ++l) {
+      const long long at = base + (long long)l * C;
+      y[at] = dy ? r * dy[at] - x[at] * k : x[at] * r;
+    }
+  }
+}
+// torch.optim.Adam (no weight decay, no amsgrad; train_latent_mapper.py:131): bc1 = 1 - beta1^t, bc2_sqrt = sqrt(1 - beta2^t) from the host
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                        long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
 // ---- fma.py:15-58 as stand-alone kernels: out = a * b + c over a broadcast 4-D index space, and the "un-broadcast" of its
 // backward (sum of x * y over the axes broadcasting expanded).  Element strides; 0 marks a broadcast / reduced axis.
 struct FmaDims {
@@ -297,6 +331,25 @@ extern "C" int smc_adaptive_avg_pool(const float* x, float* y, int64_t planes, i
   if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
   if (backward) smc::adaptive_pool_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, planes, h, w, y0, x0, hc, wc, oh, ow);
   else smc::adaptive_pool_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, planes, h, w, y0, x0, hc, wc, oh, ow);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_pixelnorm(const float* x, const float* dy, float* y, int b, int l, int c, void* stream) {
+  if (!x || !y || b < 1 || l < 1 || c < 1) return SMC_EINVAL;
+  long long blocks = smc::ceil_div_ll((long long)b * c, 256);
+  if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
+  smc::pixelnorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, dy, y, b, l, c);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
+extern "C" int smc_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1, float beta2, float eps, float bc1,
+                             float bc2_sqrt, void* stream) {
+  if (!p || !g || !m || !v || numel < 1 || !(bc1 > 0.f) || !(bc2_sqrt > 0.f)) return SMC_EINVAL;
+  long long blocks = smc::ceil_div_ll(numel, 256);
+  if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
+  smc::adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, numel, lr, beta1, beta2, eps, bc1, bc2_sqrt);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

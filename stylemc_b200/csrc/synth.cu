@@ -1238,7 +1238,10 @@ __global__ void __launch_bounds__(256) fir_bwd_kernel(const __half* __restrict__
 // the batch is walked in order so the result is deterministic.
 __global__ void __launch_bounds__(256) sgrad_finish_kernel(const float* __restrict__ T1, const float* __restrict__ R, const float* __restrict__ q,
                                                            const float* __restrict__ d, const float* __restrict__ s, long long s_stride,
-                                                           const float* __restrict__ gscale_ptr, float* __restrict__ grad_row, int N, int cin, int cout) {
+                                                           const float* __restrict__ gscale_ptr, float* __restrict__ grad_row, int N, int cin, int cout,
+                                                           float* __restrict__ grad_samples = nullptr, long long gs_stride = 0) {
+  // grad_samples (optional): the PER-SAMPLE style gradient ds[n, :] at grad_samples + n * gs_stride (the latent mapper's delta differs per
+  // image, train_latent_mapper.py:155-158); grad_row still receives the batch sum
   extern __shared__ float coef[];  // [cout] = d^2 * R for the current image, then [8][32] partial sums
   float* part = coef + cout;
   const int tx = threadIdx.x & 31, sl = threadIdx.x >> 5;
@@ -1270,7 +1273,9 @@ __global__ void __launch_bounds__(256) sgrad_finish_kernel(const float* __restri
       float tt = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) tt += part[k * 32 + tx];
-      acc += T1[(long long)n * cin + i] - s[n * s_stride + i] * tt;
+      const float ds = T1[(long long)n * cin + i] - s[n * s_stride + i] * tt;
+      acc += ds;
+      if (grad_samples) grad_samples[n * gs_stride + i] = ds / __ldg(gscale_ptr);
     }
   }
   if (sl == 0 && i < cin) grad_row[i] += acc / __ldg(gscale_ptr);
@@ -1808,9 +1813,10 @@ extern "C" int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int 
 }
 
 extern "C" int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
-                                const float* gscale, float* grad_row, int n, int cin, int cout, void* stream) {
+                                const float* gscale, float* grad_row, int n, int cin, int cout, float* grad_samples, int64_t gs_stride, void* stream) {
   if (!t1 || !r || !q || !d || !s || !gscale || !grad_row || n < 1 || cin < 1 || cout < 1) return SMC_EINVAL;
-  sgrad_finish_kernel<<<ceil_div(cin, 32), 256, (cout + 256) * sizeof(float), (cudaStream_t)stream>>>(t1, r, q, d, s, s_stride, gscale, grad_row, n, cin, cout);
+  sgrad_finish_kernel<<<ceil_div(cin, 32), 256, (cout + 256) * sizeof(float), (cudaStream_t)stream>>>(t1, r, q, d, s, s_stride, gscale, grad_row, n, cin, cout,
+                                                                                                     grad_samples, gs_stride);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

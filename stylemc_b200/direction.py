@@ -245,14 +245,17 @@ class DirectionFinder:
     def _use_id(self):
         return getattr(self, 'id_loss', None) is not None and self.identity_loss_coef != 0.0
 
-    def loss_and_grad(self, styles, global_count=None):
+    def loss_and_grad(self, styles, global_count=None, styles_edit=None, per_sample=False):
         """styles [n, 26, 512] (this rank's shard, device) -> (grad [8, 512] summed over the shard, clip-loss partial sum).
-        ``global_count`` is the number of seeds in the whole step (all ranks); the CLIP loss is their mean (clip_loss.py:34)."""
+        ``global_count`` is the number of seeds in the whole step (all ranks); the CLIP loss is their mean (clip_loss.py:34).
+        ``styles_edit`` (optional [n, 26, 512]): the edited S of every image instead of ``styles + direction()`` (the latent mapper's delta
+        differs per image); ``per_sample=True`` returns the gradient w.r.t. each image's own trainable rows, [n, 8, 512]."""
         n_total = styles.shape[0]
         count = n_total if global_count is None else global_count
         grad = torch.zeros([len(self.rows), synthesis.STYLE_WIDTH], dtype=torch.float32, device=self.device)
         part_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._id_part = torch.zeros(1, dtype=torch.float32, device=self.device)
+        samples = []
         direction = self.direction()
         eng = self.engine
         loss0 = self.clips[0][1]
@@ -260,7 +263,7 @@ class DirectionFinder:
         need_src = getattr(loss0, 'needs_source', True) or self._use_id()     # nada_global alone never looks at the original image
         for lo in range(0, n_total, self.micro_batch):
             s = styles[lo:lo + self.micro_batch].to(self.device, torch.float32)
-            s2 = s + direction                                                        # find_direction.py:308
+            s2 = s + direction if styles_edit is None else styles_edit[lo:lo + self.micro_batch].to(self.device, torch.float32)   # find_direction.py:308
             e_s = [None] * len(self.clips)
             if self.overlap and need_src:
                 cur = torch.cuda.current_stream(self.device)
@@ -299,9 +302,15 @@ class DirectionFinder:
                     g_img = g_img + g_id
                     self._id_part += part_id
             with _phase('synthesis_bwd'):
-                grad += eng.backward(saved, g_img, self.rows, self.noise_mode)
+                if per_sample:
+                    g_sum, g_each = eng.backward(saved, g_img, self.rows, self.noise_mode, per_sample=True)
+                    grad += g_sum
+                    samples.append(g_each)
+                else:
+                    grad += eng.backward(saved, g_img, self.rows, self.noise_mode)
         # with the identity term the partial sums travel together: [clip, identity] (one all-reduce either way)
-        return grad, (torch.cat([part_sum, self._id_part]) if self._use_id() else part_sum)
+        parts = torch.cat([part_sum, self._id_part]) if self._use_id() else part_sum
+        return (torch.cat(samples), parts) if per_sample else (grad, parts)
 
     def step_graph(self, styles, lr=None, global_count=None):
         """``step`` replayed from a CUDA graph: the ~500 launches of a step (two streams, the NCCL all-reduce included) are captured once per

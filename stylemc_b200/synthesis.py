@@ -327,12 +327,14 @@ class SynthesisEngine:
         return xs_list, img, saved
 
     # ---- backward ------------------------------------------------------------------------------
-    def backward(self, saved, g_img, trainable_rows, noise_mode='const', grad_scale_target=256.0):
+    def backward(self, saved, g_img, trainable_rows, noise_mode='const', grad_scale_target=256.0, per_sample=False):
         """Gradient of a scalar loss w.r.t. the trainable S rows, summed over the batch.
 
         saved: SavedForward of the pass that produced img; g_img = dL/dimg [N, 3, R, R] fp32.
         Returns grad [len(trainable_rows), 512] fp32 (zero beyond each layer's channel count), i.e. exactly
-        ``delta.grad`` of find_direction.py:336 for delta broadcast over the batch (:307-308)."""
+        ``delta.grad`` of find_direction.py:336 for delta broadcast over the batch (:307-308).  ``per_sample=True`` returns
+        ``(grad, grad_samples [N, len(trainable_rows), 512])``: the gradient w.r.t. each image's own S rows (the latent mapper's delta differs
+        per image, train_latent_mapper.py:155-158)."""
         styles, last = saved.styles, saved.until_k
         n = styles.shape[0]
         dev = self.device
@@ -351,6 +353,7 @@ class SynthesisEngine:
         if getattr(saved, 'grad_rows', None) is not None and not want <= saved.grad_rows:
             raise RuntimeError(f'the forward pass saved activations for style rows {sorted(saved.grad_rows)} only; asked for {sorted(want)}')
         grad = torch.zeros([len(trainable_rows), STYLE_WIDTH], dtype=torch.float32, device=dev)
+        grad_samples = torch.zeros([n, len(trainable_rows), STYLE_WIDTH], dtype=torch.float32, device=dev) if per_sample else None
         g_img = g_img.float().contiguous()
         with torch.cuda.device(dev):
             amax = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -470,5 +473,6 @@ class SynthesisEngine:
                 d = saved.d1[k] if which == 1 else saved.d0[k]
                 sp, ss = self._srow(styles, row)
                 _lib.call('smc_sgrad_finish', _lib.ptr(t1), _lib.ptr(rr), _lib.ptr(L.q), _lib.ptr(d), sp, ss, _lib.ptr(gscale),
-                          _lib.ptr(grad[i]), n, L.cin, L.cout, _lib.stream())
-        return grad
+                          _lib.ptr(grad[i]), n, L.cin, L.cout, _lib.ptr(grad_samples[0, i]) if per_sample else None,
+                          grad_samples.stride(0) if per_sample else 0, _lib.stream())
+        return (grad, grad_samples) if per_sample else grad

@@ -136,3 +136,27 @@ def test_idloss_golden(golden):
     grad, = torch.autograd.grad(loss, y_hat)
     assert abs(loss.item() - float(g['loss'])) <= 1e-6
     assert ((grad - T(g['grad'])).norm() / T(g['grad']).norm()).item() <= 1e-4
+
+
+def test_mapper_golden(golden):
+    """oracle.mapper (latent_mappers.Mapper restatement + one train_latent_mapper.py:150-176 loss) against the reference's REAL Mapper and
+    REAL find_direction.compute_loss (tests/golden/mapper64.npz): delta, loss terms, parameter gradients."""
+    from oracle import idloss, mapper
+    g, gs = golden('mapper64'), golden('synth64')
+    p = mapper.random_mapper_params(seed=3)
+    with torch.no_grad():
+        assert (mapper.mapper_forward(p, T(g['x'])) - T(g['delta'])).abs().max().item() <= 1e-6
+    G = synthesis.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    shapes = synthesis.get_temp_shapes(G)
+    S = T(gs['styles'])
+    assert torch.equal(S[:, direction.S_TRAINABLE_ROWS], T(g['x']))
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    loss_fn = direction.CLIPLoss(vit.CLIP(seed=0), vit.synthetic_tokens('pos'), vit.synthetic_tokens('neg'))
+    o = mapper.mapper_step_loss(G, shapes, loss_fn, pr, S[:2], 100, id_params=idloss.random_irse50_params(seed=0), identity_loss_coef=0.6)
+    for k in ('loss', 'clip_loss', 'identity_loss', 'l2_loss'):
+        assert abs(o[k].item() - float(g[k])) <= 1e-6, k
+    grads = dict(zip(pr, torch.autograd.grad(o['loss'], list(pr.values()))))
+    for k, gr in grads.items():
+        assert abs(gr.norm().item() - float(g['gradnorm.' + k])) <= 1e-4 * float(g['gradnorm.' + k]), k
+        if 'grad.' + k in g:
+            assert ((gr - T(g['grad.' + k])).norm() / T(g['grad.' + k]).norm()).item() <= 1e-4, k
