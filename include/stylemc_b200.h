@@ -169,7 +169,8 @@ int smc_igemm_config(int key, int value);
  * [N, 26, 512] S tensor addressed as base pointer + n * stride. */
 /* A/B diagnostics (process-global, not thread-safe): key 0 / 1 / 2 = use the newer smc_fir_act / smc_fir_bwd / smc_act_bwd kernels,
  * key 3 = the warp-row streaming smc_upfirdn2d kernels (all default on; 0 selects the older kernel);
- * key 4 = smc_resample_fwd/bwd run the vertical pass first for >= 2x down-sampling. */
+ * key 4 = smc_resample_fwd/bwd run the vertical pass first for >= 2x down-sampling;
+ * key 6 = the row-tile kernel (32 rows x a run of outputs per CTA, shared-memory staged) for the row-contraction passes of smc_resample_fwd/bwd (default on). */
 int smc_synth_config(int key, int value);
 int smc_demod_coefs(const float* q, const float* s, int64_t s_stride, float* d, int n, int cin, int cout, void* stream);
 /* c_pitch >= c is the channel pitch of the NHWC side (channels c .. c_pitch-1 are left untouched: zero them once). */
@@ -197,10 +198,14 @@ int smc_act_bwd(const void* y, const void* y_lo, int n, int h, int w, int c, con
                 float alpha, float gain, float clamp, void* gd, void* gd_lo, float* t1, float* r, void* stream);
 int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int w, int c, const float* fk, const float* fsep_host, void* planes,
                 void* planes_lo, void* stream);
-/* grad_samples (optional): also writes the per-sample style gradient ds[n, 0..cin) at grad_samples + n * gs_stride (latent mapper). */
-int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
+/* t1 [n, cin] is read (the T1 sums of smc_act_bwd) and OVERWRITTEN with the loss-scaled per-sample gradient ds[n, i]; grad_row receives their sum over
+ * n in index order.  grad_samples (optional): also writes ds[n, 0..cin) / gscale at grad_samples + n * gs_stride (latent mapper). */
+int smc_sgrad_finish(float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
                      const float* gscale, float* grad_row, int n, int cin, int cout, float* grad_samples, int64_t gs_stride, void* stream);
 int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_scratch, float* gscale, void* stream);
+/* out[i] = g[i] * mask[i] * (*scale): the ToRGB clamp mask kept by smc_img_finish (bytes, 0 / 1) and the loss scale (device scalar, NULL = 1)
+ * applied to the incoming image gradient in one pass; feeds smc_act_bwd's g_img / smc_igemm_epilogue::mask_grgb. */
+int smc_mask_scale(const float* g, const unsigned char* mask, const float* scale, float* out, int64_t numel, void* stream);
 
 /* ---- unprocess + CLIP glue (vit.cu) --------------------------------------------------------------
  * mean3 / std3 are HOST arrays of 3 floats; all other pointers are device pointers. */
@@ -209,7 +214,8 @@ int smc_grad_scale(const float* g, int64_t numel, float target, uint32_t* amax_s
 int smc_resample_fwd(const float* x, float* tmp, float* y, const int* start, const int* count, const float* wgt, int taps,
                      int planes, int in_size, int out_size, int denorm_normalize, const float* mean3, const float* std3, void* stream);
 /* mode: 1 / 2 as denorm_normalize above.  unscale: optional DEVICE pointer to the loss scale S carried by g (see smc_clip_loss);
- * gx = d/dx of the unscaled loss. */
+ * gx = d/dx of the unscaled loss.  Tables (device): start / count / wgt[out, taps] = the window of each output index, monotone in the index;
+ * oidx / count / wgt[in, taps] = their transpose, every row of oidx a run of CONSECUTIVE output indices (oidx[i][k] = oidx[i][0] + k). */
 int smc_resample_bwd(const float* g, const float* x, float* tmp, float* gx, const int* oidx, const int* count, const float* wgt,
                      int taps, int planes, int in_size, int out_size, int mode, const float* std3, const float* unscale, void* stream);
 int smc_patchify(const float* img, void* hi, void* lo, int b, int res, int ps, void* stream);
@@ -269,6 +275,10 @@ int smc_adaptive_avg_pool(const float* x, float* y, int64_t planes, int h, int w
  * smc_pixelnorm: PixelNorm over dim 1 of x [b, l, c] (encoder4editing/models/stylegan2/model.py:14-15); dy != NULL: the input gradient.
  * smc_adam_step: torch.optim.Adam without weight decay; bc1 = 1 - beta1^t and bc2_sqrt = sqrt(1 - beta2^t) are computed by the host. */
 int smc_pixelnorm(const float* x, const float* dy, float* y, int b, int l, int c, void* stream);
+/* y[m, n] = sum_k a[m * sa_m + k * sa_k] * b[n * sb_n + k * sb_k] (+ bias[n]); fp32 in / out, float64 accumulation (one rounding): torch.nn.Linear of
+ * the mapper (latent_mappers.py:16) and its three backward products through strides.  y dense [m, n]. */
+int smc_matmul_nt_f64acc(const float* a, int64_t sa_m, int64_t sa_k, const float* b, int64_t sb_n, int64_t sb_k, const float* bias, float* y,
+                         int m, int n, int k, void* stream);
 int smc_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1, float beta2, float eps, float bc1,
                   float bc2_sqrt, void* stream);
 

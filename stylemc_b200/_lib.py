@@ -85,6 +85,7 @@ SIGNATURES = {
     'smc_fir_bwd': 'pp iiii pppp p',
     'smc_sgrad_finish': 'ppppp q pp iii p q p',
     'smc_grad_scale': 'p q f pp p',
+    'smc_mask_scale': 'pppp q p',
     'smc_resample_fwd': 'pppppp i iii i pp p',
     'smc_resample_bwd': 'ppppppp i iii i p p p',
     'smc_patchify': 'ppp iii p',
@@ -108,6 +109,7 @@ SIGNATURES = {
     'smc_adaptive_avg_pool': 'pp q iiiiiiii i p',
     'smc_pixelnorm': 'ppp iii p',
     'smc_adam_step': 'pppp q ffffff p',
+    'smc_matmul_nt_f64acc': 'p qq p qq pp iii p',
     'smc_fma': 'pppp i pppp p',
     'smc_fma_reduce': 'ppp i pppp p',
     'smc_sgd_step': 'pp q fff p',

@@ -55,6 +55,26 @@ __global__ void __launch_bounds__(256) img_to_uint8_v4_kernel(const float* __res
   }
 }
 
+// out = g * mask * (*scale): the ToRGB clamp mask saved by the forward pass (smc_img_finish pass_mask) and the loss scale applied to the
+// incoming image gradient in ONE pass (was two ATen launches, the first a type-promoting uint8 x float multiply on the scalar path).
+__global__ void __launch_bounds__(256) mask_scale_v4_kernel(const float* __restrict__ g, const unsigned char* __restrict__ mask,
+                                                            const float* __restrict__ scale, float* __restrict__ out, long long n4) {
+  const float k = scale ? __ldg(scale) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = ld_stream(reinterpret_cast<const float4*>(g) + i);
+    const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask) + i);
+    st_stream(reinterpret_cast<float4*>(out) + i,
+              make_uint4(__float_as_uint(__uint_as_float(u.x) * (float)m.x * k), __float_as_uint(__uint_as_float(u.y) * (float)m.y * k),
+                         __float_as_uint(__uint_as_float(u.z) * (float)m.z * k), __float_as_uint(__uint_as_float(u.w) * (float)m.w * k)));
+  }
+}
+__global__ void __launch_bounds__(256) mask_scale_kernel(const float* __restrict__ g, const unsigned char* __restrict__ mask,
+                                                         const float* __restrict__ scale, float* __restrict__ out, long long n) {
+  const float k = scale ? __ldg(scale) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = g[i] * (float)mask[i] * k;
+}
+
 // ---- one-off weight preparation (frozen G / CLIP): [O, I, T] fp32 conv or linear weights -> the K-major tap matrices of the implicit
 // GEMM as fp16 hi / lo planes, forward [T * Op, Ip] (row t * Op + o, column i) and dgrad [T * Ip, Op] (row t * Ip + i, column o), plus
 // q[o, i] = sum_t w^2 for the demodulation coefficients.  Replaces ~15 ATen launches per layer (permute / contiguous / half / sub /
@@ -173,6 +193,29 @@ __global__ void __launch_bounds__(256) pixelnorm_kernel(const float* __restrict_
       y[at] = dy ? r * dy[at] - x[at] * k : x[at] * r;
     }
   }
+}
+// y[m, n] = sum_k a[m, k] * b[n, k] (+ bias[n]) with the products accumulated in float64 and rounded once: the mapper's Linear(512, 512)
+// layers (latent_mappers.py:16).  Their output becomes the per-image delta S, and the synthesis gradient is so sensitive to S (a 5e-6
+// perturbation of delta moves it by 8e-4: leaky-ReLU slope flips) that the split-fp16 tensor-core GEMM (~1e-6) is not accurate enough here;
+// the matrices are tiny (B * 4 rows), so the scalar pipe does it.  Element strides: any of x W^T, dy W and dy^T x without a transpose.
+__global__ void __launch_bounds__(256) matmul_nt_f64acc_kernel(const float* __restrict__ a, long long sa_m, long long sa_k, const float* __restrict__ b,
+                                                               long long sb_n, long long sb_k, const float* __restrict__ bias, float* __restrict__ y,
+                                                               int M, int N, int K) {
+  __shared__ float ta[16][17], tb[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  double acc = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // tile loads: thread (ty, tx) fetches a[m0 + ty, k0 + tx] and b[n0 + ty, k0 + tx]
+    const int am = blockIdx.y * 16 + ty, bn = blockIdx.x * 16 + ty, kk = k0 + tx;
+    ta[ty][tx] = (am < M && kk < K) ? __ldg(a + am * sa_m + kk * sa_k) : 0.f;
+    tb[ty][tx] = (bn < N && kk < K) ? __ldg(b + bn * sb_n + kk * sb_k) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += (double)ta[ty][k] * (double)tb[tx][k];
+    __syncthreads();
+  }
+  if (m < M && n < N) y[(long long)m * N + n] = (float)(acc + (bias ? (double)__ldg(bias + n) : 0.0));
 }
 // torch.optim.Adam (no weight decay, no amsgrad; train_latent_mapper.py:131): bc1 = 1 - beta1^t, bc2_sqrt = sqrt(1 - beta2^t) from the host
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -344,6 +387,16 @@ extern "C" int smc_pixelnorm(const float* x, const float* dy, float* y, int b, i
   return SMC_OK;
 }
 
+extern "C" int smc_matmul_nt_f64acc(const float* a, int64_t sa_m, int64_t sa_k, const float* b, int64_t sb_n, int64_t sb_k, const float* bias, float* y,
+                                    int m, int n, int k, void* stream) {
+  if (!a || !b || !y || m < 1 || n < 1 || k < 1) return SMC_EINVAL;
+  if (smc::ceil_div(m, 16) > 65535) return SMC_ETOOLARGE;
+  smc::matmul_nt_f64acc_kernel<<<dim3(smc::ceil_div(n, 16), smc::ceil_div(m, 16)), 256, 0, (cudaStream_t)stream>>>(a, sa_m, sa_k, b, sb_n, sb_k, bias, y, m, n,
+                                                                                                               k);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
+}
+
 extern "C" int smc_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1, float beta2, float eps, float bc1,
                              float bc2_sqrt, void* stream) {
   if (!p || !g || !m || !v || numel < 1 || !(bc1 > 0.f) || !(bc2_sqrt > 0.f)) return SMC_EINVAL;
@@ -382,6 +435,17 @@ extern "C" int smc_fma_reduce(const void* x, const void* y, void* out, int dtype
   if (dtype == SMC_F16) return smc::fma_reduce_launch<__half, float>(x, y, out, d, n_out, n_red, st);
   if (dtype == SMC_F64) return smc::fma_reduce_launch<double, double>(x, y, out, d, n_out, n_red, st);
   return SMC_EINVAL;
+}
+
+extern "C" int smc_mask_scale(const float* g, const unsigned char* mask, const float* scale, float* out, int64_t numel, void* stream) {
+  if (!g || !mask || !out || numel < 1) return SMC_EINVAL;
+  const bool v4 = numel % 4 == 0 && (((uintptr_t)g | (uintptr_t)out) & 15) == 0 && ((uintptr_t)mask & 3) == 0;
+  long long blocks = smc::ceil_div_ll(v4 ? numel / 4 : numel, 256);
+  if (blocks > smc::kNumSMs * 16) blocks = smc::kNumSMs * 16;
+  if (v4) smc::mask_scale_v4_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, mask, scale, out, numel / 4);
+  else smc::mask_scale_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, mask, scale, out, numel);
+  SMC_LAUNCH_CHECK();
+  return SMC_OK;
 }
 
 extern "C" int smc_img_to_uint8(const float* img, unsigned char* out, int n, int h, int w, int canvas_w, int x_off, void* stream) {

@@ -1234,51 +1234,56 @@ __global__ void __launch_bounds__(256) fir_bwd_kernel(const __half* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // ds[n,i] = T1[n,i] - s[n,i] * sum_o q[o,i] * d[n,o]^2 * R[n,o]  (SURVEY.md section 8a style-gradient algebra;
 // R already carries d * dL/dd), summed over the batch into the delta gradient row and unscaled.
-// One CTA = 32 columns i x 8 slices of the o loop (the per-sample sum over o is the long axis: N * cout terms per column);
-// the batch is walked in order so the result is deterministic.
-__global__ void __launch_bounds__(256) sgrad_finish_kernel(const float* __restrict__ T1, const float* __restrict__ R, const float* __restrict__ q,
+// Two launches: sgrad_sample_kernel, one CTA per (32 columns i, image n) x 8 slices of the o loop, leaves ds[n, i] (still loss-scaled) in T1;
+// sgrad_sum_kernel adds the images in index order, so the result is deterministic (and bit-identical to a serial walk of the batch: the
+// first version did that walk inside 16 CTAs, 190 us per launch for 17 MFLOP).
+__global__ void __launch_bounds__(256) sgrad_sample_kernel(float* __restrict__ T1, const float* __restrict__ R, const float* __restrict__ q,
                                                            const float* __restrict__ d, const float* __restrict__ s, long long s_stride,
-                                                           const float* __restrict__ gscale_ptr, float* __restrict__ grad_row, int N, int cin, int cout,
-                                                           float* __restrict__ grad_samples = nullptr, long long gs_stride = 0) {
+                                                           const float* __restrict__ gscale_ptr, int cin, int cout,
+                                                           float* __restrict__ grad_samples, long long gs_stride) {
   // grad_samples (optional): the PER-SAMPLE style gradient ds[n, :] at grad_samples + n * gs_stride (the latent mapper's delta differs per
-  // image, train_latent_mapper.py:155-158); grad_row still receives the batch sum
-  extern __shared__ float coef[];  // [cout] = d^2 * R for the current image, then [8][32] partial sums
+  // image, train_latent_mapper.py:155-158)
+  extern __shared__ float coef[];  // [cout] = d^2 * R of this image, then [8][32] partial sums
   float* part = coef + cout;
   const int tx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx;
-  float acc = 0.f;
-  for (int n = 0; n < N; ++n) {
-    __syncthreads();
-    for (int o = threadIdx.x; o < cout; o += blockDim.x) {
-      const float dd = d[(long long)n * cout + o];
-      coef[o] = dd * dd * R[(long long)n * cout + o];
-    }
-    __syncthreads();
-    float t2 = 0.f;
-    if (i < cin) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int o = sl;
-      for (; o + 24 < cout; o += 32) {
-        a0 += __ldg(q + (long long)o * cin + i) * coef[o];
-        a1 += __ldg(q + (long long)(o + 8) * cin + i) * coef[o + 8];
-        a2 += __ldg(q + (long long)(o + 16) * cin + i) * coef[o + 16];
-        a3 += __ldg(q + (long long)(o + 24) * cin + i) * coef[o + 24];
-      }
-      for (; o < cout; o += 8) a0 += __ldg(q + (long long)o * cin + i) * coef[o];
-      t2 = (a0 + a1) + (a2 + a3);
-    }
-    part[sl * 32 + tx] = t2;
-    __syncthreads();
-    if (sl == 0 && i < cin) {
-      float tt = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tt += part[k * 32 + tx];
-      const float ds = T1[(long long)n * cin + i] - s[n * s_stride + i] * tt;
-      acc += ds;
-      if (grad_samples) grad_samples[n * gs_stride + i] = ds / __ldg(gscale_ptr);
-    }
+  const int n = blockIdx.y;
+  for (int o = threadIdx.x; o < cout; o += blockDim.x) {
+    const float dd = d[(long long)n * cout + o];
+    coef[o] = dd * dd * R[(long long)n * cout + o];
   }
-  if (sl == 0 && i < cin) grad_row[i] += acc / __ldg(gscale_ptr);
+  __syncthreads();
+  float t2 = 0.f;
+  if (i < cin) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int o = sl;
+    for (; o + 24 < cout; o += 32) {
+      a0 += __ldg(q + (long long)o * cin + i) * coef[o];
+      a1 += __ldg(q + (long long)(o + 8) * cin + i) * coef[o + 8];
+      a2 += __ldg(q + (long long)(o + 16) * cin + i) * coef[o + 16];
+      a3 += __ldg(q + (long long)(o + 24) * cin + i) * coef[o + 24];
+    }
+    for (; o < cout; o += 8) a0 += __ldg(q + (long long)o * cin + i) * coef[o];
+    t2 = (a0 + a1) + (a2 + a3);
+  }
+  part[sl * 32 + tx] = t2;
+  __syncthreads();
+  if (sl == 0 && i < cin) {
+    float tt = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tt += part[k * 32 + tx];
+    const float ds = T1[(long long)n * cin + i] - s[n * s_stride + i] * tt;
+    T1[(long long)n * cin + i] = ds;
+    if (grad_samples) grad_samples[n * gs_stride + i] = ds / __ldg(gscale_ptr);
+  }
+}
+__global__ void __launch_bounds__(128) sgrad_sum_kernel(const float* __restrict__ ds, const float* __restrict__ gscale_ptr, float* __restrict__ grad_row,
+                                                        int N, int cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cin) return;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) acc += ds[(long long)n * cin + i];
+  grad_row[i] += acc / __ldg(gscale_ptr);
 }
 
 // gscale = 2^k with amax(|g|) * gscale in (target/2, target]: keeps the fp16 gradient planes (and their lo halves) in the
@@ -1553,12 +1558,13 @@ static int g_fir_act3 = 3;   // 0: keep the older marching kernel; 2 / 3 / 4: fi
 static int g_fir_bwd3 = 1;   // same for smc_fir_bwd (key 1)
 static int g_act_bwd2 = 1;   // same for smc_act_bwd (key 2)
 
-namespace smc { extern int g_upfirdn_rows; extern int g_resample_vfirst; extern int g_attention_tiled; }   // upfirdn2d.cu, vit.cu
+namespace smc { extern int g_upfirdn_rows; extern int g_resample_vfirst; extern int g_attention_tiled; extern int g_resample_rows; }   // upfirdn2d.cu, vit.cu
 
 extern "C" int smc_synth_config(int key, int value) {
   if (key == 3) { smc::g_upfirdn_rows = value; return SMC_OK; }
   if (key == 4) { smc::g_resample_vfirst = value; return SMC_OK; }
   if (key == 5) { smc::g_attention_tiled = value; return SMC_OK; }
+  if (key == 6) { smc::g_resample_rows = value; return SMC_OK; }
   if (key == 0) g_fir_act3 = value;
   else if (key == 1) g_fir_bwd3 = value;
   else if (key == 2) g_act_bwd2 = value;
@@ -1812,11 +1818,14 @@ extern "C" int smc_fir_bwd(const void* gd, const void* gd_lo, int n, int h, int 
   return SMC_OK;
 }
 
-extern "C" int smc_sgrad_finish(const float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
+extern "C" int smc_sgrad_finish(float* t1, const float* r, const float* q, const float* d, const float* s, int64_t s_stride,
                                 const float* gscale, float* grad_row, int n, int cin, int cout, float* grad_samples, int64_t gs_stride, void* stream) {
   if (!t1 || !r || !q || !d || !s || !gscale || !grad_row || n < 1 || cin < 1 || cout < 1) return SMC_EINVAL;
-  sgrad_finish_kernel<<<ceil_div(cin, 32), 256, (cout + 256) * sizeof(float), (cudaStream_t)stream>>>(t1, r, q, d, s, s_stride, gscale, grad_row, n, cin, cout,
-                                                                                                     grad_samples, gs_stride);
+  if (n > 65535) return SMC_ETOOLARGE;
+  sgrad_sample_kernel<<<dim3(ceil_div(cin, 32), n), 256, (cout + 256) * sizeof(float), (cudaStream_t)stream>>>(t1, r, q, d, s, s_stride, gscale, cin, cout,
+                                                                                                               grad_samples, gs_stride);
+  SMC_LAUNCH_CHECK();
+  sgrad_sum_kernel<<<ceil_div(cin, 128), 128, 0, (cudaStream_t)stream>>>(t1, gscale, grad_row, n, cin);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

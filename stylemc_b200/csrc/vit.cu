@@ -166,6 +166,81 @@ __global__ void __launch_bounds__(256) resample_hT_kernel(const float* __restric
   }
 }
 
+// Row-contraction pass with the lanes of a warp on 32 different ROWS (round 2; replaces resample_h_kernel in the forward pass and resample_hT_kernel
+// in the backward pass, which spent ~2 global loads per tap and output: 13-18 % of the HBM peak, LSU-bound).  One CTA owns 32 rows x OBT
+// outputs: the input columns those outputs read ([start[ob0], start[last] + count[last]): at most max_span) are loaded once, coalesced along
+// the row, into a shared tile with an odd pitch (pre-processing applied on the way in); warp w then computes outputs ob0 + w, w + 8, ...
+// with lane = row: the tile reads are conflict-free, the tap weights are warp-uniform loads; the results go through a second shared tile
+// so that the global stores are runs of OBT consecutive floats.  Accumulation order per output = the per-thread loop of the old kernels.
+//   out[r, ob] = post( sum_k wgt[ob * taps + k] * pre(in[r, start[ob * sstride] + k]) )
+// pre: 0 none, 1 clamp(v * 127.5 + 128, 0, 255) (find_direction.py:50), 2 v * 0.5 + 0.5 (clip_loss_nada.py:86-87)
+// post: 0 none, 1 * k127 where 0 < xmask * 127.5 + 128 < 255, else 0 (clamp backward), 2 * k127; k127 = (post == 2 ? 0.5 : 127.5) / unscale
+template <int OBT>
+__global__ void __launch_bounds__(256) resample_rows_kernel(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ start,
+                                                            int sstride, const int* __restrict__ count, const float* __restrict__ wgt, int taps,
+                                                            long long rows, int in_w, int out_w, int max_span, int pre, int post,
+                                                            const float* __restrict__ xmask, const float* __restrict__ unscale) {
+  extern __shared__ float rr_smem[];
+  const int pitch = max_span | 1;
+  float* tile = rr_smem;                      // [32][pitch]
+  float* stage = rr_smem + 32 * pitch;        // [32][OBT + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int ob0 = blockIdx.y * OBT;
+  const int obl = (ob0 + OBT < out_w ? ob0 + OBT : out_w) - 1;
+  const int c0 = __ldg(start + (long long)ob0 * sstride);
+  const int span = __ldg(start + (long long)obl * sstride) + __ldg(count + obl) - c0;
+  if (span > max_span || c0 + span > in_w) __trap();     // tables that are not monotone windows: fail loudly
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp + 8 * rr;
+    const long long row = r0 + r;
+    const float* src = in + row * in_w + c0;
+    for (int c = lane; c < span; c += 32) {
+      float v = 0.f;
+      if (row < rows) {
+        v = __ldg(src + c);
+        if (pre == 1) v = fminf(fmaxf(v * 127.5f + 128.f, 0.f), 255.f);
+        else if (pre == 2) v = fmaf(v, 0.5f, 0.5f);
+      }
+      tile[r * pitch + c] = v;
+    }
+  }
+  __syncthreads();
+  for (int j = warp; j < OBT; j += 8) {
+    const int ob = ob0 + j;
+    float acc = 0.f;
+    if (ob < out_w) {
+      const int cnt = __ldg(count + ob);
+      const float* w = wgt + (long long)ob * taps;
+      const float* t = tile + lane * pitch + (__ldg(start + (long long)ob * sstride) - c0);
+      for (int k = 0; k < cnt; ++k) acc += __ldg(w + k) * t[k];
+    }
+    stage[lane * (OBT + 1) + j] = acc;
+  }
+  __syncthreads();
+  const float k127 = post ? (post == 2 ? 0.5f : 127.5f) / (unscale ? __ldg(unscale) : 1.f) : 1.f;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp + 8 * rr;
+    const long long row = r0 + r;
+    if (row >= rows) continue;
+    for (int j = lane; j < OBT; j += 32) {
+      const int ob = ob0 + j;
+      if (ob >= out_w) break;
+      float v = stage[r * (OBT + 1) + j];
+      const long long oi = row * out_w + ob;
+      if (post == 1) {
+        const float xv = __ldg(xmask + oi) * 127.5f + 128.f;
+        v = (xv > 0.f && xv < 255.f) ? v * k127 : 0.f;
+      } else if (post == 2) {
+        v *= k127;
+      }
+      out[oi] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // [B,3,224,224] fp32 -> patch matrix [B*49, 3072] fp16 (row = b*49 + py*7 + px, col = c*1024 + ky*32 + kx):
 // the im2col of clip/model.py `conv1` (kernel = stride = 32), and its transpose for the backward.
@@ -1120,6 +1195,24 @@ static int grid1d(long long items) {
   return b < 1 ? 1 : (int)b;
 }
 
+int g_resample_rows = 1;     // smc_synth_config key 6: the row-tile kernel for the row-contraction passes of unprocess (0: the per-output kernels)
+
+// resample_rows_kernel when its shared-memory tiles fit; false = not launched (the caller falls back to the per-output kernel)
+template <int OBT>
+static bool resample_rows_launch(const float* in, float* out, const int* start, int sstride, const int* count, const float* wgt, int taps, long long rows,
+                                 int in_w, int out_w, int pre, int post, const float* xmask, const float* unscale, cudaStream_t st) {
+  if (!g_resample_rows) return false;
+  // OBT consecutive windows: the starts move by at most ceil((OBT - 1) * in / out) + 1, a window has at most `taps` entries
+  long long span = ((long long)(OBT - 1) * in_w + out_w - 1) / out_w + taps + 2;
+  if (span > in_w) span = in_w;
+  const size_t smem = ((size_t)32 * ((size_t)span | 1) + (size_t)32 * (OBT + 1)) * sizeof(float);
+  const long long row_tiles = ceil_div_ll(rows, 32);
+  if (smem > 48 * 1024 || row_tiles > 0x7fffffffLL || ceil_div(out_w, OBT) > 65535) return false;
+  resample_rows_kernel<OBT><<<dim3((unsigned)row_tiles, (unsigned)ceil_div(out_w, OBT)), 256, smem, st>>>(in, out, start, sstride, count, wgt, taps, rows, in_w,
+                                                                                                          out_w, (int)span, pre, post, xmask, unscale);
+  return true;
+}
+
 }  // namespace smc
 
 using namespace smc;
@@ -1153,8 +1246,9 @@ extern "C" int smc_resample_fwd(const float* x, float* tmp, float* y, const int*
     }
   }
   const long long rows = (long long)planes * in_size;
-  resample_h_kernel<<<grid1d(rows * out_size), 256, 0, ST>>>(x, tmp, start, count, wgt, taps, rows, in_size, out_size, denorm_normalize, 0, 1.f, 0.f,
-                                                             0.f, 0.f, 1.f, 1.f, 1.f);
+  if (!resample_rows_launch<32>(x, tmp, start, 1, count, wgt, taps, rows, in_size, out_size, denorm_normalize, 0, nullptr, nullptr, ST))
+    resample_h_kernel<<<grid1d(rows * out_size), 256, 0, ST>>>(x, tmp, start, count, wgt, taps, rows, in_size, out_size, denorm_normalize, 0, 1.f, 0.f,
+                                                               0.f, 0.f, 1.f, 1.f, 1.f);
   resample_v_kernel<<<grid1d((long long)planes * out_size * out_size), 256, 0, ST>>>(tmp, y, start, count, wgt, taps, planes, in_size, out_size,
                                                                                       out_size, denorm_normalize == 2 ? 1.f : 1.f / 255.f, m[0], m[1], m[2],
                                                                                       s[0], s[1], s[2], denorm_normalize);
@@ -1178,7 +1272,9 @@ extern "C" int smc_resample_bwd(const float* g, const float* x, float* tmp, floa
   resample_vT_kernel<<<grid1d((long long)planes * in_size * out_size), 256, 0, ST>>>(g, tmp, oidx, count, wgt, taps, planes, in_size, out_size,
                                                                                       out_size, std3[0], std3[1], std3[2], nullptr, nullptr, mode);
   const long long rows = (long long)planes * in_size;
-  resample_hT_kernel<<<grid1d(rows * in_size), 256, 0, ST>>>(tmp, x, gx, oidx, count, wgt, taps, rows, in_size, out_size, unscale, mode);
+  // (the rows of oidx are runs of consecutive output indices -- the transpose of monotone windows: only oidx[ix * taps] is read)
+  if (!resample_rows_launch<128>(tmp, gx, oidx, taps, count, wgt, taps, rows, out_size, in_size, 0, mode == 2 ? 2 : 1, x, unscale, ST))
+    resample_hT_kernel<<<grid1d(rows * in_size), 256, 0, ST>>>(tmp, x, gx, oidx, count, wgt, taps, rows, in_size, out_size, unscale, mode);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

@@ -303,7 +303,8 @@ class DirectionFinder:
                     self._id_part += part_id
             with _phase('synthesis_bwd'):
                 if per_sample:
-                    g_sum, g_each = eng.backward(saved, g_img, self.rows, self.noise_mode, per_sample=True)
+                    g_sum, g_each = eng.backward(saved, g_img, self.rows, self.noise_mode, per_sample=True,
+                                                  grad_lo=os.environ.get('STYLEMC_MAPPER_GRAD_LO', '1') != '0')
                     grad += g_sum
                     samples.append(g_each)
                 else:

@@ -4,7 +4,7 @@
 then 5 x [Linear(512, 512) -> LayerNorm([4, 512], no affine) -> LeakyReLU]); ``train_latent_mapper.py`` optimises its weights with Adam under the
 find_direction objective.  Here the synthesis + CLIP (+ identity) passes are the fused engines of ``DirectionFinder`` asked for the PER-SAMPLE style
 gradient (``SynthesisEngine.backward(per_sample=True)``), and the mapper itself is an op-level network with hand-written backward passes: the
-linears (forward, input gradient AND weight gradient -- the only trainable weights on this path) on ``smc_igemm``, PixelNorm on ``smc_pixelnorm``,
+linears (forward, input gradient AND weight gradient -- the only trainable weights on this path) on ``smc_matmul_nt_f64acc``, PixelNorm on ``smc_pixelnorm``,
 LayerNorm on ``smc_layernorm_fwd / bwd``, LeakyReLU on ``smc_bias_act``, Adam on ``smc_adam_step``.  Parameter names are the reference's
 ``state_dict`` keys (``torch.save(mapper.state_dict(), ...)``, train_latent_mapper.py:183,206), so checkpoints move both ways.
 """
@@ -12,36 +12,20 @@ import math
 
 import torch
 
-from . import _lib, direction, gemm
+from . import _lib, direction
 from .ops import bias_act
 
 ROWS, WIDTH, LAYERS = 4, 512, 5            # SubMapperModulation(layernum=4), five ModulationModules (latent_mappers.py:34-39)
 
 
-def _planes(x):
-    """fp32 [rows, k] -> hi / lo fp16 planes [2, rows, k] (``smc_split_rows``)."""
-    rows, k = x.shape
-    p = torch.empty([2, rows, k], dtype=torch.float16, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.call('smc_split_rows', _lib.ptr(x), _lib.ptr(p[0]), _lib.ptr(p[1]), rows, k, rows, 0, 0, _lib.stream())
-    return p
-
-
-def _gemm_nt(a, b, bias=None):
-    """a [m, k] @ b[n, k].T (+ bias[n]) in split precision; k is padded to a multiple of 32 with zeros."""
-    m, k = a.shape
-    n = b.shape[0]
-    kp, npad = -(-k // 32) * 32, -(-n // 32) * 32
-    if kp != k:
-        a, b = torch.nn.functional.pad(a, (0, kp - k)), torch.nn.functional.pad(b, (0, kp - k))
-    B, _, _, inv = gemm.prepare_weights(b.contiguous(), two=True, prescale=True, pad_to=32)
-    ka = gemm.pow2_prescale(a)               # gradients of 1e-5 would sit in fp16's subnormals: both operands carry a power-of-two scale
-    out = torch.empty([m, npad], dtype=torch.float32, device=a.device)
-    if bias is not None and npad != n:
-        bias = torch.nn.functional.pad(bias, (0, npad - n))
-    gemm.igemm(_planes((a * ka).contiguous()).reshape(-1, 1, m, kp), B, 1, 1, m, npad, gemm.TAPS_1X1, precision='x3', a_plane_stride_imgs=1,
-               b_rows_per_tap=npad, bias=bias, out_f32=out, acc_scale=inv / ka, acc_chunk_k=512)
-    return out[:, :n] if npad != n else out
+def _matmul_nt(a, sa, b, sb, m, n, k, bias=None):
+    """y[m, n] = sum_k a[m * sa[0] + k * sa[1]] * b[n * sb[0] + k * sb[1]] (+ bias[n]) on ``smc_matmul_nt_f64acc`` (fp32 operands, float64
+    accumulation).  Not the tensor-core GEMM: the output of these layers becomes the per-image delta S, and the synthesis gradient moves by 8e-4
+    when delta is perturbed by 5e-6 (leaky-ReLU slope flips; measured with the float64 oracle) -- the split-fp16 GEMM's 1e-6 is too coarse."""
+    y = torch.empty([m, n], dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call('smc_matmul_nt_f64acc', _lib.ptr(a), sa[0], sa[1], _lib.ptr(b), sb[0], sb[1], _lib.ptr(bias), _lib.ptr(y), m, n, k, _lib.stream())
+    return y
 
 
 class _LinearFn(torch.autograd.Function):
@@ -49,17 +33,20 @@ class _LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
+        x, w = x.contiguous(), w.contiguous()
         ctx.save_for_backward(x, w)
-        return _gemm_nt(x, w, b)
+        r, i = x.shape
+        return _matmul_nt(x, (i, 1), w, (i, 1), r, w.shape[0], i, b.contiguous())
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = _gemm_nt(dy, w.t().contiguous())                        # dy [r, o] @ W [o, i]
-        dw = _gemm_nt(dy.t().contiguous(), x.t().contiguous())       # dy^T [o, r] @ x [r, i]: contraction over the rows
+        (r, i), o = x.shape, w.shape[0]
+        dx = _matmul_nt(dy, (o, 1), w, (1, i), r, i, o)              # dx[r, i] = sum_o dy[r, o] W[o, i]
+        dw = _matmul_nt(dy, (1, o), x, (1, i), o, i, r)              # dW[o, i] = sum_r dy[r, o] x[r, i]
         from .ops.fma import _reduce_to
-        db = _reduce_to(dy, None, torch.Size([1, dy.shape[1]])).reshape(-1)
+        db = _reduce_to(dy, None, torch.Size([1, o])).reshape(-1)
         return dx, dw, db
 
 

@@ -65,6 +65,8 @@ def transpose_tables(start, count, wgt, in_size):
         cnt[i] = len(l)
         for k, (o, v) in enumerate(l):
             oidx[i, k], w[i, k] = o, v
+        # the kernels read oidx[i, 0] only: the outputs that read one input are consecutive (monotone windows)
+        assert all(o == l[0][0] + k for k, (o, _) in enumerate(l))
     return oidx, cnt, w, taps
 
 

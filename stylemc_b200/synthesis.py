@@ -168,6 +168,13 @@ class SynthesisEngine:
         _lib.call('smc_demod_coefs', _lib.ptr(layer.q), sp, ss, _lib.ptr(d), n, layer.cin, layer.cout, _lib.stream())
         return d
 
+    @staticmethod
+    def _masked_grgb(g_img, rgb_pass, gscale):
+        """g_img * rgb_pass * gscale in one kernel: the incoming image gradient under the ToRGB clamp mask of the forward pass, loss-scaled."""
+        out = torch.empty_like(g_img)
+        _lib.call('smc_mask_scale', _lib.ptr(g_img), _lib.ptr(rgb_pass), _lib.ptr(gscale), _lib.ptr(out), g_img.numel(), _lib.stream())
+        return out
+
     def _planes(self, n, h, w, c, two):
         return torch.empty([2 if two else 1, n, h, w, c], dtype=torch.float16, device=self.device)
 
@@ -327,15 +334,17 @@ class SynthesisEngine:
         return xs_list, img, saved
 
     # ---- backward ------------------------------------------------------------------------------
-    def backward(self, saved, g_img, trainable_rows, noise_mode='const', grad_scale_target=256.0, per_sample=False):
+    def backward(self, saved, g_img, trainable_rows, noise_mode='const', grad_scale_target=256.0, per_sample=False, grad_lo=None):
         """Gradient of a scalar loss w.r.t. the trainable S rows, summed over the batch.
 
         saved: SavedForward of the pass that produced img; g_img = dL/dimg [N, 3, R, R] fp32.
         Returns grad [len(trainable_rows), 512] fp32 (zero beyond each layer's channel count), i.e. exactly
         ``delta.grad`` of find_direction.py:336 for delta broadcast over the batch (:307-308).  ``per_sample=True`` returns
         ``(grad, grad_samples [N, len(trainable_rows), 512])``: the gradient w.r.t. each image's own S rows (the latent mapper's delta differs
-        per image, train_latent_mapper.py:155-158)."""
+        per image, train_latent_mapper.py:155-158).  ``grad_lo`` overrides the engine's choice of gradient planes (hi only / hi + lo) for this
+        pass: a per-sample gradient has no batch sum for the rounding of a single fp16 plane to average out in."""
         styles, last = saved.styles, saved.until_k
+        use_grad_lo = self.grad_lo if grad_lo is None else bool(grad_lo)
         n = styles.shape[0]
         dev = self.device
         trainable_rows = list(trainable_rows)
@@ -378,7 +387,7 @@ class SynthesisEngine:
                 two = prec == 'x3'             # split-precision backward for the blocks whose forward was split-precision
                 # gradient operands: the weights keep both planes; the activation gradients (loss-scaled, zero-mean rounding that averages
                 # out in the style-gradient sums) carry a lo plane only when asked to (2 MMAs per product, not 3)
-                gtwo = two and self.grad_lo
+                gtwo = two and use_grad_lo
                 gprec = prec if (gtwo or not two) else self.bwd_prec
                 stop_here = (k < lowest_k)       # below the lowest trainable block only T1 of the consumer is needed
                 # ---- conv1 output: consumers are ToRGB (g_img) and the next block's conv0 (g_up)
@@ -398,7 +407,7 @@ class SynthesisEngine:
                     if need_gd and g_up is None and t1 is None and rr is None and k in saved.rgb_pass and self.fuse_act_bwd:
                         # top block, no reduction wanted: the ToRGB clamp mask saved by the forward pass and the loss scale go into the
                         # incoming gradient, so the kernel neither recomputes the ToRGB output nor reads the lo plane of y1
-                        gi, rgb_clamp, gs = (g_img * saved.rgb_pass[k]) * gscale, -1.0, None
+                        gi, rgb_clamp, gs = self._masked_grgb(g_img, saved.rgb_pass[k], gscale), -1.0, None
                     _lib.call('smc_act_bwd', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if y1.shape[0] == 2 else None, n, res, res, L1.cout,
                               _lib.ptr(g_up), int(up_f32), sp, ss, _lib.ptr(gi), _lib.ptr(T.w), stp, sts, T.wgain,
                               _lib.ptr(T.bias), rgb_clamp, _lib.ptr(gs), _lib.ptr(d1), _lib.ptr(noise1), _lib.ptr(L1.bias), LRELU_ALPHA,
@@ -451,7 +460,7 @@ class SynthesisEngine:
                     # the block below needs no style-gradient reduction either: its conv1 activation backward, ToRGB branch included
                     # (g_rgb masked by the clamp mask saved in the forward pass), is the epilogue of this dgrad GEMM
                     y1p, d1p = saved.y1[k - 1], saved.d1[k - 1]
-                    grgb = (g_img * saved.rgb_pass[k - 1]) * gscale
+                    grgb = self._masked_grgb(g_img, saved.rgb_pass[k - 1], gscale)
                     post = (styles[:, r0, :L0.cin] * d1p).contiguous()
                     rgbw = ((styles[:, prt, :Lp.cout] * Tp.wgain * d1p).unsqueeze(1) * Tp.w.unsqueeze(0)).contiguous()      # [n, 3, C]
                     gd1_fused = self._planes(n, hin, hin, Lp.cout, gtwo)

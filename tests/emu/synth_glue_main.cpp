@@ -40,20 +40,26 @@ static int test_demod_and_sgrad() {
   std::vector<float> grad = rnd(cin);
   const std::vector<float> grad0 = grad;
   const float gscale = 8.0f;
-  emu_launch(ceil_div(cin, 32), 256, (cout + 256) * sizeof(float),
-             [&] { sgrad_finish_kernel(T1.data(), R.data(), q.data(), d.data(), s.data(), s_stride, &gscale, grad.data(), N, cin, cout); });
+  // launched as smc_sgrad_finish does: per-sample kernel on grid (ceil(cin / 32), N), which overwrites T1 with ds, then the ordered sum over n
+  const std::vector<float> T1in = T1;
+  std::vector<float> each((size_t)N * 80, NAN);
+  emu_launch(dim3(ceil_div(cin, 32), N), 256, (cout + 256) * sizeof(float),
+             [&] { sgrad_sample_kernel(T1.data(), R.data(), q.data(), d.data(), s.data(), s_stride, &gscale, cin, cout, each.data(), 80); });
+  emu_launch(ceil_div(cin, 128), 128, 0, [&] { sgrad_sum_kernel(T1.data(), &gscale, grad.data(), N, cin); });
   double e2 = 0, m2 = 0;
   for (int i = 0; i < cin; ++i) {
     double acc = 0;
     for (int n = 0; n < N; ++n) {
       double t = 0;
       for (int o = 0; o < cout; ++o) t += (double)q[(size_t)o * cin + i] * d[(size_t)n * cout + o] * d[(size_t)n * cout + o] * R[(size_t)n * cout + o];
-      acc += T1[(size_t)n * cin + i] - s[(size_t)n * s_stride + i] * t;
+      const double ds = T1in[(size_t)n * cin + i] - s[(size_t)n * s_stride + i] * t;
+      e2 = std::max(e2, std::fabs(each[(size_t)n * 80 + i] - ds / gscale));      // the per-sample gradient (latent mapper)
+      acc += ds;
     }
     const double want = grad0[i] + acc / gscale;
     e2 = std::max(e2, std::fabs(grad[i] - want)); m2 = std::max(m2, std::fabs(want));
   }
-  return report("demod_kernel", e1, m1, 2e-6) + report("sgrad_finish_kernel", e2, m2, 4e-6);
+  return report("demod_kernel", e1, m1, 2e-6) + report("sgrad_sample/sum_kernel", e2, m2, 4e-6);
 }
 
 static int test_transposes() {

@@ -29,7 +29,7 @@ GLUE_KERNELS = ['layernorm_fwd_kernel', 'layernorm_bwd_kernel', 'quickgelu_fwd_k
                 'head_proj_bwd_kernel', 'clip_loss_kernel']
 
 
-SYNTH_KERNELS = ['demod_kernel', 'pack_nhwc_kernel', ('unpack_nchw_kernel', 'template <class T>'), 'sgrad_finish_kernel']
+SYNTH_KERNELS = ['demod_kernel', 'pack_nhwc_kernel', ('unpack_nchw_kernel', 'template <class T>'), 'sgrad_sample_kernel', 'sgrad_sum_kernel']
 
 
 def extract(cu, common_cuh, kernels=KERNELS, host_functions=('attention_block_rows',)):
@@ -129,7 +129,7 @@ def test_fir_bwd3_kernel_on_the_cpu_shim(tmp_path, sanitizer):
     assert out.count('ok  ') == 3
 
 
-RESAMPLE_KERNELS = ['resample_h_kernel', 'resample_v_kernel', 'resample_vT_kernel', 'resample_hT_kernel']
+RESAMPLE_KERNELS = ['resample_h_kernel', 'resample_v_kernel', 'resample_vT_kernel', 'resample_hT_kernel', ('resample_rows_kernel', 'template <int OBT>')]
 
 
 @pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')

@@ -55,7 +55,9 @@ def test_mapper_forward_and_param_grads_vs_oracle(golden):
     delta = m(x.cuda())
     err = (delta.detach().cpu() - T(g['delta'])).abs().max().item()
     print('mapper forward max-abs err', err)
-    assert err <= 1e-4                                                   # outputs are O(1) (LayerNorm then LeakyReLU)
+    # outputs are O(1) (LayerNorm then LeakyReLU).  The bar is tight on purpose: delta is added to S, and a 5e-6 error in it moves the
+    # synthesis gradient by 8e-4 (float64 oracle) -- the linears accumulate in float64 (smc_matmul_nt_f64acc)
+    assert err <= 2e-6
     r = torch.randn(delta.shape, generator=torch.Generator().manual_seed(6))
     delta.backward(r.cuda())
     pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
@@ -90,7 +92,9 @@ def test_mapper_step_golden(golden):
         assert abs(gr.norm().item() - n_ref) <= 2e-3 * n_ref, k
         if 'grad.' + k in g:
             ref = T(g['grad.' + k])
-            worst = max(worst, ((gr.cpu() - ref).norm() / ref.norm()).item())
+            err = ((gr.cpu() - ref).norm() / ref.norm()).item()
+            print(f'  {k}: rel-l2 {err:.2e}')
+            worst = max(worst, err)
     print('worst parameter-gradient rel-l2 vs the reference', worst)
     assert worst <= 1e-3
     # one Adam step moves every parameter by ~lr (first step: |update| = lr * g / (|g| + eps))
@@ -101,8 +105,10 @@ def test_mapper_step_golden(golden):
         assert 0.0 < d <= 1.001e-3, (k, d)
 
 
-def test_per_sample_gradient_sums_to_the_shared_one():
-    """SynthesisEngine.backward(per_sample=True): the per-image style gradients sum to the shared-delta gradient (find_direction.py:307-308)."""
+def test_per_sample_gradient_sums_to_the_shared_one(monkeypatch):
+    """SynthesisEngine.backward(per_sample=True): the per-image style gradients sum to the shared-delta gradient (find_direction.py:307-308):
+    to rounding when both passes use the same gradient planes, to the two-term split's error with the per-sample
+    default (hi + lo gradient planes: no batch sum for a single plane's rounding to average out in)."""
     from stylemc_b200 import clip, direction
     G = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)
     ws = torch.randn(3, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(21))
@@ -113,4 +119,7 @@ def test_per_sample_gradient_sums_to_the_shared_one():
     g_sum, _ = f.loss_and_grad(S.cuda(), 3)
     g_each, _ = f.loss_and_grad(S.cuda(), 3, per_sample=True)
     assert g_each.shape == (3, 8, 512)
+    assert ((g_each.sum(0) - g_sum).norm() / g_sum.norm()).item() <= 1e-3
+    monkeypatch.setenv('STYLEMC_MAPPER_GRAD_LO', '0')
+    g_each, _ = f.loss_and_grad(S.cuda(), 3, per_sample=True)
     assert ((g_each.sum(0) - g_sum).norm() / g_sum.norm()).item() <= 1e-5

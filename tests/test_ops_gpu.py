@@ -255,3 +255,16 @@ def test_conv2d_gradfix_entry_points_golden(golden):
     assert conv2d_gradfix.weight_gradients_disabled is False
     with pytest.raises(RuntimeError):
         conv2d_gradfix.conv2d(x, w, stride=2)
+
+
+def test_mask_scale_kernel():
+    """smc_mask_scale: g * mask * scale (the ToRGB clamp mask and the loss scale on the incoming image gradient) == the two ATen multiplies."""
+    from stylemc_b200 import _lib
+    gen = torch.Generator().manual_seed(11)
+    for shape in ((2, 3, 64, 64), (1, 3, 5, 7)):                       # vector path / scalar tail path
+        g = torch.randn(shape, generator=gen).cuda()
+        m = (torch.rand(shape, generator=gen) > 0.3).to(torch.uint8).cuda()
+        k = torch.tensor([64.0], device='cuda')
+        out = torch.empty_like(g)
+        _lib.call('smc_mask_scale', _lib.ptr(g), _lib.ptr(m), _lib.ptr(k), _lib.ptr(out), g.numel(), _lib.stream())
+        assert torch.equal(out, (g * m) * k)
