@@ -185,8 +185,11 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const float* __restr
   float* tile = rr_smem;                      // [32][pitch]
   float* stage = rr_smem + 32 * pitch;        // [32][OBT + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long r0 = (long long)blockIdx.x * 32;
-  const int ob0 = blockIdx.y * OBT;
+  // output tiles of one row tile are consecutive blocks: together they read whole rows (DRAM page locality; with the row tiles fastest
+  // every block fetched 32 isolated 0.6-KB segments and the forward pass ran at 1.3 TB/s)
+  const int n_obt = (out_w + OBT - 1) / OBT;
+  const long long r0 = (long long)(blockIdx.x / n_obt) * 32;
+  const int ob0 = (int)(blockIdx.x % n_obt) * OBT;
   const int obl = (ob0 + OBT < out_w ? ob0 + OBT : out_w) - 1;
   const int c0 = __ldg(start + (long long)ob0 * sstride);
   const int span = __ldg(start + (long long)obl * sstride) + __ldg(count + obl) - c0;
@@ -1206,9 +1209,9 @@ static bool resample_rows_launch(const float* in, float* out, const int* start, 
   long long span = ((long long)(OBT - 1) * in_w + out_w - 1) / out_w + taps + 2;
   if (span > in_w) span = in_w;
   const size_t smem = ((size_t)32 * ((size_t)span | 1) + (size_t)32 * (OBT + 1)) * sizeof(float);
-  const long long row_tiles = ceil_div_ll(rows, 32);
-  if (smem > 48 * 1024 || row_tiles > 0x7fffffffLL || ceil_div(out_w, OBT) > 65535) return false;
-  resample_rows_kernel<OBT><<<dim3((unsigned)row_tiles, (unsigned)ceil_div(out_w, OBT)), 256, smem, st>>>(in, out, start, sstride, count, wgt, taps, rows, in_w,
+  const long long blocks = ceil_div_ll(rows, 32) * ceil_div(out_w, OBT);
+  if (smem > 48 * 1024 || blocks > 0x7fffffffLL) return false;
+  resample_rows_kernel<OBT><<<(unsigned)blocks, 256, smem, st>>>(in, out, start, sstride, count, wgt, taps, rows, in_w,
                                                                                                           out_w, (int)span, pre, post, xmask, unscale);
   return true;
 }

@@ -14,7 +14,7 @@ template <int OBT, class F> static void rows_launch(long long rows, int in_w, in
   long long span = ((long long)(OBT - 1) * in_w + out_w - 1) / out_w + taps + 2;
   if (span > in_w) span = in_w;
   const size_t smem = ((size_t)32 * ((size_t)span | 1) + (size_t)32 * (OBT + 1)) * sizeof(float);
-  emu_launch(dim3((unsigned)((rows + 31) / 32), (unsigned)((out_w + OBT - 1) / OBT)), 256, smem, [&] { body((int)span); });
+  emu_launch((int)(((rows + 31) / 32) * ((out_w + OBT - 1) / OBT)), 256, smem, [&] { body((int)span); });
 }
 static int same(const std::vector<float>& a, const std::vector<float>& b, const char* what) {
   for (size_t i = 0; i < a.size(); ++i)
