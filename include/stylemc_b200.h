@@ -115,6 +115,9 @@ typedef struct smc_igemm_epilogue {
   // ToRGB branch of the same backward step (optional, with mask_y): v gets, before the activation slope,
   //   + sum_j rgb_w[n, j, o] * mask_grgb[n * rgb_sn + j * rgb_sj + h * rgb_sh + w]   (mask_grgb = masked, loss-scaled dL/drgb, fp32)
   const float* mask_grgb;
+  // Fused ToRGB over several N tiles (n_out > the kernel's N tile): N tile t adds into rgb_acc + t * rgb_snt (one partial-sum image per N
+  // tile, summed in index order by smc_img_finish: deterministic).  0: every N tile adds into the same image (sum order not fixed).
+  int64_t rgb_snt;
 } smc_igemm_epilogue;
 
 typedef struct smc_igemm_desc {
@@ -185,9 +188,10 @@ int smc_fir_act(const void* planes, int planes_is_half, int n, int h, int w, int
 /* img[n, j, y, x] = clamp(img[n, j, y, x] + b[j]) + upsample2d(img_prev)[n, j, y, x]   (in place; img holds the fused-ToRGB sums of
  * smc_igemm's rgb_acc; ToRGBLayer bias/clamp and utils.py:45-49; img_prev [N, 3, H/2, W/2] or NULL for the first block).
  * pass_mask (optional, [N, 3, H, W] bytes): 1 where the clamp passes the gradient (|img + b| < clamp, bias_act.cu:136-142), kept for
- * the backward pass so that it need not recompute the ToRGB output. */
+ * the backward pass so that it need not recompute the ToRGB output.
+ * parts > 1: img + q * part_stride (q < parts) are the per-N-tile partial sums of smc_igemm_epilogue::rgb_snt; they are added first, in index order. */
 int smc_img_finish(float* img, const float* img_prev, const float* b_rgb, float clamp, const float* fk_up, int n, int h, int w,
-                   unsigned char* pass_mask, void* stream);
+                   unsigned char* pass_mask, int parts, int64_t part_stride, void* stream);
 int smc_torgb(const void* x_hi, const void* x_lo, int n, int h, int w, int c, const float* w_rgb, const float* s_t,
               int64_t st_stride, float wgain, const float* b_rgb, float clamp, const float* img_prev, const float* fk_up,
               float* img, const float* s_next, int64_t sn_stride, void* xs_hi, void* xs_lo, void* stream);

@@ -35,7 +35,7 @@ class Epilogue(ctypes.Structure):
                 ('acc_scale', ctypes.c_float),
                 ('out_raw_lo', ctypes.c_void_p), ('rgb_w', ctypes.c_void_p), ('rgb_acc', ctypes.c_void_p),
                 ('rgb_sn', ctypes.c_int64), ('rgb_sj', ctypes.c_int64), ('rgb_sh', ctypes.c_int64),
-                ('mask_y', ctypes.c_void_p), ('mask_y_lo', ctypes.c_void_p), ('mask_grgb', ctypes.c_void_p)]
+                ('mask_y', ctypes.c_void_p), ('mask_y_lo', ctypes.c_void_p), ('mask_grgb', ctypes.c_void_p), ('rgb_snt', ctypes.c_int64)]
 
 
 class IgemmDesc(ctypes.Structure):
@@ -79,7 +79,7 @@ SIGNATURES = {
     'smc_pack_nhwc': 'p q p q pp iiii p',
     'smc_unpack_nchw': 'p i pp iiii p',
     'smc_fir_act': 'p i iiii pppp fff p q pppp p',
-    'smc_img_finish': 'ppp f p iii pp',
+    'smc_img_finish': 'ppp f p iii p i q p',
     'smc_torgb': 'pp iiii pp q f p f ppp p q pp p',
     'smc_act_bwd': 'pp iiii p i p q ppp q f p f pppp fff pppp p',
     'smc_fir_bwd': 'pp iiii pppp p',

@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         }
         }   // generic epilogue
         if (e.rgb_acc) {
-          float* ra = e.rgb_acc + (long long)n * e.rgb_sn + (long long)h * e.rgb_sh + w;
+          float* ra = e.rgb_acc + (long long)tl.nt * e.rgb_snt + (long long)n * e.rgb_sn + (long long)h * e.rgb_sh + w;
           atomicAdd(ra, rgb0);
           atomicAdd(ra + e.rgb_sj, rgb1);
           atomicAdd(ra + 2 * e.rgb_sj, rgb2);

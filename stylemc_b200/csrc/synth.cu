@@ -679,16 +679,20 @@ __global__ void __launch_bounds__(256) fir_bwd2_kernel(const __half* __restrict_
 // ---------------------------------------------------------------------------------------------------
 // Tail of the fused ToRGB path (the conv1 epilogue of hconv.cu accumulated the 1x1 modulated conv into img):
 // img = clamp(img + b[j]) + upsample2d(img_prev)   (ToRGBLayer bias_act(clamp) [UPSTREAM]; utils.py:45-49).
+// parts > 1: the conv1 epilogue kept one partial-sum image per N tile of the GEMM (img + q * part_stride, q < parts); they are added here in index
+// order (deterministic), into plane 0.
 __global__ void __launch_bounds__(256) img_finish_kernel(float* __restrict__ img, const float* __restrict__ img_prev, const float* __restrict__ b_rgb,
                                                          float clamp, const float* __restrict__ fk_up, int N, int H, int W,
-                                                         unsigned char* __restrict__ pass_mask) {
+                                                         unsigned char* __restrict__ pass_mask, int parts = 1, long long part_stride = 0) {
   const long long total = (long long)N * 3 * H * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int xq = (int)(idx % W);
     const long long t = idx / W;
     const int yy = (int)(t % H);
     const long long nj = t / H;
-    float r = img[idx] + __ldg(b_rgb + (int)(nj % 3));
+    float r = img[idx];
+    for (int q = 1; q < parts; ++q) r += img[idx + q * part_stride];
+    r += __ldg(b_rgb + (int)(nj % 3));
     if (pass_mask) pass_mask[idx] = (clamp < 0.f || (r > -clamp && r < clamp)) ? 1 : 0;
     if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
     if (img_prev) {
@@ -1628,7 +1632,7 @@ extern "C" int smc_fir_act(const void* planes, int planes_is_half, int n, int h,
 // the previous image that the 4x4 up-sampling filter touches are loaded once.
 __global__ void __launch_bounds__(256) img_finish4_kernel(float* __restrict__ img, const float* __restrict__ img_prev, const float* __restrict__ b_rgb,
                                                           float clamp, const float* __restrict__ fk_up, int N, int H, int W,
-                                                          unsigned char* __restrict__ pass_mask) {
+                                                          unsigned char* __restrict__ pass_mask, int parts = 1, long long part_stride = 0) {
   const int wq = W >> 2;
   const long long total = (long long)N * 3 * H * wq;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -1638,6 +1642,10 @@ __global__ void __launch_bounds__(256) img_finish4_kernel(float* __restrict__ im
     const long long nj = t / H;
     float4* p4 = reinterpret_cast<float4*>(img + (nj * H + yy) * (long long)W) + q;
     float4 v = *p4;
+    for (int pq = 1; pq < parts; ++pq) {                 // partial sums of the other N tiles (part_stride is a multiple of 4 floats)
+      const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p4) + pq * part_stride);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
     const float b = __ldg(b_rgb + (int)(nj % 3));
     float r[4] = {v.x + b, v.y + b, v.z + b, v.w + b};
     if (pass_mask) {
@@ -1682,14 +1690,15 @@ __global__ void __launch_bounds__(256) img_finish4_kernel(float* __restrict__ im
 }
 
 extern "C" int smc_img_finish(float* img, const float* img_prev, const float* b_rgb, float clamp, const float* fk_up, int n, int h, int w,
-                              unsigned char* pass_mask, void* stream) {
-  if (!img || !b_rgb || n < 1 || h < 1 || w < 1) return SMC_EINVAL;
+                              unsigned char* pass_mask, int parts, int64_t part_stride, void* stream) {
+  if (!img || !b_rgb || n < 1 || h < 1 || w < 1 || parts < 1 || (parts > 1 && part_stride < (int64_t)n * 3 * h * w)) return SMC_EINVAL;
   if (img_prev && (!fk_up || (h & 1) || (w & 1))) return SMC_EINVAL;
-  if ((w & 3) == 0 && (((uintptr_t)img) & 15) == 0 && (((uintptr_t)pass_mask) & 3) == 0)
+  if ((w & 3) == 0 && (((uintptr_t)img) & 15) == 0 && (((uintptr_t)pass_mask) & 3) == 0 && (parts == 1 || (part_stride & 3) == 0))
     img_finish4_kernel<<<grid_for((long long)n * 3 * h * (w >> 2), 256), 256, 0, (cudaStream_t)stream>>>(img, img_prev, b_rgb, clamp, fk_up, n, h, w,
-                                                                                                        pass_mask);
+                                                                                                        pass_mask, parts, part_stride);
   else
-    img_finish_kernel<<<grid_for((long long)n * 3 * h * w, 256), 256, 0, (cudaStream_t)stream>>>(img, img_prev, b_rgb, clamp, fk_up, n, h, w, pass_mask);
+    img_finish_kernel<<<grid_for((long long)n * 3 * h * w, 256), 256, 0, (cudaStream_t)stream>>>(img, img_prev, b_rgb, clamp, fk_up, n, h, w, pass_mask,
+                                                                                                 parts, part_stride);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }

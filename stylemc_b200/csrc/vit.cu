@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) resample_hT_kernel(const float* __restric
 //   out[r, ob] = post( sum_k wgt[ob * taps + k] * pre(in[r, start[ob * sstride] + k]) )
 // pre: 0 none, 1 clamp(v * 127.5 + 128, 0, 255) (find_direction.py:50), 2 v * 0.5 + 0.5 (clip_loss_nada.py:86-87)
 // post: 0 none, 1 * k127 where 0 < xmask * 127.5 + 128 < 255, else 0 (clamp backward), 2 * k127; k127 = (post == 2 ? 0.5 : 127.5) / unscale
-template <int OBT>
+template <int OBT, int MAXT>   // MAXT >= taps: the tap loop is fully unrolled (predicated on the window length): 3 instructions per tap, no loop overhead
 __global__ void __launch_bounds__(256) resample_rows_kernel(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ start,
                                                             int sstride, const int* __restrict__ count, const float* __restrict__ wgt, int taps,
                                                             long long rows, int in_w, int out_w, int max_span, int pre, int post,
@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(256) resample_rows_kernel(const float* __restr
       const int cnt = __ldg(count + ob);
       const float* w = wgt + (long long)ob * taps;
       const float* t = tile + lane * pitch + (__ldg(start + (long long)ob * sstride) - c0);
-      for (int k = 0; k < cnt; ++k) acc += __ldg(w + k) * t[k];
+#pragma unroll
+      for (int k = 0; k < MAXT; ++k)
+        if (k < cnt) acc += __ldg(w + k) * t[k];            // cnt is warp-uniform; beyond it the tile holds nothing defined
     }
     stage[lane * (OBT + 1) + j] = acc;
   }
@@ -1211,8 +1213,14 @@ static bool resample_rows_launch(const float* in, float* out, const int* start, 
   const size_t smem = ((size_t)32 * ((size_t)span | 1) + (size_t)32 * (OBT + 1)) * sizeof(float);
   const long long blocks = ceil_div_ll(rows, 32) * ceil_div(out_w, OBT);
   if (smem > 48 * 1024 || blocks > 0x7fffffffLL) return false;
-  resample_rows_kernel<OBT><<<(unsigned)blocks, 256, smem, st>>>(in, out, start, sstride, count, wgt, taps, rows, in_w,
-                                                                                                          out_w, (int)span, pre, post, xmask, unscale);
+  if (taps <= 8)
+    resample_rows_kernel<OBT, 8><<<(unsigned)blocks, 256, smem, st>>>(in, out, start, sstride, count, wgt, taps, rows, in_w, out_w, (int)span, pre, post, xmask, unscale);
+  else if (taps <= 12)
+    resample_rows_kernel<OBT, 12><<<(unsigned)blocks, 256, smem, st>>>(in, out, start, sstride, count, wgt, taps, rows, in_w, out_w, (int)span, pre, post, xmask, unscale);
+  else if (taps <= 24)
+    resample_rows_kernel<OBT, 24><<<(unsigned)blocks, 256, smem, st>>>(in, out, start, sstride, count, wgt, taps, rows, in_w, out_w, (int)span, pre, post, xmask, unscale);
+  else
+    return false;
   return true;
 }
 

@@ -36,7 +36,7 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
           row_scale=None, post_scale=None, bias=None, noise=None, noise_strides=(0, 0), act=0, alpha=0.2, gain=1.0,
           clamp=-1.0, residual=None, out_f32=None, out_hi=None, out_lo=None, out_raw=None, out_strides=None, out_offset=0,
           tile=None, acc_scale=1.0, acc_chunk_k=0, out_raw_lo=None, rgb_w=None, rgb_acc=None, mask_y=None, mask_y_lo=None, mask_grgb=None,
-          problems=None):
+          problems=None, rgb_part_stride=0):
     """Launch one implicit GEMM.
 
     A: fp16 tensor viewed as [NA, HA, WA, C] (NA includes the hi/lo planes stacked on the image axis).
@@ -45,6 +45,7 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
     out_strides: (sn, sh, sw) element strides of the output; default dense NHWC [n_img, H, W, n_out].
     problems: optional [(ntaps, out_offset), ...] (2..4 entries): a problem group (smc_igemm_desc::nprob) -- ``taps`` is the concatenation of
        the problems' tap lists, problem q writes to ``out_offset + problems[q][1]`` (elements).  One launch, the input is read once.
+    rgb_part_stride: element stride between the per-N-tile partial-sum images of the fused ToRGB (smc_igemm_epilogue::rgb_snt); 0 = one image.
     mask_y (+ mask_y_lo): fused activation backward (smc_igemm_epilogue::mask_y): out = acc * post_scale * lrelu'(mask_y) * clamp mask,
        optionally + rgb_w . mask_grgb (fp32 NCHW [n_img, 3, H, W]) before the slope.
     """
@@ -87,9 +88,10 @@ def igemm(A, B, n_img, H, W, n_out, taps, precision='x1', a_plane_stride_imgs=No
     e.o_off = out_offset
     e.acc_scale = acc_scale
     e.out_raw_lo, e.rgb_w, e.rgb_acc = _lib.ptr(out_raw_lo), _lib.ptr(rgb_w), _lib.ptr(rgb_acc)
-    if rgb_acc is not None:          # NCHW fp32 [n_img, 3, H, W]
+    if rgb_acc is not None:          # NCHW fp32 [n_img, 3, H, W]; rgb_part_stride > 0: one such image per N tile of the kernel, that many elements apart
         assert rgb_acc.dtype == torch.float32 and rgb_acc.is_contiguous() and rgb_w is not None and rgb_w.is_contiguous()
         e.rgb_sn, e.rgb_sj, e.rgb_sh = rgb_acc.stride(0), rgb_acc.stride(1), rgb_acc.stride(2)
+        e.rgb_snt = rgb_part_stride
     e.mask_y, e.mask_y_lo, e.mask_grgb = _lib.ptr(mask_y), _lib.ptr(mask_y_lo), _lib.ptr(mask_grgb)
     if mask_grgb is not None:
         assert mask_grgb.dtype == torch.float32 and mask_grgb.is_contiguous() and rgb_w is not None and rgb_w.is_contiguous() and rgb_acc is None

@@ -119,6 +119,7 @@ class SynthesisEngine:
         self.fuse_torgb = os.environ.get('STYLEMC_HCONV') != '0'      # the fused epilogue exists in hconv.cu only
         self.group_parities = os.environ.get('STYLEMC_CONV0_GROUP') != '0'  # conv0: the four parity GEMMs as one problem-group launch
         self.fuse_act_bwd = os.environ.get('STYLEMC_FUSE_ACT_BWD') != '0'   # also needs fuse_torgb (both live in hconv.cu)
+        self.fuse_rgb_wide = os.environ.get('STYLEMC_FUSE_RGB_WIDE') != '0'  # fused ToRGB also for layers of several N tiles (cout > 128)
         # backward pass: hi + lo planes for the activation GRADIENTS too (3 MMAs per product) instead of a hi plane (2 MMAs); measured
         # identical style gradients to the 4th digit (tests/diag/diag_grad_planes.py), so off by default
         self.grad_lo = os.environ.get('STYLEMC_GRAD_LO', '0') != '0'
@@ -196,27 +197,36 @@ class SynthesisEngine:
         return y
 
     @staticmethod
-    def _fusable(L, res):
-        """conv1 layers that run on the halo-tile kernel (csrc/hconv.cu) with a single N tile (cout <= 128: every block from 256 px
-        up in config-f, where the bytes are) take ToRGB and the next style multiply in their epilogue.  With one N tile exactly two
-        threads add into each rgb value, so the atomic accumulation is order-independent (deterministic)."""
-        return res >= 32 and L.cin % 32 == 0 and L.cout % 32 == 0 and L.cout <= 128
+    def _rgb_parts(L):
+        """N tiles of the halo-tile kernel for this layer's forward conv (csrc/hconv.cu picks 128 / 64 / 32 by divisibility): the fused ToRGB
+        keeps one partial-sum image per N tile (two threads add into each value of it, so the atomic accumulation is order-independent),
+        and smc_img_finish adds the images in index order: deterministic whatever the channel count."""
+        bn = 128 if L.cout % 128 == 0 else (64 if L.cout % 64 == 0 else 32)
+        return L.cout // bn
+
+    def _fusable(self, L, res):
+        """conv1 layers that run on the halo-tile kernel (csrc/hconv.cu) take ToRGB and the next style multiply in their epilogue: every block
+        from 32 px up (round 1 / 2: only the single-N-tile layers from 256 px up; the 512 / 256-channel blocks ran smc_torgb, a separate
+        pass over y, and had no saved ToRGB clamp mask for the fused activation backward).  STYLEMC_FUSE_RGB_WIDE=0 restores that."""
+        return res >= 32 and L.cin % 32 == 0 and L.cout % 32 == 0 and (self.fuse_rgb_wide or L.cout <= 128)
 
     def _conv1_fused(self, L, T, xs, d, noise, styles, rt, row_next, n, res, prec, two, keep_y, next_two, y_full=True):
         """conv1 with everything that consumes its output fused into the GEMM epilogue: the saved activation y (hi/lo, only when
         it is needed), xs_next = y * styles[:, row_next] for the next block's conv0, and the ToRGB 1x1 modulated conv accumulated
-        into a zeroed fp32 image (finished by smc_img_finish).  Returns (y or None, xs_next or None, rgb accumulator)."""
+        into zeroed fp32 images, one per N tile of the kernel (summed and finished by smc_img_finish).  Returns (y or None, xs_next or None,
+        rgb accumulators [parts, n, 3, res, res])."""
         y = self._planes(n, res, res, L.cout, two and y_full) if keep_y else None
         xn = self._planes(n, res, res, L.cout, next_two) if row_next is not None else None
         post = styles[:, row_next, :L.cout].contiguous() if row_next is not None else None
         rgb_w = ((styles[:, rt, :L.cout] * T.wgain).unsqueeze(1) * T.w.unsqueeze(0)).contiguous()        # [n, 3, C]
-        acc = torch.zeros([n, 3, res, res], dtype=torch.float32, device=self.device)
+        parts = self._rgb_parts(L)
+        acc = torch.zeros([parts, n, 3, res, res], dtype=torch.float32, device=self.device)
         gemm.igemm(xs.reshape(-1, res, res, L.cin), L.B_fwd, n, res, res, L.cout, gemm.TAPS_3X3, precision=prec, acc_chunk_k=self._acc_k(res),
                    a_plane_stride_imgs=n, b_rows_per_tap=9 * L.cout, row_scale=d, bias=L.bias, noise=noise,
                    noise_strides=(res, 1), act=1, alpha=LRELU_ALPHA, gain=L.gain, clamp=L.clamp,
                    out_raw=y[0] if keep_y else None, out_raw_lo=y[1] if (keep_y and y.shape[0] == 2) else None,
                    post_scale=post, out_hi=xn[0] if xn is not None else None, out_lo=xn[1] if (xn is not None and next_two) else None,
-                   rgb_w=rgb_w, rgb_acc=acc)
+                   rgb_w=rgb_w, rgb_acc=acc[0], rgb_part_stride=acc.stride(0) if parts > 1 else 0)
         return y, xn, acc
 
     def _conv0(self, L, xs, d, noise, styles, row_next, n, hin, prec, want_lo, save_lo=False, save_full=True):
@@ -301,7 +311,8 @@ class SynthesisEngine:
                                                              (has_next and self.rows[k + 1][0] in grad_rows))
                     rgb_pass = torch.empty([n, 3, res, res], dtype=torch.uint8, device=self.device) if save else None
                     _lib.call('smc_img_finish', _lib.ptr(new_img), _lib.ptr(img), _lib.ptr(T.bias), T.clamp, _lib.ptr(self.fk4), n, res, res,
-                              _lib.ptr(rgb_pass), _lib.stream())
+                              _lib.ptr(rgb_pass), new_img.shape[0], new_img.stride(0), _lib.stream())
+                    new_img = new_img[0]                      # the partial sums of the N tiles were added into plane 0
                     if rgb_pass is not None:
                         saved.rgb_pass[k] = rgb_pass
                     xs = xs_next
@@ -404,9 +415,10 @@ class SynthesisEngine:
                     stp, sts = self._srow(styles, rt)
                     noise1 = self._noise(L1, noise_mode, n)
                     gi, rgb_clamp, gs = (g_img if need_gd else None), T.clamp, gscale
-                    if need_gd and g_up is None and t1 is None and rr is None and k in saved.rgb_pass and self.fuse_act_bwd:
-                        # top block, no reduction wanted: the ToRGB clamp mask saved by the forward pass and the loss scale go into the
-                        # incoming gradient, so the kernel neither recomputes the ToRGB output nor reads the lo plane of y1
+                    if need_gd and k in saved.rgb_pass and self.fuse_act_bwd and (self.fuse_rgb_wide or (g_up is None and t1 is None and rr is None)):
+                        # the ToRGB clamp mask saved by the forward pass and the loss scale go into the incoming gradient, so the kernel does
+                        # not recompute the ToRGB output (a second pass over y1); at the top block, where no reduction is wanted either, it
+                        # does not read the lo plane of y1 (smc_act_bwd picks act_bwd_rgb_kernel)
                         gi, rgb_clamp, gs = self._masked_grgb(g_img, saved.rgb_pass[k], gscale), -1.0, None
                     _lib.call('smc_act_bwd', _lib.ptr(y1[0]), _lib.ptr(y1[1]) if y1.shape[0] == 2 else None, n, res, res, L1.cout,
                               _lib.ptr(g_up), int(up_f32), sp, ss, _lib.ptr(gi), _lib.ptr(T.w), stp, sts, T.wgain,

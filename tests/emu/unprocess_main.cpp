@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
   // the row-tile kernel that replaces it by default (lanes on rows, shared-memory staged): must reproduce it bit for bit
   std::vector<float> tmp_r((size_t)planes * in * out, NAN);
   rows_launch<32>(rows, in, out, taps, [&](int span) {
-    resample_rows_kernel<32>(x.data(), tmp_r.data(), start.data(), 1, count.data(), wgt.data(), taps, rows, in, out, span, 1, 0, nullptr, nullptr);
+    resample_rows_kernel<32, 24>(x.data(), tmp_r.data(), start.data(), 1, count.data(), wgt.data(), taps, rows, in, out, span, 1, 0, nullptr, nullptr);
   });
   int bad = same(tmp_r, tmp, "resample_rows_kernel<32> (forward)");
   emu_launch(grid1d((long long)planes * out * out), 256, 0, [&] {
@@ -73,7 +73,7 @@ int main(int argc, char** argv) {
   });
   std::vector<float> gx_r((size_t)planes * in * in, NAN);
   rows_launch<128>(rows, out, in, taps_t, [&](int span) {
-    resample_rows_kernel<128>(tmp2.data(), gx_r.data(), oidx.data(), taps_t, count_t.data(), wgt_t.data(), taps_t, rows, out, in, span, 0, 1, x.data(), &unscale);
+    resample_rows_kernel<128, 8>(tmp2.data(), gx_r.data(), oidx.data(), taps_t, count_t.data(), wgt_t.data(), taps_t, rows, out, in, span, 0, 1, x.data(), &unscale);
   });
   bad += same(gx_r, gx, "resample_rows_kernel<128> (backward)");
   if (bad) return 5;

@@ -129,7 +129,7 @@ def test_fir_bwd3_kernel_on_the_cpu_shim(tmp_path, sanitizer):
     assert out.count('ok  ') == 3
 
 
-RESAMPLE_KERNELS = ['resample_h_kernel', 'resample_v_kernel', 'resample_vT_kernel', 'resample_hT_kernel', ('resample_rows_kernel', 'template <int OBT>')]
+RESAMPLE_KERNELS = ['resample_h_kernel', 'resample_v_kernel', 'resample_vT_kernel', 'resample_hT_kernel', ('resample_rows_kernel', 'template <int OBT, int MAXT>')]
 
 
 @pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')
@@ -209,7 +209,7 @@ def test_img_finish_kernels_on_the_cpu_shim(tmp_path, sanitizer):
     """The tail of the fused ToRGB path (csrc/synth.cu img_finish4_kernel / img_finish_kernel: bias, clamp + saved mask, skip-image
     upsample) against a float64 restatement; the kernel is picked as smc_img_finish picks it."""
     out = build_and_run(tmp_path, sanitizer, 'img_finish_main.cpp', ['img_finish_kernel', 'img_finish4_kernel'], (), source='synth.cu')
-    assert out.count('ok  ') == 4
+    assert out.count('ok  ') == 6
 
 
 @pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++')

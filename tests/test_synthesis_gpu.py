@@ -70,3 +70,33 @@ def test_style_gradient_vs_oracle_autograd(golden, precision, tol):
     rel = ((grad - ref).norm() / ref.norm()).item()
     print(f'{precision}: total grad rel-l2 err {rel:.3e}')
     assert rel <= tol
+
+
+def test_fused_torgb_over_several_n_tiles(monkeypatch):
+    """conv1 layers of 256 / 512 channels (2 / 4 N tiles of the halo-tile kernel) take ToRGB in their epilogue with one partial-sum image per
+    N tile (smc_igemm_epilogue::rgb_snt, summed in index order by smc_img_finish): bit-identical from run to run, and equal to the separate
+    smc_torgb pass (STYLEMC_FUSE_RGB_WIDE=0) to fp32 rounding, forward and backward (saved ToRGB clamp mask instead of the recomputation)."""
+    from stylemc_b200 import synthesis
+    G = o_syn.make_generator(64, seed=3, channel_base=16384, channel_max=512)      # 32 px: 512 channels, 64 px: 256 channels
+    ws = torch.randn(3, G.synthesis.num_ws, 512, generator=torch.Generator().manual_seed(5))
+    S, _ = o_syn.get_styles(G, ws, o_syn.split_ws(G, ws))
+    S = S.cuda()
+    g_img = torch.randn(3, 3, 64, 64, generator=torch.Generator().manual_seed(6)).cuda()
+
+    def run(wide):
+        monkeypatch.setenv('STYLEMC_FUSE_RGB_WIDE', '1' if wide else '0')
+        eng = synthesis.SynthesisEngine(G, 'cuda', precision='x3p')
+        assert eng.fuse_rgb_wide == wide
+        _, img, saved = eng.forward(S, save=True, grad_rows=TRAINABLE)
+        assert (len(saved.rgb_pass) > 0) == wide        # 32 / 64 px blocks: fused (with a saved clamp mask) only in the wide mode
+        return img, eng.backward(saved, g_img, TRAINABLE)
+
+    img_a, grad_a = run(True)
+    img_b, grad_b = run(True)
+    assert torch.equal(img_a, img_b)                                      # (the style-gradient sums use float atomics: equal to rounding only)
+    assert ((grad_a - grad_b).norm() / grad_b.norm()).item() <= 1e-5
+    img_c, grad_c = run(False)
+    err = (img_a - img_c).abs().max().item()
+    rel = ((grad_a - grad_c).norm() / grad_c.norm()).item()
+    print(f'fused vs separate ToRGB: img max-abs diff {err:.2e}, style-gradient rel-l2 {rel:.2e}')
+    assert err <= 2e-5 and rel <= 1e-4
