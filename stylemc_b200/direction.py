@@ -170,6 +170,7 @@ class DirectionFinder:
                  trainable_rows=S_TRAINABLE_SPACE_CHANNELS, original_precision=None, clip_loss_type='default', id_loss=None,
                  identity_loss_coef=0.0):
         self.device = torch.device(device)
+        self._src_cache = {}                 # (source_key, first row, rows) -> CLIP embeddings of the un-edited images (loss_and_grad)
         self.engine = utils.engine_for(G, self.device, precision)
         # the original-image branch carries no gradient (find_direction.py:312); it may run in another engine mode (diagnostics:
         # tests/diag/diag_original_branch.py measures what that does to the loss and the gradient).  Default: the same engine.
@@ -245,11 +246,16 @@ class DirectionFinder:
     def _use_id(self):
         return getattr(self, 'id_loss', None) is not None and self.identity_loss_coef != 0.0
 
-    def loss_and_grad(self, styles, global_count=None, styles_edit=None, per_sample=False):
+    def loss_and_grad(self, styles, global_count=None, styles_edit=None, per_sample=False, source_key=None):
         """styles [n, 26, 512] (this rank's shard, device) -> (grad [8, 512] summed over the shard, clip-loss partial sum).
         ``global_count`` is the number of seeds in the whole step (all ranks); the CLIP loss is their mean (clip_loss.py:34).
         ``styles_edit`` (optional [n, 26, 512]): the edited S of every image instead of ``styles + direction()`` (the latent mapper's delta
-        differs per image); ``per_sample=True`` returns the gradient w.r.t. each image's own trainable rows, [n, 8, 512]."""
+        differs per image); ``per_sample=True`` returns the gradient w.r.t. each image's own trainable rows, [n, 8, 512].
+        ``source_key`` (hashable, optional): names this batch of styles.  The CLIP embedding of the un-edited images depends on the styles
+        only, never on delta, and the reference loop draws the same batches again and again (find_direction.py:303-304 over n_epochs): the
+        first step that sees a key keeps the embeddings (512 floats per image and tower), later steps with that key skip the whole
+        original-image branch (a third of a step).  The caller guarantees that a key always comes with the same styles.  Not used with the
+        identity term (it needs the original IMAGE) and never by bench.py (a step there does all of its work)."""
         n_total = styles.shape[0]
         count = n_total if global_count is None else global_count
         grad = torch.zeros([len(self.rows), synthesis.STYLE_WIDTH], dtype=torch.float32, device=self.device)
@@ -265,7 +271,12 @@ class DirectionFinder:
             s = styles[lo:lo + self.micro_batch].to(self.device, torch.float32)
             s2 = s + direction if styles_edit is None else styles_edit[lo:lo + self.micro_batch].to(self.device, torch.float32)   # find_direction.py:308
             e_s = [None] * len(self.clips)
-            if self.overlap and need_src:
+            cache_key = (source_key, lo, s.shape[0]) if (source_key is not None and need_src and not self._use_id()) else None
+            cached = self._src_cache.get(cache_key) if cache_key is not None else None
+            need_run = need_src and cached is None
+            if cached is not None:
+                e_s = cached
+            if self.overlap and need_run:
                 cur = torch.cuda.current_stream(self.device)
                 if self._side is None:
                     self._side = torch.cuda.Stream(self.device)
@@ -277,16 +288,18 @@ class DirectionFinder:
                 _, img, saved = eng.forward(s2, self.until_k, self.noise_mode, save=True, grad_rows=self.rows)   # :309
             with _phase('unprocess_fwd'):
                 u_t = resample.unprocess_fwd(img, mode=pre)                                        # :159-160
-            if not self.overlap and need_src:
+            if not self.overlap and need_run:
                 e_s = self._encode_original(s)
             g224 = gscale = None
             for i, (model, loss_fn, weight) in enumerate(self.clips):
                 with _phase('clip_fwd'):
                     e_t, csaved = model.encode_image_fwd(u_t, save=True)
-                if self.overlap and need_src and i == 0:
+                if self.overlap and need_run and i == 0:
                     cur.wait_stream(self._side)
                     for e in e_s:
                         e.record_stream(cur)
+                if cache_key is not None and cached is None and i == 0:
+                    self._src_cache[cache_key] = e_s
                 part, d_t, gs = loss_fn.loss_and_grad(e_s[i], e_t, self.clip_loss_coef * weight, 1.0 / count)
                 with _phase('clip_bwd'):
                     g = model.encode_image_bwd(csaved, d_t)
@@ -344,15 +357,16 @@ class DirectionFinder:
         _lib.launch_count += launches            # kernels of this library inside the replayed graph (bench.py's gpu_launches claim)
         return out
 
-    def step(self, styles, lr=None, global_count=None):
-        """One optimisation step on this rank's shard.  Returns a dict of device scalars (loss, clip_loss, l2_loss, grad_norm)."""
+    def step(self, styles, lr=None, global_count=None, source_key=None):
+        """One optimisation step on this rank's shard.  Returns a dict of device scalars (loss, clip_loss, l2_loss, grad_norm).
+        ``source_key``: see ``loss_and_grad`` (skips the original-image branch for a batch of styles seen before)."""
         lr = self.lr if lr is None else lr
         if self.world > 1 and global_count is None:
             # shard sizes of the other ranks are unknown (ragged / empty shards): sum un-normalised, divide by the all-reduced count
-            grad, part = self.loss_and_grad(styles, 1)
+            grad, part = self.loss_and_grad(styles, 1, source_key=source_key)
             grad, part = allreduce_step(grad, part, self.group, local_rows=styles.shape[0])
         else:
-            grad, part = self.loss_and_grad(styles, styles.shape[0] if global_count is None else global_count)
+            grad, part = self.loss_and_grad(styles, styles.shape[0] if global_count is None else global_count, source_key=source_key)
             if self.world > 1:
                 grad, part = allreduce_step(grad, part, self.group)
         numel = self.delta.numel()
