@@ -203,3 +203,28 @@ def test_full_size_1024_properties():
     f = finder(G, 1024, micro_batch=4)
     _, img512, _ = f.engine.forward(S.cuda(), until_k=7)
     assert img512.shape == (4, 3, 512, 512)
+
+
+@pytest.mark.parametrize('overlap', [True, False])
+def test_original_branch_cache_gives_the_same_trajectory(golden, overlap):
+    """``step(source_key=...)``: the CLIP embedding of the un-edited images depends on the styles only (find_direction.py:311-312 runs it under
+    the same styles whenever a batch index recurs, :303-304), so later steps on a batch seen before skip the original-image branch.  Three steps
+    on two alternating batches with and without the cache: same losses, same delta; the branch runs once per batch."""
+    g = golden('step64')
+    G = o_syn.make_generator(64, seed=1, channel_base=2048, channel_max=512)
+    o_syn.get_temp_shapes(G)
+    styles = torch.as_tensor(g['styles']).cuda()
+    batches = [styles[:2], styles[1:3]]
+    runs = {}
+    for cached in (False, True):
+        f = finder(G, 64)
+        f.overlap = overlap
+        f.delta.copy_(torch.as_tensor(g['delta']).cuda())
+        calls = []
+        enc = f._encode_original
+        f._encode_original = lambda s, _enc=enc, _calls=calls: (_calls.append(1), _enc(s))[1]
+        losses = [f.step(batches[i % 2], lr=0.3, source_key=(i % 2) if cached else None)['loss'].item() for i in range(4)]
+        runs[cached] = (losses, f.delta.clone(), len(calls))
+    assert runs[False][2] == 4 and runs[True][2] == 2
+    assert max(abs(a - b) for a, b in zip(runs[False][0], runs[True][0])) <= 1e-6
+    assert ((runs[True][1] - runs[False][1]).norm() / runs[False][1].norm()).item() <= 1e-5
