@@ -95,7 +95,8 @@ def loop_worker(rank, world, port, outdir):
     f.delta = torch.zeros(1, 8, 512)
     log = []
 
-    def step(styles, lr=None, global_count=None):
+    def step(styles, lr=None, global_count=None, source_key=None):
+        assert source_key is not None and source_key[2] - source_key[1] == styles.shape[0]     # (batch index, first row, last row) of this shard
         ids = styles[:, 0, 0].tolist()
         rows = torch.zeros(11)
         rows[[int(i) for i in ids]] = 1

@@ -275,7 +275,7 @@ def test_npz_formats_and_find_direction_loop(tmp_path):
     f.delta = torch.zeros(1, 8, 512)
     calls = []
 
-    def step(styles, lr=None, global_count=None):
+    def step(styles, lr=None, global_count=None, source_key=None):
         calls.append((styles.shape[0], lr, global_count, styles[0, 0, 0].item()))
         f.delta += 1.0
         return dict(loss=torch.tensor(0.0))
@@ -307,7 +307,7 @@ def test_npz_formats_and_find_direction_loop(tmp_path):
         io.find_direction(f, S, batch_size=11, n_epochs=1, zero_init='raise')
     assert not calls
     seen = []
-    f.step = lambda styles, lr=None, global_count=None: seen.append(f.delta.clone()) or dict(loss=torch.tensor(0.0))
+    f.step = lambda styles, lr=None, global_count=None, source_key=None: seen.append(f.delta.clone()) or dict(loss=torch.tensor(0.0))
     with pytest.warns(UserWarning, match='delta == 0'):
         io.find_direction(f, S, batch_size=11, n_epochs=1)
     assert len(seen) == 1 and seen[0].abs().min().item() > 0 and 0.005 < seen[0].std().item() < 0.02
