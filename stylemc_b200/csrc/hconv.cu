@@ -785,6 +785,21 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
             hc_epilogue_modconv<CW, false>(acc, e, nz, acc_scale, HcVec<false>{rs}, HcVec<false>{bs}, HcVec<false>{ps}, HcVec<false>{rw}, 0u, p.n_out, opix,
                                            rgb0, rgb1, rgb2);
           }
+        } else if (BN <= 64 && e.out_f32 && f32_aligned32 && !e.out_hi && !e.out_raw && !e.rgb_acc && !ps && !bs && !e.residual && e.noise == nullptr &&
+                   e.act == 0 && e.gain == 1.f && e.clamp < 0.f && (((uintptr_t)e.row_scale) & 15) == 0) {
+          // (not in the 128-wide kernels: their epilogue threads already spill at 96 registers, and the extra path cost them 4-7 %)
+          // conv0's parity planes and the fp32 dgrad outputs: v = acc * acc_scale (* row_scale), one 32-byte store per 8 channels.
+          // The generic loop below spends ~10 instructions per element on this (scalar parameter loads, dead predicated branches); with
+          // tiles of 16-64 MMAs per problem the 16 epilogue warps, not the tensor pipe, set the pace of these launches.
+#pragma unroll
+          for (int c0 = 0; c0 < CW; c0 += 8) {
+            float r8[8], v[8];
+            if (rs) hc_ld8(rs + c0, r8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = rs ? (acc[c0 + i] * acc_scale) * r8[i] : acc[c0 + i] * acc_scale;     // the generic path's operation order
+            hc_st32(e.out_f32 + opix + c0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                    make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+          }
         } else {
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 8) {
