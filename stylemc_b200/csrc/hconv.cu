@@ -31,6 +31,9 @@ constexpr int HC_MAX_TAPS = 16;
 constexpr int HC_THREADS = 32 * (3 + 16);
 constexpr int HC_EPI_THREADS = 32 * 16;
 constexpr int HC_BAR_BYTES = 1024;                 // mbarriers + TMEM slot
+#ifndef HC_STAGE_MIN
+#define HC_STAGE_MIN 32            // smallest N tile whose epilogue parameter vectors are staged in shared memory (hconv_kernel::STAGE)
+#endif
 constexpr int HC_PSTAGE_VECS = 6;                  // staged epilogue vectors per tile (hconv_kernel::pstage)
 static constexpr int hc_pstage_bytes(int bn) { return 2 * HC_PSTAGE_VECS * bn * 4; }
 
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
   constexpr int SETCOLS = (TWO_PASS ? 2 : 1) * HC_MB * BLK;
   constexpr int SETS = (2 * SETCOLS <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (SETS * SETCOLS) < 32 ? 32 : (SETS * SETCOLS);
-  constexpr bool STAGE = BN >= 64;                             // epilogue parameter vectors staged in shared memory (HcVec)
+  constexpr bool STAGE = BN >= HC_STAGE_MIN;                             // epilogue parameter vectors staged in shared memory (HcVec)
   constexpr uint32_t MMA_M = PAIR ? 256 : 128;                 // cta_group::2: 128 rows from each CTA of the pair
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
   constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
@@ -1050,22 +1053,39 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   const int mode = !x3 ? HC_X1 : ((BN <= 64 && !(g_hconv_mask & 256)) ? HC_X3_MERGED : HC_X3_TWO_PASS);
   const int passes = mode == HC_X3_TWO_PASS ? 2 : 1;
   const int stages_per_tile = (d->C / KC) * T * passes;      // all problems together
-  p.b_resident = (d->n_out == BN && stages_per_tile <= 32 && stages_per_tile * (BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1)) <= 96 * 1024) ? 1 : 0;
+  const bool can_reside = d->n_out == BN && stages_per_tile <= 32 && stages_per_tile * (BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1)) <= 96 * 1024;
+  int b_bytes = 0, saved_b_bytes = 0;
+  size_t smem_fixed = 0, saved_fixed = 0;
+  HcParams saved_plan;
+  // attempt 0: resident weights where they fit; attempt 1 (only when the preferred tile width did not fit beside them): a weight ring
+  for (int attempt = 0; attempt < 2; ++attempt) {
+  p.b_resident = (can_reside && attempt == 0) ? 1 : 0;
   // CTA pair (cta_group::2): the 128-wide N tiles are bound by the shared-memory operand fetch of the MMAs (8 KB per 128 x 128 x 16
   // instruction); a pair reads the weight tile once for 2 x 128 rows.  The two CTAs take the same tile of two consecutive images.
   p.pair = (g_hconv_pair && BN == 128 && mode != HC_X3_MERGED && d->n_img % 2 == 0 && !p.b_resident) ? 1 : 0;
-  const int b_bytes = BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1) / (p.pair ? 2 : 1);        // one ring stage (per CTA)
+  b_bytes = BN * KC * 2 * (mode == HC_X3_MERGED ? 2 : 1) / (p.pair ? 2 : 1);        // one ring stage (per CTA)
   if (p.b_resident) {
     p.nb = stages_per_tile;
   } else {
     p.nb = g_hconv_nb > 0 ? g_hconv_nb : (b_bytes >= 16384 ? 4 : (b_bytes >= 8192 ? 6 : 8));
     p.nb = p.nb < 2 ? 2 : (p.nb > 32 ? 32 : p.nb);
   }
-  const size_t smem_fixed = 1024 + (size_t)p.nb * b_bytes + HC_BAR_BYTES + (size_t)hc_pstage_bytes(BN);
-  const int wt_cands[4] = {g_hconv_wt > 0 ? g_hconv_wt : 64, 32, 16, 8};
+  smem_fixed = 1024 + (size_t)p.nb * b_bytes + HC_BAR_BYTES + (size_t)hc_pstage_bytes(BN);
+  // Widths just above a multiple of 64 (the parity planes of the stride-2 transposed conv are 2^k + 1 wide) get column tiles of
+  // ceil(W / floor(W / 64)) <= 80 pixels: with 64-wide tiles a 65-pixel row became a 64-wide and a 1-wide column tile, and the second one
+  // cost as many position tiles as the first (conv0 at 128 / 256 / 512 / 1024 px ran 2.0 / 1.5 / 1.25 / 1.12 times the useful MMAs).
+  int wt_first = 64;
+  if (g_hconv_wt > 0) {
+    wt_first = g_hconv_wt;
+  } else if (d->W > 64 && d->W % 64 != 0) {
+    const int bal = ceil_div(d->W, d->W / 64);
+    if (bal <= 80) wt_first = bal;
+  }
+  const int wt_cands[5] = {wt_first, 64, 32, 16, 8};
   const bool short_tiles = d->C / KC <= 2;            // few MMAs per tile: prefetch A tiles further ahead
   p.Wt = 0;
-  for (int ci = 0; ci < 4 && p.Wt == 0; ++ci) {
+  int chosen = -1;
+  for (int ci = 0; ci < 5 && p.Wt == 0; ++ci) {
     const int wt = d->W < wt_cands[ci] ? d->W : wt_cands[ci];
     const int wp = wt + padW;
     const int rb = (HC_MT % wp == 0) ? HC_MT / wp + padH : ceil_div(HC_MT, wp) + 1 + padH;
@@ -1089,6 +1109,14 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
       nl = 0;
     }
     p.Wt = wt; p.Wp = wp; p.RB = rb; p.na_hi = nh; p.na_lo = nl;
+    chosen = ci;
+  }
+  if (attempt == 1) {
+    if (chosen != 0) { p = saved_plan; b_bytes = saved_b_bytes; smem_fixed = saved_fixed; }    // the ring did not help: keep the resident plan
+    break;
+  }
+  if (chosen == 0 || !p.b_resident || wt_first == 64) break;      // else: retry with a weight ring, which leaves room for the preferred width
+  saved_plan = p; saved_b_bytes = b_bytes; saved_fixed = smem_fixed;
   }
   if (p.Wt == 0) return SMC_EUNSUPPORTED;
   p.col_tiles = ceil_div(d->W, p.Wt);

@@ -65,7 +65,7 @@ def check(o, base_taps, x3, halo):
         assert 2 <= o.grid <= 148 and o.grid % 2 == 0 and o.grid // 2 <= o.super_tiles
     else:
         assert 1 <= o.grid <= 148 and o.grid <= o.super_tiles
-    assert o.Wp - o.Wt == halo and o.Wt <= 64
+    assert o.Wp - o.Wt == halo and o.Wt <= 80          # 64, or ceil(W / floor(W / 64)) for the 2^k + 1 wide parity planes (no 1-pixel column tile)
     assert o.na_hi >= 2 and (o.na_lo >= 1 if x3 else o.na_lo == 0)
     assert sum(o.prob_ntaps[q] for q in range(o.nprob)) == base_taps
     for q in range(o.nprob):
@@ -109,6 +109,8 @@ def test_every_synthesis_gemm_of_the_1024_network_has_a_plan(n, x3):
             assert rc == 0, (res, rc)
             check(o, 9, x3, halo=1)
             assert o.nprob == 4 and [o.prob_ntaps[q] for q in range(4)] == [4, 2, 2, 1]
+            if hin + 1 > 64:            # 65 / 129 / 257 / 513 columns: 1 / 2 / 4 / 8 column tiles of 65, not 64-wide tiles plus a 1-pixel one
+                assert -(-(hin + 1) // o.Wt) == (hin + 1) // 64, (hin + 1, o.Wt)
             assert bool(o.a_share) == (cin == 64 and (c <= 64 or not x3))
         # ... and its dgrad from the four gradient parity planes (four A sources)
         rc, o = plan(make_desc(n, hin, hin, c, cin, gemm.up2_dgrad_taps(n), x3, 512 if x3 else 0, a_imgs=4 * n, HA=hin + 1, WA=hin + 1, rows_b=9 * cin))
