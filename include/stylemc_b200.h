@@ -164,7 +164,8 @@ int smc_igemm_plan(const smc_igemm_desc* desc, smc_igemm_plan_info* out);
  *   key 2: weight-stage ring depth (0 = by stage size)   key 3: tile width Wt in pixels (0 = widest that fits, <= 64)
  *   key 4: persistent grid size (0 = one CTA per SM)      key 5: bit mask of conv kinds routed to hconv.cu (diagnostics)
  *   key 6: smallest H * W the auto mode routes to hconv.cu (default 64)
- *   key 7: CTA-pair launches (tcgen05 cta_group::2) for 128-wide N tiles over an even number of images: 1 on (default), 0 off */
+ *   key 7: CTA-pair launches (tcgen05 cta_group::2) for 128-wide N tiles over an even number of images: 1 on (default), 0 off
+ *   key 8: the plain-epilogue instantiation for fp32-output GEMMs on 128-wide tiles (CLIP linears, conv0 planes): 1 on (default), 0 off */
 int smc_igemm_config(int key, int value);
 
 /* ---- synthesis glue (synth.cu) -------------------------------------------------------------------

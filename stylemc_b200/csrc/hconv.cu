@@ -400,7 +400,10 @@ __device__ __forceinline__ void hc_epilogue_actbwd(const float (&acc)[CW], const
 enum { HC_X1 = 0, HC_X3_TWO_PASS = 1, HC_X3_MERGED = 2 };
 // ALO: the A operand has a lo plane (three-term split); false = two-term split (hi plane only).  A template parameter, not a field of
 // HcParams: the flag sits inside the MMA issue loop, and a run-time branch there cost the 32-channel layers 10-15 %.
-template <int BN, int KC, int MODE, bool PAIR = false, bool ALO = true>
+// EPI: 0 = every fused epilogue; 1 = the plain one only (fp32 output = acc * acc_scale [* row_scale] [+ bias] [+ residual]: CLIP linears, conv0's
+// parity planes, fp32 dgrad outputs).  A separate instantiation because the 128-wide epilogue threads (64 accumulators each) sit at the register
+// limit: every path compiled into the kernel costs all of them spills (adding the lean path to EPI 0 made the convolutions 4-7 % slower).
+template <int BN, int KC, int MODE, bool PAIR = false, bool ALO = true, int EPI = 0>
 __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB,
                                                               const __grid_constant__ HcParams p) {
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
           }
         }
       };
-      if (STAGE) {
+      if (STAGE && EPI == 0) {
         locate();
         // the vectors depend on (image, N tile) only: consecutive tiles of a CTA mostly share them (always at 512 / 1024 px), so they are
         // re-staged -- into the other buffer, followed by one barrier of the 16 epilogue warps -- only when that pair changes; every
@@ -761,6 +764,41 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         if (lane == 0) { if (PAIR) mbar_arrive_leader(drained); else mbar_arrive(drained); }
       }
       // ---- fused epilogue + stores for this thread's position
+      if constexpr (EPI == 1) {
+        const int qpos = tl.q0 + m;
+        const int hh = hc_div(qpos, p.div_wp);
+        const int wr = qpos - hh * p.Wp, ww = tl.w0 + wr;
+        if ((wr < p.Wt) && (ww < p.W) && (hh < p.H)) {
+          const int oc = tl.nt * BN + ch * CW;
+          const long long op = e.o_off + p.probs[tl.prob].o_off + (long long)tl.n * e.o_sn + (long long)hh * e.o_sh + (long long)ww * e.o_sw + oc;
+          const float* rs = e.row_scale ? e.row_scale + (long long)tl.n * p.n_out + oc : nullptr;
+          const float* bs = e.bias ? e.bias + oc : nullptr;
+#pragma unroll
+          for (int c0 = 0; c0 < CW; c0 += 8) {
+            float v[8], t8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = acc[c0 + i] * acc_scale;                   // the operation order of the generic path
+            if (rs) {
+              hc_ld8(rs + c0, t8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= t8[i];
+            }
+            if (bs) {
+              hc_ld8(bs + c0, t8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += t8[i];
+            }
+            if (e.residual) {
+              hc_ld8(e.residual + op + c0, t8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += t8[i];
+            }
+            hc_st32(e.out_f32 + op + c0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                    make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+          }
+        }
+        continue;
+      }
       if (!STAGE) locate();
       if (valid) {
         const int n = tl.n;
@@ -903,6 +941,7 @@ static int g_hconv_grid = 0;
 static int g_hconv_minpos = 64;     // auto mode: smallest H * W routed to this kernel
 static int g_hconv_mask = 7;   // bit 0: single-source convs with > 4 taps, bit 1: <= 4 taps, bit 2: multi-source (up2 dgrad)
 static int g_hconv_pair = 1;   // CTA-pair (cta_group::2) launches for 128-wide N tiles over an even number of images
+static int g_hconv_plain = 1;  // plain-epilogue instantiation (EPI = 1) for fp32-output GEMMs on 128-wide tiles
 
 static smc_igemm_plan_info* g_plan_out = nullptr;   // set only inside smc_igemm_plan (diagnostics, not thread-safe)
 
@@ -914,31 +953,32 @@ void hconv_config(int key, int value) {
   if (key == 5) g_hconv_mask = value;
   if (key == 6) g_hconv_minpos = value;
   if (key == 7) g_hconv_pair = value;
+  if (key == 8) g_hconv_plain = value;
 }
 
-template <int BN, int KC, int MODE, bool ALO>
+template <int BN, int KC, int MODE, bool ALO, int EPI = 0>
 static int hc_launch_a(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
   static SmemOptIn opt_in;
-  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE, false, ALO>, smem); e != cudaSuccess) return (int)e;
-  hconv_kernel<BN, KC, MODE, false, ALO><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
+  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE, false, ALO, EPI>, smem); e != cudaSuccess) return (int)e;
+  hconv_kernel<BN, KC, MODE, false, ALO, EPI><<<grid, HC_THREADS, smem, st>>>(ma, mb, p);
   SMC_LAUNCH_CHECK();
   return SMC_OK;
 }
-template <int BN, int KC, int MODE>
+template <int BN, int KC, int MODE, int EPI = 0>
 static int hc_launch(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
   if constexpr (MODE != HC_X1) {
-    if (!p.a_lo_term) return hc_launch_a<BN, KC, MODE, false>(ma, mb, p, grid, smem, st);
+    if (!p.a_lo_term) return hc_launch_a<BN, KC, MODE, false, EPI>(ma, mb, p, grid, smem, st);
   }
-  return hc_launch_a<BN, KC, MODE, true>(ma, mb, p, grid, smem, st);
+  return hc_launch_a<BN, KC, MODE, true, EPI>(ma, mb, p, grid, smem, st);
 }
 // CTA-pair launch: clusters of two CTAs (the two SMs of a TPC), grid = 2 x clusters
-template <int BN, int KC, int MODE, bool ALO = true>
+template <int BN, int KC, int MODE, bool ALO = true, int EPI = 0>
 static int hc_launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const HcParams& p, int grid, size_t smem, cudaStream_t st) {
   if constexpr (MODE != HC_X1 && ALO) {
-    if (!p.a_lo_term) return hc_launch_pair<BN, KC, MODE, false>(ma, mb, p, grid, smem, st);
+    if (!p.a_lo_term) return hc_launch_pair<BN, KC, MODE, false, EPI>(ma, mb, p, grid, smem, st);
   }
   static SmemOptIn opt_in;
-  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE, true, ALO>, smem); e != cudaSuccess) return (int)e;
+  if (cudaError_t e = smem_opt_in(opt_in, hconv_kernel<BN, KC, MODE, true, ALO, EPI>, smem); e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
   cfg.blockDim = dim3(HC_THREADS, 1, 1);
@@ -949,7 +989,7 @@ static int hc_launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const Hc
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, hconv_kernel<BN, KC, MODE, true, ALO>, ma, mb, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, hconv_kernel<BN, KC, MODE, true, ALO, EPI>, ma, mb, p);
   if (e != cudaSuccess) return (int)e;
   SMC_LAUNCH_CHECK();
   return SMC_OK;
@@ -1323,6 +1363,21 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
     if (r != CUDA_SUCCESS) return SMC_EDRIVER;
   }
   const int max_grid = g_hconv_grid > 0 ? g_hconv_grid : sm_count();
+  // plain epilogue (hconv_kernel EPI = 1): fp32 output = acc * acc_scale [* row_scale] [+ bias] [+ residual] and nothing else
+  const smc_igemm_epilogue& pe = p.epi;
+  const bool plain = g_hconv_plain && BN == 128 && KC == 64 && pe.out_f32 && !pe.out_hi && !pe.out_lo && !pe.out_raw && !pe.out_raw_lo && !pe.rgb_acc && !pe.rgb_w &&
+                     !pe.post_scale && !pe.noise && !pe.mask_y && pe.act == 0 && pe.gain == 1.f && pe.clamp < 0.f &&
+                     ((((uintptr_t)pe.out_f32 | (uintptr_t)pe.residual) & 31) == 0) && ((((uintptr_t)pe.row_scale | (uintptr_t)pe.bias) & 15) == 0);
+  if (plain) {
+    if (p.pair) {
+      const int max_clusters = max_grid / 2;
+      const int grid2 = 2 * (p.super_tiles < max_clusters ? (int)p.super_tiles : max_clusters);
+      return mode == HC_X1 ? hc_launch_pair<128, 64, HC_X1, true, 1>(ma, mb, p, grid2, smem, st)
+                           : hc_launch_pair<128, 64, HC_X3_TWO_PASS, true, 1>(ma, mb, p, grid2, smem, st);
+    }
+    const int grid1 = p.super_tiles < max_grid ? (int)p.super_tiles : max_grid;
+    return mode == HC_X1 ? hc_launch<128, 64, HC_X1, 1>(ma, mb, p, grid1, smem, st) : hc_launch<128, 64, HC_X3_TWO_PASS, 1>(ma, mb, p, grid1, smem, st);
+  }
   if (p.pair) {
     const int max_clusters = max_grid / 2;
     const int grid2 = 2 * (p.super_tiles < max_clusters ? (int)p.super_tiles : max_clusters);

@@ -34,7 +34,8 @@ def wmat(w_oihw, two, transpose=False):
 
 
 CASES = [(2, 64, 64, 32, 32), (1, 128, 128, 48, 40), (2, 64, 128, 64, 64), (1, 192, 64, 33, 70), (1, 32, 32, 64, 64),
-         (2, 64, 32, 40, 40), (1, 32, 64, 37, 129), (1, 256, 256, 32, 32), (3, 96, 96, 32, 32)]
+         (2, 64, 32, 40, 40), (1, 32, 64, 37, 129), (1, 256, 256, 32, 32), (3, 96, 96, 32, 32),
+         (1, 64, 32, 9, 65), (1, 32, 32, 8, 513), (1, 64, 64, 8, 150)]     # widths 2^k + 1: column tiles of 65 (no 1-pixel tile); 150: 64-wide tiles
 
 
 @pytest.mark.parametrize('n,c,o,h,w', CASES)
