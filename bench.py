@@ -81,7 +81,7 @@ def synth_flops_per_image(blocks, until_k):
 
 # DRAM bytes per launch of the dominant shape, from the committed ncu capture (key = n_img, H, W, Cin, Cout, taps); None when not captured
 TOP_KERNEL_DRAM_BYTES = {(64, 1024, 1024, 32, 32, 9): 12.99e9}   # mean of the 3 launches per step: 10.49 (no-grad fwd), 15.42 (grad fwd), 13.07 GB (dgrad, hi-only gradient planes)
-TRAFFIC_SOURCE = 'ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r02f_hconv_launches.md (rows 14, 78, 177) and r02f_top_kernel.md'
+TRAFFIC_SOURCE = 'ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r02g_hconv_launches.md (rows 14, 78, 177) and r02f_top_kernel.md'
 
 VIT_FLOPS_FWD = 2 * (49 * 3072 * 768 + 12 * 50 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) + 12 * 12 * 2 * 50 * 50 * 64)   # per image
 VIT_B16_FLOPS_FWD = 2 * (196 * 768 * 768 + 12 * 197 * (768 * 2304 + 768 * 768 + 2 * 768 * 3072) + 12 * 12 * 2 * 197 * 197 * 64)   # 35.2 GFLOP
