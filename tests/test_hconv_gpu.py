@@ -223,3 +223,55 @@ def test_cta_pair_launch_equals_single_cta_kernel_bitwise(n, c, o, h, w, x3):
     assert torch.equal(outs[0], outs[1])
     ref = F.conv2d(x.double(), wt.double(), padding=1).permute(0, 2, 3, 1)
     assert rel(outs[1], ref) <= (2e-6 if x3 else 1e-5)
+
+
+def test_epilogue_family_instantiations_equal_the_all_in_one_kernel_bitwise():
+    """The 128-wide kernels are instantiated once per epilogue family (hconv_kernel EPI 1 plain fp32 output, 2 modulated conv, 3 fused activation
+    backward: csrc/hconv.cu; no register spills) and the family is chosen on the host.  ``smc_igemm_config(8, 0)`` routes everything through
+    the all-in-one kernel (EPI 0) again: same arithmetic, so every output must be bit-identical."""
+    from stylemc_b200 import _lib, gemm
+    g = torch.Generator(device='cuda').manual_seed(9)
+    n, c, o, h, w = 4, 128, 256, 24, 40
+    x = torch.randn(n, c, h, w, device='cuda', generator=g)
+    wt = torch.randn(o, c, 3, 3, device='cuda', generator=g) * 0.1
+    d = torch.rand(n, o, device='cuda', generator=g) + 0.5
+    s = torch.randn(n, o, device='cuda', generator=g)
+    bias = torch.randn(o, device='cuda', generator=g)
+    noise = torch.randn(h, w, device='cuda', generator=g)
+    rgb_w = torch.randn(n, 3, o, device='cuda', generator=g) * 0.1
+    res = torch.randn(n, h, w, o, device='cuda', generator=g)
+    ymask = (torch.randn(n, h, w, o, device='cuda', generator=g) * 2).half()
+    grgb = torch.randn(n, 3, h, w, device='cuda', generator=g)
+    A, B = planes(x, True), wmat(wt, True)
+    kw = dict(precision='x3', acc_chunk_k=512, a_plane_stride_imgs=n, b_rows_per_tap=9 * o)
+
+    def run():
+        outs = []
+        # family 2: the modulated-conv epilogue with every output and the fused ToRGB (two N tiles: two partial-sum images)
+        y, xs = (torch.empty(2, n, h, w, o, device='cuda', dtype=torch.float16) for _ in range(2))
+        acc = torch.zeros(2, n, 3, h, w, device='cuda')
+        gemm.igemm(A, B, n, h, w, o, gemm.TAPS_3X3, row_scale=d, bias=bias, noise=noise, noise_strides=(w, 1), act=1, alpha=0.2, gain=2 ** 0.5,
+                   clamp=3.0, out_raw=y[0], out_raw_lo=y[1], post_scale=s, out_hi=xs[0], out_lo=xs[1], rgb_w=rgb_w, rgb_acc=acc[0],
+                   rgb_part_stride=acc.stride(0), **kw)
+        outs += [y, xs, acc]
+        # family 3: the fused activation backward with the ToRGB branch
+        gd = torch.empty(2, n, h, w, o, device='cuda', dtype=torch.float16)
+        gemm.igemm(A, B, n, h, w, o, gemm.TAPS_3X3, post_scale=s, alpha=0.2, gain=2 ** 0.5, clamp=3.0, mask_y=ymask, mask_grgb=grgb, rgb_w=rgb_w,
+                   out_hi=gd[0], out_lo=gd[1], **kw)
+        outs.append(gd)
+        # family 1: plain fp32 outputs (conv0 planes: row_scale; CLIP linears: bias + residual)
+        p1, p2 = torch.empty(n, h, w, o, device='cuda'), torch.empty(n, h, w, o, device='cuda')
+        gemm.igemm(A, B, n, h, w, o, gemm.TAPS_3X3, row_scale=d, out_f32=p1, **kw)
+        gemm.igemm(A, B, n, h, w, o, gemm.TAPS_3X3, bias=bias, residual=res, out_f32=p2, acc_scale=0.5, **kw)
+        outs += [p1, p2]
+        return outs
+
+    try:
+        _lib.call('smc_igemm_config', 8, 0)
+        ref = run()
+    finally:
+        _lib.call('smc_igemm_config', 8, 1)
+    new = run()
+    for a, b in zip(new, ref):
+        assert torch.equal(a, b)
+    assert ref[0].float().abs().max().item() > 0 and ref[3].float().abs().max().item() > 0
