@@ -243,6 +243,10 @@ class DirectionFinder:
             e_s = [model.encode_image_fwd(u_s, save=False)[0] for model, _, _ in self.clips]
             return e_s + [original] if self._use_id() else e_s
 
+    def clear_source_cache(self):
+        """Forget the cached original-image embeddings (``source_key``): call it when the styles behind a key change (a new styles_array)."""
+        self._src_cache.clear()
+
     def _use_id(self):
         return getattr(self, 'id_loss', None) is not None and self.identity_loss_coef != 0.0
 
