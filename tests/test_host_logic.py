@@ -249,6 +249,71 @@ def test_direction_finder_combines_towers_and_loss_scales(towers, overlap, monke
     assert ((grad.double() - g_want[0]).norm() / g_want.norm()).item() <= 1e-5
 
 
+@pytest.mark.parametrize('overlap', [False, True])
+def test_direction_finder_source_key_skips_the_original_branch(overlap, monkeypatch):
+    """Host logic of ``loss_and_grad(source_key=...)`` with stand-in engines on the CPU: the original-image branch (find_direction.py:311-312) runs
+    once per (key, micro-batch), later calls reuse its embeddings and return the same loss and gradient; without a key nothing is cached."""
+    import contextlib
+    from stylemc_b200 import direction
+
+    class FakeStream:
+        def wait_stream(self, other):
+            pass
+    if overlap:
+        monkeypatch.setattr(torch.cuda, 'current_stream', lambda device=None: FakeStream())
+        monkeypatch.setattr(torch.cuda, 'Stream', lambda device=None: FakeStream())
+        monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())
+        monkeypatch.setattr(torch.Tensor, 'record_stream', lambda self, s: None)
+    gen = torch.Generator().manual_seed(3)
+    A = torch.randn(26 * 512, 3 * 4 * 4, generator=gen, dtype=torch.float64) * 0.02
+    W = torch.randn(3 * 4 * 4, 16, generator=gen, dtype=torch.float64)
+    text = torch.nn.functional.normalize(torch.randn(1, 16, generator=gen, dtype=torch.float64), dim=1)
+    calls = dict(nograd=0, grad=0)
+
+    class Engine:
+        def forward(self, s, until_k, noise_mode, save, grad_rows=None):
+            calls['grad' if save else 'nograd'] += 1
+            return None, (s.double().reshape(len(s), -1) @ A).reshape(len(s), 3, 4, 4), s
+
+        def backward(self, saved, g_img, rows_, noise_mode):
+            return (g_img.reshape(len(g_img), -1) @ A.t()).reshape(len(g_img), 26, 512)[:, rows_].sum(0)
+
+    class Tower:
+        def encode_image_fwd(self, u, save):
+            return u.flatten(1) @ W, (u.shape if save else None)
+
+        def encode_image_bwd(self, saved, d):
+            return (d @ W.t()).reshape(saved)
+
+    class Loss:
+        def loss_and_grad(self, e_s, e_t, c, inv_count):
+            e_t = e_t.detach().requires_grad_(True)
+            part = -c * inv_count * torch.nn.functional.cosine_similarity(e_t - e_s, text).sum()
+            d, = torch.autograd.grad(part, e_t)
+            return part.detach().reshape(1), d, torch.ones(1, dtype=torch.float64)
+
+    monkeypatch.setattr(direction.resample, 'unprocess_fwd', lambda img, mode='unprocess': img)
+    monkeypatch.setattr(direction.resample, 'unprocess_bwd', lambda g, img, unscale=None, mode='unprocess': g / unscale)
+    f = object.__new__(direction.DirectionFinder)
+    f.device, f.engine, f.until_k, f.noise_mode, f.micro_batch, f.rows = torch.device('cpu'), Engine(), 3, 'const', 2, direction.S_TRAINABLE_SPACE_CHANNELS
+    f.clip_loss_coef, f.overlap, f._side, f._src_cache = 1.0, overlap, None, {}
+    f.clips = [(Tower(), Loss(), 1.0)]
+    f.delta = 0.1 * torch.randn(1, 8, 512, generator=gen)
+    styles = torch.randn(5, 26, 512, generator=gen)                      # three micro-batches (2 + 2 + 1)
+    g0, p0 = f.loss_and_grad(styles, global_count=5)
+    assert calls == dict(nograd=3, grad=3) and not f._src_cache
+    g1, p1 = f.loss_and_grad(styles, global_count=5, source_key='batch 7')
+    assert calls == dict(nograd=6, grad=6) and len(f._src_cache) == 3
+    g2, p2 = f.loss_and_grad(styles, global_count=5, source_key='batch 7')
+    assert calls == dict(nograd=6, grad=9)                               # the original-image branch did not run again
+    for g, p_ in ((g1, p1), (g2, p2)):
+        assert torch.equal(g, g0) and torch.equal(p_, p0)
+    f.loss_and_grad(styles[:3], global_count=3, source_key='batch 8')      # another key: computed (2 micro-batches) and kept
+    assert calls['nograd'] == 8 and len(f._src_cache) == 5
+    f.clear_source_cache()
+    assert not f._src_cache
+
+
 def test_npz_formats_and_find_direction_loop(tmp_path):
     """the w / s / direction npz layouts (generate_w.py:51, w_s_converter.py:82, find_direction.py:260,334,351,
     generate_fromS.py:114,125) and the optimisation loop's bookkeeping (iteration count, cosine LR, batch slices, checkpoints,
