@@ -134,11 +134,11 @@ def lib():
             raise RuntimeError('libstylemc_b200.so ABI version mismatch; rebuild')
         _lib = handle
         for key, env in ((0, 'STYLEMC_HCONV'), (2, 'STYLEMC_HCONV_NB'), (3, 'STYLEMC_HCONV_WT'), (4, 'STYLEMC_HCONV_GRID'), (5, 'STYLEMC_HCONV_MASK'), (6, 'STYLEMC_HCONV_MINPOS'),
-                         (7, 'STYLEMC_HCONV_PAIR')):
+                         (7, 'STYLEMC_HCONV_PAIR'), (8, 'STYLEMC_HCONV_EPI')):
             if os.environ.get(env):          # diagnostics only: A/B the halo-tile conv kernel against the per-tap kernel
                 handle.smc_igemm_config(key, int(os.environ[env]))
         for key, env in ((0, 'STYLEMC_FIR_ACT3'), (1, 'STYLEMC_FIR_BWD3'), (2, 'STYLEMC_ACT_BWD2'), (3, 'STYLEMC_UPFIRDN_ROWS'), (4, 'STYLEMC_RESAMPLE_VFIRST'),
-                         (5, 'STYLEMC_ATTENTION_TILED')):
+                         (5, 'STYLEMC_ATTENTION_TILED'), (6, 'STYLEMC_RESAMPLE_ROWS')):
             if os.environ.get(env):          # diagnostics only: A/B the newer glue kernels against the older ones
                 handle.smc_synth_config(key, int(os.environ[env]))
     return _lib
