@@ -227,7 +227,7 @@ def test_cta_pair_launch_equals_single_cta_kernel_bitwise(n, c, o, h, w, x3):
 
 def test_epilogue_family_instantiations_equal_the_all_in_one_kernel_bitwise():
     """The 128-wide kernels are instantiated once per epilogue family (hconv_kernel EPI 1 plain fp32 output, 2 modulated conv, 3 fused activation
-    backward: csrc/hconv.cu; no register spills) and the family is chosen on the host.  ``smc_igemm_config(8, 0)`` routes everything through
+    backward: csrc/hconv.cu; about half the register spills of the all-in-one kernel) and the family is chosen on the host.  ``smc_igemm_config(8, 0)`` routes everything through
     the all-in-one kernel (EPI 0) again: same arithmetic, so every output must be bit-identical."""
     from stylemc_b200 import _lib, gemm
     g = torch.Generator(device='cuda').manual_seed(9)
